@@ -1,0 +1,217 @@
+"""CPU oracle for the detection hot path -- TEST INFRASTRUCTURE ONLY.
+
+A ctypes front-end to ``oracle/yolo_oracle.c`` (a plain-C restatement of
+``models/yolo_loss.py``, ``utils/box.py``, ``utils/iou.py`` and the arithmetic of
+``torchvision.ops.nms``; every C function cites the reference file:line it
+follows).  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this package; the product
+(``mobilenet_yolo_pytorch_b200``) never does.
+
+Parity status: **pinned** -- ``tests/test_oracle_golden.py`` checks it against
+fixtures in ``tests/golden/`` generated from the reference's own Python by
+``tests/golden/make_golden.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+_SRC = os.path.join(_HERE, "yolo_oracle.c")
+_lock = threading.Lock()
+_lib = None
+
+NMS_IOU_THRESHOLD = 0.45  # utils/box.py:28
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle (gcc, a second or two).  Returns the .so path."""
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(_SRC):
+        return _SO
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+    base = [cc, "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-fvisibility=hidden", "-shared", "-o", _SO, _SRC]
+    try:
+        subprocess.check_call(base[:4] + ["-fopenmp"] + base[4:] + ["-lm"], stderr=subprocess.DEVNULL)
+    except (subprocess.CalledProcessError, OSError):
+        subprocess.check_call(base + ["-lm"])  # scalar build if libgomp is missing
+    return _SO
+
+
+def lib() -> C.CDLL:
+    global _lib
+    with _lock:
+        if _lib is None:
+            _lib = C.CDLL(build())
+            _lib.oracle_get_max_threads.restype = C.c_int
+            _lib.oracle_target_loss.restype = C.c_int
+    return _lib
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(C.c_int(int(n)))
+
+
+def max_threads() -> int:
+    return int(lib().oracle_get_max_threads())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _p(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def scaled_anchors(anchors, img_size) -> np.ndarray:
+    """yolo_loss.py:214 -- python-double division, then rounded to fp32 (:67-68)."""
+    return np.array([[aw / img_size[0], ah / img_size[1]] for aw, ah in anchors], dtype=np.float64).astype(np.float32)
+
+
+def decode_head(head, anchor_wh, num_classes: int, conf_thr: float):
+    """YOLOLoss.get_pred_boxes (yolo_loss.py:180-204).  ``anchor_wh`` is this
+    head's (A,2) scaled anchors.  Returns (list of (n_b,7) arrays, list of id arrays)."""
+    x = _f32(head)
+    N, ch, H, W = x.shape
+    A = ch // (5 + num_classes)
+    cells = A * H * W
+    rows = np.zeros((N, cells, 7), np.float32)
+    count = np.zeros(N, np.int32)
+    ids = np.zeros((N, cells), np.int32)
+    aw = _f32(anchor_wh)
+    lib().oracle_decode_head(_p(x), N, A, num_classes, H, W, _p(aw), C.c_float(np.float32(conf_thr)), _p(rows),
+                             _p(count), _p(ids))
+    return [rows[b, :count[b]].copy() for b in range(N)], [ids[b, :count[b]].copy() for b in range(N)]
+
+
+def nms(cands, num_classes: int, iou_thr: float = NMS_IOU_THRESHOLD):
+    """utils.box.nms (box.py:11-31) on per-image concatenated candidates
+    (list of (n_b,7)).  Returns (list of (k_b,7), list of kept index arrays)."""
+    N = len(cands)
+    K = max([len(c) for c in cands] + [1])
+    rows = np.zeros((N, K, 7), np.float32)
+    count = np.zeros(N, np.int32)
+    for b, c in enumerate(cands):
+        rows[b, :len(c)] = c
+        count[b] = len(c)
+    out = np.zeros_like(rows)
+    oc = np.zeros(N, np.int32)
+    oi = np.zeros((N, K), np.int32)
+    lib().oracle_nms(_p(rows), _p(count), N, K, num_classes, C.c_double(iou_thr), _p(out), _p(oc), _p(oi))
+    return [out[b, :oc[b]].copy() for b in range(N)], [oi[b, :oc[b]].copy() for b in range(N)]
+
+
+def decode_nms_padded(head0, head1, anchor_wh2, num_classes: int, conf_thr: float,
+                      iou_thr: float = NMS_IOU_THRESHOLD, want_cand: bool = False):
+    """Fixed-stride form used for timing and full-size checks: returns
+    (out (N,K,7), out_count (N,), out_idx (N,K)[, cand, cand_count, cand_ids])."""
+    h0, h1 = _f32(head0), _f32(head1)
+    N, ch, H0, W0 = h0.shape
+    _, _, H1, W1 = h1.shape
+    A = ch // (5 + num_classes)
+    K = A * H0 * W0 + A * H1 * W1
+    out = np.zeros((N, K, 7), np.float32)
+    oc = np.zeros(N, np.int32)
+    oi = np.zeros((N, K), np.int32)
+    cand = np.zeros((N, K, 7), np.float32) if want_cand else None
+    cc = np.zeros(N, np.int32) if want_cand else None
+    ci = np.zeros((N, K), np.int32) if want_cand else None
+    aw = _f32(anchor_wh2).reshape(2, A, 2)
+    lib().oracle_decode_nms(_p(h0), _p(h1), N, A, num_classes, H0, W0, H1, W1, _p(aw),
+                            C.c_float(np.float32(conf_thr)), C.c_double(iou_thr), _p(out), _p(oc), _p(oi),
+                            _p(cand), _p(cc), _p(ci))
+    if want_cand:
+        return out, oc, oi, cand, cc, ci
+    return out, oc, oi
+
+
+def decode_nms(head0, head1, anchor_wh2, num_classes: int, conf_thr: float, iou_thr: float = NMS_IOU_THRESHOLD):
+    """mbv2_yolo.py:158-160 inference branch.  Returns (list of (k_b,7) detections,
+    list of kept global candidate ids (head1 ids offset by A*H0*W0))."""
+    out, oc, oi, cand, cc, ci = decode_nms_padded(head0, head1, anchor_wh2, num_classes, conf_thr, iou_thr, True)
+    dets = [out[b, :oc[b]].copy() for b in range(len(oc))]
+    ids = [ci[b][oi[b, :oc[b]]].copy() for b in range(len(oc))]
+    return dets, ids
+
+
+def pairwise(set_1, set_2, mode: str = "iou") -> np.ndarray:
+    """utils/iou.py: 'inter' = find_intersection, 'union' = find_union, 'iou' = find_jaccard_overlap."""
+    a, b = _f32(set_1).reshape(-1, 4), _f32(set_2).reshape(-1, 4)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    m = {"inter": 0, "union": 1, "iou": 2}[mode]
+    if out.size:
+        lib().oracle_pairwise(_p(a), a.shape[0], _p(b), b.shape[0], m, _p(out))
+    return out
+
+
+def box_ciou(box1, box2):
+    """YOLOLoss.box_ciou (yolo_loss.py:257-293): returns (iou - term, iou)."""
+    o = np.zeros(2, np.float32)
+    lib().oracle_box_ciou(_p(_f32(box1)), _p(_f32(box2)), _p(o))
+    return float(o[0]), float(o[1])
+
+
+def box_giou(box1, box2):
+    """YOLOLoss.box_giou (yolo_loss.py:295-317)."""
+    o = np.zeros(2, np.float32)
+    lib().oracle_box_giou(_p(_f32(box1)), _p(_f32(box2)), _p(o))
+    return float(o[0]), float(o[1])
+
+
+SCALAR_NAMES = ("loss", "recall", "avg_iou", "obj", "no_obj", "cls", "count_per_img", "l_dense", "l_iou", "sum_w",
+                "n_assign", "sum_sq_w", "iou_num", "iou_wsum", "sum_conf", "n_recall")
+
+
+def pack_targets(targets):
+    """list[N] of (n_b,5) -> (G,5) fp32 rows + (N+1,) int32 offsets."""
+    offs = np.zeros(len(targets) + 1, np.int32)
+    rows = []
+    for b, t in enumerate(targets):
+        t = _f32(t).reshape(-1, 5)
+        rows.append(t)
+        offs[b + 1] = offs[b] + t.shape[0]
+    gt = np.concatenate(rows, 0) if rows else np.zeros((0, 5), np.float32)
+    if gt.shape[0] == 0:
+        gt = np.zeros((1, 5), np.float32)  # keep a valid pointer
+    return _f32(gt), offs
+
+
+def target_loss(head, targets, anchors, mask, num_classes, img_size, ignore_threshold, iou_thresh, iou_weighting,
+                want_dense: bool = False):
+    """YOLOLoss.forward(input, targets) (yolo_loss.py:206-236) for one head.
+    Returns dict(scalars..., assign (n,6) int32 rows (b,t,k,gj,gi,best_n), terms (n,3))."""
+    x = _f32(head)
+    N, ch, H, W = x.shape
+    A = len(mask)
+    sa = scaled_anchors(anchors, img_size)
+    gt, offs = pack_targets(targets)
+    G = int(offs[-1])
+    max_assign = max(1, G * A)
+    assign = np.zeros((max_assign, 6), np.int32)
+    terms = np.zeros((max_assign, 3), np.float32)
+    scal = np.zeros(16, np.float64)
+    tg = np.zeros((N, A, H, W, num_classes + 1), np.float32) if want_dense else None
+    wg = np.zeros((N, A, H, W, num_classes + 1), np.float32) if want_dense else None
+    m = _i32(mask)
+    n = lib().oracle_target_loss(_p(x), N, A, num_classes, H, W, _p(sa), sa.shape[0], _p(m), _p(gt), _p(offs),
+                                 C.c_float(np.float32(ignore_threshold)), C.c_float(np.float32(iou_thresh)),
+                                 C.c_float(np.float32(iou_weighting)), _p(scal), _p(assign), _p(terms), max_assign,
+                                 _p(tg), _p(wg))
+    if n < 0:
+        raise IndexError("GT cell index out of range (the reference raises IndexError here, yolo_loss.py:149)")
+    res = {k: float(v) for k, v in zip(SCALAR_NAMES, scal)}
+    res["assign"] = assign[:n].copy()
+    res["terms"] = terms[:n].copy()
+    if want_dense:
+        res["targets"], res["weights"] = tg, wg
+    return res
