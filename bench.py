@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- decode + NMS images/s of the MobileNet-YOLO detection hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload cfg2|cfg2_sparse|cfg3|cfg5|cfg4_loss]
+
+A "step" is one pass of the hot path over one batch of synthetic head tensors
+(BASELINE.json configs[1]: MobileNetV2-YOLO 352x352 VOC heads, batch 256 per GPU,
+torch.randn heads, val_conf 0.3).  With N > 1 (launched under torchrun, one rank
+per GPU) the batch shards by image: every rank owns 256 images (weak scaling);
+there is no collective in the data path.  Rank 0 prints ONE JSON line.
+
+Keys beyond the base contract: `roofline` (dominant kernel, algorithmic bytes /
+CUDA-event time vs the measured HBM peak), `cpu_baseline` (the CPU oracle port on
+this box's host cores), `e2e` (same metric through the host-buffer C-ABI call,
+H2D + D2H inside the timed region), `extra` (sparse-head variant, NMS-only and
+all-gather timings).
+
+`--impl reference` times the reference's algorithm on the CPU: the reference is
+pure Python that cannot travel to the GPU box (/root/reference is absent there)
+so the arm runs the oracle port (oracle/yolo_oracle.c, OpenMP over all host
+threads) -- see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+VOC_ANCHORS = [[143, 265], [153, 121], [280, 279], [20, 37], [49, 94], [73, 201]]   # models/voc/config.yaml:20-26
+BDD_ANCHORS = [[34, 47], [66, 93], [122, 182], [6, 11], [11, 43], [16, 22]]         # models/bdd100k/config.yaml:17-23
+MASK = [[0, 1, 2], [3, 4, 5]]
+
+WORKLOADS = {
+    # name: (batch per GPU, classes, grids (H,W) of head0/head1, anchors, img_size [W,H], val_conf, conf logit shift)
+    "cfg2": dict(N=256, C=20, grids=[(11, 11), (22, 22)], anchors=VOC_ANCHORS, img=[352, 352], conf=0.3, shift=0.0,
+                 desc="MobileNetV2-YOLO 352x352 VOC 20-class heads, batch 256 per GPU, randn heads, val_conf 0.3"),
+    "cfg2_sparse": dict(N=256, C=20, grids=[(11, 11), (22, 22)], anchors=VOC_ANCHORS, img=[352, 352], conf=0.3,
+                        shift=-2.6, desc="cfg2 with objectness logits shifted by -2.6 (~4% of cells pass, as trained heads do)"),
+    "cfg3": dict(N=128, C=10, grids=[(12, 20), (24, 40)], anchors=BDD_ANCHORS, img=[640, 384], conf=0.3, shift=0.0,
+                 desc="MobileNetV3-YOLO BDD100k 10-class 640x384 heads, batch 1024/8 = 128 per GPU"),
+    "cfg5": dict(N=512, C=20, grids=[(13, 13), (26, 26)], anchors=VOC_ANCHORS, img=[416, 416], conf=0.001, shift=0.0,
+                 desc="dense-candidate NMS stress: 416x416 heads, val_conf 0.001, batch 4096/8 = 512 per GPU"),
+}
+A = 3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
+    return ap.parse_args()
+
+
+def make_heads(wl, N, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    C = wl["C"]
+    hs = []
+    for (H, W) in wl["grids"]:
+        h = torch.randn(N, A * (5 + C), H, W, generator=g)
+        if wl["shift"]:
+            h.view(N, A, 5 + C, H, W)[:, :, 4] += wl["shift"]
+        h = h.contiguous()
+        hs.append(h.pin_memory() if pin else h)
+    return hs
+
+
+def anchor_tables(wl):
+    sa = np.array([[aw / wl["img"][0], ah / wl["img"][1]] for aw, ah in wl["anchors"]], np.float64).astype(np.float32)
+    return np.stack([sa[MASK[0]], sa[MASK[1]]])
+
+
+def bytes_in_per_image(wl):
+    return sum(4 * A * (5 + wl["C"]) * H * W for (H, W) in wl["grids"])
+
+
+def cells_per_image(wl):
+    return sum(A * H * W for (H, W) in wl["grids"])
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """NVML poll (the recipe's nvidia-smi clocks line, at a few ms instead of 200 ms
+    so that sub-second timed regions are still seen)."""
+
+    def __init__(self, index):
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+            self.max_sm = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.003)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU (oracle) arm
+def cpu_decode_nms_rate(wl, budget_s=12.0, max_reps=50):
+    """images/s of the CPU oracle port on this box's cores, bounded sample."""
+    import oracle
+    N = wl["N"]
+    h0, h1 = make_heads(wl, N, seed=0)
+    h0, h1 = h0.numpy(), h1.numpy()
+    tables = anchor_tables(wl)
+    oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])  # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    reps = 0
+    times = []
+    while reps < max_reps and time.perf_counter() - t0 < budget_s:
+        t = time.perf_counter()
+        oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])
+        times.append(time.perf_counter() - t)
+        reps += 1
+    med = statistics.median(times)
+    return N / med, reps, med
+
+
+def run_reference(args, wl):
+    """--impl reference: the CPU path (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    N = wl["N"]
+    h0, h1 = make_heads(wl, N, seed=0)
+    h0, h1 = h0.numpy(), h1.numpy()
+    tables = anchor_tables(wl)
+    for _ in range(max(1, min(args.warmup, 3))):
+        oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])
+    steps = max(1, min(args.steps, 40))  # each step = one pass over the same batch of N images; bounded
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])
+    dt = time.perf_counter() - t0
+    val = N * steps / dt
+    line = {
+        "impl": "reference", "metric": "decode+NMS images/sec", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "batch": N},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": oracle.max_threads(), "kind": "port",
+                         "sample": f"{steps} passes over the full {N}-image batch (oracle/yolo_oracle.c, OpenMP)"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python and /root/reference does not exist on the GPU box; this arm is the "
+                "C restatement of its algorithm (pinned by tests/golden), all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def time_loop(fn, steps, stream=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1)  # ms
+
+
+def run_b200(args, wl):
+    import torch.distributed as dist
+    from mobilenet_yolo_pytorch_b200 import _lib, ops
+    from mobilenet_yolo_pytorch_b200 import dist as b2dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, C, conf = wl["N"], wl["C"], wl["conf"]
+    tables = anchor_tables(wl)
+    K = cells_per_image(wl)
+
+    # R rotating input sets so that successive steps never find their heads in the 126 MB L2
+    in_bytes = N * bytes_in_per_image(wl)
+    R = max(4, int(np.ceil(400e6 / in_bytes)))
+    sets = []
+    for r in range(R):
+        h0, h1 = make_heads(wl, N, seed=1000 * rank + r)
+        sets.append((h0.to(dev), h1.to(dev)))
+    out = torch.empty((N, K, 7), dtype=torch.float32, device=dev)
+    cnt = torch.empty((N,), dtype=torch.int32, device=dev)
+
+    def step(i):
+        h0, h1 = sets[i % R]
+        ops.decode_nms_padded(h0, h1, tables, C, conf, out=out, out_count=cnt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    # kept rows per launch (for the algorithmic bytes), averaged over the rotating sets
+    kept = []
+    for r in range(R):
+        step(r)
+        kept.append(int(cnt.sum().item()))
+    kept_per_launch = float(np.mean(kept))
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = time_loop(step, args.steps)
+    launches = _lib.launch_count() - l0
+    barrier()
+    # keep the same launch loop running ~0.4 s so the clock sampler sees the GPU under this load
+    if sampler:
+        t_end = time.perf_counter() + 0.4
+        i = 0
+        while time.perf_counter() < t_end:
+            step(i)
+            i += 1
+            if i % 256 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI host call (H2D + kernel + D2H inside)
+    hh0, hh1 = make_heads(wl, N, seed=7 + rank, pin=True)
+    ho = torch.empty((N, K, 7), dtype=torch.float32).pin_memory()
+    hc = torch.empty((N,), dtype=torch.int32).pin_memory()
+    for _ in range(3):
+        ops.decode_nms_host(hh0, hh1, tables, C, conf, device=local, out=ho, out_count=hc)
+    e2e_steps = max(3, min(args.steps, 30))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.decode_nms_host(hh0, hh1, tables, C, conf, device=local, out=ho, out_count=hc)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * N * e2e_steps / float(t.item())
+
+    extra = {}
+    if not args.no_extra:
+        # sparse-head variant of the same workload (trained heads pass ~4% of cells)
+        if wl["shift"] == 0.0:
+            wls = dict(wl, shift=-2.6)
+            ssets = []
+            for r in range(R):
+                h0, h1 = make_heads(wls, N, seed=5000 + 1000 * rank + r)
+                ssets.append((h0.to(dev), h1.to(dev)))
+
+            def sstep(i):
+                h0, h1 = ssets[i % R]
+                ops.decode_nms_padded(h0, h1, tables, C, conf, out=out, out_count=cnt)
+
+            for i in range(5):
+                sstep(i)
+            skept = []
+            for r in range(R):
+                sstep(r)
+                skept.append(int(cnt.sum().item()))
+            barrier()
+            sms = time_loop(sstep, args.steps) / args.steps
+            sbytes = in_bytes + 28 * float(np.mean(skept)) + 4 * N
+            extra["sparse_heads"] = {"images_per_s_per_gpu": N / (sms * 1e-3), "ms_per_step": sms,
+                                     "kept_rows_per_image": float(np.mean(skept)) / N,
+                                     "algorithmic_gbs": sbytes / (sms * 1e-3) / 1e9}
+            del ssets
+        # all-gather of the fixed-stride detections (the only collective the path may need)
+        if world > 1:
+            def gstep(i):
+                step(i)
+                b2dist.all_gather_detections(out, cnt)
+            for i in range(3):
+                gstep(i)
+            barrier()
+            gms = time_loop(gstep, max(10, args.steps // 4)) / max(10, args.steps // 4)
+            tg = torch.tensor([gms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            extra["with_allgather"] = {"images_per_s": world * N / (float(tg.item()) * 1e-3),
+                                       "ms_per_step": float(tg.item()),
+                                       "bytes_gathered_per_rank": int(world * N * (K + 1) * 28)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        algo_bytes = in_bytes + 28.0 * kept_per_launch + 4 * N
+        achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "decode_nms_traffic.json")))
+            traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        cpu_val, cpu_reps, cpu_med = cpu_decode_nms_rate(wl)
+        import oracle
+        line = {
+            "metric": "decode+NMS images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": N, "global_batch": world * N,
+                       "cells_per_image": K, "kept_rows_per_image": kept_per_launch / N,
+                       "l2": f"{R} rotating input sets ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2, so every step reads its heads from HBM",
+                       "parallelism": f"dp{world} by image, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "decode_nms_kernel<MODE_FUSED>",
+                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src + ", of measured"},
+            "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": oracle.max_threads(), "kind": "port",
+                             "sample": f"{cpu_reps} passes over the same {N}-image batch, median {cpu_med * 1e3:.1f} ms "
+                                       "(oracle/yolo_oracle.c, OpenMP, all host threads)"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(in_bytes),
+                    "d2h_bytes_per_step": int(N * K * 28 + 4 * N), "steps": e2e_steps,
+                    "api": "b200yolo_decode_nms_host (pinned host heads -> host detections, chunked 3-stream pipeline)",
+                    "timer": "host wall clock around the synchronous calls, max over ranks"},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

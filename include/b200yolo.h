@@ -1,0 +1,166 @@
+/*
+ * b200yolo.h -- C ABI of libb200yolo.so: the B200 (sm_100a) detection hot path of
+ * MobileNet-YOLO (decode -> confidence threshold -> per-class NMS; pairwise IoU;
+ * YOLOLoss target assignment + loss).
+ *
+ * The library is the drop-in boundary.  Every entry point
+ * replaces one Python-level function of the reference; the reference-side
+ * binding is a ctypes stub.  Reference citations are relative
+ * to the upstream repo root (eric612/Mobilenet-YOLO-Pytorch).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - "dev" pointers are device memory owned by the caller; the library never
+ *    allocates, frees or retains device memory passed to it (the *_host entry
+ *    point owns an internal, reusable staging context).
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*;
+ *    NULL = legacy default stream) and performs no host synchronisation, so
+ *    calls are CUDA-graph capturable.  The *_host entry point is synchronous.
+ *  - return value: 0 on success, a negative B200YOLO_E* code otherwise;
+ *    b200yolo_last_error() returns a thread-local message.  Nothing throws.
+ *  - head tensors are fp32, contiguous, NCHW: (N, A*(5+C), H, W); element
+ *    (b,a,t,j,i) at (((b*A+a)*(5+C)+t)*H+j)*W+i   (models/yolo_loss.py:84,186).
+ *  - candidate / detection rows are 7 floats:
+ *    [x1, y1, x2, y2, conf, class_score, class_index]   (models/yolo_loss.py:199).
+ *  - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef B200YOLO_H
+#define B200YOLO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200YOLO_VERSION 100 /* 0.1.0 */
+
+#define B200YOLO_OK 0
+#define B200YOLO_EINVAL (-1)      /* bad argument / shape */
+#define B200YOLO_EUNSUPPORTED (-2) /* shape exceeds what one CTA's shared memory can stage */
+#define B200YOLO_ECUDA (-3)       /* a CUDA runtime call failed (see last_error) */
+#define B200YOLO_ERANGE (-4)      /* a GT box maps outside the grid (reference: IndexError) */
+
+#define B200YOLO_MAX_ANCHORS 8      /* anchors per head (reference: 3) */
+#define B200YOLO_MAX_ALL_ANCHORS 16 /* anchors over all heads (reference: 6) */
+
+int b200yolo_version(void);
+const char *b200yolo_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (all
+ * streams); bench.py reports the delta over the timed region as gpu_launches. */
+unsigned long long b200yolo_launch_count(void);
+
+/* Largest number of candidate cells per image (sum over heads of A*H*W) that
+ * the fused / NMS kernels can stage in one CTA's shared memory on `device`. */
+int b200yolo_max_cells(int device);
+
+/*
+ * YOLOLoss.get_pred_boxes  (models/yolo_loss.py:180-204; dispatch :238-241).
+ * One head.  anchor_wh is a HOST array [A][2]: this head's anchors already
+ * divided by img_size (yolo_loss.py:214) and rounded to fp32.
+ *   rows  dev [N][A*H*W][7]  rows with conf > conf_thr, (a,j,i) row-major (:203)
+ *   count dev [N]
+ *   ids   dev [N][A*H*W] cell id (a*H+j)*W+i per emitted row, or NULL
+ */
+int b200yolo_decode_head(const float *head, int N, int A, int C, int H, int W, const float *anchor_wh,
+                         float conf_thr, float *rows, int *count, int *ids, void *stream);
+
+/*
+ * utils.box.nms  (utils/box.py:11-31) incl. the arithmetic of
+ * torchvision.ops.nms (call site utils/box.py:28): per image concatenate the
+ * two heads' candidates (:17), per class (:20-22) score = col5*col4 (:27),
+ * stable descending sort, greedy suppression iff (double)iou > iou_thr.
+ *   cand0/cand1 dev [N][stride0|1][7], count0/count1 dev [N]
+ *   out       dev [N][stride0+stride1][7]: class-ascending blocks, score-descending
+ *   out_count dev [N]
+ *   out_idx   dev [N][stride0+stride1]: index into the image's concatenated
+ *             candidate list of every output row (the "keep indices"), or NULL
+ */
+int b200yolo_nms(const float *cand0, const int *count0, int stride0, const float *cand1, const int *count1,
+                 int stride1, int N, int C, double iou_thr, float *out, int *out_count, int *out_idx, void *stream);
+
+/*
+ * Fused inference post-process of a two-head detector: what
+ * models/mbv2_yolo.py:158-160 computes with two YOLOLoss.forward calls and
+ * utils.box.nms, in ONE kernel launch with no host synchronisation.
+ *   anchor_wh HOST [2][A][2] scaled anchors of head 0 then head 1
+ *   out       dev [N][K][7], K = A*H0*W0 + A*H1*W1; out_count dev [N]
+ *   out_idx   dev [N][K] global cell id of every kept row (head-1 ids are offset
+ *             by A*H0*W0), or NULL
+ */
+int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                        int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
+                        int *out_count, int *out_idx, void *stream);
+
+/*
+ * Same computation from HOST buffers (the reference-facing call bench.py times
+ * as "e2e"): heads are copied host->device in image chunks on two streams,
+ * post-processed, and detections + counts copied back, overlapped.  Pinned
+ * host memory is recommended (pageable works, slower).  Synchronous.
+ */
+int b200yolo_decode_nms_host(const float *head0, const float *head1, int N, int A, int C, int H0, int W0,
+                             int H1, int W1, const float *anchor_wh, float conf_thr, double iou_thr,
+                             float *out, int *out_count, int device);
+
+/*
+ * utils.iou.find_intersection / find_union / find_jaccard_overlap
+ * (utils/iou.py:4-13, 14-31, 32-49).  mode 0 / 1 / 2.  set1 dev [n1][4],
+ * set2 dev [n2][4] xyxy; out dev [n1][n2].
+ */
+int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int mode, float *out, void *stream);
+
+/*
+ * YOLOLoss.forward(input, targets)  (models/yolo_loss.py:206-236): get_target
+ * (:77-178: decode, pred-vs-GT ignore mask, anchor-vs-GT IoU, best-anchor
+ * assignment, CIoU terms, class targets, stats) fused with weighted_mse_loss
+ * (:53-60) into partial sums.  One head.
+ *   anchors_all HOST [NA][2] ALL anchors / img_size, fp32;  mask HOST [A]
+ *   gt        dev [G][5] rows [cls(1-based), cx, cy, w, h]; gt_off dev [N+1]
+ *   G         total number of GT rows (= gt_off[N] on the host)
+ *   sums      dev double[16], OVERWRITTEN with this call's partial sums (see
+ *             B200YOLO_S_* below).  Data-parallel callers all-reduce(SUM) this
+ *             vector across ranks, then call b200yolo_loss_finalize.
+ *   assign    dev int32 [G][A][4] = (assigned?, gj, gi, best_n) per (GT, k), or NULL
+ *   terms     dev float [G][A][2] = (ciou value v, iou) per (GT, k), or NULL
+ *   status    dev int32[1], overwritten: 0 ok, 1 a GT maps outside the grid or has
+ *             a class outside [1,C] (reference: IndexError), 2 more than 1024 GT
+ *             boxes in one image
+ *   grad      dev (N, A*(5+C), H, W) or NULL: reserved (must be NULL in this version)
+ *   workspace dev, b200yolo_target_loss_workspace_bytes(N) bytes: per-image partial
+ *             sums, reduced in image order so results are bitwise reproducible
+ */
+size_t b200yolo_target_loss_workspace_bytes(int N);
+int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
+                         const int *mask, const float *gt, const int *gt_off, int G, float ignore_thr,
+                         float iou_thr, double *sums, int *assign, float *terms, int *status, float *grad,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* indices into the partial-sum vector of b200yolo_target_loss */
+enum {
+    B200YOLO_S_SQW = 0,      /* sum (o-t)^2 w           (yolo_loss.py:54-58) */
+    B200YOLO_S_W = 1,        /* sum w                   (:55) */
+    B200YOLO_S_IOU_SQ = 2,   /* sum_i (v_i-1)^2         (:224, quirk Q6: weights cancel) */
+    B200YOLO_S_IOU_W = 3,    /* sum_i (2-area_i)        (:160) */
+    B200YOLO_S_NASSIGN = 4,  /* count                   (:146) */
+    B200YOLO_S_OBJ = 5,      /* sum conf at assigned    (:152) */
+    B200YOLO_S_CONF_ALL = 6, /* sum conf over all cells (:98) */
+    B200YOLO_S_CLS = 7,      /* sum class score         (:169) */
+    B200YOLO_S_IOU = 8,      /* sum iou                 (:165) */
+    B200YOLO_S_RECALL = 9,   /* #(iou > ignore_thr)     (:163-164) */
+    B200YOLO_S_NCELLS = 10,  /* N*A*H*W                 (:99) */
+    B200YOLO_S_NIMG = 11,    /* N                       (:178) */
+    B200YOLO_S_COUNT = 16
+};
+
+/*
+ * Host-side finalisation (yolo_loss.py:170-178, 219-236) from (all-reduced)
+ * partial sums: result[7] = loss, recall, avg_iou, obj, no_obj, cls, count/N.
+ */
+int b200yolo_loss_finalize(const double *sums, float iou_weighting, double *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200YOLO_H */

@@ -1,0 +1,20 @@
+"""mobilenet_yolo_pytorch_b200 -- the B200 (sm_100a) detection hot path of
+eric612/Mobilenet-YOLO-Pytorch behind the reference's own entry points:
+
+    YOLOLoss                      <- models/yolo_loss.py::YOLOLoss
+    nms, wh_to_x2y2               <- utils/box.py
+    find_intersection/union/jaccard_overlap  <- utils/iou.py
+    decode_nms                    <- the inference branch of models/mbv2_yolo.py:158-160, fused
+
+All computation happens in libb200yolo.so (hand-written CUDA, C ABI in
+include/b200yolo.h); PyTorch only provides device memory, streams and
+torch.distributed.  There is no CPU fallback.
+"""
+from . import _lib, ops
+from .box import nms, wh_to_x2y2
+from .fused import decode_nms, decode_nms_padded, head_anchor_table, patch_reference
+from .iou import find_intersection, find_jaccard_overlap, find_union
+from .yolo_loss import YOLOLoss
+
+__all__ = ["YOLOLoss", "nms", "wh_to_x2y2", "find_intersection", "find_union", "find_jaccard_overlap", "decode_nms",
+           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops"]

@@ -1,0 +1,279 @@
+// b200yolo.cu -- C ABI (include/b200yolo.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -shared -Xcompiler -fPIC  (see mobilenet_yolo_pytorch_b200/build.py)
+#include "../../include/b200yolo.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "decode_nms.cuh"
+#include "pairwise.cuh"
+#include "target_loss.cuh"
+
+using namespace b200yolo;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail(B200YOLO_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                         \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);    \
+    } while (0)
+
+int smem_optin(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+    return v;
+}
+
+int current_device(int *dev) {
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    return 0;
+}
+
+void fill_head(HeadDesc &h, const float *ptr, int A, int H, int W, const float *anchor_wh) {
+    h.ptr = ptr;
+    h.H = H;
+    h.W = W;
+    h.HW = H * W;
+    h.cells = A * H * W;
+    h.invHW = 1.0f / (float)(H * W);
+    h.invW = 1.0f / (float)W;
+    h.fW = (float)W;
+    h.fH = (float)H;
+    for (int a = 0; a < kMaxAnchors; ++a) {
+        h.aw[a] = (a < A) ? anchor_wh[2 * a] : 0.f;
+        h.ah[a] = (a < A) ? anchor_wh[2 * a + 1] : 0.f;
+    }
+}
+
+IouThr make_thr(double thr) {
+    IouThr t;
+    t.thr = thr;
+    t.thr_f = (float)thr;
+    t.fast_ok = (thr > 0.0 && thr <= 1.0) ? 1 : 0;
+    return t;
+}
+
+template <int MODE>
+int launch_dn(const DNParams &p, cudaStream_t st) {
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    const SmemLayout L = make_layout(p.Kmax, p.C, MODE);
+    const int lim = smem_optin(dev);
+    if ((int)L.total > lim)
+        return fail(B200YOLO_EUNSUPPORTED,
+                    "%d candidate cells per image with %d classes need %u B of shared memory (limit %d B)", p.Kmax,
+                    p.C, L.total, lim);
+    static std::mutex mu;
+    static int configured[64] = {0};  // largest smem size opted into, per device
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (dev < 64 && configured[dev] < (int)L.total) {
+            CUDA_TRY(cudaFuncSetAttribute(decode_nms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            configured[dev] = lim;
+        }
+    }
+    if (p.N == 0) return 0;
+    decode_nms_kernel<MODE><<<p.N, kThreads, L.total, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200yolo_version(void) { return B200YOLO_VERSION; }
+const char *b200yolo_last_error(void) { return g_err; }
+unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
+
+int b200yolo_max_cells(int device) {
+    const int lim = smem_optin(device);
+    int lo = 0, hi = 1 << 16;
+    while (lo < hi) {  // largest Kmax whose fused layout fits (C = 80 as a conservative class count)
+        int mid = (lo + hi + 1) / 2;
+        if ((int)make_layout(mid, 80, MODE_FUSED).total <= lim) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+int b200yolo_decode_head(const float *head, int N, int A, int C, int H, int W, const float *anchor_wh,
+                         float conf_thr, float *rows, int *count, int *ids, void *stream) {
+    if (!head || !anchor_wh || !rows || !count) return fail(B200YOLO_EINVAL, "decode_head: null pointer");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H < 1 || W < 1)
+        return fail(B200YOLO_EINVAL, "decode_head: bad shape N=%d A=%d C=%d H=%d W=%d", N, A, C, H, W);
+    if ((long long)A * H * W > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_head: more than 65535 cells per image");
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    fill_head(p.head[0], head, A, H, W, anchor_wh);
+    p.nheads = 1;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.Kmax = A * H * W;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(0.45);
+    p.out = rows; p.out_count = count; p.out_idx = ids;
+    return launch_dn<MODE_DECODE>(p, (cudaStream_t)stream);
+}
+
+int b200yolo_nms(const float *cand0, const int *count0, int stride0, const float *cand1, const int *count1,
+                 int stride1, int N, int C, double iou_thr, float *out, int *out_count, int *out_idx, void *stream) {
+    if (!cand0 || !count0 || !out || !out_count) return fail(B200YOLO_EINVAL, "nms: null pointer");
+    if ((cand1 == nullptr) != (count1 == nullptr)) return fail(B200YOLO_EINVAL, "nms: cand1/count1 mismatch");
+    if (!cand1) stride1 = 0;
+    if (N < 0 || C < 1 || C > 4096 || stride0 < 0 || stride1 < 0 || stride0 + stride1 < 1)
+        return fail(B200YOLO_EINVAL, "nms: bad shape N=%d C=%d strides=%d,%d", N, C, stride0, stride1);
+    if (stride0 + stride1 > 65535) return fail(B200YOLO_EUNSUPPORTED, "nms: more than 65535 candidates per image");
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "nms: NaN threshold");
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    p.nheads = 0;
+    p.N = N; p.A = 0; p.C = C; p.attrs = 5 + C;
+    p.Kmax = stride0 + stride1;
+    p.iou = make_thr(iou_thr);
+    p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    p.cand[0] = cand0; p.cand_count[0] = count0; p.cand_stride[0] = stride0;
+    p.cand[1] = cand1; p.cand_count[1] = count1; p.cand_stride[1] = stride1;
+    return launch_dn<MODE_NMS>(p, (cudaStream_t)stream);
+}
+
+int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                        int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
+                        int *out_count, int *out_idx, void *stream) {
+    if (!head0 || !head1 || !anchor_wh || !out || !out_count) return fail(B200YOLO_EINVAL, "decode_nms: null pointer");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
+        return fail(B200YOLO_EINVAL, "decode_nms: bad shape");
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms: NaN threshold");
+    const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
+    if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms: more than 65535 cells per image");
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    fill_head(p.head[0], head0, A, H0, W0, anchor_wh);
+    fill_head(p.head[1], head1, A, H1, W1, anchor_wh + 2 * A);
+    p.nheads = 2;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.Kmax = (int)cells;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(iou_thr);
+    p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
+}
+
+int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int mode, float *out, void *stream) {
+    if (n1 < 0 || n2 < 0 || mode < 0 || mode > 2) return fail(B200YOLO_EINVAL, "pairwise: bad argument");
+    if (n1 == 0 || n2 == 0) return 0;
+    if (!set1 || !set2 || !out) return fail(B200YOLO_EINVAL, "pairwise: null pointer");
+    if (((uintptr_t)set1 | (uintptr_t)set2) & 15) return fail(B200YOLO_EINVAL, "pairwise: boxes must be 16-byte aligned");
+    dim3 grid((n2 + kPairTile - 1) / kPairTile, (n1 + kPairRows - 1) / kPairRows);
+    if (grid.y > 65535) return fail(B200YOLO_EUNSUPPORTED, "pairwise: n1 too large");
+    pairwise_kernel<<<grid, kPairTile, 0, (cudaStream_t)stream>>>((const float4 *)set1, n1, (const float4 *)set2, n2,
+                                                                   mode, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
+                         const int *mask, const float *gt, const int *gt_off, int G, float ignore_thr,
+                         float iou_thr, double *sums, int *assign, float *terms, int *status, float *grad,
+                         void *workspace, size_t workspace_bytes, void *stream) {
+    if (!head || !anchors_all || !mask || !gt_off || !sums || !status)
+        return fail(B200YOLO_EINVAL, "target_loss: null pointer");
+    if (G > 0 && !gt) return fail(B200YOLO_EINVAL, "target_loss: null gt");
+    if (grad) return fail(B200YOLO_EUNSUPPORTED, "target_loss: grad output is reserved (not implemented)");
+    if (N < 0 || A < 1 || A > kMaxAnchors || NA < A || NA > B200YOLO_MAX_ALL_ANCHORS || C < 1 || C > 4096 || H < 1 ||
+        W < 1 || G < 0)
+        return fail(B200YOLO_EINVAL, "target_loss: bad shape");
+    for (int k = 0; k < A; ++k)
+        if (mask[k] < 0 || mask[k] >= NA) return fail(B200YOLO_EINVAL, "target_loss: mask[%d]=%d out of range", k, mask[k]);
+    TLParams p;
+    memset(&p, 0, sizeof(p));
+    p.head = head;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C; p.H = H; p.W = W; p.HW = H * W; p.cells = A * H * W;
+    p.NA = NA;
+    p.invHW = 1.0f / (float)(H * W);
+    p.invW = 1.0f / (float)W;
+    p.fW = (float)W; p.fH = (float)H;
+    for (int a = 0; a < NA; ++a) { p.aw_all[a] = anchors_all[2 * a]; p.ah_all[a] = anchors_all[2 * a + 1]; }
+    for (int k = 0; k < A; ++k) p.mask[k] = mask[k];
+    p.gt = gt; p.gt_off = gt_off; p.G = G;
+    p.ignore_thr = ignore_thr; p.iou_thr = iou_thr;
+    p.sums = sums; p.assign = assign; p.terms = terms; p.status = status;
+    if (N > 0 && (!workspace || workspace_bytes < b200yolo_target_loss_workspace_bytes(N)))
+        return fail(B200YOLO_EINVAL, "target_loss: workspace too small (%zu < %zu)", workspace_bytes,
+                    b200yolo_target_loss_workspace_bytes(N));
+    p.partial = (double *)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    const uint32_t smem = tl_smem_bytes(p.cells);
+    const int lim = smem_optin(dev);
+    if ((int)smem > lim)
+        return fail(B200YOLO_EUNSUPPORTED, "target_loss: %d cells per image need %u B of shared memory (limit %d B)",
+                    p.cells, smem, lim);
+    {
+        static std::mutex mu;
+        static bool configured[64] = {false};
+        std::lock_guard<std::mutex> g(mu);
+        if (dev < 64 && !configured[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(target_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            configured[dev] = true;
+        }
+    }
+    CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
+    if (N > 0) {
+        target_loss_kernel<<<N, kTLThreads, smem, st>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+    }
+    target_loss_reduce_kernel<<<1, kTLSums * 32, 0, st>>>(p.partial, N, sums);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+size_t b200yolo_target_loss_workspace_bytes(int N) { return (size_t)(N > 0 ? N : 1) * kTLSums * sizeof(double); }
+
+int b200yolo_loss_finalize(const double *s, float iou_weighting, double *r) {
+    if (!s || !r) return fail(B200YOLO_EINVAL, "loss_finalize: null pointer");
+    const double count = s[B200YOLO_S_NASSIGN];
+    const double l_dense = s[B200YOLO_S_SQW] / s[B200YOLO_S_W];                 // yolo_loss.py:54-58
+    const double l_iou = count > 0 ? s[B200YOLO_S_IOU_SQ] / count : 0.0;        // :222-224 (quirk Q6)
+    r[0] = l_dense + l_iou * (double)iou_weighting;                             // :234
+    if (count > 0) {                                                            // :170-175
+        r[1] = s[B200YOLO_S_RECALL] / count;
+        r[2] = s[B200YOLO_S_IOU] / count;
+        r[3] = s[B200YOLO_S_OBJ] / count;
+        r[4] = (s[B200YOLO_S_CONF_ALL] - s[B200YOLO_S_OBJ]) / (s[B200YOLO_S_NCELLS] - count);
+        r[5] = s[B200YOLO_S_CLS] / count;
+    } else {
+        r[1] = r[2] = r[3] = r[4] = r[5] = 0.0;                                 // :176-177
+    }
+    r[6] = s[B200YOLO_S_NIMG] > 0 ? count / s[B200YOLO_S_NIMG] : 0.0;           // :178
+    return 0;
+}
+
+}  // extern "C"
+
+#include "host_pipeline.inl"

@@ -1,0 +1,101 @@
+// common.cuh -- shared device helpers for the b200yolo kernels (sm_100a).
+//
+// Arithmetic rules: every reference op is one fp32
+// rounding, so this translation unit is compiled with -fmad=false and without
+// --use_fast_math; FMA is used only where written explicitly (guard-band
+// filters whose exact fallback decides the close calls).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200yolo {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// yolo_loss.py:19 / :187-189 -- 1/(1+exp(-x)) with the accurate expf and an
+// IEEE (round-to-nearest) divide.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ float ldg_f(const float *p) { return __ldg(p); }
+
+// streaming load: head tensors are read exactly once
+__device__ __forceinline__ float ld_stream_f(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Order-preserving map float -> uint32 (ascending).  NaN sorts above +inf (torch
+// sort treats NaN as the largest value); -0.0 == +0.0.
+__device__ __forceinline__ uint32_t float_order_key(float s) {
+    uint32_t b = __float_as_uint(s);
+    if (s != s) return 0xffffffffu;
+    if (b == 0x80000000u) b = 0u;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// xyxy box area exactly as torchvision nms / utils/iou.py:39-40: (x2-x1)*(y2-y1)
+__device__ __forceinline__ float box_area(const float4 &b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+
+// torchvision nms_kernel semantics (call site utils/box.py:28):
+//   inter = max(0, min(x2)-max(x1)) * max(0, min(y2)-max(y1))
+//   iou   = inter / ((area_a + area_b) - inter)        (fp32, IEEE divide)
+//   suppress iff (double)iou > thr
+// The divide is skipped when a guard-banded multiply already decides: with
+// u > 0, |(inter - thr*u)/u| > 4e-6 is >10x every rounding involved (thr_f vs
+// thr 3e-8, one FMA rounding, the quotient's 6e-8), so the sign of d is the
+// exact answer; anything closer, u <= 0 or NaN takes the exact path.
+struct IouThr {
+    double thr;
+    float thr_f;
+    int fast_ok;  // thr in (0, 1]
+};
+
+__device__ __forceinline__ bool nms_suppress(const float4 &a, float area_a, const float4 &b, float area_b,
+                                             const IouThr &t) {
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    float inter = __fmul_rn(w, h);
+    float u = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    if (t.fast_ok && u > 0.0f) {
+        float d = __fmaf_rn(-t.thr_f, u, inter);
+        float e = __fmul_rn(4e-6f, u);
+        if (d > e) return true;
+        if (d < -e) return false;
+    }
+    float ovr = __fdiv_rn(inter, u);
+    return (double)ovr > t.thr;
+}
+
+// utils/iou.py:4-13 find_intersection for one pair (clamp(min=0) keeps NaN)
+__device__ __forceinline__ float pair_inter(const float4 &a, const float4 &b) {
+    float lx = fmaxf(a.x, b.x), ly = fmaxf(a.y, b.y);
+    float ux = fminf(a.z, b.z), uy = fminf(a.w, b.w);
+    float dx = __fsub_rn(ux, lx), dy = __fsub_rn(uy, ly);
+    dx = (dx < 0.0f) ? 0.0f : dx;
+    dy = (dy < 0.0f) ? 0.0f : dy;
+    return __fmul_rn(dx, dy);
+}
+// utils/iou.py:44  union = area1 + area2 - inter
+__device__ __forceinline__ float pair_union(float area_a, float area_b, float inter) {
+    return __fsub_rn(__fadd_rn(area_a, area_b), inter);
+}
+
+// warp inclusive scan (int)
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(kFullMask, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace b200yolo

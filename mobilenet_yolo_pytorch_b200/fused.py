@@ -1,0 +1,64 @@
+"""The fused inference branch of ``yolo.forward`` (models/mbv2_yolo.py:158-160):
+two ``YOLOLoss.forward`` calls and ``utils.box.nms`` become ONE kernel launch with
+no host synchronisation; the only D2H transfer is the per-image count vector
+needed to build the reference's ragged Python list."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def head_anchor_table(yolo_losses: Sequence) -> np.ndarray:
+    """(2, A, 2) scaled anchors of the two heads, from two YOLOLoss-like objects
+    (needs .anchors, .mask, .img_size -- the reference's own attributes)."""
+    assert len(yolo_losses) == 2
+    tabs = []
+    for l in yolo_losses:
+        sa = ops.scaled_anchors(l.anchors, l.img_size)
+        tabs.append(sa[list(l.mask)])
+    return np.stack(tabs).astype(np.float32)
+
+
+def decode_nms_padded(out0: torch.Tensor, out1: torch.Tensor, yolo_losses: Sequence, num_classes: Optional[int] = None,
+                      want_idx: bool = False, **buffers):
+    """Sync-free form: returns (dets (N,K,7), count (N,) int32 [, cell ids (N,K)])."""
+    l0, l1 = yolo_losses
+    if l0.val_conf != l1.val_conf:
+        raise RuntimeError("the fused path needs the same val_conf on both heads (the reference keeps them equal: "
+                           "inference.py:46-47, train.py:417-418)")
+    C = num_classes if num_classes is not None else l0.num_classes
+    return ops.decode_nms_padded(out0, out1, head_anchor_table(yolo_losses), C, l0.val_conf, want_idx=want_idx,
+                                 **buffers)
+
+
+def decode_nms(out0: torch.Tensor, out1: torch.Tensor, yolo_losses: Sequence, num_classes: Optional[int] = None,
+               return_indices: bool = False):
+    """Drop-in value of ``nms((loss0(out0), loss1(out1)), num_classes)``: list[N] of (k_b, 7)."""
+    res = decode_nms_padded(out0, out1, yolo_losses, num_classes, want_idx=return_indices)
+    dets, count = res[0], res[1]
+    counts = count.cpu().tolist()
+    lst = [dets[b, :k] for b, k in enumerate(counts)]
+    if return_indices:
+        return lst, [res[2][b, :k] for b, k in enumerate(counts)]
+    return lst
+
+
+def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_yolo=None) -> None:
+    """Swap the reference's entry points for the B200 ones inside already-imported
+    reference modules.  Pass the modules you want patched."""
+    from . import box as _box, iou as _iou, yolo_loss as _yl
+    if models_yolo_loss is not None:
+        models_yolo_loss.YOLOLoss = _yl.YOLOLoss
+    if utils_box is not None:
+        utils_box.nms = _box.nms
+    if utils_iou is not None:
+        utils_iou.find_intersection = _iou.find_intersection
+        utils_iou.find_union = _iou.find_union
+        utils_iou.find_jaccard_overlap = _iou.find_jaccard_overlap
+    if mbv2_yolo is not None:
+        mbv2_yolo.YOLOLoss = _yl.YOLOLoss
+        mbv2_yolo.nms = _box.nms

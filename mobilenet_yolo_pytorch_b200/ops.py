@@ -1,0 +1,219 @@
+"""Thin tensor-level wrappers over the C ABI (device pointers + current stream).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation
+is a kernel in libb200yolo.so.  Inputs must be CUDA tensors -- there is no CPU
+path (north star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NMS_IOU_THRESHOLD = 0.45  # utils/box.py:28
+
+
+def scaled_anchors(anchors: Sequence[Sequence[float]], img_size: Sequence[float]) -> np.ndarray:
+    """yolo_loss.py:214: python-double division, rounded to fp32 when it enters a
+    FloatTensor (pre_maps :67-68)."""
+    return np.array([[aw / img_size[0], ah / img_size[1]] for aw, ah in anchors], dtype=np.float64).astype(np.float32)
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the b200yolo kernels have no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what} must be float32 (got {t.dtype})")
+
+
+def _host_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class CandidateList(list):
+    """list[N] of (n_b, 7) views, as YOLOLoss.forward(input) returns it
+    (yolo_loss.py:202-204), that also remembers the padded device buffer it views
+    so utils.box.nms can consume it without repacking."""
+    padded: torch.Tensor  # (N, stride, 7)
+    counts: torch.Tensor  # (N,) int32, device
+    ids: Optional[torch.Tensor]  # (N, stride) int32 cell ids, device
+
+
+def _as_list(padded: torch.Tensor, counts_dev: torch.Tensor, ids: Optional[torch.Tensor] = None) -> CandidateList:
+    counts = counts_dev.cpu().tolist()  # the one D2H sync needed to build a ragged python list
+    out = CandidateList(padded[b, :n] for b, n in enumerate(counts))
+    out.padded, out.counts, out.ids = padded, counts_dev, ids
+    out.host_counts = counts
+    return out
+
+
+def decode_head_padded(head: torch.Tensor, anchor_wh, num_classes: int, conf_thr: float, want_ids: bool = False):
+    """b200yolo_decode_head: returns (rows (N,cells,7), count (N,) int32[, ids (N,cells) int32])."""
+    _require_cuda(head, "head")
+    head = head.contiguous()
+    N, ch, H, W = head.shape
+    attrs = 5 + num_classes
+    if ch % attrs:
+        raise RuntimeError(f"channel dim {ch} is not a multiple of 5+num_classes={attrs}")
+    A = ch // attrs
+    aw = _host_f32(anchor_wh).reshape(A, 2)
+    cells = A * H * W
+    with torch.cuda.device(head.device):
+        rows = torch.empty((N, cells, 7), dtype=torch.float32, device=head.device)
+        count = torch.empty((N,), dtype=torch.int32, device=head.device)
+        ids = torch.empty((N, cells), dtype=torch.int32, device=head.device) if want_ids else None
+        _lib.check(_lib.load().b200yolo_decode_head(
+            head.data_ptr(), N, A, num_classes, H, W, aw.ctypes.data, float(np.float32(conf_thr)), rows.data_ptr(),
+            count.data_ptr(), ids.data_ptr() if want_ids else None, _stream(head)))
+    return (rows, count, ids) if want_ids else (rows, count)
+
+
+def nms_padded(cand0: torch.Tensor, count0: torch.Tensor, cand1: Optional[torch.Tensor], count1: Optional[torch.Tensor],
+               num_classes: int, iou_thr: float = NMS_IOU_THRESHOLD, want_idx: bool = False):
+    """b200yolo_nms on fixed-stride candidates: returns (out (N,S,7), out_count (N,)[, out_idx (N,S)])."""
+    _require_cuda(cand0, "cand0")
+    cand0 = cand0.contiguous()
+    N, s0 = cand0.shape[0], cand0.shape[1]
+    s1 = 0
+    if cand1 is not None:
+        _require_cuda(cand1, "cand1")
+        cand1 = cand1.contiguous()
+        s1 = cand1.shape[1]
+    S = max(s0 + s1, 1)
+    with torch.cuda.device(cand0.device):
+        out = torch.empty((N, S, 7), dtype=torch.float32, device=cand0.device)
+        oc = torch.empty((N,), dtype=torch.int32, device=cand0.device)
+        oi = torch.empty((N, S), dtype=torch.int32, device=cand0.device) if want_idx else None
+        _lib.check(_lib.load().b200yolo_nms(
+            cand0.data_ptr(), count0.data_ptr(), s0, cand1.data_ptr() if cand1 is not None else None,
+            count1.data_ptr() if cand1 is not None else None, s1, N, num_classes, float(iou_thr), out.data_ptr(),
+            oc.data_ptr(), oi.data_ptr() if want_idx else None, _stream(cand0)))
+    return (out, oc, oi) if want_idx else (out, oc)
+
+
+def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
+                      iou_thr: float = NMS_IOU_THRESHOLD, want_idx: bool = False,
+                      out: Optional[torch.Tensor] = None, out_count: Optional[torch.Tensor] = None,
+                      out_idx: Optional[torch.Tensor] = None):
+    """b200yolo_decode_nms: ONE launch, no host sync.  Returns (out (N,K,7), out_count (N,)[, out_idx (N,K)]).
+    Pre-allocated outputs may be passed (CUDA-graph capture, NCCL send buffers)."""
+    _require_cuda(head0, "head0")
+    _require_cuda(head1, "head1")
+    head0, head1 = head0.contiguous(), head1.contiguous()
+    N, ch, H0, W0 = head0.shape
+    N1, ch1, H1, W1 = head1.shape
+    attrs = 5 + num_classes
+    if N1 != N or ch1 != ch or ch % attrs:
+        raise RuntimeError("head shapes do not match (N, A*(5+C), H, W) for both heads")
+    A = ch // attrs
+    K = A * H0 * W0 + A * H1 * W1
+    aw = _host_f32(anchor_wh2).reshape(2, A, 2)
+    with torch.cuda.device(head0.device):
+        if out is None:
+            out = torch.empty((N, K, 7), dtype=torch.float32, device=head0.device)
+        if out_count is None:
+            out_count = torch.empty((N,), dtype=torch.int32, device=head0.device)
+        if want_idx and out_idx is None:
+            out_idx = torch.empty((N, K), dtype=torch.int32, device=head0.device)
+        _lib.check(_lib.load().b200yolo_decode_nms(
+            head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
+            float(np.float32(conf_thr)), float(iou_thr), out.data_ptr(), out_count.data_ptr(),
+            out_idx.data_ptr() if want_idx else None, _stream(head0)))
+    return (out, out_count, out_idx) if want_idx else (out, out_count)
+
+
+def decode_nms_host(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
+                    iou_thr: float = NMS_IOU_THRESHOLD, device: int = 0, out: Optional[torch.Tensor] = None,
+                    out_count: Optional[torch.Tensor] = None):
+    """b200yolo_decode_nms_host: HOST tensors in (pinned recommended), HOST padded
+    detections out; chunked H2D / kernel / D2H pipeline inside the library."""
+    if head0.is_cuda or head1.is_cuda:
+        raise RuntimeError("decode_nms_host takes host tensors")
+    head0, head1 = head0.contiguous(), head1.contiguous()
+    N, ch, H0, W0 = head0.shape
+    _, _, H1, W1 = head1.shape
+    attrs = 5 + num_classes
+    A = ch // attrs
+    K = A * H0 * W0 + A * H1 * W1
+    aw = _host_f32(anchor_wh2).reshape(2, A, 2)
+    if out is None:
+        out = torch.empty((N, K, 7), dtype=torch.float32).pin_memory()
+    if out_count is None:
+        out_count = torch.empty((N,), dtype=torch.int32).pin_memory()
+    _lib.check(_lib.load().b200yolo_decode_nms_host(
+        head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
+        float(np.float32(conf_thr)), float(iou_thr), out.data_ptr(), out_count.data_ptr(), int(device)))
+    return out, out_count
+
+
+def pairwise(set_1: torch.Tensor, set_2: torch.Tensor, mode: int) -> torch.Tensor:
+    _require_cuda(set_1, "set_1")
+    _require_cuda(set_2, "set_2")
+    a = set_1.reshape(-1, 4).contiguous()
+    b = set_2.reshape(-1, 4).contiguous()
+    with torch.cuda.device(a.device):
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+        _lib.check(_lib.load().b200yolo_pairwise(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], mode,
+                                                 out.data_ptr(), _stream(a)))
+    return out
+
+
+def pack_targets(targets, device) -> Tuple[torch.Tensor, torch.Tensor, int, List[int]]:
+    """list[N] of (n_b,5) tensors/arrays (reference: CPU tensors, train.py:246) ->
+    one pinned (G,5) buffer + (N+1,) offsets, one async H2D each."""
+    counts = [int(t.shape[0]) if hasattr(t, "shape") and len(t.shape) else 0 for t in targets]
+    G = sum(counts)
+    offs = np.zeros(len(targets) + 1, np.int32)
+    np.cumsum(counts, out=offs[1:])
+    host = torch.empty((max(G, 1), 5), dtype=torch.float32).pin_memory()
+    o = 0
+    for t, n in zip(targets, counts):
+        if n:
+            host[o:o + n].copy_(torch.as_tensor(t, dtype=torch.float32).reshape(n, 5))
+            o += n
+    gt = host.to(device, non_blocking=True)
+    off_d = torch.from_numpy(offs).pin_memory().to(device, non_blocking=True)
+    return gt, off_d, G, counts
+
+
+def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,
+                     mask: Sequence[int], num_classes: int, ignore_thr: float, iou_thr: float,
+                     want_assign: bool = False):
+    """b200yolo_target_loss: returns (sums (16,) float64 device, status (1,) int32 device[, assign, terms])."""
+    _require_cuda(head, "head")
+    head = head.contiguous()
+    N, ch, H, W = head.shape
+    A = len(mask)
+    if ch != A * (5 + num_classes):
+        raise RuntimeError("head channel dim does not match len(mask)*(5+num_classes)")
+    sa = _host_f32(anchors_all_scaled).reshape(-1, 2)
+    m = np.ascontiguousarray(np.asarray(mask, dtype=np.int32))
+    lib = _lib.load()
+    with torch.cuda.device(head.device):
+        sums = torch.empty((_lib.S_COUNT,), dtype=torch.float64, device=head.device)
+        status = torch.empty((1,), dtype=torch.int32, device=head.device)
+        ws_bytes = int(lib.b200yolo_target_loss_workspace_bytes(N))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=head.device)
+        assign = torch.empty((max(G, 1), A, 4), dtype=torch.int32, device=head.device) if want_assign else None
+        terms = torch.empty((max(G, 1), A, 2), dtype=torch.float32, device=head.device) if want_assign else None
+        _lib.check(lib.b200yolo_target_loss(
+            head.data_ptr(), N, A, num_classes, H, W, sa.ctypes.data, sa.shape[0], m.ctypes.data, gt.data_ptr(),
+            gt_off.data_ptr(), int(G), float(np.float32(ignore_thr)), float(np.float32(iou_thr)), sums.data_ptr(),
+            assign.data_ptr() if want_assign else None, terms.data_ptr() if want_assign else None,
+            status.data_ptr(), None, ws.data_ptr(), ws_bytes, _stream(head)))
+    return (sums, status, assign, terms) if want_assign else (sums, status)
+
+
+def loss_finalize(sums_host: np.ndarray, iou_weighting: float) -> np.ndarray:
+    s = np.ascontiguousarray(np.asarray(sums_host, dtype=np.float64))
+    r = np.zeros(7, np.float64)
+    _lib.check(_lib.load().b200yolo_loss_finalize(s.ctypes.data, float(np.float32(iou_weighting)), r.ctypes.data))
+    return r

@@ -1,0 +1,87 @@
+"""Drop-in for the reference's ``models/yolo_loss.py::YOLOLoss`` (constructor,
+mutable attributes and both ``forward`` return conventions, yolo_loss.py:33-50,
+206-241) whose work is done by the sm_100a kernels in libb200yolo.so."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class YOLOLoss(nn.Module):
+    """Same signature as the reference (yolo_loss.py:33).
+
+    ``forward(input)``            -> list[N] of (n_b, 7) rows
+        ``[x1, y1, x2, y2, conf, class_score, class_index]`` with ``conf > val_conf``
+        in (a, j, i) row-major order (yolo_loss.py:180-204).
+    ``forward(input, targets)``   -> ``(loss, recall, avg_iou, obj, no_obj, cls_score, count)``
+        in the order of yolo_loss.py:236; ``targets`` is the reference's list[N] of
+        CPU ``(n_b, 5)`` tensors ``[cls(1-based), cx, cy, w, h]``.
+
+    ``val_conf``, ``img_size``, ``ignore_threshold``, ``iou_thresh``, ``iou_weighting``,
+    ``anchors`` and ``mask`` stay plain mutable attributes because the reference's
+    callers overwrite them (mbv2_yolo.py:139-140, inference.py:46-47, train.py:149-150,
+    417-418).
+
+    ``process_group``: optional torch.distributed group.  When set, the batch is a
+    shard of a data-parallel batch and the 16 partial sums are all-reduced (NCCL)
+    before the batch-global normalisation of yolo_loss.py:55,224,170-178.
+    """
+
+    def __init__(self, anchors, mask, num_classes, img_size, ignore_threshold, iou_thresh, val_conf=0.1,
+                 iou_weighting=0.01, process_group=None):
+        super().__init__()
+        self.anchors = anchors
+        self.mask = mask
+        self.num_mask = len(mask)
+        self.num_anchors = len(anchors)
+        self.num_classes = num_classes
+        self.bbox_attrs = 5 + num_classes
+        self.img_size = img_size
+        self.ignore_threshold = ignore_threshold
+        self.val_conf = val_conf
+        self.label_smooth_eps = 0.1  # yolo_loss.py:48; the kernel hard-codes the resulting 0.95 / 0.05
+        self.iou_thresh = iou_thresh
+        self.iou_weighting = iou_weighting
+        self.process_group = process_group
+        self.last_sums: Optional[torch.Tensor] = None
+
+    # yolo_loss.py:214
+    def scaled_anchors(self):
+        return ops.scaled_anchors(self.anchors, self.img_size)
+
+    def head_anchor_wh(self):
+        return self.scaled_anchors()[list(self.mask)]
+
+    def get_pred_boxes(self, input: torch.Tensor) -> ops.CandidateList:
+        rows, count, ids = ops.decode_head_padded(input, self.head_anchor_wh(), self.num_classes, self.val_conf,
+                                                  want_ids=True)
+        return ops._as_list(rows, count, ids)
+
+    def forward(self, input: torch.Tensor, targets=None):
+        if targets is None:
+            return self.get_pred_boxes(input)
+        N = input.size(0)
+        gt, gt_off, G, _ = ops.pack_targets(targets, input.device)
+        sums, status = ops.target_loss_sums(input, gt, gt_off, G, self.scaled_anchors(), self.mask, self.num_classes,
+                                            self.ignore_threshold, self.iou_thresh)
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.process_group)
+            dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.process_group)
+        self.last_sums = sums
+        host = torch.cat((sums, status.to(torch.float64))).cpu().numpy()  # one D2H sync (the reference has ~5 per GT)
+        st = int(host[-1])
+        if st == 1:
+            raise IndexError("a GT box maps outside the grid or has a class outside [1, num_classes] "
+                             "(the reference raises IndexError at yolo_loss.py:149)")
+        if st == 2:
+            raise RuntimeError("more than 1024 GT boxes in one image are not supported by the target-assignment kernel")
+        r = ops.loss_finalize(host[:_lib.S_COUNT], self.iou_weighting)
+        loss = torch.tensor(r[0], dtype=torch.float32, device=input.device)
+        no_obj = torch.tensor(r[4], dtype=torch.float32, device=input.device) if r[6] > 0 else 0
+        # yolo_loss.py:236 -- loss, recall, avg_iou, obj, no_obj (tensor), cls_score, count/bs
+        return loss, float(r[1]), float(r[2]), float(r[3]), no_obj, float(r[5]), float(r[6])

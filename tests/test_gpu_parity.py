@@ -1,0 +1,396 @@
+"""GPU parity tests (run on the B200 box: python -m pytest tests -m gpu).
+
+Every test calls the CUDA path through the C ABI (via the thin ctypes/torch shim)
+and checks it against the CPU oracle on the same seeded inputs and against the
+golden fixtures produced by the reference itself.
+
+Bars (BASELINE.json north_star): floats <= 1e-5 relative in fp32; candidate sets,
+NMS keep indices and anchor assignments bit-exact.  Index-level comparisons are
+made on IDENTICAL inputs (the oracle's NMS is fed the GPU's own decoded rows),
+because sigmoid/exp differ by an ulp between CPU libm and CUDA.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden, unpack_ragged
+
+import mobilenet_yolo_pytorch_b200 as b200
+from mobilenet_yolo_pytorch_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ATOL = 1e-6
+
+VOC_ANCHORS = [[143, 265], [153, 121], [280, 279], [20, 37], [49, 94], [73, 201]]
+BDD_ANCHORS = [[34, 47], [66, 93], [122, 182], [6, 11], [11, 43], [16, 22]]
+MASK = [[0, 1, 2], [3, 4, 5]]
+
+
+def make_heads(N, C, grids, seed, conf_shift=0.0, A=3):
+    g = torch.Generator().manual_seed(seed)
+    hs = []
+    for (H, W) in grids:
+        h = torch.randn(N, A * (5 + C), H, W, generator=g)
+        if conf_shift:
+            h.view(N, A, 5 + C, H, W)[:, :, 4] += conf_shift
+        hs.append(h.contiguous())
+    return hs
+
+
+def anchor_tables(anchors, img_size):
+    sa = oracle.scaled_anchors(anchors, img_size)
+    return np.stack([sa[MASK[0]], sa[MASK[1]]])
+
+
+def check_candidates(gpu_rows, gpu_ids, ora_rows, ora_ids, thr):
+    """same candidate set (cell ids) except cells whose conf sits within 1e-6 of the
+    threshold; common rows agree to 1e-5; class ids agree unless the top-2 class
+    scores are a near tie."""
+    for b in range(len(ora_rows)):
+        gi, oi = gpu_ids[b], ora_ids[b]
+        common, ga, oa = np.intersect1d(gi, oi, return_indices=True)
+        for extra, rows, ids in ((np.setdiff1d(gi, oi), gpu_rows[b], gi), (np.setdiff1d(oi, gi), ora_rows[b], oi)):
+            for cid in extra:
+                conf = rows[np.where(ids == cid)[0][0], 4]
+                assert abs(conf - np.float32(thr)) < 1e-6, f"image {b} cell {cid}: candidate set differs, conf={conf}"
+        g, o = gpu_rows[b][ga], ora_rows[b][oa]
+        np.testing.assert_allclose(g[:, :6], o[:, :6], rtol=RTOL, atol=ATOL)
+        bad = g[:, 6] != o[:, 6]
+        assert bad.sum() <= 2, f"{bad.sum()} class-id mismatches"  # near ties only, vanishingly rare
+        # order: ids strictly increasing = reference row-major order (yolo_loss.py:203)
+        assert np.all(np.diff(gi) > 0)
+
+
+def gpu_decode(head, anchor_wh, C, thr, dev):
+    rows, cnt, ids = ops.decode_head_padded(head.to(dev), anchor_wh, C, thr, want_ids=True)
+    cnt = cnt.cpu().numpy()
+    rows, ids = rows.cpu().numpy(), ids.cpu().numpy()
+    return [rows[b, :cnt[b]] for b in range(len(cnt))], [ids[b, :cnt[b]] for b in range(len(cnt))]
+
+
+# ----------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2"])
+def test_decode_head_vs_golden_and_oracle(case, cuda_device):
+    d = load_golden(case)
+    C, thr = int(d["num_classes"]), float(d["val_conf"])
+    sa = oracle.scaled_anchors(d["anchors"].tolist(), d["img_size"].tolist())
+    for i in range(2):
+        head = torch.from_numpy(d[f"head{i}"])
+        aw = sa[d["mask"][i]]
+        g_rows, g_ids = gpu_decode(head, aw, C, thr, cuda_device)
+        o_rows, o_ids = oracle.decode_head(d[f"head{i}"], aw, C, thr)
+        check_candidates(g_rows, g_ids, o_rows, o_ids, thr)
+        ref = unpack_ragged(d, f"p{i}")  # the reference's own rows
+        assert [len(r) for r in g_rows] == [len(r) for r in ref]
+        for a, b in zip(g_rows, ref):
+            np.testing.assert_allclose(a[:, :6], b.reshape(-1, 7)[:, :6], rtol=RTOL, atol=ATOL)
+            assert np.array_equal(a[:, 6], b.reshape(-1, 7)[:, 6])
+
+
+def test_yololoss_forward_eval_dropin(cuda_device):
+    """module surface: same ctor, attributes and list-of-(n,7) return (yolo_loss.py:33,206-241)."""
+    d = load_golden("voc_n2_conf03")
+    l = b200.YOLOLoss(VOC_ANCHORS, MASK[1], 20, [352, 352], 0.56, 0.55)
+    l.val_conf = 0.3  # callers mutate it (inference.py:46-47)
+    out = l(torch.from_numpy(d["head1"]).to(cuda_device))
+    ref = unpack_ragged(d, "p1")
+    assert isinstance(out, list) and len(out) == 2
+    for a, b in zip(out, ref):
+        assert a.is_cuda and a.shape == b.reshape(-1, 7).shape
+        np.testing.assert_allclose(a.cpu().numpy()[:, :6], b.reshape(-1, 7)[:, :6], rtol=RTOL, atol=ATOL)
+
+
+# ----------------------------------------------------------------------------- nms
+@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2", "nms_ties"])
+def test_nms_on_reference_candidates_bit_exact(case, cuda_device):
+    """utils.box.nms fed the reference's own candidate rows: kept rows and keep
+    indices must equal the reference's (torchvision) bit for bit."""
+    d = load_golden(case)
+    C = int(d["num_classes"])
+    p0 = [torch.from_numpy(np.ascontiguousarray(a.reshape(-1, 7))).to(cuda_device) for a in unpack_ragged(d, "p0")]
+    p1 = [torch.from_numpy(np.ascontiguousarray(a.reshape(-1, 7))).to(cuda_device) for a in unpack_ragged(d, "p1")]
+    dets, idx = b200.nms((p0, p1), C, return_indices=True)
+    ref_det, ref_idx = unpack_ragged(d, "det"), unpack_ragged(d, "det_idx")
+    for a, ia, b, ib in zip(dets, idx, ref_det, ref_idx):
+        assert np.array_equal(ia.cpu().numpy(), ib.reshape(-1))
+        assert np.array_equal(a.cpu().numpy(), b.reshape(-1, 7))
+
+
+def synth_candidates(n, C, seed, one_class=False, dup_scores=False):
+    r = np.random.RandomState(seed)
+    c = r.rand(n, 2).astype(np.float32)
+    wh = (r.rand(n, 2) * 0.3 + 0.02).astype(np.float32)
+    rows = np.zeros((n, 7), np.float32)
+    rows[:, 0:2] = c - wh / 2
+    rows[:, 2:4] = c + wh / 2
+    rows[:, 4] = r.rand(n).astype(np.float32)
+    rows[:, 5] = r.rand(n).astype(np.float32)
+    if dup_scores:  # heavy ties: scores from a handful of values
+        rows[:, 4] = r.choice([0.5, 0.25, 1.0], n).astype(np.float32)
+        rows[:, 5] = r.choice([0.5, 1.0], n).astype(np.float32)
+    rows[:, 6] = 0 if one_class else r.randint(0, C, n)
+    return rows
+
+
+@pytest.mark.parametrize("n0,n1,C,one_class,dup", [
+    (0, 0, 20, False, False), (1, 0, 20, False, False), (0, 1, 3, False, False), (31, 33, 1, True, False),
+    (363, 1452, 20, False, False), (363, 1452, 20, True, False),  # one giant class: 57 row tiles
+    (200, 700, 5, False, True), (64, 64, 2, False, True), (900, 2000, 80, False, False),
+])
+def test_nms_vs_oracle_shapes_and_ties(n0, n1, C, one_class, dup, cuda_device):
+    N = 3
+    c0 = [synth_candidates(n0, C, 10 + b, one_class, dup) for b in range(N)]
+    c1 = [synth_candidates(n1, C, 20 + b, one_class, dup) for b in range(N)]
+    c0[1] = c0[1][: n0 // 2]  # ragged
+    p0 = [torch.from_numpy(a).to(cuda_device) for a in c0]
+    p1 = [torch.from_numpy(a).to(cuda_device) for a in c1]
+    dets, idx = b200.nms((p0, p1), C, return_indices=True)
+    o_det, o_idx = oracle.nms([np.concatenate((a, b), 0) for a, b in zip(c0, c1)], C)
+    for a, ia, b, ib in zip(dets, idx, o_det, o_idx):
+        assert np.array_equal(ia.cpu().numpy(), ib)
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_nms_drops_rows_with_non_class_labels(cuda_device):
+    rows = synth_candidates(50, 4, 1)
+    rows[3, 6] = 2.5
+    rows[4, 6] = 7.0
+    rows[5, 6] = -1.0
+    p0 = [torch.from_numpy(rows).to(cuda_device)]
+    p1 = [torch.zeros(0, 7, device=cuda_device)]
+    dets, idx = b200.nms((p0, p1), 4, return_indices=True)
+    o_det, o_idx = oracle.nms([rows], 4)
+    assert np.array_equal(idx[0].cpu().numpy(), o_idx[0]) and np.array_equal(dets[0].cpu().numpy(), o_det[0])
+    assert not set(idx[0].cpu().numpy().tolist()) & {3, 4, 5}
+
+
+# ----------------------------------------------------------------------------- fused decode + nms
+def run_fused(h0, h1, tables, C, thr, dev):
+    out, cnt, idx = ops.decode_nms_padded(h0.to(dev), h1.to(dev), tables, C, thr, want_idx=True)
+    torch.cuda.synchronize()
+    cnt = cnt.cpu().numpy()
+    out, idx = out.cpu().numpy(), idx.cpu().numpy()
+    return [out[b, :cnt[b]] for b in range(len(cnt))], [idx[b, :cnt[b]] for b in range(len(cnt))]
+
+
+def check_fused_against_oracle(h0, h1, tables, C, thr, dev):
+    """(1) the fused kernel's candidates == the stand-alone decode kernel's; (2) the
+    oracle's NMS fed those SAME candidate rows keeps exactly the same cells in the
+    same order; (3) rows are bit-identical to the candidates they came from."""
+    dets, ids = run_fused(h0, h1, tables, C, thr, dev)
+    r0, i0 = gpu_decode(h0, tables[0], C, thr, dev)
+    r1, i1 = gpu_decode(h1, tables[1], C, thr, dev)
+    cells0 = h0.shape[1] // (5 + C) * h0.shape[2] * h0.shape[3]
+    cands = [np.concatenate((a, b), 0) for a, b in zip(r0, r1)]
+    cids = [np.concatenate((a, b + cells0)) for a, b in zip(i0, i1)]
+    o_det, o_idx = oracle.nms(cands, C)
+    for b in range(len(dets)):
+        assert np.array_equal(ids[b], cids[b][o_idx[b]]), f"image {b}: kept cell ids differ"
+        assert np.array_equal(dets[b], o_det[b], equal_nan=True), f"image {b}: kept rows differ"
+    return dets, ids
+
+
+@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2"])
+def test_fused_vs_golden(case, cuda_device):
+    d = load_golden(case)
+    C, thr = int(d["num_classes"]), float(d["val_conf"])
+    sa = oracle.scaled_anchors(d["anchors"].tolist(), d["img_size"].tolist())
+    tables = np.stack([sa[d["mask"][0]], sa[d["mask"][1]]])
+    h0, h1 = torch.from_numpy(d["head0"]), torch.from_numpy(d["head1"])
+    dets, _ = check_fused_against_oracle(h0, h1, tables, C, thr, cuda_device)
+    ref = unpack_ragged(d, "det")  # what the reference returned on the same heads
+    assert [len(x) for x in dets] == [len(x) for x in ref]
+    for a, b in zip(dets, ref):
+        np.testing.assert_allclose(a[:, :6], b.reshape(-1, 7)[:, :6], rtol=RTOL, atol=ATOL)
+        assert np.array_equal(a[:, 6], b.reshape(-1, 7)[:, 6])
+
+
+@pytest.mark.parametrize("name,N,C,grids,anchors,img,thr,shift", [
+    ("cfg1_voc_b1", 1, 20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0),
+    ("cfg2_voc_b256", 256, 20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0),
+    ("cfg2_sparse", 64, 20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, -2.6),
+    ("cfg3_bdd_640x384", 32, 10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384], 0.3, 0.0),
+    ("cfg5_416_dense", 16, 20, [(13, 13), (26, 26)], VOC_ANCHORS, [416, 416], 0.001, 0.0),
+    ("all_pass", 3, 20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], -1.0, 0.0),
+    ("one_class", 2, 1, [(7, 5), (14, 10)], VOC_ANCHORS, [160, 224], 0.3, 0.0),
+    ("coco80", 2, 80, [(10, 10), (20, 20)], VOC_ANCHORS, [320, 320], 0.3, 0.0),
+])
+def test_fused_configs_vs_oracle(name, N, C, grids, anchors, img, thr, shift, cuda_device):
+    h0, h1 = make_heads(N, C, grids, seed=0, conf_shift=shift)
+    tables = anchor_tables(anchors, img)
+    dets, ids = check_fused_against_oracle(h0, h1, tables, C, thr, cuda_device)
+    # end-to-end against the pure-CPU oracle (its own sigmoid/exp): same kept cells
+    # except near-threshold flips, floats to 1e-5
+    o_det, o_ids = oracle.decode_nms(h0.numpy(), h1.numpy(), tables, C, thr)
+    n_same = sum(int(np.array_equal(a, b)) for a, b in zip(ids, o_ids))
+    assert n_same >= len(ids) - max(1, len(ids) // 50), f"{len(ids) - n_same} images differ from the CPU oracle"
+    for a, ia, b, ib in zip(dets, ids, o_det, o_ids):
+        if np.array_equal(ia, ib):
+            np.testing.assert_allclose(a[:, :6], b[:, :6], rtol=RTOL, atol=ATOL)
+
+
+def test_fused_matches_separate_entry_points(cuda_device):
+    """decode_nms(out0,out1) == nms((loss0(out0), loss1(out1))) -- the three separate
+    entry points stay callable and equal."""
+    h0, h1 = make_heads(4, 20, [(11, 11), (22, 22)], seed=3)
+    losses = [b200.YOLOLoss(VOC_ANCHORS, MASK[i], 20, [352, 352], 0.6, 0.55, val_conf=0.3) for i in range(2)]
+    d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+    sep = b200.nms((losses[0](d0), losses[1](d1)), 20)
+    fus = b200.decode_nms(d0, d1, losses, 20)
+    assert len(sep) == len(fus) == 4
+    for a, b in zip(sep, fus):
+        assert torch.equal(a, b)
+
+
+def test_large_logits_and_class_ties(cuda_device):
+    """saturated sigmoids: many classes tie at exactly 1.0 -> first index wins
+    (torch.max :198); huge tw/th overflow to inf boxes without hanging NMS."""
+    N, C = 2, 20
+    h0, h1 = make_heads(N, C, [(11, 11), (22, 22)], seed=5)
+    v0 = h0.view(N, 3, 25, 11, 11)
+    v0[:, :, 5:] = 30.0 + torch.arange(C).view(1, 1, C, 1, 1).float()  # all sigmoid == 1.0
+    v1 = h1.view(N, 3, 25, 22, 22)
+    v1[:, :, 5:][:, :, 3] = 20.0
+    v1[:, :, 5:][:, :, 7] = 20.0                                        # exact tie between 3 and 7
+    v1[0, 0, 2, 0, 0] = 200.0                                           # exp overflow
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    dets, ids = check_fused_against_oracle(h0, h1, tables, C, 0.3, cuda_device)
+    o_det, o_ids = oracle.decode_nms(h0.numpy(), h1.numpy(), tables, C, 0.3)
+    for a, b in zip(dets, o_det):
+        assert set(np.unique(a[:, 6])) == set(np.unique(b[:, 6]))
+    cells0 = 3 * 121
+    for a, ia in zip(dets, ids):
+        assert np.all(a[ia < cells0, 6] == 0.0)
+        assert np.all(a[ia >= cells0, 6] == 3.0)
+
+
+def test_host_pipeline_equals_device_call(cuda_device):
+    h0, h1 = make_heads(37, 20, [(11, 11), (22, 22)], seed=9)
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    out_h, cnt_h = ops.decode_nms_host(h0.pin_memory(), h1.pin_memory(), tables, 20, 0.3, device=cuda_device.index or 0)
+    out_d, cnt_d = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, 20, 0.3)
+    assert torch.equal(cnt_h, cnt_d.cpu())
+    for b in range(37):
+        k = int(cnt_h[b])
+        assert torch.equal(out_h[b, :k], out_d[b, :k].cpu())
+
+
+def test_unsupported_shape_fails_loudly(cuda_device):
+    C = 20
+    h0 = torch.zeros(1, 75, 26, 26, device=cuda_device)
+    h1 = torch.zeros(1, 75, 52, 52, device=cuda_device)  # 10140 cells: more than one CTA can stage
+    with pytest.raises(RuntimeError, match="shared memory"):
+        ops.decode_nms_padded(h0, h1, anchor_tables(VOC_ANCHORS, [832, 832]), C, 0.3)
+
+
+# ----------------------------------------------------------------------------- pairwise IoU
+def test_pairwise_vs_golden_and_oracle(cuda_device):
+    d = load_golden("iou")
+    a, b = torch.from_numpy(d["a"]).to(cuda_device), torch.from_numpy(d["b"]).to(cuda_device)
+    for fn, mode in ((b200.find_intersection, "inter"), (b200.find_union, "union"), (b200.find_jaccard_overlap, "iou")):
+        got = fn(a, b).cpu().numpy()
+        np.testing.assert_allclose(got, d[mode], rtol=1e-6, atol=1e-7, equal_nan=True)
+        assert np.array_equal(got, oracle.pairwise(d["a"], d["b"], mode), equal_nan=True)  # same IEEE ops: bit-exact
+    r = np.random.RandomState(0)
+    big_a = np.sort(r.rand(1000, 2, 2), axis=1).reshape(1000, 4).astype(np.float32)[:, [0, 1, 2, 3]]
+    big_b = np.sort(r.rand(777, 2, 2), axis=1).reshape(777, 4).astype(np.float32)
+    got = b200.find_jaccard_overlap(torch.from_numpy(big_a).to(cuda_device), torch.from_numpy(big_b).to(cuda_device))
+    assert np.array_equal(got.cpu().numpy(), oracle.pairwise(big_a, big_b, "iou"), equal_nan=True)
+    assert b200.find_jaccard_overlap(torch.zeros(0, 4, device=cuda_device), b).shape == (0, 53)
+
+
+# ----------------------------------------------------------------------------- target assignment + loss
+def run_loss(head, targets, anchors, mask, C, img, ign, iou_t, iou_w, dev):
+    gt, off, G, _ = ops.pack_targets([torch.from_numpy(np.asarray(t, np.float32)) for t in targets], dev)
+    sums, status, assign, terms = ops.target_loss_sums(torch.from_numpy(head).to(dev), gt, off, G,
+                                                       oracle.scaled_anchors(anchors, img), mask, C, ign, iou_t,
+                                                       want_assign=True)
+    assert int(status.item()) == 0
+    res = ops.loss_finalize(sums.cpu().numpy(), iou_w)
+    return res, sums.cpu().numpy(), assign.cpu().numpy()[:G], terms.cpu().numpy()[:G]
+
+
+def compare_loss_with_oracle(head, targets, anchors, mask, C, img, ign, iou_t, iou_w, dev):
+    res, sums, assign, terms = run_loss(head, targets, anchors, mask, C, img, ign, iou_t, iou_w, dev)
+    o = oracle.target_loss(head, targets, anchors, mask, C, img, ign, iou_t, iou_w)
+    # assignments bit-exact: the oracle lists (b,t,k,gj,gi,best_n) in reference order
+    offs = np.concatenate(([0], np.cumsum([len(t) for t in targets])))
+    flags = assign[:, :, 0]
+    got = [(b, t, k, assign[offs[b] + t, k, 1], assign[offs[b] + t, k, 2], assign[offs[b] + t, k, 3])
+           for b in range(len(targets)) for t in range(len(targets[b])) for k in range(len(mask))
+           if flags[offs[b] + t, k]]
+    assert np.array_equal(np.array(got, np.int32).reshape(-1, 6), o["assign"])
+    assert int(round(sums[4])) == len(o["assign"])
+    want = np.array([o["loss"], o["recall"], o["avg_iou"], o["obj"], o["no_obj"], o["cls"], o["count_per_img"]])
+    np.testing.assert_allclose(res, want, rtol=RTOL, atol=1e-7)
+    if len(got):
+        tv = np.array([terms[offs[b] + t, k] for (b, t, k, _, _, _) in got])
+        np.testing.assert_allclose(tv[:, 0], o["terms"][:, 0], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(tv[:, 1], o["terms"][:, 1], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(sums[1], o["sum_w"], rtol=0, atol=0)  # weight count is an integer: exact
+    return res
+
+
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+def test_target_loss_vs_golden(case, cuda_device):
+    d = load_golden(case)
+    C = int(d["num_classes"])
+    targets = unpack_ragged(d, "targets")
+    for i in range(2):
+        res = compare_loss_with_oracle(d[f"head{i}"], targets, d["anchors"].tolist(), d["mask"][i].tolist(), C,
+                                       d["img_size"].tolist(), float(d["ignore_thresh"][i]), float(d["iou_thresh"]),
+                                       float(d["iou_weighting"]), cuda_device)
+        np.testing.assert_allclose(res, d[f"tuple{i}"], rtol=RTOL, atol=1e-7)  # the reference's own 7-tuple
+        # assignment flags vs the reference mirror
+        _, _, assign, _ = run_loss(d[f"head{i}"], targets, d["anchors"].tolist(), d["mask"][i].tolist(), C,
+                                   d["img_size"].tolist(), float(d["ignore_thresh"][i]), float(d["iou_thresh"]),
+                                   float(d["iou_weighting"]), cuda_device)
+        assert int(assign[:, :, 0].sum()) == len(d[f"assign{i}"])
+
+
+def synth_targets(N, G, C, seed):
+    r = np.random.RandomState(seed)
+    out = []
+    for b in range(N):
+        n = G if np.isscalar(G) else G[b]
+        wh = r.rand(n, 2) * 0.45 + 0.02
+        c = wh / 2 + r.rand(n, 2) * (1 - wh)
+        cls = r.randint(1, C + 1, (n, 1))
+        out.append(np.concatenate((cls, c, wh), 1).astype(np.float32))
+    return out
+
+
+@pytest.mark.parametrize("N,G,grid,C", [(8, 100, (11, 11), 20), (8, 100, (22, 22), 20), (5, [0, 1, 300, 7, 0], (22, 22), 20),
+                                         (4, 50, (12, 20), 10), (2, 1024, (26, 26), 3)])
+def test_target_loss_vs_oracle_config4_shapes(N, G, grid, C, cuda_device):
+    head = make_heads(N, C, [grid], seed=1)[0].numpy()
+    targets = synth_targets(N, G, C, seed=2)
+    img = [grid[1] * 16, grid[0] * 16]
+    compare_loss_with_oracle(head, targets, VOC_ANCHORS, MASK[1], C, img, 0.5623606200028424, 0.5497280113447018,
+                             0.021830872589525777, cuda_device)
+
+
+def test_yololoss_forward_train_dropin(cuda_device):
+    d = load_golden("loss_voc_n3")
+    targets = [torch.from_numpy(np.ascontiguousarray(t)) for t in unpack_ragged(d, "targets")]
+    l = b200.YOLOLoss(d["anchors"].tolist(), d["mask"][0].tolist(), 20, d["img_size"].tolist(),
+                      float(d["ignore_thresh"][0]), float(d["iou_thresh"]), iou_weighting=float(d["iou_weighting"]))
+    tup = l(torch.from_numpy(d["head0"]).to(cuda_device), targets)
+    assert len(tup) == 7 and isinstance(tup[0], torch.Tensor) and tup[0].is_cuda
+    got = np.array([float(tup[0]), tup[1], tup[2], tup[3], float(tup[4]), tup[5], tup[6]])
+    np.testing.assert_allclose(got, d["tuple0"], rtol=RTOL, atol=1e-7)
+    # bitwise reproducible run to run (fixed-order reduction)
+    tup2 = l(torch.from_numpy(d["head0"]).to(cuda_device), targets)
+    assert float(tup2[0]) == float(tup[0])
+
+
+def test_target_loss_out_of_range_gt_raises(cuda_device):
+    l = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.55)
+    head = make_heads(1, 20, [(11, 11)], seed=0)[0].to(cuda_device)
+    with pytest.raises(IndexError):
+        l(head, [torch.tensor([[1.0, 1.0, 0.5, 0.1, 0.1]])])  # cx == 1.0 -> gi == W (yolo_loss.py:128,149)
+    empty = l(head, [torch.zeros(0, 5)])  # no GT at all: loss is the pure no-object term, stats 0
+    assert empty[1:] == (0.0, 0.0, 0.0, 0, 0.0, 0.0)
