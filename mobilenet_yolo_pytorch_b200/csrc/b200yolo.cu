@@ -10,7 +10,7 @@
 #include <cstring>
 #include <mutex>
 
-#include "decode_nms.cuh"
+#include "decode_nms.cuh"  // (after the helpers it uses)
 #include "pairwise.cuh"
 #include "target_loss.cuh"
 
@@ -51,14 +51,16 @@ int current_device(int *dev) {
     return 0;
 }
 
+uint32_t div_magic(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (unsigned long long)d - 1) / (unsigned long long)d); }
+
 void fill_head(HeadDesc &h, const float *ptr, int A, int H, int W, const float *anchor_wh) {
     h.ptr = ptr;
     h.H = H;
     h.W = W;
     h.HW = H * W;
     h.cells = A * H * W;
-    h.invHW = 1.0f / (float)(H * W);
-    h.invW = 1.0f / (float)W;
+    h.magicHW = div_magic(H * W);
+    h.magicW = div_magic(W);
     h.fW = (float)W;
     h.fH = (float)H;
     for (int a = 0; a < kMaxAnchors; ++a) {
@@ -70,35 +72,56 @@ void fill_head(HeadDesc &h, const float *ptr, int A, int H, int W, const float *
 IouThr make_thr(double thr) {
     IouThr t;
     t.thr = thr;
-    t.thr_f = (float)thr;
     t.fast_ok = (thr > 0.0 && thr <= 1.0) ? 1 : 0;
+    const double tt = t.fast_ok ? thr / (1.0 + thr) : 0.0;  // iou > thr <=> inter > tt * (area_a + area_b)
+    t.t_hi = (float)(tt * (1.0 + 1e-5));
+    t.t_lo = (float)(tt * (1.0 - 1e-5));
     return t;
 }
 
-template <int MODE>
-int launch_dn(const DNParams &p, cudaStream_t st) {
-    int dev = 0;
-    if (int rc = current_device(&dev)) return rc;
-    const SmemLayout L = make_layout(p.Kmax, p.C, MODE);
-    const int lim = smem_optin(dev);
-    if ((int)L.total > lim)
-        return fail(B200YOLO_EUNSUPPORTED,
-                    "%d candidate cells per image with %d classes need %u B of shared memory (limit %d B)", p.Kmax,
-                    p.C, L.total, lim);
+// Two CTAs of 512 threads share an SM when one image's staging fits half of the
+// shared memory; larger images get the whole SM and 1024 threads.
+constexpr int kSmemHalfSM = (228 * 1024) / 2 - 1024;
+
+template <int MODE, int THREADS>
+int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     static std::mutex mu;
-    static int configured[64] = {0};  // largest smem size opted into, per device
+    static int configured[64] = {0};  // smem size opted into, per device
     {
         std::lock_guard<std::mutex> g(mu);
         if (dev < 64 && configured[dev] < (int)L.total) {
-            CUDA_TRY(cudaFuncSetAttribute(decode_nms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-            configured[dev] = lim;
+            CUDA_TRY(cudaFuncSetAttribute(decode_nms_kernel<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem_optin(dev)));
+            configured[dev] = smem_optin(dev);
         }
     }
-    if (p.N == 0) return 0;
-    decode_nms_kernel<MODE><<<p.N, kThreads, L.total, st>>>(p);
+    decode_nms_kernel<MODE, THREADS><<<p.N, THREADS, L.total, st>>>(p, L);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+template <int MODE>
+int launch_dn(DNParams &p, cudaStream_t st) {
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    const int lim = smem_optin(dev);
+    const SmemLayout base = make_layout(p.K, p.C, MODE, 0);
+    if ((int)base.total > lim)
+        return fail(B200YOLO_EUNSUPPORTED,
+                    "%d candidate cells per image with %d classes need %u B of shared memory (limit %d B)", p.K, p.C,
+                    base.total, lim);
+    if (p.N == 0) return 0;
+    if (MODE == MODE_DECODE) {
+        if ((int)base.total <= kSmemHalfSM && kSmemHalfSM <= lim) return launch_dn_t<MODE, 512>(p, base, dev, st);
+        return launch_dn_t<MODE, 1024>(p, base, dev, st);
+    }
+    const bool half = (int)base.total <= kSmemHalfSM && kSmemHalfSM <= lim;
+    const int budget = half ? kSmemHalfSM : lim;
+    const SmemLayout L = make_layout(p.K, p.C, MODE, (uint32_t)(budget - (int)base.total));
+    p.mask_cap_words = (int)L.mask_words;
+    if (half) return launch_dn_t<MODE, 512>(p, L, dev, st);
+    return launch_dn_t<MODE, 1024>(p, L, dev, st);
 }
 
 }  // namespace
@@ -112,9 +135,9 @@ unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
 int b200yolo_max_cells(int device) {
     const int lim = smem_optin(device);
     int lo = 0, hi = 1 << 16;
-    while (lo < hi) {  // largest Kmax whose fused layout fits (C = 80 as a conservative class count)
+    while (lo < hi) {  // largest K whose fused layout fits (C = 80 as a conservative class count)
         int mid = (lo + hi + 1) / 2;
-        if ((int)make_layout(mid, 80, MODE_FUSED).total <= lim) lo = mid; else hi = mid - 1;
+        if ((int)make_layout(mid, 80, MODE_FUSED, 0).total <= lim) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -130,7 +153,7 @@ int b200yolo_decode_head(const float *head, int N, int A, int C, int H, int W, c
     fill_head(p.head[0], head, A, H, W, anchor_wh);
     p.nheads = 1;
     p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
-    p.Kmax = A * H * W;
+    p.K = A * H * W;
     p.conf_thr = conf_thr;
     p.iou = make_thr(0.45);
     p.out = rows; p.out_count = count; p.out_idx = ids;
@@ -150,7 +173,7 @@ int b200yolo_nms(const float *cand0, const int *count0, int stride0, const float
     memset(&p, 0, sizeof(p));
     p.nheads = 0;
     p.N = N; p.A = 0; p.C = C; p.attrs = 5 + C;
-    p.Kmax = stride0 + stride1;
+    p.K = stride0 + stride1;
     p.iou = make_thr(iou_thr);
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;
     p.cand[0] = cand0; p.cand_count[0] = count0; p.cand_stride[0] = stride0;
@@ -173,7 +196,7 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
     fill_head(p.head[1], head1, A, H1, W1, anchor_wh + 2 * A);
     p.nheads = 2;
     p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
-    p.Kmax = (int)cells;
+    p.K = (int)cells;
     p.conf_thr = conf_thr;
     p.iou = make_thr(iou_thr);
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;

@@ -47,29 +47,25 @@ __device__ __forceinline__ float box_area(const float4 &b) { return __fmul_rn(__
 //   inter = max(0, min(x2)-max(x1)) * max(0, min(y2)-max(y1))
 //   iou   = inter / ((area_a + area_b) - inter)        (fp32, IEEE divide)
 //   suppress iff (double)iou > thr
-// The divide is skipped when a guard-banded multiply already decides: with
-// u > 0, |(inter - thr*u)/u| > 4e-6 is >10x every rounding involved (thr_f vs
-// thr 3e-8, one FMA rounding, the quotient's 6e-8), so the sign of d is the
-// exact answer; anything closer, u <= 0 or NaN takes the exact path.
+// The hot loop (decode_nms.cuh, pair masks) decides most pairs without the divide:
+// with t = thr/(1+thr), iou > thr <=> inter > t*(area_a+area_b) in exact arithmetic,
+// and every rounding on either side is < 5e-7 relative, so outside a 1e-5 guard
+// band (t_hi, t_lo) the cheap comparison IS the exact answer; inside the band, for
+// degenerate boxes (area not in [1e-30, 1e30]) and for thr outside (0,1] this exact
+// routine decides.
 struct IouThr {
     double thr;
-    float thr_f;
-    int fast_ok;  // thr in (0, 1]
+    float t_hi, t_lo;  // thr/(1+thr) * (1 +- 1e-5)
+    int fast_ok;       // thr in (0, 1]
 };
 
-__device__ __forceinline__ bool nms_suppress(const float4 &a, float area_a, const float4 &b, float area_b,
-                                             const IouThr &t) {
+__device__ __forceinline__ bool nms_suppress_exact(const float4 &a, float area_a, const float4 &b, float area_b,
+                                                   const IouThr &t) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
     float inter = __fmul_rn(w, h);
     float u = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-    if (t.fast_ok && u > 0.0f) {
-        float d = __fmaf_rn(-t.thr_f, u, inter);
-        float e = __fmul_rn(4e-6f, u);
-        if (d > e) return true;
-        if (d < -e) return false;
-    }
     float ovr = __fdiv_rn(inter, u);
     return (double)ovr > t.thr;
 }

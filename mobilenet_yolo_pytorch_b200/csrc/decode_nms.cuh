@@ -1,43 +1,55 @@
-// decode_nms.cuh -- YOLO-head decode + confidence threshold + per-class NMS.
+// decode_nms.cuh -- YOLO-head decode + confidence threshold + per-class NMS (sm_100a).
 //
-// One CTA per image.  Everything about one image (<= a few thousand candidate
-// boxes) is staged in shared memory; the head tensors are read from HBM once,
-// coalesced (threads walk the contiguous H*W plane of one attribute), and only
-// the kept rows are written back.  Phases (all inside one launch):
+// One CTA per image; everything about one image lives in shared memory, the head
+// tensors are read from HBM exactly once and only kept rows are written back.
 //
-//   A1  objectness plane -> sigmoid -> `conf > thr` -> ORDER-PRESERVING compaction
-//       (warp ballot + popc prefix, block scan of warp totals): candidate k keeps
-//       the reference's (head, a, j, i) row-major order (yolo_loss.py:201-203).
-//   A2  one thread per surviving candidate: box decode (yolo_loss.py:186-196,
-//       243-247), class max/argmax (:198), per-class histogram.
-//   B   exclusive scan of the class histogram -> class segments (box.py:20-22).
-//   C   scatter 64-bit sort keys (score desc, candidate order asc = stable sort
-//       of torchvision.ops.nms) into class segments; rank-sort inside each
-//       segment; permute boxes into sorted order.
-//   D   per class (one warp each): 32x32 bitmask-tiled greedy NMS -- the diagonal
-//       tile is resolved with a ballot/bitmask sweep, its kept rows are then
-//       applied to all later column tiles (suppressed rows are never visited).
-//   E   class-ascending / score-descending output order (box.py:29-30): scan of
-//       per-class kept counts, then a flat coalesced store of the kept rows.
+//   P1 decode     thread per cell, ALL 5+C attribute planes of the cell loaded at
+//                 once (coalesced: consecutive lanes = consecutive cells of a plane;
+//                 every load is independent, so ~13 x THREADS x 4 B are in flight
+//                 per CTA).  conf = sigmoid(tc) > thr (yolo_loss.py:189,201); for
+//                 passing cells: class max / argmax (:198), box (:186-196,243-247),
+//                 one 32-byte record in shared memory, pass bit (ballot) and the
+//                 per-class arrival index (one shared atomic).
+//   P2 class scan exclusive scan of the class histogram -> class segments
+//                 (box.py:20-22), tiles, pair-slot and bitmask offsets.
+//   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort
+//                 of torchvision.ops.nms) into class segments.
+//   P4 rank sort  rank inside the class segment -> `sord` (sorted position -> record).
+//   P5 pair masks ALL threads: for every pair (row i < column j) of a class, bit i
+//                 of column j's mask = "i suppresses j".  Column j and column
+//                 n-1-j share a lane, so every lane does n-1 tests (balanced) while
+//                 row records are broadcast from shared memory.  The test is a
+//                 divide-free two-sided filter (inter > t*(area_i+area_j) with a
+//                 1e-5 guard band, t = thr/(1+thr)); only pairs inside the band run
+//                 the exact torchvision arithmetic (inter/(Sa+Sb-inter) > thr in
+//                 double).  Result bits are accumulated with FFMA (fma pipe) so the
+//                 alu pipe (FMNMX/FSET) is not the only one working.
+//   P6 sweep      one warp per class walks 32-column tiles: columns suppressed by a
+//                 kept row of an earlier tile drop out with one AND per tile, the
+//                 diagonal tile is resolved with ballot/shfl in ascending order.
+//   P7-9 output   class-ascending / score-descending rows (box.py:29-30): scan of the
+//                 kept bitmap, then a flat coalesced store.
 //
-// The same phases are reused by the stand-alone decode (A1,A2 + store) and NMS
-// (load rows, B..E) kernels, which back YOLOLoss.forward(input) and
-// utils.box.nms separately.
+// If the masks of all classes do not fit the shared-memory budget, P5/P6 run in
+// rounds (groups of whole classes, or column-tile chunks of one huge class).
+//
+// The stand-alone decode (P1 + ordered compaction + store) and NMS (load rows,
+// P2..P9) kernels back YOLOLoss.forward(input) and utils.box.nms separately.
 #pragma once
 #include "common.cuh"
 
 namespace b200yolo {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
 constexpr int kMaxAnchors = 8;
+constexpr uint32_t kNoClass = 0xffffu;
 
 enum { MODE_FUSED = 0, MODE_DECODE = 1, MODE_NMS = 2 };
 
 struct HeadDesc {
     const float *ptr;
-    int H, W, HW, cells;  // cells = A*H*W
-    float invHW, invW, fW, fH;
+    int H, W, HW, cells;         // cells = A*H*W
+    uint32_t magicHW, magicW;    // ceil(2^32/d) for exact n/d, n < 65536 (0: d == 1)
+    float fW, fH;
     float aw[kMaxAnchors], ah[kMaxAnchors];  // anchors / img_size (yolo_loss.py:214)
 };
 
@@ -45,7 +57,8 @@ struct DNParams {
     HeadDesc head[2];
     int nheads;
     int N, A, C, attrs;
-    int Kmax;  // row stride of out / out_idx (= total cells, or stride0+stride1 in NMS mode)
+    int K;               // candidate slots per image = row stride of out / out_idx
+    int mask_cap_words;  // capacity of the pair-mask buffer (32-bit words)
     float conf_thr;
     IouThr iou;
     float *out;
@@ -57,452 +70,683 @@ struct DNParams {
     int cand_stride[2];
 };
 
+// 32-byte candidate record, indexed by cell id (candidate id)
+struct __align__(16) Rec {
+    float4 box;   // x1 y1 x2 y2            (output columns 0-3)
+    float conf;   //                         (column 4)
+    float score;  // class score             (column 5)
+    float ta_hi;  // t*(1+1e-5)*area   (+inf: always take the exact path)
+    float ta_lo;  // t*(1-1e-5)*area   (-inf: always take the exact path)
+};
+
 struct SmemLayout {
-    uint32_t box, sbox, key, conf, cscore, sarea, cell, order, cls, alive;
-    uint32_t hist, start, kcount, kstart, wcount, misc, total;
+    uint32_t rec, clsidx, sord, key, passbits, keptbits, tilepref, cls, rounds, misc, total;
+    uint32_t mask_words;  // words available at `key` (keys are dead once ranks are known)
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(int Kmax, int C, int mode) {
+// per-class int arrays, each (C+1) long
+enum { CA_CNT = 0, CA_START, CA_KTILE, CA_SLOT, CA_MASK, CA_NUM };
+// misc ints
+enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_SLOTS, M_CTR, M_TOTAL, M_KV, M_NUM = 16 };
+
+__host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32_t extra_mask_bytes) {
     SmemLayout L;
-    uint32_t K = align_up((uint32_t)(Kmax > 0 ? Kmax : 1), 16);
-    uint32_t Cp = align_up((uint32_t)C + 2, 4);
-    uint32_t o = 0;
+    const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
+    const uint32_t Cp = align_up((uint32_t)C + 1, 4);
+    const uint32_t tiles = Kp / 32 + (uint32_t)C + 1;
     const bool nms = (mode != MODE_DECODE);
-    L.box = o; o += 16 * K;
-    L.sbox = o; o += nms ? 16 * K : 0;
-    L.key = o; o += nms ? 8 * K : 0;   // (outsrc, uint16, aliases key after the rank phase)
-    L.conf = o; o += 4 * K;
-    L.cscore = o; o += 4 * K;
-    L.sarea = o; o += nms ? 4 * K : 0;
-    L.cell = o; o += 4 * K;
-    L.order = o; o += nms ? 2 * K : 0;
-    L.cls = o; o += 2 * K;
-    L.alive = o; o += nms ? K : 0;
+    uint32_t o = 0;
+    L.rec = o; o += 32 * Kp;
+    L.clsidx = o; o += 4 * Kp;
+    L.sord = o; o += nms ? 4 * (2 * Kp + 64) : 2 * Kp;  // decode mode: u16 output order
+    L.key = o; o += nms ? 8 * Kp + (extra_mask_bytes & ~15u) : 0;
+    L.mask_words = nms ? (8 * Kp + (extra_mask_bytes & ~15u)) / 4 : 0;
+    L.passbits = o; o += 4 * (Kp / 32);
+    L.keptbits = o; o += nms ? 4 * tiles : 0;
+    L.tilepref = o; o += 4 * (tiles + 1);
     o = align_up(o, 16);
-    L.hist = o; o += 4 * Cp;
-    L.start = o; o += 4 * Cp;
-    L.kcount = o; o += 4 * Cp;
-    L.kstart = o; o += 4 * Cp;
-    L.wcount = o; o += 4 * 2 * kWarps;
-    L.misc = o; o += 64;
+    L.cls = o; o += nms ? 4 * Cp * CA_NUM : 0;
+    L.rounds = o; o += nms ? 8 * (tiles + (uint32_t)C + 2) : 0;
+    L.misc = o; o += 4 * M_NUM;
     L.total = align_up(o, 16);
     return L;
 }
 
 struct Smem {
-    float4 *box, *sbox;
+    Rec *rec;
+    uint32_t *clsidx;   // (class << 16) | arrival index inside the class
+    uint32_t *sord;     // sorted position -> shared-space address of the record
+    uint16_t *outsrc;   // output row -> cell id (aliases sord in decode mode, keys otherwise)
     unsigned long long *key;
-    uint16_t *outsrc;
-    float *conf, *cscore, *sarea;
-    uint32_t *cell;
-    uint16_t *order, *cls;
-    uint8_t *alive;
-    int *hist, *start, *kcount, *kstart, *wcount, *misc;
+    uint32_t *mask;     // aliases key
+    uint32_t *passbits, *keptbits, *tilepref;
+    int *cnt, *start, *ktile, *slot, *maskbase;
+    uint2 *rounds;      // x = c_lo | c_hi << 16, y = t0 | t1 << 16
+    int *misc;
+    uint32_t rec_saddr;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) {
+__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, int C, int mode) {
     Smem s;
-    s.box = reinterpret_cast<float4 *>(base + L.box);
-    s.sbox = reinterpret_cast<float4 *>(base + L.sbox);
+    const uint32_t Cp = align_up((uint32_t)C + 1, 4);
+    s.rec = reinterpret_cast<Rec *>(base + L.rec);
+    s.clsidx = reinterpret_cast<uint32_t *>(base + L.clsidx);
+    s.sord = reinterpret_cast<uint32_t *>(base + L.sord);
     s.key = reinterpret_cast<unsigned long long *>(base + L.key);
-    s.outsrc = reinterpret_cast<uint16_t *>(base + L.key);
-    s.conf = reinterpret_cast<float *>(base + L.conf);
-    s.cscore = reinterpret_cast<float *>(base + L.cscore);
-    s.sarea = reinterpret_cast<float *>(base + L.sarea);
-    s.cell = reinterpret_cast<uint32_t *>(base + L.cell);
-    s.order = reinterpret_cast<uint16_t *>(base + L.order);
-    s.cls = reinterpret_cast<uint16_t *>(base + L.cls);
-    s.alive = reinterpret_cast<uint8_t *>(base + L.alive);
-    s.hist = reinterpret_cast<int *>(base + L.hist);
-    s.start = reinterpret_cast<int *>(base + L.start);
-    s.kcount = reinterpret_cast<int *>(base + L.kcount);
-    s.kstart = reinterpret_cast<int *>(base + L.kstart);
-    s.wcount = reinterpret_cast<int *>(base + L.wcount);
+    s.mask = reinterpret_cast<uint32_t *>(base + L.key);
+    s.outsrc = (mode == MODE_DECODE) ? reinterpret_cast<uint16_t *>(base + L.sord)
+                                     : reinterpret_cast<uint16_t *>(base + L.key);
+    s.passbits = reinterpret_cast<uint32_t *>(base + L.passbits);
+    s.keptbits = reinterpret_cast<uint32_t *>(base + L.keptbits);
+    s.tilepref = reinterpret_cast<uint32_t *>(base + L.tilepref);
+    int *ca = reinterpret_cast<int *>(base + L.cls);
+    s.cnt = ca + CA_CNT * Cp;
+    s.start = ca + CA_START * Cp;
+    s.ktile = ca + CA_KTILE * Cp;
+    s.slot = ca + CA_SLOT * Cp;
+    s.maskbase = ca + CA_MASK * Cp;
+    s.rounds = reinterpret_cast<uint2 *>(base + L.rounds);
     s.misc = reinterpret_cast<int *>(base + L.misc);
+    s.rec_saddr = (uint32_t)__cvta_generic_to_shared(s.rec);
     return s;
 }
 
-constexpr uint16_t kNoClass = 0xffffu;
+__device__ __forceinline__ int fastdiv(int n, int d, uint32_t magic) {
+    (void)d;
+    return magic ? (int)__umulhi((uint32_t)n, magic) : n;  // exact for n < 65536
+}
+
+__device__ __forceinline__ int tri(int x) { return (x * (x + 1)) >> 1; }
+
+__device__ __forceinline__ void lds_rec(uint32_t saddr, float4 &box, float2 &ta) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(box.x), "=f"(box.y), "=f"(box.z), "=f"(box.w)
+                 : "r"(saddr));
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+24];" : "=f"(ta.x), "=f"(ta.y) : "r"(saddr));
+}
+
+__device__ __forceinline__ float4 lds_box(uint32_t saddr) {
+    float4 b;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(saddr));
+    return b;
+}
+
+// guard-banded area terms of one box for the divide-free pair filter
+__device__ __forceinline__ void make_ta(const float4 &b, const IouThr &t, float &hi, float &lo) {
+    const float a = box_area(b);
+    const bool ok = t.fast_ok && a >= 1e-30f && a <= 1e30f;
+    hi = ok ? __fmul_rn(a, t.t_hi) : INFINITY;
+    lo = ok ? __fmul_rn(a, t.t_lo) : -INFINITY;
+}
 
 // ---------------------------------------------------------------------------
-// A1: objectness threshold + order-preserving compaction.  Returns K (uniform).
+// P1: decode every cell of the image (both heads), single pass
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int phase_threshold_compact(const DNParams &p, const Smem &s, int b) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int THREADS, bool HIST>
+__device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, int b) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int K = p.K, C = p.C;
     const int cells0 = p.head[0].cells;
-    const int total = cells0 + (p.nheads > 1 ? p.head[1].cells : 0);
-    int base_k = 0;
-    int parity = 0;
-    for (int base = 0; base < total; base += kThreads, parity ^= 1) {
+    for (int base = 0; base < K; base += THREADS) {
         const int cid = base + tid;
         bool pass = false;
-        float conf = 0.0f;
-        if (cid < total) {
+        if (cid < K) {
             const bool h1 = cid >= cells0;
             const HeadDesc &hd = h1 ? p.head[1] : p.head[0];
             const int local = h1 ? cid - cells0 : cid;
-            const int a = (int)(((float)local + 0.5f) * hd.invHW);
-            const int pos = local - a * hd.HW;
-            const float *q = hd.ptr + ((size_t)(b * p.A + a) * p.attrs + 4) * hd.HW + pos;
-            conf = sigmoid_f(ld_stream_f(q));   // yolo_loss.py:189,197
-            pass = conf > p.conf_thr;           // :201 (threshold already rounded to fp32)
-        }
-        const unsigned bal = __ballot_sync(kFullMask, pass);
-        if (lane == 0) s.wcount[parity * kWarps + warp] = __popc(bal);
-        __syncthreads();
-        int before = 0, all = 0;
+            const int HW = hd.HW;
+            const int a = fastdiv(local, HW, hd.magicHW);
+            const int pos = local - a * HW;
+            const float *q = hd.ptr + ((size_t)(b * p.A + a) * p.attrs) * HW + pos;
+            const float tc = __ldcs(q + 4 * (size_t)HW);
+            const float tx = __ldcs(q), ty = __ldcs(q + HW);
+            const float tw = __ldcs(q + 2 * (size_t)HW), th = __ldcs(q + 3 * (size_t)HW);
+            const float *qc = q + 5 * (size_t)HW;
+
+            // class max over the raw logits; sigmoid is only evaluated where it can
+            // change the (value, first-argmax) of torch.max(sigmoid(logits)) (:198)
+            float m1 = __ldcs(qc), m2 = -INFINITY;
+            int i1 = 0;
+            for (int c0 = 1; c0 < C; c0 += 8) {
+                float x[8];
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const int c = s.wcount[parity * kWarps + w];
-            before += (w < warp) ? c : 0;
-            all += c;
-        }
-        if (pass) {
-            const int k = base_k + before + __popc(bal & lanemask_lt());
-            s.cell[k] = (uint32_t)cid;
-            s.conf[k] = conf;
-        }
-        base_k += all;
-        // wcount is double-buffered by chunk parity, so one barrier per chunk suffices
-    }
-    return base_k;
-}
-
-// ---------------------------------------------------------------------------
-// A2: decode the surviving candidates.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, int b, int K, bool want_hist) {
-    const int cells0 = p.head[0].cells;
-    const int C = p.C;
-    for (int k = threadIdx.x; k < K; k += kThreads) {
-        const int cid = (int)s.cell[k];
-        const bool h1 = cid >= cells0;
-        const HeadDesc &hd = h1 ? p.head[1] : p.head[0];
-        const int local = h1 ? cid - cells0 : cid;
-        const int a = (int)(((float)local + 0.5f) * hd.invHW);
-        const int pos = local - a * hd.HW;
-        const int j = (int)(((float)pos + 0.5f) * hd.invW);
-        const int i = pos - j * hd.W;
-        const int HW = hd.HW;
-        const float *q = hd.ptr + ((size_t)(b * p.A + a) * p.attrs) * HW + pos;
-        const float tx = ld_stream_f(q), ty = ld_stream_f(q + HW);
-        const float tw = ld_stream_f(q + 2 * HW), th = ld_stream_f(q + 3 * HW);
-        const float *qc = q + 5 * (size_t)HW;
-
-        // class max over the raw logits; sigmoid is only evaluated where it can
-        // change the (value, first-argmax) of torch.max(sigmoid(logits)) (:198)
-        float m1 = ld_stream_f(qc), m2 = -INFINITY;
-        int i1 = 0;
-        int c = 1;
-        for (; c + 4 <= C; c += 4) {
-            float x0 = ld_stream_f(qc + (size_t)(c + 0) * HW), x1 = ld_stream_f(qc + (size_t)(c + 1) * HW);
-            float x2 = ld_stream_f(qc + (size_t)(c + 2) * HW), x3 = ld_stream_f(qc + (size_t)(c + 3) * HW);
-            if (x0 > m1) { m2 = m1; m1 = x0; i1 = c; } else m2 = fmaxf(m2, x0);
-            if (x1 > m1) { m2 = m1; m1 = x1; i1 = c + 1; } else m2 = fmaxf(m2, x1);
-            if (x2 > m1) { m2 = m1; m1 = x2; i1 = c + 2; } else m2 = fmaxf(m2, x2);
-            if (x3 > m1) { m2 = m1; m1 = x3; i1 = c + 3; } else m2 = fmaxf(m2, x3);
-        }
-        for (; c < C; ++c) {
-            float x0 = ld_stream_f(qc + (size_t)c * HW);
-            if (x0 > m1) { m2 = m1; m1 = x0; i1 = c; } else m2 = fmaxf(m2, x0);
-        }
-        const float e1 = expf(-m1);
-        float best = __fdiv_rn(1.0f, __fadd_rn(1.0f, e1));  // sigmoid(m1)
-        int bi = i1;
-        // d/dt ln(sigmoid(t)) = 1 - sigmoid(t) >= e1*best on (-inf, m1], so any logit
-        // below m1 - 2^-19/(e1*best) has a sigmoid smaller by > 2^-19 relative (>10x
-        // the evaluation error) and cannot win or tie.  Everything inside the window
-        // is evaluated exactly like the reference (sigmoid first, then first max).
-        const float win = __fdiv_rn(1.9073486e-06f, __fmul_rn(e1, best));
-        if (C > 1 && !(m2 < __fsub_rn(m1, win))) {
-            const float lo = __fsub_rn(m1, win);
-            best = -1.0f;
-            bi = 0;
-            for (int cc = 0; cc < C; ++cc) {
-                const float x = __ldg(qc + (size_t)cc * HW);
-                if (!(x < lo)) {
-                    const float sg = sigmoid_f(x);
-                    if (sg > best) { best = sg; bi = cc; }
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + u;
+                    x[u] = (c < C) ? __ldcs(qc + (size_t)c * HW) : -INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (x[u] > m1) { m2 = m1; m1 = x[u]; i1 = c0 + u; } else m2 = fmaxf(m2, x[u]);
                 }
             }
-            if (best < 0.0f) { best = sigmoid_f(m1); bi = i1; }  // only NaN logits in the window
+            const float conf = sigmoid_f(tc);   // yolo_loss.py:189,197
+            pass = conf > p.conf_thr;           // :201 (threshold already rounded to fp32)
+            if (pass) {
+                const float e1 = expf(-m1);
+                float best = __fdiv_rn(1.0f, __fadd_rn(1.0f, e1));  // sigmoid(m1)
+                int bi = i1;
+                // d/dt ln(sigmoid(t)) = 1 - sigmoid(t) >= e1*best on (-inf, m1], so any logit
+                // below m1 - 2^-19/(e1*best) has a sigmoid smaller by > 2^-19 relative (>10x
+                // the evaluation error) and cannot win or tie.  Everything inside the window
+                // is evaluated exactly like the reference (sigmoid first, then first max).
+                const float win = __fdiv_rn(1.9073486e-06f, __fmul_rn(e1, best));
+                if (C > 1 && !(m2 < __fsub_rn(m1, win))) {
+                    const float lo = __fsub_rn(m1, win);
+                    best = -1.0f;
+                    bi = 0;
+                    for (int cc = 0; cc < C; ++cc) {
+                        const float x = __ldg(qc + (size_t)cc * HW);
+                        if (!(x < lo)) {
+                            const float sg = sigmoid_f(x);
+                            if (sg > best) { best = sg; bi = cc; }
+                        }
+                    }
+                    if (best < 0.0f) { best = sigmoid_f(m1); bi = i1; }  // only NaN logits in the window
+                }
+                const int j = fastdiv(pos, hd.W, hd.magicW);
+                const int i = pos - j * hd.W;
+                const float sx = sigmoid_f(tx), sy = sigmoid_f(ty);          // :187
+                const float ew = expf(tw), eh = expf(th);                    // :188
+                const float cx = __fdiv_rn(__fadd_rn(sx, (float)i), hd.fW);  // :194
+                const float cy = __fdiv_rn(__fadd_rn(sy, (float)j), hd.fH);
+                const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
+                const float bh = __fmul_rn(eh, hd.ah[a]);
+                Rec r;
+                r.box.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                // :244
+                r.box.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                // :245
+                r.box.z = __fadd_rn(bw, r.box.x);                            // :246
+                r.box.w = __fadd_rn(bh, r.box.y);                            // :247
+                r.conf = conf;
+                r.score = best;
+                make_ta(r.box, p.iou, r.ta_hi, r.ta_lo);
+                float4 *dst = reinterpret_cast<float4 *>(&s.rec[cid]);
+                dst[0] = r.box;
+                dst[1] = make_float4(r.conf, r.score, r.ta_hi, r.ta_lo);
+                uint32_t idx = 0;
+                if (HIST) idx = (uint32_t)atomicAdd(&s.cnt[bi], 1);
+                s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+            }
         }
-
-        const float sx = sigmoid_f(tx), sy = sigmoid_f(ty);          // :187
-        const float ew = expf(tw), eh = expf(th);                    // :188
-        const float cx = __fdiv_rn(__fadd_rn(sx, (float)i), hd.fW);  // :194
-        const float cy = __fdiv_rn(__fadd_rn(sy, (float)j), hd.fH);
-        const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
-        const float bh = __fmul_rn(eh, hd.ah[a]);
-        float4 bx;
-        bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244
-        bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
-        bx.z = __fadd_rn(bw, bx.x);                                  // :246
-        bx.w = __fadd_rn(bh, bx.y);                                  // :247
-        s.box[k] = bx;
-        s.cscore[k] = best;
-        s.cls[k] = (uint16_t)bi;
-        if (want_hist) atomicAdd(&s.hist[bi], 1);
+        const unsigned bal = __ballot_sync(kFullMask, pass);
+        if (lane == 0 && cid < K) s.passbits[cid >> 5] = bal;
     }
 }
 
 // ---------------------------------------------------------------------------
-// MODE_NMS: load already-decoded rows (two heads, box.py:17) into the same staging
+// MODE_NMS: load already-decoded rows (two heads, box.py:17) into the records
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int phase_load_rows(const DNParams &p, const Smem &s, int b) {
-    const int K0 = p.cand_count[0][b];
-    const int K1 = p.cand[1] ? p.cand_count[1][b] : 0;
-    const int K = K0 + K1;
+template <int THREADS>
+__device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s, int b) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int K0 = min(p.cand_count[0][b], p.cand_stride[0]);
+    const int K1 = p.cand[1] ? min(p.cand_count[1][b], p.cand_stride[1]) : 0;
+    const int Kb = K0 + K1;
     const float *r0 = p.cand[0] + (size_t)b * p.cand_stride[0] * 7;
     const float *r1 = p.cand[1] ? p.cand[1] + (size_t)b * p.cand_stride[1] * 7 : nullptr;
-    float *boxf = reinterpret_cast<float *>(s.box);
-    for (int f = threadIdx.x; f < 7 * K; f += kThreads) {
-        const int row = f / 7, col = f - 7 * row;
-        const float v = (row < K0) ? __ldg(r0 + f) : __ldg(r1 + (f - 7 * K0));
-        if (col < 4) boxf[4 * row + col] = v;
-        else if (col == 4) s.conf[row] = v;
-        else if (col == 5) s.cscore[row] = v;
-        else {
+    for (int base = 0; base < p.K; base += THREADS) {
+        const int row = base + tid;
+        bool ok = false;
+        if (row < Kb) {
+            const float *src = (row < K0) ? r0 + (size_t)row * 7 : r1 + (size_t)(row - K0) * 7;
+            Rec r;
+            r.box = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+            r.conf = __ldg(src + 4);
+            r.score = __ldg(src + 5);
+            const float v = __ldg(src + 6);
             const int c = (int)v;  // rows whose class column is not an integer in [0,C) match no `== i` (box.py:21)
-            const bool ok = (v == (float)c) && c >= 0 && c < p.C;
-            s.cls[row] = ok ? (uint16_t)c : kNoClass;
-            s.cell[row] = (uint32_t)row;
-            if (ok) atomicAdd(&s.hist[c], 1);
+            ok = (v == (float)c) && c >= 0 && c < p.C;
+            if (ok) {
+                make_ta(r.box, p.iou, r.ta_hi, r.ta_lo);
+                float4 *dst = reinterpret_cast<float4 *>(&s.rec[row]);
+                dst[0] = r.box;
+                dst[1] = make_float4(r.conf, r.score, r.ta_hi, r.ta_lo);
+                const uint32_t idx = (uint32_t)atomicAdd(&s.cnt[c], 1);
+                s.clsidx[row] = ((uint32_t)c << 16) | idx;
+            }
         }
+        const unsigned bal = __ballot_sync(kFullMask, ok);
+        if (lane == 0 && row < p.K) s.passbits[row >> 5] = bal;
     }
-    return K;
 }
 
 // ---------------------------------------------------------------------------
-// B: exclusive scan of hist[0..C) -> start[0..C]; hist is zeroed (reused as the
-// scatter cursor).  Executed by warp 0.
+// P2 (warp 0): class segments, kept-bitmap tiles, and the round table
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void warp_scan_classes(int *cnt, int *start, int C, bool zero_cnt) {
+__device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s) {
     const int lane = threadIdx.x & 31;
-    int carry = 0;
+    const int C = p.C;
+    int carryS = 0, carryT = 0, words = 0;
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
-        const int v = (c < C) ? cnt[c] : 0;
-        const int inc = warp_inclusive_scan(v, lane);
+        const int n = (c < C) ? s.cnt[c] : 0;
+        const int T = (n + 31) >> 5;
+        const int incS = warp_inclusive_scan(n, lane);
+        const int incT = warp_inclusive_scan(T, lane);
         if (c < C) {
-            start[c] = carry + inc - v;
-            if (zero_cnt) cnt[c] = 0;
+            s.start[c] = carryS + incS - n;
+            s.ktile[c] = carryT + incT - T;
         }
-        carry += __shfl_sync(kFullMask, inc, 31);
+        carryS += __shfl_sync(kFullMask, incS, 31);
+        carryT += __shfl_sync(kFullMask, incT, 31);
+        words += 32 * tri(T);
     }
-    if (lane == 0) start[C] = carry;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) words += __shfl_xor_sync(kFullMask, words, o);
+    if (lane == 0) {
+        s.start[C] = carryS;
+        s.ktile[C] = carryT;
+        s.misc[M_KV] = carryS;
+        const int cap = p.mask_cap_words;
+        if (words <= cap) {
+            s.rounds[0] = make_uint2((uint32_t)C << 16, 0xffffu << 16);
+            s.misc[M_NROUNDS] = 1;
+        } else {
+            // rare: groups of whole classes, or column-tile chunks of one huge class
+            int r = 0, c = 0;
+            while (c < C) {
+                const int T = (s.cnt[c] + 31) >> 5;
+                if (32 * tri(T) > cap) {
+                    int t0 = 0;
+                    while (t0 < T) {
+                        int t1 = t0, acc = 0;
+                        while (t1 < T && acc + 32 * (t1 + 1) <= cap) { acc += 32 * (t1 + 1); ++t1; }
+                        if (t1 == t0) ++t1;  // cannot happen: host guarantees cap >= Kp >= 32*T
+                        s.rounds[r++] = make_uint2((uint32_t)c | ((uint32_t)(c + 1) << 16), (uint32_t)t0 | ((uint32_t)t1 << 16));
+                        t0 = t1;
+                    }
+                    ++c;
+                } else {
+                    const int c_lo = c;
+                    int acc = 0;
+                    while (c < C) {
+                        const int w = 32 * tri((s.cnt[c] + 31) >> 5);
+                        if (acc + w > cap) break;
+                        acc += w;
+                        ++c;
+                    }
+                    s.rounds[r++] = make_uint2((uint32_t)c_lo | ((uint32_t)c << 16), 0xffffu << 16);
+                }
+            }
+            s.misc[M_NROUNDS] = r;
+        }
+    }
+    __syncwarp();
+}
+
+// per round (warp 0): pair-slot and mask offsets of the round's classes
+__device__ __forceinline__ void warp_round_prefix(const Smem &s, int r) {
+    const int lane = threadIdx.x & 31;
+    const uint2 rd = s.rounds[r];
+    const int c_lo = rd.x & 0xffff, c_hi = rd.x >> 16, t0 = rd.y & 0xffff, t1 = rd.y >> 16;
+    int carryS = 0, carryM = 0;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        const int c = c0 + lane;
+        int slots = 0, words = 0;
+        if (c < c_hi) {
+            const int n = s.cnt[c];
+            const int T = (n + 31) >> 5;
+            const int te = min(T, t1);
+            const int j0 = 32 * t0, j1 = min(n, 32 * te);
+            if (j1 > j0) {
+                slots = (j1 - j0 + 1) >> 1;
+                words = 32 * (tri(te) - tri(t0));
+            }
+        }
+        const int incS = warp_inclusive_scan(slots, lane);
+        const int incM = warp_inclusive_scan(words, lane);
+        if (c < c_hi) {
+            s.slot[c] = carryS + incS - slots;
+            s.maskbase[c] = carryM + incM - words;
+        }
+        carryS += __shfl_sync(kFullMask, incS, 31);
+        carryM += __shfl_sync(kFullMask, incM, 31);
+    }
+    if (lane == 0) {
+        s.slot[c_hi] = carryS;
+        s.misc[M_CLO] = c_lo; s.misc[M_CHI] = c_hi; s.misc[M_T0] = t0; s.misc[M_T1] = t1;
+        s.misc[M_SLOTS] = carryS;
+        s.misc[M_CTR] = 0;
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
-// C: class-segmented stable sort by score (descending)
+// P3/P4: class-segmented stable sort by score (descending)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s, int K) {
-    for (int k = threadIdx.x; k < K; k += kThreads) {
-        const uint16_t c = s.cls[k];
-        if (c == kNoClass) continue;
-        const float sc = __fmul_rn(s.cscore[k], s.conf[k]);  // box.py:27 scores = col5*col4
+template <int THREADS>
+__device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s) {
+    for (int cid = threadIdx.x; cid < p.K; cid += THREADS) {
+        if (!((s.passbits[cid >> 5] >> (cid & 31)) & 1u)) continue;
+        const uint32_t ci = s.clsidx[cid];
+        const Rec &r = s.rec[cid];
+        const float sc = __fmul_rn(r.score, r.conf);  // box.py:27 scores = col5*col4
         const unsigned long long key =
-            ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)k);
-        const int slot = s.start[c] + atomicAdd(&s.hist[c], 1);
-        s.key[slot] = key;
+            ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)cid);
+        s.key[s.start[ci >> 16] + (int)(ci & 0xffffu)] = key;
     }
 }
 
-__device__ __forceinline__ void phase_rank_sort(const Smem &s, int Kv) {
-    for (int t = threadIdx.x; t < Kv; t += kThreads) {
+template <int THREADS>
+__device__ __forceinline__ void phase_rank_sort(const Smem &s, int Kv, int sord_len) {
+    for (int t = threadIdx.x; t < sord_len; t += THREADS) {
+        if (t >= Kv) {
+            s.sord[t] = s.rec_saddr;  // padding: any valid record
+            continue;
+        }
         const unsigned long long key = s.key[t];
-        const uint32_t k = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-        const int c = s.cls[k];
+        const uint32_t cid = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+        const int c = (int)(s.clsidx[cid] >> 16);
         const int st = s.start[c], en = s.start[c + 1];
         int rank = 0;
-        for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
-        const int pos = st + rank;
-        const float4 bx = s.box[k];
-        s.order[pos] = (uint16_t)k;
-        s.sbox[pos] = bx;
-        s.sarea[pos] = box_area(bx);
-        s.alive[pos] = 1;
+        int u = st;
+        for (; u + 4 <= en; u += 4) {
+            const unsigned long long k0 = s.key[u], k1 = s.key[u + 1], k2 = s.key[u + 2], k3 = s.key[u + 3];
+            rank += (k0 > key) + (k1 > key) + (k2 > key) + (k3 > key);
+        }
+        for (; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
+        s.sord[st + rank] = s.rec_saddr + 32u * cid;
     }
 }
 
 // ---------------------------------------------------------------------------
-// D: greedy NMS of one class segment by one warp, 32x32 bitmask tiles.
-// Returns the number of kept boxes (warp-uniform).
+// P5: pair masks
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int warp_nms_class(const Smem &s, int st, int n, const IouThr &thr) {
+// exact torchvision decision for one pair (row record address, column box)
+__device__ __forceinline__ bool pair_exact(uint32_t row_saddr, const float4 &cb, const IouThr &thr) {
+    const float4 rb = lds_box(row_saddr);
+    return nms_suppress_exact(rb, box_area(rb), cb, box_area(cb), thr);
+}
+
+// one 16-row group for up to two columns; returns 16 result bits per column
+template <bool DO_A>
+__device__ __forceinline__ void pair_group16(const uint32_t *ord, const float4 &ca, float ca_hi, float ca_lo,
+                                             const float4 &cb, float cb_hi, float cb_lo, const IouThr &thr,
+                                             uint32_t &bitsA, uint32_t &bitsB) {
+    float aS = 0.f, aM = 0.f, bS = 0.f, bM = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        float4 R;
+        float2 T;
+        lds_rec(ord[k], R, T);
+        const float wk = (float)(1u << k);
+        {
+            const float w = fmaxf(__fsub_rn(fminf(R.z, cb.z), fmaxf(R.x, cb.x)), 0.0f);
+            const float h = __fsub_rn(fminf(R.w, cb.w), fmaxf(R.y, cb.y));
+            const float inter = __fmul_rn(w, h);
+            const float pS = (inter > __fadd_rn(T.x, cb_hi)) ? 1.0f : 0.0f;
+            const float pM = (inter > __fadd_rn(T.y, cb_lo)) ? 1.0f : 0.0f;
+            bS = __fmaf_rn(pS, wk, bS);
+            bM = __fmaf_rn(pM, wk, bM);
+        }
+        if (DO_A) {
+            const float w = fmaxf(__fsub_rn(fminf(R.z, ca.z), fmaxf(R.x, ca.x)), 0.0f);
+            const float h = __fsub_rn(fminf(R.w, ca.w), fmaxf(R.y, ca.y));
+            const float inter = __fmul_rn(w, h);
+            const float pS = (inter > __fadd_rn(T.x, ca_hi)) ? 1.0f : 0.0f;
+            const float pM = (inter > __fadd_rn(T.y, ca_lo)) ? 1.0f : 0.0f;
+            aS = __fmaf_rn(pS, wk, aS);
+            aM = __fmaf_rn(pM, wk, aM);
+        }
+    }
+    uint32_t uS = __float2uint_rn(bS), uM = __float2uint_rn(bM);
+    if (uS != uM) {  // pairs inside the guard band (or flagged boxes): exact arithmetic decides
+        for (uint32_t amb = uS ^ uM; amb;) {
+            const int k = __ffs(amb) - 1;
+            amb &= amb - 1u;
+            if (pair_exact(ord[k], cb, thr)) uS |= 1u << k; else uS &= ~(1u << k);
+        }
+    }
+    bitsB = uS;
+    if (DO_A) {
+        uS = __float2uint_rn(aS);
+        uM = __float2uint_rn(aM);
+        if (uS != uM) {
+            for (uint32_t amb = uS ^ uM; amb;) {
+                const int k = __ffs(amb) - 1;
+                amb &= amb - 1u;
+                if (pair_exact(ord[k], ca, thr)) uS |= 1u << k; else uS &= ~(1u << k);
+            }
+        }
+        bitsA = uS;
+    }
+}
+
+__device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
     const int lane = threadIdx.x & 31;
-    const int ntiles = (n + 31) >> 5;
-    int kept_total = 0;
-    for (int rt = 0; rt < ntiles; ++rt) {
-        const int r = rt * 32 + lane;
-        const bool valid = r < n;
-        float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-        float marea = 0.f;
-        bool alive_me = false;
-        if (valid) {
-            alive_me = s.alive[st + r] != 0;
-            me = s.sbox[st + r];
-            marea = s.sarea[st + r];
+    const int c_lo = s.misc[M_CLO], c_hi = s.misc[M_CHI], t0 = s.misc[M_T0], t1 = s.misc[M_T1];
+    const int total = s.misc[M_SLOTS];
+    const int tri0 = tri(t0);
+    for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&s.misc[M_CTR], 1);
+        chunk = __shfl_sync(kFullMask, chunk, 0);
+        if (chunk * 32 >= total) break;
+        const int slot = chunk * 32 + lane;
+        const bool act = slot < total;
+        int lo = c_lo, hi = c_hi;  // largest c in [c_lo, c_hi) with slot[c] <= slot
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s.slot[mid] <= slot) lo = mid; else hi = mid;
         }
-        const unsigned alive_in = __ballot_sync(kFullMask, alive_me);
-        if (alive_in == 0u) continue;
-        // diagonal tile: bit i of colword = "row i (earlier, still alive) overlaps me"
-        unsigned colword = 0u;
-        const float4 *rowb = s.sbox + st + rt * 32;
-        const float *rowa = s.sarea + st + rt * 32;
-        // (the last alive row of the tile has no later column inside it)
-        for (unsigned rem = alive_in; rem & (rem - 1u);) {
-            const int i = __ffs(rem) - 1;
-            rem &= rem - 1u;
-            const float4 rb = rowb[i];
-            const float ra = rowa[i];
-            if (alive_me && lane > i && nms_suppress(rb, ra, me, marea, thr)) colword |= 1u << i;
+        const int c = lo;
+        const int n = s.cnt[c];
+        const int rowbase = s.start[c];
+        const int j0 = 32 * t0, j1 = min(n, 32 * min((n + 31) >> 5, t1));
+        const int h = slot - s.slot[c];
+        const int jA = j0 + h, jB = j1 - 1 - h;   // the short and the long column of this lane
+        const bool hasA = act && jA < jB;
+        const int tripA = hasA ? jA : 0, tripB = act ? jB : 0;  // rows 0..trip-1 precede the column
+        const uint32_t *ord = s.sord + rowbase;
+        float4 ca, cb;
+        float2 ta, tb;
+        lds_rec(ord[hasA ? jA : 0], ca, ta);
+        lds_rec(ord[act ? jB : 0], cb, tb);
+        const int maxA = __reduce_max_sync(kFullMask, tripA), maxB = __reduce_max_sync(kFullMask, tripB);
+        const int nwA = (maxA + 31) >> 5, nwB = (maxB + 31) >> 5;
+        const int ctA = jA >> 5, ctB = jB >> 5;
+        uint32_t *mA = s.mask + s.maskbase[c] + (tri(ctA) - tri0) * 32 + (jA & 31);
+        uint32_t *mB = s.mask + s.maskbase[c] + (tri(ctB) - tri0) * 32 + (jB & 31);
+        for (int w = 0; w < nwB; ++w) {
+            uint32_t a0 = 0, a1 = 0, b0, b1;
+            if (w < nwA) {
+                pair_group16<true>(ord + 32 * w, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a0, b0);
+                pair_group16<true>(ord + 32 * w + 16, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a1, b1);
+            } else {
+                pair_group16<false>(ord + 32 * w, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a0, b0);
+                pair_group16<false>(ord + 32 * w + 16, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a1, b1);
+            }
+            // rows >= the column index (own bit, later rows, other classes) are masked off
+            if (act && w <= ctB) {
+                uint32_t word = b0 | (b1 << 16);
+                if (w == ctB) word &= (1u << (jB & 31)) - 1u;
+                mB[w * 32] = word;
+            }
+            if (hasA && w <= ctA) {
+                uint32_t word = a0 | (a1 << 16);
+                if (w == ctA) word &= (1u << (jA & 31)) - 1u;
+                mA[w * 32] = word;
+            }
         }
-        // sweep: rows without any overlap bit are kept outright; the others are
-        // resolved in ascending order against the kept mask built so far
-        const unsigned nz = __ballot_sync(kFullMask, colword != 0u);
-        unsigned kept = alive_in & ~nz;
-        for (unsigned rem = nz; rem;) {
-            const int i = __ffs(rem) - 1;
-            rem &= rem - 1u;
-            const unsigned cw = __shfl_sync(kFullMask, colword, i);
-            if ((cw & kept) == 0u) kept |= 1u << i;
-        }
-        if (valid && alive_me && !((kept >> lane) & 1u)) s.alive[st + r] = 0;
-        kept_total += __popc(kept);
-        // apply this tile's kept rows to every later column tile
-        for (int ct = rt + 1; ct < ntiles; ++ct) {
-            const int j = ct * 32 + lane;
-            bool a = (j < n) && (s.alive[st + j] != 0);
-            if (!__any_sync(kFullMask, a)) continue;
-            float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
-            float ca = 0.f;
-            if (a) { cb = s.sbox[st + j]; ca = s.sarea[st + j]; }
-            const bool was = a;
-            for (unsigned rem = kept; rem;) {
+        // ceil(j/32) row words were computed; the diagonal word of a column with
+        // j % 32 == 0 holds no earlier row and may lie beyond the warp's loop
+        if (act && nwB <= ctB) mB[ctB * 32] = 0u;
+        if (hasA && nwB <= ctA) mA[ctA * 32] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// P6: sweep -- one warp per class, 32-column tiles in score order
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ void phase_sweep(const Smem &s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c_lo = s.misc[M_CLO], c_hi = s.misc[M_CHI], t0 = s.misc[M_T0], t1 = s.misc[M_T1];
+    const int tri0 = tri(t0);
+    for (int c = c_lo + warp; c < c_hi; c += THREADS / 32) {
+        const int n = s.cnt[c];
+        const int T = (n + 31) >> 5;
+        const int te = min(T, t1);
+        uint32_t *kept_w = s.keptbits + s.ktile[c];
+        const uint32_t *mbase = s.mask + s.maskbase[c];
+        for (int ct = t0; ct < te; ++ct) {
+            const int j = 32 * ct + lane;
+            const uint32_t *col = mbase + (tri(ct) - tri0) * 32 + lane;
+            uint32_t sup = 0u;
+            int rt = 0;
+            for (; rt + 4 <= ct; rt += 4) {
+                sup |= (col[rt * 32] & kept_w[rt]) | (col[(rt + 1) * 32] & kept_w[rt + 1]) |
+                       (col[(rt + 2) * 32] & kept_w[rt + 2]) | (col[(rt + 3) * 32] & kept_w[rt + 3]);
+            }
+            for (; rt < ct; ++rt) sup |= col[rt * 32] & kept_w[rt];
+            const bool alive = (j < n) && (sup == 0u);
+            const unsigned alive_mask = __ballot_sync(kFullMask, alive);
+            const uint32_t diag = alive ? (col[ct * 32] & alive_mask) : 0u;
+            const unsigned nz = __ballot_sync(kFullMask, diag != 0u);
+            unsigned kept = alive_mask & ~nz;
+            for (unsigned rem = nz; rem;) {
                 const int i = __ffs(rem) - 1;
                 rem &= rem - 1u;
-                const float4 rb = rowb[i];
-                const float ra = rowa[i];
-                if (a && nms_suppress(rb, ra, cb, ca, thr)) a = false;
+                const unsigned cw = __shfl_sync(kFullMask, diag, i);
+                if ((cw & kept) == 0u) kept |= 1u << i;
             }
-            if (was && !a) s.alive[st + j] = 0;
+            if (lane == 0) kept_w[ct] = kept;
+            __syncwarp();
         }
-        __syncwarp();
-    }
-    return kept_total;
-}
-
-// E1: per class, map kept sorted positions to output rows
-__device__ __forceinline__ void warp_emit_class(const Smem &s, int st, int n, int out_base) {
-    const int lane = threadIdx.x & 31;
-    int run = out_base;
-    for (int r0 = 0; r0 < n; r0 += 32) {
-        const int r = r0 + lane;
-        const bool a = (r < n) && (s.alive[st + r] != 0);
-        const unsigned bal = __ballot_sync(kFullMask, a);
-        if (a) s.outsrc[run + __popc(bal & lanemask_lt())] = s.order[st + r];
-        run += __popc(bal);
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) decode_nms_kernel(const DNParams p) {
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemLayout L = make_layout(p.Kmax, p.C, MODE);
-    const Smem s = carve(smem_raw, L);
+    const Smem s = carve(smem_raw, L, p.C, MODE);
     const int b = blockIdx.x;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int C = p.C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, K = p.K;
+    constexpr int kWarps = THREADS / 32;
 
     if (MODE != MODE_DECODE) {
-        for (int c = tid; c <= C; c += kThreads) { s.hist[c] = 0; s.kcount[c] = 0; }
+        for (int c = tid; c <= C; c += THREADS) s.cnt[c] = 0;
         __syncthreads();
     }
 
-    int K;
-    if (MODE == MODE_NMS) {
-        K = phase_load_rows(p, s, b);
-    } else {
-        K = phase_threshold_compact(p, s, b);
-        __syncthreads();
-        phase_decode(p, s, b, K, MODE == MODE_FUSED);
-    }
+    if (MODE == MODE_NMS) phase_load_rows<THREADS>(p, s, b);
+    else phase_decode<THREADS, MODE == MODE_FUSED>(p, s, b);
     __syncthreads();
+
+    const int nwords = (K + 31) >> 5;
 
     if (MODE == MODE_DECODE) {
         // YOLOLoss.get_pred_boxes output: rows in candidate order (:203)
-        float *o = p.out + (size_t)b * p.Kmax * 7;
-        const float *boxf = reinterpret_cast<const float *>(s.box);
-        for (int f = tid; f < 7 * K; f += kThreads) {
+        if (warp == 0) {
+            int carry = 0;
+            for (int w0 = 0; w0 < nwords; w0 += 32) {
+                const int w = w0 + lane;
+                const int v = (w < nwords) ? __popc(s.passbits[w]) : 0;
+                const int inc = warp_inclusive_scan(v, lane);
+                if (w < nwords) s.tilepref[w] = carry + inc - v;
+                carry += __shfl_sync(kFullMask, inc, 31);
+            }
+            if (lane == 0) s.misc[M_TOTAL] = carry;
+        }
+        __syncthreads();
+        for (int cid = tid; cid < K; cid += THREADS) {
+            const uint32_t bits = s.passbits[cid >> 5];
+            if ((bits >> (cid & 31)) & 1u) s.outsrc[s.tilepref[cid >> 5] + __popc(bits & ((1u << (cid & 31)) - 1u))] = (uint16_t)cid;
+        }
+        __syncthreads();
+        const int T = s.misc[M_TOTAL];
+        float *o = p.out + (size_t)b * K * 7;
+        const float *recf = reinterpret_cast<const float *>(s.rec);
+        for (int f = tid; f < 7 * T; f += THREADS) {
             const int row = f / 7, col = f - 7 * row;
-            float v;
-            if (col < 4) v = boxf[4 * row + col];
-            else if (col == 4) v = s.conf[row];
-            else if (col == 5) v = s.cscore[row];
-            else v = (float)s.cls[row];   // cls_idx.float() :199
-            o[f] = v;
+            const int cid = s.outsrc[row];
+            o[f] = (col < 6) ? recf[8 * cid + col] : (float)(s.clsidx[cid] >> 16);  // cls_idx.float() :199
         }
-        if (p.out_idx) {
-            const int cells0 = p.head[0].cells;
-            (void)cells0;
-            for (int k = tid; k < K; k += kThreads) p.out_idx[(size_t)b * p.Kmax + k] = (int)s.cell[k];
-        }
-        if (tid == 0) p.out_count[b] = K;
+        if (p.out_idx)
+            for (int r = tid; r < T; r += THREADS) p.out_idx[(size_t)b * K + r] = (int)s.outsrc[r];
+        if (tid == 0) p.out_count[b] = T;
         return;
     }
 
-    // B
-    if (warp == 0) warp_scan_classes(s.hist, s.start, C, true);
-    __syncthreads();
-    const int Kv = s.start[C];
-    // C
-    phase_scatter_keys(p, s, K);
-    __syncthreads();
-    phase_rank_sort(s, Kv);
-    __syncthreads();
-    // D
-    for (int c = warp; c < C; c += kWarps) {
-        const int st = s.start[c], n = s.start[c + 1] - st;
-        if (n == 0) continue;
-        const int kept = warp_nms_class(s, st, n, p.iou);
-        if ((tid & 31) == 0) s.kcount[c] = kept;
+    // P2
+    if (warp == 0) {
+        warp_class_scan(p, s);
+        warp_round_prefix(s, 0);
     }
     __syncthreads();
-    // E
-    if (warp == 0) warp_scan_classes(s.kcount, s.kstart, C, false);
+    const int Kv = s.misc[M_KV];
+    const int nrounds = s.misc[M_NROUNDS];
+    // P3, P4
+    phase_scatter_keys<THREADS>(p, s);
     __syncthreads();
-    const int T = s.kstart[C];
-    for (int c = warp; c < C; c += kWarps) {
-        const int st = s.start[c], n = s.start[c + 1] - st;
-        if (n == 0) continue;
-        warp_emit_class(s, st, n, s.kstart[c]);
+    phase_rank_sort<THREADS>(s, Kv, 2 * (int)align_up((uint32_t)K, 32) + 64);
+    __syncthreads();
+    // P5, P6
+    for (int r = 0;;) {
+        phase_pairs(p, s);
+        __syncthreads();
+        phase_sweep<THREADS>(s);
+        __syncthreads();
+        if (++r >= nrounds) break;
+        if (warp == 0) warp_round_prefix(s, r);
+        __syncthreads();
+    }
+    // P7: exclusive scan of the kept bitmap (tile granularity)
+    const int ntiles = s.ktile[C];
+    if (warp == 0) {
+        int carry = 0;
+        for (int g0 = 0; g0 < ntiles; g0 += 32) {
+            const int g = g0 + lane;
+            const int v = (g < ntiles) ? __popc(s.keptbits[g]) : 0;
+            const int inc = warp_inclusive_scan(v, lane);
+            if (g < ntiles) s.tilepref[g] = carry + inc - v;
+            carry += __shfl_sync(kFullMask, inc, 31);
+        }
+        if (lane == 0) s.misc[M_TOTAL] = carry;
     }
     __syncthreads();
-    {
-        float *o = p.out + (size_t)b * p.Kmax * 7;
-        const float *boxf = reinterpret_cast<const float *>(s.box);
-        for (int f = tid; f < 7 * T; f += kThreads) {
-            const int row = f / 7, col = f - 7 * row;
-            const int k = s.outsrc[row];
-            float v;
-            if (MODE == MODE_NMS) {
-                // gather the caller's own row (pred_this_cls[index], box.py:29) bit-for-bit
-                const int K0 = p.cand_count[0][b];
-                v = (k < K0) ? __ldg(p.cand[0] + ((size_t)b * p.cand_stride[0] + k) * 7 + col)
-                             : __ldg(p.cand[1] + ((size_t)b * p.cand_stride[1] + (k - K0)) * 7 + col);
-            } else {
-                if (col < 4) v = boxf[4 * k + col];
-                else if (col == 4) v = s.conf[k];
-                else if (col == 5) v = s.cscore[k];
-                else v = (float)s.cls[k];
+    // P8: output row -> cell id (the mask buffer is dead now; outsrc aliases it)
+    for (int c = warp; c < C; c += kWarps) {
+        const int n = s.cnt[c];
+        const int kt = s.ktile[c], st = s.start[c];
+        for (int ct = 0; 32 * ct < n; ++ct) {
+            const uint32_t word = s.keptbits[kt + ct];
+            if ((word >> lane) & 1u) {
+                const uint32_t cid = (s.sord[st + 32 * ct + lane] - s.rec_saddr) >> 5;
+                s.outsrc[s.tilepref[kt + ct] + __popc(word & lanemask_lt())] = (uint16_t)cid;
             }
-            o[f] = v;
+        }
+    }
+    __syncthreads();
+    // P9: flat coalesced store
+    {
+        const int T = s.misc[M_TOTAL];
+        float *o = p.out + (size_t)b * K * 7;
+        const float *recf = reinterpret_cast<const float *>(s.rec);
+        if (MODE == MODE_NMS) {
+            // gather the caller's own row (pred_this_cls[index], box.py:29) bit-for-bit
+            const int K0 = min(p.cand_count[0][b], p.cand_stride[0]);
+            const float *r0 = p.cand[0] + (size_t)b * p.cand_stride[0] * 7;
+            const float *r1 = p.cand[1] ? p.cand[1] + (size_t)b * p.cand_stride[1] * 7 : nullptr;
+            for (int f = tid; f < 7 * T; f += THREADS) {
+                const int row = f / 7, col = f - 7 * row;
+                const int k = s.outsrc[row];
+                o[f] = (k < K0) ? __ldg(r0 + (size_t)k * 7 + col) : __ldg(r1 + (size_t)(k - K0) * 7 + col);
+            }
+        } else {
+            for (int f = tid; f < 7 * T; f += THREADS) {
+                const int row = f / 7, col = f - 7 * row;
+                const int cid = s.outsrc[row];
+                o[f] = (col < 6) ? recf[8 * cid + col] : (float)(s.clsidx[cid] >> 16);
+            }
         }
         if (p.out_idx)
-            for (int r = tid; r < T; r += kThreads) p.out_idx[(size_t)b * p.Kmax + r] = (int)s.cell[s.outsrc[r]];
+            for (int r = tid; r < T; r += THREADS) p.out_idx[(size_t)b * K + r] = (int)s.outsrc[r];
         if (tid == 0) p.out_count[b] = T;
     }
 }
