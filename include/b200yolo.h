@@ -52,6 +52,11 @@ const char *b200yolo_last_error(void);
  * streams); bench.py reports the delta over the timed region as gpu_launches. */
 unsigned long long b200yolo_launch_count(void);
 
+/* Profiling aid (profiles/phase_times.py): when set to a device buffer of
+ * [N][16] uint64, the fused / NMS kernels record %globaltimer (ns) at their phase
+ * boundaries for every image.  NULL (the default) disables it. */
+void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
+
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that
  * the fused / NMS kernels can stage in one CTA's shared memory on `device`. */
 int b200yolo_max_cells(int device);

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -19,6 +20,7 @@ using namespace b200yolo;
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<unsigned long long *> g_dbg{nullptr};  // profiling aid, see b200yolo_debug_phase_stamps
 std::atomic<unsigned long long> g_launches{0};
 
 int fail(int code, const char *fmt, ...) {
@@ -63,6 +65,8 @@ void fill_head(HeadDesc &h, const float *ptr, int A, int H, int W, const float *
     h.magicW = div_magic(W);
     h.fW = (float)W;
     h.fH = (float)H;
+    h.rW = 1.0f / (float)W;
+    h.rH = 1.0f / (float)H;
     for (int a = 0; a < kMaxAnchors; ++a) {
         h.aw[a] = (a < A) ? anchor_wh[2 * a] : 0.f;
         h.ah[a] = (a < A) ? anchor_wh[2 * a + 1] : 0.f;
@@ -120,6 +124,12 @@ int launch_dn(DNParams &p, cudaStream_t st) {
     const int budget = half ? kSmemHalfSM : lim;
     const SmemLayout L = make_layout(p.K, p.C, MODE, (uint32_t)(budget - (int)base.total));
     p.mask_cap_words = (int)L.mask_words;
+    p.B = pick_buckets(p.C);
+    p.dbg = g_dbg.load();
+    {
+        static const int env_flags = [] { const char *e = getenv("B200YOLO_FLAGS"); return e ? atoi(e) : 0; }();
+        p.flags = env_flags;
+    }
     if (half) return launch_dn_t<MODE, 512>(p, L, dev, st);
     return launch_dn_t<MODE, 1024>(p, L, dev, st);
 }
@@ -131,6 +141,8 @@ extern "C" {
 int b200yolo_version(void) { return B200YOLO_VERSION; }
 const char *b200yolo_last_error(void) { return g_err; }
 unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
+
+void b200yolo_debug_phase_stamps(unsigned long long *dev_buf) { g_dbg.store(dev_buf); }
 
 int b200yolo_max_cells(int device) {
     const int lim = smem_optin(device);

@@ -16,6 +16,13 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // IEEE (round-to-nearest) divide.
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
+// Inference decode (YOLOLoss.get_pred_boxes) uses the SFU forms: ex2.approx + rcp.approx,
+// <= ~4 ulp + |x|*6e-8 relative, well inside the 1e-5 contract on decoded floats; it is
+// ~20 instructions cheaper per transcendental than the IEEE forms above, and the decode
+// phase is issue-bound.  The training path (target_loss.cuh) keeps the IEEE forms.
+__device__ __forceinline__ float exp_fast(float x) { return __expf(x); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x))); }
+
 __device__ __forceinline__ float ldg_f(const float *p) { return __ldg(p); }
 
 // streaming load: head tensors are read exactly once

@@ -49,7 +49,7 @@ struct HeadDesc {
     const float *ptr;
     int H, W, HW, cells;         // cells = A*H*W
     uint32_t magicHW, magicW;    // ceil(2^32/d) for exact n/d, n < 65536 (0: d == 1)
-    float fW, fH;
+    float fW, fH, rW, rH;        // grid size and its fp32 reciprocal
     float aw[kMaxAnchors], ah[kMaxAnchors];  // anchors / img_size (yolo_loss.py:214)
 };
 
@@ -59,6 +59,9 @@ struct DNParams {
     int N, A, C, attrs;
     int K;               // candidate slots per image = row stride of out / out_idx
     int mask_cap_words;  // capacity of the pair-mask buffer (32-bit words)
+    int B;               // score buckets per class of the counting sort (power of two)
+    int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch
+    unsigned long long *dbg;  // optional [N][16] phase time stamps (ns, globaltimer), NULL in production
     float conf_thr;
     IouThr iou;
     float *out;
@@ -80,7 +83,7 @@ struct __align__(16) Rec {
 };
 
 struct SmemLayout {
-    uint32_t rec, clsidx, sord, key, passbits, keptbits, tilepref, cls, rounds, misc, total;
+    uint32_t rec, clsidx, sord, key, passbits, keptbits, tilepref, cls, cntb, rounds, misc, total;
     uint32_t mask_words;  // words available at `key` (keys are dead once ranks are known)
 };
 
@@ -89,7 +92,14 @@ __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v
 // per-class int arrays, each (C+1) long
 enum { CA_CNT = 0, CA_START, CA_KTILE, CA_SLOT, CA_MASK, CA_NUM };
 // misc ints
-enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_SLOTS, M_CTR, M_TOTAL, M_KV, M_NUM = 16 };
+enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_SLOTS, M_CTR, M_TOTAL, M_KV, M_WSUM = 16, M_NUM = 16 + 32 };
+
+// score buckets per class: C*B counters, at most 2048 (8 KB)
+__host__ __device__ inline int pick_buckets(int C) {
+    int B = 64;
+    while (B > 1 && C * B > 2048) B >>= 1;
+    return B;
+}
 
 __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32_t extra_mask_bytes) {
     SmemLayout L;
@@ -108,6 +118,7 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32
     L.tilepref = o; o += 4 * (tiles + 1);
     o = align_up(o, 16);
     L.cls = o; o += nms ? 4 * Cp * CA_NUM : 0;
+    L.cntb = o; o += nms ? 4 * align_up((uint32_t)(C * pick_buckets(C)) + 1, 4) : 0;
     L.rounds = o; o += nms ? 8 * (tiles + (uint32_t)C + 2) : 0;
     L.misc = o; o += 4 * M_NUM;
     L.total = align_up(o, 16);
@@ -123,6 +134,7 @@ struct Smem {
     uint32_t *mask;     // aliases key
     uint32_t *passbits, *keptbits, *tilepref;
     int *cnt, *start, *ktile, *slot, *maskbase;
+    int *cntb;          // [C*B+1] per (class, score bucket): arrival counter, then exclusive prefix
     uint2 *rounds;      // x = c_lo | c_hi << 16, y = t0 | t1 << 16
     int *misc;
     uint32_t rec_saddr;
@@ -147,6 +159,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, 
     s.ktile = ca + CA_KTILE * Cp;
     s.slot = ca + CA_SLOT * Cp;
     s.maskbase = ca + CA_MASK * Cp;
+    s.cntb = reinterpret_cast<int *>(base + L.cntb);
     s.rounds = reinterpret_cast<uint2 *>(base + L.rounds);
     s.misc = reinterpret_cast<int *>(base + L.misc);
     s.rec_saddr = (uint32_t)__cvta_generic_to_shared(s.rec);
@@ -159,6 +172,14 @@ __device__ __forceinline__ int fastdiv(int n, int d, uint32_t magic) {
 }
 
 __device__ __forceinline__ int tri(int x) { return (x * (x + 1)) >> 1; }
+
+__device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[(size_t)b * 16 + k] = t;
+    }
+}
 
 __device__ __forceinline__ void lds_rec(uint32_t saddr, float4 &box, float2 &ta) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -181,96 +202,167 @@ __device__ __forceinline__ void make_ta(const float4 &b, const IouThr &t, float 
     lo = ok ? __fmul_rn(a, t.t_lo) : -INFINITY;
 }
 
+// score bucket of the counting sort: monotone non-increasing in the sort key
+// (NaN scores sort first, like torch's descending sort)
+__device__ __forceinline__ int score_bucket(float sc, int B) {
+    const float top = (float)(B - 1);
+    const float f = (sc != sc) ? top : fminf(fmaxf(__fmul_rn(sc, (float)B), 0.0f), top);
+    return B - 1 - (int)f;
+}
+
+// Ask the L2 to fetch [ptr, ptr+bytes) from HBM (cp.async.bulk.prefetch: the copy engine
+// streams it, no registers, no issue slots).  Only the 16-byte-aligned interior is
+// requested; the few bytes around it arrive with the ordinary loads.
+__device__ __forceinline__ void l2_prefetch_span(const void *ptr, size_t bytes) {
+    const uintptr_t lo = ((uintptr_t)ptr + 15) & ~(uintptr_t)15;
+    const uintptr_t hi = ((uintptr_t)ptr + bytes) & ~(uintptr_t)15;
+    if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+}
+
+// class score of a cell whose top logits are closer than the sigmoid's evaluation
+// error: evaluate like the reference (sigmoid first, then first max, yolo_loss.py:198)
+__device__ __noinline__ float class_tie_break(const float *qc, int HW, int C, float lo, float m1, int i1, int *bi_out) {
+    float best = -1.0f;
+    int bi = 0;
+    for (int cc = 0; cc < C; ++cc) {
+        const float x = __ldg(qc + (size_t)cc * HW);
+        if (!(x < lo)) {
+            const float sg = sigmoid_fast(x);
+            if (sg > best) { best = sg; bi = cc; }
+        }
+    }
+    if (best < 0.0f) { best = sigmoid_fast(m1); bi = i1; }  // only NaN logits in the window
+    *bi_out = bi;
+    return best;
+}
+
+constexpr int kClsChunk = 24;  // class planes loaded per batch (all in flight before the first use)
+
 // ---------------------------------------------------------------------------
-// P1: decode every cell of the image (both heads), single pass
+// P1: decode every cell of the image, single pass over the heads.  All 5+C plane
+// loads of a cell are issued before the first use (C <= 24; larger C: batches of 24).
 // ---------------------------------------------------------------------------
-template <int THREADS, bool HIST>
+template <int THREADS, int MODE>
 __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, int b) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int K = p.K, C = p.C;
-    const int cells0 = p.head[0].cells;
-    for (int base = 0; base < K; base += THREADS) {
-        const int cid = base + tid;
-        bool pass = false;
-        if (cid < K) {
-            const bool h1 = cid >= cells0;
-            const HeadDesc &hd = h1 ? p.head[1] : p.head[0];
-            const int local = h1 ? cid - cells0 : cid;
-            const int HW = hd.HW;
-            const int a = fastdiv(local, HW, hd.magicHW);
-            const int pos = local - a * HW;
-            const float *q = hd.ptr + ((size_t)(b * p.A + a) * p.attrs) * HW + pos;
-            const float tc = __ldcs(q + 4 * (size_t)HW);
-            const float tx = __ldcs(q), ty = __ldcs(q + HW);
-            const float tw = __ldcs(q + 2 * (size_t)HW), th = __ldcs(q + 3 * (size_t)HW);
-            const float *qc = q + 5 * (size_t)HW;
-
-            // class max over the raw logits; sigmoid is only evaluated where it can
-            // change the (value, first-argmax) of torch.max(sigmoid(logits)) (:198)
-            float m1 = __ldcs(qc), m2 = -INFINITY;
-            int i1 = 0;
-            for (int c0 = 1; c0 < C; c0 += 8) {
-                float x[8];
+    const int C = p.C;
+    int cid0 = 0;
+    if ((p.flags >> 8) && (tid >> 5) >= THREADS / 64) __nanosleep((unsigned)(p.flags >> 8) * 100u);  // experiment
+#pragma unroll 1
+    for (int hh = 0; hh < p.nheads; ++hh) {
+        const HeadDesc &hd = p.head[hh];
+        const int HW = hd.HW;
+        const float *hb = hd.ptr + (size_t)b * p.A * p.attrs * HW;  // uniform
+#pragma unroll 1
+        for (int base = 0; base < hd.cells; base += THREADS) {
+            const int local = base + tid;
+            bool pass = false;
+            if (local < hd.cells) {
+                const int cid = cid0 + local;
+                const int a = fastdiv(local, HW, hd.magicHW);
+                const int pos = local - a * HW;
+                const float *q = hb + (uint32_t)(a * p.attrs * HW + pos);
+                const float tx = __ldcs(q); q += HW;
+                const float ty = __ldcs(q); q += HW;
+                const float tw = __ldcs(q); q += HW;
+                const float th = __ldcs(q); q += HW;
+                const float tc = __ldcs(q); q += HW;
+                const float *qc = q;
+                // class max over the raw logits: value, first argmax and whether any other
+                // logit lies within `win` of it (then sigmoid rounding could change the result
+                // of torch.max(sigmoid(logits)), :198, and the exact tie-break runs)
+                float m1 = -INFINITY;
+                int i1 = 0;
+                bool tie = false;
+                float conf = 0.f, e1 = 0.f, best = 0.f, win = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += kClsChunk) {
+                    // groups of 4 planes behind uniform branches; inside a group the plane index is
+                    // clamped to the last class (duplicates are masked out of `near` below), so the
+                    // loads carry no predicate and no default value
+                    float x[kClsChunk];
+                    const int nv = min(C - c0, kClsChunk);  // uniform
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int c = c0 + u;
-                    x[u] = (c < C) ? __ldcs(qc + (size_t)c * HW) : -INFINITY;
-                }
+                    for (int g = 0; g < kClsChunk / 4; ++g) {
+                        if (4 * g < nv) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (x[u] > m1) { m2 = m1; m1 = x[u]; i1 = c0 + u; } else m2 = fmaxf(m2, x[u]);
-                }
-            }
-            const float conf = sigmoid_f(tc);   // yolo_loss.py:189,197
-            pass = conf > p.conf_thr;           // :201 (threshold already rounded to fp32)
-            if (pass) {
-                const float e1 = expf(-m1);
-                float best = __fdiv_rn(1.0f, __fadd_rn(1.0f, e1));  // sigmoid(m1)
-                int bi = i1;
-                // d/dt ln(sigmoid(t)) = 1 - sigmoid(t) >= e1*best on (-inf, m1], so any logit
-                // below m1 - 2^-19/(e1*best) has a sigmoid smaller by > 2^-19 relative (>10x
-                // the evaluation error) and cannot win or tie.  Everything inside the window
-                // is evaluated exactly like the reference (sigmoid first, then first max).
-                const float win = __fdiv_rn(1.9073486e-06f, __fmul_rn(e1, best));
-                if (C > 1 && !(m2 < __fsub_rn(m1, win))) {
-                    const float lo = __fsub_rn(m1, win);
-                    best = -1.0f;
-                    bi = 0;
-                    for (int cc = 0; cc < C; ++cc) {
-                        const float x = __ldg(qc + (size_t)cc * HW);
-                        if (!(x < lo)) {
-                            const float sg = sigmoid_f(x);
-                            if (sg > best) { best = sg; bi = cc; }
+                            for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = __ldcs(q + (size_t)min(u, nv - 1) * HW);
                         }
                     }
-                    if (best < 0.0f) { best = sigmoid_f(m1); bi = i1; }  // only NaN logits in the window
+                    q += (size_t)nv * HW;
+                    if (c0 == 0) {
+                        conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
+                        pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
+                    }
+                    float cm = x[0];
+#pragma unroll
+                    for (int g = 0; g < kClsChunk / 4; ++g) {
+                        if (4 * g < nv) cm = fmaxf(fmaxf(cm, fmaxf(x[4 * g], x[4 * g + 1])), fmaxf(x[4 * g + 2], x[4 * g + 3]));
+                    }
+                    if (pass) {
+                        // d/dt ln(sigmoid(t)) = 1 - sigmoid(t) >= e*s on (-inf, m], so a logit below
+                        // m - 2^-17/(e*s) has a sigmoid smaller by > 2^-17 relative (>10x the
+                        // evaluation error) and cannot win or tie
+                        const float m_new = fmaxf(m1, cm);
+                        e1 = exp_fast(-m_new);
+                        best = __fdividef(1.0f, __fadd_rn(1.0f, e1));  // sigmoid(m_new)
+                        win = __fdividef(7.6293945e-06f, __fmul_rn(e1, best));
+                        const float lo = __fsub_rn(m_new, win);
+                        float near = 0.f;  // bit u: x[u] >= lo   (FSET + FFMA: exact for 24 bits)
+#pragma unroll
+                        for (int g = 0; g < kClsChunk / 4; ++g) {
+                            if (4 * g < nv) {
+#pragma unroll
+                                for (int u = 4 * g; u < 4 * g + 4; ++u)
+                                    near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << u), near);
+                            }
+                        }
+                        const uint32_t nb = __float2uint_rn(near) & (0xffffffffu >> (32 - nv));
+                        // previous chunks: their max m1 must lie below the window too
+                        const bool prev_near = (c0 > 0) && !(m1 < lo);
+                        if (cm > m1 || c0 == 0) { i1 = c0 + __ffs(nb) - 1; tie = (nb & (nb - 1u)) != 0u || prev_near || nb == 0u; }
+                        else tie = tie || nb != 0u;
+                        m1 = m_new;
+                    } else {
+                        m1 = fmaxf(m1, cm);
+                    }
                 }
-                const int j = fastdiv(pos, hd.W, hd.magicW);
-                const int i = pos - j * hd.W;
-                const float sx = sigmoid_f(tx), sy = sigmoid_f(ty);          // :187
-                const float ew = expf(tw), eh = expf(th);                    // :188
-                const float cx = __fdiv_rn(__fadd_rn(sx, (float)i), hd.fW);  // :194
-                const float cy = __fdiv_rn(__fadd_rn(sy, (float)j), hd.fH);
-                const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
-                const float bh = __fmul_rn(eh, hd.ah[a]);
-                Rec r;
-                r.box.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                // :244
-                r.box.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                // :245
-                r.box.z = __fadd_rn(bw, r.box.x);                            // :246
-                r.box.w = __fadd_rn(bh, r.box.y);                            // :247
-                r.conf = conf;
-                r.score = best;
-                make_ta(r.box, p.iou, r.ta_hi, r.ta_lo);
-                float4 *dst = reinterpret_cast<float4 *>(&s.rec[cid]);
-                dst[0] = r.box;
-                dst[1] = make_float4(r.conf, r.score, r.ta_hi, r.ta_lo);
-                uint32_t idx = 0;
-                if (HIST) idx = (uint32_t)atomicAdd(&s.cnt[bi], 1);
-                s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+                if (pass) {
+                    int bi = i1;
+                    if (C > 1 && tie) best = class_tie_break(qc, HW, C, __fsub_rn(m1, win), m1, i1, &bi);
+                    const int j = fastdiv(pos, hd.W, hd.magicW);
+                    const int i = pos - j * hd.W;
+                    const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
+                    const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
+                    const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194 (x * 1/W)
+                    const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+                    const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
+                    const float bh = __fmul_rn(eh, hd.ah[a]);
+                    float4 bx;
+                    bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244
+                    bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
+                    bx.z = __fadd_rn(bw, bx.x);                                  // :246
+                    bx.w = __fadd_rn(bh, bx.y);                                  // :247
+                    float hi, lo;
+                    make_ta(bx, p.iou, hi, lo);
+                    float4 *dst = reinterpret_cast<float4 *>(&s.rec[cid]);
+                    dst[0] = bx;
+                    dst[1] = make_float4(conf, best, hi, lo);
+                    uint32_t idx = 0;
+                    if (MODE == MODE_FUSED)
+                        idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
+                    s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+                } else if (MODE == MODE_FUSED) {
+                    s.clsidx[cid] = 0xffffffffu;
+                }
             }
+            if (MODE == MODE_DECODE) {  // single head: candidate ids are 32-aligned per warp
+                const unsigned bal = __ballot_sync(kFullMask, pass);
+                if (lane == 0 && local < hd.cells) s.passbits[local >> 5] = bal;
+            }
+            if (MODE == MODE_FUSED) stamp(p, b, 8 + min(7, hh * 4 + base / THREADS));
         }
-        const unsigned bal = __ballot_sync(kFullMask, pass);
-        if (lane == 0 && cid < K) s.passbits[cid >> 5] = bal;
+        cid0 += hd.cells;
     }
 }
 
@@ -279,7 +371,7 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
 // ---------------------------------------------------------------------------
 template <int THREADS>
 __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s, int b) {
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int K0 = min(p.cand_count[0][b], p.cand_stride[0]);
     const int K1 = p.cand[1] ? min(p.cand_count[1][b], p.cand_stride[1]) : 0;
     const int Kb = K0 + K1;
@@ -302,12 +394,12 @@ __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s
                 float4 *dst = reinterpret_cast<float4 *>(&s.rec[row]);
                 dst[0] = r.box;
                 dst[1] = make_float4(r.conf, r.score, r.ta_hi, r.ta_lo);
-                const uint32_t idx = (uint32_t)atomicAdd(&s.cnt[c], 1);
+                const uint32_t idx =
+                    (uint32_t)atomicAdd(&s.cntb[c * p.B + score_bucket(__fmul_rn(r.score, r.conf), p.B)], 1);
                 s.clsidx[row] = ((uint32_t)c << 16) | idx;
             }
         }
-        const unsigned bal = __ballot_sync(kFullMask, ok);
-        if (lane == 0 && row < p.K) s.passbits[row >> 5] = bal;
+        if (row < p.K && !ok) s.clsidx[row] = 0xffffffffu;
     }
 }
 
@@ -320,24 +412,25 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
     int carryS = 0, carryT = 0, words = 0;
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
-        const int n = (c < C) ? s.cnt[c] : 0;
+        const int st = (c < C) ? s.cntb[c * p.B] : 0;
+        const int n = (c < C) ? s.cntb[(c + 1) * p.B] - st : 0;
         const int T = (n + 31) >> 5;
-        const int incS = warp_inclusive_scan(n, lane);
         const int incT = warp_inclusive_scan(T, lane);
         if (c < C) {
-            s.start[c] = carryS + incS - n;
+            s.cnt[c] = n;
+            s.start[c] = st;
             s.ktile[c] = carryT + incT - T;
         }
-        carryS += __shfl_sync(kFullMask, incS, 31);
         carryT += __shfl_sync(kFullMask, incT, 31);
         words += 32 * tri(T);
     }
+    carryS = s.cntb[C * p.B];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) words += __shfl_xor_sync(kFullMask, words, o);
     if (lane == 0) {
+        s.cnt[C] = 0;
         s.start[C] = carryS;
         s.ktile[C] = carryT;
-        s.misc[M_KV] = carryS;
         const int cap = p.mask_cap_words;
         if (words <= cap) {
             s.rounds[0] = make_uint2((uint32_t)C << 16, 0xffffu << 16);
@@ -413,23 +506,54 @@ __device__ __forceinline__ void warp_round_prefix(const Smem &s, int r) {
 }
 
 // ---------------------------------------------------------------------------
-// P3/P4: class-segmented stable sort by score (descending)
+// P2a (all threads): exclusive scan of the (class, score bucket) counters in place
+// -> sorted-position base of every bucket; total -> misc[M_KV]
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ void block_scan_buckets(const DNParams &p, const Smem &s) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NB = p.C * p.B;
+    const int per = (NB + THREADS - 1) / THREADS;
+    const int lo = min(tid * per, NB), hi = min(lo + per, NB);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += s.cntb[i];
+    const int inc = warp_inclusive_scan(sum, lane);
+    if (lane == 31) s.misc[M_WSUM + warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = (lane < THREADS / 32) ? s.misc[M_WSUM + lane] : 0;
+        const int w = warp_inclusive_scan(v, lane);
+        s.misc[M_WSUM + lane] = w - v;
+        if (lane == 31) { s.misc[M_KV] = w; s.cntb[NB] = w; }
+    }
+    __syncthreads();
+    int base = s.misc[M_WSUM + warp] + inc - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int t = s.cntb[i];
+        s.cntb[i] = base;
+        base += t;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// P3/P4: class-major counting sort on score buckets, then rank inside the bucket:
+// the stable descending score sort of torchvision.ops.nms, per class
 // ---------------------------------------------------------------------------
 template <int THREADS>
 __device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s) {
     for (int cid = threadIdx.x; cid < p.K; cid += THREADS) {
-        if (!((s.passbits[cid >> 5] >> (cid & 31)) & 1u)) continue;
         const uint32_t ci = s.clsidx[cid];
+        if (ci == 0xffffffffu) continue;
         const Rec &r = s.rec[cid];
         const float sc = __fmul_rn(r.score, r.conf);  // box.py:27 scores = col5*col4
         const unsigned long long key =
             ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)cid);
-        s.key[s.start[ci >> 16] + (int)(ci & 0xffffu)] = key;
+        s.key[s.cntb[(int)(ci >> 16) * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
     }
 }
 
 template <int THREADS>
-__device__ __forceinline__ void phase_rank_sort(const Smem &s, int Kv, int sord_len) {
+__device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv, int sord_len) {
     for (int t = threadIdx.x; t < sord_len; t += THREADS) {
         if (t >= Kv) {
             s.sord[t] = s.rec_saddr;  // padding: any valid record
@@ -437,15 +561,11 @@ __device__ __forceinline__ void phase_rank_sort(const Smem &s, int Kv, int sord_
         }
         const unsigned long long key = s.key[t];
         const uint32_t cid = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-        const int c = (int)(s.clsidx[cid] >> 16);
-        const int st = s.start[c], en = s.start[c + 1];
+        const Rec &r = s.rec[cid];
+        const int cq = (int)(s.clsidx[cid] >> 16) * p.B + score_bucket(__fmul_rn(r.score, r.conf), p.B);
+        const int st = s.cntb[cq], en = s.cntb[cq + 1];
         int rank = 0;
-        int u = st;
-        for (; u + 4 <= en; u += 4) {
-            const unsigned long long k0 = s.key[u], k1 = s.key[u + 1], k2 = s.key[u + 2], k3 = s.key[u + 3];
-            rank += (k0 > key) + (k1 > key) + (k2 > key) + (k3 > key);
-        }
-        for (; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
+        for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
         s.sord[st + rank] = s.rec_saddr + 32u * cid;
     }
 }
@@ -454,7 +574,7 @@ __device__ __forceinline__ void phase_rank_sort(const Smem &s, int Kv, int sord_
 // P5: pair masks
 // ---------------------------------------------------------------------------
 // exact torchvision decision for one pair (row record address, column box)
-__device__ __forceinline__ bool pair_exact(uint32_t row_saddr, const float4 &cb, const IouThr &thr) {
+__device__ __noinline__ bool pair_exact(uint32_t row_saddr, const float4 &cb, const IouThr &thr) {
     const float4 rb = lds_box(row_saddr);
     return nms_suppress_exact(rb, box_area(rb), cb, box_area(cb), thr);
 }
@@ -544,33 +664,31 @@ __device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
         lds_rec(ord[hasA ? jA : 0], ca, ta);
         lds_rec(ord[act ? jB : 0], cb, tb);
         const int maxA = __reduce_max_sync(kFullMask, tripA), maxB = __reduce_max_sync(kFullMask, tripB);
-        const int nwA = (maxA + 31) >> 5, nwB = (maxB + 31) >> 5;
+        const int ngA = (maxA + 15) >> 4, ngB = (maxB + 15) >> 4;  // 16-row groups
         const int ctA = jA >> 5, ctB = jB >> 5;
         uint32_t *mA = s.mask + s.maskbase[c] + (tri(ctA) - tri0) * 32 + (jA & 31);
         uint32_t *mB = s.mask + s.maskbase[c] + (tri(ctB) - tri0) * 32 + (jB & 31);
-        for (int w = 0; w < nwB; ++w) {
-            uint32_t a0 = 0, a1 = 0, b0, b1;
-            if (w < nwA) {
-                pair_group16<true>(ord + 32 * w, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a0, b0);
-                pair_group16<true>(ord + 32 * w + 16, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a1, b1);
+        uint32_t wA = 0u, wB = 0u;
+        for (int g = 0; g < ngB; ++g) {
+            uint32_t a16 = 0u, b16;
+            if (g < ngA) pair_group16<true>(ord + 16 * g, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a16, b16);
+            else pair_group16<false>(ord + 16 * g, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a16, b16);
+            if (!(g & 1)) {
+                wA = a16;
+                wB = b16;
+                if (g + 1 < ngB) continue;
             } else {
-                pair_group16<false>(ord + 32 * w, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a0, b0);
-                pair_group16<false>(ord + 32 * w + 16, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a1, b1);
+                wA |= a16 << 16;
+                wB |= b16 << 16;
             }
             // rows >= the column index (own bit, later rows, other classes) are masked off
-            if (act && w <= ctB) {
-                uint32_t word = b0 | (b1 << 16);
-                if (w == ctB) word &= (1u << (jB & 31)) - 1u;
-                mB[w * 32] = word;
-            }
-            if (hasA && w <= ctA) {
-                uint32_t word = a0 | (a1 << 16);
-                if (w == ctA) word &= (1u << (jA & 31)) - 1u;
-                mA[w * 32] = word;
-            }
+            const int w = g >> 1;
+            if (act && w <= ctB) mB[w * 32] = (w == ctB) ? (wB & ((1u << (jB & 31)) - 1u)) : wB;
+            if (hasA && w <= ctA) mA[w * 32] = (w == ctA) ? (wA & ((1u << (jA & 31)) - 1u)) : wA;
         }
         // ceil(j/32) row words were computed; the diagonal word of a column with
         // j % 32 == 0 holds no earlier row and may lie beyond the warp's loop
+        const int nwB = (ngB + 1) >> 1;
         if (act && nwB <= ctB) mB[ctB * 32] = 0u;
         if (hasA && nwB <= ctA) mA[ctA * 32] = 0u;
     }
@@ -594,22 +712,23 @@ __device__ __forceinline__ void phase_sweep(const Smem &s) {
             const int j = 32 * ct + lane;
             const uint32_t *col = mbase + (tri(ct) - tri0) * 32 + lane;
             uint32_t sup = 0u;
-            int rt = 0;
-            for (; rt + 4 <= ct; rt += 4) {
-                sup |= (col[rt * 32] & kept_w[rt]) | (col[(rt + 1) * 32] & kept_w[rt + 1]) |
-                       (col[(rt + 2) * 32] & kept_w[rt + 2]) | (col[(rt + 3) * 32] & kept_w[rt + 3]);
-            }
-            for (; rt < ct; ++rt) sup |= col[rt * 32] & kept_w[rt];
+#pragma unroll 2
+            for (int rt = 0; rt < ct; ++rt) sup |= col[rt * 32] & kept_w[rt];
             const bool alive = (j < n) && (sup == 0u);
             const unsigned alive_mask = __ballot_sync(kFullMask, alive);
             const uint32_t diag = alive ? (col[ct * 32] & alive_mask) : 0u;
             const unsigned nz = __ballot_sync(kFullMask, diag != 0u);
+            // columns without any alive earlier overlap are kept outright; the rest are
+            // decided in parallel as soon as all their earlier overlaps are decided (the
+            // lowest undecided column always is, so every pass makes progress)
             unsigned kept = alive_mask & ~nz;
-            for (unsigned rem = nz; rem;) {
-                const int i = __ffs(rem) - 1;
-                rem &= rem - 1u;
-                const unsigned cw = __shfl_sync(kFullMask, diag, i);
-                if ((cw & kept) == 0u) kept |= 1u << i;
+            for (unsigned und = nz; und;) {
+                const bool mine = (und >> lane) & 1u;
+                const bool dead = mine && (diag & kept) != 0u;
+                const bool keep = mine && !dead && (diag & und) == 0u;
+                const unsigned d = __ballot_sync(kFullMask, dead), k = __ballot_sync(kFullMask, keep);
+                kept |= k;
+                und &= ~(d | k);
             }
             if (lane == 0) kept_w[ct] = kept;
             __syncwarp();
@@ -629,14 +748,28 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     const int C = p.C, K = p.K;
     constexpr int kWarps = THREADS / 32;
 
+    stamp(p, b, 0);
+    if (MODE != MODE_NMS) {
+        // one thread per (head, anchor) slab: start the HBM -> L2 stream of this image now
+        if (tid == 0 && !(p.flags & 1)) {
+            const size_t img0 = (size_t)p.A * p.attrs * p.head[0].HW;
+            l2_prefetch_span(p.head[0].ptr + (size_t)b * img0, img0 * sizeof(float));
+            if (p.nheads > 1 && !(p.flags & 2)) {
+                const size_t img1 = (size_t)p.A * p.attrs * p.head[1].HW;
+                l2_prefetch_span(p.head[1].ptr + (size_t)b * img1, img1 * sizeof(float));
+            }
+        }
+    }
     if (MODE != MODE_DECODE) {
-        for (int c = tid; c <= C; c += THREADS) s.cnt[c] = 0;
+        for (int i = tid; i <= C * p.B; i += THREADS) s.cntb[i] = 0;
         __syncthreads();
     }
+    stamp(p, b, 15);
 
     if (MODE == MODE_NMS) phase_load_rows<THREADS>(p, s, b);
-    else phase_decode<THREADS, MODE == MODE_FUSED>(p, s, b);
+    else phase_decode<THREADS, MODE>(p, s, b);
     __syncthreads();
+    stamp(p, b, 1);
 
     const int nwords = (K + 31) >> 5;
 
@@ -673,56 +806,60 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         return;
     }
 
-    // P2
+    // P2, P3 (warp 0's class bookkeeping overlaps the key scatter of the others)
+    block_scan_buckets<THREADS>(p, s);
+    __syncthreads();
     if (warp == 0) {
         warp_class_scan(p, s);
         warp_round_prefix(s, 0);
     }
-    __syncthreads();
-    const int Kv = s.misc[M_KV];
-    const int nrounds = s.misc[M_NROUNDS];
-    // P3, P4
     phase_scatter_keys<THREADS>(p, s);
     __syncthreads();
-    phase_rank_sort<THREADS>(s, Kv, 2 * (int)align_up((uint32_t)K, 32) + 64);
+    stamp(p, b, 2);
+    const int Kv = s.misc[M_KV];
+    const int nrounds = s.misc[M_NROUNDS];
+    // P4
+    phase_rank_sort<THREADS>(p, s, Kv, 2 * (int)align_up((uint32_t)K, 32) + 64);
     __syncthreads();
+    stamp(p, b, 3);
     // P5, P6
     for (int r = 0;;) {
         phase_pairs(p, s);
         __syncthreads();
+        stamp(p, b, 4);
         phase_sweep<THREADS>(s);
         __syncthreads();
+        stamp(p, b, 5);
         if (++r >= nrounds) break;
         if (warp == 0) warp_round_prefix(s, r);
         __syncthreads();
     }
-    // P7: exclusive scan of the kept bitmap (tile granularity)
+    // P7/P8: output row -> cell id (the mask buffer is dead now; outsrc aliases it).  Every
+    // warp sums the kept counts of the tiles before its class itself (no serial scan phase).
     const int ntiles = s.ktile[C];
-    if (warp == 0) {
-        int carry = 0;
-        for (int g0 = 0; g0 < ntiles; g0 += 32) {
-            const int g = g0 + lane;
-            const int v = (g < ntiles) ? __popc(s.keptbits[g]) : 0;
-            const int inc = warp_inclusive_scan(v, lane);
-            if (g < ntiles) s.tilepref[g] = carry + inc - v;
-            carry += __shfl_sync(kFullMask, inc, 31);
+    for (int c = warp; c <= C; c += kWarps) {
+        const int kt = s.ktile[c];
+        int before = 0;
+        for (int g = lane; g < kt; g += 32) before += __popc(s.keptbits[g]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFullMask, before, o);
+        if (c == C) {
+            if (lane == 0) s.misc[M_TOTAL] = before;
+            break;
         }
-        if (lane == 0) s.misc[M_TOTAL] = carry;
-    }
-    __syncthreads();
-    // P8: output row -> cell id (the mask buffer is dead now; outsrc aliases it)
-    for (int c = warp; c < C; c += kWarps) {
-        const int n = s.cnt[c];
-        const int kt = s.ktile[c], st = s.start[c];
+        const int n = s.cnt[c], st = s.start[c];
         for (int ct = 0; 32 * ct < n; ++ct) {
             const uint32_t word = s.keptbits[kt + ct];
             if ((word >> lane) & 1u) {
                 const uint32_t cid = (s.sord[st + 32 * ct + lane] - s.rec_saddr) >> 5;
-                s.outsrc[s.tilepref[kt + ct] + __popc(word & lanemask_lt())] = (uint16_t)cid;
+                s.outsrc[before + __popc(word & lanemask_lt())] = (uint16_t)cid;
             }
+            before += __popc(word);
         }
     }
+    (void)ntiles;
     __syncthreads();
+    stamp(p, b, 6);
     // P9: flat coalesced store
     {
         const int T = s.misc[M_TOTAL];
@@ -749,6 +886,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
             for (int r = tid; r < T; r += THREADS) p.out_idx[(size_t)b * K + r] = (int)s.outsrc[r];
         if (tid == 0) p.out_count[b] = T;
     }
+    stamp(p, b, 7);
 }
 
 }  // namespace b200yolo
