@@ -76,16 +76,22 @@ void fill_head(HeadDesc &h, const float *ptr, int A, int H, int W, const float *
 IouThr make_thr(double thr) {
     IouThr t;
     t.thr = thr;
-    t.fast_ok = (thr > 0.0 && thr <= 1.0) ? 1 : 0;
+    t.fast_ok = (thr >= 0.01 && thr <= 1.0) ? 1 : 0;
     const double tt = t.fast_ok ? thr / (1.0 + thr) : 0.0;  // iou > thr <=> inter > tt * (area_a + area_b)
-    t.t_hi = (float)(tt * (1.0 + 1e-5));
-    t.t_lo = (float)(tt * (1.0 - 1e-5));
+    t.ts = (float)tt * 1.220703125e-4f;                     // * 2^-13, exact
     return t;
 }
 
-// Two CTAs of 512 threads share an SM when one image's staging fits half of the
-// shared memory; larger images get the whole SM and 1024 threads.
-constexpr int kSmemHalfSM = (228 * 1024) / 2 - 1024;
+// Shared-memory tiers.  The decode phase streams the heads through L1, and L1 is what
+// the resident CTAs' shared memory leaves of the SM's 228 KB (carve-out steps ... 132,
+// 164, 196, 228 KB), so the layout is kept as small as the image allows:
+//   <= 80 KB : two CTAs of 512 threads per SM, 164 KB carve-out, 64 KB of L1
+//   <= 113 KB: two CTAs of 512 threads per SM, no L1 to speak of
+//   <= 162 KB: one CTA of 1024 threads per SM, 64 KB of L1
+//   else     : one CTA of 1024 threads, up to the opt-in limit (227 KB)
+constexpr int kTier2x64 = 80 * 1024;
+constexpr int kTier2x0 = (228 * 1024) / 2 - 1024;
+constexpr int kTier1x64 = 162 * 1024;
 
 template <int MODE, int THREADS>
 int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
@@ -116,21 +122,22 @@ int launch_dn(DNParams &p, cudaStream_t st) {
                     "%d candidate cells per image with %d classes need %u B of shared memory (limit %d B)", p.K, p.C,
                     base.total, lim);
     if (p.N == 0) return 0;
-    if (MODE == MODE_DECODE) {
-        if ((int)base.total <= kSmemHalfSM && kSmemHalfSM <= lim) return launch_dn_t<MODE, 512>(p, base, dev, st);
-        return launch_dn_t<MODE, 1024>(p, base, dev, st);
-    }
-    const bool half = (int)base.total <= kSmemHalfSM && kSmemHalfSM <= lim;
-    const int budget = half ? kSmemHalfSM : lim;
-    const SmemLayout L = make_layout(p.K, p.C, MODE, (uint32_t)(budget - (int)base.total));
-    p.mask_cap_words = (int)L.mask_words;
     p.B = pick_buckets(p.C);
     p.dbg = g_dbg.load();
     {
         static const int env_flags = [] { const char *e = getenv("B200YOLO_FLAGS"); return e ? atoi(e) : 0; }();
         p.flags = env_flags;
     }
-    if (half) return launch_dn_t<MODE, 512>(p, L, dev, st);
+    const int need = (int)base.total;
+    int budget = lim;
+    bool two = false;
+    if (need <= kTier2x64 && kTier2x64 <= lim) { budget = kTier2x64; two = true; }
+    else if (need <= kTier2x0 && kTier2x0 <= lim) { budget = kTier2x0; two = true; }
+    else if (need <= kTier1x64 && kTier1x64 <= lim) budget = kTier1x64;
+    if (p.flags & 4) { budget = (need <= kTier2x0 && kTier2x0 <= lim) ? kTier2x0 : lim; }  // experiment: old sizing
+    // the pair masks get whatever the tier leaves (MODE_DECODE has none)
+    const SmemLayout L = (MODE == MODE_DECODE) ? base : make_layout(p.K, p.C, MODE, (uint32_t)(budget - need));
+    if (two) return launch_dn_t<MODE, 512>(p, L, dev, st);
     return launch_dn_t<MODE, 1024>(p, L, dev, st);
 }
 

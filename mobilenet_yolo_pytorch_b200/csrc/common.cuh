@@ -56,25 +56,25 @@ __device__ __forceinline__ float box_area(const float4 &b) { return __fmul_rn(__
 //   suppress iff (double)iou > thr
 // The hot loop (decode_nms.cuh, pair masks) decides most pairs without the divide:
 // with t = thr/(1+thr), iou > thr <=> inter > t*(area_a+area_b) in exact arithmetic,
-// and every rounding on either side is < 5e-7 relative, so outside a 1e-5 guard
-// band (t_hi, t_lo) the cheap comparison IS the exact answer; inside the band, for
-// degenerate boxes (area not in [1e-30, 1e30]) and for thr outside (0,1] this exact
-// routine decides.
+// and every rounding on either side is < 5e-7 relative, so when the two sides differ
+// by more than 1e-5 relative the cheap comparison IS the exact answer; closer calls,
+// degenerate boxes (area not in [1e-20, 1e20], |coordinate| >= 4096, NaN) and thr
+// outside [0.01, 1] are decided by this exact routine.
 struct IouThr {
     double thr;
-    float t_hi, t_lo;  // thr/(1+thr) * (1 +- 1e-5)
-    int fast_ok;       // thr in (0, 1]
+    float ts;     // thr/(1+thr) * 2^-13 (the pair test works on widths scaled into [0,1))
+    int fast_ok;  // thr in [0.01, 1]
 };
 
 __device__ __forceinline__ bool nms_suppress_exact(const float4 &a, float area_a, const float4 &b, float area_b,
-                                                   const IouThr &t) {
+                                                   double thr) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
     float inter = __fmul_rn(w, h);
     float u = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     float ovr = __fdiv_rn(inter, u);
-    return (double)ovr > t.thr;
+    return (double)ovr > thr;
 }
 
 // utils/iou.py:4-13 find_intersection for one pair (clamp(min=0) keeps NaN)

@@ -3,45 +3,49 @@
 // One CTA per image; everything about one image lives in shared memory, the head
 // tensors are read from HBM exactly once and only kept rows are written back.
 //
+// Shared memory is kept SMALL on purpose (<= 80 KB per CTA for the 352x352 VOC heads):
+// the decode phase streams the heads with ordinary coalesced loads whose in-flight
+// lines live in L1, and L1 is what the CTAs' shared memory leaves of the SM's 228 KB
+// (profiles/micro/load_pattern.cu: the same load pattern runs at 4.3 TB/s with 64 KB of
+// L1 and at 2.9 TB/s with none).  So: structure-of-arrays records, and one region `U`
+// that is reused by phase (class/arrival index + sort keys -> sorted order + pair masks
+// -> output order).
+//
 //   P1 decode     thread per cell, ALL 5+C attribute planes of the cell loaded at
-//                 once (coalesced: consecutive lanes = consecutive cells of a plane;
-//                 every load is independent, so ~13 x THREADS x 4 B are in flight
-//                 per CTA).  conf = sigmoid(tc) > thr (yolo_loss.py:189,201); for
-//                 passing cells: class max / argmax (:198), box (:186-196,243-247),
-//                 one 32-byte record in shared memory, pass bit (ballot) and the
-//                 per-class arrival index (one shared atomic).
-//   P2 class scan exclusive scan of the class histogram -> class segments
-//                 (box.py:20-22), tiles, pair-slot and bitmask offsets.
-//   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort
-//                 of torchvision.ops.nms) into class segments.
-//   P4 rank sort  rank inside the class segment -> `sord` (sorted position -> record).
-//   P5 pair masks ALL threads: for every pair (row i < column j) of a class, bit i
-//                 of column j's mask = "i suppresses j".  Column j and column
-//                 n-1-j share a lane, so every lane does n-1 tests (balanced) while
-//                 row records are broadcast from shared memory.  The test is a
-//                 divide-free two-sided filter (inter > t*(area_i+area_j) with a
-//                 1e-5 guard band, t = thr/(1+thr)); only pairs inside the band run
-//                 the exact torchvision arithmetic (inter/(Sa+Sb-inter) > thr in
-//                 double).  Result bits are accumulated with FFMA (fma pipe) so the
-//                 alu pipe (FMNMX/FSET) is not the only one working.
-//   P6 sweep      one warp per class walks 32-column tiles: columns suppressed by a
-//                 kept row of an earlier tile drop out with one AND per tile, the
-//                 diagonal tile is resolved with ballot/shfl in ascending order.
-//   P7-9 output   class-ascending / score-descending rows (box.py:29-30): scan of the
+//                 once (coalesced: consecutive lanes = consecutive cells of a plane).
+//                 conf = sigmoid(tc) > thr (yolo_loss.py:189,201); for passing cells:
+//                 class max / argmax (:198), box (:186-196,243-247) -> box[], cs[], ta[],
+//                 and the per-(class, score bucket) arrival index (one shared atomic).
+//   P2 scans      exclusive scan of the (class, bucket) histogram -> class segments
+//                 (box.py:20-22), kept-bitmap tiles, the round table.
+//   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort of
+//                 torchvision.ops.nms) into their (class, bucket) segment.
+//   P4 rank       rank inside the bucket -> `sord` (sorted position -> cell id).
+//   P5 pairs+sweep  dynamic warp tasks.  A task is one 32-row strip of one class: the
+//                 lane keeps its row's box in registers and walks the later columns
+//                 (broadcast from shared memory), 32 columns per mask word.  The test is
+//                 divide-free: iou > thr  <=>  inter > t*(area_r+area_c), t = thr/(1+thr);
+//                 d = t*(area_r+area_c) - w*h is one FFMA and its SIGN BIT is the mask
+//                 bit (one funnel shift).  |d| <= 1e-5*t*(area sum) (or any degenerate
+//                 box in the class) sends the lane to the exact torchvision arithmetic
+//                 (inter/(Sa+Sb-inter) > thr in double).  The warp that finishes the last
+//                 strip of a class sweeps it at once (no block barrier): per 32-column
+//                 tile, OR the mask words of the kept earlier rows, then resolve the
+//                 diagonal block by walking only the rows that suppress something.
+//   P6 output     class-ascending / score-descending rows (box.py:29-30): scan of the
 //                 kept bitmap, then a flat coalesced store.
 //
-// If the masks of all classes do not fit the shared-memory budget, P5/P6 run in
-// rounds (groups of whole classes, or column-tile chunks of one huge class).
+// If the masks of all classes do not fit `U`, P5 runs in rounds (groups of whole
+// classes, or column-tile chunks of one huge class) with a block barrier in between.
 //
 // The stand-alone decode (P1 + ordered compaction + store) and NMS (load rows,
-// P2..P9) kernels back YOLOLoss.forward(input) and utils.box.nms separately.
+// P2..P6) kernels back YOLOLoss.forward(input) and utils.box.nms separately.
 #pragma once
 #include "common.cuh"
 
 namespace b200yolo {
 
 constexpr int kMaxAnchors = 8;
-constexpr uint32_t kNoClass = 0xffffu;
 
 enum { MODE_FUSED = 0, MODE_DECODE = 1, MODE_NMS = 2 };
 
@@ -58,9 +62,8 @@ struct DNParams {
     int nheads;
     int N, A, C, attrs;
     int K;               // candidate slots per image = row stride of out / out_idx
-    int mask_cap_words;  // capacity of the pair-mask buffer (32-bit words)
     int B;               // score buckets per class of the counting sort (power of two)
-    int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch
+    int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads, 4 = old smem sizing
     unsigned long long *dbg;  // optional [N][16] phase time stamps (ns, globaltimer), NULL in production
     float conf_thr;
     IouThr iou;
@@ -73,34 +76,32 @@ struct DNParams {
     int cand_stride[2];
 };
 
-// 32-byte candidate record, indexed by cell id (candidate id)
-struct __align__(16) Rec {
-    float4 box;   // x1 y1 x2 y2            (output columns 0-3)
-    float conf;   //                         (column 4)
-    float score;  // class score             (column 5)
-    float ta_hi;  // t*(1+1e-5)*area   (+inf: always take the exact path)
-    float ta_lo;  // t*(1-1e-5)*area   (-inf: always take the exact path)
-};
-
 struct SmemLayout {
-    uint32_t rec, clsidx, sord, key, passbits, keptbits, tilepref, cls, cntb, rounds, misc, total;
-    uint32_t mask_words;  // words available at `key` (keys are dead once ranks are known)
+    uint32_t box, cs, ta, cntb, cls, tasks, keptbits, tilepref, passbits, rounds, misc, U, total;
+    uint32_t u_bytes;     // bytes in U
+    uint32_t mask_off;    // masks / output order start here (after sord)
+    uint32_t mask_words;  // 32-bit words available for pair masks
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // per-class int arrays, each (C+1) long
-enum { CA_CNT = 0, CA_START, CA_KTILE, CA_SLOT, CA_MASK, CA_NUM };
+enum { CA_CNT = 0, CA_START, CA_KTILE, CA_MASK, CA_TBASE, CA_DONE, CA_FLAG, CA_NUM };
 // misc ints
-enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_SLOTS, M_CTR, M_TOTAL, M_KV, M_WSUM = 16, M_NUM = 16 + 32 };
+enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_NTASK, M_CTR, M_TOTAL, M_KV, M_WSUM = 16, M_NUM = 16 + 32 };
 
 // score buckets per class: C*B counters, at most 2048 (8 KB)
 __host__ __device__ inline int pick_buckets(int C) {
     int B = 64;
-    while (B > 1 && C * B > 2048) B >>= 1;
+    while (B > 1 && C * B > 1536) B >>= 1;
     return B;
 }
 
+// U region by phase (Kp = K rounded up to 32):
+//   decode .. key scatter   clsidx u32[Kp] | key u64[Kp]
+//   rank .. sweep           sord u16[Kp+32] | pair masks u32[mask_words]
+//   output                  sord            | outsrc u16[Kp] | outcls u16[Kp]
+//   (MODE_DECODE)           clsidx u32[Kp]  | outsrc u16[Kp]
 __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32_t extra_mask_bytes) {
     SmemLayout L;
     const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
@@ -108,61 +109,74 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32
     const uint32_t tiles = Kp / 32 + (uint32_t)C + 1;
     const bool nms = (mode != MODE_DECODE);
     uint32_t o = 0;
-    L.rec = o; o += 32 * Kp;
-    L.clsidx = o; o += 4 * Kp;
-    L.sord = o; o += nms ? 4 * (2 * Kp + 64) : 2 * Kp;  // decode mode: u16 output order
-    L.key = o; o += nms ? 8 * Kp + (extra_mask_bytes & ~15u) : 0;
-    L.mask_words = nms ? (8 * Kp + (extra_mask_bytes & ~15u)) / 4 : 0;
-    L.passbits = o; o += 4 * (Kp / 32);
+    L.box = o; o += 16 * Kp;
+    L.cs = o; o += 8 * Kp;
+    L.ta = o; o += nms ? 4 * Kp : 0;
+    L.cntb = o; o += nms ? 4 * align_up((uint32_t)(C * pick_buckets(C)) + 1, 4) : 0;
+    L.cls = o; o += nms ? 4 * Cp * CA_NUM : 0;
+    L.tasks = o; o += nms ? 4 * tiles : 0;
     L.keptbits = o; o += nms ? 4 * tiles : 0;
     L.tilepref = o; o += 4 * (tiles + 1);
-    o = align_up(o, 16);
-    L.cls = o; o += nms ? 4 * Cp * CA_NUM : 0;
-    L.cntb = o; o += nms ? 4 * align_up((uint32_t)(C * pick_buckets(C)) + 1, 4) : 0;
+    L.passbits = o; o += nms ? 0 : 4 * (Kp / 32);
+    o = align_up(o, 8);
     L.rounds = o; o += nms ? 8 * (tiles + (uint32_t)C + 2) : 0;
     L.misc = o; o += 4 * M_NUM;
-    L.total = align_up(o, 16);
+    o = align_up(o, 16);
+    L.U = o;
+    L.u_bytes = nms ? 12 * Kp + (extra_mask_bytes & ~15u) : 6 * Kp;
+    const uint32_t sord_bytes = nms ? align_up(2 * (Kp + 32), 16) : 4 * Kp;
+    L.mask_off = L.U + sord_bytes;
+    L.mask_words = (L.u_bytes - sord_bytes) / 4;
+    L.total = align_up(L.U + L.u_bytes, 16);
     return L;
 }
 
 struct Smem {
-    Rec *rec;
-    uint32_t *clsidx;   // (class << 16) | arrival index inside the class
-    uint32_t *sord;     // sorted position -> shared-space address of the record
-    uint16_t *outsrc;   // output row -> cell id (aliases sord in decode mode, keys otherwise)
+    float4 *box;        // [Kp] x1 y1 x2 y2 by cell id            (output columns 0-3)
+    float2 *cs;         // [Kp] conf, class score                 (columns 4, 5)
+    float *ta;          // [Kp] t * area * 2^-13 (NaN: degenerate box, the class takes the exact path)
+    uint32_t *clsidx;   // [Kp] (class << 16) | arrival index inside the (class, bucket); ~0u: not a candidate
     unsigned long long *key;
-    uint32_t *mask;     // aliases key
-    uint32_t *passbits, *keptbits, *tilepref;
-    int *cnt, *start, *ktile, *slot, *maskbase;
+    uint16_t *sord;     // sorted position -> cell id
+    uint32_t *mask;     // pair-mask words
+    uint16_t *outsrc;   // output row -> cell id
+    uint16_t *outcls;   // output row -> class
+    uint32_t *passbits, *keptbits, *tilepref, *tasks;
+    int *cnt, *start, *ktile, *maskbase, *tbase, *done, *flag;
     int *cntb;          // [C*B+1] per (class, score bucket): arrival counter, then exclusive prefix
     uint2 *rounds;      // x = c_lo | c_hi << 16, y = t0 | t1 << 16
     int *misc;
-    uint32_t rec_saddr;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, int C, int mode) {
+__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, int K, int C, int mode) {
     Smem s;
+    const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
     const uint32_t Cp = align_up((uint32_t)C + 1, 4);
-    s.rec = reinterpret_cast<Rec *>(base + L.rec);
-    s.clsidx = reinterpret_cast<uint32_t *>(base + L.clsidx);
-    s.sord = reinterpret_cast<uint32_t *>(base + L.sord);
-    s.key = reinterpret_cast<unsigned long long *>(base + L.key);
-    s.mask = reinterpret_cast<uint32_t *>(base + L.key);
-    s.outsrc = (mode == MODE_DECODE) ? reinterpret_cast<uint16_t *>(base + L.sord)
-                                     : reinterpret_cast<uint16_t *>(base + L.key);
+    s.box = reinterpret_cast<float4 *>(base + L.box);
+    s.cs = reinterpret_cast<float2 *>(base + L.cs);
+    s.ta = reinterpret_cast<float *>(base + L.ta);
+    s.clsidx = reinterpret_cast<uint32_t *>(base + L.U);
+    s.key = reinterpret_cast<unsigned long long *>(base + L.U + 4 * Kp);
+    s.sord = reinterpret_cast<uint16_t *>(base + L.U);
+    s.mask = reinterpret_cast<uint32_t *>(base + L.mask_off);
+    s.outsrc = reinterpret_cast<uint16_t *>(base + L.mask_off);
+    s.outcls = reinterpret_cast<uint16_t *>(base + L.mask_off + 2 * Kp);
     s.passbits = reinterpret_cast<uint32_t *>(base + L.passbits);
     s.keptbits = reinterpret_cast<uint32_t *>(base + L.keptbits);
     s.tilepref = reinterpret_cast<uint32_t *>(base + L.tilepref);
+    s.tasks = reinterpret_cast<uint32_t *>(base + L.tasks);
     int *ca = reinterpret_cast<int *>(base + L.cls);
     s.cnt = ca + CA_CNT * Cp;
     s.start = ca + CA_START * Cp;
     s.ktile = ca + CA_KTILE * Cp;
-    s.slot = ca + CA_SLOT * Cp;
     s.maskbase = ca + CA_MASK * Cp;
+    s.tbase = ca + CA_TBASE * Cp;
+    s.done = ca + CA_DONE * Cp;
+    s.flag = ca + CA_FLAG * Cp;
     s.cntb = reinterpret_cast<int *>(base + L.cntb);
     s.rounds = reinterpret_cast<uint2 *>(base + L.rounds);
     s.misc = reinterpret_cast<int *>(base + L.misc);
-    s.rec_saddr = (uint32_t)__cvta_generic_to_shared(s.rec);
+    (void)mode;
     return s;
 }
 
@@ -181,25 +195,14 @@ __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
     }
 }
 
-__device__ __forceinline__ void lds_rec(uint32_t saddr, float4 &box, float2 &ta) {
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(box.x), "=f"(box.y), "=f"(box.z), "=f"(box.w)
-                 : "r"(saddr));
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+24];" : "=f"(ta.x), "=f"(ta.y) : "r"(saddr));
-}
-
-__device__ __forceinline__ float4 lds_box(uint32_t saddr) {
-    float4 b;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(saddr));
-    return b;
-}
-
-// guard-banded area terms of one box for the divide-free pair filter
-__device__ __forceinline__ void make_ta(const float4 &b, const IouThr &t, float &hi, float &lo) {
+// t * area * 2^-13 of one box for the divide-free pair test, NaN when the fast test
+// must not be trusted for this box (the whole class then runs the exact arithmetic)
+__device__ __forceinline__ float make_ta(const float4 &b, const IouThr &t) {
     const float a = box_area(b);
-    const bool ok = t.fast_ok && a >= 1e-30f && a <= 1e30f;
-    hi = ok ? __fmul_rn(a, t.t_hi) : INFINITY;
-    lo = ok ? __fmul_rn(a, t.t_lo) : -INFINITY;
+    const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    // comparisons are false for NaN coordinates / areas
+    const bool ok = t.fast_ok && a >= 1e-20f && a <= 1e20f && big < 4096.0f;  // a NaN coordinate makes the area NaN
+    return ok ? __fmul_rn(a, t.ts) : __int_as_float(0x7fc00000);
 }
 
 // score bucket of the counting sort: monotone non-increasing in the sort key
@@ -208,6 +211,10 @@ __device__ __forceinline__ int score_bucket(float sc, int B) {
     const float top = (float)(B - 1);
     const float f = (sc != sc) ? top : fminf(fmaxf(__fmul_rn(sc, (float)B), 0.0f), top);
     return B - 1 - (int)f;
+}
+
+__device__ __forceinline__ float order_key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);  // 0xffffffff -> NaN
 }
 
 // Ask the L2 to fetch [ptr, ptr+bytes) from HBM (cp.async.bulk.prefetch: the copy engine
@@ -247,7 +254,6 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = p.C;
     int cid0 = 0;
-    if ((p.flags >> 8) && (tid >> 5) >= THREADS / 64) __nanosleep((unsigned)(p.flags >> 8) * 100u);  // experiment
 #pragma unroll 1
     for (int hh = 0; hh < p.nheads; ++hh) {
         const HeadDesc &hd = p.head[hh];
@@ -261,13 +267,17 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
                 const int cid = cid0 + local;
                 const int a = fastdiv(local, HW, hd.magicHW);
                 const int pos = local - a * HW;
-                const float *q = hb + (uint32_t)(a * p.attrs * HW + pos);
-                const float tx = __ldcs(q); q += HW;
-                const float ty = __ldcs(q); q += HW;
-                const float tw = __ldcs(q); q += HW;
-                const float th = __ldcs(q); q += HW;
-                const float tc = __ldcs(q); q += HW;
-                const float *qc = q;
+                // addresses: one IMAD.WIDE each (64-bit base + 32-bit plane stride * constant)
+                const char *q = reinterpret_cast<const char *>(hb + (uint32_t)(a * p.attrs * HW + pos));
+                const uint32_t st = (uint32_t)HW * 4u;  // plane stride in bytes
+#define B200_LD(u) __ldcs(reinterpret_cast<const float *>(q + (uint64_t)st * (uint32_t)(u)))
+                const float tx = B200_LD(0);
+                const float ty = B200_LD(1);
+                const float tw = B200_LD(2);
+                const float th = B200_LD(3);
+                const float tc = B200_LD(4);
+                q += (uint64_t)st * 5u;
+                const float *qc = reinterpret_cast<const float *>(q);
                 // class max over the raw logits: value, first argmax and whether any other
                 // logit lies within `win` of it (then sigmoid rounding could change the result
                 // of torch.max(sigmoid(logits)), :198, and the exact tie-break runs)
@@ -277,19 +287,22 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
                 float conf = 0.f, e1 = 0.f, best = 0.f, win = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < C; c0 += kClsChunk) {
-                    // groups of 4 planes behind uniform branches; inside a group the plane index is
-                    // clamped to the last class (duplicates are masked out of `near` below), so the
-                    // loads carry no predicate and no default value
+                    // groups of 4 planes behind uniform branches; only the last, partial group clamps
+                    // its plane index to the last class (duplicates are masked out of `near` below),
+                    // so the loads carry no predicate and no default value
                     float x[kClsChunk];
                     const int nv = min(C - c0, kClsChunk);  // uniform
 #pragma unroll
                     for (int g = 0; g < kClsChunk / 4; ++g) {
-                        if (4 * g < nv) {
+                        if (4 * g + 4 <= nv) {
 #pragma unroll
-                            for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = __ldcs(q + (size_t)min(u, nv - 1) * HW);
+                            for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(u);
+                        } else if (4 * g < nv) {
+#pragma unroll
+                            for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(min(u, nv - 1));
                         }
                     }
-                    q += (size_t)nv * HW;
+                    q += (uint64_t)st * (uint32_t)nv;
                     if (c0 == 0) {
                         conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
                         pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
@@ -343,24 +356,24 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
                     bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
                     bx.z = __fadd_rn(bw, bx.x);                                  // :246
                     bx.w = __fadd_rn(bh, bx.y);                                  // :247
-                    float hi, lo;
-                    make_ta(bx, p.iou, hi, lo);
-                    float4 *dst = reinterpret_cast<float4 *>(&s.rec[cid]);
-                    dst[0] = bx;
-                    dst[1] = make_float4(conf, best, hi, lo);
+                    s.box[cid] = bx;
+                    s.cs[cid] = make_float2(conf, best);
                     uint32_t idx = 0;
-                    if (MODE == MODE_FUSED)
+                    if (MODE == MODE_FUSED) {
+                        s.ta[cid] = make_ta(bx, p.iou);
                         idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
+                    }
                     s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
                 } else if (MODE == MODE_FUSED) {
                     s.clsidx[cid] = 0xffffffffu;
                 }
             }
+#undef B200_LD
             if (MODE == MODE_DECODE) {  // single head: candidate ids are 32-aligned per warp
                 const unsigned bal = __ballot_sync(kFullMask, pass);
                 if (lane == 0 && local < hd.cells) s.passbits[local >> 5] = bal;
             }
-            if (MODE == MODE_FUSED) stamp(p, b, 8 + min(7, hh * 4 + base / THREADS));
+            if (MODE == MODE_FUSED) stamp(p, b, 8 + min(6, hh * 4 + base / THREADS));
         }
         cid0 += hd.cells;
     }
@@ -382,20 +395,16 @@ __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s
         bool ok = false;
         if (row < Kb) {
             const float *src = (row < K0) ? r0 + (size_t)row * 7 : r1 + (size_t)(row - K0) * 7;
-            Rec r;
-            r.box = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
-            r.conf = __ldg(src + 4);
-            r.score = __ldg(src + 5);
+            const float4 bx = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+            const float conf = __ldg(src + 4), score = __ldg(src + 5);
             const float v = __ldg(src + 6);
             const int c = (int)v;  // rows whose class column is not an integer in [0,C) match no `== i` (box.py:21)
             ok = (v == (float)c) && c >= 0 && c < p.C;
             if (ok) {
-                make_ta(r.box, p.iou, r.ta_hi, r.ta_lo);
-                float4 *dst = reinterpret_cast<float4 *>(&s.rec[row]);
-                dst[0] = r.box;
-                dst[1] = make_float4(r.conf, r.score, r.ta_hi, r.ta_lo);
-                const uint32_t idx =
-                    (uint32_t)atomicAdd(&s.cntb[c * p.B + score_bucket(__fmul_rn(r.score, r.conf), p.B)], 1);
+                s.box[row] = bx;
+                s.cs[row] = make_float2(conf, score);
+                s.ta[row] = make_ta(bx, p.iou);
+                const uint32_t idx = (uint32_t)atomicAdd(&s.cntb[c * p.B + score_bucket(__fmul_rn(score, conf), p.B)], 1);
                 s.clsidx[row] = ((uint32_t)c << 16) | idx;
             }
         }
@@ -406,10 +415,10 @@ __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s
 // ---------------------------------------------------------------------------
 // P2 (warp 0): class segments, kept-bitmap tiles, and the round table
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s) {
+__device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s, int mask_cap_words) {
     const int lane = threadIdx.x & 31;
     const int C = p.C;
-    int carryS = 0, carryT = 0, words = 0;
+    int carryT = 0, words = 0;
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
         const int st = (c < C) ? s.cntb[c * p.B] : 0;
@@ -424,14 +433,13 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
         carryT += __shfl_sync(kFullMask, incT, 31);
         words += 32 * tri(T);
     }
-    carryS = s.cntb[C * p.B];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) words += __shfl_xor_sync(kFullMask, words, o);
     if (lane == 0) {
         s.cnt[C] = 0;
-        s.start[C] = carryS;
+        s.start[C] = s.cntb[C * p.B];
         s.ktile[C] = carryT;
-        const int cap = p.mask_cap_words;
+        const int cap = mask_cap_words;
         if (words <= cap) {
             s.rounds[0] = make_uint2((uint32_t)C << 16, 0xffffu << 16);
             s.misc[M_NROUNDS] = 1;
@@ -445,7 +453,7 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
                     while (t0 < T) {
                         int t1 = t0, acc = 0;
                         while (t1 < T && acc + 32 * (t1 + 1) <= cap) { acc += 32 * (t1 + 1); ++t1; }
-                        if (t1 == t0) ++t1;  // cannot happen: host guarantees cap >= Kp >= 32*T
+                        if (t1 == t0) ++t1;  // cannot happen: cap >= Kp >= 32*T
                         s.rounds[r++] = make_uint2((uint32_t)c | ((uint32_t)(c + 1) << 16), (uint32_t)t0 | ((uint32_t)t1 << 16));
                         t0 = t1;
                     }
@@ -468,7 +476,7 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
     __syncwarp();
 }
 
-// per round (warp 0): pair-slot and mask offsets of the round's classes
+// per round (warp 0): mask offsets, strip-task table and completion counters of the round's classes
 __device__ __forceinline__ void warp_round_prefix(const Smem &s, int r) {
     const int lane = threadIdx.x & 31;
     const uint2 rd = s.rounds[r];
@@ -476,30 +484,30 @@ __device__ __forceinline__ void warp_round_prefix(const Smem &s, int r) {
     int carryS = 0, carryM = 0;
     for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         const int c = c0 + lane;
-        int slots = 0, words = 0;
+        int strips = 0, words = 0;
         if (c < c_hi) {
-            const int n = s.cnt[c];
-            const int T = (n + 31) >> 5;
+            const int T = (s.cnt[c] + 31) >> 5;
             const int te = min(T, t1);
-            const int j0 = 32 * t0, j1 = min(n, 32 * te);
-            if (j1 > j0) {
-                slots = (j1 - j0 + 1) >> 1;
+            if (te > t0) {
+                strips = te;  // every row tile below te has blocks in column tiles [max(rt,t0), te)
                 words = 32 * (tri(te) - tri(t0));
             }
         }
-        const int incS = warp_inclusive_scan(slots, lane);
+        const int incS = warp_inclusive_scan(strips, lane);
         const int incM = warp_inclusive_scan(words, lane);
         if (c < c_hi) {
-            s.slot[c] = carryS + incS - slots;
+            const int tb = carryS + incS - strips;
+            s.tbase[c] = tb;
             s.maskbase[c] = carryM + incM - words;
+            s.done[c] = 0;
+            for (int rt = 0; rt < strips; ++rt) s.tasks[tb + rt] = ((uint32_t)c << 16) | (uint32_t)rt;
         }
         carryS += __shfl_sync(kFullMask, incS, 31);
         carryM += __shfl_sync(kFullMask, incM, 31);
     }
     if (lane == 0) {
-        s.slot[c_hi] = carryS;
         s.misc[M_CLO] = c_lo; s.misc[M_CHI] = c_hi; s.misc[M_T0] = t0; s.misc[M_T1] = t1;
-        s.misc[M_SLOTS] = carryS;
+        s.misc[M_NTASK] = carryS;
         s.misc[M_CTR] = 0;
     }
     __syncwarp();
@@ -538,200 +546,148 @@ __device__ __forceinline__ void block_scan_buckets(const DNParams &p, const Smem
 // ---------------------------------------------------------------------------
 // P3/P4: class-major counting sort on score buckets, then rank inside the bucket:
 // the stable descending score sort of torchvision.ops.nms, per class
+// key = score order key (32) | class (16) | 0xffff - cell id (16)
 // ---------------------------------------------------------------------------
 template <int THREADS>
 __device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s) {
     for (int cid = threadIdx.x; cid < p.K; cid += THREADS) {
         const uint32_t ci = s.clsidx[cid];
         if (ci == 0xffffffffu) continue;
-        const Rec &r = s.rec[cid];
-        const float sc = __fmul_rn(r.score, r.conf);  // box.py:27 scores = col5*col4
+        const float2 cs = s.cs[cid];
+        const float sc = __fmul_rn(cs.y, cs.x);  // box.py:27 scores = col5*col4
+        const uint32_t c = ci >> 16;
         const unsigned long long key =
-            ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)cid);
-        s.key[s.cntb[(int)(ci >> 16) * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
+            ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)((c << 16) | (0xffffu - (uint32_t)cid));
+        s.key[s.cntb[(int)c * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
+        const float ta = s.ta[cid];
+        if (ta != ta) s.flag[c] = 1;  // degenerate box: the class runs the exact pair arithmetic
     }
 }
 
 template <int THREADS>
-__device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv, int sord_len) {
-    for (int t = threadIdx.x; t < sord_len; t += THREADS) {
-        if (t >= Kv) {
-            s.sord[t] = s.rec_saddr;  // padding: any valid record
-            continue;
-        }
+__device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv) {
+    for (int t = threadIdx.x; t < Kv; t += THREADS) {
         const unsigned long long key = s.key[t];
-        const uint32_t cid = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-        const Rec &r = s.rec[cid];
-        const int cq = (int)(s.clsidx[cid] >> 16) * p.B + score_bucket(__fmul_rn(r.score, r.conf), p.B);
+        const uint32_t lo32 = (uint32_t)key;
+        const uint32_t cid = 0xffffu - (lo32 & 0xffffu);
+        const int cq = (int)(lo32 >> 16) * p.B + score_bucket(order_key_to_float((uint32_t)(key >> 32)), p.B);
         const int st = s.cntb[cq], en = s.cntb[cq + 1];
         int rank = 0;
         for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
-        s.sord[st + rank] = s.rec_saddr + 32u * cid;
+        s.sord[st + rank] = (uint16_t)cid;
     }
 }
 
 // ---------------------------------------------------------------------------
-// P5: pair masks
+// P5: pair masks (row-major words: bit k of word (rt, ct)[lane] = row 32rt+lane suppresses
+// column 32ct+k) and the sweep
 // ---------------------------------------------------------------------------
-// exact torchvision decision for one pair (row record address, column box)
-__device__ __noinline__ bool pair_exact(uint32_t row_saddr, const float4 &cb, const IouThr &thr) {
-    const float4 rb = lds_box(row_saddr);
-    return nms_suppress_exact(rb, box_area(rb), cb, box_area(cb), thr);
+constexpr float kPairEps = 1e-5f;
+
+// exact torchvision decisions of one row against the columns of one tile (slow path)
+__device__ __noinline__ uint32_t block_exact(const float4 *box, const uint16_t *ordc, int ncol, const float4 R, double thr) {
+    const float ra = box_area(R);
+    uint32_t word = 0u;
+    for (int k = 0; k < ncol; ++k) {
+        const float4 Cb = box[ordc[k]];
+        if (nms_suppress_exact(R, ra, Cb, box_area(Cb), thr)) word |= 1u << k;
+    }
+    return word;
 }
 
-// one 16-row group for up to two columns; returns 16 result bits per column
-template <bool DO_A>
-__device__ __forceinline__ void pair_group16(const uint32_t *ord, const float4 &ca, float ca_hi, float ca_lo,
-                                             const float4 &cb, float cb_hi, float cb_lo, const IouThr &thr,
-                                             uint32_t &bitsA, uint32_t &bitsB) {
-    float aS = 0.f, aM = 0.f, bS = 0.f, bM = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        float4 R;
-        float2 T;
-        lds_rec(ord[k], R, T);
-        const float wk = (float)(1u << k);
-        {
-            const float w = fmaxf(__fsub_rn(fminf(R.z, cb.z), fmaxf(R.x, cb.x)), 0.0f);
-            const float h = __fsub_rn(fminf(R.w, cb.w), fmaxf(R.y, cb.y));
-            const float inter = __fmul_rn(w, h);
-            const float pS = (inter > __fadd_rn(T.x, cb_hi)) ? 1.0f : 0.0f;
-            const float pM = (inter > __fadd_rn(T.y, cb_lo)) ? 1.0f : 0.0f;
-            bS = __fmaf_rn(pS, wk, bS);
-            bM = __fmaf_rn(pM, wk, bM);
-        }
-        if (DO_A) {
-            const float w = fmaxf(__fsub_rn(fminf(R.z, ca.z), fmaxf(R.x, ca.x)), 0.0f);
-            const float h = __fsub_rn(fminf(R.w, ca.w), fmaxf(R.y, ca.y));
-            const float inter = __fmul_rn(w, h);
-            const float pS = (inter > __fadd_rn(T.x, ca_hi)) ? 1.0f : 0.0f;
-            const float pM = (inter > __fadd_rn(T.y, ca_lo)) ? 1.0f : 0.0f;
-            aS = __fmaf_rn(pS, wk, aS);
-            aM = __fmaf_rn(pM, wk, aM);
-        }
+__device__ __forceinline__ uint32_t block_fast(const Smem &s, const uint16_t *ordc, int ncol, const float4 R, float rta,
+                                               double thr) {
+    uint32_t bits = 0u;
+    float m = INFINITY;
+#pragma unroll 4
+    for (int k = 0; k < ncol; ++k) {
+        const int ccid = ordc[k];
+        const float4 Cb = s.box[ccid];
+        const float cta = s.ta[ccid];
+        const float w = __fsub_rn(fminf(R.z, Cb.z), fmaxf(R.x, Cb.x));
+        const float h = __fsub_rn(fminf(R.w, Cb.w), fmaxf(R.y, Cb.y));
+        const float ws = __saturatef(__fmul_rn(w, 1.220703125e-4f));  // max(w, 0) * 2^-13 (exact; |coords| < 4096)
+        const float sum = __fadd_rn(rta, cta);                         // t * (area_r + area_c) * 2^-13
+        const float d = __fmaf_rn(-ws, h, sum);                        // < 0  <=>  inter > t * (area sum)
+        m = fminf(m, __fmaf_rn(sum, -kPairEps, fabsf(d)));             // <= 0: too close to call
+        bits = __funnelshift_l(__float_as_uint(d), bits, 1);           // sign bit -> mask bit
     }
-    uint32_t uS = __float2uint_rn(bS), uM = __float2uint_rn(bM);
-    if (uS != uM) {  // pairs inside the guard band (or flagged boxes): exact arithmetic decides
-        for (uint32_t amb = uS ^ uM; amb;) {
-            const int k = __ffs(amb) - 1;
-            amb &= amb - 1u;
-            if (pair_exact(ord[k], cb, thr)) uS |= 1u << k; else uS &= ~(1u << k);
-        }
-    }
-    bitsB = uS;
-    if (DO_A) {
-        uS = __float2uint_rn(aS);
-        uM = __float2uint_rn(aM);
-        if (uS != uM) {
-            for (uint32_t amb = uS ^ uM; amb;) {
-                const int k = __ffs(amb) - 1;
-                amb &= amb - 1u;
-                if (pair_exact(ord[k], ca, thr)) uS |= 1u << k; else uS &= ~(1u << k);
-            }
-        }
-        bitsA = uS;
-    }
+    uint32_t word = __brev(bits) >> (32 - ncol);  // column k was shifted in k-th: bit ncol-1-k -> bit k
+    if (m <= 0.0f) word = block_exact(s.box, ordc, ncol, R, thr);
+    return word;
 }
 
-__device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
+// sweep of one class over the column tiles [t0, te) (earlier tiles' kept words are final)
+__device__ __forceinline__ void sweep_class(const Smem &s, int c, int t0, int te, int tri0) {
     const int lane = threadIdx.x & 31;
-    const int c_lo = s.misc[M_CLO], c_hi = s.misc[M_CHI], t0 = s.misc[M_T0], t1 = s.misc[M_T1];
-    const int total = s.misc[M_SLOTS];
+    const int n = s.cnt[c];
+    uint32_t *kept_w = s.keptbits + s.ktile[c];
+    const uint32_t *mb = s.mask + s.maskbase[c];
+    for (int ct = t0; ct < te; ++ct) {
+        const uint32_t *blk = mb + (tri(ct) - tri0) * 32 + lane;
+        uint32_t sup = 0u;
+        for (int rt = 0; rt < ct; ++rt) {
+            const uint32_t wv = blk[rt * 32];
+            if ((kept_w[rt] >> lane) & 1u) sup |= wv;
+        }
+        sup = __reduce_or_sync(kFullMask, sup);
+        const int ncol = min(32, n - 32 * ct);
+        const uint32_t valid = (ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u);
+        const uint32_t alive = valid & ~sup;
+        // diagonal block: only rows that are alive and suppress an alive column need a turn
+        const uint32_t D = ((alive >> lane) & 1u) ? (blk[ct * 32] & alive) : 0u;
+        uint32_t nz = __ballot_sync(kFullMask, D != 0u);
+        uint32_t rem = alive;
+        while (nz) {
+            const int i = __ffs(nz) - 1;
+            nz &= nz - 1u;
+            const uint32_t Di = __shfl_sync(kFullMask, D, i);
+            if ((rem >> i) & 1u) rem &= ~Di;
+        }
+        if (lane == 0) kept_w[ct] = rem;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void phase_pairs_sweep(const DNParams &p, const Smem &s) {
+    const int lane = threadIdx.x & 31;
+    const int t0 = s.misc[M_T0], t1 = s.misc[M_T1];
+    const int ntask = s.misc[M_NTASK];
     const int tri0 = tri(t0);
     for (;;) {
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&s.misc[M_CTR], 1);
-        chunk = __shfl_sync(kFullMask, chunk, 0);
-        if (chunk * 32 >= total) break;
-        const int slot = chunk * 32 + lane;
-        const bool act = slot < total;
-        int lo = c_lo, hi = c_hi;  // largest c in [c_lo, c_hi) with slot[c] <= slot
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s.slot[mid] <= slot) lo = mid; else hi = mid;
-        }
-        const int c = lo;
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&s.misc[M_CTR], 1);
+        q = __shfl_sync(kFullMask, q, 0);
+        if (q >= ntask) break;
+        const uint32_t tk = s.tasks[q];
+        const int c = (int)(tk >> 16), rt = (int)(tk & 0xffffu);
         const int n = s.cnt[c];
-        const int rowbase = s.start[c];
-        const int j0 = 32 * t0, j1 = min(n, 32 * min((n + 31) >> 5, t1));
-        const int h = slot - s.slot[c];
-        const int jA = j0 + h, jB = j1 - 1 - h;   // the short and the long column of this lane
-        const bool hasA = act && jA < jB;
-        const int tripA = hasA ? jA : 0, tripB = act ? jB : 0;  // rows 0..trip-1 precede the column
-        const uint32_t *ord = s.sord + rowbase;
-        float4 ca, cb;
-        float2 ta, tb;
-        lds_rec(ord[hasA ? jA : 0], ca, ta);
-        lds_rec(ord[act ? jB : 0], cb, tb);
-        const int maxA = __reduce_max_sync(kFullMask, tripA), maxB = __reduce_max_sync(kFullMask, tripB);
-        const int ngA = (maxA + 15) >> 4, ngB = (maxB + 15) >> 4;  // 16-row groups
-        const int ctA = jA >> 5, ctB = jB >> 5;
-        uint32_t *mA = s.mask + s.maskbase[c] + (tri(ctA) - tri0) * 32 + (jA & 31);
-        uint32_t *mB = s.mask + s.maskbase[c] + (tri(ctB) - tri0) * 32 + (jB & 31);
-        uint32_t wA = 0u, wB = 0u;
-        for (int g = 0; g < ngB; ++g) {
-            uint32_t a16 = 0u, b16;
-            if (g < ngA) pair_group16<true>(ord + 16 * g, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a16, b16);
-            else pair_group16<false>(ord + 16 * g, ca, ta.x, ta.y, cb, tb.x, tb.y, p.iou, a16, b16);
-            if (!(g & 1)) {
-                wA = a16;
-                wB = b16;
-                if (g + 1 < ngB) continue;
-            } else {
-                wA |= a16 << 16;
-                wB |= b16 << 16;
-            }
-            // rows >= the column index (own bit, later rows, other classes) are masked off
-            const int w = g >> 1;
-            if (act && w <= ctB) mB[w * 32] = (w == ctB) ? (wB & ((1u << (jB & 31)) - 1u)) : wB;
-            if (hasA && w <= ctA) mA[w * 32] = (w == ctA) ? (wA & ((1u << (jA & 31)) - 1u)) : wA;
+        const int te = min((n + 31) >> 5, t1);
+        const uint16_t *ord = s.sord + s.start[c];
+        const int row = 32 * rt + lane;
+        const int rcid = ord[min(row, n - 1)];
+        const float4 R = s.box[rcid];
+        const float rta = s.ta[rcid];
+        const bool slow = s.flag[c] != 0;
+        uint32_t *mb = s.mask + s.maskbase[c];
+        for (int ct = max(rt, t0); ct < te; ++ct) {
+            const int ncol = min(32, n - 32 * ct);
+            uint32_t word = slow ? block_exact(s.box, ord + 32 * ct, ncol, R, p.iou.thr)
+                                 : block_fast(s, ord + 32 * ct, ncol, R, rta, p.iou.thr);
+            if (ct == rt) word &= ~((2u << lane) - 1u);  // only LATER columns (2u << 31 == 0: none)
+            if (row >= n) word = 0u;
+            mb[(tri(ct) - tri0 + rt) * 32 + lane] = word;
         }
-        // ceil(j/32) row words were computed; the diagonal word of a column with
-        // j % 32 == 0 holds no earlier row and may lie beyond the warp's loop
-        const int nwB = (ngB + 1) >> 1;
-        if (act && nwB <= ctB) mB[ctB * 32] = 0u;
-        if (hasA && nwB <= ctA) mA[ctA * 32] = 0u;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// P6: sweep -- one warp per class, 32-column tiles in score order
-// ---------------------------------------------------------------------------
-template <int THREADS>
-__device__ __forceinline__ void phase_sweep(const Smem &s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c_lo = s.misc[M_CLO], c_hi = s.misc[M_CHI], t0 = s.misc[M_T0], t1 = s.misc[M_T1];
-    const int tri0 = tri(t0);
-    for (int c = c_lo + warp; c < c_hi; c += THREADS / 32) {
-        const int n = s.cnt[c];
-        const int T = (n + 31) >> 5;
-        const int te = min(T, t1);
-        uint32_t *kept_w = s.keptbits + s.ktile[c];
-        const uint32_t *mbase = s.mask + s.maskbase[c];
-        for (int ct = t0; ct < te; ++ct) {
-            const int j = 32 * ct + lane;
-            const uint32_t *col = mbase + (tri(ct) - tri0) * 32 + lane;
-            uint32_t sup = 0u;
-#pragma unroll 2
-            for (int rt = 0; rt < ct; ++rt) sup |= col[rt * 32] & kept_w[rt];
-            const bool alive = (j < n) && (sup == 0u);
-            const unsigned alive_mask = __ballot_sync(kFullMask, alive);
-            const uint32_t diag = alive ? (col[ct * 32] & alive_mask) : 0u;
-            const unsigned nz = __ballot_sync(kFullMask, diag != 0u);
-            // columns without any alive earlier overlap are kept outright; the rest are
-            // decided in parallel as soon as all their earlier overlaps are decided (the
-            // lowest undecided column always is, so every pass makes progress)
-            unsigned kept = alive_mask & ~nz;
-            for (unsigned und = nz; und;) {
-                const bool mine = (und >> lane) & 1u;
-                const bool dead = mine && (diag & kept) != 0u;
-                const bool keep = mine && !dead && (diag & und) == 0u;
-                const unsigned d = __ballot_sync(kFullMask, dead), k = __ballot_sync(kFullMask, keep);
-                kept |= k;
-                und &= ~(d | k);
-            }
-            if (lane == 0) kept_w[ct] = kept;
-            __syncwarp();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            old = atomicAdd(&s.done[c], 1);
+        }
+        old = __shfl_sync(kFullMask, old, 0);
+        if (old == te - 1) {  // last strip of the class in this round: its masks are complete
+            __threadfence_block();
+            sweep_class(s, c, t0, te, tri0);
         }
     }
 }
@@ -742,7 +698,7 @@ __device__ __forceinline__ void phase_sweep(const Smem &s) {
 template <int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve(smem_raw, L, p.C, MODE);
+    const Smem s = carve(smem_raw, L, p.K, p.C, MODE);
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.C, K = p.K;
@@ -750,11 +706,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
 
     stamp(p, b, 0);
     if (MODE != MODE_NMS) {
-        // one thread per (head, anchor) slab: start the HBM -> L2 stream of this image now
+        // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
+        // only issue after the launch ramp) finds its lines on the way.  Prefetching the whole image
+        // is slower: the demand loads then queue behind 46 MB of prefetches (profiles/r01/NOTES.md).
         if (tid == 0 && !(p.flags & 1)) {
             const size_t img0 = (size_t)p.A * p.attrs * p.head[0].HW;
             l2_prefetch_span(p.head[0].ptr + (size_t)b * img0, img0 * sizeof(float));
-            if (p.nheads > 1 && !(p.flags & 2)) {
+            if (p.nheads > 1 && (p.flags & 8)) {
                 const size_t img1 = (size_t)p.A * p.attrs * p.head[1].HW;
                 l2_prefetch_span(p.head[1].ptr + (size_t)b * img1, img1 * sizeof(float));
             }
@@ -762,6 +720,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     }
     if (MODE != MODE_DECODE) {
         for (int i = tid; i <= C * p.B; i += THREADS) s.cntb[i] = 0;
+        for (int i = tid; i <= C; i += THREADS) s.flag[i] = 0;
         __syncthreads();
     }
     stamp(p, b, 15);
@@ -794,11 +753,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         __syncthreads();
         const int T = s.misc[M_TOTAL];
         float *o = p.out + (size_t)b * K * 7;
-        const float *recf = reinterpret_cast<const float *>(s.rec);
+        const float *boxf = reinterpret_cast<const float *>(s.box);
+        const float *csf = reinterpret_cast<const float *>(s.cs);
         for (int f = tid; f < 7 * T; f += THREADS) {
             const int row = f / 7, col = f - 7 * row;
             const int cid = s.outsrc[row];
-            o[f] = (col < 6) ? recf[8 * cid + col] : (float)(s.clsidx[cid] >> 16);  // cls_idx.float() :199
+            o[f] = (col < 4) ? boxf[4 * cid + col] : (col < 6) ? csf[2 * cid + col - 4] : (float)(s.clsidx[cid] >> 16);  // cls_idx.float() :199
         }
         if (p.out_idx)
             for (int r = tid; r < T; r += THREADS) p.out_idx[(size_t)b * K + r] = (int)s.outsrc[r];
@@ -810,7 +770,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     block_scan_buckets<THREADS>(p, s);
     __syncthreads();
     if (warp == 0) {
-        warp_class_scan(p, s);
+        warp_class_scan(p, s, (int)L.mask_words);
         warp_round_prefix(s, 0);
     }
     phase_scatter_keys<THREADS>(p, s);
@@ -819,24 +779,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     const int Kv = s.misc[M_KV];
     const int nrounds = s.misc[M_NROUNDS];
     // P4
-    phase_rank_sort<THREADS>(p, s, Kv, 2 * (int)align_up((uint32_t)K, 32) + 64);
+    phase_rank_sort<THREADS>(p, s, Kv);
     __syncthreads();
     stamp(p, b, 3);
-    // P5, P6
+    // P5
     for (int r = 0;;) {
-        phase_pairs(p, s);
+        phase_pairs_sweep(p, s);
         __syncthreads();
-        stamp(p, b, 4);
-        phase_sweep<THREADS>(s);
-        __syncthreads();
-        stamp(p, b, 5);
         if (++r >= nrounds) break;
         if (warp == 0) warp_round_prefix(s, r);
         __syncthreads();
     }
-    // P7/P8: output row -> cell id (the mask buffer is dead now; outsrc aliases it).  Every
+    stamp(p, b, 4);
+    stamp(p, b, 5);
+    // P6: output row -> cell id (the mask buffer is dead now; outsrc aliases it).  Every
     // warp sums the kept counts of the tiles before its class itself (no serial scan phase).
-    const int ntiles = s.ktile[C];
     for (int c = warp; c <= C; c += kWarps) {
         const int kt = s.ktile[c];
         int before = 0;
@@ -851,20 +808,19 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         for (int ct = 0; 32 * ct < n; ++ct) {
             const uint32_t word = s.keptbits[kt + ct];
             if ((word >> lane) & 1u) {
-                const uint32_t cid = (s.sord[st + 32 * ct + lane] - s.rec_saddr) >> 5;
-                s.outsrc[before + __popc(word & lanemask_lt())] = (uint16_t)cid;
+                const int r = before + __popc(word & lanemask_lt());
+                s.outsrc[r] = s.sord[st + 32 * ct + lane];
+                s.outcls[r] = (uint16_t)c;
             }
             before += __popc(word);
         }
     }
-    (void)ntiles;
     __syncthreads();
     stamp(p, b, 6);
-    // P9: flat coalesced store
+    // flat coalesced store
     {
         const int T = s.misc[M_TOTAL];
         float *o = p.out + (size_t)b * K * 7;
-        const float *recf = reinterpret_cast<const float *>(s.rec);
         if (MODE == MODE_NMS) {
             // gather the caller's own row (pred_this_cls[index], box.py:29) bit-for-bit
             const int K0 = min(p.cand_count[0][b], p.cand_stride[0]);
@@ -876,10 +832,16 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
                 o[f] = (k < K0) ? __ldg(r0 + (size_t)k * 7 + col) : __ldg(r1 + (size_t)(k - K0) * 7 + col);
             }
         } else {
+            const float *boxf = reinterpret_cast<const float *>(s.box);
+            const float *csf = reinterpret_cast<const float *>(s.cs);
             for (int f = tid; f < 7 * T; f += THREADS) {
                 const int row = f / 7, col = f - 7 * row;
                 const int cid = s.outsrc[row];
-                o[f] = (col < 6) ? recf[8 * cid + col] : (float)(s.clsidx[cid] >> 16);
+                float v;
+                if (col < 4) v = boxf[4 * cid + col];
+                else if (col < 6) v = csf[2 * cid + col - 4];
+                else v = (float)s.outcls[row];
+                o[f] = v;
             }
         }
         if (p.out_idx)

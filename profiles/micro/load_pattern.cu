@@ -167,11 +167,74 @@ __global__ void __launch_bounds__(512, 2) k_tma(const float *h0, const float *h1
     if (acc == 12345.678f) out[b * blockDim.x + tid] = acc;
 }
 
+
+// ---- variant 4: plane-major stages.  One bulk copy per stage = a CONTIGUOUS run of whole planes of one
+// (image, anchor) slab (16-byte-aligned superset of it), S-slot ring, thread per cell keeps a running value.
+template <int S, int SLOT>
+__global__ void __launch_bounds__(512, 2) k_planes(const float *h0, const float *h1, int HW0, int HW1, float *out) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + S * SLOT);  // full[S], empty[S]
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(saddr(&bars[i]), 1); mbar_init(saddr(&bars[S + i]), 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int G1 = max(1, min(25, (SLOT - 32) / (HW1 * 4)));   // planes per stage, head 1
+    const int G0 = max(1, min(25, (SLOT - 32) / (HW0 * 4)));
+    const int per0 = (25 + G0 - 1) / G0, per1 = (25 + G1 - 1) / G1;
+    const int nst = 3 * per0 + 3 * per1;
+    auto stage_desc = [&](int st, const float *&src, int &planes, int &HW) {
+        if (st < 3 * per0) {
+            const int a = st / per0, g = st - a * per0;
+            HW = HW0; planes = min(G0, 25 - g * G0);
+            src = h0 + ((size_t)(b * 3 + a) * 25 + g * G0) * HW0;
+        } else {
+            st -= 3 * per0;
+            const int a = st / per1, g = st - a * per1;
+            HW = HW1; planes = min(G1, 25 - g * G1);
+            src = h1 + ((size_t)(b * 3 + a) * 25 + g * G1) * HW1;
+        }
+    };
+    auto issue = [&](int st) {
+        const float *src; int planes, HW;
+        stage_desc(st, src, planes, HW);
+        const uintptr_t lo = (uintptr_t)src & ~(uintptr_t)15, hi = ((uintptr_t)(src + (size_t)planes * HW) + 15) & ~(uintptr_t)15;
+        const uint32_t full = saddr(&bars[st % S]);
+        mbar_expect_tx(full, (uint32_t)(hi - lo));
+        bulk_g2s(saddr(sm + (st % S) * SLOT), (const void *)lo, (uint32_t)(hi - lo), full);
+    };
+    float acc = 0.f, m = -1e30f;
+    if (tid == 0) for (int st = 0; st < min(S - 1, nst); ++st) issue(st);
+    for (int st = 0; st < nst; ++st) {
+        const int slot = st % S, use = st / S;
+        if (tid == 0) {
+            const int nx = st + S - 1;
+            if (nx < nst) {
+                const int nslot = nx % S, nuse = nx / S;
+                if (nuse > 0) mbar_wait(saddr(&bars[S + nslot]), (uint32_t)((nuse - 1) & 1));
+                issue(nx);
+            }
+        }
+        const float *src; int planes, HW;
+        stage_desc(st, src, planes, HW);
+        mbar_wait(saddr(&bars[slot]), (uint32_t)(use & 1));
+        const float *stg = reinterpret_cast<const float *>(sm + slot * SLOT + ((uintptr_t)src & 15));
+        if (tid < HW) {
+            for (int u = 0; u < planes; ++u) m = fmaxf(m, stg[u * HW + tid]);
+        }
+        acc += m;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(saddr(&bars[S + slot]));
+    }
+    if (acc == 12345.678f) out[b * blockDim.x + tid] = acc;
+}
+
 int main(int argc, char **argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 256, HW0 = 121, HW1 = 484, R = 9;
     std::vector<float *> h0(R), h1(R);
     for (int r = 0; r < R; ++r) {
-        CK(cudaMalloc(&h0[r], (size_t)N * 75 * HW0 * 4));
+        CK(cudaMalloc(&h0[r], (size_t)N * 75 * HW0 * 4 + 64));
         CK(cudaMalloc(&h1[r], (size_t)N * 75 * HW1 * 4));
         CK(cudaMemset(h0[r], 0, (size_t)N * 75 * HW0 * 4));
         CK(cudaMemset(h1[r], 0, (size_t)N * 75 * HW1 * 4));
@@ -209,6 +272,13 @@ int main(int argc, char **argv) {
     run("tma ring G=5 S=4 (2 CTA/SM)", k_tma<5, 4>, 512, half);
     run("tma ring G=5 S=6 (2 CTA/SM)", k_tma<5, 6>, 512, half);
     run("tma ring G=25 S=2 (2 CTA/SM)", k_tma<25, 2>, 512, half);
+    run("planes S=3 slot 12.2K (2 CTA/SM, 113K)", k_planes<3, 12544>, 512, half);
+    run("planes S=4 slot 12.2K (2 CTA/SM, 113K)", k_planes<4, 12544>, 512, half);
+    run("planes S=3 slot 12.2K (smem 40K)", k_planes<3, 12544>, 512, 40 * 1024);
+    run("planes S=6 slot 12.2K (2 CTA/SM, 113K)", k_planes<6, 12544>, 512, half);
+    run("planes S=2 slot 24.3K (2 CTA/SM, 113K)", k_planes<2, 24832>, 512, half);
+    run("planes S=3 slot 24.3K (2 CTA/SM, 113K)", k_planes<3, 24832>, 512, half);
+    run("planes S=8 slot 6.2K (2 CTA/SM, 113K)", k_planes<8, 6400>, 512, half);
     run("flat float4 (2 CTA/SM)", k_flat, 512, half);
     run("flat float4 x8 (2 CTA/SM)", k_flat8, 512, half);
     run("flat float4 x8 (no smem limit)", k_flat8, 512, 1024);
