@@ -57,6 +57,11 @@ unsigned long long b200yolo_launch_count(void);
  * boundaries for every image.  NULL (the default) disables it. */
 void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
 
+/* Experiment / test switches of the fused kernel (initialised from the B200YOLO_FLAGS
+ * environment variable): 1 = no L2 prefetch of head 0, 8 = prefetch both heads, 16 = never
+ * use the compile-time head shapes (every shape then runs the runtime-stride decode). */
+void b200yolo_debug_set_flags(int flags);
+
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that
  * the fused / NMS kernels can stage in one CTA's shared memory on `device`. */
 int b200yolo_max_cells(int device);

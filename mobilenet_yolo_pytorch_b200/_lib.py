@@ -25,6 +25,7 @@ SIGNATURES = {
     "b200yolo_launch_count": (C.c_ulonglong, []),
     "b200yolo_max_cells": (C.c_int, [C.c_int]),
     "b200yolo_debug_phase_stamps": (None, [C.c_void_p]),
+    "b200yolo_debug_set_flags": (None, [C.c_int]),
     "b200yolo_decode_head": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_float,
                                        c_f32p, c_i32p, c_i32p, C.c_void_p]),
     "b200yolo_nms": (C.c_int, [c_f32p, c_i32p, C.c_int, c_f32p, c_i32p, C.c_int, C.c_int, C.c_int, C.c_double,

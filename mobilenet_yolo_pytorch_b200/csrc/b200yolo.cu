@@ -22,6 +22,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long *> g_dbg{nullptr};  // profiling aid, see b200yolo_debug_phase_stamps
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_flags{[] { const char *e = getenv("B200YOLO_FLAGS"); return e ? atoi(e) : 0; }()};  // experiment switches
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -93,22 +94,40 @@ constexpr int kTier2x64 = 80 * 1024;
 constexpr int kTier2x0 = (228 * 1024) / 2 - 1024;
 constexpr int kTier1x64 = 162 * 1024;
 
-template <int MODE, int THREADS>
+template <int MODE, int THREADS, int SHAPE>
 int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     static std::mutex mu;
     static int configured[64] = {0};  // smem size opted into, per device
     {
         std::lock_guard<std::mutex> g(mu);
         if (dev < 64 && configured[dev] < (int)L.total) {
-            CUDA_TRY(cudaFuncSetAttribute(decode_nms_kernel<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CUDA_TRY(cudaFuncSetAttribute(decode_nms_kernel<MODE, THREADS, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           smem_optin(dev)));
             configured[dev] = smem_optin(dev);
         }
     }
-    decode_nms_kernel<MODE, THREADS><<<p.N, THREADS, L.total, st>>>(p, L);
+    decode_nms_kernel<MODE, THREADS, SHAPE><<<p.N, THREADS, L.total, st>>>(p, L);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// compile-time head shapes of the fused kernel (decode_nms.cuh, ShapeT): the reference's own configurations
+template <int S>
+bool shape_is(const DNParams &p) {
+    using SH = ShapeT<S>;
+    return p.nheads == 2 && p.C == SH::C && p.head[0].HW == SH::HW0 && p.head[0].W == SH::W0 && p.head[1].HW == SH::HW1 &&
+           p.head[1].W == SH::W1;
+}
+
+template <int MODE, int THREADS>
+int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
+    if (MODE == MODE_FUSED && !(p.flags & 16)) {  // flag 16: force the runtime-shape path (tests)
+        if (THREADS == 512 && shape_is<1>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 1 : 0>(p, L, dev, st);
+        if (THREADS == 512 && shape_is<2>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 2 : 0>(p, L, dev, st);
+        if (THREADS == 1024 && shape_is<3>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 1024) ? 3 : 0>(p, L, dev, st);
+    }
+    return launch_dn_t<MODE, THREADS, 0>(p, L, dev, st);
 }
 
 template <int MODE>
@@ -116,29 +135,24 @@ int launch_dn(DNParams &p, cudaStream_t st) {
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;
     const int lim = smem_optin(dev);
-    const SmemLayout base = make_layout(p.K, p.C, MODE, 0);
-    if ((int)base.total > lim)
+    const SmemLayout base1k = make_layout(p.K, p.C, MODE, 1024, 0);
+    if ((int)base1k.total > lim)
         return fail(B200YOLO_EUNSUPPORTED,
                     "%d candidate cells per image with %d classes need %u B of shared memory (limit %d B)", p.K, p.C,
-                    base.total, lim);
+                    base1k.total, lim);
     if (p.N == 0) return 0;
     p.B = pick_buckets(p.C);
     p.dbg = g_dbg.load();
-    {
-        static const int env_flags = [] { const char *e = getenv("B200YOLO_FLAGS"); return e ? atoi(e) : 0; }();
-        p.flags = env_flags;
-    }
-    const int need = (int)base.total;
-    int budget = lim;
-    bool two = false;
-    if (need <= kTier2x64 && kTier2x64 <= lim) { budget = kTier2x64; two = true; }
-    else if (need <= kTier2x0 && kTier2x0 <= lim) { budget = kTier2x0; two = true; }
-    else if (need <= kTier1x64 && kTier1x64 <= lim) budget = kTier1x64;
-    if (p.flags & 4) { budget = (need <= kTier2x0 && kTier2x0 <= lim) ? kTier2x0 : lim; }  // experiment: old sizing
+    p.flags = g_flags.load();
+    const int need512 = (int)make_layout(p.K, p.C, MODE, 512, 0).total;
+    const int need = (int)base1k.total;
     // the pair masks get whatever the tier leaves (MODE_DECODE has none)
-    const SmemLayout L = (MODE == MODE_DECODE) ? base : make_layout(p.K, p.C, MODE, (uint32_t)(budget - need));
-    if (two) return launch_dn_t<MODE, 512>(p, L, dev, st);
-    return launch_dn_t<MODE, 1024>(p, L, dev, st);
+    if (need512 <= kTier2x64 && kTier2x64 <= lim)
+        return launch_dn_shape<MODE, 512>(p, make_layout(p.K, p.C, MODE, 512, (MODE == MODE_DECODE) ? 0u : (uint32_t)(kTier2x64 - need512)), dev, st);
+    if (need512 <= kTier2x0 && kTier2x0 <= lim)
+        return launch_dn_shape<MODE, 512>(p, make_layout(p.K, p.C, MODE, 512, (MODE == MODE_DECODE) ? 0u : (uint32_t)(kTier2x0 - need512)), dev, st);
+    const int budget = (need <= kTier1x64 && kTier1x64 <= lim) ? kTier1x64 : lim;
+    return launch_dn_shape<MODE, 1024>(p, make_layout(p.K, p.C, MODE, 1024, (MODE == MODE_DECODE) ? 0u : (uint32_t)(budget - need)), dev, st);
 }
 
 }  // namespace
@@ -150,13 +164,14 @@ const char *b200yolo_last_error(void) { return g_err; }
 unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
 
 void b200yolo_debug_phase_stamps(unsigned long long *dev_buf) { g_dbg.store(dev_buf); }
+void b200yolo_debug_set_flags(int flags) { g_flags.store(flags); }
 
 int b200yolo_max_cells(int device) {
     const int lim = smem_optin(device);
     int lo = 0, hi = 1 << 16;
     while (lo < hi) {  // largest K whose fused layout fits (C = 80 as a conservative class count)
         int mid = (lo + hi + 1) / 2;
-        if ((int)make_layout(mid, 80, MODE_FUSED, 0).total <= lim) lo = mid; else hi = mid - 1;
+        if ((int)make_layout(mid, 80, MODE_FUSED, 1024, 0).total <= lim) lo = mid; else hi = mid - 1;
     }
     return lo;
 }

@@ -16,12 +16,23 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // IEEE (round-to-nearest) divide.
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// Inference decode (YOLOLoss.get_pred_boxes) uses the SFU forms: ex2.approx + rcp.approx,
-// <= ~4 ulp + |x|*6e-8 relative, well inside the 1e-5 contract on decoded floats; it is
-// ~20 instructions cheaper per transcendental than the IEEE forms above, and the decode
-// phase is issue-bound.  The training path (target_loss.cuh) keeps the IEEE forms.
-__device__ __forceinline__ float exp_fast(float x) { return __expf(x); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x))); }
+// Inference decode (YOLOLoss.get_pred_boxes) uses the SFU forms directly: ex2.approx.ftz and
+// rcp.approx.ftz are one MUFU instruction each (no range fix-ups; results below 2^-126 flush to
+// zero), <= ~4 ulp + |x|*6e-8 relative, well inside the 1e-5 contract on decoded floats.  The decode
+// phase is issue-bound, and the IEEE forms above cost ~20 instructions more per transcendental.
+// The training path (target_loss.cuh) keeps the IEEE forms.
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(__fmul_rn(x, 1.4426950408889634f)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(__fadd_rn(1.0f, ex2_fast(__fmul_rn(x, -1.4426950408889634f)))); }
 
 __device__ __forceinline__ float ldg_f(const float *p) { return __ldg(p); }
 

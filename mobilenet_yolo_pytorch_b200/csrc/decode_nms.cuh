@@ -7,20 +7,27 @@
 // the decode phase streams the heads with ordinary coalesced loads whose in-flight
 // lines live in L1, and L1 is what the CTAs' shared memory leaves of the SM's 228 KB
 // (profiles/micro/load_pattern.cu: the same load pattern runs at 4.3 TB/s with 64 KB of
-// L1 and at 2.9 TB/s with none).  So: structure-of-arrays records, and one region `U`
-// that is reused by phase (class/arrival index + sort keys -> sorted order + pair masks
-// -> output order).
+// L1 and at 2.9 TB/s with none).  So: structure-of-arrays records by cell id (box 16 B,
+// conf/score 8 B) and one region `U` that is reused by phase.
+//
+// The kernel is issue-bound once the heads are in (profiles/r01: 0.67 of the issue
+// slots used while an SM is active), so every phase is written for instruction count:
 //
 //   P1 decode     thread per cell, ALL 5+C attribute planes of the cell loaded at
 //                 once (coalesced: consecutive lanes = consecutive cells of a plane).
+//                 The reference's shapes (VOC 352 / 416, BDD 640x384) are compiled with
+//                 the plane stride as a constant, so the 5+C loads are one base register
+//                 plus immediates; any other shape takes the runtime-stride path.
 //                 conf = sigmoid(tc) > thr (yolo_loss.py:189,201); for passing cells:
-//                 class max / argmax (:198), box (:186-196,243-247) -> box[], cs[], ta[],
+//                 class max / argmax (:198), box (:186-196,243-247) -> box[], cs[],
 //                 and the per-(class, score bucket) arrival index (one shared atomic).
 //   P2 scans      exclusive scan of the (class, bucket) histogram -> class segments
 //                 (box.py:20-22), kept-bitmap tiles, the round table.
 //   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort of
 //                 torchvision.ops.nms) into their (class, bucket) segment.
-//   P4 rank       rank inside the bucket -> `sord` (sorted position -> cell id).
+//   P4 rank       rank inside the bucket -> `sord`: sorted position -> {shared-memory
+//                 address of the box, t * area}.  The pair loop then needs two loads and no
+//                 address arithmetic per column.
 //   P5 pairs+sweep  dynamic warp tasks.  A task is one 32-row strip of one class: the
 //                 lane keeps its row's box in registers and walks the later columns
 //                 (broadcast from shared memory), 32 columns per mask word.  The test is
@@ -32,8 +39,10 @@
 //                 strip of a class sweeps it at once (no block barrier): per 32-column
 //                 tile, OR the mask words of the kept earlier rows, then resolve the
 //                 diagonal block by walking only the rows that suppress something.
-//   P6 output     class-ascending / score-descending rows (box.py:29-30): scan of the
-//                 kept bitmap, then a flat coalesced store.
+//   P6 output     class-ascending / score-descending rows (box.py:29-30).  A warp owns
+//                 32-column tiles of the kept bitmap: the rows of a tile are consecutive
+//                 in the output, so the warp assembles them in a 896-byte scratch and
+//                 stores them with coalesced 4-byte stores.
 //
 // If the masks of all classes do not fit `U`, P5 runs in rounds (groups of whole
 // classes, or column-tile chunks of one huge class) with a block barrier in between.
@@ -49,6 +58,13 @@ constexpr int kMaxAnchors = 8;
 
 enum { MODE_FUSED = 0, MODE_DECODE = 1, MODE_NMS = 2 };
 
+// Compile-time head shapes (0 = runtime).  SHAPE ids are chosen by the host from (C, H, W) of both heads.
+template <int SHAPE> struct ShapeT { static constexpr int C = 0, HW0 = 0, W0 = 0, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<1> { static constexpr int C = 20, HW0 = 121, W0 = 11, HW1 = 484, W1 = 22; };  // VOC 352x352 (models/voc/config.yaml)
+template <> struct ShapeT<2> { static constexpr int C = 20, HW0 = 169, W0 = 13, HW1 = 676, W1 = 26; };  // 416x416 (inference.py:112)
+template <> struct ShapeT<3> { static constexpr int C = 10, HW0 = 240, W0 = 20, HW1 = 960, W1 = 40; };  // BDD100k 640x384, 10 classes
+constexpr int kNumShapes = 4;
+
 struct HeadDesc {
     const float *ptr;
     int H, W, HW, cells;         // cells = A*H*W
@@ -63,7 +79,7 @@ struct DNParams {
     int N, A, C, attrs;
     int K;               // candidate slots per image = row stride of out / out_idx
     int B;               // score buckets per class of the counting sort (power of two)
-    int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads, 4 = old smem sizing
+    int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads
     unsigned long long *dbg;  // optional [N][16] phase time stamps (ns, globaltimer), NULL in production
     float conf_thr;
     IouThr iou;
@@ -77,9 +93,9 @@ struct DNParams {
 };
 
 struct SmemLayout {
-    uint32_t box, cs, ta, cntb, cls, tasks, keptbits, tilepref, passbits, rounds, misc, U, total;
+    uint32_t box, cs, cntb, cls, tasks, tilecls, keptbits, tilepref, passbits, rounds, misc, U, total;
     uint32_t u_bytes;     // bytes in U
-    uint32_t mask_off;    // masks / output order start here (after sord)
+    uint32_t mask_off;    // keys, then pair masks, then the output scratch start here (after sord)
     uint32_t mask_words;  // 32-bit words available for pair masks
 };
 
@@ -90,19 +106,21 @@ enum { CA_CNT = 0, CA_START, CA_KTILE, CA_MASK, CA_TBASE, CA_DONE, CA_FLAG, CA_N
 // misc ints
 enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_NTASK, M_CTR, M_TOTAL, M_KV, M_WSUM = 16, M_NUM = 16 + 32 };
 
-// score buckets per class: C*B counters, at most 2048 (8 KB)
+// score buckets per class: C*B counters, at most 1536 (6 KB)
 __host__ __device__ inline int pick_buckets(int C) {
     int B = 64;
     while (B > 1 && C * B > 1536) B >>= 1;
     return B;
 }
 
+constexpr uint32_t kScratchPerWarp = 32 * 7 * 4;  // P6: 32 output rows of 7 floats
+
 // U region by phase (Kp = K rounded up to 32):
-//   decode .. key scatter   clsidx u32[Kp] | key u64[Kp]
-//   rank .. sweep           sord u16[Kp+32] | pair masks u32[mask_words]
-//   output                  sord            | outsrc u16[Kp] | outcls u16[Kp]
-//   (MODE_DECODE)           clsidx u32[Kp]  | outsrc u16[Kp]
-__host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32_t extra_mask_bytes) {
+//   decode .. key scatter   clsidx u32[Kp] ........ | key u64[Kp]
+//   rank .. sweep           sord uint2[Kp] ........ | (key, dead after rank) pair masks u32[mask_words]
+//   output                  sord .................. | per-warp row scratch
+//   (MODE_DECODE)           clsidx u32[Kp] | outsrc u16[Kp]
+__host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int threads, uint32_t extra_mask_bytes) {
     SmemLayout L;
     const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
     const uint32_t Cp = align_up((uint32_t)C + 1, 4);
@@ -111,20 +129,23 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32
     uint32_t o = 0;
     L.box = o; o += 16 * Kp;
     L.cs = o; o += 8 * Kp;
-    L.ta = o; o += nms ? 4 * Kp : 0;
     L.cntb = o; o += nms ? 4 * align_up((uint32_t)(C * pick_buckets(C)) + 1, 4) : 0;
     L.cls = o; o += nms ? 4 * Cp * CA_NUM : 0;
     L.tasks = o; o += nms ? 4 * tiles : 0;
     L.keptbits = o; o += nms ? 4 * tiles : 0;
-    L.tilepref = o; o += 4 * (tiles + 1);
+    L.tilepref = o; o += nms ? 0 : 4 * (tiles + 1);
     L.passbits = o; o += nms ? 0 : 4 * (Kp / 32);
+    L.tilecls = o; o += nms ? align_up(2 * tiles, 4) : 0;
     o = align_up(o, 8);
     L.rounds = o; o += nms ? 8 * (tiles + (uint32_t)C + 2) : 0;
     L.misc = o; o += 4 * M_NUM;
     o = align_up(o, 16);
     L.U = o;
-    L.u_bytes = nms ? 12 * Kp + (extra_mask_bytes & ~15u) : 6 * Kp;
-    const uint32_t sord_bytes = nms ? align_up(2 * (Kp + 32), 16) : 4 * Kp;
+    const uint32_t scratch = (uint32_t)(threads / 32) * kScratchPerWarp;
+    uint32_t tail = 8 * Kp + (extra_mask_bytes & ~15u);  // keys; pair masks; output scratch
+    if (tail < scratch) tail = scratch;
+    L.u_bytes = nms ? 8 * Kp + tail : 6 * Kp;
+    const uint32_t sord_bytes = nms ? 8 * Kp : 4 * Kp;
     L.mask_off = L.U + sord_bytes;
     L.mask_words = (L.u_bytes - sord_bytes) / 4;
     L.total = align_up(L.U + L.u_bytes, 16);
@@ -134,18 +155,19 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, uint32
 struct Smem {
     float4 *box;        // [Kp] x1 y1 x2 y2 by cell id            (output columns 0-3)
     float2 *cs;         // [Kp] conf, class score                 (columns 4, 5)
-    float *ta;          // [Kp] t * area * 2^-13 (NaN: degenerate box, the class takes the exact path)
     uint32_t *clsidx;   // [Kp] (class << 16) | arrival index inside the (class, bucket); ~0u: not a candidate
     unsigned long long *key;
-    uint16_t *sord;     // sorted position -> cell id
+    uint2 *sord;        // sorted position -> {shared address of box[cell], t * area * 2^-13 (NaN: degenerate)}
     uint32_t *mask;     // pair-mask words
-    uint16_t *outsrc;   // output row -> cell id
-    uint16_t *outcls;   // output row -> class
+    float *scratch;     // P6: per-warp 32 x 7 floats
+    uint16_t *outsrc;   // MODE_DECODE: output row -> cell id
+    uint16_t *tilecls;  // kept-bitmap tile -> class
     uint32_t *passbits, *keptbits, *tilepref, *tasks;
     int *cnt, *start, *ktile, *maskbase, *tbase, *done, *flag;
     int *cntb;          // [C*B+1] per (class, score bucket): arrival counter, then exclusive prefix
     uint2 *rounds;      // x = c_lo | c_hi << 16, y = t0 | t1 << 16
     int *misc;
+    uint32_t box_saddr; // shared-window address of box[0]
 };
 
 __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, int K, int C, int mode) {
@@ -154,13 +176,13 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, 
     const uint32_t Cp = align_up((uint32_t)C + 1, 4);
     s.box = reinterpret_cast<float4 *>(base + L.box);
     s.cs = reinterpret_cast<float2 *>(base + L.cs);
-    s.ta = reinterpret_cast<float *>(base + L.ta);
     s.clsidx = reinterpret_cast<uint32_t *>(base + L.U);
-    s.key = reinterpret_cast<unsigned long long *>(base + L.U + 4 * Kp);
-    s.sord = reinterpret_cast<uint16_t *>(base + L.U);
+    s.key = reinterpret_cast<unsigned long long *>(base + L.mask_off);
+    s.sord = reinterpret_cast<uint2 *>(base + L.U);
     s.mask = reinterpret_cast<uint32_t *>(base + L.mask_off);
-    s.outsrc = reinterpret_cast<uint16_t *>(base + L.mask_off);
-    s.outcls = reinterpret_cast<uint16_t *>(base + L.mask_off + 2 * Kp);
+    s.scratch = reinterpret_cast<float *>(base + L.mask_off);
+    s.outsrc = reinterpret_cast<uint16_t *>(base + L.U + 4 * Kp);
+    s.tilecls = reinterpret_cast<uint16_t *>(base + L.tilecls);
     s.passbits = reinterpret_cast<uint32_t *>(base + L.passbits);
     s.keptbits = reinterpret_cast<uint32_t *>(base + L.keptbits);
     s.tilepref = reinterpret_cast<uint32_t *>(base + L.tilepref);
@@ -176,12 +198,12 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, 
     s.cntb = reinterpret_cast<int *>(base + L.cntb);
     s.rounds = reinterpret_cast<uint2 *>(base + L.rounds);
     s.misc = reinterpret_cast<int *>(base + L.misc);
+    s.box_saddr = (uint32_t)__cvta_generic_to_shared(base + L.box);
     (void)mode;
     return s;
 }
 
-__device__ __forceinline__ int fastdiv(int n, int d, uint32_t magic) {
-    (void)d;
+__device__ __forceinline__ int fastdiv(int n, uint32_t magic) {
     return magic ? (int)__umulhi((uint32_t)n, magic) : n;  // exact for n < 65536
 }
 
@@ -193,6 +215,13 @@ __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.dbg[(size_t)b * 16 + k] = t;
     }
+}
+
+// shared-memory loads by shared-window address (the pair loop: no address arithmetic)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
 }
 
 // t * area * 2^-13 of one box for the divide-free pair test, NaN when the fast test
@@ -243,48 +272,84 @@ __device__ __noinline__ float class_tie_break(const float *qc, int HW, int C, fl
     return best;
 }
 
-constexpr int kClsChunk = 24;  // class planes loaded per batch (all in flight before the first use)
+constexpr int kClsChunk = 24;  // class planes loaded per batch on the runtime-shape path
+
+// Window below the largest logit m inside which another logit could tie with it after the sigmoid is
+// rounded: d/dt ln(sigmoid(t)) = 1 - sigmoid(t) >= e*s on (-inf, m] (e = exp(-m), s = sigmoid(m)), so a
+// logit below m - 2^-17/(e*s) has a sigmoid smaller by > 2^-17 relative (>10x the evaluation error) and
+// cannot win or tie.  Returns sigmoid(m) in *best.
+__device__ __forceinline__ float tie_window(float m, float *best) {
+    const float e1 = exp_fast(-m);
+    const float s1 = rcp_fast(__fadd_rn(1.0f, e1));
+    *best = s1;
+    return __fmul_rn(7.6293945e-06f, rcp_fast(__fmul_rn(e1, s1)));
+}
 
 // ---------------------------------------------------------------------------
-// P1: decode every cell of the image, single pass over the heads.  All 5+C plane
-// loads of a cell are issued before the first use (C <= 24; larger C: batches of 24).
+// P1: decode every cell of one head, single pass.  All 5+C plane loads of a cell are
+// issued before the first use.  CT/HWT/WT > 0: compile-time class count and grid.
 // ---------------------------------------------------------------------------
-template <int THREADS, int MODE>
-__device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, int b) {
+template <int THREADS, int MODE, int CT, int HWT, int WT>
+__device__ __forceinline__ void decode_head(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int C = p.C;
-    int cid0 = 0;
+    constexpr bool kStatic = (CT > 0);
+    const int C = kStatic ? CT : p.C;
+    const int attrs = C + 5;
+    const int HW = kStatic ? HWT : hd.HW;
+    const int W = kStatic ? WT : hd.W;
+    const int cells = p.A * HW;
+    const float *hb = hd.ptr + (size_t)b * p.A * attrs * HW;  // uniform
 #pragma unroll 1
-    for (int hh = 0; hh < p.nheads; ++hh) {
-        const HeadDesc &hd = p.head[hh];
-        const int HW = hd.HW;
-        const float *hb = hd.ptr + (size_t)b * p.A * p.attrs * HW;  // uniform
-#pragma unroll 1
-        for (int base = 0; base < hd.cells; base += THREADS) {
-            const int local = base + tid;
-            bool pass = false;
-            if (local < hd.cells) {
-                const int cid = cid0 + local;
-                const int a = fastdiv(local, HW, hd.magicHW);
-                const int pos = local - a * HW;
-                // addresses: one IMAD.WIDE each (64-bit base + 32-bit plane stride * constant)
-                const char *q = reinterpret_cast<const char *>(hb + (uint32_t)(a * p.attrs * HW + pos));
+    for (int base = 0; base < cells; base += THREADS) {
+        const int local = base + tid;
+        bool pass = false;
+        if (local < cells) {
+            const int cid = cid0 + local;
+            const int a = kStatic ? (local / HW) : fastdiv(local, hd.magicHW);
+            const int pos = local - a * HW;
+            const float *q = hb + (uint32_t)(a * attrs * HW + pos);
+            float tx, ty, tw, th, tc;
+            float m1 = -INFINITY, best = 0.f, win = 0.f, conf = 0.f;
+            int i1 = 0;
+            bool tie = false;
+            if (kStatic) {
+                // one base register + immediates
+                float x[CT > 0 ? CT : 1];
+                tx = __ldcs(q);
+                ty = __ldcs(q + HWT);
+                tw = __ldcs(q + 2 * HWT);
+                th = __ldcs(q + 3 * HWT);
+                tc = __ldcs(q + 4 * HWT);
+#pragma unroll
+                for (int u = 0; u < CT; ++u) x[u] = __ldcs(q + (5 + u) * HWT);
+                conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
+                pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
+                if (pass) {
+                    float cm = x[0];
+#pragma unroll
+                    for (int u = 1; u < CT; ++u) cm = fmaxf(cm, x[u]);
+                    m1 = cm;
+                    win = tie_window(m1, &best);
+                    const float lo = __fsub_rn(m1, win);
+                    float near = 0.f;  // bit u: x[u] >= lo   (FSET + FFMA: exact for 24 bits)
+#pragma unroll
+                    for (int u = 0; u < CT; ++u) near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << (u % 24)), near);
+                    static_assert(CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
+                    const uint32_t nb = __float2uint_rn(near);
+                    i1 = __ffs(nb) - 1;
+                    tie = (nb & (nb - 1u)) != 0u || nb == 0u;
+                    if (nb == 0u) i1 = 0;
+                }
+            } else {
+                const char *qb = reinterpret_cast<const char *>(q);
                 const uint32_t st = (uint32_t)HW * 4u;  // plane stride in bytes
-#define B200_LD(u) __ldcs(reinterpret_cast<const float *>(q + (uint64_t)st * (uint32_t)(u)))
-                const float tx = B200_LD(0);
-                const float ty = B200_LD(1);
-                const float tw = B200_LD(2);
-                const float th = B200_LD(3);
-                const float tc = B200_LD(4);
-                q += (uint64_t)st * 5u;
-                const float *qc = reinterpret_cast<const float *>(q);
-                // class max over the raw logits: value, first argmax and whether any other
-                // logit lies within `win` of it (then sigmoid rounding could change the result
-                // of torch.max(sigmoid(logits)), :198, and the exact tie-break runs)
-                float m1 = -INFINITY;
-                int i1 = 0;
-                bool tie = false;
-                float conf = 0.f, e1 = 0.f, best = 0.f, win = 0.f;
+#define B200_LD(u) __ldcs(reinterpret_cast<const float *>(qb + (uint64_t)st * (uint32_t)(u)))
+                tx = B200_LD(0);
+                ty = B200_LD(1);
+                tw = B200_LD(2);
+                th = B200_LD(3);
+                tc = B200_LD(4);
+                qb += (uint64_t)st * 5u;
 #pragma unroll 1
                 for (int c0 = 0; c0 < C; c0 += kClsChunk) {
                     // groups of 4 planes behind uniform branches; only the last, partial group clamps
@@ -302,10 +367,10 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
                             for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(min(u, nv - 1));
                         }
                     }
-                    q += (uint64_t)st * (uint32_t)nv;
+                    qb += (uint64_t)st * (uint32_t)nv;
                     if (c0 == 0) {
-                        conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
-                        pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
+                        conf = sigmoid_fast(tc);
+                        pass = conf > p.conf_thr;
                     }
                     float cm = x[0];
 #pragma unroll
@@ -313,15 +378,10 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
                         if (4 * g < nv) cm = fmaxf(fmaxf(cm, fmaxf(x[4 * g], x[4 * g + 1])), fmaxf(x[4 * g + 2], x[4 * g + 3]));
                     }
                     if (pass) {
-                        // d/dt ln(sigmoid(t)) = 1 - sigmoid(t) >= e*s on (-inf, m], so a logit below
-                        // m - 2^-17/(e*s) has a sigmoid smaller by > 2^-17 relative (>10x the
-                        // evaluation error) and cannot win or tie
                         const float m_new = fmaxf(m1, cm);
-                        e1 = exp_fast(-m_new);
-                        best = __fdividef(1.0f, __fadd_rn(1.0f, e1));  // sigmoid(m_new)
-                        win = __fdividef(7.6293945e-06f, __fmul_rn(e1, best));
+                        win = tie_window(m_new, &best);
                         const float lo = __fsub_rn(m_new, win);
-                        float near = 0.f;  // bit u: x[u] >= lo   (FSET + FFMA: exact for 24 bits)
+                        float near = 0.f;
 #pragma unroll
                         for (int g = 0; g < kClsChunk / 4; ++g) {
                             if (4 * g < nv) {
@@ -340,42 +400,38 @@ __device__ __forceinline__ void phase_decode(const DNParams &p, const Smem &s, i
                         m1 = fmaxf(m1, cm);
                     }
                 }
-                if (pass) {
-                    int bi = i1;
-                    if (C > 1 && tie) best = class_tie_break(qc, HW, C, __fsub_rn(m1, win), m1, i1, &bi);
-                    const int j = fastdiv(pos, hd.W, hd.magicW);
-                    const int i = pos - j * hd.W;
-                    const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
-                    const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
-                    const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194 (x * 1/W)
-                    const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
-                    const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
-                    const float bh = __fmul_rn(eh, hd.ah[a]);
-                    float4 bx;
-                    bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244
-                    bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
-                    bx.z = __fadd_rn(bw, bx.x);                                  // :246
-                    bx.w = __fadd_rn(bh, bx.y);                                  // :247
-                    s.box[cid] = bx;
-                    s.cs[cid] = make_float2(conf, best);
-                    uint32_t idx = 0;
-                    if (MODE == MODE_FUSED) {
-                        s.ta[cid] = make_ta(bx, p.iou);
-                        idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
-                    }
-                    s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
-                } else if (MODE == MODE_FUSED) {
-                    s.clsidx[cid] = 0xffffffffu;
-                }
-            }
 #undef B200_LD
-            if (MODE == MODE_DECODE) {  // single head: candidate ids are 32-aligned per warp
-                const unsigned bal = __ballot_sync(kFullMask, pass);
-                if (lane == 0 && local < hd.cells) s.passbits[local >> 5] = bal;
             }
-            if (MODE == MODE_FUSED) stamp(p, b, 8 + min(6, hh * 4 + base / THREADS));
+            if (pass) {
+                int bi = i1;
+                if (C > 1 && tie) best = class_tie_break(q + 5 * HW, HW, C, __fsub_rn(m1, win), m1, i1, &bi);
+                const int j = kStatic ? (pos / W) : fastdiv(pos, hd.magicW);
+                const int i = pos - j * W;
+                const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
+                const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
+                const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194 (x * 1/W)
+                const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+                const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
+                const float bh = __fmul_rn(eh, hd.ah[a]);
+                float4 bx;
+                bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244
+                bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
+                bx.z = __fadd_rn(bw, bx.x);                                  // :246
+                bx.w = __fadd_rn(bh, bx.y);                                  // :247
+                s.box[cid] = bx;
+                s.cs[cid] = make_float2(conf, best);
+                uint32_t idx = 0;
+                if (MODE == MODE_FUSED) idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
+                s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+            } else if (MODE == MODE_FUSED) {
+                s.clsidx[cid] = 0xffffffffu;
+            }
         }
-        cid0 += hd.cells;
+        if (MODE == MODE_DECODE) {  // single head: candidate ids are 32-aligned per warp
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (lane == 0 && local < cells) s.passbits[local >> 5] = bal;
+        }
+        if (MODE == MODE_FUSED) stamp(p, b, 8 + min(6, hh * 4 + base / THREADS));
     }
 }
 
@@ -403,7 +459,6 @@ __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s
             if (ok) {
                 s.box[row] = bx;
                 s.cs[row] = make_float2(conf, score);
-                s.ta[row] = make_ta(bx, p.iou);
                 const uint32_t idx = (uint32_t)atomicAdd(&s.cntb[c * p.B + score_bucket(__fmul_rn(score, conf), p.B)], 1);
                 s.clsidx[row] = ((uint32_t)c << 16) | idx;
             }
@@ -426,9 +481,11 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
         const int T = (n + 31) >> 5;
         const int incT = warp_inclusive_scan(T, lane);
         if (c < C) {
+            const int kt = carryT + incT - T;
             s.cnt[c] = n;
             s.start[c] = st;
-            s.ktile[c] = carryT + incT - T;
+            s.ktile[c] = kt;
+            for (int t = 0; t < T; ++t) s.tilecls[kt + t] = (uint16_t)c;
         }
         carryT += __shfl_sync(kFullMask, incT, 31);
         words += 32 * tri(T);
@@ -559,8 +616,6 @@ __device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem
         const unsigned long long key =
             ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)((c << 16) | (0xffffu - (uint32_t)cid));
         s.key[s.cntb[(int)c * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
-        const float ta = s.ta[cid];
-        if (ta != ta) s.flag[c] = 1;  // degenerate box: the class runs the exact pair arithmetic
     }
 }
 
@@ -570,11 +625,14 @@ __device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s
         const unsigned long long key = s.key[t];
         const uint32_t lo32 = (uint32_t)key;
         const uint32_t cid = 0xffffu - (lo32 & 0xffffu);
-        const int cq = (int)(lo32 >> 16) * p.B + score_bucket(order_key_to_float((uint32_t)(key >> 32)), p.B);
+        const int c = (int)(lo32 >> 16);
+        const int cq = c * p.B + score_bucket(order_key_to_float((uint32_t)(key >> 32)), p.B);
         const int st = s.cntb[cq], en = s.cntb[cq + 1];
         int rank = 0;
         for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
-        s.sord[st + rank] = (uint16_t)cid;
+        const float ta = make_ta(s.box[cid], p.iou);
+        if (ta != ta) s.flag[c] = 1;  // degenerate box: the class runs the exact pair arithmetic
+        s.sord[st + rank] = make_uint2(s.box_saddr + 16u * cid, __float_as_uint(ta));
     }
 }
 
@@ -585,35 +643,40 @@ __device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s
 constexpr float kPairEps = 1e-5f;
 
 // exact torchvision decisions of one row against the columns of one tile (slow path)
-__device__ __noinline__ uint32_t block_exact(const float4 *box, const uint16_t *ordc, int ncol, const float4 R, double thr) {
+__device__ __noinline__ uint32_t block_exact(const uint2 *ordc, int ncol, const float4 R, double thr) {
     const float ra = box_area(R);
     uint32_t word = 0u;
     for (int k = 0; k < ncol; ++k) {
-        const float4 Cb = box[ordc[k]];
+        const float4 Cb = lds_f4(ordc[k].x);
         if (nms_suppress_exact(R, ra, Cb, box_area(Cb), thr)) word |= 1u << k;
     }
     return word;
 }
 
-__device__ __forceinline__ uint32_t block_fast(const Smem &s, const uint16_t *ordc, int ncol, const float4 R, float rta,
-                                               double thr) {
+__device__ __forceinline__ void pair_step(const uint2 e, const float4 &R, float rta, uint32_t &bits, float &m) {
+    const float4 Cb = lds_f4(e.x);
+    const float cta = __uint_as_float(e.y);
+    const float w = __fsub_rn(fminf(R.z, Cb.z), fmaxf(R.x, Cb.x));
+    const float h = __fsub_rn(fminf(R.w, Cb.w), fmaxf(R.y, Cb.y));
+    const float ws = __saturatef(__fmul_rn(w, 1.220703125e-4f));  // max(w, 0) * 2^-13 (exact; |coords| < 4096)
+    const float sum = __fadd_rn(rta, cta);                         // t * (area_r + area_c) * 2^-13
+    const float d = __fmaf_rn(-ws, h, sum);                        // < 0  <=>  inter > t * (area sum)
+    m = fminf(m, __fmaf_rn(sum, -kPairEps, fabsf(d)));             // <= 0: too close to call
+    bits = __funnelshift_l(__float_as_uint(d), bits, 1);           // sign bit -> mask bit
+}
+
+__device__ __forceinline__ uint32_t block_fast(const uint2 *ordc, int ncol, const float4 R, float rta, double thr) {
     uint32_t bits = 0u;
     float m = INFINITY;
-#pragma unroll 4
-    for (int k = 0; k < ncol; ++k) {
-        const int ccid = ordc[k];
-        const float4 Cb = s.box[ccid];
-        const float cta = s.ta[ccid];
-        const float w = __fsub_rn(fminf(R.z, Cb.z), fmaxf(R.x, Cb.x));
-        const float h = __fsub_rn(fminf(R.w, Cb.w), fmaxf(R.y, Cb.y));
-        const float ws = __saturatef(__fmul_rn(w, 1.220703125e-4f));  // max(w, 0) * 2^-13 (exact; |coords| < 4096)
-        const float sum = __fadd_rn(rta, cta);                         // t * (area_r + area_c) * 2^-13
-        const float d = __fmaf_rn(-ws, h, sum);                        // < 0  <=>  inter > t * (area sum)
-        m = fminf(m, __fmaf_rn(sum, -kPairEps, fabsf(d)));             // <= 0: too close to call
-        bits = __funnelshift_l(__float_as_uint(d), bits, 1);           // sign bit -> mask bit
+    if (ncol == 32) {
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) pair_step(ordc[k], R, rta, bits, m);
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < ncol; ++k) pair_step(ordc[k], R, rta, bits, m);
     }
     uint32_t word = __brev(bits) >> (32 - ncol);  // column k was shifted in k-th: bit ncol-1-k -> bit k
-    if (m <= 0.0f) word = block_exact(s.box, ordc, ncol, R, thr);
+    if (m <= 0.0f) word = block_exact(ordc, ncol, R, thr);
     return word;
 }
 
@@ -663,20 +726,19 @@ __device__ __forceinline__ void phase_pairs_sweep(const DNParams &p, const Smem 
         const int c = (int)(tk >> 16), rt = (int)(tk & 0xffffu);
         const int n = s.cnt[c];
         const int te = min((n + 31) >> 5, t1);
-        const uint16_t *ord = s.sord + s.start[c];
+        const uint2 *ord = s.sord + s.start[c];
         const int row = 32 * rt + lane;
-        const int rcid = ord[min(row, n - 1)];
-        const float4 R = s.box[rcid];
-        const float rta = s.ta[rcid];
+        const uint2 re = ord[min(row, n - 1)];
+        const float4 R = lds_f4(re.x);
+        const float rta = __uint_as_float(re.y);
         const bool slow = s.flag[c] != 0;
-        uint32_t *mb = s.mask + s.maskbase[c];
+        uint32_t *mb = s.mask + s.maskbase[c] + (rt - tri0) * 32 + lane;
         for (int ct = max(rt, t0); ct < te; ++ct) {
             const int ncol = min(32, n - 32 * ct);
-            uint32_t word = slow ? block_exact(s.box, ord + 32 * ct, ncol, R, p.iou.thr)
-                                 : block_fast(s, ord + 32 * ct, ncol, R, rta, p.iou.thr);
+            uint32_t word = slow ? block_exact(ord + 32 * ct, ncol, R, p.iou.thr) : block_fast(ord + 32 * ct, ncol, R, rta, p.iou.thr);
             if (ct == rt) word &= ~((2u << lane) - 1u);  // only LATER columns (2u << 31 == 0: none)
             if (row >= n) word = 0u;
-            mb[(tri(ct) - tri0 + rt) * 32 + lane] = word;
+            mb[tri(ct) * 32] = word;
         }
         __syncwarp();
         int old = 0;
@@ -693,22 +755,82 @@ __device__ __forceinline__ void phase_pairs_sweep(const DNParams &p, const Smem 
 }
 
 // ---------------------------------------------------------------------------
-// kernel
+// P6: output.  Tile g of the kept bitmap holds up to 32 rows that are consecutive in the
+// output (class-ascending, score-descending); the warp assembles them in its scratch and
+// writes them with coalesced stores.
 // ---------------------------------------------------------------------------
 template <int MODE, int THREADS>
+__device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, int b) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+    const int ntiles = s.ktile[p.C];
+    float *o = p.out + (size_t)b * p.K * 7;
+    float *scr = s.scratch + warp * (32 * 7);
+    // MODE_NMS: the caller's own rows are gathered bit-for-bit (pred_this_cls[index], box.py:29)
+    const int K0 = (MODE == MODE_NMS) ? min(p.cand_count[0][b], p.cand_stride[0]) : 0;
+    const float *r0 = (MODE == MODE_NMS) ? p.cand[0] + (size_t)b * p.cand_stride[0] * 7 : nullptr;
+    const float *r1 = (MODE == MODE_NMS && p.cand[1]) ? p.cand[1] + (size_t)b * p.cand_stride[1] * 7 : nullptr;
+    for (int g = warp; g <= ntiles; g += kWarps) {
+        // rows before this tile
+        int before = 0;
+        for (int t = lane; t < g; t += 32) before += __popc(s.keptbits[t]);
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
+        if (g == ntiles) {
+            if (lane == 0) p.out_count[b] = before;
+            break;
+        }
+        const uint32_t word = s.keptbits[g];
+        const int nk = __popc(word);
+        if (nk == 0) continue;
+        const int c = s.tilecls[g];
+        const int pos = s.start[c] + 32 * (g - s.ktile[c]) + lane;
+        if ((word >> lane) & 1u) {
+            const int r = __popc(word & lanemask_lt());
+            const uint32_t cid = (s.sord[pos].x - s.box_saddr) >> 4;
+            float *d = scr + 7 * r;
+            if (MODE == MODE_NMS) {
+                const float *src = ((int)cid < K0) ? r0 + (size_t)cid * 7 : r1 + (size_t)((int)cid - K0) * 7;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) d[k] = __ldg(src + k);
+            } else {
+                const float4 bx = s.box[cid];
+                const float2 cs = s.cs[cid];
+                d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
+                d[4] = cs.x; d[5] = cs.y;
+                d[6] = (float)c;  // cls_idx.float() (yolo_loss.py:199)
+            }
+            if (p.out_idx) p.out_idx[(size_t)b * p.K + before + r] = (int)cid;
+        }
+        __syncwarp();
+        float *dst = o + (size_t)7 * before;
+        const int nf = 7 * nk;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int f = 32 * k + lane;
+            if (f < nf) dst[f] = scr[f];
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+template <int MODE, int THREADS, int SHAPE>
 __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, L, p.K, p.C, MODE);
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.C, K = p.K;
-    constexpr int kWarps = THREADS / 32;
+    using SH = ShapeT<SHAPE>;
 
     stamp(p, b, 0);
     if (MODE != MODE_NMS) {
         // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
         // only issue after the launch ramp) finds its lines on the way.  Prefetching the whole image
-        // is slower: the demand loads then queue behind 46 MB of prefetches (profiles/r01/NOTES.md).
+        // is slower: the demand loads then queue behind 46 MB of prefetches.
         if (tid == 0 && !(p.flags & 1)) {
             const size_t img0 = (size_t)p.A * p.attrs * p.head[0].HW;
             l2_prefetch_span(p.head[0].ptr + (size_t)b * img0, img0 * sizeof(float));
@@ -725,15 +847,18 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     }
     stamp(p, b, 15);
 
-    if (MODE == MODE_NMS) phase_load_rows<THREADS>(p, s, b);
-    else phase_decode<THREADS, MODE>(p, s, b);
+    if (MODE == MODE_NMS) {
+        phase_load_rows<THREADS>(p, s, b);
+    } else {
+        decode_head<THREADS, MODE, SH::C, SH::HW0, SH::W0>(p, s, b, p.head[0], 0, 0);
+        if (MODE == MODE_FUSED) decode_head<THREADS, MODE, SH::C, SH::HW1, SH::W1>(p, s, b, p.head[1], p.head[0].cells, 1);
+    }
     __syncthreads();
     stamp(p, b, 1);
 
-    const int nwords = (K + 31) >> 5;
-
     if (MODE == MODE_DECODE) {
         // YOLOLoss.get_pred_boxes output: rows in candidate order (:203)
+        const int nwords = (K + 31) >> 5;
         if (warp == 0) {
             int carry = 0;
             for (int w0 = 0; w0 < nwords; w0 += 32) {
@@ -792,62 +917,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     }
     stamp(p, b, 4);
     stamp(p, b, 5);
-    // P6: output row -> cell id (the mask buffer is dead now; outsrc aliases it).  Every
-    // warp sums the kept counts of the tiles before its class itself (no serial scan phase).
-    for (int c = warp; c <= C; c += kWarps) {
-        const int kt = s.ktile[c];
-        int before = 0;
-        for (int g = lane; g < kt; g += 32) before += __popc(s.keptbits[g]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFullMask, before, o);
-        if (c == C) {
-            if (lane == 0) s.misc[M_TOTAL] = before;
-            break;
-        }
-        const int n = s.cnt[c], st = s.start[c];
-        for (int ct = 0; 32 * ct < n; ++ct) {
-            const uint32_t word = s.keptbits[kt + ct];
-            if ((word >> lane) & 1u) {
-                const int r = before + __popc(word & lanemask_lt());
-                s.outsrc[r] = s.sord[st + 32 * ct + lane];
-                s.outcls[r] = (uint16_t)c;
-            }
-            before += __popc(word);
-        }
-    }
-    __syncthreads();
     stamp(p, b, 6);
-    // flat coalesced store
-    {
-        const int T = s.misc[M_TOTAL];
-        float *o = p.out + (size_t)b * K * 7;
-        if (MODE == MODE_NMS) {
-            // gather the caller's own row (pred_this_cls[index], box.py:29) bit-for-bit
-            const int K0 = min(p.cand_count[0][b], p.cand_stride[0]);
-            const float *r0 = p.cand[0] + (size_t)b * p.cand_stride[0] * 7;
-            const float *r1 = p.cand[1] ? p.cand[1] + (size_t)b * p.cand_stride[1] * 7 : nullptr;
-            for (int f = tid; f < 7 * T; f += THREADS) {
-                const int row = f / 7, col = f - 7 * row;
-                const int k = s.outsrc[row];
-                o[f] = (k < K0) ? __ldg(r0 + (size_t)k * 7 + col) : __ldg(r1 + (size_t)(k - K0) * 7 + col);
-            }
-        } else {
-            const float *boxf = reinterpret_cast<const float *>(s.box);
-            const float *csf = reinterpret_cast<const float *>(s.cs);
-            for (int f = tid; f < 7 * T; f += THREADS) {
-                const int row = f / 7, col = f - 7 * row;
-                const int cid = s.outsrc[row];
-                float v;
-                if (col < 4) v = boxf[4 * cid + col];
-                else if (col < 6) v = csf[2 * cid + col - 4];
-                else v = (float)s.outcls[row];
-                o[f] = v;
-            }
-        }
-        if (p.out_idx)
-            for (int r = tid; r < T; r += THREADS) p.out_idx[(size_t)b * K + r] = (int)s.outsrc[r];
-        if (tid == 0) p.out_count[b] = T;
-    }
+    // P6 (the mask buffer is dead now; the row scratch aliases it)
+    phase_output<MODE, THREADS>(p, s, b);
     stamp(p, b, 7);
 }
 
