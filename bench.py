@@ -201,6 +201,51 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- loss target assignment (config 4)
+VOC_IGNORE = [0.6076333316652263, 0.5623606200028424]   # models/voc/config.yaml:27-29
+VOC_IOU_THRESH = 0.5497280113447018                      # :31
+VOC_IOU_WEIGHTING = 0.021830872589525777                 # :12
+
+
+def make_targets(N, G, C, seed):
+    """cls~U{1..C}, w,h~U(0.02,0.47), cx~U(w/2,1-w/2), cy likewise."""
+    r = np.random.RandomState(seed)
+    out = []
+    for _ in range(N):
+        wh = r.uniform(0.02, 0.47, (G, 2))
+        c = wh / 2 + r.rand(G, 2) * (1 - wh)
+        out.append(np.concatenate((r.randint(1, C + 1, (G, 1)), c, wh), 1).astype(np.float32))
+    return out
+
+
+def time_loss(dev, N, G, steps=100, seed=1):
+    """YOLOLoss.forward(input, targets) partial sums for BOTH VOC-352 heads (2 launches of
+    target_loss_kernel + 2 tiny reductions per step), heads resident in HBM."""
+    from mobilenet_yolo_pytorch_b200 import ops
+    wl = WORKLOADS["cfg2"]
+    C = wl["C"]
+    sa = np.array([[aw / 352, ah / 352] for aw, ah in VOC_ANCHORS], np.float64).astype(np.float32)
+    targets = make_targets(N, G, C, seed)
+    gt, gt_off, Gt, _ = ops.pack_targets([torch.from_numpy(t) for t in targets], dev)
+    in_bytes = N * bytes_in_per_image(wl)
+    R = max(3, int(np.ceil(300e6 / in_bytes)))
+    sets = [tuple(h.to(dev) for h in make_heads(wl, N, seed=100 + r)) for r in range(R)]
+
+    def step(i):
+        h0, h1 = sets[i % R]
+        ops.target_loss_sums(h0, gt, gt_off, Gt, sa, MASK[0], C, VOC_IGNORE[0], VOC_IOU_THRESH)
+        ops.target_loss_sums(h1, gt, gt_off, Gt, sa, MASK[1], C, VOC_IGNORE[1], VOC_IOU_THRESH)
+
+    for i in range(5):
+        step(i)
+    torch.cuda.synchronize()
+    ms = time_loop(step, steps) / steps
+    algo = in_bytes + 2 * 20 * N * G
+    return {"images_per_s_per_gpu": N / (ms * 1e-3), "ms_per_step": ms, "batch": N, "gt_per_image": G,
+            "algorithmic_bytes_per_step": algo, "algorithmic_gbs": algo / (ms * 1e-3) / 1e9,
+            "iou_pairs_per_step": N * G * cells_per_image(wl)}
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def time_loop(fn, steps, stream=None):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

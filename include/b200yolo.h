@@ -138,8 +138,9 @@ int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int 
  *             a class outside [1,C] (reference: IndexError), 2 more than 1024 GT
  *             boxes in one image
  *   grad      dev (N, A*(5+C), H, W) or NULL: reserved (must be NULL in this version)
- *   workspace dev, b200yolo_target_loss_workspace_bytes(N) bytes: per-image partial
- *             sums, reduced in image order so results are bitwise reproducible
+ *   workspace dev, b200yolo_target_loss_workspace_bytes(N) bytes: per-CTA partial sums
+ *             (up to 8 CTAs share an image), reduced in a fixed order so results are
+ *             bitwise reproducible run to run
  */
 size_t b200yolo_target_loss_workspace_bytes(int N);
 int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,

@@ -276,6 +276,8 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
     for (int k = 0; k < A; ++k) p.mask[k] = mask[k];
     p.gt = gt; p.gt_off = gt_off; p.G = G;
     p.ignore_thr = ignore_thr; p.iou_thr = iou_thr;
+    // iou < thr <=> inter < thr/(1+thr) * (area_g + area_p); outside [0.01, 1] every cell takes the exact path
+    p.ts = (ignore_thr >= 0.01f && ignore_thr <= 1.0f) ? (float)((double)ignore_thr / (1.0 + (double)ignore_thr)) * 1.220703125e-4f : 0.0f;
     p.sums = sums; p.assign = assign; p.terms = terms; p.status = status;
     if (N > 0 && (!workspace || workspace_bytes < b200yolo_target_loss_workspace_bytes(N)))
         return fail(B200YOLO_EINVAL, "target_loss: workspace too small (%zu < %zu)", workspace_bytes,
@@ -289,28 +291,43 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
     if ((int)smem > lim)
         return fail(B200YOLO_EUNSUPPORTED, "target_loss: %d cells per image need %u B of shared memory (limit %d B)",
                     p.cells, smem, lim);
+    int nsm = 148;
     {
         static std::mutex mu;
         static bool configured[64] = {false};
+        static int sm_count[64] = {0};
         std::lock_guard<std::mutex> g(mu);
         if (dev < 64 && !configured[dev]) {
             CUDA_TRY(cudaFuncSetAttribute(target_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
             configured[dev] = true;
         }
+        if (dev < 64 && sm_count[dev] > 0) nsm = sm_count[dev];
     }
+    // CTAs per image: enough to put ~3 CTAs on every SM when the batch alone cannot, slices of >= 256 cells
+    int S = 1;
+    if (N > 0) {
+        S = (3 * nsm + N - 1) / N;
+        const int smax = (p.cells + kTLThreads - 1) / kTLThreads;
+        if (S > smax) S = smax;
+        if (S > kTLMaxSplit) S = kTLMaxSplit;
+        if (S < 1) S = 1;
+    }
+    p.S = S;
+    p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
     CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     if (N > 0) {
-        target_loss_kernel<<<N, kTLThreads, smem, st>>>(p);
+        target_loss_kernel<<<N * S, kTLThreads, smem, st>>>(p);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
     }
-    target_loss_reduce_kernel<<<1, kTLSums * 32, 0, st>>>(p.partial, N, sums);
+    target_loss_reduce_kernel<<<1, kTLSums * 32, 0, st>>>(p.partial, N * S, sums);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-size_t b200yolo_target_loss_workspace_bytes(int N) { return (size_t)(N > 0 ? N : 1) * kTLSums * sizeof(double); }
+size_t b200yolo_target_loss_workspace_bytes(int N) { return (size_t)(N > 0 ? N : 1) * kTLMaxSplit * kTLSums * sizeof(double); }
 
 int b200yolo_loss_finalize(const double *s, float iou_weighting, double *r) {
     if (!s || !r) return fail(B200YOLO_EINVAL, "loss_finalize: null pointer");

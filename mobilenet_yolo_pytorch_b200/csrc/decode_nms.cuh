@@ -117,7 +117,7 @@ constexpr uint32_t kScratchPerWarp = 32 * 7 * 4;  // P6: 32 output rows of 7 flo
 
 // U region by phase (Kp = K rounded up to 32):
 //   decode .. key scatter   clsidx u32[Kp] ........ | key u64[Kp]
-//   rank .. sweep           sord uint2[Kp] ........ | (key, dead after rank) pair masks u32[mask_words]
+//   rank .. sweep           sord uint2[Kp + 8] .... | (key, dead after rank) pair masks u32[mask_words]
 //   output                  sord .................. | per-warp row scratch
 //   (MODE_DECODE)           clsidx u32[Kp] | outsrc u16[Kp]
 __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int threads, uint32_t extra_mask_bytes) {
@@ -144,8 +144,8 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int th
     const uint32_t scratch = (uint32_t)(threads / 32) * kScratchPerWarp;
     uint32_t tail = 8 * Kp + (extra_mask_bytes & ~15u);  // keys; pair masks; output scratch
     if (tail < scratch) tail = scratch;
-    L.u_bytes = nms ? 8 * Kp + tail : 6 * Kp;
-    const uint32_t sord_bytes = nms ? 8 * Kp : 4 * Kp;
+    const uint32_t sord_bytes = nms ? 8 * Kp + 64 : 4 * Kp;  // + 8 padding entries (the pair loop reads whole chunks of 8)
+    L.u_bytes = nms ? sord_bytes + tail : 6 * Kp;
     L.mask_off = L.U + sord_bytes;
     L.mask_words = (L.u_bytes - sord_bytes) / 4;
     L.total = align_up(L.U + L.u_bytes, 16);
@@ -621,6 +621,7 @@ __device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem
 
 template <int THREADS>
 __device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv) {
+    if (threadIdx.x < 8) s.sord[Kv + threadIdx.x] = make_uint2(s.box_saddr, 0x7fc00000u);  // padding: a valid address, NaN area
     for (int t = threadIdx.x; t < Kv; t += THREADS) {
         const unsigned long long key = s.key[t];
         const uint32_t lo32 = (uint32_t)key;
@@ -668,14 +669,16 @@ __device__ __forceinline__ void pair_step(const uint2 e, const float4 &R, float 
 __device__ __forceinline__ uint32_t block_fast(const uint2 *ordc, int ncol, const float4 R, float rta, double thr) {
     uint32_t bits = 0u;
     float m = INFINITY;
-    if (ncol == 32) {
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) pair_step(ordc[k], R, rta, bits, m);
-    } else {
+    // chunks of 8 columns; a partial last chunk reads up to 7 entries past the class (the next class's
+    // entries, or the NaN-area padding after the last one): their bits are dropped below, a NaN never
+    // lowers m, and a false "too close" only costs the exact path
+    const int nr = (ncol + 7) & ~7;
 #pragma unroll 1
-        for (int k = 0; k < ncol; ++k) pair_step(ordc[k], R, rta, bits, m);
+    for (int k0 = 0; k0 < nr; k0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pair_step(ordc[k0 + k], R, rta, bits, m);
     }
-    uint32_t word = __brev(bits) >> (32 - ncol);  // column k was shifted in k-th: bit ncol-1-k -> bit k
+    uint32_t word = (__brev(bits) >> (32 - nr)) & (0xffffffffu >> (32 - ncol));  // column k was shifted in k-th
     if (m <= 0.0f) word = block_exact(ordc, ncol, R, thr);
     return word;
 }
@@ -770,12 +773,14 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
     const int K0 = (MODE == MODE_NMS) ? min(p.cand_count[0][b], p.cand_stride[0]) : 0;
     const float *r0 = (MODE == MODE_NMS) ? p.cand[0] + (size_t)b * p.cand_stride[0] * 7 : nullptr;
     const float *r1 = (MODE == MODE_NMS && p.cand[1]) ? p.cand[1] + (size_t)b * p.cand_stride[1] * 7 : nullptr;
-    for (int g = warp; g <= ntiles; g += kWarps) {
-        // rows before this tile
-        int before = 0;
-        for (int t = lane; t < g; t += 32) before += __popc(s.keptbits[t]);
+    // each warp owns a contiguous range of tiles: one prefix over the kept bitmap per warp
+    const int per = (ntiles + kWarps) / kWarps;  // ceil((ntiles + 1) / kWarps): "tile" ntiles writes the count
+    const int g0 = warp * per, g1 = min(g0 + per, ntiles + 1);
+    int before = 0;
+    for (int t = lane; t < g0; t += 32) before += __popc(s.keptbits[t]);
 #pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
+    for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
+    for (int g = g0; g < g1; ++g) {
         if (g == ntiles) {
             if (lane == 0) p.out_count[b] = before;
             break;
@@ -811,6 +816,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
             if (f < nf) dst[f] = scr[f];
         }
         __syncwarp();
+        before += nk;
     }
 }
 
@@ -829,8 +835,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     stamp(p, b, 0);
     if (MODE != MODE_NMS) {
         // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
-        // only issue after the launch ramp) finds its lines on the way.  Prefetching the whole image
-        // is slower: the demand loads then queue behind 46 MB of prefetches.
+        // only issue after the launch ramp) finds its lines on the way (-1 us).  Prefetching more --
+        // the whole image up front, or one decode round ahead -- is slower by 1-2 us (measured,
+        // profiles/r01/NOTES.md): the demand loads then queue behind the prefetches.
         if (tid == 0 && !(p.flags & 1)) {
             const size_t img0 = (size_t)p.A * p.attrs * p.head[0].HW;
             l2_prefetch_span(p.head[0].ptr + (size_t)b * img0, img0 * sizeof(float));

@@ -5,22 +5,28 @@
 // walks GT boxes in a Python loop with ~5 device syncs per assignment.  Only
 // cells with weight > 0 contribute to the loss, so nothing dense is needed:
 //
-//   one CTA per image
-//   P1  thread per GT box: xyxy (:112-113), IoU against ALL anchor shapes (:132),
-//       best anchor = first argmax (:133), cell (gj, gi) (:128,136-137), assignment
-//       flags k == index(best) or iou[mask[k]] > iou_thresh (:138-145); assigned
-//       (GT, k) pairs are appended to a shared-memory list and their cells flagged.
+//   grid N*S: S CTAs per image, each owning a slice of the image's cells
+//   P1  thread per GT box (replicated in the S CTAs of an image): xyxy (:112-113), IoU
+//       against ALL anchor shapes (:132), best anchor = first argmax (:133), cell (gj, gi)
+//       (:128,136-137), assignment flags k == index(best) or iou[mask[k]] > iou_thresh
+//       (:138-145); assigned (GT, k) pairs are appended to a shared-memory list and their
+//       cells flagged.
 //   P2  thread per cell, coalesced head reads: conf = sigmoid(tc); flagged cells
-//       contribute (conf-1)^2 (:149-150); otherwise the decoded box (:84-92) is
-//       tested against every GT box staged in shared memory: weight 1 / target 0
-//       iff max_g IoU < ignore_threshold (:115-125), else the cell is ignored.
-//   P3  thread per assignment: CIoU term (box_ciou :257-293), recall / iou / obj /
-//       class-score stats (:151-169); the first assignment of each distinct cell
-//       adds the class-channel loss with the union of assigned classes at 0.95,
-//       the rest at 0.05 (class_loss :425-434 -- order independent, duplicates
-//       counted exactly like the sequential reference).
-//   P4  deterministic reduction: per-image partial sums -> workspace, then a
-//       single-CTA kernel adds them in image order into sums[16].
+//       contribute (conf-1)^2 (:149-150); otherwise the decoded box (:84-92) is tested
+//       against every GT box staged in shared memory: weight 1 / target 0 iff
+//       max_g IoU < ignore_threshold (:115-125), else the cell is ignored.  This is the
+//       hot loop (config 4: 92.9 M box pairs) and it is divide-free and branch-free:
+//       iou < thr <=> inter < t*(area_g+area_p), t = thr/(1+thr); d = t*(areas) - w*h is
+//       one FFMA, the cell keeps min d and min(|d| - 1e-5*t*(areas)); only a cell with a pair
+//       closer than 1e-5 to the threshold (or a degenerate box) re-runs its GT loop with
+//       the reference's IEEE arithmetic (inter/union < thr).
+//   P3  warp per assignment (first CTA of the image): CIoU term (box_ciou :257-293),
+//       recall / iou / obj / class-score stats (:151-169); the first assignment of each
+//       distinct cell adds the class-channel loss, lanes = classes, with the union of
+//       assigned classes at 0.95, the rest at 0.05 (class_loss :425-434 -- order
+//       independent, duplicates counted exactly like the sequential reference).
+//   P4  deterministic reduction: per-CTA partial sums -> workspace, then a
+//       single-CTA kernel adds them in a fixed order into sums[16].
 //
 // Loss normalisers are batch-global (:55, :224), so the kernel returns SUMS; the
 // division happens after the (optional) cross-rank all-reduce, in
@@ -36,10 +42,13 @@ constexpr int kTLMaxGT = 1024;         // GT boxes per image staged in shared me
 constexpr int kTLMaxAllAnchors = 16;
 constexpr int kTLMaxAnchors = 8;
 constexpr int kTLSums = 16;
+constexpr int kTLMaxSplit = 8;         // CTAs per image
+constexpr float kTLEps = 1e-5f;
 
 struct TLParams {
     const float *head;
     int N, A, C, attrs, H, W, HW, cells, NA;
+    int S, chunk;  // CTAs per image; cells per CTA (multiple of 32)
     float invHW, invW, fW, fH;
     float aw_all[kTLMaxAllAnchors], ah_all[kTLMaxAllAnchors];
     int mask[kTLMaxAnchors];
@@ -47,8 +56,9 @@ struct TLParams {
     const int *gt_off;
     int G;
     float ignore_thr, iou_thr;
+    float ts;        // ignore_thr/(1+ignore_thr) * 2^-13 (0: the divide-free test is off)
     double *sums;
-    double *partial;  // [N][kTLSums]
+    double *partial;  // [N][S][kTLSums]
     int *assign;      // [G][A][4] or null
     float *terms;     // [G][A][2] or null
     int *status;
@@ -59,23 +69,24 @@ struct TLAssign {
     uint32_t t;     // GT index inside the image
 };
 
+constexpr int kTLMaxAssign = kTLMaxGT * kTLMaxAnchors / 2;
+
 __host__ __device__ inline uint32_t tl_smem_bytes(int cells) {
     uint32_t o = 0;
     o += 16 * kTLMaxGT;                       // gt xyxy
     o += 4 * kTLMaxGT;                        // gt area
+    o += 4 * kTLMaxGT;                        // gt t*area*2^-13
     o += 4 * kTLMaxGT;                        // gt class (0-based)
-    o += 8 * kTLMaxGT * kTLMaxAnchors / 2;    // assignment list (capacity 4 * kTLMaxGT entries)
+    o += 8 * kTLMaxAssign;                    // assignment list
     o += ((uint32_t)cells + 15u) / 16u * 16u; // assigned-cell flags
     o += 8 * kTLSums * kTLWarps;              // reduction scratch
     o += 64;
     return o;
 }
-constexpr int kTLMaxAssign = kTLMaxGT * kTLMaxAnchors / 2;
 
 // decode one cell's box exactly like get_target (:84-92) + wh_to_x2y2 (:243-247)
-__device__ __forceinline__ float4 tl_decode_box(const float *q, int HW, int i, int j, float fW, float fH, float aw,
-                                                float ah) {
-    const float tx = __ldg(q), ty = __ldg(q + HW), tw = __ldg(q + 2 * HW), th = __ldg(q + 3 * HW);
+__device__ __forceinline__ float4 tl_decode_box(float tx, float ty, float tw, float th, int i, int j, float fW, float fH,
+                                                float aw, float ah) {
     const float sx = sigmoid_f(tx), sy = sigmoid_f(ty);
     const float ew = expf(tw), eh = expf(th);
     const float cx = __fdiv_rn(__fadd_rn(sx, (float)i), fW);
@@ -93,6 +104,13 @@ __device__ __forceinline__ float4 tl_decode_box(const float *q, int HW, int i, i
 __device__ __forceinline__ float tl_iou(const float4 &a, float area_a, const float4 &b, float area_b) {
     const float inter = pair_inter(a, b);
     return __fdiv_rn(inter, pair_union(area_a, area_b, inter));
+}
+
+// t * area * 2^-13 for the divide-free test; NaN when the box must take the exact path
+__device__ __forceinline__ float tl_ta(const float4 &b, float area, float ts) {
+    const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    const bool ok = ts > 0.0f && area >= 1e-20f && area <= 1e20f && big < 4096.0f;
+    return ok ? __fmul_rn(area, ts) : __int_as_float(0x7fc00000);
 }
 
 // box_ciou (yolo_loss.py:257-293) with box1 = gt, box2 = pred; returns v = iou - term
@@ -135,34 +153,48 @@ __device__ __forceinline__ float tl_box_giou(const float4 &b1, const float4 &b2,
     return __fsub_rn(iou, term);
 }
 
+// exact max_g IoU < ignore_threshold (:115-125): torch.max propagates NaN, NaN < thr is false
+__device__ __noinline__ bool tl_below_exact(const float4 *gbox, const float *garea, int nG, const float4 pb, float pa, float thr) {
+    bool below = true;
+    for (int t = 0; t < nG; ++t) {
+        const float4 gb = gbox[t];
+        const float inter = pair_inter(gb, pb);
+        const float u = pair_union(garea[t], pa, inter);
+        below = below && (__fdiv_rn(inter, u) < thr);
+    }
+    return below;
+}
+
 __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams p) {
     extern __shared__ __align__(16) unsigned char tl_smem[];
     float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
     float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * kTLMaxGT);
-    int *s_gcls = reinterpret_cast<int *>(tl_smem + 20 * kTLMaxGT);
-    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 24 * kTLMaxGT);
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 24 * kTLMaxGT + 8 * kTLMaxAssign);
+    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * kTLMaxGT);
+    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * kTLMaxGT);
+    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * kTLMaxGT);
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * kTLMaxGT + 8 * kTLMaxAssign);
     const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
-    double *s_red = reinterpret_cast<double *>(tl_smem + 24 * kTLMaxGT + 8 * kTLMaxAssign + flag_bytes);
+    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * kTLMaxGT + 8 * kTLMaxAssign + flag_bytes);
     int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
 
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
+    const bool lead = (split == 0);  // the CTA of the image that owns the per-GT outputs and the assignments
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g0 = p.gt_off[b];
     int nG = p.gt_off[b + 1] - g0;
     const int HW = p.HW, W = p.W, H = p.H, A = p.A, C = p.C;
 
-    if (tid == 0) s_misc[0] = 0;  // assignment list length
+    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }  // assignment list length; any degenerate GT box
     for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
     if (nG > kTLMaxGT) {
-        if (tid == 0) atomicMax(p.status, 2);  // too many GT boxes for one image
-        nG = 0;                                // (the shim raises; keep the kernel well defined)
+        if (tid == 0 && lead) atomicMax(p.status, 2);  // too many GT boxes for one image
+        nG = 0;                                        // (the shim raises; keep the kernel well defined)
     }
     __syncthreads();
 
-    double acc[12];
+    double acc[10];
 #pragma unroll
-    for (int q = 0; q < 12; ++q) acc[q] = 0.0;
+    for (int q = 0; q < 10; ++q) acc[q] = 0.0;
 
     // ---------------- P1: per-GT anchor matching ----------------
     for (int t = tid; t < nG; t += kTLThreads) {
@@ -173,13 +205,17 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
         bx.y = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
         bx.z = __fadd_rn(gw, bx.x);
         bx.w = __fadd_rn(gh, bx.y);
+        const float barea = box_area(bx);
+        const float bta = tl_ta(bx, barea, p.ts);
         s_gbox[t] = bx;
-        s_garea[t] = box_area(bx);
+        s_garea[t] = barea;
+        s_gta[t] = bta;
+        if (bta != bta) s_misc[1] = 1;
         const int cls = (int)__fsub_rn(gc, 1.0f);                   // :131,147
         s_gcls[t] = cls;
         const int gi = (int)__fmul_rn(gx, p.fW), gj = (int)__fmul_rn(gy, p.fH);  // :128,136-137
         const bool ok = gi >= 0 && gi < W && gj >= 0 && gj < H && cls >= 0 && cls < C;
-        if (!ok) atomicMax(p.status, 1);
+        if (!ok && lead) atomicMax(p.status, 1);
         // anchor-vs-GT IoU on (0,0,w,h) shapes, ALL anchors (:129-133)
         const float4 gb = make_float4(0.f, 0.f, gw, gh);
         const float ga = box_area(gb);
@@ -194,11 +230,11 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
         }
         for (int k = 0; k < A; ++k) {
             const bool asg = ok && (p.mask[k] == best_n || ((over >> p.mask[k]) & 1u));  // :141-145
-            if (p.assign) {
+            if (p.assign && lead) {
                 int *r = p.assign + ((size_t)(g0 + t) * A + k) * 4;
                 r[0] = asg ? 1 : 0; r[1] = gj; r[2] = gi; r[3] = best_n;
             }
-            if (p.terms && !asg) {
+            if (p.terms && lead && !asg) {
                 float *r = p.terms + ((size_t)(g0 + t) * A + k) * 2;
                 r[0] = 0.f; r[1] = 0.f;
             }
@@ -208,7 +244,7 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
                 if (e < kTLMaxAssign) {
                     s_list[e].cell = cell;
                     s_list[e].t = (uint32_t)t;
-                } else {
+                } else if (lead) {
                     atomicMax(p.status, 2);
                 }
                 s_flag[cell] = 1;
@@ -217,112 +253,139 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
     }
     __syncthreads();
     const int nE = min(s_misc[0], kTLMaxAssign);
+    const bool gt_degenerate = s_misc[1] != 0;
 
     // ---------------- P2: per-cell objectness / ignore mask ----------------
-    const int cells_pad = (p.cells + 31) & ~31;
-    for (int cell = tid; cell < cells_pad; cell += kTLThreads) {
-        const bool valid = cell < p.cells;
-        bool undecided = false;  // still "max IoU < ignore_threshold so far"
-        float conf = 0.f;
-        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-        float pa = 0.f;
-        if (valid) {
-            const int a = (int)(((float)cell + 0.5f) * p.invHW);
-            const int pos = cell - a * HW;
-            const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
-            conf = sigmoid_f(__ldg(q + 4 * (size_t)HW));            // output[...,0] :87
-            acc[B200YOLO_S_CONF_ALL] += (double)conf;               // :98
-            if (s_flag[cell]) {                                     // :149-150 target 1, weight 1
-                const float df = __fsub_rn(conf, 1.0f);
-                acc[B200YOLO_S_SQW] += (double)__fmul_rn(df, df);
-                acc[B200YOLO_S_W] += 1.0;
-            } else if (nG == 0) {                                   // :108-111
+    const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
+    for (int cell = cell_lo + tid; cell < cell_hi; cell += kTLThreads) {
+        const int a = (int)(((float)cell + 0.5f) * p.invHW);
+        const int pos = cell - a * HW;
+        const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
+        const bool flagged = s_flag[cell] != 0;
+        const bool need_box = !flagged && nG > 0;
+        float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f;
+        if (need_box) {
+            tx = __ldcs(q);
+            ty = __ldcs(q + HW);
+            tw = __ldcs(q + 2 * (size_t)HW);
+            th = __ldcs(q + 3 * (size_t)HW);
+        }
+        const float conf = sigmoid_f(__ldg(q + 4 * (size_t)HW));    // output[...,0] :87
+        acc[B200YOLO_S_CONF_ALL] += (double)conf;                   // :98
+        if (flagged) {                                              // :149-150 target 1, weight 1
+            const float df = __fsub_rn(conf, 1.0f);
+            acc[B200YOLO_S_SQW] += (double)__fmul_rn(df, df);
+            acc[B200YOLO_S_W] += 1.0;
+        } else if (nG == 0) {                                       // :108-111
+            acc[B200YOLO_S_SQW] += (double)__fmul_rn(conf, conf);
+            acc[B200YOLO_S_W] += 1.0;
+        } else {
+            const int j = (int)(((float)pos + 0.5f) * p.invW);
+            const int i = pos - j * W;
+            const float4 pb = tl_decode_box(tx, ty, tw, th, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
+            const float pa = box_area(pb);
+            const float pta = tl_ta(pb, pa, p.ts);
+            // divide-free pass over the GT boxes: d > 0 <=> iou < thr
+            float dmin = INFINITY, m = INFINITY;
+#pragma unroll 4
+            for (int t = 0; t < nG; ++t) {
+                const float4 gb = s_gbox[t];
+                const float w = __fsub_rn(fminf(pb.z, gb.z), fmaxf(pb.x, gb.x));
+                const float h = __fsub_rn(fminf(pb.w, gb.w), fmaxf(pb.y, gb.y));
+                const float ws = __saturatef(__fmul_rn(w, 1.220703125e-4f));  // max(w,0) * 2^-13
+                const float sum = __fadd_rn(pta, s_gta[t]);
+                const float d = __fmaf_rn(-ws, h, sum);
+                dmin = fminf(dmin, d);
+                m = fminf(m, __fmaf_rn(sum, -kTLEps, fabsf(d)));
+            }
+            bool below;
+            if (gt_degenerate || pta != pta || !(m > 0.0f)) below = tl_below_exact(s_gbox, s_garea, nG, pb, pa, p.ignore_thr);
+            else below = dmin > 0.0f;
+            if (below) {                                            // :123-125 weight 1, target 0
                 acc[B200YOLO_S_SQW] += (double)__fmul_rn(conf, conf);
                 acc[B200YOLO_S_W] += 1.0;
-            } else {
-                const int j = (int)(((float)pos + 0.5f) * p.invW);
-                const int i = pos - j * W;
-                pb = tl_decode_box(q, HW, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
-                pa = box_area(pb);
-                undecided = true;
             }
         }
-        if (nG > 0) {
-            bool below = undecided;
-            for (int t = 0; t < nG; ++t) {
-                if (!__any_sync(kFullMask, below)) break;
-                if (below) {
-                    const float4 gb = s_gbox[t];
-                    const float inter = pair_inter(gb, pb);
-                    const float u = pair_union(s_garea[t], pa, inter);
-                    // iou < thr, decided without the divide unless within 4e-6 of the threshold
-                    bool lt;
-                    const float d = __fmaf_rn(-p.ignore_thr, u, inter);
-                    const float e = __fmul_rn(4e-6f, u);
-                    if (u > 0.0f && d < -e) lt = true;
-                    else if (u > 0.0f && d > e) lt = false;
-                    else lt = __fdiv_rn(inter, u) < p.ignore_thr;   // NaN -> false (torch.max propagates NaN)
-                    below = lt;
+    }
+
+    // ---------------- P3: per-assignment terms (warp per assignment) ----------------
+    if (lead) {
+        for (int e = warp; e < nE; e += kTLWarps) {
+            const uint32_t cell = s_list[e].cell;
+            const int t = (int)s_list[e].t;
+            const int a = (int)(((float)cell + 0.5f) * p.invHW);
+            const int pos = (int)cell - a * HW;
+            const int j = (int)(((float)pos + 0.5f) * p.invW);
+            const int i = pos - j * W;
+            const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
+            const int cls = s_gcls[t];
+            // lanes 0..4 fetch the five box/conf logits, lane 5 the GT's class logit
+            float v5 = 0.f;
+            if (lane < 6) v5 = __ldg(q + (size_t)(lane < 5 ? lane : 5 + cls) * HW);
+            const float tx = __shfl_sync(kFullMask, v5, 0), ty = __shfl_sync(kFullMask, v5, 1);
+            const float tw = __shfl_sync(kFullMask, v5, 2), th = __shfl_sync(kFullMask, v5, 3);
+            const float tc = __shfl_sync(kFullMask, v5, 4), tk = __shfl_sync(kFullMask, v5, 5);
+            // duplicates of this cell in the list: is this its first entry, which classes are assigned
+            bool earlier = false;
+            for (int f0 = 0; f0 < nE; f0 += 32) {
+                const int f = f0 + lane;
+                const bool same = f < nE && s_list[f].cell == cell;
+                earlier = earlier || (__ballot_sync(kFullMask, same && f < e) != 0u);
+            }
+            if (lane == 0) {
+                const float4 pb = tl_decode_box(tx, ty, tw, th, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
+                const float conf = sigmoid_f(tc);
+                const float4 gb = s_gbox[t];
+                float iou;
+                const float v = tl_box_ciou(gb, pb, &iou);              // :157
+                const float wt = __fsub_rn(2.0f, s_garea[t]);           // :160
+                const float dv = __fsub_rn(v, 1.0f);
+                acc[B200YOLO_S_IOU_SQ] += (double)__fmul_rn(dv, dv);
+                acc[B200YOLO_S_IOU_W] += (double)wt;
+                acc[B200YOLO_S_NASSIGN] += 1.0;                         // :146
+                acc[B200YOLO_S_OBJ] += (double)conf;                    // :152
+                acc[B200YOLO_S_IOU] += (double)iou;                     // :165
+                if (iou > p.ignore_thr) acc[B200YOLO_S_RECALL] += 1.0;  // :163
+                acc[B200YOLO_S_CLS] += (double)sigmoid_f(tk);           // :169
+                if (p.terms) {
+                    float *r = p.terms + ((size_t)(g0 + t) * A + a) * 2;  // cell = (k*H+gj)*W+gi -> k == a
+                    r[0] = v; r[1] = iou;
                 }
             }
-            if (undecided && below) {                               // :123-125 weight 1, target 0
-                acc[B200YOLO_S_SQW] += (double)__fmul_rn(conf, conf);
-                acc[B200YOLO_S_W] += 1.0;
+            // class channels: once per distinct cell, by its first list entry; lanes = classes
+            if (!earlier) {
+                double sq = 0.0;
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    const int c = c0 + lane;
+                    float o = 0.f;
+                    if (c < C) o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
+                    bool hit = (c == cls);
+                    for (int f0 = 0; f0 < nE; f0 += 32) {
+                        const int f = f0 + lane;
+                        unsigned bal = __ballot_sync(kFullMask, f < nE && s_list[f].cell == cell);
+                        while (bal) {
+                            const int f2 = f0 + __ffs(bal) - 1;
+                            bal &= bal - 1u;
+                            hit = hit || (s_gcls[s_list[f2].t] == c);
+                        }
+                    }
+                    if (c < C) {
+                        const float tv = hit ? 0.95f : 0.05f;           // :426-433
+                        const float df = __fsub_rn(o, tv);
+                        sq += (double)__fmul_rn(df, df);
+                    }
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) sq += __shfl_xor_sync(kFullMask, sq, sh);
+                if (lane == 0) {
+                    acc[B200YOLO_S_SQW] += sq;
+                    acc[B200YOLO_S_W] += (double)C;
+                }
             }
         }
     }
 
-    // ---------------- P3: per-assignment terms ----------------
-    for (int e = tid; e < nE; e += kTLThreads) {
-        const uint32_t cell = s_list[e].cell;
-        const int t = (int)s_list[e].t;
-        const int a = (int)(((float)cell + 0.5f) * p.invHW);
-        const int pos = (int)cell - a * HW;
-        const int j = (int)(((float)pos + 0.5f) * p.invW);
-        const int i = pos - j * W;
-        const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
-        const float4 pb = tl_decode_box(q, HW, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
-        const float conf = sigmoid_f(__ldg(q + 4 * (size_t)HW));
-        const float4 gb = s_gbox[t];
-        float iou;
-        const float v = tl_box_ciou(gb, pb, &iou);                  // :157
-        const float wt = __fsub_rn(2.0f, s_garea[t]);               // :160
-        const float dv = __fsub_rn(v, 1.0f);
-        acc[B200YOLO_S_IOU_SQ] += (double)__fmul_rn(dv, dv);
-        acc[B200YOLO_S_IOU_W] += (double)wt;
-        acc[B200YOLO_S_NASSIGN] += 1.0;                             // :146
-        acc[B200YOLO_S_OBJ] += (double)conf;                        // :152
-        acc[B200YOLO_S_IOU] += (double)iou;                         // :165
-        if (iou > p.ignore_thr) acc[B200YOLO_S_RECALL] += 1.0;      // :163
-        const int cls = s_gcls[t];
-        acc[B200YOLO_S_CLS] += (double)sigmoid_f(__ldg(q + (size_t)(5 + cls) * HW));  // :169
-        if (p.terms) {
-            // locate k: cell = (k*H+gj)*W+gi -> k == a
-            float *r = p.terms + ((size_t)(g0 + t) * A + a) * 2;
-            r[0] = v; r[1] = iou;
-        }
-        // class channels: once per distinct cell, by its first list entry
-        bool first = true;
-        for (int f = 0; f < e; ++f)
-            if (s_list[f].cell == cell) { first = false; break; }
-        if (first) {
-            double sq = 0.0;
-            for (int c = 0; c < C; ++c) {
-                const float o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
-                bool hit = (c == cls);
-                if (!hit)
-                    for (int f = e + 1; f < nE; ++f)
-                        if (s_list[f].cell == cell && s_gcls[s_list[f].t] == c) { hit = true; break; }
-                const float tv = hit ? 0.95f : 0.05f;               // :426-433
-                const float df = __fsub_rn(o, tv);
-                sq += (double)__fmul_rn(df, df);
-            }
-            acc[B200YOLO_S_SQW] += sq;
-            acc[B200YOLO_S_W] += (double)C;
-        }
-    }
-
-    // ---------------- P4: block reduction -> per-image partials ----------------
+    // ---------------- P4: block reduction -> per-CTA partials ----------------
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
         double v = acc[q];
@@ -335,17 +398,17 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
         double v = 0.0;
         if (tid < 10)
             for (int w = 0; w < kTLWarps; ++w) v += s_red[tid * kTLWarps + w];
-        else if (tid == B200YOLO_S_NCELLS) v = (double)p.cells;
-        else if (tid == B200YOLO_S_NIMG) v = 1.0;
-        p.partial[(size_t)b * kTLSums + tid] = v;
+        else if (tid == B200YOLO_S_NCELLS && lead) v = (double)p.cells;
+        else if (tid == B200YOLO_S_NIMG && lead) v = 1.0;
+        p.partial[((size_t)b * p.S + split) * kTLSums + tid] = v;
     }
 }
 
-// fixed-order sum over images -> sums[16] (bitwise reproducible run to run)
-__global__ void __launch_bounds__(kTLSums * 32) target_loss_reduce_kernel(const double *partial, int N, double *sums) {
+// fixed-order sum over the per-CTA partials -> sums[16] (bitwise reproducible run to run)
+__global__ void __launch_bounds__(kTLSums * 32) target_loss_reduce_kernel(const double *partial, int rows, double *sums) {
     const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v = 0.0;
-    for (int b = lane; b < N; b += 32) v += partial[(size_t)b * kTLSums + q];
+    for (int b = lane; b < rows; b += 32) v += partial[(size_t)b * kTLSums + q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
     if (lane == 0) sums[q] = v;

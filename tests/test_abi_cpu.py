@@ -34,7 +34,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert rc == -1 and b"null" in lib.b200yolo_last_error()
     rc = lib.b200yolo_pairwise(None, -1, None, 2, 2, None, None)
     assert rc == -1
-    assert lib.b200yolo_target_loss_workspace_bytes(4) == 4 * 16 * 8
+    assert lib.b200yolo_target_loss_workspace_bytes(4) == 4 * 8 * 16 * 8  # N x (CTAs per image <= 8) x 16 doubles
 
 
 def test_loss_finalize_matches_reference_formulas(lib):

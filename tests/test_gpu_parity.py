@@ -232,6 +232,31 @@ def test_fused_configs_vs_oracle(name, N, C, grids, anchors, img, thr, shift, cu
             np.testing.assert_allclose(a[:, :6], b[:, :6], rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("C,grids,anchors,img", [
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352]),
+    (20, [(13, 13), (26, 26)], VOC_ANCHORS, [416, 416]),
+    (10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384]),
+])
+def test_compile_time_shapes_equal_runtime_shape_path(C, grids, anchors, img, cuda_device):
+    """The reference's own head shapes run a kernel compiled with the plane stride as a
+    constant; debug flag 16 forces the runtime-stride kernel.  Same arithmetic: bit-equal."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    h0, h1 = make_heads(5, C, grids, seed=21)
+    tables = anchor_tables(anchors, img)
+    lib = _lib.load()
+    try:
+        lib.b200yolo_debug_set_flags(0)
+        a = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, C, 0.3, want_idx=True)
+        lib.b200yolo_debug_set_flags(16)
+        b = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, C, 0.3, want_idx=True)
+    finally:
+        lib.b200yolo_debug_set_flags(0)
+    cnt = a[1].cpu().numpy()
+    assert np.array_equal(cnt, b[1].cpu().numpy()) and cnt.sum() > 0
+    for i, k in enumerate(cnt):
+        assert torch.equal(a[0][i, :k], b[0][i, :k]) and torch.equal(a[2][i, :k], b[2][i, :k])
+
+
 def test_fused_matches_separate_entry_points(cuda_device):
     """decode_nms(out0,out1) == nms((loss0(out0), loss1(out1))) -- the three separate
     entry points stay callable and equal."""
