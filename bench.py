@@ -168,6 +168,22 @@ def cpu_decode_nms_rate(wl, budget_s=12.0, max_reps=50):
     return N / med, reps, med
 
 
+def cpu_loss_rate(N, G):
+    """images/s of the CPU oracle port for YOLOLoss.forward(input, targets), both VOC heads."""
+    import oracle
+    wl = WORKLOADS["cfg2"]
+    h0, h1 = make_heads(wl, N, seed=100)
+    targets = make_targets(N, G, wl["C"], 1)
+    args = [(h0.numpy(), MASK[0], VOC_IGNORE[0]), (h1.numpy(), MASK[1], VOC_IGNORE[1])]
+    best = 1e9
+    for _ in range(3):
+        t = time.perf_counter()
+        for h, m, ign in args:
+            oracle.target_loss(h, targets, VOC_ANCHORS, m, wl["C"], [352, 352], ign, VOC_IOU_THRESH, VOC_IOU_WEIGHTING)
+        best = min(best, time.perf_counter() - t)
+    return N / best
+
+
 def run_reference(args, wl):
     """--impl reference: the CPU path (oracle port), rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -233,8 +249,8 @@ def time_loss(dev, N, G, steps=100, seed=1):
 
     def step(i):
         h0, h1 = sets[i % R]
-        ops.target_loss_sums(h0, gt, gt_off, Gt, sa, MASK[0], C, VOC_IGNORE[0], VOC_IOU_THRESH)
-        ops.target_loss_sums(h1, gt, gt_off, Gt, sa, MASK[1], C, VOC_IGNORE[1], VOC_IOU_THRESH)
+        ops.target_loss_sums(h0, gt, gt_off, Gt, sa, MASK[0], C, VOC_IGNORE[0], VOC_IOU_THRESH, max_gt=G)
+        ops.target_loss_sums(h1, gt, gt_off, Gt, sa, MASK[1], C, VOC_IGNORE[1], VOC_IOU_THRESH, max_gt=G)
 
     for i in range(5):
         step(i)
@@ -374,6 +390,39 @@ def run_b200(args, wl):
                                      "kept_rows_per_image": float(np.mean(skept)) / N,
                                      "algorithmic_gbs": sbytes / (sms * 1e-3) / 1e9}
             del ssets
+        # the same steps issued round-robin on two streams (separate output buffers): consecutive launches
+        # overlap, so one launch's decode (memory phase) runs under the other's NMS (issue-bound phase)
+        s2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        o2 = [torch.empty_like(out) for _ in range(2)]
+        c2 = [torch.empty_like(cnt) for _ in range(2)]
+
+        def pstep(i):
+            h0, h1 = sets[i % R]
+            with torch.cuda.stream(s2[i & 1]):
+                ops.decode_nms_padded(h0, h1, tables, C, conf, out=o2[i & 1], out_count=c2[i & 1])
+
+        for i in range(6):
+            pstep(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pstep(i)
+        torch.cuda.synchronize()
+        pms = (time.perf_counter() - t0) * 1e3 / args.steps
+        extra["two_streams"] = {"images_per_s_per_gpu": N / (pms * 1e-3), "ms_per_step": pms,
+                                "note": "throughput of overlapped launches (host wall clock); the headline value is single-stream"}
+        # YOLOLoss target assignment + loss sums, BASELINE config 4 (both heads, 100 GT boxes per image)
+        if rank == 0:
+            try:
+                lN = 512
+                lres = time_loss(dev, lN, 100, steps=max(20, args.steps // 2))
+                lres["hbm_frac"] = lres["algorithmic_gbs"] / float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) \
+                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else lres["algorithmic_gbs"] / 6650.0
+                lres["bound"] = "issue (92.9 M box pairs x ~14 instructions), not HBM"
+                lres["cpu_port_images_per_s"] = cpu_loss_rate(32, 100)
+                extra["loss_cfg4"] = lres
+            except Exception as e:  # noqa: BLE001
+                extra["loss_cfg4"] = {"error": repr(e)}
         # all-gather of the fixed-stride detections (the only collective the path may need)
         if world > 1:
             def gstep(i):

@@ -129,14 +129,16 @@ int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int 
  *   anchors_all HOST [NA][2] ALL anchors / img_size, fp32;  mask HOST [A]
  *   gt        dev [G][5] rows [cls(1-based), cx, cy, w, h]; gt_off dev [N+1]
  *   G         total number of GT rows (= gt_off[N] on the host)
+ *   max_gt_per_image  upper bound on the GT rows of any one image (sizes the shared-memory
+ *             staging; 0 = unknown: min(G, 1024) is assumed).  At most 1024.
  *   sums      dev double[16], OVERWRITTEN with this call's partial sums (see
  *             B200YOLO_S_* below).  Data-parallel callers all-reduce(SUM) this
  *             vector across ranks, then call b200yolo_loss_finalize.
  *   assign    dev int32 [G][A][4] = (assigned?, gj, gi, best_n) per (GT, k), or NULL
  *   terms     dev float [G][A][2] = (ciou value v, iou) per (GT, k), or NULL
  *   status    dev int32[1], overwritten: 0 ok, 1 a GT maps outside the grid or has
- *             a class outside [1,C] (reference: IndexError), 2 more than 1024 GT
- *             boxes in one image
+ *             a class outside [1,C] (reference: IndexError), 2 an image has more GT
+ *             boxes than max_gt_per_image / 1024
  *   grad      dev (N, A*(5+C), H, W) or NULL: reserved (must be NULL in this version)
  *   workspace dev, b200yolo_target_loss_workspace_bytes(N) bytes: per-CTA partial sums
  *             (up to 8 CTAs share an image), reduced in a fixed order so results are
@@ -145,8 +147,8 @@ int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int 
 size_t b200yolo_target_loss_workspace_bytes(int N);
 int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
                          const int *mask, const float *gt, const int *gt_off, int G, float ignore_thr,
-                         float iou_thr, double *sums, int *assign, float *terms, int *status, float *grad,
-                         void *workspace, size_t workspace_bytes, void *stream);
+                         float iou_thr, int max_gt_per_image, double *sums, int *assign, float *terms, int *status,
+                         float *grad, void *workspace, size_t workspace_bytes, void *stream);
 
 /* indices into the partial-sum vector of b200yolo_target_loss */
 enum {

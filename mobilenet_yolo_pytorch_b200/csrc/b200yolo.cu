@@ -253,8 +253,8 @@ int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int 
 
 int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
                          const int *mask, const float *gt, const int *gt_off, int G, float ignore_thr,
-                         float iou_thr, double *sums, int *assign, float *terms, int *status, float *grad,
-                         void *workspace, size_t workspace_bytes, void *stream) {
+                         float iou_thr, int max_gt_per_image, double *sums, int *assign, float *terms, int *status,
+                         float *grad, void *workspace, size_t workspace_bytes, void *stream) {
     if (!head || !anchors_all || !mask || !gt_off || !sums || !status)
         return fail(B200YOLO_EINVAL, "target_loss: null pointer");
     if (G > 0 && !gt) return fail(B200YOLO_EINVAL, "target_loss: null gt");
@@ -286,7 +286,12 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;
-    const uint32_t smem = tl_smem_bytes(p.cells);
+    // shared-memory staging sized for the largest image (the caller's bound, else min(G, 1024))
+    int gcap = (max_gt_per_image > 0) ? max_gt_per_image : G;
+    if (gcap > kTLMaxGT) gcap = kTLMaxGT;
+    if (gcap < 1) gcap = 1;
+    p.gcap = (gcap + 3) / 4 * 4;
+    const uint32_t smem = tl_smem_bytes(p.cells, p.gcap, A);
     const int lim = smem_optin(dev);
     if ((int)smem > lim)
         return fail(B200YOLO_EUNSUPPORTED, "target_loss: %d cells per image need %u B of shared memory (limit %d B)",

@@ -20,9 +20,9 @@
 //       one FFMA, the cell keeps min d and min(|d| - 1e-5*t*(areas)); only a cell with a pair
 //       closer than 1e-5 to the threshold (or a degenerate box) re-runs its GT loop with
 //       the reference's IEEE arithmetic (inter/union < thr).
-//   P3  warp per assignment (first CTA of the image): CIoU term (box_ciou :257-293),
-//       recall / iou / obj / class-score stats (:151-169); the first assignment of each
-//       distinct cell adds the class-channel loss, lanes = classes, with the union of
+//   P3  (first CTA of the image) thread per assignment: CIoU term (box_ciou :257-293),
+//       recall / iou / obj / class-score stats (:151-169); then warp per distinct assigned
+//       cell: the class-channel loss, lanes = classes, with the union of
 //       assigned classes at 0.95, the rest at 0.05 (class_loss :425-434 -- order
 //       independent, duplicates counted exactly like the sequential reference).
 //   P4  deterministic reduction: per-CTA partial sums -> workspace, then a
@@ -49,6 +49,7 @@ struct TLParams {
     const float *head;
     int N, A, C, attrs, H, W, HW, cells, NA;
     int S, chunk;  // CTAs per image; cells per CTA (multiple of 32)
+    int gcap;      // GT boxes per image the shared-memory staging holds (<= kTLMaxGT); the list holds A*gcap assignments
     float invHW, invW, fW, fH;
     float aw_all[kTLMaxAllAnchors], ah_all[kTLMaxAllAnchors];
     int mask[kTLMaxAnchors];
@@ -69,15 +70,13 @@ struct TLAssign {
     uint32_t t;     // GT index inside the image
 };
 
-constexpr int kTLMaxAssign = kTLMaxGT * kTLMaxAnchors / 2;
-
-__host__ __device__ inline uint32_t tl_smem_bytes(int cells) {
+__host__ __device__ inline uint32_t tl_smem_bytes(int cells, int gcap, int A) {
     uint32_t o = 0;
-    o += 16 * kTLMaxGT;                       // gt xyxy
-    o += 4 * kTLMaxGT;                        // gt area
-    o += 4 * kTLMaxGT;                        // gt t*area*2^-13
-    o += 4 * kTLMaxGT;                        // gt class (0-based)
-    o += 8 * kTLMaxAssign;                    // assignment list
+    o += 16 * (uint32_t)gcap;                 // gt xyxy
+    o += 4 * (uint32_t)gcap;                  // gt area
+    o += 4 * (uint32_t)gcap;                  // gt t*area*2^-13
+    o += 4 * (uint32_t)gcap;                  // gt class (0-based)
+    o += 8 * (uint32_t)(gcap * A);            // assignment list (every GT can be assigned to all A anchors of the head)
     o += ((uint32_t)cells + 15u) / 16u * 16u; // assigned-cell flags
     o += 8 * kTLSums * kTLWarps;              // reduction scratch
     o += 64;
@@ -167,14 +166,15 @@ __device__ __noinline__ bool tl_below_exact(const float4 *gbox, const float *gar
 
 __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams p) {
     extern __shared__ __align__(16) unsigned char tl_smem[];
+    const uint32_t gcap = (uint32_t)p.gcap, lcap = (uint32_t)(p.gcap * p.A);
     float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
-    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * kTLMaxGT);
-    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * kTLMaxGT);
-    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * kTLMaxGT);
-    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * kTLMaxGT);
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * kTLMaxGT + 8 * kTLMaxAssign);
+    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * gcap);
+    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * gcap);
+    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * gcap);
+    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * gcap);
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * gcap + 8 * lcap);
     const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
-    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * kTLMaxGT + 8 * kTLMaxAssign + flag_bytes);
+    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * gcap + 8 * lcap + flag_bytes);
     int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
 
     const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
 
     if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }  // assignment list length; any degenerate GT box
     for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
-    if (nG > kTLMaxGT) {
-        if (tid == 0 && lead) atomicMax(p.status, 2);  // too many GT boxes for one image
+    if (nG > p.gcap) {
+        if (tid == 0 && lead) atomicMax(p.status, 2);  // more GT boxes in one image than the staging holds
         nG = 0;                                        // (the shim raises; keep the kernel well defined)
     }
     __syncthreads();
@@ -241,18 +241,14 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
             if (asg) {
                 const uint32_t cell = (uint32_t)((k * H + gj) * W + gi);
                 const int e = atomicAdd(&s_misc[0], 1);
-                if (e < kTLMaxAssign) {
-                    s_list[e].cell = cell;
-                    s_list[e].t = (uint32_t)t;
-                } else if (lead) {
-                    atomicMax(p.status, 2);
-                }
+                s_list[e].cell = cell;  // e < A * nG <= A * gcap
+                s_list[e].t = (uint32_t)t;
                 s_flag[cell] = 1;
             }
         }
     }
     __syncthreads();
-    const int nE = min(s_misc[0], kTLMaxAssign);
+    const int nE = s_misc[0];
     const bool gt_degenerate = s_misc[1] != 0;
 
     // ---------------- P2: per-cell objectness / ignore mask ----------------
@@ -308,9 +304,10 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
         }
     }
 
-    // ---------------- P3: per-assignment terms (warp per assignment) ----------------
+    // ---------------- P3a: per-assignment terms (thread per assignment) ----------------
+    constexpr uint32_t kDup = 0x80000000u;  // s_list[e].t bit 31: an earlier entry has the same cell
     if (lead) {
-        for (int e = warp; e < nE; e += kTLWarps) {
+        for (int e = tid; e < nE; e += kTLThreads) {
             const uint32_t cell = s_list[e].cell;
             const int t = (int)s_list[e].t;
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
@@ -319,68 +316,66 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
             const int i = pos - j * W;
             const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
             const int cls = s_gcls[t];
-            // lanes 0..4 fetch the five box/conf logits, lane 5 the GT's class logit
-            float v5 = 0.f;
-            if (lane < 6) v5 = __ldg(q + (size_t)(lane < 5 ? lane : 5 + cls) * HW);
-            const float tx = __shfl_sync(kFullMask, v5, 0), ty = __shfl_sync(kFullMask, v5, 1);
-            const float tw = __shfl_sync(kFullMask, v5, 2), th = __shfl_sync(kFullMask, v5, 3);
-            const float tc = __shfl_sync(kFullMask, v5, 4), tk = __shfl_sync(kFullMask, v5, 5);
-            // duplicates of this cell in the list: is this its first entry, which classes are assigned
-            bool earlier = false;
-            for (int f0 = 0; f0 < nE; f0 += 32) {
-                const int f = f0 + lane;
-                const bool same = f < nE && s_list[f].cell == cell;
-                earlier = earlier || (__ballot_sync(kFullMask, same && f < e) != 0u);
+            const float tx = __ldg(q), ty = __ldg(q + HW), tw = __ldg(q + 2 * (size_t)HW), th = __ldg(q + 3 * (size_t)HW);
+            const float tc = __ldg(q + 4 * (size_t)HW), tk = __ldg(q + (size_t)(5 + cls) * HW);
+            const float4 pb = tl_decode_box(tx, ty, tw, th, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
+            const float conf = sigmoid_f(tc);
+            const float4 gb = s_gbox[t];
+            float iou;
+            const float v = tl_box_ciou(gb, pb, &iou);                  // :157
+            const float wt = __fsub_rn(2.0f, s_garea[t]);               // :160
+            const float dv = __fsub_rn(v, 1.0f);
+            acc[B200YOLO_S_IOU_SQ] += (double)__fmul_rn(dv, dv);
+            acc[B200YOLO_S_IOU_W] += (double)wt;
+            acc[B200YOLO_S_NASSIGN] += 1.0;                             // :146
+            acc[B200YOLO_S_OBJ] += (double)conf;                        // :152
+            acc[B200YOLO_S_IOU] += (double)iou;                         // :165
+            if (iou > p.ignore_thr) acc[B200YOLO_S_RECALL] += 1.0;      // :163
+            acc[B200YOLO_S_CLS] += (double)sigmoid_f(tk);               // :169
+            if (p.terms) {
+                float *r = p.terms + ((size_t)(g0 + t) * A + a) * 2;    // cell = (k*H+gj)*W+gi -> k == a
+                r[0] = v; r[1] = iou;
             }
-            if (lane == 0) {
-                const float4 pb = tl_decode_box(tx, ty, tw, th, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
-                const float conf = sigmoid_f(tc);
-                const float4 gb = s_gbox[t];
-                float iou;
-                const float v = tl_box_ciou(gb, pb, &iou);              // :157
-                const float wt = __fsub_rn(2.0f, s_garea[t]);           // :160
-                const float dv = __fsub_rn(v, 1.0f);
-                acc[B200YOLO_S_IOU_SQ] += (double)__fmul_rn(dv, dv);
-                acc[B200YOLO_S_IOU_W] += (double)wt;
-                acc[B200YOLO_S_NASSIGN] += 1.0;                         // :146
-                acc[B200YOLO_S_OBJ] += (double)conf;                    // :152
-                acc[B200YOLO_S_IOU] += (double)iou;                     // :165
-                if (iou > p.ignore_thr) acc[B200YOLO_S_RECALL] += 1.0;  // :163
-                acc[B200YOLO_S_CLS] += (double)sigmoid_f(tk);           // :169
-                if (p.terms) {
-                    float *r = p.terms + ((size_t)(g0 + t) * A + a) * 2;  // cell = (k*H+gj)*W+gi -> k == a
-                    r[0] = v; r[1] = iou;
-                }
-            }
-            // class channels: once per distinct cell, by its first list entry; lanes = classes
-            if (!earlier) {
-                double sq = 0.0;
-                for (int c0 = 0; c0 < C; c0 += 32) {
-                    const int c = c0 + lane;
-                    float o = 0.f;
-                    if (c < C) o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
-                    bool hit = (c == cls);
-                    for (int f0 = 0; f0 < nE; f0 += 32) {
-                        const int f = f0 + lane;
-                        unsigned bal = __ballot_sync(kFullMask, f < nE && s_list[f].cell == cell);
-                        while (bal) {
-                            const int f2 = f0 + __ffs(bal) - 1;
-                            bal &= bal - 1u;
-                            hit = hit || (s_gcls[s_list[f2].t] == c);
-                        }
-                    }
-                    if (c < C) {
-                        const float tv = hit ? 0.95f : 0.05f;           // :426-433
-                        const float df = __fsub_rn(o, tv);
-                        sq += (double)__fmul_rn(df, df);
+            bool dup = false;
+            for (int f = 0; f < e; ++f) dup = dup || (s_list[f].cell == cell);
+            if (dup) s_list[e].t = (uint32_t)t | kDup;
+        }
+        __syncthreads();  // (lead is uniform in the CTA)
+        // ------------ P3b: class channels, once per distinct cell (its first list entry); warp per cell, lanes = classes
+        for (int e = warp; e < nE; e += kTLWarps) {
+            const uint32_t te = s_list[e].t;
+            if (te & kDup) continue;
+            const uint32_t cell = s_list[e].cell;
+            const int a = (int)(((float)cell + 0.5f) * p.invHW);
+            const int pos = (int)cell - a * HW;
+            const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
+            const int cls = s_gcls[te];
+            double sq = 0.0;
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                float o = 0.f;
+                if (c < C) o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
+                bool hit = (c == cls);
+                for (int f0 = e + 1 - ((e + 1) & 31); f0 < nE; f0 += 32) {  // later entries of the same cell
+                    const int f = f0 + lane;
+                    unsigned bal = __ballot_sync(kFullMask, f > e && f < nE && s_list[f].cell == cell);
+                    while (bal) {
+                        const int f2 = f0 + __ffs(bal) - 1;
+                        bal &= bal - 1u;
+                        hit = hit || (s_gcls[s_list[f2].t & ~kDup] == c);
                     }
                 }
+                if (c < C) {
+                    const float tv = hit ? 0.95f : 0.05f;               // :426-433
+                    const float df = __fsub_rn(o, tv);
+                    sq += (double)__fmul_rn(df, df);
+                }
+            }
 #pragma unroll
-                for (int sh = 16; sh > 0; sh >>= 1) sq += __shfl_xor_sync(kFullMask, sq, sh);
-                if (lane == 0) {
-                    acc[B200YOLO_S_SQW] += sq;
-                    acc[B200YOLO_S_W] += (double)C;
-                }
+            for (int sh = 16; sh > 0; sh >>= 1) sq += __shfl_xor_sync(kFullMask, sq, sh);
+            if (lane == 0) {
+                acc[B200YOLO_S_SQW] += sq;
+                acc[B200YOLO_S_W] += (double)C;
             }
         }
     }

@@ -15,6 +15,7 @@ import torch
 from . import _lib
 
 NMS_IOU_THRESHOLD = 0.45  # utils/box.py:28
+_WORKSPACES = {}  # (device index, stream) -> cached target-loss workspace tensor
 
 
 def scaled_anchors(anchors: Sequence[Sequence[float]], img_size: Sequence[float]) -> np.ndarray:
@@ -186,7 +187,7 @@ def pack_targets(targets, device) -> Tuple[torch.Tensor, torch.Tensor, int, List
 
 def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,
                      mask: Sequence[int], num_classes: int, ignore_thr: float, iou_thr: float,
-                     want_assign: bool = False):
+                     want_assign: bool = False, max_gt: int = 0):
     """b200yolo_target_loss: returns (sums (16,) float64 device, status (1,) int32 device[, assign, terms])."""
     _require_cuda(head, "head")
     head = head.contiguous()
@@ -198,17 +199,22 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
     m = np.ascontiguousarray(np.asarray(mask, dtype=np.int32))
     lib = _lib.load()
     with torch.cuda.device(head.device):
-        sums = torch.empty((_lib.S_COUNT,), dtype=torch.float64, device=head.device)
-        status = torch.empty((1,), dtype=torch.int32, device=head.device)
+        # one allocation: 16 partial sums (f64) + the status word; the per-CTA workspace is cached per
+        # (device, stream) and reused (calls on one stream are ordered, so reuse is safe)
+        buf = torch.empty((_lib.S_COUNT + 1,), dtype=torch.float64, device=head.device)
+        sums, status = buf[:_lib.S_COUNT], buf[_lib.S_COUNT:].view(torch.int32)[:1]
         ws_bytes = int(lib.b200yolo_target_loss_workspace_bytes(N))
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=head.device)
+        key = (head.device.index, torch.cuda.current_stream(head.device).cuda_stream)
+        ws = _WORKSPACES.get(key)
+        if ws is None or ws.numel() < ws_bytes:
+            ws = _WORKSPACES[key] = torch.empty((ws_bytes,), dtype=torch.uint8, device=head.device)
         assign = torch.empty((max(G, 1), A, 4), dtype=torch.int32, device=head.device) if want_assign else None
         terms = torch.empty((max(G, 1), A, 2), dtype=torch.float32, device=head.device) if want_assign else None
         _lib.check(lib.b200yolo_target_loss(
             head.data_ptr(), N, A, num_classes, H, W, sa.ctypes.data, sa.shape[0], m.ctypes.data, gt.data_ptr(),
-            gt_off.data_ptr(), int(G), float(np.float32(ignore_thr)), float(np.float32(iou_thr)), sums.data_ptr(),
+            gt_off.data_ptr(), int(G), float(np.float32(ignore_thr)), float(np.float32(iou_thr)), int(max_gt), sums.data_ptr(),
             assign.data_ptr() if want_assign else None, terms.data_ptr() if want_assign else None,
-            status.data_ptr(), None, ws.data_ptr(), ws_bytes, _stream(head)))
+            status.data_ptr(), None, ws.data_ptr(), ws.numel(), _stream(head)))
     return (sums, status, assign, terms) if want_assign else (sums, status)
 
 

@@ -65,9 +65,9 @@ class YOLOLoss(nn.Module):
         if targets is None:
             return self.get_pred_boxes(input)
         N = input.size(0)
-        gt, gt_off, G, _ = ops.pack_targets(targets, input.device)
+        gt, gt_off, G, counts = ops.pack_targets(targets, input.device)
         sums, status = ops.target_loss_sums(input, gt, gt_off, G, self.scaled_anchors(), self.mask, self.num_classes,
-                                            self.ignore_threshold, self.iou_thresh)
+                                            self.ignore_threshold, self.iou_thresh, max_gt=max(counts + [1]))
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.process_group)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none --csv`)
-per kernel: launches, total / mean duration and share of all GPU time in the capture.
+per (kernel, grid size): launches, total / mean duration and share of all GPU time in the capture.
 Usage: launch_share.py launches.csv"""
 import collections
 import csv
@@ -9,11 +9,11 @@ import sys
 tot = collections.defaultdict(lambda: [0, 0.0])
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
 hdr = rows[0]
-ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+ki, vi, mi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("Grid Size")
 for r in rows[1:]:
     if r[mi] != "gpu__time_duration.sum":
         continue
-    t = tot[r[ki]]
+    t = tot[r[ki].split('(')[0].replace('void ', '') + ' grid=' + r[gi].replace(' ', '')]
     t[0] += 1
     t[1] += float(r[vi].replace(",", ""))
 allns = sum(v[1] for v in tot.values()) or 1.0
