@@ -10,11 +10,11 @@ All computation happens in libb200yolo.so (hand-written CUDA, C ABI in
 include/b200yolo.h); PyTorch only provides device memory, streams and
 torch.distributed.  There is no CPU fallback.
 """
-from . import _lib, ops
+from . import _lib, dist, ops
 from .box import nms, wh_to_x2y2
 from .fused import decode_nms, decode_nms_padded, head_anchor_table, patch_reference
 from .iou import find_intersection, find_jaccard_overlap, find_union
 from .yolo_loss import YOLOLoss
 
 __all__ = ["YOLOLoss", "nms", "wh_to_x2y2", "find_intersection", "find_union", "find_jaccard_overlap", "decode_nms",
-           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops"]
+           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops", "dist"]
