@@ -148,9 +148,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU (oracle) arm
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_decode_nms_rate(wl, budget_s=12.0, max_reps=50):
     """images/s of the CPU oracle port on this box's cores, bounded sample."""
     import oracle
+    oracle.set_threads(host_threads())
     N = wl["N"]
     h0, h1 = make_heads(wl, N, seed=0)
     h0, h1 = h0.numpy(), h1.numpy()
@@ -171,6 +180,7 @@ def cpu_decode_nms_rate(wl, budget_s=12.0, max_reps=50):
 def cpu_loss_rate(N, G):
     """images/s of the CPU oracle port for YOLOLoss.forward(input, targets), both VOC heads."""
     import oracle
+    oracle.set_threads(host_threads())
     wl = WORKLOADS["cfg2"]
     h0, h1 = make_heads(wl, N, seed=100)
     targets = make_targets(N, G, wl["C"], 1)
@@ -190,6 +200,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     import oracle
+    oracle.set_threads(host_threads())
     N = wl["N"]
     h0, h1 = make_heads(wl, N, seed=0)
     h0, h1 = h0.numpy(), h1.numpy()

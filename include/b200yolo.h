@@ -53,8 +53,9 @@ const char *b200yolo_last_error(void);
 unsigned long long b200yolo_launch_count(void);
 
 /* Profiling aid (profiles/phase_times.py): when set to a device buffer of
- * [N][16] uint64, the fused / NMS kernels record %globaltimer (ns) at their phase
- * boundaries for every image.  NULL (the default) disables it. */
+ * [N][32] uint64, the fused / NMS kernels record %globaltimer (ns; slots 0-15) and the SM
+ * cycle counter (slots 16-31) at their phase boundaries for every image.  NULL (the
+ * default) disables it. */
 void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
 
 /* Experiment / test switches of the fused kernel (initialised from the B200YOLO_FLAGS

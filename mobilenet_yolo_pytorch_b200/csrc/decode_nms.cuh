@@ -80,7 +80,7 @@ struct DNParams {
     int K;               // candidate slots per image = row stride of out / out_idx
     int B;               // score buckets per class of the counting sort (power of two)
     int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads
-    unsigned long long *dbg;  // optional [N][16] phase time stamps (ns, globaltimer), NULL in production
+    unsigned long long *dbg;  // optional [N][32] phase time stamps (16 x globaltimer ns, 16 x SM clock), NULL in production
     float conf_thr;
     IouThr iou;
     float *out;
@@ -209,11 +209,14 @@ __device__ __forceinline__ int fastdiv(int n, uint32_t magic) {
 
 __device__ __forceinline__ int tri(int x) { return (x * (x + 1)) >> 1; }
 
+// profiling aid: slot k of image b gets %globaltimer (ns, 256 ns resolution, comparable across SMs) and,
+// 16 slots further, the SM's cycle counter (comparable inside the CTA only)
 __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
     if (p.dbg && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.dbg[(size_t)b * 16 + k] = t;
+        p.dbg[(size_t)b * 32 + k] = t;
+        p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
     }
 }
 
@@ -287,16 +290,100 @@ __device__ __forceinline__ float tie_window(float m, float *best) {
 
 // ---------------------------------------------------------------------------
 // P1: decode every cell of one head, single pass.  All 5+C plane loads of a cell are
-// issued before the first use.  CT/HWT/WT > 0: compile-time class count and grid.
+// issued before the first use.
 // ---------------------------------------------------------------------------
-template <int THREADS, int MODE, int CT, int HWT, int WT>
-__device__ __forceinline__ void decode_head(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
+// box arithmetic + records of one passing cell (yolo_loss.py:186-199, 243-247)
+template <int MODE>
+__device__ __forceinline__ void emit_candidate(const DNParams &p, const Smem &s, const HeadDesc &hd, int cid, int a, int i, int j,
+                                               float tx, float ty, float tw, float th, float conf, float best, int bi) {
+    const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
+    const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
+    const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194 (x * 1/W)
+    const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+    const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
+    const float bh = __fmul_rn(eh, hd.ah[a]);
+    float4 bx;
+    bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244
+    bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
+    bx.z = __fadd_rn(bw, bx.x);                                  // :246
+    bx.w = __fadd_rn(bh, bx.y);                                  // :247
+    s.box[cid] = bx;
+    s.cs[cid] = make_float2(conf, best);
+    uint32_t idx = 0;
+    if (MODE == MODE_FUSED) idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
+    s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+}
+
+// Compile-time class count and grid: the 5+C loads are one base register plus immediates.  FIRST: this
+// is the first decode of the kernel -- the block barrier that orders the zeroing of the histogram before
+// the first shared atomic is taken AFTER the first round's loads are in flight (hides ~0.5 us of start-up
+// behind the first HBM round trip).
+template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST>
+__device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
+    static_assert(CT >= 1 && CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
     const int tid = threadIdx.x, lane = tid & 31;
-    constexpr bool kStatic = (CT > 0);
-    const int C = kStatic ? CT : p.C;
+    constexpr int attrs = CT + 5;
+    const int cells = p.A * HWT;
+    const float *hb = hd.ptr + (size_t)b * p.A * attrs * HWT;  // uniform
+#pragma unroll 1
+    for (int base = 0; base < cells; base += THREADS) {
+        const int local = base + tid;
+        const bool active = local < cells;
+        const int a = local / HWT;
+        const int pos = local - a * HWT;
+        const float *q = hb + (uint32_t)(a * attrs * HWT + pos);
+        float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, tc = 0.f;
+        float x[CT];
+        if (active) {
+            tx = __ldcs(q);
+            ty = __ldcs(q + HWT);
+            tw = __ldcs(q + 2 * HWT);
+            th = __ldcs(q + 3 * HWT);
+            tc = __ldcs(q + 4 * HWT);
+#pragma unroll
+            for (int u = 0; u < CT; ++u) x[u] = __ldcs(q + (5 + u) * HWT);
+        }
+        if (FIRST && base == 0) __syncthreads();
+        bool pass = false;
+        if (active) {
+            const int cid = cid0 + local;
+            const float conf = sigmoid_fast(tc);  // yolo_loss.py:189,197
+            pass = conf > p.conf_thr;             // :201 (threshold already rounded to fp32)
+            if (pass) {
+                float m1 = x[0];
+#pragma unroll
+                for (int u = 1; u < CT; ++u) m1 = fmaxf(m1, x[u]);
+                float best;
+                const float win = tie_window(m1, &best);
+                const float lo = __fsub_rn(m1, win);
+                float near = 0.f;  // bit u: x[u] >= lo   (FSET + FFMA: exact for 24 bits)
+#pragma unroll
+                for (int u = 0; u < CT; ++u) near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << u), near);
+                const uint32_t nb = __float2uint_rn(near);
+                int bi = nb ? __ffs(nb) - 1 : 0;
+                const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
+                if (CT > 1 && tie) best = class_tie_break(q + 5 * HWT, HWT, CT, lo, m1, bi, &bi);
+                const int j = pos / WT;
+                emit_candidate<MODE>(p, s, hd, cid, a, pos - j * WT, j, tx, ty, tw, th, conf, best, bi);
+            } else if (MODE == MODE_FUSED) {
+                s.clsidx[cid] = 0xffffffffu;
+            }
+        }
+        if (MODE == MODE_DECODE) {  // single head: candidate ids are 32-aligned per warp
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (lane == 0 && active) s.passbits[local >> 5] = bal;
+        }
+        if (MODE == MODE_FUSED) stamp(p, b, 8 + min(3, hh + base / THREADS));
+    }
+}
+
+// Runtime class count and grid (any shape): plane stride in a register, classes in chunks of 24.
+template <int THREADS, int MODE>
+__device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int C = p.C;
     const int attrs = C + 5;
-    const int HW = kStatic ? HWT : hd.HW;
-    const int W = kStatic ? WT : hd.W;
+    const int HW = hd.HW;
     const int cells = p.A * HW;
     const float *hb = hd.ptr + (size_t)b * p.A * attrs * HW;  // uniform
 #pragma unroll 1
@@ -305,124 +392,77 @@ __device__ __forceinline__ void decode_head(const DNParams &p, const Smem &s, in
         bool pass = false;
         if (local < cells) {
             const int cid = cid0 + local;
-            const int a = kStatic ? (local / HW) : fastdiv(local, hd.magicHW);
+            const int a = fastdiv(local, hd.magicHW);
             const int pos = local - a * HW;
             const float *q = hb + (uint32_t)(a * attrs * HW + pos);
-            float tx, ty, tw, th, tc;
             float m1 = -INFINITY, best = 0.f, win = 0.f, conf = 0.f;
             int i1 = 0;
             bool tie = false;
-            if (kStatic) {
-                // one base register + immediates
-                float x[CT > 0 ? CT : 1];
-                tx = __ldcs(q);
-                ty = __ldcs(q + HWT);
-                tw = __ldcs(q + 2 * HWT);
-                th = __ldcs(q + 3 * HWT);
-                tc = __ldcs(q + 4 * HWT);
+            const char *qb = reinterpret_cast<const char *>(q);
+            const uint32_t st = (uint32_t)HW * 4u;  // plane stride in bytes
+#define B200_LD(u) __ldcs(reinterpret_cast<const float *>(qb + (uint64_t)st * (uint32_t)(u)))
+            const float tx = B200_LD(0);
+            const float ty = B200_LD(1);
+            const float tw = B200_LD(2);
+            const float th = B200_LD(3);
+            const float tc = B200_LD(4);
+            qb += (uint64_t)st * 5u;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += kClsChunk) {
+                // groups of 4 planes behind uniform branches; only the last, partial group clamps
+                // its plane index to the last class (duplicates are masked out of `near` below),
+                // so the loads carry no predicate and no default value
+                float x[kClsChunk];
+                const int nv = min(C - c0, kClsChunk);  // uniform
 #pragma unroll
-                for (int u = 0; u < CT; ++u) x[u] = __ldcs(q + (5 + u) * HWT);
-                conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
-                pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
+                for (int g = 0; g < kClsChunk / 4; ++g) {
+                    if (4 * g + 4 <= nv) {
+#pragma unroll
+                        for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(u);
+                    } else if (4 * g < nv) {
+#pragma unroll
+                        for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(min(u, nv - 1));
+                    }
+                }
+                qb += (uint64_t)st * (uint32_t)nv;
+                if (c0 == 0) {
+                    conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
+                    pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
+                }
+                float cm = x[0];
+#pragma unroll
+                for (int g = 0; g < kClsChunk / 4; ++g) {
+                    if (4 * g < nv) cm = fmaxf(fmaxf(cm, fmaxf(x[4 * g], x[4 * g + 1])), fmaxf(x[4 * g + 2], x[4 * g + 3]));
+                }
                 if (pass) {
-                    float cm = x[0];
-#pragma unroll
-                    for (int u = 1; u < CT; ++u) cm = fmaxf(cm, x[u]);
-                    m1 = cm;
-                    win = tie_window(m1, &best);
-                    const float lo = __fsub_rn(m1, win);
+                    const float m_new = fmaxf(m1, cm);
+                    win = tie_window(m_new, &best);
+                    const float lo = __fsub_rn(m_new, win);
                     float near = 0.f;  // bit u: x[u] >= lo   (FSET + FFMA: exact for 24 bits)
 #pragma unroll
-                    for (int u = 0; u < CT; ++u) near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << (u % 24)), near);
-                    static_assert(CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
-                    const uint32_t nb = __float2uint_rn(near);
-                    i1 = __ffs(nb) - 1;
-                    tie = (nb & (nb - 1u)) != 0u || nb == 0u;
-                    if (nb == 0u) i1 = 0;
-                }
-            } else {
-                const char *qb = reinterpret_cast<const char *>(q);
-                const uint32_t st = (uint32_t)HW * 4u;  // plane stride in bytes
-#define B200_LD(u) __ldcs(reinterpret_cast<const float *>(qb + (uint64_t)st * (uint32_t)(u)))
-                tx = B200_LD(0);
-                ty = B200_LD(1);
-                tw = B200_LD(2);
-                th = B200_LD(3);
-                tc = B200_LD(4);
-                qb += (uint64_t)st * 5u;
-#pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += kClsChunk) {
-                    // groups of 4 planes behind uniform branches; only the last, partial group clamps
-                    // its plane index to the last class (duplicates are masked out of `near` below),
-                    // so the loads carry no predicate and no default value
-                    float x[kClsChunk];
-                    const int nv = min(C - c0, kClsChunk);  // uniform
-#pragma unroll
                     for (int g = 0; g < kClsChunk / 4; ++g) {
-                        if (4 * g + 4 <= nv) {
+                        if (4 * g < nv) {
 #pragma unroll
-                            for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(u);
-                        } else if (4 * g < nv) {
-#pragma unroll
-                            for (int u = 4 * g; u < 4 * g + 4; ++u) x[u] = B200_LD(min(u, nv - 1));
+                            for (int u = 4 * g; u < 4 * g + 4; ++u)
+                                near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << u), near);
                         }
                     }
-                    qb += (uint64_t)st * (uint32_t)nv;
-                    if (c0 == 0) {
-                        conf = sigmoid_fast(tc);
-                        pass = conf > p.conf_thr;
-                    }
-                    float cm = x[0];
-#pragma unroll
-                    for (int g = 0; g < kClsChunk / 4; ++g) {
-                        if (4 * g < nv) cm = fmaxf(fmaxf(cm, fmaxf(x[4 * g], x[4 * g + 1])), fmaxf(x[4 * g + 2], x[4 * g + 3]));
-                    }
-                    if (pass) {
-                        const float m_new = fmaxf(m1, cm);
-                        win = tie_window(m_new, &best);
-                        const float lo = __fsub_rn(m_new, win);
-                        float near = 0.f;
-#pragma unroll
-                        for (int g = 0; g < kClsChunk / 4; ++g) {
-                            if (4 * g < nv) {
-#pragma unroll
-                                for (int u = 4 * g; u < 4 * g + 4; ++u)
-                                    near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << u), near);
-                            }
-                        }
-                        const uint32_t nb = __float2uint_rn(near) & (0xffffffffu >> (32 - nv));
-                        // previous chunks: their max m1 must lie below the window too
-                        const bool prev_near = (c0 > 0) && !(m1 < lo);
-                        if (cm > m1 || c0 == 0) { i1 = c0 + __ffs(nb) - 1; tie = (nb & (nb - 1u)) != 0u || prev_near || nb == 0u; }
-                        else tie = tie || nb != 0u;
-                        m1 = m_new;
-                    } else {
-                        m1 = fmaxf(m1, cm);
-                    }
+                    const uint32_t nb = __float2uint_rn(near) & (0xffffffffu >> (32 - nv));
+                    // previous chunks: their max m1 must lie below the window too
+                    const bool prev_near = (c0 > 0) && !(m1 < lo);
+                    if (cm > m1 || c0 == 0) { i1 = c0 + __ffs(nb) - 1; tie = (nb & (nb - 1u)) != 0u || prev_near || nb == 0u; }
+                    else tie = tie || nb != 0u;
+                    m1 = m_new;
+                } else {
+                    m1 = fmaxf(m1, cm);
                 }
-#undef B200_LD
             }
+#undef B200_LD
             if (pass) {
                 int bi = i1;
                 if (C > 1 && tie) best = class_tie_break(q + 5 * HW, HW, C, __fsub_rn(m1, win), m1, i1, &bi);
-                const int j = kStatic ? (pos / W) : fastdiv(pos, hd.magicW);
-                const int i = pos - j * W;
-                const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
-                const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
-                const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194 (x * 1/W)
-                const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
-                const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
-                const float bh = __fmul_rn(eh, hd.ah[a]);
-                float4 bx;
-                bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244
-                bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));                   // :245
-                bx.z = __fadd_rn(bw, bx.x);                                  // :246
-                bx.w = __fadd_rn(bh, bx.y);                                  // :247
-                s.box[cid] = bx;
-                s.cs[cid] = make_float2(conf, best);
-                uint32_t idx = 0;
-                if (MODE == MODE_FUSED) idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
-                s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+                const int j = fastdiv(pos, hd.magicW);
+                emit_candidate<MODE>(p, s, hd, cid, a, pos - j * hd.W, j, tx, ty, tw, th, conf, best, bi);
             } else if (MODE == MODE_FUSED) {
                 s.clsidx[cid] = 0xffffffffu;
             }
@@ -431,7 +471,7 @@ __device__ __forceinline__ void decode_head(const DNParams &p, const Smem &s, in
             const unsigned bal = __ballot_sync(kFullMask, pass);
             if (lane == 0 && local < cells) s.passbits[local >> 5] = bal;
         }
-        if (MODE == MODE_FUSED) stamp(p, b, 8 + min(6, hh * 4 + base / THREADS));
+        if (MODE == MODE_FUSED) stamp(p, b, 8 + min(3, hh + base / THREADS));
     }
 }
 
@@ -492,6 +532,7 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) words += __shfl_xor_sync(kFullMask, words, o);
+    __syncwarp();  // lane 0 reads the other lanes' cnt[] below
     if (lane == 0) {
         s.cnt[C] = 0;
         s.start[C] = s.cntb[C * p.B];
@@ -847,18 +888,22 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
             }
         }
     }
+    constexpr bool kStaticShape = (MODE == MODE_FUSED && SH::C > 0);
     if (MODE != MODE_DECODE) {
         for (int i = tid; i <= C * p.B; i += THREADS) s.cntb[i] = 0;
         for (int i = tid; i <= C; i += THREADS) s.flag[i] = 0;
-        __syncthreads();
+        if (!kStaticShape) __syncthreads();  // (compile-time shapes: the barrier sits behind the first round's loads)
     }
     stamp(p, b, 15);
 
-    if (MODE == MODE_NMS) {
+    if constexpr (MODE == MODE_NMS) {
         phase_load_rows<THREADS>(p, s, b);
+    } else if constexpr (kStaticShape) {
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true>(p, s, b, p.head[0], 0, 0);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false>(p, s, b, p.head[1], p.head[0].cells, 1);
     } else {
-        decode_head<THREADS, MODE, SH::C, SH::HW0, SH::W0>(p, s, b, p.head[0], 0, 0);
-        if (MODE == MODE_FUSED) decode_head<THREADS, MODE, SH::C, SH::HW1, SH::W1>(p, s, b, p.head[1], p.head[0].cells, 1);
+        decode_head_rt<THREADS, MODE>(p, s, b, p.head[0], 0, 0);
+        if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE>(p, s, b, p.head[1], p.head[0].cells, 1);
     }
     __syncthreads();
     stamp(p, b, 1);
@@ -901,11 +946,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     // P2, P3 (warp 0's class bookkeeping overlaps the key scatter of the others)
     block_scan_buckets<THREADS>(p, s);
     __syncthreads();
+    stamp(p, b, 12);
     if (warp == 0) {
         warp_class_scan(p, s, (int)L.mask_words);
         warp_round_prefix(s, 0);
     }
+    stamp(p, b, 13);
     phase_scatter_keys<THREADS>(p, s);
+    stamp(p, b, 14);
     __syncthreads();
     stamp(p, b, 2);
     const int Kv = s.misc[M_KV];
@@ -923,8 +971,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         __syncthreads();
     }
     stamp(p, b, 4);
-    stamp(p, b, 5);
-    stamp(p, b, 6);
     // P6 (the mask buffer is dead now; the row scratch aliases it)
     phase_output<MODE, THREADS>(p, s, b);
     stamp(p, b, 7);

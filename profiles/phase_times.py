@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Per-phase wall time of the fused decode+NMS kernel from in-kernel %globaltimer stamps
-(b200yolo_debug_phase_stamps).  Prints, per workload, the median over images of each phase
-and the span of the whole launch (first CTA start -> last CTA end)."""
+"""Per-phase time of the fused decode+NMS kernel from in-kernel stamps (b200yolo_debug_phase_stamps):
+%globaltimer (256 ns resolution) for the launch span across CTAs, the SM cycle counter for the phases
+inside a CTA.  Prints, per workload, the median over images of each phase.
+    PHASE_N=32 python profiles/phase_times.py cfg2 cfg2_sparse"""
 import os
 import sys
 
@@ -12,15 +13,20 @@ import torch
 import bench
 from mobilenet_yolo_pytorch_b200 import _lib, ops
 
-NAMES = ["init", "decode", "scan+scatter", "rank", "pairs", "sweep", "out-prefix", "store"]
+# stamp slots in kernel order (decode_nms.cuh)
+ORDER = [(0, "start"), (15, "init"), (8, "decode round 1"), (9, "decode round 2"), (10, "decode round 3"),
+         (11, "decode round 4+"), (1, "decode done (barrier)"), (12, "bucket scan"), (13, "class scan + round table (warp 0)"),
+         (14, "key scatter (warp 0's share)"), (2, "scatter barrier"), (3, "rank + barrier"), (4, "pairs + sweep + barrier"),
+         (7, "output")]
 dev = torch.device("cuda", 0)
+MHZ = 1965.0
 for name in sys.argv[1:] or ["cfg2", "cfg2_sparse"]:
     wl = bench.WORKLOADS[name]
-    N = wl["N"]
+    N = int(os.environ.get("PHASE_N", wl["N"]))
     tables = bench.anchor_tables(wl)
     sets = [tuple(h.to(dev) for h in bench.make_heads(wl, N, seed=s)) for s in range(3)]
     big = torch.empty(64 << 20, dtype=torch.float32, device=dev)
-    dbg = torch.zeros((N, 16), dtype=torch.int64, device=dev)
+    dbg = torch.zeros((N, 32), dtype=torch.int64, device=dev)
     for i in range(4):
         big.fill_(float(i))
         if i == 3:
@@ -29,15 +35,15 @@ for name in sys.argv[1:] or ["cfg2", "cfg2_sparse"]:
     torch.cuda.synchronize()
     _lib.load().b200yolo_debug_phase_stamps(None)
     raw = dbg.cpu().numpy().astype(np.float64)
-    rr = raw[:, 8:16]
-    print("   decode rounds (warp 0 of each CTA, us after CTA start, median):",
-          " ".join(f"{np.median(rr[:, k] - raw[:, 0]) / 1e3:.2f}" for k in range(7) if rr[:, k].max() > 0),
-          "| init done at", f"{np.median(rr[:, 7] - raw[:, 0]) / 1e3:.2f}")
-    t = raw[:, :8]
-    t0 = t[:, 0].min()
-    d = np.diff(t, axis=1) / 1e3
-    print(f"== {name}: launch span {(t[:, 7].max() - t0) / 1e3:.1f} us; CTA start spread {(t[:, 0].max() - t0) / 1e3:.1f} us; "
-          f"CTA duration median {np.median(t[:, 7] - t[:, 0]) / 1e3:.1f} max {(t[:, 7] - t[:, 0]).max() / 1e3:.1f} us")
-    for k in range(7):
-        print(f"   {NAMES[k + 1]:<13} median {np.median(d[:, k]):6.2f}  p90 {np.percentile(d[:, k], 90):6.2f}  max {d[:, k].max():6.2f} us"
-              f"   (ends at median {np.median(t[:, k + 1] - t0) / 1e3:6.2f} us)")
+    g, c = raw[:, :16], raw[:, 16:]
+    t0 = g[:, 0].min()
+    print(f"== {name} N={N}: launch span {(g[:, 7].max() - t0) / 1e3:.1f} us; CTA start spread {(g[:, 0].max() - t0) / 1e3:.1f} us; "
+          f"CTA duration (SM clock @ {MHZ:.0f} MHz) median {np.median(c[:, 7] - c[:, 0]) / MHZ:.2f} max {(c[:, 7] - c[:, 0]).max() / MHZ:.2f} us")
+    prev = 0
+    for slot, label in ORDER[1:]:
+        if c[:, slot].max() == 0:
+            continue
+        d = (c[:, slot] - c[:, prev]) / MHZ
+        print(f"   {label:<36} median {np.median(d):6.2f}  p90 {np.percentile(d, 90):6.2f}  max {d.max():6.2f} us"
+              f"   (ends at median {np.median(c[:, slot] - c[:, 0]) / MHZ:6.2f} us)")
+        prev = slot
