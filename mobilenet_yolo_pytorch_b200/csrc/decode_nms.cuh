@@ -213,9 +213,11 @@ __device__ __forceinline__ int tri(int x) { return (x * (x + 1)) >> 1; }
 // 16 slots further, the SM's cycle counter (comparable inside the CTA only)
 __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
     if (p.dbg && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.dbg[(size_t)b * 32 + k] = t;
+        if (k == 0 || k == 7) {  // (reading %globaltimer costs several hundred ns: only at the CTA's two ends)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.dbg[(size_t)b * 32 + k] = t;
+        }
         p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
     }
 }
@@ -510,20 +512,37 @@ __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s
 // ---------------------------------------------------------------------------
 // P2 (warp 0): class segments, kept-bitmap tiles, and the round table
 // ---------------------------------------------------------------------------
+// (warp 0) class segment starts: exclusive scan of cnt[] -> start[]; total -> misc[M_KV]
+__device__ __forceinline__ void warp_class_starts(const DNParams &p, const Smem &s) {
+    const int lane = threadIdx.x & 31;
+    const int C = p.C;
+    int carry = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const int n = (c < C) ? s.cnt[c] : 0;
+        const int inc = warp_inclusive_scan(n, lane);
+        if (c < C) s.start[c] = carry + inc - n;
+        carry += __shfl_sync(kFullMask, inc, 31);
+    }
+    if (lane == 0) {
+        s.cnt[C] = 0;
+        s.start[C] = carry;
+        s.misc[M_KV] = carry;
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s, int mask_cap_words) {
     const int lane = threadIdx.x & 31;
     const int C = p.C;
     int carryT = 0, words = 0;
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
-        const int st = (c < C) ? s.cntb[c * p.B] : 0;
-        const int n = (c < C) ? s.cntb[(c + 1) * p.B] - st : 0;
+        const int n = (c < C) ? s.cnt[c] : 0;
         const int T = (n + 31) >> 5;
         const int incT = warp_inclusive_scan(T, lane);
         if (c < C) {
             const int kt = carryT + incT - T;
-            s.cnt[c] = n;
-            s.start[c] = st;
             s.ktile[c] = kt;
             for (int t = 0; t < T; ++t) s.tilecls[kt + t] = (uint16_t)c;
         }
@@ -534,8 +553,6 @@ __device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s
     for (int o = 16; o > 0; o >>= 1) words += __shfl_xor_sync(kFullMask, words, o);
     __syncwarp();  // lane 0 reads the other lanes' cnt[] below
     if (lane == 0) {
-        s.cnt[C] = 0;
-        s.start[C] = s.cntb[C * p.B];
         s.ktile[C] = carryT;
         const int cap = mask_cap_words;
         if (words <= cap) {
@@ -612,32 +629,24 @@ __device__ __forceinline__ void warp_round_prefix(const Smem &s, int r) {
 }
 
 // ---------------------------------------------------------------------------
-// P2a (all threads): exclusive scan of the (class, score bucket) counters in place
-// -> sorted-position base of every bucket; total -> misc[M_KV]
+// P2a (warp per class): exclusive scan of the class's score-bucket counters in place (position of the
+// bucket INSIDE the class segment); cnt[c] = candidates of the class
 // ---------------------------------------------------------------------------
 template <int THREADS>
-__device__ __forceinline__ void block_scan_buckets(const DNParams &p, const Smem &s) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NB = p.C * p.B;
-    const int per = (NB + THREADS - 1) / THREADS;
-    const int lo = min(tid * per, NB), hi = min(lo + per, NB);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += s.cntb[i];
-    const int inc = warp_inclusive_scan(sum, lane);
-    if (lane == 31) s.misc[M_WSUM + warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        const int v = (lane < THREADS / 32) ? s.misc[M_WSUM + lane] : 0;
-        const int w = warp_inclusive_scan(v, lane);
-        s.misc[M_WSUM + lane] = w - v;
-        if (lane == 31) { s.misc[M_KV] = w; s.cntb[NB] = w; }
-    }
-    __syncthreads();
-    int base = s.misc[M_WSUM + warp] + inc - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int t = s.cntb[i];
-        s.cntb[i] = base;
-        base += t;
+__device__ __forceinline__ void scan_buckets_per_class(const DNParams &p, const Smem &s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int B = p.B;                    // power of two <= 64
+    const int per = (B + 31) >> 5;        // 1 or 2 consecutive buckets per lane
+    for (int c = warp; c < p.C; c += THREADS / 32) {
+        int *cb = s.cntb + c * B;
+        const int i0 = lane * per;
+        const int v0 = (i0 < B) ? cb[i0] : 0;
+        const int v1 = (per == 2) ? cb[i0 + 1] : 0;
+        const int sum = v0 + v1;
+        const int inc = warp_inclusive_scan(sum, lane);
+        if (i0 < B) cb[i0] = inc - sum;
+        if (per == 2) cb[i0 + 1] = inc - sum + v0;
+        if (lane == 31) s.cnt[c] = inc;
     }
 }
 
@@ -647,8 +656,8 @@ __device__ __forceinline__ void block_scan_buckets(const DNParams &p, const Smem
 // key = score order key (32) | class (16) | 0xffff - cell id (16)
 // ---------------------------------------------------------------------------
 template <int THREADS>
-__device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s) {
-    for (int cid = threadIdx.x; cid < p.K; cid += THREADS) {
+__device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s, int tid, int nthr) {
+    for (int cid = tid; cid < p.K; cid += nthr) {
         const uint32_t ci = s.clsidx[cid];
         if (ci == 0xffffffffu) continue;
         const float2 cs = s.cs[cid];
@@ -656,20 +665,22 @@ __device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem
         const uint32_t c = ci >> 16;
         const unsigned long long key =
             ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)((c << 16) | (0xffffu - (uint32_t)cid));
-        s.key[s.cntb[(int)c * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
+        s.key[s.start[c] + s.cntb[(int)c * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
     }
 }
 
 template <int THREADS>
-__device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv) {
-    if (threadIdx.x < 8) s.sord[Kv + threadIdx.x] = make_uint2(s.box_saddr, 0x7fc00000u);  // padding: a valid address, NaN area
-    for (int t = threadIdx.x; t < Kv; t += THREADS) {
+__device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv, int tid, int nthr) {
+    if (tid < 8) s.sord[Kv + tid] = make_uint2(s.box_saddr, 0x7fc00000u);  // padding: a valid address, NaN area
+    for (int t = tid; t < Kv; t += nthr) {
         const unsigned long long key = s.key[t];
         const uint32_t lo32 = (uint32_t)key;
         const uint32_t cid = 0xffffu - (lo32 & 0xffffu);
         const int c = (int)(lo32 >> 16);
-        const int cq = c * p.B + score_bucket(order_key_to_float((uint32_t)(key >> 32)), p.B);
-        const int st = s.cntb[cq], en = s.cntb[cq + 1];
+        const int bk = score_bucket(order_key_to_float((uint32_t)(key >> 32)), p.B);
+        const int base = s.start[c];
+        const int st = base + s.cntb[c * p.B + bk];
+        const int en = base + ((bk == p.B - 1) ? s.cnt[c] : s.cntb[c * p.B + bk + 1]);
         int rank = 0;
         for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
         const float ta = make_ta(s.box[cid], p.iou);
@@ -943,25 +954,28 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         return;
     }
 
-    // P2, P3 (warp 0's class bookkeeping overlaps the key scatter of the others)
-    block_scan_buckets<THREADS>(p, s);
+    // P2: bucket positions inside each class (warp per class), then the class starts (warp 0)
+    scan_buckets_per_class<THREADS>(p, s);
     __syncthreads();
     stamp(p, b, 12);
+    if (warp == 0) warp_class_starts(p, s);
+    __syncthreads();
+    stamp(p, b, 13);
+    const int Kv = s.misc[M_KV];
     if (warp == 0) {
+        // kept-bitmap tiles, round table, strip tasks: only the pair phase needs them, so warp 0 builds
+        // them while the other warps sort
         warp_class_scan(p, s, (int)L.mask_words);
         warp_round_prefix(s, 0);
+    } else {
+        // P3 / P4 on the other warps (named barrier 1 between the key scatter and the ranking)
+        phase_scatter_keys<THREADS>(p, s, tid - 32, THREADS - 32);
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS - 32) : "memory");
+        phase_rank_sort<THREADS>(p, s, Kv, tid - 32, THREADS - 32);
     }
-    stamp(p, b, 13);
-    phase_scatter_keys<THREADS>(p, s);
-    stamp(p, b, 14);
-    __syncthreads();
-    stamp(p, b, 2);
-    const int Kv = s.misc[M_KV];
-    const int nrounds = s.misc[M_NROUNDS];
-    // P4
-    phase_rank_sort<THREADS>(p, s, Kv);
     __syncthreads();
     stamp(p, b, 3);
+    const int nrounds = s.misc[M_NROUNDS];
     // P5
     for (int r = 0;;) {
         phase_pairs_sweep(p, s);

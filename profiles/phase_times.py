@@ -15,9 +15,9 @@ from mobilenet_yolo_pytorch_b200 import _lib, ops
 
 # stamp slots in kernel order (decode_nms.cuh)
 ORDER = [(0, "start"), (15, "init"), (8, "decode round 1"), (9, "decode round 2"), (10, "decode round 3"),
-         (11, "decode round 4+"), (1, "decode done (barrier)"), (12, "bucket scan"), (13, "class scan + round table (warp 0)"),
-         (14, "key scatter (warp 0's share)"), (2, "scatter barrier"), (3, "rank + barrier"), (4, "pairs + sweep + barrier"),
-         (7, "output")]
+         (11, "decode round 4+"), (1, "decode done (barrier)"), (12, "bucket scan per class + barrier"),
+         (13, "class starts (warp 0) + barrier"), (3, "tables (warp 0) | scatter, rank (others) + barrier"),
+         (4, "pairs + sweep + barrier"), (7, "output")]
 dev = torch.device("cuda", 0)
 MHZ = 1965.0
 for name in sys.argv[1:] or ["cfg2", "cfg2_sparse"]:
