@@ -268,9 +268,26 @@ def time_loss(dev, N, G, steps=100, seed=1):
     torch.cuda.synchronize()
     ms = time_loop(step, steps) / steps
     algo = in_bytes + 2 * 20 * N * G
-    return {"images_per_s_per_gpu": N / (ms * 1e-3), "ms_per_step": ms, "batch": N, "gt_per_image": G,
-            "algorithmic_bytes_per_step": algo, "algorithmic_gbs": algo / (ms * 1e-3) / 1e9,
-            "iou_pairs_per_step": N * G * cells_per_image(wl)}
+    res = {"images_per_s_per_gpu": N / (ms * 1e-3), "ms_per_step": ms, "batch": N, "gt_per_image": G,
+           "algorithmic_bytes_per_step": algo, "algorithmic_gbs": algo / (ms * 1e-3) / 1e9,
+           "iou_pairs_per_step": N * G * cells_per_image(wl)}
+    # forward + backward (grad_input of both heads; every element written once: + in_bytes of stores)
+    states = [torch.empty((N, A * H * W), dtype=torch.uint8, device=dev) for (H, W) in wl["grids"]]
+
+    def step_fb(i):
+        for k, h in enumerate(sets[i % R]):
+            sums, _ = ops.target_loss_sums(h, gt, gt_off, Gt, sa, MASK[k], C, VOC_IGNORE[k], VOC_IOU_THRESH, max_gt=G,
+                                           cell_state=states[k])
+            ops.target_loss_backward(h, gt, gt_off, Gt, sa, MASK[k], C, VOC_IOU_THRESH, states[k], sums, VOC_IOU_WEIGHTING,
+                                     max_gt=G)
+
+    for i in range(5):
+        step_fb(i)
+    torch.cuda.synchronize()
+    ms_fb = time_loop(step_fb, steps) / steps
+    res["fwd_bwd"] = {"ms_per_step": ms_fb, "images_per_s_per_gpu": N / (ms_fb * 1e-3),
+                      "algorithmic_gbs": (algo + in_bytes) / (ms_fb * 1e-3) / 1e9}
+    return res
 
 
 # ----------------------------------------------------------------------------- B200 arm

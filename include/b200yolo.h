@@ -140,7 +140,8 @@ int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int 
  *   status    dev int32[1], overwritten: 0 ok, 1 a GT maps outside the grid or has
  *             a class outside [1,C] (reference: IndexError), 2 an image has more GT
  *             boxes than max_gt_per_image / 1024
- *   grad      dev (N, A*(5+C), H, W) or NULL: reserved (must be NULL in this version)
+ *   cell_state dev uint8 [N][A*H*W] or NULL: per cell 0 = ignored (weight 0), 1 = no-object (weight 1,
+ *             target 0), 2 = assigned; b200yolo_target_loss_backward consumes it
  *   workspace dev, b200yolo_target_loss_workspace_bytes(N) bytes: per-CTA partial sums
  *             (up to 8 CTAs share an image), reduced in a fixed order so results are
  *             bitwise reproducible run to run
@@ -149,7 +150,24 @@ size_t b200yolo_target_loss_workspace_bytes(int N);
 int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
                          const int *mask, const float *gt, const int *gt_off, int G, float ignore_thr,
                          float iou_thr, int max_gt_per_image, double *sums, int *assign, float *terms, int *status,
-                         float *grad, void *workspace, size_t workspace_bytes, void *stream);
+                         unsigned char *cell_state, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Backward of YOLOLoss.forward(input, targets): d loss / d input exactly as the reference's autograd
+ * graph defines it (loss.backward() in train.py:282): the custom sigmoid passes gradients through
+ * unchanged (models/yolo_loss.py:15-32), exp has its true derivative (:86), objectness / class entries
+ * with weight 1 get 2 (o - t) / sum(w) (:53-60), the CIoU loss (:154-159, 224) reaches tx, ty, tw, th of
+ * the assigned cells (alpha is not detached, :283).
+ *   cell_state dev: what b200yolo_target_loss wrote for the same head, GT and thresholds
+ *   sums       dev double[16]: the partial sums AFTER the cross-rank all-reduce (read on the device, no
+ *              host synchronisation): the gradient of a shard is scaled by the batch-global normalisers
+ *   grad_out   dev float[1] = d(total)/d(loss), or NULL for 1
+ *   grad_input dev (N, A*(5+C), H, W): every element is written
+ */
+int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
+                                  const int *mask, const float *gt, const int *gt_off, int G, float iou_thr,
+                                  int max_gt_per_image, const unsigned char *cell_state, const double *sums,
+                                  float iou_weighting, const float *grad_out, float *grad_input, void *stream);
 
 /* indices into the partial-sum vector of b200yolo_target_loss */
 enum {

@@ -39,6 +39,9 @@ SIGNATURES = {
     "b200yolo_target_loss": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, c_i32p,
                                        c_f32p, c_i32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, c_i32p, c_f32p,
                                        c_i32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200yolo_target_loss_backward": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, c_i32p,
+                                                c_f32p, c_i32p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_float, c_f32p, c_f32p, C.c_void_p]),
     "b200yolo_loss_finalize": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
 }
 

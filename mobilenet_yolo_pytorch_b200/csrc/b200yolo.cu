@@ -254,11 +254,10 @@ int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int 
 int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
                          const int *mask, const float *gt, const int *gt_off, int G, float ignore_thr,
                          float iou_thr, int max_gt_per_image, double *sums, int *assign, float *terms, int *status,
-                         float *grad, void *workspace, size_t workspace_bytes, void *stream) {
+                         unsigned char *cell_state, void *workspace, size_t workspace_bytes, void *stream) {
     if (!head || !anchors_all || !mask || !gt_off || !sums || !status)
         return fail(B200YOLO_EINVAL, "target_loss: null pointer");
     if (G > 0 && !gt) return fail(B200YOLO_EINVAL, "target_loss: null gt");
-    if (grad) return fail(B200YOLO_EUNSUPPORTED, "target_loss: grad output is reserved (not implemented)");
     if (N < 0 || A < 1 || A > kMaxAnchors || NA < A || NA > B200YOLO_MAX_ALL_ANCHORS || C < 1 || C > 4096 || H < 1 ||
         W < 1 || G < 0)
         return fail(B200YOLO_EINVAL, "target_loss: bad shape");
@@ -278,7 +277,7 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
     p.ignore_thr = ignore_thr; p.iou_thr = iou_thr;
     // iou < thr <=> inter < thr/(1+thr) * (area_g + area_p); outside [0.01, 1] every cell takes the exact path
     p.ts = (ignore_thr >= 0.01f && ignore_thr <= 1.0f) ? (float)((double)ignore_thr / (1.0 + (double)ignore_thr)) * 1.220703125e-4f : 0.0f;
-    p.sums = sums; p.assign = assign; p.terms = terms; p.status = status;
+    p.sums = sums; p.assign = assign; p.terms = terms; p.status = status; p.cell_state = cell_state;
     if (N > 0 && (!workspace || workspace_bytes < b200yolo_target_loss_workspace_bytes(N)))
         return fail(B200YOLO_EINVAL, "target_loss: workspace too small (%zu < %zu)", workspace_bytes,
                     b200yolo_target_loss_workspace_bytes(N));
@@ -327,6 +326,74 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
         CUDA_TRY(cudaGetLastError());
     }
     target_loss_reduce_kernel<<<1, kTLSums * 32, 0, st>>>(p.partial, N * S, sums);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H, int W, const float *anchors_all, int NA,
+                                  const int *mask, const float *gt, const int *gt_off, int G, float iou_thr,
+                                  int max_gt_per_image, const unsigned char *cell_state, const double *sums,
+                                  float iou_weighting, const float *grad_out, float *grad_input, void *stream) {
+    if (!head || !anchors_all || !mask || !gt_off || !sums || !cell_state || !grad_input)
+        return fail(B200YOLO_EINVAL, "target_loss_backward: null pointer");
+    if (G > 0 && !gt) return fail(B200YOLO_EINVAL, "target_loss_backward: null gt");
+    if (N < 0 || A < 1 || A > kMaxAnchors || NA < A || NA > B200YOLO_MAX_ALL_ANCHORS || C < 1 || C > 4096 || H < 1 ||
+        W < 1 || G < 0)
+        return fail(B200YOLO_EINVAL, "target_loss_backward: bad shape");
+    for (int k = 0; k < A; ++k)
+        if (mask[k] < 0 || mask[k] >= NA) return fail(B200YOLO_EINVAL, "target_loss_backward: mask[%d]=%d out of range", k, mask[k]);
+    if (N == 0) return 0;
+    TLParams p;
+    memset(&p, 0, sizeof(p));
+    p.head = head;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C; p.H = H; p.W = W; p.HW = H * W; p.cells = A * H * W;
+    p.NA = NA;
+    p.invHW = 1.0f / (float)(H * W);
+    p.invW = 1.0f / (float)W;
+    p.fW = (float)W; p.fH = (float)H;
+    for (int a = 0; a < NA; ++a) { p.aw_all[a] = anchors_all[2 * a]; p.ah_all[a] = anchors_all[2 * a + 1]; }
+    for (int k = 0; k < A; ++k) p.mask[k] = mask[k];
+    p.gt = gt; p.gt_off = gt_off; p.G = G;
+    p.iou_thr = iou_thr;
+    p.sums = const_cast<double *>(sums);
+    p.cell_state_in = cell_state;
+    p.grad_out = grad_out;
+    p.grad_input = grad_input;
+    p.iou_weighting = iou_weighting;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    int gcap = (max_gt_per_image > 0) ? max_gt_per_image : G;
+    if (gcap > kTLMaxGT) gcap = kTLMaxGT;
+    if (gcap < 1) gcap = 1;
+    p.gcap = (gcap + 3) / 4 * 4;
+    const uint32_t smem = tl_smem_bytes(p.cells, p.gcap, A, true);
+    const int lim = smem_optin(dev);
+    if ((int)smem > lim)
+        return fail(B200YOLO_EUNSUPPORTED, "target_loss_backward: %d cells per image need %u B of shared memory (limit %d B)",
+                    p.cells, smem, lim);
+    int nsm = 148;
+    {
+        static std::mutex mu;
+        static bool configured[64] = {false};
+        static int sm_count[64] = {0};
+        std::lock_guard<std::mutex> g(mu);
+        if (dev < 64 && !configured[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(target_loss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+            configured[dev] = true;
+        }
+        if (dev < 64 && sm_count[dev] > 0) nsm = sm_count[dev];
+    }
+    int S = (4 * nsm + N - 1) / N;
+    const int smax = (p.cells + kTLThreads - 1) / kTLThreads;
+    if (S > smax) S = smax;
+    if (S > kTLMaxSplit) S = kTLMaxSplit;
+    if (S < 1) S = 1;
+    p.S = S;
+    p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
+    target_loss_backward_kernel<<<N * S, kTLThreads, smem, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

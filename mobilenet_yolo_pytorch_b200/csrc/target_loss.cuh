@@ -63,6 +63,12 @@ struct TLParams {
     int *assign;      // [G][A][4] or null
     float *terms;     // [G][A][2] or null
     int *status;
+    unsigned char *cell_state;  // [N][cells] or null: 0 ignored, 1 no-object (weight 1, target 0), 2 assigned
+    // backward only
+    const unsigned char *cell_state_in;
+    const float *grad_out;      // device scalar d(total)/d(loss), or null = 1
+    float *grad_input;          // (N, A*(5+C), H, W)
+    float iou_weighting;
 };
 
 struct TLAssign {
@@ -70,7 +76,7 @@ struct TLAssign {
     uint32_t t;     // GT index inside the image
 };
 
-__host__ __device__ inline uint32_t tl_smem_bytes(int cells, int gcap, int A) {
+__host__ __device__ inline uint32_t tl_smem_bytes(int cells, int gcap, int A, bool backward = false) {
     uint32_t o = 0;
     o += 16 * (uint32_t)gcap;                 // gt xyxy
     o += 4 * (uint32_t)gcap;                  // gt area
@@ -80,6 +86,7 @@ __host__ __device__ inline uint32_t tl_smem_bytes(int cells, int gcap, int A) {
     o += ((uint32_t)cells + 15u) / 16u * 16u; // assigned-cell flags
     o += 8 * kTLSums * kTLWarps;              // reduction scratch
     o += 64;
+    if (backward) o += 32 * (uint32_t)(gcap * A);  // per-assignment box-gradient contributions (4 doubles)
     return o;
 }
 
@@ -164,39 +171,13 @@ __device__ __noinline__ bool tl_below_exact(const float4 *gbox, const float *gar
     return below;
 }
 
-__global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams p) {
-    extern __shared__ __align__(16) unsigned char tl_smem[];
-    const uint32_t gcap = (uint32_t)p.gcap, lcap = (uint32_t)(p.gcap * p.A);
-    float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
-    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * gcap);
-    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * gcap);
-    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * gcap);
-    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * gcap);
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * gcap + 8 * lcap);
-    const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
-    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * gcap + 8 * lcap + flag_bytes);
-    int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
-
-    const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
-    const bool lead = (split == 0);  // the CTA of the image that owns the per-GT outputs and the assignments
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g0 = p.gt_off[b];
-    int nG = p.gt_off[b + 1] - g0;
-    const int HW = p.HW, W = p.W, H = p.H, A = p.A, C = p.C;
-
-    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }  // assignment list length; any degenerate GT box
-    for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
-    if (nG > p.gcap) {
-        if (tid == 0 && lead) atomicMax(p.status, 2);  // more GT boxes in one image than the staging holds
-        nG = 0;                                        // (the shim raises; keep the kernel well defined)
-    }
-    __syncthreads();
-
-    double acc[10];
-#pragma unroll
-    for (int q = 0; q < 10; ++q) acc[q] = 0.0;
-
-    // ---------------- P1: per-GT anchor matching ----------------
+// P1: per-GT anchor matching (yolo_loss.py:112-113, 127-145): stages the image's GT boxes, appends the assigned
+// (GT, k) pairs to s_list and flags their cells.  `lead` CTAs also write the per-GT outputs and the status.
+__device__ __forceinline__ void tl_match_gt(const TLParams &p, int b, int g0, int nG, bool lead, float4 *s_gbox, float *s_garea,
+                                            float *s_gta, int *s_gcls, TLAssign *s_list, uint8_t *s_flag, int *s_misc) {
+    const int tid = threadIdx.x;
+    const int W = p.W, H = p.H, A = p.A, C = p.C;
+    (void)b;
     for (int t = tid; t < nG; t += kTLThreads) {
         const float *g = p.gt + 5 * (size_t)(g0 + t);
         const float gc = __ldg(g), gx = __ldg(g + 1), gy = __ldg(g + 2), gw = __ldg(g + 3), gh = __ldg(g + 4);
@@ -247,6 +228,41 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams p) {
+    extern __shared__ __align__(16) unsigned char tl_smem[];
+    const uint32_t gcap = (uint32_t)p.gcap, lcap = (uint32_t)(p.gcap * p.A);
+    float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
+    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * gcap);
+    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * gcap);
+    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * gcap);
+    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * gcap);
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * gcap + 8 * lcap);
+    const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
+    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * gcap + 8 * lcap + flag_bytes);
+    int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
+
+    const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
+    const bool lead = (split == 0);  // the CTA of the image that owns the per-GT outputs and the assignments
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g0 = p.gt_off[b];
+    int nG = p.gt_off[b + 1] - g0;
+    const int HW = p.HW, W = p.W, H = p.H, A = p.A, C = p.C;
+
+    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }  // assignment list length; any degenerate GT box
+    for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
+    if (nG > p.gcap) {
+        if (tid == 0 && lead) atomicMax(p.status, 2);  // more GT boxes in one image than the staging holds
+        nG = 0;                                        // (the shim raises; keep the kernel well defined)
+    }
+    __syncthreads();
+
+    double acc[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) acc[q] = 0.0;
+
+    tl_match_gt(p, b, g0, nG, lead, s_gbox, s_garea, s_gta, s_gcls, s_list, s_flag, s_misc);
     __syncthreads();
     const int nE = s_misc[0];
     const bool gt_degenerate = s_misc[1] != 0;
@@ -268,10 +284,12 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
         }
         const float conf = sigmoid_f(__ldg(q + 4 * (size_t)HW));    // output[...,0] :87
         acc[B200YOLO_S_CONF_ALL] += (double)conf;                   // :98
+        unsigned char state = 1;
         if (flagged) {                                              // :149-150 target 1, weight 1
             const float df = __fsub_rn(conf, 1.0f);
             acc[B200YOLO_S_SQW] += (double)__fmul_rn(df, df);
             acc[B200YOLO_S_W] += 1.0;
+            state = 2;
         } else if (nG == 0) {                                       // :108-111
             acc[B200YOLO_S_SQW] += (double)__fmul_rn(conf, conf);
             acc[B200YOLO_S_W] += 1.0;
@@ -300,8 +318,11 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
             if (below) {                                            // :123-125 weight 1, target 0
                 acc[B200YOLO_S_SQW] += (double)__fmul_rn(conf, conf);
                 acc[B200YOLO_S_W] += 1.0;
+            } else {
+                state = 0;
             }
         }
+        if (p.cell_state) p.cell_state[(size_t)b * p.cells + cell] = state;
     }
 
     // ---------------- P3a: per-assignment terms (thread per assignment) ----------------
@@ -396,6 +417,194 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
         else if (tid == B200YOLO_S_NCELLS && lead) v = (double)p.cells;
         else if (tid == B200YOLO_S_NIMG && lead) v = 1.0;
         p.partial[((size_t)b * p.S + split) * kTLSums + tid] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Backward: d loss / d input as the reference's autograd graph defines it (yolo_loss.py:15-32, 84-92,
+// 154-159, 219-234).  The custom sigmoid passes gradients through unchanged, exp has its true derivative;
+// only entries of `targets` overwritten with constants carry a gradient 2 (o - t) w / sum(w); the CIoU loss
+// sum_i (v_i - 1)^2 / n_assign (weights cancel, :224) reaches tx, ty, tw, th of the assigned cells through
+// the decoded box (alpha is not detached, :283).  The normalisers sum(w) and n_assign are read from the
+// (all-reduced) partial sums in device memory, so the gradient of a data-parallel shard is scaled by the
+// batch-global denominators.  Every element of grad_input is written exactly once.
+// ---------------------------------------------------------------------------
+struct TLBox4d { double x, y, z, w; };
+
+// v = iou - ciou_term and dv/d(pred xyxy) (box1 = gt, box2 = pred), fp64
+__device__ __forceinline__ double tl_ciou_grad(const float4 &gt, const TLBox4d &pr, double dv[4]) {
+    const double a1 = gt.x, b1 = gt.y, a2 = gt.z, b2 = gt.w;
+    const double p1 = pr.x, q1 = pr.y, p2 = pr.z, q2 = pr.w;
+    auto sel = [](double lhs, double rhs) { return lhs > rhs ? 1.0 : (lhs == rhs ? 0.5 : 0.0); };  // d max(lhs, rhs) / d lhs
+    const double iw_raw = fmin(a2, p2) - fmax(a1, p1), ih_raw = fmin(b2, q2) - fmax(b1, q1);
+    const double iw = fmax(iw_raw, 0.0), ih = fmax(ih_raw, 0.0);
+    double d_iw[4] = {0, 0, 0, 0}, d_ih[4] = {0, 0, 0, 0};
+    if (iw_raw >= 0.0) { d_iw[2] = sel(a2, p2); d_iw[0] = -sel(p1, a1); }   // d min(a2,p2)/dp2 = [p2 < a2]
+    if (ih_raw >= 0.0) { d_ih[3] = sel(b2, q2); d_ih[1] = -sel(q1, b1); }
+    const double inter = iw * ih;
+    const double area1 = (a2 - a1) * (b2 - b1);
+    const double w2 = p2 - p1, h2 = q2 - q1;
+    const double d_w2[4] = {-1, 0, 1, 0}, d_h2[4] = {0, -1, 0, 1};
+    const double uni = area1 + w2 * h2 - inter;
+    const double iou = inter / uni;
+    const double cw = fmax(a2, p2) - fmin(a1, p1), ch = fmax(b2, q2) - fmin(b1, q1);
+    const double d_cw[4] = {-sel(a1, p1), 0, sel(p2, a2), 0};               // d(-min(a1,p1))/dp1 = -[p1 < a1]
+    const double d_ch[4] = {0, -sel(b1, q1), 0, sel(q2, b2)};
+    const double c = cw * ch;
+    const double dx = (a2 + a1) * 0.5 - (p2 + p1) * 0.5, dy = (b1 + b2) * 0.5 - (q1 + q2) * 0.5;
+    const double u = dx * dx + dy * dy;
+    const double d_u[4] = {-dx, -dy, -dx, -dy};
+    const double kk = 4.0 / (3.14159265358979323846 * 3.14159265358979323846);
+    const double delta = atan(w2 / h2) - atan((a2 - a1) / (b2 - b1));
+    const double Aar = kk * delta * delta;
+    const double D = 1.0 - iou + Aar + 0.000001;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double d_inter = d_iw[q] * ih + iw * d_ih[q];
+        const double d_union = d_w2[q] * h2 + w2 * d_h2[q] - d_inter;
+        const double d_iou = (d_inter * uni - inter * d_union) / (uni * uni);
+        const double d_c = d_cw[q] * ch + cw * d_ch[q];
+        const double d_dd = (d_u[q] * c - u * d_c) / (c * c);
+        const double d_A = 2.0 * kk * delta * (h2 * d_w2[q] - w2 * d_h2[q]) / (h2 * h2 + w2 * w2);
+        const double d_D = -d_iou + d_A;
+        const double d_f = (2.0 * Aar * d_A * D - Aar * Aar * d_D) / (D * D);
+        dv[q] = (c == 0.0) ? 0.0 : d_iou - d_dd - d_f;
+    }
+    return (c == 0.0) ? 0.0 : iou - (u / c + Aar * Aar / D);
+}
+
+__global__ void __launch_bounds__(kTLThreads) target_loss_backward_kernel(const TLParams p) {
+    extern __shared__ __align__(16) unsigned char tl_smem[];
+    const uint32_t gcap = (uint32_t)p.gcap, lcap = (uint32_t)(p.gcap * p.A);
+    float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
+    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * gcap);
+    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * gcap);
+    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * gcap);
+    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * gcap);
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * gcap + 8 * lcap);
+    const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
+    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * gcap + 8 * lcap + flag_bytes);
+    int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
+
+    const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
+    const bool lead = (split == 0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g0 = p.gt_off[b];
+    int nG = p.gt_off[b + 1] - g0;
+    const int HW = p.HW, W = p.W, A = p.A, C = p.C;
+    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }
+    for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
+    if (nG > p.gcap) nG = 0;  // (the forward call reported it)
+    __syncthreads();
+    tl_match_gt(p, b, g0, nG, false, s_gbox, s_garea, s_gta, s_gcls, s_list, s_flag, s_misc);
+    __syncthreads();
+    const int nE = s_misc[0];
+
+    const double go = p.grad_out ? (double)__ldg(p.grad_out) : 1.0;
+    const double inv_w = go * 2.0 / p.sums[B200YOLO_S_W];                                    // d L_dense / d o = 2 (o - t) w / sum w
+    const double n_assign = p.sums[B200YOLO_S_NASSIGN];
+    const double inv_n = n_assign > 0.0 ? go * (double)p.iou_weighting * 2.0 / n_assign : 0.0;  // d (w_iou * L_iou) / d v = 2 (v - 1) / n
+    float *gbase = p.grad_input + (size_t)b * A * p.attrs * HW;
+    const float *hbase = p.head + (size_t)b * A * p.attrs * HW;
+
+    // ---- every cell that is not assigned: only the objectness channel can carry a gradient
+    const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
+    for (int cell = cell_lo + tid; cell < cell_hi; cell += kTLThreads) {
+        if (s_flag[cell]) continue;
+        const int a = (int)(((float)cell + 0.5f) * p.invHW);
+        const int pos = cell - a * HW;
+        const size_t off = (size_t)a * p.attrs * HW + pos;
+        const unsigned char st = p.cell_state_in[(size_t)b * p.cells + cell];
+        const float tc = __ldg(hbase + off + 4 * (size_t)HW);
+        float gconf = 0.f;
+        if (st == 1) gconf = (float)((double)sigmoid_f(tc) * inv_w);  // target 0
+        float *g = gbase + off;
+        for (int t = 0; t < p.attrs; ++t) __stcs(g + (size_t)t * HW, t == 4 ? gconf : 0.f);
+    }
+
+    // ---- assigned cells (first CTA of the image)
+    if (lead) {
+        // thread per assignment: its CIoU gradient w.r.t. (tx, ty, tw, th) of its cell, fp64 on the fp32 decoded box
+        double4 *s_contrib = reinterpret_cast<double4 *>(s_misc + 16);
+        for (int e = tid; e < nE; e += kTLThreads) {
+            const uint32_t cell = s_list[e].cell;
+            const int a = (int)(((float)cell + 0.5f) * p.invHW);
+            const int pos = (int)cell - a * HW;
+            const int j = (int)(((float)pos + 0.5f) * p.invW);
+            const int i = pos - j * W;
+            const float *q = hbase + (size_t)a * p.attrs * HW + pos;
+            const float tx = __ldg(q), ty = __ldg(q + HW), tw = __ldg(q + 2 * (size_t)HW), th = __ldg(q + 3 * (size_t)HW);
+            const float aw = p.aw_all[p.mask[a]], ah = p.ah_all[p.mask[a]];
+            const float4 pb = tl_decode_box(tx, ty, tw, th, i, j, p.fW, p.fH, aw, ah);  // the forward's fp32 box (:84-92)
+            TLBox4d pr;
+            pr.x = pb.x; pr.y = pb.y; pr.z = pb.z; pr.w = pb.w;
+            double dv[4];
+            const double v = tl_ciou_grad(s_gbox[s_list[e].t], pr, dv);
+            const double gl = inv_n * (v - 1.0);
+            const double bw = (double)__fmul_rn(expf(tw), aw), bh = (double)__fmul_rn(expf(th), ah);
+            double4 c4;
+            c4.x = gl * (dv[0] + dv[2]) / (double)p.fW;   // d x1/d sx = d x2/d sx = 1/W; the sigmoid passes through
+            c4.y = gl * (dv[1] + dv[3]) / (double)p.fH;
+            c4.z = gl * (dv[2] - dv[0]) * 0.5 * bw;       // d x1/d bw = -1/2, d x2/d bw = +1/2, d bw/d tw = bw
+            c4.w = gl * (dv[3] - dv[1]) * 0.5 * bh;
+            s_contrib[e] = c4;
+        }
+        __syncthreads();  // (lead is uniform in the CTA)
+        // warp per distinct cell (its first list entry): sum over the cell's duplicates, objectness, classes
+        for (int e = warp; e < nE; e += kTLWarps) {
+            const uint32_t cell = s_list[e].cell;
+            bool earlier = false;
+            for (int f0 = 0; f0 < e; f0 += 32) {
+                const int f = f0 + lane;
+                earlier = earlier || (__ballot_sync(kFullMask, f < e && s_list[f].cell == cell) != 0u);
+            }
+            if (earlier) continue;
+            const int a = (int)(((float)cell + 0.5f) * p.invHW);
+            const int pos = (int)cell - a * HW;
+            const size_t off = (size_t)a * p.attrs * HW + pos;
+            const float *q = hbase + off;
+            float *g = gbase + off;
+            const float tc = __ldg(q + 4 * (size_t)HW);
+            double gx = 0.0, gy = 0.0, gw = 0.0, gh = 0.0;
+            for (int f0 = e - (e & 31); f0 < nE; f0 += 32) {
+                const int f = f0 + lane;
+                if (f >= e && f < nE && s_list[f].cell == cell) {
+                    const double4 c4 = s_contrib[f];
+                    gx += c4.x; gy += c4.y; gw += c4.z; gh += c4.w;
+                }
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                gx += __shfl_xor_sync(kFullMask, gx, sh);
+                gy += __shfl_xor_sync(kFullMask, gy, sh);
+                gw += __shfl_xor_sync(kFullMask, gw, sh);
+                gh += __shfl_xor_sync(kFullMask, gh, sh);
+            }
+            if (lane == 0) {
+                g[0] = (float)gx;
+                g[HW] = (float)gy;
+                g[2 * (size_t)HW] = (float)gw;
+                g[3 * (size_t)HW] = (float)gh;
+                g[4 * (size_t)HW] = (float)(((double)sigmoid_f(tc) - 1.0) * inv_w);  // target 1 (:149-150)
+            }
+            // class channels: target 0.95 for every class assigned to the cell, 0.05 otherwise (:425-434)
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                float o = 0.f;
+                if (c < C) o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
+                bool hit = false;
+                for (int f0 = e - (e & 31); f0 < nE; f0 += 32) {
+                    const int f = f0 + lane;
+                    unsigned bal = __ballot_sync(kFullMask, f >= e && f < nE && s_list[f].cell == cell);
+                    while (bal) {
+                        const int f2 = f0 + __ffs(bal) - 1;
+                        bal &= bal - 1u;
+                        hit = hit || (s_gcls[s_list[f2].t] == c);
+                    }
+                }
+                if (c < C) g[(size_t)(5 + c) * HW] = (float)(((double)o - (hit ? (double)0.95f : (double)0.05f)) * inv_w);
+            }
+        }
     }
 }
 

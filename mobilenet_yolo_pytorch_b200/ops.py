@@ -187,8 +187,9 @@ def pack_targets(targets, device) -> Tuple[torch.Tensor, torch.Tensor, int, List
 
 def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,
                      mask: Sequence[int], num_classes: int, ignore_thr: float, iou_thr: float,
-                     want_assign: bool = False, max_gt: int = 0):
-    """b200yolo_target_loss: returns (sums (16,) float64 device, status (1,) int32 device[, assign, terms])."""
+                     want_assign: bool = False, max_gt: int = 0, cell_state: Optional[torch.Tensor] = None):
+    """b200yolo_target_loss: returns (sums (16,) float64 device, status (1,) int32 device[, assign, terms]).
+    ``cell_state``: optional (N, A*H*W) uint8 output consumed by ``target_loss_backward``."""
     _require_cuda(head, "head")
     head = head.contiguous()
     N, ch, H, W = head.shape
@@ -214,8 +215,33 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
             head.data_ptr(), N, A, num_classes, H, W, sa.ctypes.data, sa.shape[0], m.ctypes.data, gt.data_ptr(),
             gt_off.data_ptr(), int(G), float(np.float32(ignore_thr)), float(np.float32(iou_thr)), int(max_gt), sums.data_ptr(),
             assign.data_ptr() if want_assign else None, terms.data_ptr() if want_assign else None,
-            status.data_ptr(), None, ws.data_ptr(), ws.numel(), _stream(head)))
+            status.data_ptr(), cell_state.data_ptr() if cell_state is not None else None, ws.data_ptr(), ws.numel(),
+            _stream(head)))
     return (sums, status, assign, terms) if want_assign else (sums, status)
+
+
+def target_loss_backward(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,
+                         mask: Sequence[int], num_classes: int, iou_thr: float, cell_state: torch.Tensor,
+                         sums: torch.Tensor, iou_weighting: float, grad_out: Optional[torch.Tensor] = None,
+                         max_gt: int = 0) -> torch.Tensor:
+    """b200yolo_target_loss_backward: d loss / d head, same shape as ``head``.  ``sums`` is the (all-reduced)
+    device vector of the forward call, ``grad_out`` an optional device scalar."""
+    _require_cuda(head, "head")
+    head = head.contiguous()
+    N, ch, H, W = head.shape
+    A = len(mask)
+    sa = _host_f32(anchors_all_scaled).reshape(-1, 2)
+    m = np.ascontiguousarray(np.asarray(mask, dtype=np.int32))
+    with torch.cuda.device(head.device):
+        grad = torch.empty_like(head)
+        go = None
+        if grad_out is not None:
+            go = grad_out.detach().to(device=head.device, dtype=torch.float32).reshape(1).contiguous()
+        _lib.check(_lib.load().b200yolo_target_loss_backward(
+            head.data_ptr(), N, A, num_classes, H, W, sa.ctypes.data, sa.shape[0], m.ctypes.data, gt.data_ptr(),
+            gt_off.data_ptr(), int(G), float(np.float32(iou_thr)), int(max_gt), cell_state.data_ptr(), sums.data_ptr(),
+            float(np.float32(iou_weighting)), go.data_ptr() if go is not None else None, grad.data_ptr(), _stream(head)))
+    return grad
 
 
 def loss_finalize(sums_host: np.ndarray, iou_weighting: float) -> np.ndarray:

@@ -64,10 +64,14 @@ class YOLOLoss(nn.Module):
     def forward(self, input: torch.Tensor, targets=None):
         if targets is None:
             return self.get_pred_boxes(input)
-        N = input.size(0)
         gt, gt_off, G, counts = ops.pack_targets(targets, input.device)
-        sums, status = ops.target_loss_sums(input, gt, gt_off, G, self.scaled_anchors(), self.mask, self.num_classes,
-                                            self.ignore_threshold, self.iou_thresh, max_gt=max(counts + [1]))
+        max_gt = max(counts + [1])
+        need_grad = torch.is_grad_enabled() and input.requires_grad
+        x = input.detach()
+        N, _, H, W = x.shape
+        state = torch.empty((N, self.num_mask * H * W), dtype=torch.uint8, device=x.device) if need_grad else None
+        sums, status = ops.target_loss_sums(x, gt, gt_off, G, self.scaled_anchors(), self.mask, self.num_classes,
+                                            self.ignore_threshold, self.iou_thresh, max_gt=max_gt, cell_state=state)
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.process_group)
@@ -82,6 +86,30 @@ class YOLOLoss(nn.Module):
             raise RuntimeError("more than 1024 GT boxes in one image are not supported by the target-assignment kernel")
         r = ops.loss_finalize(host[:_lib.S_COUNT], self.iou_weighting)
         loss = torch.tensor(r[0], dtype=torch.float32, device=input.device)
+        if need_grad:
+            # loss.backward() (train.py:282) runs b200yolo_target_loss_backward on the saved cell states and the
+            # batch-global sums
+            loss = _LossGrad.apply(input, loss, self, gt, gt_off, G, max_gt, state, sums)
         no_obj = torch.tensor(r[4], dtype=torch.float32, device=input.device) if r[6] > 0 else 0
         # yolo_loss.py:236 -- loss, recall, avg_iou, obj, no_obj (tensor), cls_score, count/bs
         return loss, float(r[1]), float(r[2]), float(r[3]), no_obj, float(r[5]), float(r[6])
+
+
+class _LossGrad(torch.autograd.Function):
+    """Attaches the analytic gradient of the fused loss to the autograd graph: forward returns the loss value
+    computed by the kernels, backward launches ``b200yolo_target_loss_backward``."""
+
+    @staticmethod
+    def forward(ctx, input, loss_value, module, gt, gt_off, G, max_gt, state, sums):
+        ctx.save_for_backward(input.detach(), gt, gt_off, state, sums)
+        ctx.cfg = (G, max_gt, module.scaled_anchors(), list(module.mask), module.num_classes, module.iou_thresh,
+                   module.iou_weighting)
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, gt, gt_off, state, sums = ctx.saved_tensors
+        G, max_gt, sa, mask, C, iou_thr, iou_w = ctx.cfg
+        grad = ops.target_loss_backward(x, gt, gt_off, G, sa, mask, C, iou_thr, state, sums, iou_w, grad_out=grad_output,
+                                        max_gt=max_gt)
+        return (grad,) + (None,) * 8

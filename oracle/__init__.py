@@ -14,6 +14,7 @@ fixtures in ``tests/golden/`` generated from the reference's own Python by
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 import threading
@@ -215,3 +216,106 @@ def target_loss(head, targets, anchors, mask, num_classes, img_size, ignore_thre
     if want_dense:
         res["targets"], res["weights"] = tg, wg
     return res
+
+
+def _ciou_value_and_grad(gt, pr):
+    """v = iou - ciou_term of YOLOLoss.box_ciou(box1=gt, box2=pred) (yolo_loss.py:257-293) and dv/d(pred xyxy),
+    float64, differentiating every operation of the reference's graph (alpha is NOT detached, :283;
+    max/min/clamp pass the gradient to the selected operand)."""
+    a1, b1, a2, b2 = [float(x) for x in gt]
+    p1, q1, p2, q2 = [float(x) for x in pr]
+    g = np.zeros
+    # intersection (utils/iou.py:4-13)
+    lox, loy, hix, hiy = max(a1, p1), max(b1, q1), min(a2, p2), min(b2, q2)
+    iw_raw, ih_raw = hix - lox, hiy - loy
+    iw, ih = max(iw_raw, 0.0), max(ih_raw, 0.0)
+    d_iw = g(4)
+    d_ih = g(4)
+    if iw_raw >= 0:
+        d_iw[2] = 1.0 if p2 < a2 else (0.5 if p2 == a2 else 0.0)
+        d_iw[0] = -(1.0 if p1 > a1 else (0.5 if p1 == a1 else 0.0))
+    if ih_raw >= 0:
+        d_ih[3] = 1.0 if q2 < b2 else (0.5 if q2 == b2 else 0.0)
+        d_ih[1] = -(1.0 if q1 > b1 else (0.5 if q1 == b1 else 0.0))
+    inter = iw * ih
+    d_inter = d_iw * ih + iw * d_ih
+    area1 = (a2 - a1) * (b2 - b1)
+    w2, h2 = p2 - p1, q2 - q1
+    d_w2 = np.array([-1.0, 0, 1.0, 0])
+    d_h2 = np.array([0, -1.0, 0, 1.0])
+    area2 = w2 * h2
+    d_area2 = d_w2 * h2 + w2 * d_h2
+    union = area1 + area2 - inter
+    d_union = d_area2 - d_inter
+    iou = inter / union
+    d_iou = (d_inter * union - inter * d_union) / (union * union)
+    # enclosing box area (box_c :249-256, :264)
+    cw, ch = max(a2, p2) - min(a1, p1), max(b2, q2) - min(b1, q1)
+    d_cw = np.array([-(1.0 if p1 < a1 else (0.5 if p1 == a1 else 0.0)), 0, (1.0 if p2 > a2 else (0.5 if p2 == a2 else 0.0)), 0])
+    d_ch = np.array([0, -(1.0 if q1 < b1 else (0.5 if q1 == b1 else 0.0)), 0, (1.0 if q2 > b2 else (0.5 if q2 == b2 else 0.0))])
+    c = cw * ch
+    d_c = d_cw * ch + cw * d_ch
+    # centre distance (:269-272)
+    dx, dy = (a2 + a1) / 2 - (p2 + p1) / 2, (b1 + b2) / 2 - (q1 + q2) / 2
+    u = dx * dx + dy * dy
+    d_u = np.array([-dx, -dy, -dx, -dy])
+    dd = u / c
+    d_dd = (d_u * c - u * d_c) / (c * c)
+    # aspect-ratio term (:279-283); "ar_gt" is the PRED box's w/h in the reference
+    w1, h1 = a2 - a1, b2 - b1
+    k = 4.0 / (math.pi * math.pi)
+    delta = math.atan(w2 / h2) - math.atan(w1 / h1)
+    d_delta = (h2 * d_w2 - w2 * d_h2) / (h2 * h2 + w2 * w2)
+    A = k * delta * delta
+    d_A = 2.0 * k * delta * d_delta
+    D = 1.0 - iou + A + 0.000001
+    d_D = -d_iou + d_A
+    f = A * A / D                      # alpha * ar_loss
+    d_f = (2.0 * A * d_A * D - A * A * d_D) / (D * D)
+    if c == 0.0:                       # :286-287 term = iou -> v = 0
+        return 0.0, iou, np.zeros(4)
+    return iou - (dd + f), iou, d_iou - d_dd - d_f
+
+
+def target_loss_backward(head, targets, anchors, mask, num_classes, img_size, ignore_threshold, iou_thresh,
+                         iou_weighting, grad_out: float = 1.0):
+    """d loss / d input of YOLOLoss.forward(input, targets) (yolo_loss.py:206-236) as the reference's autograd
+    graph defines it: the custom sigmoid (:15-32) passes gradients through unchanged, exp has its true
+    derivative, only entries of `targets` overwritten with constants (weight 1) carry a gradient
+    2 (o - t) w / sum(w) (:53-60), and the CIoU loss sum_i (v_i - 1)^2 / n_assign (:224, weights cancel)
+    reaches tx, ty, tw, th of the assigned cells through the decoded box.  float64 maths, float32 result."""
+    x = _f32(head)
+    N, ch, H, W = x.shape
+    A = len(mask)
+    attrs = 5 + num_classes
+    fwd = target_loss(x, targets, anchors, mask, num_classes, img_size, ignore_threshold, iou_thresh, iou_weighting,
+                      want_dense=True)
+    xv = x.reshape(N, A, attrs, H, W).astype(np.float64)
+    grad = np.zeros_like(xv)
+    out = 1.0 / (1.0 + np.exp(-xv[:, :, 4:]))                       # (N,A,C+1,H,W)
+    tg = np.moveaxis(fwd["targets"].astype(np.float64), 4, 2)       # (N,A,H,W,C+1) -> (N,A,C+1,H,W)
+    wg = np.moveaxis(fwd["weights"].astype(np.float64), 4, 2)
+    sw = wg.sum()
+    grad[:, :, 4:] = 2.0 * (out - tg) * wg / sw                     # identity through the custom sigmoid
+    n = len(fwd["assign"])
+    sa = scaled_anchors(anchors, img_size).astype(np.float64)
+    for (b, t, k, gj, gi, _bn) in fwd["assign"]:
+        tb = _f32(targets[b]).reshape(-1, 5)[t]
+        cx, cy, w, h = [np.float32(v) for v in tb[1:5]]
+        g1 = np.float32(cx - w / np.float32(2))
+        g2 = np.float32(cy - h / np.float32(2))
+        gtb = (g1, g2, np.float32(w + g1), np.float32(h + g2))      # :112-113 in fp32 like the reference
+        tx, ty, tw, th = xv[b, k, 0:4, gj, gi]
+        sx, sy = 1.0 / (1.0 + math.exp(-tx)), 1.0 / (1.0 + math.exp(-ty))
+        bw, bh = math.exp(tw) * sa[mask[k]][0], math.exp(th) * sa[mask[k]][1]
+        pcx, pcy = (sx + gi) / W, (sy + gj) / H
+        p1, q1 = pcx - bw / 2, pcy - bh / 2
+        pr = (p1, q1, bw + p1, bh + q1)
+        v, _iou, dv = _ciou_value_and_grad(gtb, pr)
+        gl = float(iou_weighting) * 2.0 * (v - 1.0) / n             # d(iou_weighting * sum (v-1)^2 / n) / dv
+        # d pred / d (tx,ty,tw,th): sigmoid passes through (d sx/d tx = 1), exp is exact
+        grad[b, k, 0, gj, gi] += gl * (dv[0] + dv[2]) / W
+        grad[b, k, 1, gj, gi] += gl * (dv[1] + dv[3]) / H
+        grad[b, k, 2, gj, gi] += gl * (dv[2] - dv[0]) * 0.5 * bw
+        grad[b, k, 3, gj, gi] += gl * (dv[3] - dv[1]) * 0.5 * bh
+    return (grad * float(grad_out)).reshape(N, ch, H, W).astype(np.float32)

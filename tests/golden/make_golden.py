@@ -292,6 +292,11 @@ def case_loss(name, cfg, N, counts, seed, nonsquare=False):
         d[f"weights{i}"] = wg.numpy()
         d[f"ciou_terms{i}"] = ious.numpy().reshape(-1)
         d[f"ciou_weights{i}"] = iouw.numpy().reshape(-1)
+        # d loss / d input by the reference's own autograd graph (custom pass-through sigmoid :15-32, exp,
+        # the in-place wh_to_x2y2, box_ciou with alpha NOT detached, batch-global normalisers)
+        hg = h.clone().requires_grad_(True)
+        l(hg, targets)[0].backward()
+        d[f"grad{i}"] = hg.grad.numpy().copy()
         print(name, "head", i, "tuple", d[f"tuple{i}"], "assign", len(mirror))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
 

@@ -419,3 +419,55 @@ def test_target_loss_out_of_range_gt_raises(cuda_device):
         l(head, [torch.tensor([[1.0, 1.0, 0.5, 0.1, 0.1]])])  # cx == 1.0 -> gi == W (yolo_loss.py:128,149)
     empty = l(head, [torch.zeros(0, 5)])  # no GT at all: loss is the pure no-object term, stats 0
     assert empty[1:] == (0.0, 0.0, 0.0, 0, 0.0, 0.0)
+
+
+# ----------------------------------------------------------------------------- loss backward
+GRAD_TOL = 1e-5  # |d| <= GRAD_TOL * max|grad| (the reference's autograd itself runs in fp32)
+
+
+def gpu_loss_grad(head, targets, anchors, mask, C, img, ign, iou_t, iou_w, dev, grad_out=None):
+    l = b200.YOLOLoss(anchors, mask, C, img, ign, iou_t, iou_weighting=iou_w)
+    x = torch.from_numpy(np.asarray(head, np.float32)).to(dev).requires_grad_(True)
+    tup = l(x, [torch.from_numpy(np.asarray(t, np.float32)) for t in targets])
+    assert tup[0].requires_grad
+    if grad_out is None:
+        tup[0].backward()
+    else:
+        (tup[0] * grad_out).backward()
+    return x.grad.cpu().numpy(), tup
+
+
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+def test_loss_backward_vs_reference_autograd_golden(case, cuda_device):
+    d = load_golden(case)
+    targets = unpack_ragged(d, "targets")
+    for i in range(2):
+        args = (d[f"head{i}"], targets, d["anchors"].tolist(), d["mask"][i].tolist(), int(d["num_classes"]),
+                d["img_size"].tolist(), float(d["ignore_thresh"][i]), float(d["iou_thresh"]), float(d["iou_weighting"]))
+        g, tup = gpu_loss_grad(*args, cuda_device)
+        ref = d[f"grad{i}"]                     # input.grad after the reference's loss.backward()
+        assert np.array_equal(g != 0, ref != 0), "gradient support differs from the reference"
+        assert np.abs(g - ref).max() <= GRAD_TOL * np.abs(ref).max()
+        o = oracle.target_loss_backward(*args)
+        assert np.abs(g - o).max() <= GRAD_TOL * np.abs(o).max()
+        np.testing.assert_allclose(float(tup[0].detach()), d[f"tuple{i}"][0], rtol=RTOL)
+
+
+@pytest.mark.parametrize("N,G,grid,C", [(8, 100, (11, 11), 20), (8, 100, (22, 22), 20), (5, [0, 1, 300, 7, 0], (22, 22), 20),
+                                        (3, 40, (12, 20), 10)])
+def test_loss_backward_vs_oracle_config4_shapes(N, G, grid, C, cuda_device):
+    head = make_heads(N, C, [grid], seed=17)[0].numpy()
+    targets = synth_targets(N, G, C, seed=23)
+    mask = MASK[0] if grid[0] <= 12 else MASK[1]
+    args = (head, targets, VOC_ANCHORS, mask, C, [352, 352], 0.5623606200028424, 0.5497280113447018, 0.021830872589525777)
+    g, _ = gpu_loss_grad(*args, cuda_device, grad_out=2.5)
+    o = oracle.target_loss_backward(*args, grad_out=2.5)
+    assert np.array_equal(g != 0, o != 0)
+    assert np.abs(g - o).max() <= GRAD_TOL * np.abs(o).max()
+
+
+def test_loss_without_grad_has_no_graph(cuda_device):
+    head = make_heads(2, 20, [(11, 11)], seed=3)[0].to(cuda_device)
+    l = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.55)
+    tup = l(head, [torch.from_numpy(t) for t in synth_targets(2, 5, 20, seed=1)])
+    assert not tup[0].requires_grad

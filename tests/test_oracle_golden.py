@@ -97,3 +97,25 @@ def test_out_of_range_gt_raises():
     t = [np.array([[1.0, 1.0, 0.5, 0.1, 0.1]], np.float32)] + [np.zeros((0, 5), np.float32)] * 2  # cx == 1.0
     with pytest.raises(IndexError):
         oracle.target_loss(d["head0"], t, d["anchors"].tolist(), d["mask"][0].tolist(), 20, [352, 352], 0.6, 0.5, 0.02)
+
+
+GRAD_TOL = 1e-5  # |d| <= GRAD_TOL * max|grad|: the reference's autograd runs in fp32
+
+
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+def test_target_loss_backward_matches_reference_autograd(case):
+    """oracle.target_loss_backward (analytic, float64) vs input.grad after the reference's own
+    loss.backward() (tests/golden/make_golden.py)."""
+    d = load_golden(case)
+    targets = unpack_ragged(d, "targets")
+    for i in range(2):
+        g = oracle.target_loss_backward(d[f"head{i}"], targets, d["anchors"].tolist(), d["mask"][i].tolist(),
+                                        int(d["num_classes"]), d["img_size"].tolist(), float(d["ignore_thresh"][i]),
+                                        float(d["iou_thresh"]), float(d["iou_weighting"]))
+        ref = d[f"grad{i}"]
+        assert np.array_equal(g != 0, ref != 0), "gradient support differs"
+        assert np.abs(g - ref).max() <= GRAD_TOL * np.abs(ref).max()
+        # box channels of assigned cells carry the CIoU gradient
+        A, attrs = len(d["mask"][i]), 5 + int(d["num_classes"])
+        box = ref.reshape(ref.shape[0], A, attrs, *ref.shape[2:])[:, :, :4]
+        assert (box != 0).any()
