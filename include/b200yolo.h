@@ -169,6 +169,28 @@ int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H,
                                   int max_gt_per_image, const unsigned char *cell_state, const double *sums,
                                   float iou_weighting, const float *grad_out, float *grad_input, void *stream);
 
+/*
+ * utils.eval_mAP.calculate_mAP  (utils/eval_mAP.py:134-188, eval_class_ap :65-132,
+ * eval_single_image_recall :8-63; called from train.py:421 on the NMS output): per class the greedy
+ * detection <-> ground-truth matching of every image (IoU > iou_thr, 'difficult' objects ignored), then
+ * the 11-point interpolated average precision over the score-sorted detections.
+ *   det_boxes dev [D][4] xyxy (16-byte aligned), det_labels dev int32 [D] in 1..n_classes-1,
+ *   det_scores dev [D], det_off dev int32 [N+1]: the detections of image b are rows det_off[b]..det_off[b+1]
+ *             in the order the reference would see them (train.py:385-388)
+ *   true_boxes dev [T][4], true_labels dev int32 [T], true_difficult dev uint8 [T], true_off dev [N+1]
+ *   recall_thresholds HOST float[n_thresholds <= 16]: torch.arange(0, 1.1, .1) in the reference (:120)
+ *   ap, tp_sum, fp_sum dev float [n_classes-1]: average precision, #true / #false positives per class
+ *             (mAP = mean of ap, taken by the caller)
+ *   workspace dev, b200yolo_map_eval_workspace_bytes(D, T, N, n_classes) bytes
+ * Score ties are ordered by detection index (the reference's torch.sort leaves them unspecified).
+ */
+size_t b200yolo_map_eval_workspace_bytes(int D, int T, int N, int n_classes);
+int b200yolo_map_eval(const float *det_boxes, const int *det_labels, const float *det_scores, const int *det_off, int D,
+                      const float *true_boxes, const int *true_labels, const unsigned char *true_difficult,
+                      const int *true_off, int T, int N, int n_classes, float iou_thr, const float *recall_thresholds,
+                      int n_thresholds, float *ap, float *tp_sum, float *fp_sum, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 /* indices into the partial-sum vector of b200yolo_target_loss */
 enum {
     B200YOLO_S_SQW = 0,      /* sum (o-t)^2 w           (yolo_loss.py:54-58) */

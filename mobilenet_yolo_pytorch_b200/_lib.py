@@ -43,6 +43,10 @@ SIGNATURES = {
                                                 c_f32p, c_i32p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_float, c_f32p, c_f32p, C.c_void_p]),
     "b200yolo_loss_finalize": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "b200yolo_map_eval_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200yolo_map_eval": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int, c_f32p, c_i32p, C.c_void_p, c_i32p, C.c_int,
+                                    C.c_int, C.c_int, C.c_float, c_f32p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
 }
 
 # partial-sum slots (enum in include/b200yolo.h)

@@ -14,6 +14,7 @@
 #include "decode_nms.cuh"  // (after the helpers it uses)
 #include "pairwise.cuh"
 #include "target_loss.cuh"
+#include "map_eval.cuh"
 
 using namespace b200yolo;
 
@@ -394,6 +395,59 @@ int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H,
     p.S = S;
     p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
     target_loss_backward_kernel<<<N * S, kTLThreads, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static size_t map_align(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t b200yolo_map_eval_workspace_bytes(int D, int T, int N, int n_classes) {
+    const size_t Cf = (size_t)(n_classes > 1 ? n_classes - 1 : 1);
+    return map_align((size_t)(T > 0 ? T : 1)) + map_align(2 * Cf * sizeof(int)) + map_align((size_t)(D > 0 ? D : 1)) +
+           map_align(Cf * (size_t)(N > 0 ? N : 1) * sizeof(int)) + map_align((2 * (size_t)(D > 0 ? D : 1) + Cf) * sizeof(unsigned long long));
+}
+
+int b200yolo_map_eval(const float *det_boxes, const int *det_labels, const float *det_scores, const int *det_off, int D,
+                      const float *true_boxes, const int *true_labels, const unsigned char *true_difficult,
+                      const int *true_off, int T, int N, int n_classes, float iou_thr, const float *recall_thresholds,
+                      int n_thresholds, float *ap, float *tp_sum, float *fp_sum, void *workspace, size_t workspace_bytes,
+                      void *stream) {
+    if (!det_off || !true_off || !ap || !tp_sum || !fp_sum || !workspace || !recall_thresholds)
+        return fail(B200YOLO_EINVAL, "map_eval: null pointer");
+    if ((D > 0 && (!det_boxes || !det_labels || !det_scores)) || (T > 0 && (!true_boxes || !true_labels || !true_difficult)))
+        return fail(B200YOLO_EINVAL, "map_eval: null data pointer");
+    if (N < 0 || D < 0 || T < 0 || n_classes < 2 || n_thresholds < 1 || n_thresholds > kMapMaxThr)
+        return fail(B200YOLO_EINVAL, "map_eval: bad argument");
+    if (D >= (1 << 30)) return fail(B200YOLO_EUNSUPPORTED, "map_eval: more than 2^30 detections");
+    if ((D > 0 && ((uintptr_t)det_boxes & 15)) || (T > 0 && ((uintptr_t)true_boxes & 15)))
+        return fail(B200YOLO_EINVAL, "map_eval: boxes must be 16-byte aligned");
+    if (workspace_bytes < b200yolo_map_eval_workspace_bytes(D, T, N, n_classes))
+        return fail(B200YOLO_EINVAL, "map_eval: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    MapParams p;
+    memset(&p, 0, sizeof(p));
+    p.det_boxes = det_boxes; p.det_labels = det_labels; p.det_scores = det_scores; p.det_off = det_off;
+    p.true_boxes = true_boxes; p.true_labels = true_labels; p.true_difficult = true_difficult; p.true_off = true_off;
+    p.N = N; p.Cf = n_classes - 1; p.iou_thr = iou_thr;
+    p.n_thr = n_thresholds;
+    for (int i = 0; i < n_thresholds; ++i) p.thr[i] = recall_thresholds[i];
+    const size_t Cf = (size_t)p.Cf;
+    unsigned char *w = (unsigned char *)workspace;
+    p.detected = w; w += map_align((size_t)(T > 0 ? T : 1));
+    p.M = (int *)w; p.n_easy = p.M + Cf; w += map_align(2 * Cf * sizeof(int));
+    const size_t zero_bytes = (size_t)(w - (unsigned char *)workspace);   // detected[], M[], n_easy[] start at zero
+    p.flags = w; w += map_align((size_t)(D > 0 ? D : 1));
+    p.cnt = (int *)w; w += map_align(Cf * (size_t)(N > 0 ? N : 1) * sizeof(int));
+    p.keys = (unsigned long long *)w;
+    p.ap = ap; p.tp_sum = tp_sum; p.fp_sum = fp_sum;
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, zero_bytes, st));
+    if (N > 0) {
+        map_match_kernel<<<N, kMapMatchThreads, 0, st>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+    }
+    map_class_kernel<<<p.Cf, kMapClassThreads, 0, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -47,7 +47,7 @@ def decode_nms(out0: torch.Tensor, out1: torch.Tensor, yolo_losses: Sequence, nu
     return lst
 
 
-def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_yolo=None) -> None:
+def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_yolo=None, utils_eval_map=None) -> None:
     """Swap the reference's entry points for the B200 ones inside already-imported
     reference modules.  Pass the modules you want patched."""
     from . import box as _box, iou as _iou, yolo_loss as _yl
@@ -62,3 +62,6 @@ def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_
     if mbv2_yolo is not None:
         mbv2_yolo.YOLOLoss = _yl.YOLOLoss
         mbv2_yolo.nms = _box.nms
+    if utils_eval_map is not None:
+        from . import eval_mAP as _em
+        utils_eval_map.calculate_mAP = _em.calculate_mAP

@@ -319,3 +319,90 @@ def target_loss_backward(head, targets, anchors, mask, num_classes, img_size, ig
         grad[b, k, 2, gj, gi] += gl * (dv[2] - dv[0]) * 0.5 * bw
         grad[b, k, 3, gj, gi] += gl * (dv[3] - dv[1]) * 0.5 * bh
     return (grad * float(grad_out)).reshape(N, ch, H, W).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- mAP (utils/eval_mAP.py), SURVEY 8 f2
+def _iou_f32(box, boxes):
+    """find_jaccard_overlap of one box against (n,4) boxes in float32 (utils/iou.py:32-49)."""
+    box = np.asarray(box, np.float32)
+    boxes = np.asarray(boxes, np.float32).reshape(-1, 4)
+    lo = np.maximum(box[:2], boxes[:, :2])
+    hi = np.minimum(box[2:], boxes[:, 2:])
+    d = hi - lo
+    d = np.where(d < 0, np.float32(0), d).astype(np.float32)   # clamp(min=0) keeps NaN
+    inter = (d[:, 0] * d[:, 1]).astype(np.float32)
+    a1 = np.float32((box[2] - box[0]) * (box[3] - box[1]))
+    a2 = ((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])).astype(np.float32)
+    union = ((a1 + a2).astype(np.float32) - inter).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (inter / union).astype(np.float32)
+
+
+def map_match_image(det_boxes, det_labels, true_boxes, true_labels, true_difficulties, c, iou_thr=0.5):
+    """eval_single_image_recall (utils/eval_mAP.py:8-63) for class ``c``: (tp, fp) flags of the image's class-c
+    detections in the order given, and the number of non-difficult class-c objects."""
+    tsel = np.asarray(true_labels) == c
+    dsel = np.asarray(det_labels) == c
+    tb = np.asarray(true_boxes, np.float32).reshape(-1, 4)[tsel]
+    td = np.asarray(true_difficulties).reshape(-1)[tsel]
+    n_easy = int((1 - td.astype(np.int64)).sum())                    # :17
+    db = np.asarray(det_boxes, np.float32).reshape(-1, 4)[dsel]
+    tp = np.zeros(len(db), np.float32)
+    fp = np.zeros(len(db), np.float32)
+    detected = np.zeros(len(tb), np.uint8)
+    for d in range(len(db)):                                          # :32
+        if len(tb) == 0:
+            fp[d] = 1                                                 # :37-39
+            continue
+        ov = _iou_f32(db[d], tb)                                      # :41
+        if np.isnan(ov).any():                                        # torch.max propagates NaN; NaN > 0.5 is False
+            fp[d] = 1
+            continue
+        ind = int(np.argmax(ov))                                      # first maximum (:42)
+        if ov[ind] > np.float32(iou_thr):                             # :51
+            if td[ind] == 0:                                          # :53
+                if detected[ind] == 0:
+                    tp[d] = 1
+                    detected[ind] = 1
+                else:
+                    fp[d] = 1
+        else:
+            fp[d] = 1                                                 # :61-62
+    return tp, fp, n_easy
+
+
+def calculate_map(det_boxes, det_labels, det_scores, true_boxes, true_labels, true_difficulties, n_classes, iou_thr=0.5):
+    """calculate_mAP (utils/eval_mAP.py:134-188) with eval_class_ap (:65-132): lists over images; labels 1..n_classes-1
+    (0 = background).  Returns (ap (n_classes-1,) float32, mAP, tp sums, fp sums).  Ties in score are ordered by
+    (image, detection) index -- the reference's torch.sort leaves them unspecified."""
+    aps = np.zeros(n_classes - 1, np.float32)
+    tps = np.zeros(n_classes - 1, np.float32)
+    fps = np.zeros(n_classes - 1, np.float32)
+    rec_thr = np.arange(0, 1.1, 0.1, dtype=np.float32)               # torch.arange(0, 1.1, .1) (:120), compared as fp32
+    for c in range(1, n_classes):
+        tp_all, fp_all, sc_all, n_easy = [], [], [], 0
+        for b in range(len(det_boxes)):
+            tp, fp, ne = map_match_image(det_boxes[b], det_labels[b], true_boxes[b], true_labels[b], true_difficulties[b], c, iou_thr)
+            tp_all.append(tp)
+            fp_all.append(fp)
+            sc_all.append(np.asarray(det_scores[b], np.float32).reshape(-1)[np.asarray(det_labels[b]) == c])
+            n_easy += ne
+        tp_all = np.concatenate(tp_all) if tp_all else np.zeros(0, np.float32)
+        fp_all = np.concatenate(fp_all) if fp_all else np.zeros(0, np.float32)
+        sc_all = np.concatenate(sc_all) if sc_all else np.zeros(0, np.float32)
+        order = np.argsort(-sc_all, kind="stable")                   # :107
+        tp_s, fp_s = tp_all[order], fp_all[order]
+        ctp = np.cumsum(tp_s, dtype=np.float32)                       # :113-114
+        cfp = np.cumsum(fp_s, dtype=np.float32)
+        prec = (ctp / ((ctp + cfp).astype(np.float32) + np.float32(1e-10))).astype(np.float32)   # :115-116
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rec = (ctp / np.float32(n_easy)).astype(np.float32)      # :117
+        p11 = np.zeros(11, np.float32)
+        for i, t in enumerate(rec_thr):                               # :121-126
+            above = rec >= t
+            if above.any():
+                p11[i] = prec[above].max()
+        aps[c - 1] = p11.mean(dtype=np.float32)
+        tps[c - 1] = tp_s.sum()
+        fps[c - 1] = fp_s.sum()
+    return aps, float(aps.mean(dtype=np.float32)), tps, fps

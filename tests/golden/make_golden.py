@@ -309,6 +309,45 @@ def check_pre_maps_patch():
     assert torch.equal(g0, g1) and torch.equal(a0, a1), "pre_maps patch is not identical on square grids"
 
 
+def case_map(name, N, C, seed):
+    """utils/eval_mAP.py::calculate_mAP on synthetic detections / ground truth (SURVEY 8 f2): detections are
+    jittered copies of GT boxes (some with the wrong label) plus random boxes, random scores; some GT boxes are
+    'difficult'; some images have no GT or no detections; the last class has no GT at all."""
+    from utils.eval_mAP import calculate_mAP
+    r = np.random.RandomState(seed)
+    lists = {k: [] for k in ("det_boxes", "det_labels", "det_scores", "true_boxes", "true_labels", "true_difficulties")}
+    for b in range(N):
+        ng = 0 if b % 7 == 3 else r.randint(1, 7)
+        nd = 0 if b % 5 == 4 else r.randint(1, 18)
+        g = np.sort(r.rand(ng, 2, 2), axis=1).reshape(ng, 4).astype(np.float32)
+        gl = r.randint(1, C - 1, ng)                      # labels 1..C-2: class C-1 never has ground truth
+        d, dl = [], []
+        for _ in range(nd):
+            if ng and r.rand() < 0.6:
+                j = r.randint(ng)
+                d.append(g[j] + r.randn(4).astype(np.float32) * 0.03)
+                dl.append(gl[j] if r.rand() < 0.8 else r.randint(1, C))
+            else:
+                d.append(np.sort(r.rand(2, 2), axis=0).reshape(4).astype(np.float32))
+                dl.append(r.randint(1, C))
+        lists["det_boxes"].append(np.array(d, np.float32).reshape(-1, 4))
+        lists["det_labels"].append(np.array(dl, np.int64).reshape(-1))
+        lists["det_scores"].append(r.rand(nd).astype(np.float32))
+        lists["true_boxes"].append(g.reshape(-1, 4))
+        lists["true_labels"].append(gl.astype(np.int64).reshape(-1))
+        lists["true_difficulties"].append((r.rand(ng) < 0.2).astype(np.uint8))
+    names = ["background"] + [f"c{i}" for i in range(1, C)]
+    t = {k: [torch.from_numpy(x) for x in v] for k, v in lists.items()}
+    aps, m, tp, fp = calculate_mAP(t["det_boxes"], t["det_labels"], t["det_scores"], t["true_boxes"], t["true_labels"],
+                                   t["true_difficulties"], names)
+    d = dict(n_classes=np.int32(C), ap=np.array(list(aps.values()), np.float32), mAP=np.float64(m),
+             tp=np.array(list(tp.values()), np.float32), fp=np.array(list(fp.values()), np.float32))
+    for k, v in lists.items():
+        pack_ragged(k, [x.astype(np.float32) if x.dtype != np.uint8 and x.dtype != np.int64 else x for x in v], d)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "mAP", m, "AP", d["ap"])
+
+
 def main():
     torch.set_num_threads(1)
     check_pre_maps_patch()
@@ -320,6 +359,7 @@ def main():
     case_iou()
     case_loss("loss_voc_n3", VOC, 3, [6, 0, 14], 5)
     case_loss("loss_bdd_nonsquare_n2", BDD, 2, [9, 4], 6, nonsquare=True)
+    case_map("map_n40_c6", 40, 6, 11)
 
 
 if __name__ == "__main__":

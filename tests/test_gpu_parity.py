@@ -471,3 +471,72 @@ def test_loss_without_grad_has_no_graph(cuda_device):
     l = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.55)
     tup = l(head, [torch.from_numpy(t) for t in synth_targets(2, 5, 20, seed=1)])
     assert not tup[0].requires_grad
+
+
+# ----------------------------------------------------------------------------- mAP
+MAP_KEYS = ("det_boxes", "det_labels", "det_scores", "true_boxes", "true_labels", "true_difficulties")
+
+
+def gpu_map(L, n_classes, dev):
+    t = [[torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in lst] for lst in L]
+    names = ["background"] + [f"c{i}" for i in range(1, n_classes)]
+    aps, m, tp, fp = b200.calculate_mAP(*t, names)
+    return (np.array(list(aps.values()), np.float32), m, np.array(list(tp.values()), np.float32),
+            np.array(list(fp.values()), np.float32))
+
+
+def test_map_vs_reference_golden(cuda_device):
+    d = load_golden("map_n40_c6")
+    L = [unpack_ragged(d, k) for k in MAP_KEYS]
+    ap, m, tp, fp = gpu_map(L, int(d["n_classes"]), cuda_device)
+    assert np.array_equal(tp, d["tp"]) and np.array_equal(fp, d["fp"])       # every TP / FP decision bit-exact
+    np.testing.assert_allclose(ap, d["ap"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m, float(d["mAP"]), rtol=1e-6)
+
+
+@pytest.mark.parametrize("N,C,maxdet,seed", [(300, 21, 60, 1), (7, 3, 5000, 2), (64, 81, 200, 3)])
+def test_map_vs_oracle_random(N, C, maxdet, seed, cuda_device):
+    """larger cases: many images (multi-chunk scans), one class with > 4096 detections (global-memory sort),
+    more classes than threads per matching CTA allows in one pass"""
+    r = np.random.RandomState(seed)
+    L = [[] for _ in MAP_KEYS]
+    for b in range(N):
+        ng, nd = r.randint(0, 12), r.randint(0, maxdet + 1)
+        g = np.sort(r.rand(ng, 2, 2), axis=1).reshape(ng, 4).astype(np.float32)
+        gl = r.randint(1, C, ng)
+        db = np.sort(r.rand(nd, 2, 2), axis=1).reshape(nd, 4).astype(np.float32)
+        dl = r.randint(1, C, nd)
+        if ng:
+            pick = r.randint(0, ng, nd)
+            near = r.rand(nd) < 0.5
+            db[near] = g[pick[near]] + r.randn(int(near.sum()), 4).astype(np.float32) * 0.02
+            dl[near] = gl[pick[near]]
+        for lst, v in zip(L, (db, dl.astype(np.int64), r.rand(nd).astype(np.float32), g, gl.astype(np.int64),
+                              (r.rand(ng) < 0.15).astype(np.uint8))):
+            lst.append(v)
+    ap, m, tp, fp = gpu_map(L, C, cuda_device)
+    o_ap, o_m, o_tp, o_fp = oracle.calculate_map(*L, C)
+    assert np.array_equal(tp, o_tp) and np.array_equal(fp, o_fp)
+    np.testing.assert_allclose(ap, o_ap, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m, o_m, rtol=1e-6)
+
+
+def test_map_on_nms_output(cuda_device):
+    """train.py:test() wiring: det_boxes = preds[:, :4], det_labels = preds[:, 6] + 1, det_scores = preds[:, 4] *
+    preds[:, 5] (:385-388) from the fused decode + NMS output."""
+    C = 20
+    h0, h1 = make_heads(6, C, [(11, 11), (22, 22)], seed=31, conf_shift=-2.6)
+    dets = [x.cpu().numpy() for x in ops_decode_list(h0, h1, C, cuda_device)]
+    gts = synth_targets(6, 8, C, seed=5)
+    L = [[d[:, :4] for d in dets], [d[:, 6].astype(np.int64) + 1 for d in dets], [d[:, 4] * d[:, 5] for d in dets],
+         [np.stack([g[:, 1] - g[:, 3] / 2, g[:, 2] - g[:, 4] / 2, g[:, 1] + g[:, 3] / 2, g[:, 2] + g[:, 4] / 2], 1).astype(np.float32) for g in gts],
+         [g[:, 0].astype(np.int64) for g in gts], [np.zeros(len(g), np.uint8) for g in gts]]
+    ap, m, tp, fp = gpu_map(L, C + 1, cuda_device)
+    o_ap, o_m, o_tp, o_fp = oracle.calculate_map(*L, C + 1)
+    assert np.array_equal(tp, o_tp) and np.array_equal(fp, o_fp)
+    np.testing.assert_allclose(ap, o_ap, rtol=1e-6, atol=1e-7)
+
+
+def ops_decode_list(h0, h1, C, dev):
+    out, cnt = ops.decode_nms_padded(h0.to(dev), h1.to(dev), anchor_tables(VOC_ANCHORS, [352, 352]), C, 0.3)
+    return [out[b, :k] for b, k in enumerate(cnt.cpu().tolist())]

@@ -119,3 +119,17 @@ def test_target_loss_backward_matches_reference_autograd(case):
         A, attrs = len(d["mask"][i]), 5 + int(d["num_classes"])
         box = ref.reshape(ref.shape[0], A, attrs, *ref.shape[2:])[:, :, :4]
         assert (box != 0).any()
+
+
+MAP_KEYS = ("det_boxes", "det_labels", "det_scores", "true_boxes", "true_labels", "true_difficulties")
+
+
+def test_map_matches_reference_calculate_mAP():
+    """oracle.calculate_map vs utils/eval_mAP.py::calculate_mAP run by make_golden.py (difficult objects, empty
+    images, a class without ground truth)."""
+    d = load_golden("map_n40_c6")
+    L = [unpack_ragged(d, k) for k in MAP_KEYS]
+    ap, m, tp, fp = oracle.calculate_map(*L, int(d["n_classes"]))
+    np.testing.assert_allclose(ap, d["ap"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m, float(d["mAP"]), rtol=1e-6)
+    assert np.array_equal(tp, d["tp"]) and np.array_equal(fp, d["fp"])
