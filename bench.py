@@ -418,6 +418,18 @@ def run_b200(args, wl):
                                      "kept_rows_per_image": float(np.mean(skept)) / N,
                                      "algorithmic_gbs": sbytes / (sms * 1e-3) / 1e9}
             del ssets
+        # the same loop without programmatic dependent launch (debug flag 2): every launch waits for the previous
+        # one to drain -- the serialized per-launch time, comparable with ncu's gpu__time_duration
+        _lib.load().b200yolo_debug_set_flags(2)
+        try:
+            for i in range(5):
+                step(i)
+            barrier()
+            ser_ms = time_loop(step, args.steps) / args.steps
+        finally:
+            _lib.load().b200yolo_debug_set_flags(0)
+        extra["serialized_launches"] = {"ms_per_step": ser_ms, "images_per_s_per_gpu": N / (ser_ms * 1e-3),
+                                        "note": "plain stream order (no programmatic dependent launch)"}
         # the same steps issued round-robin on two streams (separate output buffers): consecutive launches
         # overlap, so one launch's decode (memory phase) runs under the other's NMS (issue-bound phase)
         s2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
@@ -491,6 +503,9 @@ def run_b200(args, wl):
             "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": N, "global_batch": world * N,
                        "cells_per_image": K, "kept_rows_per_image": kept_per_launch / N,
                        "l2": f"{R} rotating input sets ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2, so every step reads its heads from HBM",
+                       "launch": "one kernel per step on one stream; consecutive launches overlap through programmatic dependent "
+                                 "launch (a launch starts on free SM slots while the previous one finishes, and waits for it before "
+                                 "writing); extra.serialized_launches is the same loop in plain stream order",
                        "parallelism": f"dp{world} by image, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "decode_nms_kernel<MODE_FUSED>",

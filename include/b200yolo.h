@@ -59,7 +59,8 @@ unsigned long long b200yolo_launch_count(void);
 void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
 
 /* Experiment / test switches of the fused kernel (initialised from the B200YOLO_FLAGS
- * environment variable): 1 = no L2 prefetch of head 0, 8 = prefetch both heads, 16 = never
+ * environment variable): 1 = no L2 prefetch of head 0, 2 = no programmatic dependent launch (consecutive
+ * launches then run in plain stream order), 8 = prefetch both heads, 16 = never
  * use the compile-time head shapes (every shape then runs the runtime-stride decode). */
 void b200yolo_debug_set_flags(int flags);
 

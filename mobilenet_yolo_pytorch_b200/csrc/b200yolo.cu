@@ -107,7 +107,19 @@ int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
             configured[dev] = smem_optin(dev);
         }
     }
-    decode_nms_kernel<MODE, THREADS, SHAPE><<<p.N, THREADS, L.total, st>>>(p, L);
+    // programmatic dependent launch: consecutive launches of this kernel overlap (decode_nms.cuh, pdl_trigger / pdl_wait)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)p.N);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (p.flags & 2) ? 0 : 1;  // flag 2: plain stream order
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, decode_nms_kernel<MODE, THREADS, SHAPE>, p, L));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

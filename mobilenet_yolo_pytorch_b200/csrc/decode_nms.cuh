@@ -222,6 +222,16 @@ __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
     }
 }
 
+// Programmatic dependent launch (the host sets cudaLaunchAttributeProgrammaticStreamSerialization): the NEXT
+// kernel in the stream may start once every CTA of this one has executed pdl_trigger(); it must execute
+// pdl_wait() -- which returns when this grid has completed and its writes are visible -- before it touches
+// anything this kernel writes.  Only a kernel that triggers can be overtaken, so an ordinary producer of the
+// head tensors (a convolution) still completes before any of our CTAs starts; between two of our own launches
+// the only shared data are the output buffers, which every mode writes after pdl_wait().  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // shared-memory loads by shared-window address (the pair loop: no address arithmetic)
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
     float4 v;
@@ -884,6 +894,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     const int C = p.C, K = p.K;
     using SH = ShapeT<SHAPE>;
 
+    pdl_trigger();  // the next launch may start filling free SM slots right away (it waits before it writes)
+    if (MODE == MODE_NMS || p.dbg) pdl_wait();  // (inputs written by our own decode kernels; debug stamps are global stores)
     stamp(p, b, 0);
     if (MODE != MODE_NMS) {
         // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
@@ -940,6 +952,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         }
         __syncthreads();
         const int T = s.misc[M_TOTAL];
+        pdl_wait();
         float *o = p.out + (size_t)b * K * 7;
         const float *boxf = reinterpret_cast<const float *>(s.box);
         const float *csf = reinterpret_cast<const float *>(s.cs);
@@ -986,6 +999,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     }
     stamp(p, b, 4);
     // P6 (the mask buffer is dead now; the row scratch aliases it)
+    pdl_wait();
     phase_output<MODE, THREADS>(p, s, b);
     stamp(p, b, 7);
 }

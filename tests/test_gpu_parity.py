@@ -540,3 +540,59 @@ def test_map_on_nms_output(cuda_device):
 def ops_decode_list(h0, h1, C, dev):
     out, cnt = ops.decode_nms_padded(h0.to(dev), h1.to(dev), anchor_tables(VOC_ANCHORS, [352, 352]), C, 0.3)
     return [out[b, :k] for b, k in enumerate(cnt.cpu().tolist())]
+
+
+# ----------------------------------------------------------------------------- programmatic dependent launch
+def test_back_to_back_launches_overlap_safely(cuda_device):
+    """Consecutive launches overlap (programmatic dependent launch): a launch may start while the previous one
+    is still running, but waits for it before writing.  Same output buffers reused by alternating inputs, no
+    host sync in between; every intermediate result must equal the plain-stream-order result (debug flag 2)."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    C = 20
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    sets = [tuple(h.to(cuda_device) for h in make_heads(64, C, [(11, 11), (22, 22)], seed=40 + k, conf_shift=-1.0 * k))
+            for k in range(3)]
+    K = 3 * (121 + 484)
+    lib = _lib.load()
+    expected = []
+    try:
+        lib.b200yolo_debug_set_flags(2)
+        for h0, h1 in sets:
+            o, c = ops.decode_nms_padded(h0, h1, tables, C, 0.3)
+            expected.append((o.clone(), c.clone()))
+    finally:
+        lib.b200yolo_debug_set_flags(0)
+    out = torch.empty((64, K, 7), dtype=torch.float32, device=cuda_device)
+    cnt = torch.empty((64,), dtype=torch.int32, device=cuda_device)
+    snaps = []
+    for i in range(30):
+        h0, h1 = sets[i % 3]
+        ops.decode_nms_padded(h0, h1, tables, C, 0.3, out=out, out_count=cnt)
+        if i % 4 == 3:                       # an ordinary kernel in between: must see the finished result
+            snaps.append((i % 3, out.clone(), cnt.clone()))
+    torch.cuda.synchronize()
+    snaps.append((29 % 3, out, cnt))
+    for k, o, c in snaps:
+        eo, ec = expected[k]
+        assert torch.equal(c, ec)
+        for b in range(64):
+            n = int(ec[b])
+            assert torch.equal(o[b, :n], eo[b, :n])
+
+
+def test_decode_then_nms_chain_without_sync(cuda_device):
+    """YOLOLoss.forward x2 -> utils.box.nms launched back to back: the NMS kernel reads rows the decode kernels
+    write, so it must wait for them even though it may start early."""
+    C = 20
+    h0, h1 = make_heads(48, C, [(11, 11), (22, 22)], seed=77)
+    d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    ref_out, ref_cnt = ops.decode_nms_padded(d0, d1, tables, C, 0.3)
+    for _ in range(10):
+        r0, c0 = ops.decode_head_padded(d0, tables[0], C, 0.3)
+        r1, c1 = ops.decode_head_padded(d1, tables[1], C, 0.3)
+        out, cnt = ops.nms_padded(r0, c0, r1, c1, C)
+        assert torch.equal(cnt, ref_cnt)
+        for b in (0, 17, 47):
+            n = int(ref_cnt[b])
+            assert torch.equal(out[b, :n], ref_out[b, :n])
