@@ -332,15 +332,27 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
     }
     p.S = S;
     p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
-    CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
+    // both kernels use programmatic dependent launch: the next call's target_loss_kernel overlaps this call's tail
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_flags.load() & 2) ? 0 : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (N > 0) {
-        target_loss_kernel<<<N * S, kTLThreads, smem, st>>>(p);
+        cfg.gridDim = dim3((unsigned)(N * S));
+        cfg.blockDim = dim3(kTLThreads);
+        cfg.dynamicSmemBytes = smem;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, target_loss_kernel, p));
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        CUDA_TRY(cudaGetLastError());
     }
-    target_loss_reduce_kernel<<<1, kTLSums * 32, 0, st>>>(p.partial, N * S, sums);
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(kTLSums * 32);
+    cfg.dynamicSmemBytes = 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, target_loss_reduce_kernel, (const double *)p.partial, N * S, sums, status));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

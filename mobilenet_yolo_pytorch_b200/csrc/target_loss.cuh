@@ -44,6 +44,7 @@ constexpr int kTLMaxAnchors = 8;
 constexpr int kTLSums = 16;
 constexpr int kTLMaxSplit = 8;         // CTAs per image
 constexpr float kTLEps = 1e-5f;
+constexpr int kTLStatusSlot = 12;      // slot of the per-CTA partial sums that carries the status (max-reduced)
 
 struct TLParams {
     const float *head;
@@ -172,7 +173,8 @@ __device__ __noinline__ bool tl_below_exact(const float4 *gbox, const float *gar
 }
 
 // P1: per-GT anchor matching (yolo_loss.py:112-113, 127-145): stages the image's GT boxes, appends the assigned
-// (GT, k) pairs to s_list and flags their cells.  `lead` CTAs also write the per-GT outputs and the status.
+// (GT, k) pairs to s_list and flags their cells.  `lead` CTAs also write the per-GT outputs and the status
+// (s_misc[2]; it travels to the host through slot 12 of the CTA's partial sums).
 __device__ __forceinline__ void tl_match_gt(const TLParams &p, int b, int g0, int nG, bool lead, float4 *s_gbox, float *s_garea,
                                             float *s_gta, int *s_gcls, TLAssign *s_list, uint8_t *s_flag, int *s_misc) {
     const int tid = threadIdx.x;
@@ -196,7 +198,7 @@ __device__ __forceinline__ void tl_match_gt(const TLParams &p, int b, int g0, in
         s_gcls[t] = cls;
         const int gi = (int)__fmul_rn(gx, p.fW), gj = (int)__fmul_rn(gy, p.fH);  // :128,136-137
         const bool ok = gi >= 0 && gi < W && gj >= 0 && gj < H && cls >= 0 && cls < C;
-        if (!ok && lead) atomicMax(p.status, 1);
+        if (!ok && lead) atomicMax(&s_misc[2], 1);
         // anchor-vs-GT IoU on (0,0,w,h) shapes, ALL anchors (:129-133)
         const float4 gb = make_float4(0.f, 0.f, gw, gh);
         const float ga = box_area(gb);
@@ -250,13 +252,18 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
     int nG = p.gt_off[b + 1] - g0;
     const int HW = p.HW, W = p.W, H = p.H, A = p.A, C = p.C;
 
-    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }  // assignment list length; any degenerate GT box
+    // Programmatic dependent launch (see decode_nms.cuh): the next kernel of the stream may start now; this one
+    // waits for its predecessor before its first global store (the workspace of partial sums is shared by
+    // consecutive calls; the optional per-GT / per-cell outputs are written early, so they wait here).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.assign || p.terms || p.cell_state) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; }  // assignment list length; any degenerate GT box; status
     for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
-    if (nG > p.gcap) {
-        if (tid == 0 && lead) atomicMax(p.status, 2);  // more GT boxes in one image than the staging holds
-        nG = 0;                                        // (the shim raises; keep the kernel well defined)
-    }
     __syncthreads();
+    if (nG > p.gcap) {
+        if (tid == 0 && lead) s_misc[2] = 2;  // more GT boxes in one image than the staging holds
+        nG = 0;                               // (the shim raises; keep the kernel well defined)
+    }
 
     double acc[10];
 #pragma unroll
@@ -416,6 +423,8 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
             for (int w = 0; w < kTLWarps; ++w) v += s_red[tid * kTLWarps + w];
         else if (tid == B200YOLO_S_NCELLS && lead) v = (double)p.cells;
         else if (tid == B200YOLO_S_NIMG && lead) v = 1.0;
+        else if (tid == kTLStatusSlot) v = (double)s_misc[2];
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         p.partial[((size_t)b * p.S + split) * kTLSums + tid] = v;
     }
 }
@@ -608,10 +617,20 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_backward_kernel(const 
     }
 }
 
-// fixed-order sum over the per-CTA partials -> sums[16] (bitwise reproducible run to run)
-__global__ void __launch_bounds__(kTLSums * 32) target_loss_reduce_kernel(const double *partial, int rows, double *sums) {
+// fixed-order sum over the per-CTA partials -> sums[16] (bitwise reproducible run to run); slot 12 carries the
+// status and is max-reduced into status[0]
+__global__ void __launch_bounds__(kTLSums * 32) target_loss_reduce_kernel(const double *partial, int rows, double *sums, int *status) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the partial sums of the kernel before
     const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v = 0.0;
+    if (q == kTLStatusSlot) {
+        for (int b = lane; b < rows; b += 32) v = fmax(v, partial[(size_t)b * kTLSums + q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFullMask, v, o));
+        if (lane == 0) { status[0] = (int)v; sums[q] = 0.0; }
+        return;
+    }
     for (int b = lane; b < rows; b += 32) v += partial[(size_t)b * kTLSums + q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
