@@ -515,7 +515,7 @@ def run_b200(args, wl):
                                        "(oracle/yolo_oracle.c, OpenMP, all host threads)"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(in_bytes),
                     "d2h_bytes_per_step": int(N * K * 28 + 4 * N), "steps": e2e_steps,
-                    "api": "b200yolo_decode_nms_host (pinned host heads -> host detections, chunked 3-stream pipeline)",
+                    "api": "b200yolo_decode_nms_host (pinned host heads -> host detections, 4 chunks on 3 streams: H2D, kernel and D2H overlap)",
                     "timer": "host wall clock around the synchronous calls, max over ranks"},
             "gpu_launches": int(launches) * world,
             "clocks": clocks,

@@ -57,9 +57,13 @@ extern "C" int b200yolo_decode_nms_host(const float *head0, const float *head1, 
     const size_t attrs = 5 + (size_t)C;
     const size_t per0 = (size_t)A * attrs * H0 * W0, per1 = (size_t)A * attrs * H1 * W1;  // floats per image
     const size_t K = (size_t)A * H0 * W0 + (size_t)A * H1 * W1;
-    // chunk so that ~8 chunks cover the batch, at least 8 images each
-    int chunk = (N + 7) / 8;
+    // chunk so that ~4 chunks cover the batch, at least 8 images each
+    int chunk = (N + 3) / 4;  // 4 chunks: measured best for the 256-image batch (profiles/e2e_sweep.py)
     if (chunk < 8) chunk = 8;
+    {
+        static const int env_chunk = [] { const char *e = getenv("B200YOLO_HOST_CHUNK"); return e ? atoi(e) : 0; }();
+        if (env_chunk > 0) chunk = env_chunk;  // tuning knob: images per pipeline chunk
+    }
     if (chunk > N) chunk = N;
     std::lock_guard<std::mutex> lock(g_host_mu);
     HostCtx &cx = g_host_ctx[device];
