@@ -119,7 +119,8 @@ int b200yolo_decode_nms_host(const float *head0, const float *head1, int N, int 
 /*
  * utils.iou.find_intersection / find_union / find_jaccard_overlap
  * (utils/iou.py:4-13, 14-31, 32-49).  mode 0 / 1 / 2.  set1 dev [n1][4],
- * set2 dev [n2][4] xyxy; out dev [n1][n2].
+ * set2 dev [n2][4] xyxy; out dev [n1][n2].  mode 3 / 4: YOLOLoss.box_giou / box_ciou value
+ * iou - term with box1 = set1 row, box2 = set2 row (models/yolo_loss.py:295-317 / 257-293).
  */
 int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int mode, float *out, void *stream);
 

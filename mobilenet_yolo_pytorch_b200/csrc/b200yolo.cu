@@ -12,8 +12,8 @@
 #include <mutex>
 
 #include "decode_nms.cuh"  // (after the helpers it uses)
-#include "pairwise.cuh"
 #include "target_loss.cuh"
+#include "pairwise.cuh"
 #include "map_eval.cuh"
 
 using namespace b200yolo;
@@ -44,8 +44,14 @@ int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 int smem_optin(int device) {
+    static std::atomic<int> cache[64];  // (zero-initialised; the attribute never changes)
+    if (device >= 0 && device < 64) {
+        const int c = cache[device].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+    if (device >= 0 && device < 64) cache[device].store(v, std::memory_order_relaxed);
     return v;
 }
 
@@ -251,7 +257,7 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
 }
 
 int b200yolo_pairwise(const float *set1, int n1, const float *set2, int n2, int mode, float *out, void *stream) {
-    if (n1 < 0 || n2 < 0 || mode < 0 || mode > 2) return fail(B200YOLO_EINVAL, "pairwise: bad argument");
+    if (n1 < 0 || n2 < 0 || mode < 0 || mode > 4) return fail(B200YOLO_EINVAL, "pairwise: bad argument");
     if (n1 == 0 || n2 == 0) return 0;
     if (!set1 || !set2 || !out) return fail(B200YOLO_EINVAL, "pairwise: null pointer");
     if (((uintptr_t)set1 | (uintptr_t)set2) & 15) return fail(B200YOLO_EINVAL, "pairwise: boxes must be 16-byte aligned");

@@ -34,15 +34,6 @@ __device__ __forceinline__ float rcp_fast(float x) {
 __device__ __forceinline__ float exp_fast(float x) { return ex2_fast(__fmul_rn(x, 1.4426950408889634f)); }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(__fadd_rn(1.0f, ex2_fast(__fmul_rn(x, -1.4426950408889634f)))); }
 
-__device__ __forceinline__ float ldg_f(const float *p) { return __ldg(p); }
-
-// streaming load: head tensors are read exactly once
-__device__ __forceinline__ float ld_stream_f(const float *p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

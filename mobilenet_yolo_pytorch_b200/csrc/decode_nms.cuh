@@ -63,7 +63,6 @@ template <int SHAPE> struct ShapeT { static constexpr int C = 0, HW0 = 0, W0 = 0
 template <> struct ShapeT<1> { static constexpr int C = 20, HW0 = 121, W0 = 11, HW1 = 484, W1 = 22; };  // VOC 352x352 (models/voc/config.yaml)
 template <> struct ShapeT<2> { static constexpr int C = 20, HW0 = 169, W0 = 13, HW1 = 676, W1 = 26; };  // 416x416 (inference.py:112)
 template <> struct ShapeT<3> { static constexpr int C = 10, HW0 = 240, W0 = 20, HW1 = 960, W1 = 40; };  // BDD100k 640x384, 10 classes
-constexpr int kNumShapes = 4;
 
 struct HeadDesc {
     const float *ptr;

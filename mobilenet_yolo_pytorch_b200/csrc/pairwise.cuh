@@ -1,9 +1,11 @@
 // pairwise.cuh -- utils/iou.py: find_intersection / find_union /
-// find_jaccard_overlap as one (n1, n2) kernel.  set_2 is staged in shared memory
+// find_jaccard_overlap as one (n1, n2) kernel; modes 3 / 4 evaluate YOLOLoss.box_giou / box_ciou
+// (models/yolo_loss.py:295-317 / 257-293; value = iou - term, box1 = row, box2 = column).  set_2 is staged in shared memory
 // in tiles; each thread owns one set_1 row and streams a coalesced output row
 // segment (consecutive threads -> consecutive columns).
 #pragma once
 #include "common.cuh"
+#include "target_loss.cuh"
 
 namespace b200yolo {
 
@@ -32,9 +34,12 @@ __global__ void __launch_bounds__(kPairTile) pairwise_kernel(const float4 *__res
     for (int r = 0; r < nr; ++r) {
         const float inter = pair_inter(rows[r], b);  // iou.py:4-13
         float v = inter;
-        if (mode >= 1) {
+        if (mode == 1 || mode == 2) {
             const float u = pair_union(rarea[r], barea, inter);  // iou.py:44
             v = (mode == 1) ? u : __fdiv_rn(inter, u);           // iou.py:49
+        } else if (mode >= 3) {
+            float iou;
+            v = (mode == 3) ? tl_box_giou(rows[r], b, &iou) : tl_box_ciou(rows[r], b, &iou);
         }
         out[(size_t)(r0 + r) * n2 + col] = v;
     }

@@ -100,6 +100,21 @@ def nms_padded(cand0: torch.Tensor, count0: torch.Tensor, cand1: Optional[torch.
     return (out, oc, oi) if want_idx else (out, oc)
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs ~3 us)."""
+
+    def __init__(self, dev: torch.device):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
                       iou_thr: float = NMS_IOU_THRESHOLD, want_idx: bool = False,
                       out: Optional[torch.Tensor] = None, out_count: Optional[torch.Tensor] = None,
@@ -108,7 +123,10 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
     Pre-allocated outputs may be passed (CUDA-graph capture, NCCL send buffers)."""
     _require_cuda(head0, "head0")
     _require_cuda(head1, "head1")
-    head0, head1 = head0.contiguous(), head1.contiguous()
+    if not head0.is_contiguous():
+        head0 = head0.contiguous()
+    if not head1.is_contiguous():
+        head1 = head1.contiguous()
     N, ch, H0, W0 = head0.shape
     N1, ch1, H1, W1 = head1.shape
     attrs = 5 + num_classes
@@ -116,18 +134,22 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
         raise RuntimeError("head shapes do not match (N, A*(5+C), H, W) for both heads")
     A = ch // attrs
     K = A * H0 * W0 + A * H1 * W1
-    aw = _host_f32(anchor_wh2).reshape(2, A, 2)
-    with torch.cuda.device(head0.device):
+    aw = anchor_wh2 if (isinstance(anchor_wh2, np.ndarray) and anchor_wh2.dtype == np.float32
+                        and anchor_wh2.flags.c_contiguous and anchor_wh2.size == 4 * A) else _host_f32(anchor_wh2).reshape(2, A, 2)
+    dev = head0.device
+    with _on_device(dev):
         if out is None:
-            out = torch.empty((N, K, 7), dtype=torch.float32, device=head0.device)
+            out = torch.empty((N, K, 7), dtype=torch.float32, device=dev)
         if out_count is None:
-            out_count = torch.empty((N,), dtype=torch.int32, device=head0.device)
+            out_count = torch.empty((N,), dtype=torch.int32, device=dev)
         if want_idx and out_idx is None:
-            out_idx = torch.empty((N, K), dtype=torch.int32, device=head0.device)
-        _lib.check(_lib.load().b200yolo_decode_nms(
+            out_idx = torch.empty((N, K), dtype=torch.int32, device=dev)
+        rc = _lib.load().b200yolo_decode_nms(
             head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
             float(np.float32(conf_thr)), float(iou_thr), out.data_ptr(), out_count.data_ptr(),
-            out_idx.data_ptr() if want_idx else None, _stream(head0)))
+            out_idx.data_ptr() if want_idx else None, torch.cuda.current_stream(dev).cuda_stream)
+        if rc:
+            _lib.check(rc)
     return (out, out_count, out_idx) if want_idx else (out, out_count)
 
 

@@ -56,6 +56,14 @@ class YOLOLoss(nn.Module):
     def head_anchor_wh(self):
         return self.scaled_anchors()[list(self.mask)]
 
+    def box_ciou(self, box1: torch.Tensor, box2: torch.Tensor):
+        """yolo_loss.py:257-293: (iou - ciou_term, iou), each (n1, n2) (the reference calls it with one box each)."""
+        return ops.pairwise(box1, box2, 4), ops.pairwise(box1, box2, 2)
+
+    def box_giou(self, box1: torch.Tensor, box2: torch.Tensor):
+        """yolo_loss.py:295-317 (dead code upstream, kept for completeness): (iou - giou_term, iou)."""
+        return ops.pairwise(box1, box2, 3), ops.pairwise(box1, box2, 2)
+
     def get_pred_boxes(self, input: torch.Tensor) -> ops.CandidateList:
         rows, count, ids = ops.decode_head_padded(input, self.head_anchor_wh(), self.num_classes, self.val_conf,
                                                   want_ids=True)

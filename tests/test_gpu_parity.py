@@ -596,3 +596,17 @@ def test_decode_then_nms_chain_without_sync(cuda_device):
         for b in (0, 17, 47):
             n = int(ref_cnt[b])
             assert torch.equal(out[b, :n], ref_out[b, :n])
+
+
+def test_box_ciou_giou_vs_reference_golden(cuda_device):
+    """YOLOLoss.box_ciou / box_giou (yolo_loss.py:257-317) on the matched pairs of tests/golden/iou.npz."""
+    d = load_golden("iou")
+    n = d["ciou"].shape[0]
+    a = torch.from_numpy(d["a"][:n]).to(cuda_device)
+    b = torch.from_numpy(d["b"][:n]).to(cuda_device)
+    l = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.5)
+    cv, ci = l.box_ciou(a, b)
+    gv, gi = l.box_giou(a, b)
+    for got, want in ((cv, d["ciou"][:, 0]), (ci, d["ciou"][:, 1]), (gv, d["giou"][:, 0]), (gi, d["giou"][:, 1])):
+        g = torch.diagonal(got).cpu().numpy()
+        np.testing.assert_allclose(g, want, rtol=RTOL, atol=ATOL, equal_nan=True)
