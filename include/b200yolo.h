@@ -193,6 +193,25 @@ int b200yolo_map_eval(const float *det_boxes, const int *det_labels, const float
                       int n_thresholds, float *ap, float *tp_sum, float *fp_sum, void *workspace, size_t workspace_bytes,
                       void *stream);
 
+/*
+ * models.seg_loss.SegLoss  (models/seg_loss.py:14-81; called at models/mbv2_yolo.py:163,170): the
+ * drivable-area head of the BDD100k multi-task model.
+ *   b200yolo_seg_loss           forward(input, targets) (:51-76): input dev (N, C, H, W), truth dev (N, H, W, C)
+ *                               (the reference permutes it, :54).  sums dev double[8], overwritten:
+ *                               [0] sum (sigmoid(x) - t)^2, [1] numel, [2] sum sigmoid(x) where t >= 0.5,
+ *                               [3] count(t >= 0.5), [4] sum sigmoid(x) where t < 0.5, [5] count(t < 0.5);
+ *                               loss = 0.05 * [0]/[1], obj = [2]/[3], no_obj = [4]/[5]  (:40-45, 65-66, 76)
+ *   b200yolo_seg_loss_backward  d (0.05 * mse) / d input with the pass-through sigmoid (:15-31):
+ *                               grad_out[0] * 0.05 * 2 (sigmoid(x) - t) / numel; grad_out dev float[1] or NULL = 1
+ *   b200yolo_seg_sigmoid        forward(input) (:77-80): out[i] = 1/(1+exp(-input[i])), i < count
+ */
+size_t b200yolo_seg_loss_workspace_bytes(void);
+int b200yolo_seg_loss(const float *input, const float *truth, int N, int C, int H, int W, double *sums, void *workspace,
+                      size_t workspace_bytes, void *stream);
+int b200yolo_seg_loss_backward(const float *input, const float *truth, int N, int C, int H, int W, const float *grad_out,
+                               float *grad_input, void *stream);
+int b200yolo_seg_sigmoid(const float *input, long long count, float *out, void *stream);
+
 /* indices into the partial-sum vector of b200yolo_target_loss */
 enum {
     B200YOLO_S_SQW = 0,      /* sum (o-t)^2 w           (yolo_loss.py:54-58) */

@@ -6,6 +6,7 @@ eric612/Mobilenet-YOLO-Pytorch behind the reference's own entry points:
     find_intersection/union/jaccard_overlap  <- utils/iou.py
     decode_nms                    <- the inference branch of models/mbv2_yolo.py:158-160, fused
     calculate_mAP                 <- utils/eval_mAP.py
+    SegLoss                       <- models/seg_loss.py
 
 All computation happens in libb200yolo.so (hand-written CUDA, C ABI in
 include/b200yolo.h); PyTorch only provides device memory, streams and
@@ -16,7 +17,8 @@ from .box import nms, wh_to_x2y2
 from .eval_mAP import calculate_mAP
 from .fused import decode_nms, decode_nms_padded, head_anchor_table, patch_reference
 from .iou import find_intersection, find_jaccard_overlap, find_union
+from .seg_loss import SegLoss
 from .yolo_loss import YOLOLoss
 
 __all__ = ["YOLOLoss", "nms", "wh_to_x2y2", "find_intersection", "find_union", "find_jaccard_overlap", "decode_nms",
-           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops", "dist", "calculate_mAP"]
+           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops", "dist", "calculate_mAP", "SegLoss"]

@@ -43,6 +43,11 @@ SIGNATURES = {
                                                 c_f32p, c_i32p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_float, c_f32p, c_f32p, C.c_void_p]),
     "b200yolo_loss_finalize": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "b200yolo_seg_loss_workspace_bytes": (C.c_size_t, []),
+    "b200yolo_seg_loss": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
+    "b200yolo_seg_loss_backward": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
+    "b200yolo_seg_sigmoid": (C.c_int, [c_f32p, C.c_longlong, c_f32p, C.c_void_p]),
     "b200yolo_map_eval_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200yolo_map_eval": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int, c_f32p, c_i32p, C.c_void_p, c_i32p, C.c_int,
                                     C.c_int, C.c_int, C.c_float, c_f32p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_void_p,

@@ -15,6 +15,7 @@
 #include "target_loss.cuh"
 #include "pairwise.cuh"
 #include "map_eval.cuh"
+#include "seg_loss.cuh"
 
 using namespace b200yolo;
 
@@ -425,6 +426,72 @@ int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H,
     p.S = S;
     p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
     target_loss_backward_kernel<<<N * S, kTLThreads, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int seg_grid(long long total, int dev) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    long long g = (total + kSegThreads - 1) / kSegThreads;
+    const long long cap = (long long)nsm * 8;   // 8 CTAs of 256 threads per SM, grid-stride above that
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+size_t b200yolo_seg_loss_workspace_bytes(void) { return (size_t)148 * 8 * 4 * kSegSums * sizeof(double); }
+
+int b200yolo_seg_loss(const float *input, const float *truth, int N, int C, int H, int W, double *sums, void *workspace,
+                      size_t workspace_bytes, void *stream) {
+    if (!input || !truth || !sums || !workspace) return fail(B200YOLO_EINVAL, "seg_loss: null pointer");
+    if (N < 1 || C < 1 || H < 1 || W < 1) return fail(B200YOLO_EINVAL, "seg_loss: bad shape");
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    SegParams p;
+    memset(&p, 0, sizeof(p));
+    p.input = input; p.truth = truth; p.C = C; p.HW = H * W;
+    p.total = (long long)N * C * H * W;
+    p.partial = (double *)workspace; p.sums = sums;
+    const int grid = seg_grid(p.total, dev);
+    if (workspace_bytes < (size_t)grid * kSegSums * sizeof(double)) return fail(B200YOLO_EINVAL, "seg_loss: workspace too small");
+    seg_loss_kernel<<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    seg_loss_reduce_kernel<<<1, kSegSums * 32, 0, (cudaStream_t)stream>>>(p.partial, grid, sums);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200yolo_seg_loss_backward(const float *input, const float *truth, int N, int C, int H, int W, const float *grad_out,
+                               float *grad_input, void *stream) {
+    if (!input || !truth || !grad_input) return fail(B200YOLO_EINVAL, "seg_loss_backward: null pointer");
+    if (N < 1 || C < 1 || H < 1 || W < 1) return fail(B200YOLO_EINVAL, "seg_loss_backward: bad shape");
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    SegParams p;
+    memset(&p, 0, sizeof(p));
+    p.input = input; p.truth = truth; p.C = C; p.HW = H * W;
+    p.total = (long long)N * C * H * W;
+    p.grad_out = grad_out; p.grad_input = grad_input;
+    seg_loss_backward_kernel<<<seg_grid(p.total, dev), kSegThreads, 0, (cudaStream_t)stream>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200yolo_seg_sigmoid(const float *input, long long count, float *out, void *stream) {
+    if (count < 0) return fail(B200YOLO_EINVAL, "seg_sigmoid: bad count");
+    if (count == 0) return 0;
+    if (!input || !out) return fail(B200YOLO_EINVAL, "seg_sigmoid: null pointer");
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    SegParams p;
+    memset(&p, 0, sizeof(p));
+    p.input = input; p.out = out; p.total = count;
+    seg_sigmoid_kernel<<<seg_grid(count, dev), kSegThreads, 0, (cudaStream_t)stream>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -406,3 +406,34 @@ def calculate_map(det_boxes, det_labels, det_scores, true_boxes, true_labels, tr
         tps[c - 1] = tp_s.sum()
         fps[c - 1] = fp_s.sum()
     return aps, float(aps.mean(dtype=np.float32)), tps, fps
+
+
+# ----------------------------------------------------------------------------- seg head (models/seg_loss.py), SURVEY 8 f4
+def seg_loss(inp, targets):
+    """SegLoss.forward(input, targets) (models/seg_loss.py:51-76): input (N,C,H,W), targets (N,H,W,C).
+    Returns (loss, obj_mean, no_obj_mean); fp32 elementwise maths, float64 sums."""
+    x = _f32(inp)
+    t = np.transpose(_f32(targets), (0, 3, 1, 2))                      # :54
+    o = (np.float32(1.0) / (np.float32(1.0) + np.exp(-x, dtype=np.float32))).astype(np.float32)   # :19
+    d = (o - t).astype(np.float32)
+    sq = (d * d).astype(np.float32)
+    loss = 0.05 * float(sq.sum(dtype=np.float64)) / x.size           # :40-45 with all-ones weights (:73), :76
+    with np.errstate(divide="ignore", invalid="ignore"):
+        obj = float(o[t >= 0.5].sum(dtype=np.float64) / np.float64((t >= 0.5).sum()))   # :65, torch.mean of empty = nan
+        no_obj = float(o[t < 0.5].sum(dtype=np.float64) / np.float64((t < 0.5).sum()))  # :66
+    return loss, obj, no_obj
+
+
+def seg_loss_backward(inp, targets, grad_out: float = 1.0):
+    """d loss / d input of SegLoss.forward(input, targets): the custom sigmoid passes gradients through (:23-31),
+    so it is grad_out * 0.05 * 2 (o - t) / numel."""
+    x = _f32(inp).astype(np.float64)
+    t = np.transpose(_f32(targets), (0, 3, 1, 2)).astype(np.float64)
+    o = 1.0 / (1.0 + np.exp(-x))
+    return (grad_out * 0.05 * 2.0 * (o - t) / x.size).astype(np.float32)
+
+
+def seg_sigmoid(inp):
+    """SegLoss.forward(input) (:77-80): sigmoid(input)[0] as a numpy array."""
+    x = _f32(inp)
+    return (np.float32(1.0) / (np.float32(1.0) + np.exp(-x[0], dtype=np.float32))).astype(np.float32)

@@ -348,6 +348,25 @@ def case_map(name, N, C, seed):
     print(name, "mAP", m, "AP", d["ap"])
 
 
+def case_seg(name, N, C, H, W, seed):
+    """models/seg_loss.py::SegLoss on a synthetic drivable-area head (SURVEY 8 f4): forward with targets (+ the
+    gradient the reference's autograd produces) and the eval forward."""
+    import models.seg_loss as sl
+    sl.device = torch.device("cpu")
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, C, H, W, generator=g)
+    t = (torch.rand(N, H, W, C, generator=g) < 0.3).float() * torch.rand(N, H, W, C, generator=g).clamp(min=0.5)
+    t[0, :2] = 0.49999                                          # values right at the 0.5 split
+    m = sl.SegLoss(C)
+    xg = x.clone().requires_grad_(True)
+    loss, obj, no_obj = m(xg, t)
+    loss.backward()
+    ev = m(x)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), input=x.numpy(), targets=t.numpy(),
+                        out=np.array([loss.item(), obj, no_obj], np.float64), grad=xg.grad.numpy(), eval=np.asarray(ev, np.float32))
+    print(name, loss.item(), obj, no_obj)
+
+
 def main():
     torch.set_num_threads(1)
     check_pre_maps_patch()
@@ -360,6 +379,7 @@ def main():
     case_loss("loss_voc_n3", VOC, 3, [6, 0, 14], 5)
     case_loss("loss_bdd_nonsquare_n2", BDD, 2, [9, 4], 6, nonsquare=True)
     case_map("map_n40_c6", 40, 6, 11)
+    case_seg("seg_n3_c2", 3, 2, 24, 40, 13)
 
 
 if __name__ == "__main__":

@@ -610,3 +610,29 @@ def test_box_ciou_giou_vs_reference_golden(cuda_device):
     for got, want in ((cv, d["ciou"][:, 0]), (ci, d["ciou"][:, 1]), (gv, d["giou"][:, 0]), (gi, d["giou"][:, 1])):
         g = torch.diagonal(got).cpu().numpy()
         np.testing.assert_allclose(g, want, rtol=RTOL, atol=ATOL, equal_nan=True)
+
+
+# ----------------------------------------------------------------------------- seg head
+def test_seg_loss_vs_reference_golden(cuda_device):
+    d = load_golden("seg_n3_c2")
+    m = b200.SegLoss(int(d["input"].shape[1]))
+    x = torch.from_numpy(d["input"]).to(cuda_device).requires_grad_(True)
+    loss, obj, no_obj = m(x, torch.from_numpy(d["targets"]))           # CPU targets like train.py:257 before .to(device)
+    np.testing.assert_allclose([float(loss.detach()), obj, no_obj], d["out"], rtol=RTOL)
+    (loss * 3.0).backward()
+    g = x.grad.cpu().numpy()
+    assert np.abs(g - 3.0 * d["grad"]).max() <= 1e-5 * np.abs(3.0 * d["grad"]).max()
+    ev = m(torch.from_numpy(d["input"]).to(cuda_device))
+    assert isinstance(ev, np.ndarray) and ev.shape == d["eval"].shape
+    np.testing.assert_allclose(ev, d["eval"], rtol=1e-6, atol=1e-7)
+
+
+def test_seg_loss_vs_oracle_large(cuda_device):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(16, 3, 96, 160, generator=g)
+    t = (torch.rand(16, 96, 160, 3, generator=g) < 0.25).float()
+    m = b200.SegLoss(3)
+    loss, obj, no_obj = m(x.to(cuda_device), t.to(cuda_device))
+    np.testing.assert_allclose([float(loss), obj, no_obj], oracle.seg_loss(x.numpy(), t.numpy()), rtol=RTOL)
+    loss0, obj0, no0 = m(x.to(cuda_device), torch.zeros_like(t))     # no pixel >= 0.5: the mean of nothing is NaN
+    assert np.isnan(obj0) and not np.isnan(no0)

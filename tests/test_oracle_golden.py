@@ -133,3 +133,12 @@ def test_map_matches_reference_calculate_mAP():
     np.testing.assert_allclose(ap, d["ap"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(m, float(d["mAP"]), rtol=1e-6)
     assert np.array_equal(tp, d["tp"]) and np.array_equal(fp, d["fp"])
+
+
+def test_seg_loss_matches_reference():
+    """oracle.seg_loss / seg_loss_backward / seg_sigmoid vs models/seg_loss.py::SegLoss and its autograd."""
+    d = load_golden("seg_n3_c2")
+    np.testing.assert_allclose(oracle.seg_loss(d["input"], d["targets"]), d["out"], rtol=1e-5)
+    g = oracle.seg_loss_backward(d["input"], d["targets"])
+    assert np.abs(g - d["grad"]).max() <= 1e-5 * np.abs(d["grad"]).max()
+    np.testing.assert_allclose(oracle.seg_sigmoid(d["input"]), d["eval"], rtol=1e-6, atol=1e-7)
