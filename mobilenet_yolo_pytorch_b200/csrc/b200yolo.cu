@@ -431,6 +431,10 @@ int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H,
     return 0;
 }
 
+static bool seg_vectorisable(const float *input, const float *truth, int C, int HW) {
+    return C >= 1 && C <= 4 && (HW % 4) == 0 && !(((uintptr_t)input | (uintptr_t)truth) & 15);
+}
+
 static int seg_grid(long long total, int dev) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -446,7 +450,8 @@ size_t b200yolo_seg_loss_workspace_bytes(void) { return (size_t)148 * 8 * 4 * kS
 int b200yolo_seg_loss(const float *input, const float *truth, int N, int C, int H, int W, double *sums, void *workspace,
                       size_t workspace_bytes, void *stream) {
     if (!input || !truth || !sums || !workspace) return fail(B200YOLO_EINVAL, "seg_loss: null pointer");
-    if (N < 1 || C < 1 || H < 1 || W < 1) return fail(B200YOLO_EINVAL, "seg_loss: bad shape");
+    if (N < 1 || C < 1 || H < 1 || W < 1 || (long long)N * ((H * W + kSegThreads - 1) / kSegThreads) > 0x7fffffffLL)
+        return fail(B200YOLO_EINVAL, "seg_loss: bad shape");
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;
     SegParams p;
@@ -454,9 +459,17 @@ int b200yolo_seg_loss(const float *input, const float *truth, int N, int C, int 
     p.input = input; p.truth = truth; p.C = C; p.HW = H * W;
     p.total = (long long)N * C * H * W;
     p.partial = (double *)workspace; p.sums = sums;
-    const int grid = seg_grid(p.total, dev);
+    const bool vec = seg_vectorisable(input, truth, C, H * W);
+    const int tile = kSegThreads * (vec ? 4 : 1);
+    p.items = N * ((H * W + tile - 1) / tile);
+    const int grid = seg_grid((long long)p.items * kSegThreads, dev);
     if (workspace_bytes < (size_t)grid * kSegSums * sizeof(double)) return fail(B200YOLO_EINVAL, "seg_loss: workspace too small");
-    seg_loss_kernel<<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!vec) seg_loss_kernel<0><<<grid, kSegThreads, 0, st>>>(p);
+    else if (C == 1) seg_loss_kernel<1><<<grid, kSegThreads, 0, st>>>(p);
+    else if (C == 2) seg_loss_kernel<2><<<grid, kSegThreads, 0, st>>>(p);
+    else if (C == 3) seg_loss_kernel<3><<<grid, kSegThreads, 0, st>>>(p);
+    else seg_loss_kernel<4><<<grid, kSegThreads, 0, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     seg_loss_reduce_kernel<<<1, kSegSums * 32, 0, (cudaStream_t)stream>>>(p.partial, grid, sums);
@@ -476,7 +489,16 @@ int b200yolo_seg_loss_backward(const float *input, const float *truth, int N, in
     p.input = input; p.truth = truth; p.C = C; p.HW = H * W;
     p.total = (long long)N * C * H * W;
     p.grad_out = grad_out; p.grad_input = grad_input;
-    seg_loss_backward_kernel<<<seg_grid(p.total, dev), kSegThreads, 0, (cudaStream_t)stream>>>(p);
+    const bool vec = seg_vectorisable(input, truth, C, H * W) && !((uintptr_t)grad_input & 15);
+    const int tile = kSegThreads * (vec ? 4 : 1);
+    p.items = N * ((H * W + tile - 1) / tile);
+    const int grid = seg_grid((long long)p.items * kSegThreads, dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!vec) seg_loss_backward_kernel<0><<<grid, kSegThreads, 0, st>>>(p);
+    else if (C == 1) seg_loss_backward_kernel<1><<<grid, kSegThreads, 0, st>>>(p);
+    else if (C == 2) seg_loss_backward_kernel<2><<<grid, kSegThreads, 0, st>>>(p);
+    else if (C == 3) seg_loss_backward_kernel<3><<<grid, kSegThreads, 0, st>>>(p);
+    else seg_loss_backward_kernel<4><<<grid, kSegThreads, 0, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -624,7 +624,7 @@ def test_seg_loss_vs_reference_golden(cuda_device):
     assert np.abs(g - 3.0 * d["grad"]).max() <= 1e-5 * np.abs(3.0 * d["grad"]).max()
     ev = m(torch.from_numpy(d["input"]).to(cuda_device))
     assert isinstance(ev, np.ndarray) and ev.shape == d["eval"].shape
-    np.testing.assert_allclose(ev, d["eval"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(ev, d["eval"], rtol=RTOL, atol=ATOL)
 
 
 def test_seg_loss_vs_oracle_large(cuda_device):
