@@ -220,6 +220,10 @@ __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
         p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
     }
 }
+// inside the decode loop the check is hoisted: `on` = p.dbg != nullptr && threadIdx.x == 0
+__device__ __forceinline__ void stamp_if(bool on, const DNParams &p, int b, int k) {
+    if (on) p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
+}
 
 // Programmatic dependent launch (the host sets cudaLaunchAttributeProgrammaticStreamSerialization): the NEXT
 // kernel in the stream may start once every CTA of this one has executed pdl_trigger(); it must execute
@@ -333,6 +337,7 @@ template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST>
 __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     static_assert(CT >= 1 && CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
     const int tid = threadIdx.x, lane = tid & 31;
+    const bool dbg_on = p.dbg != nullptr && tid == 0;
     constexpr int attrs = CT + 5;
     const int cells = p.A * HWT;
     const float *hb = hd.ptr + (size_t)b * p.A * attrs * HWT;  // uniform
@@ -384,7 +389,7 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
             const unsigned bal = __ballot_sync(kFullMask, pass);
             if (lane == 0 && active) s.passbits[local >> 5] = bal;
         }
-        if (MODE == MODE_FUSED) stamp(p, b, 8 + min(3, hh + base / THREADS));
+        if (MODE == MODE_FUSED) stamp_if(dbg_on, p, b, 8 + min(3, hh + base / THREADS));
     }
 }
 
@@ -392,6 +397,7 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
 template <int THREADS, int MODE>
 __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     const int tid = threadIdx.x, lane = tid & 31;
+    const bool dbg_on = p.dbg != nullptr && tid == 0;
     const int C = p.C;
     const int attrs = C + 5;
     const int HW = hd.HW;
@@ -482,7 +488,7 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
             const unsigned bal = __ballot_sync(kFullMask, pass);
             if (lane == 0 && local < cells) s.passbits[local >> 5] = bal;
         }
-        if (MODE == MODE_FUSED) stamp(p, b, 8 + min(3, hh + base / THREADS));
+        if (MODE == MODE_FUSED) stamp_if(dbg_on, p, b, 8 + min(3, hh + base / THREADS));
     }
 }
 
@@ -730,14 +736,24 @@ __device__ __forceinline__ void pair_step(const uint2 e, const float4 &R, float 
 __device__ __forceinline__ uint32_t block_fast(const uint2 *ordc, int ncol, const float4 R, float rta, double thr) {
     uint32_t bits = 0u;
     float m = INFINITY;
-    // chunks of 8 columns; a partial last chunk reads up to 7 entries past the class (the next class's
-    // entries, or the NaN-area padding after the last one): their bits are dropped below, a NaN never
-    // lowers m, and a false "too close" only costs the exact path
-    const int nr = (ncol + 7) & ~7;
+    // chunks of 8 columns, then one chunk of 4 or 8 for the remainder; a partial last chunk reads up to 7 entries
+    // past the class (the next class's entries, or the NaN-area padding after the last one): their bits are
+    // dropped below, a NaN never lowers m, and a false "too close" only costs the exact path
+    const int n8 = ncol & ~7, rem = ncol - n8;
 #pragma unroll 1
-    for (int k0 = 0; k0 < nr; k0 += 8) {
+    for (int k0 = 0; k0 < n8; k0 += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) pair_step(ordc[k0 + k], R, rta, bits, m);
+    }
+    int nr = n8;
+    if (rem > 4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pair_step(ordc[n8 + k], R, rta, bits, m);
+        nr += 8;
+    } else if (rem > 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pair_step(ordc[n8 + k], R, rta, bits, m);
+        nr += 4;
     }
     uint32_t word = (__brev(bits) >> (32 - nr)) & (0xffffffffu >> (32 - ncol));  // column k was shifted in k-th
     if (m <= 0.0f) word = block_exact(ordc, ncol, R, thr);
