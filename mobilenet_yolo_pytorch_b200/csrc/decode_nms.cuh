@@ -697,6 +697,7 @@ __device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s
         const int st = base + s.cntb[c * p.B + bk];
         const int en = base + ((bk == p.B - 1) ? s.cnt[c] : s.cntb[c * p.B + bk + 1]);
         int rank = 0;
+#pragma unroll 4
         for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
         const float ta = make_ta(s.box[cid], p.iou);
         if (ta != ta) s.flag[c] = 1;  // degenerate box: the class runs the exact pair arithmetic
