@@ -9,8 +9,9 @@
 //   P1  thread per GT box (replicated in the S CTAs of an image): xyxy (:112-113), IoU
 //       against ALL anchor shapes (:132), best anchor = first argmax (:133), cell (gj, gi)
 //       (:128,136-137), assignment flags k == index(best) or iou[mask[k]] > iou_thresh
-//       (:138-145); assigned (GT, k) pairs are appended to a shared-memory list and their
-//       cells flagged.
+//       (:138-145); assigned (GT, k) pairs go to a shared-memory list in (GT, k) order (block
+//       scan, so every sum is the same run to run) and their cells are flagged; duplicate
+//       assignments of a cell are chained and the distinct cells listed.
 //   P2  thread per cell, coalesced head reads: conf = sigmoid(tc); flagged cells
 //       contribute (conf-1)^2 (:149-150); otherwise the decoded box (:84-92) is tested
 //       against every GT box staged in shared memory: weight 1 / target 0 iff
@@ -21,8 +22,8 @@
 //       closer than 1e-5 to the threshold (or a degenerate box) re-runs its GT loop with
 //       the reference's IEEE arithmetic (inter/union < thr).
 //   P3  (first CTA of the image) thread per assignment: CIoU term (box_ciou :257-293),
-//       recall / iou / obj / class-score stats (:151-169); then warp per distinct assigned
-//       cell: the class-channel loss, lanes = classes, with the union of
+//       recall / iou / obj / class-score stats (:151-169); then thread per (distinct assigned
+//       cell, class): the class-channel loss with the union of
 //       assigned classes at 0.95, the rest at 0.05 (class_loss :425-434 -- order
 //       independent, duplicates counted exactly like the sequential reference).
 //   P4  deterministic reduction: per-CTA partial sums -> workspace, then a
@@ -77,18 +78,70 @@ struct TLAssign {
     uint32_t t;     // GT index inside the image
 };
 
+// Shared-memory layout of both kernels
+struct TLSmem {
+    float4 *gbox;      // [gcap] GT xyxy
+    float *garea;      // [gcap]
+    float *gta;        // [gcap] t * area * 2^-13
+    int *gcls;         // [gcap] class (0-based)
+    int2 *gtmp;        // [gcap] pass-1 result of the matching: {cell base gj*W+gi, assignment mask over k}
+    TLAssign *list;    // [A*gcap] assignments in (GT, k) order
+    uint16_t *ucell;   // [A*gcap] list index of the first assignment of every distinct cell
+    uint8_t *flag;     // [cells] cell is assigned
+    double *red;       // [kTLSums][kTLWarps]
+    int *misc;         // [16]: 0 nE, 1 any degenerate GT, 2 status, 3 nU, 4..11 warp totals of the block scans
+    double4 *contrib;  // backward: [A*gcap] box-gradient contribution of every assignment
+};
+
+__host__ __device__ inline uint32_t tl_up16(uint32_t v) { return (v + 15u) / 16u * 16u; }
+
 __host__ __device__ inline uint32_t tl_smem_bytes(int cells, int gcap, int A, bool backward = false) {
-    uint32_t o = 0;
-    o += 16 * (uint32_t)gcap;                 // gt xyxy
-    o += 4 * (uint32_t)gcap;                  // gt area
-    o += 4 * (uint32_t)gcap;                  // gt t*area*2^-13
-    o += 4 * (uint32_t)gcap;                  // gt class (0-based)
-    o += 8 * (uint32_t)(gcap * A);            // assignment list (every GT can be assigned to all A anchors of the head)
-    o += ((uint32_t)cells + 15u) / 16u * 16u; // assigned-cell flags
-    o += 8 * kTLSums * kTLWarps;              // reduction scratch
-    o += 64;
-    if (backward) o += 32 * (uint32_t)(gcap * A);  // per-assignment box-gradient contributions (4 doubles)
+    const uint32_t g = (uint32_t)gcap, l = (uint32_t)(gcap * A);
+    uint32_t o = 36 * g + 8 * l + tl_up16(2 * l) + tl_up16((uint32_t)cells) + 8 * kTLSums * kTLWarps + 64;
+    if (backward) o += 32 * l;
     return o;
+}
+
+__device__ __forceinline__ TLSmem tl_carve(unsigned char *base, int cells, int gcap, int A) {
+    const uint32_t g = (uint32_t)gcap, l = (uint32_t)(gcap * A);
+    TLSmem s;
+    uint32_t o = 0;
+    s.gbox = reinterpret_cast<float4 *>(base + o); o += 16 * g;
+    s.garea = reinterpret_cast<float *>(base + o); o += 4 * g;
+    s.gta = reinterpret_cast<float *>(base + o); o += 4 * g;
+    s.gcls = reinterpret_cast<int *>(base + o); o += 4 * g;
+    s.gtmp = reinterpret_cast<int2 *>(base + o); o += 8 * g;
+    s.list = reinterpret_cast<TLAssign *>(base + o); o += 8 * l;
+    s.ucell = reinterpret_cast<uint16_t *>(base + o); o += tl_up16(2 * l);
+    s.flag = reinterpret_cast<uint8_t *>(base + o); o += tl_up16((uint32_t)cells);
+    s.red = reinterpret_cast<double *>(base + o); o += 8 * kTLSums * kTLWarps;
+    s.misc = reinterpret_cast<int *>(base + o); o += 64;
+    s.contrib = reinterpret_cast<double4 *>(base + o);
+    return s;
+}
+
+// s_list[e].t packs the GT index (bits 0-10) and 1 + the list index of the next assignment of the same cell (bits 11-24)
+constexpr uint32_t kTLGtMask = 0x7ffu;
+__device__ __forceinline__ int tl_entry_gt(uint32_t tn) { return (int)(tn & kTLGtMask); }
+__device__ __forceinline__ int tl_entry_next(uint32_t tn) { return (int)(tn >> 11) - 1; }
+
+// block-wide exclusive scan of one int per thread (warp totals in misc[4..11]); returns the exclusive prefix and the
+// block total.  Two barriers; every thread of the CTA must call it.
+__device__ __forceinline__ int tl_block_scan(int v, int *misc, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int inc = warp_inclusive_scan(v, lane);
+    __syncthreads();  // (misc[4..11] free again)
+    if (lane == 31) misc[4 + warp] = inc;
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kTLWarps; ++w) {
+        const int t = misc[4 + w];
+        before += (w < warp) ? t : 0;
+        all += t;
+    }
+    *total = all;
+    return before + inc - v;
 }
 
 // decode one cell's box exactly like get_target (:84-92) + wh_to_x2y2 (:243-247)
@@ -172,92 +225,133 @@ __device__ __noinline__ bool tl_below_exact(const float4 *gbox, const float *gar
     return below;
 }
 
-// P1: per-GT anchor matching (yolo_loss.py:112-113, 127-145): stages the image's GT boxes, appends the assigned
-// (GT, k) pairs to s_list and flags their cells.  `lead` CTAs also write the per-GT outputs and the status
-// (s_misc[2]; it travels to the host through slot 12 of the CTA's partial sums).
-__device__ __forceinline__ void tl_match_gt(const TLParams &p, int b, int g0, int nG, bool lead, float4 *s_gbox, float *s_garea,
-                                            float *s_gta, int *s_gcls, TLAssign *s_list, uint8_t *s_flag, int *s_misc) {
+// P1: per-GT anchor matching (yolo_loss.py:112-113, 127-145): stages the image's GT boxes, then appends the assigned
+// (GT, k) pairs to the list in (GT, k) order (block scan: the list, and with it every sum, is the same run to run) and
+// flags their cells.  `lead` CTAs also write the per-GT outputs and the status (misc[2]; it travels to the host through
+// slot 12 of the CTA's partial sums).  Ends with the list complete and visible (trailing barrier); misc[0] = length.
+__device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, bool lead, const TLSmem &s) {
     const int tid = threadIdx.x;
     const int W = p.W, H = p.H, A = p.A, C = p.C;
-    (void)b;
-    for (int t = tid; t < nG; t += kTLThreads) {
-        const float *g = p.gt + 5 * (size_t)(g0 + t);
-        const float gc = __ldg(g), gx = __ldg(g + 1), gy = __ldg(g + 2), gw = __ldg(g + 3), gh = __ldg(g + 4);
-        float4 bx;                                                  // :112-113 wh_to_x2y2
-        bx.x = __fsub_rn(gx, __fmul_rn(gw, 0.5f));
-        bx.y = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
-        bx.z = __fadd_rn(gw, bx.x);
-        bx.w = __fadd_rn(gh, bx.y);
-        const float barea = box_area(bx);
-        const float bta = tl_ta(bx, barea, p.ts);
-        s_gbox[t] = bx;
-        s_garea[t] = barea;
-        s_gta[t] = bta;
-        if (bta != bta) s_misc[1] = 1;
-        const int cls = (int)__fsub_rn(gc, 1.0f);                   // :131,147
-        s_gcls[t] = cls;
-        const int gi = (int)__fmul_rn(gx, p.fW), gj = (int)__fmul_rn(gy, p.fH);  // :128,136-137
-        const bool ok = gi >= 0 && gi < W && gj >= 0 && gj < H && cls >= 0 && cls < C;
-        if (!ok && lead) atomicMax(&s_misc[2], 1);
-        // anchor-vs-GT IoU on (0,0,w,h) shapes, ALL anchors (:129-133)
-        const float4 gb = make_float4(0.f, 0.f, gw, gh);
-        const float ga = box_area(gb);
-        float best = 0.f;
-        int best_n = 0;
-        unsigned over = 0u;  // bit n: iou[n] > iou_thresh
-        for (int n = 0; n < p.NA; ++n) {
-            const float4 ab = make_float4(0.f, 0.f, p.aw_all[n], p.ah_all[n]);
-            const float v = tl_iou(gb, ga, ab, box_area(ab));
-            if (n == 0 || v > best) { best = v; best_n = n; }       // argmax = first maximum
-            if (v > p.iou_thr) over |= 1u << n;                      // :139
+    int carry = 0;
+    for (int t0 = 0; t0 < nG; t0 += kTLThreads) {  // (uniform trip count)
+        const int t = t0 + tid;
+        int cellbase = 0;
+        unsigned amask = 0u;
+        if (t < nG) {
+            const float *g = p.gt + 5 * (size_t)(g0 + t);
+            const float gc = __ldg(g), gx = __ldg(g + 1), gy = __ldg(g + 2), gw = __ldg(g + 3), gh = __ldg(g + 4);
+            float4 bx;                                                  // :112-113 wh_to_x2y2
+            bx.x = __fsub_rn(gx, __fmul_rn(gw, 0.5f));
+            bx.y = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
+            bx.z = __fadd_rn(gw, bx.x);
+            bx.w = __fadd_rn(gh, bx.y);
+            const float barea = box_area(bx);
+            const float bta = tl_ta(bx, barea, p.ts);
+            s.gbox[t] = bx;
+            s.garea[t] = barea;
+            s.gta[t] = bta;
+            if (bta != bta) s.misc[1] = 1;
+            const int cls = (int)__fsub_rn(gc, 1.0f);                   // :131,147
+            s.gcls[t] = cls;
+            const int gi = (int)__fmul_rn(gx, p.fW), gj = (int)__fmul_rn(gy, p.fH);  // :128,136-137
+            const bool ok = gi >= 0 && gi < W && gj >= 0 && gj < H && cls >= 0 && cls < C;
+            if (!ok && lead) atomicMax(&s.misc[2], 1);
+            // anchor-vs-GT IoU on (0,0,w,h) shapes, ALL anchors (:129-133)
+            const float4 gb = make_float4(0.f, 0.f, gw, gh);
+            const float ga = box_area(gb);
+            float best = 0.f;
+            int best_n = 0;
+            unsigned over = 0u;  // bit n: iou[n] > iou_thresh
+            for (int n = 0; n < p.NA; ++n) {
+                const float4 ab = make_float4(0.f, 0.f, p.aw_all[n], p.ah_all[n]);
+                const float v = tl_iou(gb, ga, ab, box_area(ab));
+                if (n == 0 || v > best) { best = v; best_n = n; }       // argmax = first maximum
+                if (v > p.iou_thr) over |= 1u << n;                      // :139
+            }
+            for (int k = 0; k < A; ++k) {
+                const bool asg = ok && (p.mask[k] == best_n || ((over >> p.mask[k]) & 1u));  // :141-145
+                if (asg) amask |= 1u << k;
+                if (p.assign && lead) {
+                    int *r = p.assign + ((size_t)(g0 + t) * A + k) * 4;
+                    r[0] = asg ? 1 : 0; r[1] = gj; r[2] = gi; r[3] = best_n;
+                }
+                if (p.terms && lead && !asg) {
+                    float *r = p.terms + ((size_t)(g0 + t) * A + k) * 2;
+                    r[0] = 0.f; r[1] = 0.f;
+                }
+            }
+            cellbase = gj * W + gi;
         }
+        int total;
+        int e = carry + tl_block_scan(__popc(amask), s.misc, &total);
         for (int k = 0; k < A; ++k) {
-            const bool asg = ok && (p.mask[k] == best_n || ((over >> p.mask[k]) & 1u));  // :141-145
-            if (p.assign && lead) {
-                int *r = p.assign + ((size_t)(g0 + t) * A + k) * 4;
-                r[0] = asg ? 1 : 0; r[1] = gj; r[2] = gi; r[3] = best_n;
-            }
-            if (p.terms && lead && !asg) {
-                float *r = p.terms + ((size_t)(g0 + t) * A + k) * 2;
-                r[0] = 0.f; r[1] = 0.f;
-            }
-            if (asg) {
-                const uint32_t cell = (uint32_t)((k * H + gj) * W + gi);
-                const int e = atomicAdd(&s_misc[0], 1);
-                s_list[e].cell = cell;  // e < A * nG <= A * gcap
-                s_list[e].t = (uint32_t)t;
-                s_flag[cell] = 1;
+            if ((amask >> k) & 1u) {
+                const uint32_t cell = (uint32_t)(k * H * W + cellbase);
+                s.list[e].cell = cell;
+                s.list[e].t = (uint32_t)t;
+                s.flag[cell] = 1;
+                ++e;
             }
         }
+        carry += total;
     }
+    if (tid == 0) s.misc[0] = carry;
+    __syncthreads();
+}
+
+// Duplicate chains and the list of distinct assigned cells (in list order): list[e].t gets the index of the next
+// assignment of the same cell; ucell[u] = index of the first assignment of the u-th distinct cell; misc[3] = count.
+// Every thread of the CTA must call it; ends with a barrier.
+__device__ __forceinline__ void tl_unique_cells(int nE, const TLSmem &s) {
+    const int tid = threadIdx.x;
+    int carry = 0;
+    for (int e0 = 0; e0 < nE; e0 += kTLThreads) {
+        const int e = e0 + tid;
+        int first = 0;
+        if (e < nE) {
+            const uint32_t cell = s.list[e].cell;
+            int nx = -1;
+            for (int f = e + 1; f < nE; ++f)
+                if (s.list[f].cell == cell) { nx = f; break; }
+            first = 1;
+            for (int f = 0; f < e; ++f)
+                if (s.list[f].cell == cell) { first = 0; break; }
+            s.list[e].t |= (uint32_t)(nx + 1) << 11;
+        }
+        int total;
+        const int u = carry + tl_block_scan(first, s.misc, &total);
+        if (first) s.ucell[u] = (uint16_t)e;
+        carry += total;
+    }
+    if (tid == 0) s.misc[3] = carry;
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams p) {
     extern __shared__ __align__(16) unsigned char tl_smem[];
-    const uint32_t gcap = (uint32_t)p.gcap, lcap = (uint32_t)(p.gcap * p.A);
-    float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
-    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * gcap);
-    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * gcap);
-    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * gcap);
-    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * gcap);
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * gcap + 8 * lcap);
-    const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
-    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * gcap + 8 * lcap + flag_bytes);
-    int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
+    const TLSmem sm = tl_carve(tl_smem, p.cells, p.gcap, p.A);
+    float4 *s_gbox = sm.gbox;
+    float *s_garea = sm.garea, *s_gta = sm.gta;
+    int *s_gcls = sm.gcls;
+    TLAssign *s_list = sm.list;
+    uint8_t *s_flag = sm.flag;
+    double *s_red = sm.red;
+    int *s_misc = sm.misc;
+    const uint32_t flag_bytes = tl_up16((uint32_t)p.cells);
 
     const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
     const bool lead = (split == 0);  // the CTA of the image that owns the per-GT outputs and the assignments
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g0 = p.gt_off[b];
     int nG = p.gt_off[b + 1] - g0;
-    const int HW = p.HW, W = p.W, H = p.H, A = p.A, C = p.C;
+    const int HW = p.HW, W = p.W, A = p.A, C = p.C;
 
     // Programmatic dependent launch (see decode_nms.cuh): the next kernel of the stream may start now; this one
     // waits for its predecessor before its first global store (the workspace of partial sums is shared by
     // consecutive calls; the optional per-GT / per-cell outputs are written early, so they wait here).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.assign || p.terms || p.cell_state) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; }  // assignment list length; any degenerate GT box; status
+    if (tid < 4) s_misc[tid] = 0;  // assignment list length; any degenerate GT box; status; distinct cells
     for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
     __syncthreads();
     if (nG > p.gcap) {
@@ -269,10 +363,11 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
 #pragma unroll
     for (int q = 0; q < 10; ++q) acc[q] = 0.0;
 
-    tl_match_gt(p, b, g0, nG, lead, s_gbox, s_garea, s_gta, s_gcls, s_list, s_flag, s_misc);
-    __syncthreads();
+    tl_match_gt(p, g0, nG, lead, sm);
     const int nE = s_misc[0];
     const bool gt_degenerate = s_misc[1] != 0;
+    if (lead) tl_unique_cells(nE, sm);  // (lead is uniform in the CTA)
+    const int nU = s_misc[3];
 
     // ---------------- P2: per-cell objectness / ignore mask ----------------
     const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
@@ -333,11 +428,10 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
     }
 
     // ---------------- P3a: per-assignment terms (thread per assignment) ----------------
-    constexpr uint32_t kDup = 0x80000000u;  // s_list[e].t bit 31: an earlier entry has the same cell
     if (lead) {
         for (int e = tid; e < nE; e += kTLThreads) {
             const uint32_t cell = s_list[e].cell;
-            const int t = (int)s_list[e].t;
+            const int t = tl_entry_gt(s_list[e].t);
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
             const int pos = (int)cell - a * HW;
             const int j = (int)(((float)pos + 0.5f) * p.invW);
@@ -364,47 +458,24 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
                 float *r = p.terms + ((size_t)(g0 + t) * A + a) * 2;    // cell = (k*H+gj)*W+gi -> k == a
                 r[0] = v; r[1] = iou;
             }
-            bool dup = false;
-            for (int f = 0; f < e; ++f) dup = dup || (s_list[f].cell == cell);
-            if (dup) s_list[e].t = (uint32_t)t | kDup;
         }
-        __syncthreads();  // (lead is uniform in the CTA)
-        // ------------ P3b: class channels, once per distinct cell (its first list entry); warp per cell, lanes = classes
-        for (int e = warp; e < nE; e += kTLWarps) {
-            const uint32_t te = s_list[e].t;
-            if (te & kDup) continue;
-            const uint32_t cell = s_list[e].cell;
+        // ------------ P3b: class channels, once per distinct cell: thread per (cell, class), all logit loads in flight
+        for (int it = tid; it < nU * C; it += kTLThreads) {
+            const int u = it / C, c = it - u * C;
+            int f = sm.ucell[u];
+            const uint32_t cell = s_list[f].cell;
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
             const int pos = (int)cell - a * HW;
-            const float *q = p.head + ((size_t)(b * A + a) * p.attrs) * HW + pos;
-            const int cls = s_gcls[te];
-            double sq = 0.0;
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                const int c = c0 + lane;
-                float o = 0.f;
-                if (c < C) o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
-                bool hit = (c == cls);
-                for (int f0 = e + 1 - ((e + 1) & 31); f0 < nE; f0 += 32) {  // later entries of the same cell
-                    const int f = f0 + lane;
-                    unsigned bal = __ballot_sync(kFullMask, f > e && f < nE && s_list[f].cell == cell);
-                    while (bal) {
-                        const int f2 = f0 + __ffs(bal) - 1;
-                        bal &= bal - 1u;
-                        hit = hit || (s_gcls[s_list[f2].t & ~kDup] == c);
-                    }
-                }
-                if (c < C) {
-                    const float tv = hit ? 0.95f : 0.05f;               // :426-433
-                    const float df = __fsub_rn(o, tv);
-                    sq += (double)__fmul_rn(df, df);
-                }
+            const float o = sigmoid_f(__ldg(p.head + ((size_t)(b * A + a) * p.attrs + 5 + c) * HW + pos));
+            bool hit = false;                                           // is c one of the classes assigned to the cell
+            while (f >= 0) {
+                const uint32_t tn = s_list[f].t;
+                hit = hit || (s_gcls[tl_entry_gt(tn)] == c);
+                f = tl_entry_next(tn);
             }
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) sq += __shfl_xor_sync(kFullMask, sq, sh);
-            if (lane == 0) {
-                acc[B200YOLO_S_SQW] += sq;
-                acc[B200YOLO_S_W] += (double)C;
-            }
+            const float df = __fsub_rn(o, hit ? 0.95f : 0.05f);         // :426-433
+            acc[B200YOLO_S_SQW] += (double)__fmul_rn(df, df);
+            acc[B200YOLO_S_W] += 1.0;
         }
     }
 
@@ -482,32 +553,31 @@ __device__ __forceinline__ double tl_ciou_grad(const float4 &gt, const TLBox4d &
     return (c == 0.0) ? 0.0 : iou - (u / c + Aar * Aar / D);
 }
 
-__global__ void __launch_bounds__(kTLThreads) target_loss_backward_kernel(const TLParams p) {
+// (min 4 CTAs per SM: the fp64 CIoU gradient, run by a few threads of the first CTA of an image, would otherwise
+// raise the register count to 115 and halve the occupancy of the streaming part)
+__global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(const TLParams p) {
     extern __shared__ __align__(16) unsigned char tl_smem[];
-    const uint32_t gcap = (uint32_t)p.gcap, lcap = (uint32_t)(p.gcap * p.A);
-    float4 *s_gbox = reinterpret_cast<float4 *>(tl_smem);
-    float *s_garea = reinterpret_cast<float *>(tl_smem + 16 * gcap);
-    float *s_gta = reinterpret_cast<float *>(tl_smem + 20 * gcap);
-    int *s_gcls = reinterpret_cast<int *>(tl_smem + 24 * gcap);
-    TLAssign *s_list = reinterpret_cast<TLAssign *>(tl_smem + 28 * gcap);
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(tl_smem + 28 * gcap + 8 * lcap);
-    const uint32_t flag_bytes = ((uint32_t)p.cells + 15u) / 16u * 16u;
-    double *s_red = reinterpret_cast<double *>(tl_smem + 28 * gcap + 8 * lcap + flag_bytes);
-    int *s_misc = reinterpret_cast<int *>(s_red + kTLSums * kTLWarps);
+    const TLSmem sm = tl_carve(tl_smem, p.cells, p.gcap, p.A);
+    float4 *s_gbox = sm.gbox;
+    int *s_gcls = sm.gcls;
+    TLAssign *s_list = sm.list;
+    uint8_t *s_flag = sm.flag;
+    int *s_misc = sm.misc;
+    const uint32_t flag_bytes = tl_up16((uint32_t)p.cells);
 
     const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
-    const bool lead = (split == 0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int g0 = p.gt_off[b];
     int nG = p.gt_off[b + 1] - g0;
-    const int HW = p.HW, W = p.W, A = p.A, C = p.C;
-    if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; }
+    const int HW = p.HW, W = p.W, A = p.A;
+    if (tid < 4) s_misc[tid] = 0;
     for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
     if (nG > p.gcap) nG = 0;  // (the forward call reported it)
     __syncthreads();
-    tl_match_gt(p, b, g0, nG, false, s_gbox, s_garea, s_gta, s_gcls, s_list, s_flag, s_misc);
-    __syncthreads();
+    tl_match_gt(p, g0, nG, false, sm);
     const int nE = s_misc[0];
+    tl_unique_cells(nE, sm);
+    const int nU = s_misc[3];
 
     const double go = p.grad_out ? (double)__ldg(p.grad_out) : 1.0;
     const double inv_w = go * 2.0 / p.sums[B200YOLO_S_W];                                    // d L_dense / d o = 2 (o - t) w / sum w
@@ -518,25 +588,46 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_backward_kernel(const 
 
     // ---- every cell that is not assigned: only the objectness channel can carry a gradient
     const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
-    for (int cell = cell_lo + tid; cell < cell_hi; cell += kTLThreads) {
-        if (s_flag[cell]) continue;
-        const int a = (int)(((float)cell + 0.5f) * p.invHW);
-        const int pos = cell - a * HW;
-        const size_t off = (size_t)a * p.attrs * HW + pos;
-        const unsigned char st = p.cell_state_in[(size_t)b * p.cells + cell];
-        const float tc = __ldg(hbase + off + 4 * (size_t)HW);
-        float gconf = 0.f;
-        if (st == 1) gconf = (float)((double)sigmoid_f(tc) * inv_w);  // target 0
-        float *g = gbase + off;
-        for (int t = 0; t < p.attrs; ++t) __stcs(g + (size_t)t * HW, t == 4 ? gconf : 0.f);
+    const bool vec = (HW & 3) == 0 && (((uintptr_t)p.grad_input | (uintptr_t)p.head) & 15) == 0;
+    if (vec) {
+        // 4 consecutive cells of one anchor plane per thread: 16-byte loads / stores (the slice bounds are multiples of 32)
+        for (int cell = cell_lo + 4 * tid; cell < cell_hi; cell += 4 * kTLThreads) {
+            const int a = (int)(((float)cell + 0.5f) * p.invHW);
+            const int pos = cell - a * HW;   // multiple of 4; HW is a multiple of 4: the group stays inside the plane
+            const size_t off = (size_t)a * p.attrs * HW + pos;
+            const uchar4 st = *reinterpret_cast<const uchar4 *>(p.cell_state_in + (size_t)b * p.cells + cell);
+            const float4 tc = __ldg(reinterpret_cast<const float4 *>(hbase + off + 4 * (size_t)HW));
+            float4 gc;
+            gc.x = (st.x == 1) ? (float)((double)sigmoid_fast(tc.x) * inv_w) : 0.f;   // target 0
+            gc.y = (st.y == 1) ? (float)((double)sigmoid_fast(tc.y) * inv_w) : 0.f;
+            gc.z = (st.z == 1) ? (float)((double)sigmoid_fast(tc.z) * inv_w) : 0.f;
+            gc.w = (st.w == 1) ? (float)((double)sigmoid_fast(tc.w) * inv_w) : 0.f;
+            // (an assigned cell of the group gets its real values below, after the barrier)
+            float *g = gbase + off;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < p.attrs; ++t) __stcs(reinterpret_cast<float4 *>(g + (size_t)t * HW), t == 4 ? gc : z);
+        }
+    } else {
+        for (int cell = cell_lo + tid; cell < cell_hi; cell += kTLThreads) {
+            if (s_flag[cell]) continue;
+            const int a = (int)(((float)cell + 0.5f) * p.invHW);
+            const int pos = cell - a * HW;
+            const size_t off = (size_t)a * p.attrs * HW + pos;
+            const unsigned char st = p.cell_state_in[(size_t)b * p.cells + cell];
+            const float tc = __ldg(hbase + off + 4 * (size_t)HW);
+            float gconf = 0.f;
+            if (st == 1) gconf = (float)((double)sigmoid_fast(tc) * inv_w);  // target 0
+            float *g = gbase + off;
+            for (int t = 0; t < p.attrs; ++t) __stcs(g + (size_t)t * HW, t == 4 ? gconf : 0.f);
+        }
     }
 
-    // ---- assigned cells (first CTA of the image)
-    if (lead) {
+    // ---- assigned cells of this CTA's slice (after the barrier: they overwrite what the streaming pass stored)
+    {
         // thread per assignment: its CIoU gradient w.r.t. (tx, ty, tw, th) of its cell, fp64 on the fp32 decoded box
-        double4 *s_contrib = reinterpret_cast<double4 *>(s_misc + 16);
         for (int e = tid; e < nE; e += kTLThreads) {
             const uint32_t cell = s_list[e].cell;
+            if ((int)cell < cell_lo || (int)cell >= cell_hi) continue;
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
             const int pos = (int)cell - a * HW;
             const int j = (int)(((float)pos + 0.5f) * p.invW);
@@ -548,7 +639,7 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_backward_kernel(const 
             TLBox4d pr;
             pr.x = pb.x; pr.y = pb.y; pr.z = pb.z; pr.w = pb.w;
             double dv[4];
-            const double v = tl_ciou_grad(s_gbox[s_list[e].t], pr, dv);
+            const double v = tl_ciou_grad(s_gbox[tl_entry_gt(s_list[e].t)], pr, dv);
             const double gl = inv_n * (v - 1.0);
             const double bw = (double)__fmul_rn(expf(tw), aw), bh = (double)__fmul_rn(expf(th), ah);
             double4 c4;
@@ -556,63 +647,43 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_backward_kernel(const 
             c4.y = gl * (dv[1] + dv[3]) / (double)p.fH;
             c4.z = gl * (dv[2] - dv[0]) * 0.5 * bw;       // d x1/d bw = -1/2, d x2/d bw = +1/2, d bw/d tw = bw
             c4.w = gl * (dv[3] - dv[1]) * 0.5 * bh;
-            s_contrib[e] = c4;
+            sm.contrib[e] = c4;
         }
-        __syncthreads();  // (lead is uniform in the CTA)
-        // warp per distinct cell (its first list entry): sum over the cell's duplicates, objectness, classes
-        for (int e = warp; e < nE; e += kTLWarps) {
-            const uint32_t cell = s_list[e].cell;
-            bool earlier = false;
-            for (int f0 = 0; f0 < e; f0 += 32) {
-                const int f = f0 + lane;
-                earlier = earlier || (__ballot_sync(kFullMask, f < e && s_list[f].cell == cell) != 0u);
-            }
-            if (earlier) continue;
+        __syncthreads();
+        // thread per (distinct cell, channel): all logit loads of the CTA are in flight together
+        const int attrs = p.attrs;
+        for (int it = tid; it < nU * attrs; it += kTLThreads) {
+            const int u = it / attrs, t = it - u * attrs;
+            int f = sm.ucell[u];
+            const uint32_t cell = s_list[f].cell;
+            if ((int)cell < cell_lo || (int)cell >= cell_hi) continue;
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
             const int pos = (int)cell - a * HW;
-            const size_t off = (size_t)a * p.attrs * HW + pos;
-            const float *q = hbase + off;
-            float *g = gbase + off;
-            const float tc = __ldg(q + 4 * (size_t)HW);
-            double gx = 0.0, gy = 0.0, gw = 0.0, gh = 0.0;
-            for (int f0 = e - (e & 31); f0 < nE; f0 += 32) {
-                const int f = f0 + lane;
-                if (f >= e && f < nE && s_list[f].cell == cell) {
-                    const double4 c4 = s_contrib[f];
-                    gx += c4.x; gy += c4.y; gw += c4.z; gh += c4.w;
+            const size_t off = ((size_t)a * attrs + t) * HW + pos;
+            float gv;
+            if (t < 4) {                                   // box channels: sum over the cell's assignments (duplicates add up)
+                double acc4 = 0.0;
+                while (f >= 0) {
+                    const double4 c4 = sm.contrib[f];
+                    acc4 += (t == 0) ? c4.x : (t == 1) ? c4.y : (t == 2) ? c4.z : c4.w;
+                    f = tl_entry_next(s_list[f].t);
                 }
-            }
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) {
-                gx += __shfl_xor_sync(kFullMask, gx, sh);
-                gy += __shfl_xor_sync(kFullMask, gy, sh);
-                gw += __shfl_xor_sync(kFullMask, gw, sh);
-                gh += __shfl_xor_sync(kFullMask, gh, sh);
-            }
-            if (lane == 0) {
-                g[0] = (float)gx;
-                g[HW] = (float)gy;
-                g[2 * (size_t)HW] = (float)gw;
-                g[3 * (size_t)HW] = (float)gh;
-                g[4 * (size_t)HW] = (float)(((double)sigmoid_f(tc) - 1.0) * inv_w);  // target 1 (:149-150)
-            }
-            // class channels: target 0.95 for every class assigned to the cell, 0.05 otherwise (:425-434)
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                const int c = c0 + lane;
-                float o = 0.f;
-                if (c < C) o = sigmoid_f(__ldg(q + (size_t)(5 + c) * HW));
-                bool hit = false;
-                for (int f0 = e - (e & 31); f0 < nE; f0 += 32) {
-                    const int f = f0 + lane;
-                    unsigned bal = __ballot_sync(kFullMask, f >= e && f < nE && s_list[f].cell == cell);
-                    while (bal) {
-                        const int f2 = f0 + __ffs(bal) - 1;
-                        bal &= bal - 1u;
-                        hit = hit || (s_gcls[s_list[f2].t] == c);
+                gv = (float)acc4;
+            } else {
+                const float o = sigmoid_f(__ldg(hbase + off));
+                float target = 1.0f;                       // objectness of an assigned cell (:149-150)
+                if (t > 4) {                               // class t-5: 0.95 if assigned to the cell, else 0.05 (:425-434)
+                    bool hit = false;
+                    while (f >= 0) {
+                        const uint32_t tn = s_list[f].t;
+                        hit = hit || (s_gcls[tl_entry_gt(tn)] == t - 5);
+                        f = tl_entry_next(tn);
                     }
+                    target = hit ? 0.95f : 0.05f;
                 }
-                if (c < C) g[(size_t)(5 + c) * HW] = (float)(((double)o - (hit ? (double)0.95f : (double)0.05f)) * inv_w);
+                gv = (float)(((double)o - (double)target) * inv_w);
             }
+            gbase[off] = gv;
         }
     }
 }
