@@ -67,7 +67,7 @@ def decode_head_padded(head: torch.Tensor, anchor_wh, num_classes: int, conf_thr
     A = ch // attrs
     aw = _host_f32(anchor_wh).reshape(A, 2)
     cells = A * H * W
-    with torch.cuda.device(head.device):
+    with _on_device(head.device):
         rows = torch.empty((N, cells, 7), dtype=torch.float32, device=head.device)
         count = torch.empty((N,), dtype=torch.int32, device=head.device)
         ids = torch.empty((N, cells), dtype=torch.int32, device=head.device) if want_ids else None
@@ -89,7 +89,7 @@ def nms_padded(cand0: torch.Tensor, count0: torch.Tensor, cand1: Optional[torch.
         cand1 = cand1.contiguous()
         s1 = cand1.shape[1]
     S = max(s0 + s1, 1)
-    with torch.cuda.device(cand0.device):
+    with _on_device(cand0.device):
         out = torch.empty((N, S, 7), dtype=torch.float32, device=cand0.device)
         oc = torch.empty((N,), dtype=torch.int32, device=cand0.device)
         oi = torch.empty((N, S), dtype=torch.int32, device=cand0.device) if want_idx else None
@@ -182,7 +182,7 @@ def pairwise(set_1: torch.Tensor, set_2: torch.Tensor, mode: int) -> torch.Tenso
     _require_cuda(set_2, "set_2")
     a = set_1.reshape(-1, 4).contiguous()
     b = set_2.reshape(-1, 4).contiguous()
-    with torch.cuda.device(a.device):
+    with _on_device(a.device):
         out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
         _lib.check(_lib.load().b200yolo_pairwise(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], mode,
                                                  out.data_ptr(), _stream(a)))
@@ -221,7 +221,7 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
     sa = _host_f32(anchors_all_scaled).reshape(-1, 2)
     m = np.ascontiguousarray(np.asarray(mask, dtype=np.int32))
     lib = _lib.load()
-    with torch.cuda.device(head.device):
+    with _on_device(head.device):
         # one allocation: 16 partial sums (f64) + the status word; the per-CTA workspace is cached per
         # (device, stream) and reused (calls on one stream are ordered, so reuse is safe)
         buf = torch.empty((_lib.S_COUNT + 1,), dtype=torch.float64, device=head.device)
@@ -254,7 +254,7 @@ def target_loss_backward(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Ten
     A = len(mask)
     sa = _host_f32(anchors_all_scaled).reshape(-1, 2)
     m = np.ascontiguousarray(np.asarray(mask, dtype=np.int32))
-    with torch.cuda.device(head.device):
+    with _on_device(head.device):
         grad = torch.empty_like(head)
         go = None
         if grad_out is not None:

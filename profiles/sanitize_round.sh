@@ -1,6 +1,11 @@
-set -x
-cd $GRAFT_REPO_ROOT
-PHASE_N=32 python profiles/phase_times.py cfg2 cfg2_sparse 2>&1 | tail -24
-PHASE_N=148 python profiles/phase_times.py cfg2 2>&1 | tail -12
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests -m gpu -x -q -k "fused_vs_golden or nms_vs_oracle or target_loss_vs_golden or large_logits or decode_head_vs_golden or one_class or coco80 or cfg1" > gpurun_out/sanitizer_memcheck.log 2>&1; echo memcheck rc=$?; tail -5 gpurun_out/sanitizer_memcheck.log
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests -m gpu -x -q -k "fused_vs_golden or target_loss_vs_golden or nms_ties" > gpurun_out/sanitizer_racecheck.log 2>&1; echo racecheck rc=$?; tail -8 gpurun_out/sanitizer_racecheck.log
+#!/bin/bash
+# compute-sanitizer over the GPU parity tests (memcheck: all kernels; racecheck: the shared-memory heavy ones).
+#   gpurun --timeout 1500 -- 'bash profiles/sanitize_round.sh'
+O=gpurun_out
+mkdir -p $O
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests -m gpu -x -q \
+  -k "golden or nms_vs_oracle or large_logits or one_class or coco80 or cfg1 or backward or map or seg or box_ciou or back_to_back or chain" \
+  > $O/sanitizer_memcheck.log 2>&1; echo memcheck rc=$?; tail -4 $O/sanitizer_memcheck.log
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests -m gpu -x -q \
+  -k "fused_vs_golden or target_loss_vs_golden or nms_ties or backward_vs_reference or map_vs_reference" \
+  > $O/sanitizer_racecheck.log 2>&1; echo racecheck rc=$?; grep -E "Race reported|RACECHECK SUMMARY" $O/sanitizer_racecheck.log | sort | uniq -c | sort -rn | head -12
