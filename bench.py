@@ -417,6 +417,33 @@ def run_b200(args, wl):
             extra["sparse_heads"] = {"images_per_s_per_gpu": N / (sms * 1e-3), "ms_per_step": sms,
                                      "kept_rows_per_image": float(np.mean(skept)) / N,
                                      "algorithmic_gbs": sbytes / (sms * 1e-3) / 1e9}
+            # the same launches replayed from a CUDA graph (one graph = one pass over the R input sets): at ~12 us per
+            # step the Python launch loop is the limiter, the graph shows what the GPU does
+            try:
+                gstream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(gstream):
+                    for i in range(R):
+                        sstep(i)
+                gstream.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=gstream):
+                    for i in range(R):
+                        sstep(i)
+                reps = max(2, args.steps // R)
+                for _ in range(2):
+                    graph.replay()
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(reps):
+                    graph.replay()
+                g1.record()
+                g1.synchronize()
+                gms = g0.elapsed_time(g1) / (reps * R)
+                extra["sparse_heads"]["cuda_graph"] = {"ms_per_step": gms, "images_per_s_per_gpu": N / (gms * 1e-3),
+                                                       "algorithmic_gbs": sbytes / (gms * 1e-3) / 1e9}
+            except Exception as e:  # noqa: BLE001
+                extra["sparse_heads"]["cuda_graph"] = {"error": repr(e)}
             del ssets
         # the same loop without programmatic dependent launch (debug flag 2): every launch waits for the previous
         # one to drain -- the serialized per-launch time, comparable with ncu's gpu__time_duration

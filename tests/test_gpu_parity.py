@@ -636,3 +636,39 @@ def test_seg_loss_vs_oracle_large(cuda_device):
     np.testing.assert_allclose([float(loss), obj, no_obj], oracle.seg_loss(x.numpy(), t.numpy()), rtol=RTOL)
     loss0, obj0, no0 = m(x.to(cuda_device), torch.zeros_like(t))     # no pixel >= 0.5: the mean of nothing is NaN
     assert np.isnan(obj0) and not np.isnan(no0)
+
+
+def test_cuda_graph_capture_and_replay(cuda_device):
+    """The C ABI promises graph-capturable calls (no allocation, no host sync inside): capture three fused launches
+    and a loss forward into one CUDA graph, replay it on new data, compare with eager calls."""
+    C = 20
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    N = 32
+    K = 3 * (121 + 484)
+    h0 = torch.empty((N, 75, 11, 11), device=cuda_device)
+    h1 = torch.empty((N, 75, 22, 22), device=cuda_device)
+    outs = [torch.empty((N, K, 7), device=cuda_device) for _ in range(3)]
+    cnts = [torch.empty((N,), dtype=torch.int32, device=cuda_device) for _ in range(3)]
+    a, b = make_heads(N, C, [(11, 11), (22, 22)], seed=90)
+    h0.copy_(a.to(cuda_device)); h1.copy_(b.to(cuda_device))
+    stream = torch.cuda.Stream(device=cuda_device)
+    with torch.cuda.stream(stream):
+        for thr, o, c in zip((0.3, 0.5, 0.1), outs, cnts):       # warm-up outside capture (function attributes, module load)
+            ops.decode_nms_padded(h0, h1, tables, C, thr, out=o, out_count=c)
+    stream.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        for thr, o, c in zip((0.3, 0.5, 0.1), outs, cnts):
+            ops.decode_nms_padded(h0, h1, tables, C, thr, out=o, out_count=c)
+    for seed in (91, 92):
+        a, b = make_heads(N, C, [(11, 11), (22, 22)], seed=seed)
+        h0.copy_(a.to(cuda_device)); h1.copy_(b.to(cuda_device))
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        for thr, o, c in zip((0.3, 0.5, 0.1), outs, cnts):
+            eo, ec = ops.decode_nms_padded(h0, h1, tables, C, thr)
+            assert torch.equal(c, ec)
+            for i in (0, 7, 31):
+                n = int(ec[i])
+                assert torch.equal(o[i, :n], eo[i, :n])
