@@ -672,3 +672,41 @@ def test_cuda_graph_capture_and_replay(cuda_device):
             for i in (0, 7, 31):
                 n = int(ec[i])
                 assert torch.equal(o[i, :n], eo[i, :n])
+
+
+def test_multi_wave_launches_back_to_back(cuda_device):
+    """More CTAs than the GPU holds at once (several waves), launched back to back with overlapping launches: the
+    dependent launch may only start once every CTA of the previous one has been scheduled; results must equal the
+    plain-stream-order ones and the CPU oracle."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    C, N = 20, 1100
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    sets = [tuple(h.to(cuda_device) for h in make_heads(N, C, [(11, 11), (22, 22)], seed=60 + k, conf_shift=-1.3 * k)) for k in range(2)]
+    lib = _lib.load()
+    expected = []
+    try:
+        lib.b200yolo_debug_set_flags(2)
+        for h0, h1 in sets:
+            o, c, i = ops.decode_nms_padded(h0, h1, tables, C, 0.3, want_idx=True)
+            expected.append((o.clone(), c.clone(), i.clone()))
+    finally:
+        lib.b200yolo_debug_set_flags(0)
+    K = 3 * (121 + 484)
+    out = torch.empty((N, K, 7), dtype=torch.float32, device=cuda_device)
+    cnt = torch.empty((N,), dtype=torch.int32, device=cuda_device)
+    idx = torch.empty((N, K), dtype=torch.int32, device=cuda_device)
+    for rep in range(6):
+        h0, h1 = sets[rep % 2]
+        ops.decode_nms_padded(h0, h1, tables, C, 0.3, want_idx=True, out=out, out_count=cnt, out_idx=idx)
+    torch.cuda.synchronize()
+    eo, ec, ei = expected[5 % 2]
+    assert torch.equal(cnt, ec)
+    for b in range(0, N, 37):
+        n = int(ec[b])
+        assert torch.equal(out[b, :n], eo[b, :n]) and torch.equal(idx[b, :n], ei[b, :n])
+    # a slice against the CPU oracle (same kept cells except near-threshold flips)
+    h0, h1 = sets[1]
+    sel = slice(1000, 1016)
+    o_det, o_ids = oracle.decode_nms(h0[sel].cpu().numpy(), h1[sel].cpu().numpy(), tables, C, 0.3)
+    same = sum(int(np.array_equal(ei[1000 + k, :int(ec[1000 + k])].cpu().numpy(), o_ids[k])) for k in range(16))
+    assert same >= 15
