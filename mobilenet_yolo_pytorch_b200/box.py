@@ -1,6 +1,7 @@
 """Drop-in for the reference's ``utils/box.py`` (``nms``, ``wh_to_x2y2``)."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import ops
@@ -38,6 +39,19 @@ def nms(preds, num_classes, return_indices: bool = False):
     p0, p1 = preds
     if len(p0) == 0:
         return ([], []) if return_indices else []
+    # both heads still undecoded (YOLOLoss.lazy_eval): the fused kernel does decode + NMS in one launch
+    if (isinstance(p0, ops.LazyCandidates) and isinstance(p1, ops.LazyCandidates) and p0.pending and p1.pending
+            and p0.conf_thr == p1.conf_thr and p0.num_classes == p1.num_classes == num_classes
+            and p0.head.shape[:2] == p1.head.shape[:2] and p0.head.device == p1.head.device):
+        tables = np.stack((p0.anchor_wh, p1.anchor_wh)).astype(np.float32)
+        res = ops.decode_nms_padded(p0.head, p1.head, tables, num_classes, p0.conf_thr, want_idx=return_indices)
+        counts = res[1].cpu().tolist()
+        dets = [res[0][b, :k] for b, k in enumerate(counts)]
+        if return_indices:
+            return dets, [res[2][b, :k] for b, k in enumerate(counts)]
+        return dets
+    p0 = p0.materialise() if isinstance(p0, ops.LazyCandidates) else p0
+    p1 = p1.materialise() if isinstance(p1, ops.LazyCandidates) else p1
     device = next((t.device for t in list(p0) + list(p1) if isinstance(t, torch.Tensor) and t.is_cuda), None)
     if device is None:
         raise RuntimeError("nms needs CUDA tensors: the b200yolo kernels have no CPU fallback")

@@ -47,10 +47,15 @@ def decode_nms(out0: torch.Tensor, out1: torch.Tensor, yolo_losses: Sequence, nu
     return lst
 
 
-def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_yolo=None, utils_eval_map=None) -> None:
+def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_yolo=None, utils_eval_map=None,
+                    fuse_inference: bool = False) -> None:
     """Swap the reference's entry points for the B200 ones inside already-imported
     reference modules.  Pass the modules you want patched."""
     from . import box as _box, iou as _iou, yolo_loss as _yl
+    if fuse_inference:
+        # YOLOLoss.forward(input) defers its decode, and nms() on the two heads runs the fused kernel: the reference's
+        # own call site (mbv2_yolo.py:158-160) becomes one launch
+        _yl.YOLOLoss.lazy_eval = True
     if models_yolo_loss is not None:
         models_yolo_loss.YOLOLoss = _yl.YOLOLoss
     if utils_box is not None:

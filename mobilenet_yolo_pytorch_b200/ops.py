@@ -7,7 +7,8 @@ path (north star: "no CPU fallback").
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from collections.abc import Sequence
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -18,7 +19,7 @@ NMS_IOU_THRESHOLD = 0.45  # utils/box.py:28
 _WORKSPACES = {}  # (device index, stream) -> cached target-loss workspace tensor
 
 
-def scaled_anchors(anchors: Sequence[Sequence[float]], img_size: Sequence[float]) -> np.ndarray:
+def scaled_anchors(anchors, img_size) -> np.ndarray:
     """yolo_loss.py:214: python-double division, rounded to fp32 when it enters a
     FloatTensor (pre_maps :67-68)."""
     return np.array([[aw / img_size[0], ah / img_size[1]] for aw, ah in anchors], dtype=np.float64).astype(np.float32)
@@ -46,6 +47,40 @@ class CandidateList(list):
     padded: torch.Tensor  # (N, stride, 7)
     counts: torch.Tensor  # (N,) int32, device
     ids: Optional[torch.Tensor]  # (N, stride) int32 cell ids, device
+
+
+class LazyCandidates(Sequence):
+    """What ``YOLOLoss.forward(input)`` returns when ``lazy_eval`` is on: the head tensor and the decode parameters
+    as they were at call time, with nothing launched yet.  ``utils.box.nms`` on two of these runs the FUSED kernel
+    (one launch instead of two decodes + NMS); any other use -- ``[b]``, iteration, ``.padded`` -- decodes first and
+    behaves like the eager list.  ``len()`` needs no work (one entry per image, yolo_loss.py:202-204)."""
+
+    def __init__(self, head: torch.Tensor, anchor_wh: np.ndarray, num_classes: int, conf_thr: float):
+        self.head, self.anchor_wh, self.num_classes, self.conf_thr = head, anchor_wh, int(num_classes), conf_thr
+        self._list: Optional[CandidateList] = None
+
+    @property
+    def pending(self) -> bool:
+        return self._list is None
+
+    def materialise(self) -> "CandidateList":
+        if self._list is None:
+            rows, count, ids = decode_head_padded(self.head, self.anchor_wh, self.num_classes, self.conf_thr, want_ids=True)
+            self._list = _as_list(rows, count, ids)
+        return self._list
+
+    def __len__(self) -> int:
+        return int(self.head.shape[0])
+
+    def __getitem__(self, i):
+        return self.materialise()[i]
+
+    def __iter__(self):
+        return iter(self.materialise())
+
+    padded = property(lambda self: self.materialise().padded)
+    counts = property(lambda self: self.materialise().counts)
+    ids = property(lambda self: self.materialise().ids)
 
 
 def _as_list(padded: torch.Tensor, counts_dev: torch.Tensor, ids: Optional[torch.Tensor] = None) -> CandidateList:
@@ -208,7 +243,7 @@ def pack_targets(targets, device) -> Tuple[torch.Tensor, torch.Tensor, int, List
 
 
 def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,
-                     mask: Sequence[int], num_classes: int, ignore_thr: float, iou_thr: float,
+                     mask, num_classes: int, ignore_thr: float, iou_thr: float,
                      want_assign: bool = False, max_gt: int = 0, cell_state: Optional[torch.Tensor] = None):
     """b200yolo_target_loss: returns (sums (16,) float64 device, status (1,) int32 device[, assign, terms]).
     ``cell_state``: optional (N, A*H*W) uint8 output consumed by ``target_loss_backward``."""
@@ -243,7 +278,7 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
 
 
 def target_loss_backward(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,
-                         mask: Sequence[int], num_classes: int, iou_thr: float, cell_state: torch.Tensor,
+                         mask, num_classes: int, iou_thr: float, cell_state: torch.Tensor,
                          sums: torch.Tensor, iou_weighting: float, grad_out: Optional[torch.Tensor] = None,
                          max_gt: int = 0) -> torch.Tensor:
     """b200yolo_target_loss_backward: d loss / d head, same shape as ``head``.  ``sums`` is the (all-reduced)

@@ -12,6 +12,8 @@ from . import _lib, ops
 
 
 class YOLOLoss(nn.Module):
+    lazy_eval = False
+
     """Same signature as the reference (yolo_loss.py:33).
 
     ``forward(input)``            -> list[N] of (n_b, 7) rows
@@ -25,6 +27,11 @@ class YOLOLoss(nn.Module):
     ``anchors`` and ``mask`` stay plain mutable attributes because the reference's
     callers overwrite them (mbv2_yolo.py:139-140, inference.py:46-47, train.py:149-150,
     417-418).
+
+    ``lazy_eval`` (class or instance attribute, default False): ``forward(input)`` then returns an
+    ``ops.LazyCandidates`` -- nothing is launched until it is used, and ``utils.box.nms`` on the two heads' results
+    (models/mbv2_yolo.py:158-160) runs the fused decode + NMS kernel, so the reference's own call sites get the
+    one-launch path.  ``patch_reference(..., fuse_inference=True)`` switches it on.
 
     ``process_group``: optional torch.distributed group.  When set, the batch is a
     shard of a data-parallel batch and the 16 partial sums are all-reduced (NCCL)
@@ -64,7 +71,10 @@ class YOLOLoss(nn.Module):
         """yolo_loss.py:295-317 (dead code upstream, kept for completeness): (iou - giou_term, iou)."""
         return ops.pairwise(box1, box2, 3), ops.pairwise(box1, box2, 2)
 
-    def get_pred_boxes(self, input: torch.Tensor) -> ops.CandidateList:
+    def get_pred_boxes(self, input: torch.Tensor):
+        if self.lazy_eval:
+            ops._require_cuda(input, "head")
+            return ops.LazyCandidates(input, self.head_anchor_wh(), self.num_classes, self.val_conf)
         rows, count, ids = ops.decode_head_padded(input, self.head_anchor_wh(), self.num_classes, self.val_conf,
                                                   want_ids=True)
         return ops._as_list(rows, count, ids)

@@ -710,3 +710,33 @@ def test_multi_wave_launches_back_to_back(cuda_device):
     o_det, o_ids = oracle.decode_nms(h0[sel].cpu().numpy(), h1[sel].cpu().numpy(), tables, C, 0.3)
     same = sum(int(np.array_equal(ei[1000 + k, :int(ec[1000 + k])].cpu().numpy(), o_ids[k])) for k in range(16))
     assert same >= 15
+
+
+def test_lazy_eval_routes_reference_call_site_to_fused_kernel(cuda_device):
+    """With YOLOLoss.lazy_eval the reference's own sequence  nms([loss0(out0), loss1(out1)], C)  (mbv2_yolo.py:158-160)
+    is ONE launch of the fused kernel; any other use of the per-head result decodes it and equals the eager list."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    C = 20
+    h0, h1 = make_heads(6, C, [(11, 11), (22, 22)], seed=8)
+    d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+    eager = [b200.YOLOLoss(VOC_ANCHORS, MASK[i], C, [352, 352], 0.6, 0.55, val_conf=0.3) for i in range(2)]
+    lazy = [b200.YOLOLoss(VOC_ANCHORS, MASK[i], C, [352, 352], 0.6, 0.55, val_conf=0.3) for i in range(2)]
+    for l in lazy:
+        l.lazy_eval = True
+    want = b200.nms((eager[0](d0), eager[1](d1)), C)
+    n0 = _lib.launch_count()
+    output = [lazy[i]((d0, d1)[i]) for i in range(2)]          # mbv2_yolo.py:158
+    assert _lib.launch_count() == n0 and len(output[0]) == 6   # nothing launched yet
+    got = b200.nms(output, C)                                  # :160
+    assert _lib.launch_count() == n0 + 1
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # using a lazy result directly decodes it
+    p1 = lazy[1](d1)
+    e1 = eager[1](d1)
+    assert all(torch.equal(a, b) for a, b in zip(p1, e1)) and torch.equal(p1[3], e1[3])
+    # mixed / already decoded inputs still work
+    got2 = b200.nms((lazy[0](d0), p1), C)
+    for a, b in zip(got2, want):
+        assert torch.equal(a, b)
