@@ -15,10 +15,10 @@ torch.distributed.  There is no CPU fallback.
 from . import _lib, dist, ops
 from .box import nms, wh_to_x2y2
 from .eval_mAP import calculate_mAP
-from .fused import decode_nms, decode_nms_padded, head_anchor_table, patch_reference
+from .fused import adjust_confidence, decode_nms, decode_nms_padded, head_anchor_table, patch_reference
 from .iou import find_intersection, find_jaccard_overlap, find_union
 from .seg_loss import SegLoss
 from .yolo_loss import YOLOLoss
 
 __all__ = ["YOLOLoss", "nms", "wh_to_x2y2", "find_intersection", "find_union", "find_jaccard_overlap", "decode_nms",
-           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops", "dist", "calculate_mAP", "SegLoss"]
+           "decode_nms_padded", "head_anchor_table", "patch_reference", "ops", "dist", "calculate_mAP", "SegLoss", "adjust_confidence"]

@@ -47,6 +47,20 @@ def decode_nms(out0: torch.Tensor, out1: torch.Tensor, yolo_losses: Sequence, nu
     return lst
 
 
+def adjust_confidence(gt_box_num, pred_box_num, conf):
+    """train.py:434-440: nudge ``val_conf`` towards 2-3 predictions per ground-truth box.  ``pred_box_num`` may be the
+    device count vector of ``decode_nms_padded`` (summed here, one D2H read) or a plain number."""
+    if isinstance(pred_box_num, torch.Tensor):
+        pred_box_num = int(pred_box_num.sum().item())
+    if isinstance(gt_box_num, torch.Tensor):
+        gt_box_num = int(gt_box_num.sum().item())
+    if pred_box_num > gt_box_num * 3:
+        conf = conf + 0.01
+    elif pred_box_num < gt_box_num * 2 and conf > 0.01:
+        conf = conf - 0.01
+    return conf
+
+
 def patch_reference(models_yolo_loss=None, utils_box=None, utils_iou=None, mbv2_yolo=None, utils_eval_map=None,
                     fuse_inference: bool = False) -> None:
     """Swap the reference's entry points for the B200 ones inside already-imported

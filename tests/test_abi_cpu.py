@@ -77,3 +77,14 @@ def test_no_cpu_fallback():
         l(torch.zeros(1, 21, 2, 2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.find_jaccard_overlap(torch.zeros(1, 4), torch.zeros(1, 4))
+
+
+def test_adjust_confidence_like_the_reference():
+    """train.py:434-440"""
+    import torch
+    import mobilenet_yolo_pytorch_b200 as m
+    assert m.adjust_confidence(10, 31, 0.3) == pytest.approx(0.31)
+    assert m.adjust_confidence(10, 19, 0.3) == pytest.approx(0.29)
+    assert m.adjust_confidence(10, 25, 0.3) == 0.3
+    assert m.adjust_confidence(10, 0, 0.01) == 0.01          # never below 0.01
+    assert m.adjust_confidence(10, torch.tensor([20, 15], dtype=torch.int32), 0.3) == pytest.approx(0.31)
