@@ -26,7 +26,7 @@ for rep in range(5):
     for _ in range(20):
         ops.decode_nms_host(hh0, hh1, tables, C, wl["conf"], device=0, out=ho, out_count=hc)
     rates.append(N * 20 / (time.perf_counter() - t0))
-print("chunk", os.environ.get("B200YOLO_HOST_CHUNK", "default(32)"), " ".join(f"{r / 1e3:.0f}k" for r in rates), "img/s")
+print("chunk", os.environ.get("B200YOLO_HOST_CHUNK", "default (N/4)"), " ".join(f"{r / 1e3:.0f}k" for r in rates), "img/s")
 # pure copy reference: the same bytes, one cudaMemcpy each way
 d0, d1 = torch.empty_like(hh0, device="cuda"), torch.empty_like(hh1, device="cuda")
 do = torch.empty_like(ho, device="cuda")
