@@ -140,12 +140,27 @@ bool shape_is(const DNParams &p) {
            p.head[1].W == SH::W1;
 }
 
+template <int S>
+bool head_is(const DNParams &p) {
+    using SH = ShapeT<S>;
+    return p.nheads == 1 && p.C == SH::C && p.head[0].HW == SH::HW0 && p.head[0].W == SH::W0;
+}
+
 template <int MODE, int THREADS>
 int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     if (MODE == MODE_FUSED && !(p.flags & 16)) {  // flag 16: force the runtime-shape path (tests)
         if (THREADS == 512 && shape_is<1>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 1 : 0>(p, L, dev, st);
         if (THREADS == 512 && shape_is<2>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 2 : 0>(p, L, dev, st);
         if (THREADS == 1024 && shape_is<3>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 1024) ? 3 : 0>(p, L, dev, st);
+    }
+    if (MODE == MODE_DECODE && THREADS == 512 && !(p.flags & 16)) {
+        constexpr bool kOn = (MODE == MODE_DECODE && THREADS == 512);
+        if (head_is<11>(p)) return launch_dn_t<MODE, THREADS, kOn ? 11 : 0>(p, L, dev, st);
+        if (head_is<12>(p)) return launch_dn_t<MODE, THREADS, kOn ? 12 : 0>(p, L, dev, st);
+        if (head_is<13>(p)) return launch_dn_t<MODE, THREADS, kOn ? 13 : 0>(p, L, dev, st);
+        if (head_is<14>(p)) return launch_dn_t<MODE, THREADS, kOn ? 14 : 0>(p, L, dev, st);
+        if (head_is<15>(p)) return launch_dn_t<MODE, THREADS, kOn ? 15 : 0>(p, L, dev, st);
+        if (head_is<16>(p)) return launch_dn_t<MODE, THREADS, kOn ? 16 : 0>(p, L, dev, st);
     }
     return launch_dn_t<MODE, THREADS, 0>(p, L, dev, st);
 }

@@ -63,6 +63,13 @@ template <int SHAPE> struct ShapeT { static constexpr int C = 0, HW0 = 0, W0 = 0
 template <> struct ShapeT<1> { static constexpr int C = 20, HW0 = 121, W0 = 11, HW1 = 484, W1 = 22; };  // VOC 352x352 (models/voc/config.yaml)
 template <> struct ShapeT<2> { static constexpr int C = 20, HW0 = 169, W0 = 13, HW1 = 676, W1 = 26; };  // 416x416 (inference.py:112)
 template <> struct ShapeT<3> { static constexpr int C = 10, HW0 = 240, W0 = 20, HW1 = 960, W1 = 40; };  // BDD100k 640x384, 10 classes
+// single heads of the same configurations (the stand-alone decode kernel, YOLOLoss.forward(input))
+template <> struct ShapeT<11> { static constexpr int C = 20, HW0 = 121, W0 = 11, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<12> { static constexpr int C = 20, HW0 = 484, W0 = 22, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<13> { static constexpr int C = 20, HW0 = 169, W0 = 13, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<14> { static constexpr int C = 20, HW0 = 676, W0 = 26, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<15> { static constexpr int C = 10, HW0 = 240, W0 = 20, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<16> { static constexpr int C = 10, HW0 = 960, W0 = 40, HW1 = 0, W1 = 0; };
 
 struct HeadDesc {
     const float *ptr;
@@ -927,7 +934,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
             }
         }
     }
-    constexpr bool kStaticShape = (MODE == MODE_FUSED && SH::C > 0);
+    constexpr bool kStaticShape = (MODE != MODE_NMS && SH::C > 0);
     if (MODE != MODE_DECODE) {
         for (int i = tid; i <= C * p.B; i += THREADS) s.cntb[i] = 0;
         for (int i = tid; i <= C; i += THREADS) s.flag[i] = 0;
@@ -937,6 +944,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
 
     if constexpr (MODE == MODE_NMS) {
         phase_load_rows<THREADS>(p, s, b);
+    } else if constexpr (kStaticShape && MODE == MODE_DECODE) {
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, false>(p, s, b, p.head[0], 0, 0);
     } else if constexpr (kStaticShape) {
         decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true>(p, s, b, p.head[0], 0, 0);
         decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false>(p, s, b, p.head[1], p.head[0].cells, 1);

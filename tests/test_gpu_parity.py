@@ -740,3 +740,28 @@ def test_lazy_eval_routes_reference_call_site_to_fused_kernel(cuda_device):
     got2 = b200.nms((lazy[0](d0), p1), C)
     for a, b in zip(got2, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,grid,anchors,img,mask", [
+    (20, (11, 11), VOC_ANCHORS, [352, 352], 0), (20, (22, 22), VOC_ANCHORS, [352, 352], 1),
+    (20, (13, 13), VOC_ANCHORS, [416, 416], 0), (20, (26, 26), VOC_ANCHORS, [416, 416], 1),
+    (10, (12, 20), BDD_ANCHORS, [640, 384], 0), (10, (24, 40), BDD_ANCHORS, [640, 384], 1),
+])
+def test_decode_head_compile_time_shapes_equal_runtime_path(C, grid, anchors, img, mask, cuda_device):
+    """YOLOLoss.forward(input) on the reference's head shapes runs a kernel with constant plane strides; debug flag 16
+    forces the runtime-stride kernel: bit-equal rows, counts and cell ids."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    head = make_heads(4, C, [grid], seed=33)[0].to(cuda_device)
+    aw = anchor_tables(anchors, img)[mask]
+    lib = _lib.load()
+    try:
+        lib.b200yolo_debug_set_flags(0)
+        a = ops.decode_head_padded(head, aw, C, 0.3, want_ids=True)
+        lib.b200yolo_debug_set_flags(16)
+        b = ops.decode_head_padded(head, aw, C, 0.3, want_ids=True)
+    finally:
+        lib.b200yolo_debug_set_flags(0)
+    cnt = a[1].cpu().numpy()
+    assert np.array_equal(cnt, b[1].cpu().numpy()) and cnt.sum() > 0
+    for i, k in enumerate(cnt):
+        assert torch.equal(a[0][i, :k], b[0][i, :k]) and torch.equal(a[2][i, :k], b[2][i, :k])
