@@ -21,8 +21,10 @@
 //                 conf = sigmoid(tc) > thr (yolo_loss.py:189,201); for passing cells:
 //                 class max / argmax (:198), box (:186-196,243-247) -> box[], cs[],
 //                 and the per-(class, score bucket) arrival index (one shared atomic).
-//   P2 scans      exclusive scan of the (class, bucket) histogram -> class segments
-//                 (box.py:20-22), kept-bitmap tiles, the round table.
+//   P2 scans      warp per class: exclusive scan of the class's score-bucket histogram; warp 0:
+//                 class segment starts (box.py:20-22).  Then warp 0 builds the kept-bitmap
+//                 tiles, the round table and the strip tasks WHILE the other warps sort (named
+//                 barrier between P3 and P4): the tables are off the critical path.
 //   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort of
 //                 torchvision.ops.nms) into their (class, bucket) segment.
 //   P4 rank       rank inside the bucket -> `sord`: sorted position -> {shared-memory
@@ -49,6 +51,9 @@
 //
 // The stand-alone decode (P1 + ordered compaction + store) and NMS (load rows,
 // P2..P6) kernels back YOLOLoss.forward(input) and utils.box.nms separately.
+//
+// Consecutive launches overlap (programmatic dependent launch, see pdl_trigger / pdl_wait below): a launch
+// starts on the SM slots its predecessor leaves free and streams its heads under the predecessor's NMS.
 #pragma once
 #include "common.cuh"
 
