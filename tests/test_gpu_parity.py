@@ -765,3 +765,22 @@ def test_decode_head_compile_time_shapes_equal_runtime_path(C, grid, anchors, im
     assert np.array_equal(cnt, b[1].cpu().numpy()) and cnt.sum() > 0
     for i, k in enumerate(cnt):
         assert torch.equal(a[0][i, :k], b[0][i, :k]) and torch.equal(a[2][i, :k], b[2][i, :k])
+
+
+def test_two_anchors_per_head_and_small_grids(cuda_device):
+    """Not the reference's 3-anchor heads: A = 2, C = 5, odd non-square grids -- decode + NMS and the loss path."""
+    A, C = 2, 5
+    anchors = [[30, 60], [80, 40], [10, 20], [25, 15]]
+    masks = [[0, 1], [2, 3]]
+    img = [144, 112]
+    g = torch.Generator().manual_seed(12)
+    h0 = torch.randn(3, A * (5 + C), 7, 9, generator=g)
+    h1 = torch.randn(3, A * (5 + C), 14, 18, generator=g)
+    sa = oracle.scaled_anchors(anchors, img)
+    tables = np.stack([sa[masks[0]], sa[masks[1]]])
+    check_fused_against_oracle(h0, h1, tables, C, 0.3, cuda_device)
+    targets = synth_targets(3, [4, 0, 11], C, seed=2)
+    compare_loss_with_oracle(h1.numpy(), targets, anchors, masks[1], C, img, 0.6, 0.5, 0.02, cuda_device)
+    gp, _ = gpu_loss_grad(h1.numpy(), targets, anchors, masks[1], C, img, 0.6, 0.5, 0.02, cuda_device)
+    go = oracle.target_loss_backward(h1.numpy(), targets, anchors, masks[1], C, img, 0.6, 0.5, 0.02)
+    assert np.array_equal(gp != 0, go != 0) and np.abs(gp - go).max() <= GRAD_TOL * np.abs(go).max()
