@@ -505,6 +505,20 @@ def run_b200(args, wl):
                                        "ms_per_step": float(tg.item()),
                                        "bytes_gathered_per_rank": int(world * N * (K + 1) * 28)}
 
+            # compact form: kept rows only (one host read of the per-rank totals to size the buffer)
+            def cstep(i):
+                step(i)
+                b2dist.all_gather_detections_compact(out, cnt)
+            for i in range(3):
+                cstep(i)
+            barrier()
+            cms = time_loop(cstep, max(10, args.steps // 4)) / max(10, args.steps // 4)
+            tc = torch.tensor([cms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            extra["with_allgather_compact"] = {"images_per_s": world * N / (float(tc.item()) * 1e-3),
+                                               "ms_per_step": float(tc.item()),
+                                               "bytes_gathered_per_rank": int(world * kept_per_launch * 28)}
+
     if rank == 0:
         peaks = {}
         try:

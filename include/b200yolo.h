@@ -117,6 +117,13 @@ int b200yolo_decode_nms_host(const float *head0, const float *head1, int N, int 
                              float *out, int *out_count, int device);
 
 /*
+ * Compaction of fixed-stride detections for the data-parallel all-gather (no counterpart in the reference, which is
+ * single-GPU): packed dev [sum count][7] gets the kept rows of image 0, 1, ... back to back (capacity N*K rows is
+ * always enough), offsets dev int32 [N+1] the first packed row of every image (offsets[N] = total).
+ */
+int b200yolo_compact_rows(const float *dets, const int *count, int N, int K, float *packed, int *offsets, void *stream);
+
+/*
  * utils.iou.find_intersection / find_union / find_jaccard_overlap
  * (utils/iou.py:4-13, 14-31, 32-49).  mode 0 / 1 / 2.  set1 dev [n1][4],
  * set2 dev [n2][4] xyxy; out dev [n1][n2].  mode 3 / 4: YOLOLoss.box_giou / box_ciou value

@@ -587,6 +587,21 @@ int b200yolo_map_eval(const float *det_boxes, const int *det_labels, const float
     return 0;
 }
 
+int b200yolo_compact_rows(const float *dets, const int *count, int N, int K, float *packed, int *offsets, void *stream) {
+    if (N < 0 || K < 1) return fail(B200YOLO_EINVAL, "compact_rows: bad shape");
+    if (!offsets || (N > 0 && (!dets || !count || !packed))) return fail(B200YOLO_EINVAL, "compact_rows: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    compact_offsets_kernel<<<1, 1024, 0, st>>>(count, N, K, offsets);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    if (N > 0) {
+        compact_rows_kernel<<<N, 128, 0, st>>>(dets, count, offsets, K, packed);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
 size_t b200yolo_target_loss_workspace_bytes(int N) { return (size_t)(N > 0 ? N : 1) * kTLMaxSplit * kTLSums * sizeof(double); }
 
 int b200yolo_loss_finalize(const double *s, float iou_weighting, double *r) {

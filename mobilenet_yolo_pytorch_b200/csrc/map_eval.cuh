@@ -210,4 +210,44 @@ __global__ void __launch_bounds__(kMapClassThreads) map_class_kernel(const MapPa
     }
 }
 
+// ---------------------------------------------------------------------------
+// Compaction of fixed-stride detections (N, K, 7) + counts into packed rows + offsets: the send buffer of the
+// data-parallel all-gather carries only kept rows (dist.all_gather_detections_compact).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_offsets_kernel(const int *count, int N, int K, int *offsets) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < N; b0 += 1024) {
+        const int b = b0 + tid;
+        const int v = (b < N) ? min(max(count[b], 0), K) : 0;
+        const int inc = warp_inclusive_scan(v, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_warp[lane];
+            const int winc = warp_inclusive_scan(w, lane);
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (b < N) offsets[b] = carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[warp] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[N] = s_carry;
+}
+
+__global__ void __launch_bounds__(128) compact_rows_kernel(const float *dets, const int *count, const int *offsets, int K,
+                                                           float *packed) {
+    const int b = blockIdx.x;
+    const int n = min(max(count[b], 0), K) * 7;
+    const float *src = dets + (size_t)b * K * 7;
+    float *dst = packed + (size_t)offsets[b] * 7;
+    for (int f = threadIdx.x; f < n; f += 128) dst[f] = __ldg(src + f);
+}
+
 }  // namespace b200yolo

@@ -37,6 +37,27 @@ def all_gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None) 
     return out[:, :K], out[:, K, 0].to(torch.int32)
 
 
+def all_gather_detections_compact(dets: torch.Tensor, counts: torch.Tensor, group=None):
+    """Like ``all_gather_detections`` but only kept rows travel: the shard's rows are packed back to back on the device
+    (``b200yolo_compact_rows``), the per-rank totals and per-image counts are gathered (tiny), and ONE all-gather moves
+    ``max total`` rows per rank -- 0.5 MB instead of 13 MB per rank for trained-like heads at 256 images.
+    Returns (rows (sum of totals, 7) in rank-then-image order, counts (world*n_local,) int32)."""
+    from . import ops
+    world = dist.get_world_size(group)
+    n = dets.shape[0]
+    packed, offsets = ops.compact_rows(dets, counts)
+    totals = torch.empty((world,), dtype=torch.int32, device=dets.device)
+    dist.all_gather_into_tensor(totals, offsets[n:n + 1].contiguous(), group=group)
+    all_counts = torch.empty((world * n,), dtype=torch.int32, device=dets.device)
+    dist.all_gather_into_tensor(all_counts, counts.contiguous(), group=group)
+    tot = totals.cpu().tolist()                      # the one host sync: buffer sizes
+    m = max(max(tot), 1)
+    recv = torch.empty((world, m, 7), dtype=torch.float32, device=dets.device)
+    dist.all_gather_into_tensor(recv, packed[:m].contiguous(), group=group)
+    rows = torch.cat([recv[r, :tot[r]] for r in range(world)], 0)
+    return rows, all_counts
+
+
 def all_reduce_loss_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return sums

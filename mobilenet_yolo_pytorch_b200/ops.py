@@ -212,6 +212,20 @@ def decode_nms_host(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_cl
     return out, out_count
 
 
+def compact_rows(dets: torch.Tensor, counts: torch.Tensor):
+    """b200yolo_compact_rows: (N, K, 7) fixed-stride detections + (N,) counts -> (packed (N*K, 7) whose first
+    offsets[N] rows are the kept rows back to back, offsets (N+1,) int32), both on the device, no host sync."""
+    _require_cuda(dets, "dets")
+    dets = dets.contiguous()
+    N, K, _ = dets.shape
+    with _on_device(dets.device):
+        packed = torch.empty((max(N * K, 1), 7), dtype=torch.float32, device=dets.device)
+        offsets = torch.empty((N + 1,), dtype=torch.int32, device=dets.device)
+        _lib.check(_lib.load().b200yolo_compact_rows(dets.data_ptr(), counts.data_ptr(), N, K, packed.data_ptr(),
+                                                     offsets.data_ptr(), _stream(dets)))
+    return packed, offsets
+
+
 def pairwise(set_1: torch.Tensor, set_2: torch.Tensor, mode: int) -> torch.Tensor:
     _require_cuda(set_1, "set_1")
     _require_cuda(set_2, "set_2")

@@ -49,10 +49,11 @@ def _worker(rank, world, port, N, q):
                                 process_group=dist.group.WORLD) for i in range(2)]
         dets, cnt = b200.decode_nms_padded(h0[lo:hi].to(dev), h1[lo:hi].to(dev), losses)
         g_dets, g_cnt = b200.dist.all_gather_detections(dets, cnt)
+        c_rows, c_cnt = b200.dist.all_gather_detections_compact(dets, cnt)
         x = h1[lo:hi].to(dev).requires_grad_(True)
         tup = losses[1](x, targets[lo:hi])
         tup[0].backward()
-        q.put((rank, g_dets.cpu().numpy(), g_cnt.cpu().numpy(), float(tup[0].detach()), [float(v) for v in tup[1:4]] + [float(tup[4]), tup[5], tup[6]],
+        q.put((rank, c_rows.cpu().numpy(), c_cnt.cpu().numpy(), g_dets.cpu().numpy(), g_cnt.cpu().numpy(), float(tup[0].detach()), [float(v) for v in tup[1:4]] + [float(tup[4]), tup[5], tup[6]],
                x.grad.cpu().numpy(), lo, hi))
     finally:
         dist.destroy_process_group()
@@ -86,8 +87,10 @@ def test_two_gpu_shards_equal_single_gpu():
     tup = losses[1](x, targets)
     tup[0].backward()
     grad = x.grad.cpu().numpy()
-    for rank, g_dets, g_cnt, loss, stats, g, lo, hi in got:
-        assert np.array_equal(g_cnt, cnt)
+    want_rows = np.concatenate([dets[b, :cnt[b]] for b in range(N)], 0)
+    for rank, c_rows, c_cnt, g_dets, g_cnt, loss, stats, g, lo, hi in got:
+        assert np.array_equal(g_cnt, cnt) and np.array_equal(c_cnt, cnt)
+        assert np.array_equal(c_rows, want_rows)            # compact gather: kept rows only, rank-then-image order
         for b in range(N):
             assert np.array_equal(g_dets[b, :cnt[b]], dets[b, :cnt[b]])
         np.testing.assert_allclose(loss, float(tup[0].detach()), rtol=1e-6)

@@ -784,3 +784,17 @@ def test_two_anchors_per_head_and_small_grids(cuda_device):
     gp, _ = gpu_loss_grad(h1.numpy(), targets, anchors, masks[1], C, img, 0.6, 0.5, 0.02, cuda_device)
     go = oracle.target_loss_backward(h1.numpy(), targets, anchors, masks[1], C, img, 0.6, 0.5, 0.02)
     assert np.array_equal(gp != 0, go != 0) and np.abs(gp - go).max() <= GRAD_TOL * np.abs(go).max()
+
+
+def test_compact_rows(cuda_device):
+    """b200yolo_compact_rows: the send buffer of the compact all-gather (kept rows back to back + offsets)."""
+    r = np.random.RandomState(4)
+    N, K = 1500, 37                       # more images than one scan chunk
+    dets = r.rand(N, K, 7).astype(np.float32)
+    cnt = r.randint(0, K + 1, N).astype(np.int32)
+    cnt[:3] = [0, K, 0]
+    packed, offs = ops.compact_rows(torch.from_numpy(dets).to(cuda_device), torch.from_numpy(cnt).to(cuda_device))
+    want_off = np.concatenate(([0], np.cumsum(cnt))).astype(np.int32)
+    assert np.array_equal(offs.cpu().numpy(), want_off)
+    want = np.concatenate([dets[b, :cnt[b]] for b in range(N)], 0)
+    assert np.array_equal(packed[:want_off[-1]].cpu().numpy(), want)
