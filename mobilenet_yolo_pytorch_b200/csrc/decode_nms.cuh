@@ -753,10 +753,15 @@ __device__ __forceinline__ uint32_t block_fast(const uint2 *ordc, int ncol, cons
     // past the class (the next class's entries, or the NaN-area padding after the last one): their bits are
     // dropped below, a NaN never lowers m, and a false "too close" only costs the exact path
     const int n8 = ncol & ~7, rem = ncol - n8;
-#pragma unroll 1
-    for (int k0 = 0; k0 < n8; k0 += 8) {
+    if (ncol == 32) {  // a full tile: one straight-line block
 #pragma unroll
-        for (int k = 0; k < 8; ++k) pair_step(ordc[k0 + k], R, rta, bits, m);
+        for (int k = 0; k < 32; ++k) pair_step(ordc[k], R, rta, bits, m);
+    } else {
+#pragma unroll 1
+        for (int k0 = 0; k0 < n8; k0 += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pair_step(ordc[k0 + k], R, rta, bits, m);
+        }
     }
     int nr = n8;
     if (rem > 4) {
