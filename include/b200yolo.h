@@ -107,6 +107,16 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
                         int *out_count, int *out_idx, void *stream);
 
 /*
+ * The same for channels-last heads: head tensors laid out (N, H, W, A*(5+C)) in memory -- what cuDNN prefers for the
+ * last convolution of the head (models/mbv2_yolo.py:82,144,153) -- so no NCHW copy is needed before the
+ * post-processing.  Same results, bit for bit, as b200yolo_decode_nms on the permuted
+ * tensors.  Limits: 5+C <= 32; B200YOLO_EUNSUPPORTED when the image leaves no shared memory for the staging.
+ */
+int b200yolo_decode_nms_nhwc(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                             int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
+                             int *out_count, int *out_idx, void *stream);
+
+/*
  * Same computation from HOST buffers (the reference-facing call bench.py times
  * as "e2e"): heads are copied host->device in image chunks on two streams,
  * post-processed, and detections + counts copied back, overlapped.  Pinned

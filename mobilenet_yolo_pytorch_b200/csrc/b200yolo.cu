@@ -148,7 +148,18 @@ bool head_is(const DNParams &p) {
 
 template <int MODE, int THREADS>
 int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
-    if (MODE == MODE_FUSED && !(p.flags & 16)) {  // flag 16: force the runtime-shape path (tests)
+    if (MODE == MODE_FUSED && p.nhwc) {
+        // the channels-last decode stages up to 16 cells per warp in the part of U behind clsidx
+        const uint32_t Kp = align_up((uint32_t)(p.K > 0 ? p.K : 1), 32);
+        const uint32_t free_bytes = (L.u_bytes > 4 * Kp) ? L.u_bytes - 4 * Kp : 0;
+        int ncs = (int)(free_bytes / ((uint32_t)(THREADS / 32) * (uint32_t)p.attrs * sizeof(float)));
+        if (ncs > kNhwcCells) ncs = kNhwcCells;
+        if (ncs < 8)
+            return fail(B200YOLO_EUNSUPPORTED, "decode_nms_nhwc: %d cells per image leave no room for the channels-last staging "
+                        "(convert the heads to NCHW)", p.K);
+        p.nhwc = ncs;
+    }
+    if (MODE == MODE_FUSED && !(p.flags & 16) && !p.nhwc) {  // flag 16: force the runtime-shape path (tests)
         if (THREADS == 512 && shape_is<1>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 1 : 0>(p, L, dev, st);
         if (THREADS == 512 && shape_is<2>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 2 : 0>(p, L, dev, st);
         if (THREADS == 1024 && shape_is<3>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 1024) ? 3 : 0>(p, L, dev, st);
@@ -269,6 +280,31 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
     p.conf_thr = conf_thr;
     p.iou = make_thr(iou_thr);
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
+}
+
+int b200yolo_decode_nms_nhwc(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                             int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
+                             int *out_count, int *out_idx, void *stream) {
+    if (!head0 || !head1 || !anchor_wh || !out || !out_count) return fail(B200YOLO_EINVAL, "decode_nms_nhwc: null pointer");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
+        return fail(B200YOLO_EINVAL, "decode_nms_nhwc: bad shape");
+    if (5 + C > kNhwcMaxAttrs)
+        return fail(B200YOLO_EUNSUPPORTED, "decode_nms_nhwc: more than %d classes (convert the heads to NCHW)", kNhwcMaxAttrs - 5);
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_nhwc: NaN threshold");
+    const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
+    if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms_nhwc: more than 65535 cells per image");
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    fill_head(p.head[0], head0, A, H0, W0, anchor_wh);
+    fill_head(p.head[1], head1, A, H1, W1, anchor_wh + 2 * A);
+    p.nheads = 2;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.K = (int)cells;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(iou_thr);
+    p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    p.nhwc = 1;
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
 }
 

@@ -91,6 +91,8 @@ struct DNParams {
     int K;               // candidate slots per image = row stride of out / out_idx
     int B;               // score buckets per class of the counting sort (power of two)
     int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads
+    int nhwc;            // > 0: heads are channels-last, (N, H, W, A*(5+C)) in memory (fused mode only); the value is the
+                         // number of cells a warp stages per step (8..16, what the free shared memory allows)
     unsigned long long *dbg;  // optional [N][32] phase time stamps (16 x globaltimer ns, 16 x SM clock), NULL in production
     float conf_thr;
     IouThr iou;
@@ -501,6 +503,83 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
             if (lane == 0 && local < cells) s.passbits[local >> 5] = bal;
         }
         if (MODE == MODE_FUSED) stamp_if(dbg_on, p, b, 8 + min(3, hh + base / THREADS));
+    }
+}
+
+// Channels-last heads (what cuDNN prefers for the head's last convolution): in memory the image is
+// (H, W, A*(5+C)), so the 5+C values of a cell are contiguous and the cells follow each other in (j, i, a) order.
+// A warp copies up to 16 consecutive cells (contiguous floats: perfectly coalesced, all loads in flight before
+// the first store) into its shared-memory scratch; the first lanes then read one cell each at stride 5+C (conflict-free
+// for the odd 5+C of the reference's configurations) and run the same arithmetic as the planar paths.  The records
+// are still indexed by the reference's candidate order (a, j, i).
+constexpr int kNhwcCells = 16;      // cells per warp step, at most
+constexpr int kNhwcMaxAttrs = 32;   // 5 + C <= 32 on this path
+
+template <int THREADS>
+__device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, float *scr_base) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = p.C, attrs = p.attrs, A = p.A;
+    const int cells = hd.cells;
+    const float *hb = hd.ptr + (size_t)b * cells * attrs;  // uniform
+    const int ncs = p.nhwc;                                // cells per warp step
+    float *scr = scr_base + warp * (ncs * attrs);
+    constexpr int kLoads = kNhwcCells * kNhwcMaxAttrs / 32;  // 16 words per lane at most
+#pragma unroll 1
+    for (int base = warp * ncs; base < cells; base += (THREADS / 32) * ncs) {
+        const int nc = min(ncs, cells - base);
+        const int nw = nc * attrs;
+        const float *src = hb + (size_t)base * attrs;
+        float v[kLoads];
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k) {
+            const int w = 32 * k + lane;
+            v[k] = (w < nw) ? __ldcs(src + w) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k) {
+            const int w = 32 * k + lane;
+            if (w < nw) scr[w] = v[k];
+        }
+        __syncwarp();
+        if (lane < nc) {
+            const int m = base + lane;                       // memory order: (j*W + i)*A + a
+            const int pos = m / A, a = m - pos * A;
+            const int j = fastdiv(pos, hd.magicW), i = pos - j * hd.W;
+            const int cid = cid0 + a * hd.HW + pos;          // reference order: (a*H + j)*W + i
+            const float *x = scr + lane * attrs;
+            const float conf = sigmoid_fast(x[4]);          // yolo_loss.py:189,197
+            if (conf > p.conf_thr) {                        // :201
+                float m1 = x[5];
+                for (int c = 1; c < C; ++c) m1 = fmaxf(m1, x[5 + c]);
+                float best;
+                const float win = tie_window(m1, &best);
+                const float lo = __fsub_rn(m1, win);
+                int bi = -1, nnear = 0;
+                for (int c = 0; c < C; ++c) {
+                    const bool nr = x[5 + c] >= lo;
+                    if (nr && bi < 0) bi = c;
+                    nnear += nr ? 1 : 0;
+                }
+                if (C > 1 && nnear != 1) {                  // near tie (or NaN logits): sigmoid first, then first maximum (:198)
+                    float bs = -1.0f;
+                    int bc = 0;
+                    for (int c = 0; c < C; ++c) {
+                        const float xv = x[5 + c];
+                        if (!(xv < lo)) {
+                            const float sg = sigmoid_fast(xv);
+                            if (sg > bs) { bs = sg; bc = c; }
+                        }
+                    }
+                    if (bs < 0.0f) { bs = sigmoid_fast(m1); bc = max(bi, 0); }
+                    best = bs;
+                    bi = bc;
+                }
+                emit_candidate<MODE_FUSED>(p, s, hd, cid, a, i, j, x[0], x[1], x[2], x[3], conf, best, max(bi, 0));
+            } else {
+                s.clsidx[cid] = 0xffffffffu;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -960,8 +1039,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true>(p, s, b, p.head[0], 0, 0);
         decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false>(p, s, b, p.head[1], p.head[0].cells, 1);
     } else {
-        decode_head_rt<THREADS, MODE>(p, s, b, p.head[0], 0, 0);
-        if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE>(p, s, b, p.head[1], p.head[0].cells, 1);
+        if (MODE == MODE_FUSED && p.nhwc) {
+            // scratch: the part of U that is free during the decode (behind clsidx); the host checked that it fits
+            float *scr = reinterpret_cast<float *>(smem_raw + L.U + 4 * align_up((uint32_t)(K > 0 ? K : 1), 32));
+            decode_head_nhwc<THREADS>(p, s, b, p.head[0], 0, scr);
+            decode_head_nhwc<THREADS>(p, s, b, p.head[1], p.head[0].cells, scr);
+        } else {
+            decode_head_rt<THREADS, MODE>(p, s, b, p.head[0], 0, 0);
+            if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE>(p, s, b, p.head[1], p.head[0].cells, 1);
+        }
     }
     __syncthreads();
     stamp(p, b, 1);

@@ -158,13 +158,18 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
     Pre-allocated outputs may be passed (CUDA-graph capture, NCCL send buffers)."""
     _require_cuda(head0, "head0")
     _require_cuda(head1, "head1")
-    if not head0.is_contiguous():
-        head0 = head0.contiguous()
-    if not head1.is_contiguous():
-        head1 = head1.contiguous()
+    attrs = 5 + num_classes
+    # channels-last heads (what cuDNN prefers) are consumed as they are; anything else becomes NCHW-contiguous
+    nhwc = (attrs <= 32 and head0.dim() == 4 and not head0.is_contiguous() and not head1.is_contiguous()
+            and head0.is_contiguous(memory_format=torch.channels_last)
+            and head1.is_contiguous(memory_format=torch.channels_last))
+    if not nhwc:
+        if not head0.is_contiguous():
+            head0 = head0.contiguous()
+        if not head1.is_contiguous():
+            head1 = head1.contiguous()
     N, ch, H0, W0 = head0.shape
     N1, ch1, H1, W1 = head1.shape
-    attrs = 5 + num_classes
     if N1 != N or ch1 != ch or ch % attrs:
         raise RuntimeError("head shapes do not match (N, A*(5+C), H, W) for both heads")
     A = ch // attrs
@@ -179,10 +184,13 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
             out_count = torch.empty((N,), dtype=torch.int32, device=dev)
         if want_idx and out_idx is None:
             out_idx = torch.empty((N, K), dtype=torch.int32, device=dev)
-        rc = _lib.load().b200yolo_decode_nms(
-            head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
-            float(np.float32(conf_thr)), float(iou_thr), out.data_ptr(), out_count.data_ptr(),
-            out_idx.data_ptr() if want_idx else None, torch.cuda.current_stream(dev).cuda_stream)
+        lib = _lib.load()
+        args = (N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data, float(np.float32(conf_thr)), float(iou_thr),
+                out.data_ptr(), out_count.data_ptr(), out_idx.data_ptr() if want_idx else None,
+                torch.cuda.current_stream(dev).cuda_stream)
+        rc = (lib.b200yolo_decode_nms_nhwc if nhwc else lib.b200yolo_decode_nms)(head0.data_ptr(), head1.data_ptr(), *args)
+        if rc == -2 and nhwc:  # no shared memory left for the channels-last staging: NCHW copies, then the planar kernel
+            rc = lib.b200yolo_decode_nms(head0.contiguous().data_ptr(), head1.contiguous().data_ptr(), *args)
         if rc:
             _lib.check(rc)
     return (out, out_count, out_idx) if want_idx else (out, out_count)

@@ -798,3 +798,29 @@ def test_compact_rows(cuda_device):
     assert np.array_equal(offs.cpu().numpy(), want_off)
     want = np.concatenate([dets[b, :cnt[b]] for b in range(N)], 0)
     assert np.array_equal(packed[:want_off[-1]].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("C,grids,anchors,img,thr,shift", [
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0),
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, -2.6),
+    (10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384], 0.3, 0.0),
+    (3, [(5, 7), (10, 14)], VOC_ANCHORS, [224, 160], 0.3, 0.0),
+])
+def test_channels_last_heads_equal_nchw(C, grids, anchors, img, thr, shift, cuda_device):
+    """SURVEY 8 f3: channels-last head tensors are consumed without an NCHW copy (b200yolo_decode_nms_nhwc);
+    detections, counts and kept cell ids equal the planar kernel's bit for bit."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    h0, h1 = make_heads(9, C, grids, seed=71, conf_shift=shift)
+    tables = anchor_tables(anchors, img)
+    d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+    want = ops.decode_nms_padded(d0, d1, tables, C, thr, want_idx=True)
+    c0 = d0.contiguous(memory_format=torch.channels_last)
+    c1 = d1.contiguous(memory_format=torch.channels_last)
+    assert not c0.is_contiguous()
+    n0 = _lib.launch_count()
+    got = ops.decode_nms_padded(c0, c1, tables, C, thr, want_idx=True)
+    assert _lib.launch_count() == n0 + 1
+    cnt = want[1].cpu().numpy()
+    assert np.array_equal(cnt, got[1].cpu().numpy()) and cnt.sum() > 0
+    for i, k in enumerate(cnt):
+        assert torch.equal(want[0][i, :k], got[0][i, :k]) and torch.equal(want[2][i, :k], got[2][i, :k])
