@@ -149,15 +149,20 @@ bool head_is(const DNParams &p) {
 template <int MODE, int THREADS>
 int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     if (MODE == MODE_FUSED && p.nhwc) {
-        // the channels-last decode stages up to 16 cells per warp in the part of U behind clsidx
+        // the channels-last decode stages 32 cells per warp in the part of U behind clsidx: as many warps as fit
         const uint32_t Kp = align_up((uint32_t)(p.K > 0 ? p.K : 1), 32);
         const uint32_t free_bytes = (L.u_bytes > 4 * Kp) ? L.u_bytes - 4 * Kp : 0;
-        int ncs = (int)(free_bytes / ((uint32_t)(THREADS / 32) * (uint32_t)p.attrs * sizeof(float)));
-        if (ncs > kNhwcCells) ncs = kNhwcCells;
-        if (ncs < 8)
+        int nwarps = (int)(free_bytes / (32u * (uint32_t)p.attrs * sizeof(float)));
+        if (nwarps > THREADS / 32) nwarps = THREADS / 32;
+        if (nwarps < 2)
             return fail(B200YOLO_EUNSUPPORTED, "decode_nms_nhwc: %d cells per image leave no room for the channels-last staging "
                         "(convert the heads to NCHW)", p.K);
-        p.nhwc = ncs;
+        p.nhwc = nwarps;
+        if (THREADS == 512 && !(p.flags & 16)) {
+            constexpr bool kOn = (MODE == MODE_FUSED && THREADS == 512);
+            if (p.C == 20) return launch_dn_t<MODE, THREADS, kOn ? 21 : 0>(p, L, dev, st);
+            if (p.C == 10) return launch_dn_t<MODE, THREADS, kOn ? 22 : 0>(p, L, dev, st);
+        }
     }
     if (MODE == MODE_FUSED && !(p.flags & 16) && !p.nhwc) {  // flag 16: force the runtime-shape path (tests)
         if (THREADS == 512 && shape_is<1>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 1 : 0>(p, L, dev, st);

@@ -75,6 +75,10 @@ template <> struct ShapeT<13> { static constexpr int C = 20, HW0 = 169, W0 = 13,
 template <> struct ShapeT<14> { static constexpr int C = 20, HW0 = 676, W0 = 26, HW1 = 0, W1 = 0; };
 template <> struct ShapeT<15> { static constexpr int C = 10, HW0 = 240, W0 = 20, HW1 = 0, W1 = 0; };
 template <> struct ShapeT<16> { static constexpr int C = 10, HW0 = 960, W0 = 40, HW1 = 0, W1 = 0; };
+// channels-last heads (decode_head_nhwc): only the class count is a compile-time constant
+template <> struct ShapeT<21> { static constexpr int C = 20, HW0 = 0, W0 = 0, HW1 = 0, W1 = 0; };
+template <> struct ShapeT<22> { static constexpr int C = 10, HW0 = 0, W0 = 0, HW1 = 0, W1 = 0; };
+template <int SHAPE> struct ShapeIsNhwc { static constexpr bool value = SHAPE >= 20 && SHAPE < 30; };
 
 struct HeadDesc {
     const float *ptr;
@@ -92,7 +96,7 @@ struct DNParams {
     int B;               // score buckets per class of the counting sort (power of two)
     int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads
     int nhwc;            // > 0: heads are channels-last, (N, H, W, A*(5+C)) in memory (fused mode only); the value is the
-                         // number of cells a warp stages per step (8..16, what the free shared memory allows)
+                         // number of warps that stage + decode (32 cells each per step; what the free shared memory allows)
     unsigned long long *dbg;  // optional [N][32] phase time stamps (16 x globaltimer ns, 16 x SM clock), NULL in production
     float conf_thr;
     IouThr iou;
@@ -508,73 +512,91 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
 
 // Channels-last heads (what cuDNN prefers for the head's last convolution): in memory the image is
 // (H, W, A*(5+C)), so the 5+C values of a cell are contiguous and the cells follow each other in (j, i, a) order.
-// A warp copies up to 16 consecutive cells (contiguous floats: perfectly coalesced, all loads in flight before
-// the first store) into its shared-memory scratch; the first lanes then read one cell each at stride 5+C (conflict-free
-// for the odd 5+C of the reference's configurations) and run the same arithmetic as the planar paths.  The records
-// are still indexed by the reference's candidate order (a, j, i).
-constexpr int kNhwcCells = 16;      // cells per warp step, at most
+// The kernel is issue-bound after the loads (profiles/r01/NOTES.md), so what counts is instructions per cell:
+// a staging warp copies 32 consecutive cells (contiguous floats: perfectly coalesced, 5+C words per lane) into
+// its shared-memory scratch, then every lane reads ONE cell at stride 5+C (conflict-free for the odd 5+C of the
+// reference's configurations) and runs the same arithmetic as the planar paths; the loads of the warp's next 32
+// cells are issued before that arithmetic, so they are in flight while it runs.  Only p.nhwc warps stage -- as
+// many as the free part of U holds scratch for (7 for the VOC heads) -- the others skip the decode: a warp that
+// fills half of its lanes costs the same issue slots as a full one.  Records keep the reference's candidate order
+// (a, j, i).  CT: compile-time class count (0 = runtime).
 constexpr int kNhwcMaxAttrs = 32;   // 5 + C <= 32 on this path
 
-template <int THREADS>
+template <int THREADS, int CT>
 __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, float *scr_base) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = p.C, attrs = p.attrs, A = p.A;
+    const int nwarps = p.nhwc;
+    if (warp >= nwarps) return;
+    const int C = CT ? CT : p.C, attrs = 5 + C, A = p.A;
     const int cells = hd.cells;
     const float *hb = hd.ptr + (size_t)b * cells * attrs;  // uniform
-    const int ncs = p.nhwc;                                // cells per warp step
-    float *scr = scr_base + warp * (ncs * attrs);
-    constexpr int kLoads = kNhwcCells * kNhwcMaxAttrs / 32;  // 16 words per lane at most
-#pragma unroll 1
-    for (int base = warp * ncs; base < cells; base += (THREADS / 32) * ncs) {
-        const int nc = min(ncs, cells - base);
-        const int nw = nc * attrs;
+    float *scr = scr_base + warp * (32 * attrs);
+    constexpr int kLoads = CT ? 5 + CT : kNhwcMaxAttrs;    // words per lane per step
+    float v[kLoads];
+    auto issue = [&](int base) {
+        const int nw = min(32, cells - base) * attrs;
         const float *src = hb + (size_t)base * attrs;
-        float v[kLoads];
 #pragma unroll
         for (int k = 0; k < kLoads; ++k) {
             const int w = 32 * k + lane;
             v[k] = (w < nw) ? __ldcs(src + w) : 0.f;
         }
+    };
+    int base = warp * 32;
+    if (base < cells) issue(base);
+#pragma unroll 1
+    for (; base < cells; base += nwarps * 32) {
+        const int nc = min(32, cells - base);
+        const int nw = nc * attrs;
 #pragma unroll
         for (int k = 0; k < kLoads; ++k) {
             const int w = 32 * k + lane;
             if (w < nw) scr[w] = v[k];
         }
         __syncwarp();
+        if (base + nwarps * 32 < cells) issue(base + nwarps * 32);  // in flight during the arithmetic below
         if (lane < nc) {
             const int m = base + lane;                       // memory order: (j*W + i)*A + a
             const int pos = m / A, a = m - pos * A;
             const int j = fastdiv(pos, hd.magicW), i = pos - j * hd.W;
             const int cid = cid0 + a * hd.HW + pos;          // reference order: (a*H + j)*W + i
-            const float *x = scr + lane * attrs;
-            const float conf = sigmoid_fast(x[4]);          // yolo_loss.py:189,197
+            const float *xs = scr + lane * attrs;
+            const float conf = sigmoid_fast(xs[4]);         // yolo_loss.py:189,197
             if (conf > p.conf_thr) {                        // :201
-                float m1 = x[5];
-                for (int c = 1; c < C; ++c) m1 = fmaxf(m1, x[5 + c]);
                 float best;
-                const float win = tie_window(m1, &best);
-                const float lo = __fsub_rn(m1, win);
-                int bi = -1, nnear = 0;
-                for (int c = 0; c < C; ++c) {
-                    const bool nr = x[5 + c] >= lo;
-                    if (nr && bi < 0) bi = c;
-                    nnear += nr ? 1 : 0;
-                }
-                if (C > 1 && nnear != 1) {                  // near tie (or NaN logits): sigmoid first, then first maximum (:198)
-                    float bs = -1.0f;
-                    int bc = 0;
+                int bi;
+                if constexpr (CT > 0) {
+                    float x[CT];
+#pragma unroll
+                    for (int u = 0; u < CT; ++u) x[u] = xs[5 + u];
+                    float m1 = x[0];
+#pragma unroll
+                    for (int u = 1; u < CT; ++u) m1 = fmaxf(m1, x[u]);
+                    const float win = tie_window(m1, &best);
+                    const float lo = __fsub_rn(m1, win);
+                    float near = 0.f;  // bit u: x[u] >= lo   (FSET + FFMA: exact for 24 bits)
+#pragma unroll
+                    for (int u = 0; u < CT; ++u) near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << u), near);
+                    const uint32_t nb = __float2uint_rn(near);
+                    bi = nb ? __ffs(nb) - 1 : 0;
+                    const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
+                    if (CT > 1 && tie) best = class_tie_break(hb + (size_t)m * attrs + 5, 1, CT, lo, m1, bi, &bi);
+                } else {
+                    float m1 = xs[5];
+                    for (int c = 1; c < C; ++c) m1 = fmaxf(m1, xs[5 + c]);
+                    const float win = tie_window(m1, &best);
+                    const float lo = __fsub_rn(m1, win);
+                    int nnear = 0;
+                    bi = -1;
                     for (int c = 0; c < C; ++c) {
-                        const float xv = x[5 + c];
-                        if (!(xv < lo)) {
-                            const float sg = sigmoid_fast(xv);
-                            if (sg > bs) { bs = sg; bc = c; }
-                        }
+                        const bool nr = xs[5 + c] >= lo;
+                        if (nr && bi < 0) bi = c;
+                        nnear += nr ? 1 : 0;
                     }
-                    if (bs < 0.0f) { bs = sigmoid_fast(m1); bc = max(bi, 0); }
-                    best = bs;
-                    bi = bc;
+                    bi = max(bi, 0);
+                    if (C > 1 && nnear != 1) best = class_tie_break(hb + (size_t)m * attrs + 5, 1, C, lo, m1, bi, &bi);
                 }
-                emit_candidate<MODE_FUSED>(p, s, hd, cid, a, i, j, x[0], x[1], x[2], x[3], conf, best, max(bi, 0));
+                emit_candidate<MODE_FUSED>(p, s, hd, cid, a, i, j, xs[0], xs[1], xs[2], xs[3], conf, best, bi);
             } else {
                 s.clsidx[cid] = 0xffffffffu;
             }
@@ -1023,7 +1045,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
             }
         }
     }
-    constexpr bool kStaticShape = (MODE != MODE_NMS && SH::C > 0);
+    constexpr bool kNhwcShape = (MODE == MODE_FUSED && ShapeIsNhwc<SHAPE>::value);
+    constexpr bool kStaticShape = (MODE != MODE_NMS && SH::C > 0 && !ShapeIsNhwc<SHAPE>::value);
     if (MODE != MODE_DECODE) {
         for (int i = tid; i <= C * p.B; i += THREADS) s.cntb[i] = 0;
         for (int i = tid; i <= C; i += THREADS) s.flag[i] = 0;
@@ -1038,12 +1061,16 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     } else if constexpr (kStaticShape) {
         decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true>(p, s, b, p.head[0], 0, 0);
         decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false>(p, s, b, p.head[1], p.head[0].cells, 1);
+    } else if constexpr (kNhwcShape) {
+        // scratch: the part of U that is free during the decode (behind clsidx); the host checked that it fits
+        float *scr = reinterpret_cast<float *>(smem_raw + L.U + 4 * align_up((uint32_t)(K > 0 ? K : 1), 32));
+        decode_head_nhwc<THREADS, SH::C>(p, s, b, p.head[0], 0, scr);
+        decode_head_nhwc<THREADS, SH::C>(p, s, b, p.head[1], p.head[0].cells, scr);
     } else {
         if (MODE == MODE_FUSED && p.nhwc) {
-            // scratch: the part of U that is free during the decode (behind clsidx); the host checked that it fits
             float *scr = reinterpret_cast<float *>(smem_raw + L.U + 4 * align_up((uint32_t)(K > 0 ? K : 1), 32));
-            decode_head_nhwc<THREADS>(p, s, b, p.head[0], 0, scr);
-            decode_head_nhwc<THREADS>(p, s, b, p.head[1], p.head[0].cells, scr);
+            decode_head_nhwc<THREADS, 0>(p, s, b, p.head[0], 0, scr);
+            decode_head_nhwc<THREADS, 0>(p, s, b, p.head[1], p.head[0].cells, scr);
         } else {
             decode_head_rt<THREADS, MODE>(p, s, b, p.head[0], 0, 0);
             if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE>(p, s, b, p.head[1], p.head[0].cells, 1);

@@ -800,17 +800,22 @@ def test_compact_rows(cuda_device):
     assert np.array_equal(packed[:want_off[-1]].cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("C,grids,anchors,img,thr,shift", [
-    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0),
-    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, -2.6),
-    (10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384], 0.3, 0.0),
-    (3, [(5, 7), (10, 14)], VOC_ANCHORS, [224, 160], 0.3, 0.0),
+@pytest.mark.parametrize("C,grids,anchors,img,thr,shift,quant", [
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0, 0),
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, -2.6, 0),
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0, 2),     # logits on a 0.5 grid: class ties everywhere
+    (10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384], 0.3, 0.0, 0),
+    (10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384], 0.3, 0.0, 2),
+    (3, [(5, 7), (10, 14)], VOC_ANCHORS, [224, 160], 0.3, 0.0, 0),
+    (3, [(5, 7), (10, 14)], VOC_ANCHORS, [224, 160], 0.3, 0.0, 2),
 ])
-def test_channels_last_heads_equal_nchw(C, grids, anchors, img, thr, shift, cuda_device):
+def test_channels_last_heads_equal_nchw(C, grids, anchors, img, thr, shift, quant, cuda_device):
     """SURVEY 8 f3: channels-last head tensors are consumed without an NCHW copy (b200yolo_decode_nms_nhwc);
     detections, counts and kept cell ids equal the planar kernel's bit for bit."""
     from mobilenet_yolo_pytorch_b200 import _lib
     h0, h1 = make_heads(9, C, grids, seed=71, conf_shift=shift)
+    if quant:
+        h0, h1 = torch.round(h0 * quant) / quant, torch.round(h1 * quant) / quant
     tables = anchor_tables(anchors, img)
     d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
     want = ops.decode_nms_padded(d0, d1, tables, C, thr, want_idx=True)
