@@ -68,17 +68,24 @@ extern "C" int b200yolo_decode_nms_host(const float *head0, const float *head1, 
     std::lock_guard<std::mutex> lock(g_host_mu);
     HostCtx &cx = g_host_ctx[device];
     if (int rc = ensure_ctx(cx, device, per0 * chunk * 4, per1 * chunk * 4, K * 7 * chunk * 4, (size_t)chunk * 4)) return rc;
-    int slot = 0;
-    for (int b0 = 0; b0 < N; b0 += chunk, slot = (slot + 1) % kSlots) {
-        const int n = (N - b0 < chunk) ? (N - b0) : chunk;
+    // one chunk: H2D -> kernel -> D2H on the slot's stream
+    auto push_chunk = [&](int b0, int n, int slot) -> int {
         cudaStream_t st = cx.stream[slot];
         CUDA_TRY(cudaMemcpyAsync(cx.d_h0[slot], head0 + per0 * b0, per0 * n * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(cx.d_h1[slot], head1 + per1 * b0, per1 * n * 4, cudaMemcpyHostToDevice, st));
-        int rc = b200yolo_decode_nms(cx.d_h0[slot], cx.d_h1[slot], n, A, C, H0, W0, H1, W1, anchor_wh, conf_thr, iou_thr,
-                                     cx.d_out[slot], cx.d_cnt[slot], nullptr, (void *)st);
-        if (rc) return rc;
+        if (int rc = b200yolo_decode_nms(cx.d_h0[slot], cx.d_h1[slot], n, A, C, H0, W0, H1, W1, anchor_wh, conf_thr, iou_thr,
+                                         cx.d_out[slot], cx.d_cnt[slot], nullptr, (void *)st))
+            return rc;
         CUDA_TRY(cudaMemcpyAsync(out_count + b0, cx.d_cnt[slot], (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(out + K * 7 * b0, cx.d_out[slot], K * 7 * n * 4, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    int rc = 0, slot = 0;
+    for (int b0 = 0; b0 < N && rc == 0; b0 += chunk, slot = (slot + 1) % kSlots)
+        rc = push_chunk(b0, (N - b0 < chunk) ? (N - b0) : chunk, slot);
+    if (rc) {  // the chunks already queued still read / write the caller's buffers: let them finish first
+        for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(cx.stream[s]);
+        return rc;
     }
     for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(cx.stream[s]));
     return 0;
