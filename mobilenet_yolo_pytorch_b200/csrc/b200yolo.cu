@@ -392,6 +392,8 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
         if (S > smax) S = smax;
         if (S > kTLMaxSplit) S = kTLMaxSplit;
         if (S < 1) S = 1;
+        static const int env_split = [] { const char *e = getenv("B200YOLO_TL_SPLIT"); return e ? atoi(e) : 0; }();
+        if (env_split > 0 && env_split <= smax && env_split <= kTLMaxSplit) S = env_split;  // tuning knob
     }
     p.S = S;
     p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
@@ -481,7 +483,19 @@ int b200yolo_target_loss_backward(const float *head, int N, int A, int C, int H,
     if (S < 1) S = 1;
     p.S = S;
     p.chunk = ((p.cells + S - 1) / S + 31) / 32 * 32;
-    target_loss_backward_kernel<<<N * S, kTLThreads, smem, st>>>(p);
+    // programmatic dependent launch, as in the forward: the kernel after this one may start during its tail
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_flags.load() & 2) ? 0 : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(N * S));
+    cfg.blockDim = dim3(kTLThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, target_loss_backward_kernel, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

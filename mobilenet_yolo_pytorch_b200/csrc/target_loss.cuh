@@ -570,15 +570,10 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
     const int g0 = p.gt_off[b];
     int nG = p.gt_off[b + 1] - g0;
     const int HW = p.HW, W = p.W, A = p.A;
-    if (tid < 4) s_misc[tid] = 0;
-    for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
-    if (nG > p.gcap) nG = 0;  // (the forward call reported it)
-    __syncthreads();
-    tl_match_gt(p, g0, nG, false, sm);
-    const int nE = s_misc[0];
-    tl_unique_cells(nE, sm);
-    const int nU = s_misc[3];
-
+    // programmatic dependent launch: the next kernel of the stream may start; this one reads what the forward
+    // call produced (sums, cell states)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const double go = p.grad_out ? (double)__ldg(p.grad_out) : 1.0;
     const double inv_w = go * 2.0 / p.sums[B200YOLO_S_W];                                    // d L_dense / d o = 2 (o - t) w / sum w
     const double n_assign = p.sums[B200YOLO_S_NASSIGN];
@@ -586,7 +581,10 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
     float *gbase = p.grad_input + (size_t)b * A * p.attrs * HW;
     const float *hbase = p.head + (size_t)b * A * p.attrs * HW;
 
-    // ---- every cell that is not assigned: only the objectness channel can carry a gradient
+
+    // ---- streaming pass first: every cell as if it were not assigned (only the objectness channel can carry a
+    // gradient).  Its stores need nothing from the matching below, so they drain while the CTA sits in the
+    // matching's barriers; the assigned cells are overwritten after those barriers.
     const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
     const bool vec = (HW & 3) == 0 && (((uintptr_t)p.grad_input | (uintptr_t)p.head) & 15) == 0;
     if (vec) {
@@ -609,7 +607,6 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
         }
     } else {
         for (int cell = cell_lo + tid; cell < cell_hi; cell += kTLThreads) {
-            if (s_flag[cell]) continue;
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
             const int pos = cell - a * HW;
             const size_t off = (size_t)a * p.attrs * HW + pos;
@@ -621,6 +618,16 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
             for (int t = 0; t < p.attrs; ++t) __stcs(g + (size_t)t * HW, t == 4 ? gconf : 0.f);
         }
     }
+
+    // ---- the image's assignments (the same deterministic list as the forward's)
+    if (tid < 4) s_misc[tid] = 0;
+    for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
+    if (nG > p.gcap) nG = 0;  // (the forward call reported it)
+    __syncthreads();
+    tl_match_gt(p, g0, nG, false, sm);
+    const int nE = s_misc[0];
+    tl_unique_cells(nE, sm);
+    const int nU = s_misc[3];
 
     // ---- assigned cells of this CTA's slice (after the barrier: they overwrite what the streaming pass stored)
     {
