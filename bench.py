@@ -52,6 +52,9 @@ WORKLOADS = {
                  desc="MobileNetV3-YOLO BDD100k 10-class 640x384 heads, batch 1024/8 = 128 per GPU"),
     "cfg5": dict(N=512, C=20, grids=[(13, 13), (26, 26)], anchors=VOC_ANCHORS, img=[416, 416], conf=0.001, shift=0.0,
                  desc="dense-candidate NMS stress: 416x416 heads, val_conf 0.001, batch 4096/8 = 512 per GPU"),
+    "cfg5_832": dict(N=128, C=20, grids=[(26, 26), (52, 52)], anchors=VOC_ANCHORS, img=[832, 832], conf=0.001, shift=0.0,
+                     desc="the ~10k-boxes-per-image reading of the stress configuration: 832x832 heads (10140 cells per "
+                          "image, all pass val_conf 0.001), batch 128 per GPU, large-image path (b200yolo_decode_nms_large)"),
 }
 A = 3
 
@@ -544,12 +547,15 @@ def run_b200(args, wl):
             "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": N, "global_batch": world * N,
                        "cells_per_image": K, "kept_rows_per_image": kept_per_launch / N,
                        "l2": f"{R} rotating input sets ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2, so every step reads its heads from HBM",
-                       "launch": "one kernel per step on one stream; consecutive launches overlap through programmatic dependent "
-                                 "launch (a launch starts on free SM slots while the previous one finishes, and waits for it before "
-                                 "writing); extra.serialized_launches is the same loop in plain stream order",
+                       "launch": ("one kernel per step on one stream; consecutive launches overlap through programmatic dependent "
+                                  "launch (a launch starts on free SM slots while the previous one finishes, and waits for it before "
+                                  "writing); extra.serialized_launches is the same loop in plain stream order")
+                       if K <= _lib.load().b200yolo_max_cells(local) else "one kernel per step on one stream, plain stream order",
                        "parallelism": f"dp{world} by image, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "decode_nms_kernel<MODE_FUSED>",
+                         "traffic": traffic,
+                         "kernel": "decode_nms_kernel<MODE_FUSED>" if K <= _lib.load().b200yolo_max_cells(local)
+                         else "decode_nms_large_kernel (more cells per image than one CTA stages in shared memory)",
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src + ", of measured"},
             "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": oracle.max_threads(), "kind": "port",
                              "sample": f"{cpu_reps} passes over the same {N}-image batch, median {cpu_med * 1e3:.1f} ms "

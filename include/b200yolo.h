@@ -117,6 +117,20 @@ int b200yolo_decode_nms_nhwc(const float *head0, const float *head1, int N, int 
                              int *out_count, int *out_idx, void *stream);
 
 /*
+ * The same for images with more candidate cells than one CTA can stage in shared memory (b200yolo_decode_nms
+ * answers B200YOLO_EUNSUPPORTED above b200yolo_max_cells(): ~5.6 k cells), e.g. the 832x832 variant of the
+ * dense-candidate stress configuration: heads (N,75,26,26) + (N,75,52,52) = 10 140 cells per image.  One CTA per
+ * image keeps only 8-byte sort keys in shared memory; the decoded records live in the caller's workspace
+ * (b200yolo_decode_nms_large_workspace_bytes(N, cells) bytes, 16-byte aligned) and the per-class greedy NMS
+ * (utils/box.py:16-30 + torchvision nms) runs tile by tile against the kept boxes, without an n^2 mask.
+ * Same outputs, same order, as b200yolo_decode_nms.  Limits: cells per image <= 16384.
+ */
+size_t b200yolo_decode_nms_large_workspace_bytes(int N, int cells_per_image);
+int b200yolo_decode_nms_large(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                              int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
+                              int *out_count, int *out_idx, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Same computation from HOST buffers (the reference-facing call bench.py times
  * as "e2e"): heads are copied host->device in image chunks on two streams,
  * post-processed, and detections + counts copied back, overlapped.  Pinned

@@ -34,6 +34,10 @@ SIGNATURES = {
                                       c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, c_i32p, C.c_void_p]),
     "b200yolo_decode_nms_nhwc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, c_i32p, C.c_void_p]),
+    "b200yolo_decode_nms_large_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "b200yolo_decode_nms_large": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, c_i32p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p]),
     "b200yolo_decode_nms_host": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, C.c_int]),
     "b200yolo_compact_rows": (C.c_int, [c_f32p, c_i32p, C.c_int, C.c_int, c_f32p, c_i32p, C.c_void_p]),

@@ -16,6 +16,7 @@
 #include "pairwise.cuh"
 #include "map_eval.cuh"
 #include "seg_loss.cuh"
+#include "large_nms.cuh"
 
 using namespace b200yolo;
 
@@ -637,6 +638,60 @@ int b200yolo_map_eval(const float *det_boxes, const int *det_labels, const float
         CUDA_TRY(cudaGetLastError());
     }
     map_class_kernel<<<p.Cf, kMapClassThreads, 0, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+size_t b200yolo_decode_nms_large_workspace_bytes(int N, int cells_per_image) {
+    if (N < 0 || cells_per_image < 0) return 0;
+    return (size_t)N * (size_t)cells_per_image * 2 * sizeof(float4);
+}
+
+int b200yolo_decode_nms_large(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                              int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
+                              int *out_count, int *out_idx, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!head0 || !head1 || !anchor_wh || !out || !out_count) return fail(B200YOLO_EINVAL, "decode_nms_large: null pointer");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
+        return fail(B200YOLO_EINVAL, "decode_nms_large: bad shape");
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_large: NaN threshold");
+    const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
+    if (cells > kLargeMaxKeys)
+        return fail(B200YOLO_EUNSUPPORTED, "decode_nms_large: %lld cells per image (limit %d)", cells, kLargeMaxKeys);
+    if (N == 0) return 0;
+    if (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < b200yolo_decode_nms_large_workspace_bytes(N, (int)cells))
+        return fail(B200YOLO_EINVAL, "decode_nms_large: workspace missing, misaligned or too small (%zu < %zu)", workspace_bytes,
+                    b200yolo_decode_nms_large_workspace_bytes(N, (int)cells));
+    LargeParams p;
+    memset(&p, 0, sizeof(p));
+    fill_head(p.head[0], head0, A, H0, W0, anchor_wh);
+    fill_head(p.head[1], head1, A, H1, W1, anchor_wh + 2 * A);
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.K = (int)cells;
+    p.P = 32;
+    while (p.P < p.K) p.P <<= 1;
+    p.T = p.K / 32 + C + 1;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(iou_thr);
+    p.rec = (float4 *)workspace;
+    p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    const size_t smem = large_smem_bytes(p.P, C, p.T);
+    const int lim = smem_optin(dev);
+    if (smem > (size_t)lim)
+        return fail(B200YOLO_EUNSUPPORTED, "decode_nms_large: %d cells, %d classes need %zu B of shared memory (limit %d B)",
+                    p.K, C, smem, lim);
+    {
+        static std::mutex mu;
+        static bool configured[64] = {false};
+        std::lock_guard<std::mutex> g(mu);
+        if (dev < 64 && !configured[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(decode_nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            configured[dev] = true;
+        }
+    }
+    decode_nms_large_kernel<<<N, kLargeThreads, smem, (cudaStream_t)stream>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

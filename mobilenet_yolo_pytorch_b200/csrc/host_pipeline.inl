@@ -16,13 +16,14 @@ struct HostCtx {
     float *d_h1[kSlots] = {nullptr, nullptr, nullptr};
     float *d_out[kSlots] = {nullptr, nullptr, nullptr};
     int *d_cnt[kSlots] = {nullptr, nullptr, nullptr};
-    size_t cap_h0 = 0, cap_h1 = 0, cap_out = 0, cap_cnt = 0;
+    float *d_ws[kSlots] = {nullptr, nullptr, nullptr};   // records of the large-image path
+    size_t cap_h0 = 0, cap_h1 = 0, cap_out = 0, cap_cnt = 0, cap_ws = 0;
 };
 
 std::mutex g_host_mu;
 HostCtx g_host_ctx[16];
 
-int ensure_ctx(HostCtx &cx, int device, size_t b_h0, size_t b_h1, size_t b_out, size_t b_cnt) {
+int ensure_ctx(HostCtx &cx, int device, size_t b_h0, size_t b_h1, size_t b_out, size_t b_cnt, size_t b_ws) {
     if (cx.device != device) {
         for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&cx.stream[s], cudaStreamNonBlocking));
         cx.device = device;
@@ -41,6 +42,7 @@ int ensure_ctx(HostCtx &cx, int device, size_t b_h0, size_t b_h1, size_t b_out, 
     if (int rc = grow(cx.d_h1, cx.cap_h1, b_h1)) return rc;
     if (int rc = grow(cx.d_out, cx.cap_out, b_out)) return rc;
     if (int rc = grow((float **)cx.d_cnt, cx.cap_cnt, b_cnt)) return rc;
+    if (int rc = grow(cx.d_ws, cx.cap_ws, b_ws)) return rc;
     return 0;
 }
 
@@ -67,15 +69,21 @@ extern "C" int b200yolo_decode_nms_host(const float *head0, const float *head1, 
     if (chunk > N) chunk = N;
     std::lock_guard<std::mutex> lock(g_host_mu);
     HostCtx &cx = g_host_ctx[device];
-    if (int rc = ensure_ctx(cx, device, per0 * chunk * 4, per1 * chunk * 4, K * 7 * chunk * 4, (size_t)chunk * 4)) return rc;
+    // images too large for the fused kernel's shared memory go through b200yolo_decode_nms_large (records in a workspace)
+    const bool large = (long long)K > (long long)b200yolo_max_cells(device);
+    const size_t b_ws = large ? b200yolo_decode_nms_large_workspace_bytes(chunk, (int)K) : 0;
+    if (int rc = ensure_ctx(cx, device, per0 * chunk * 4, per1 * chunk * 4, K * 7 * chunk * 4, (size_t)chunk * 4, b_ws)) return rc;
     // one chunk: H2D -> kernel -> D2H on the slot's stream
     auto push_chunk = [&](int b0, int n, int slot) -> int {
         cudaStream_t st = cx.stream[slot];
         CUDA_TRY(cudaMemcpyAsync(cx.d_h0[slot], head0 + per0 * b0, per0 * n * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(cx.d_h1[slot], head1 + per1 * b0, per1 * n * 4, cudaMemcpyHostToDevice, st));
-        if (int rc = b200yolo_decode_nms(cx.d_h0[slot], cx.d_h1[slot], n, A, C, H0, W0, H1, W1, anchor_wh, conf_thr, iou_thr,
-                                         cx.d_out[slot], cx.d_cnt[slot], nullptr, (void *)st))
-            return rc;
+        const int rc = large ? b200yolo_decode_nms_large(cx.d_h0[slot], cx.d_h1[slot], n, A, C, H0, W0, H1, W1, anchor_wh, conf_thr,
+                                                         iou_thr, cx.d_out[slot], cx.d_cnt[slot], nullptr, cx.d_ws[slot], cx.cap_ws,
+                                                         (void *)st)
+                             : b200yolo_decode_nms(cx.d_h0[slot], cx.d_h1[slot], n, A, C, H0, W0, H1, W1, anchor_wh, conf_thr,
+                                                   iou_thr, cx.d_out[slot], cx.d_cnt[slot], nullptr, (void *)st);
+        if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(out_count + b0, cx.d_cnt[slot], (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(out + K * 7 * b0, cx.d_out[slot], K * 7 * n * 4, cudaMemcpyDeviceToHost, st));
         return 0;

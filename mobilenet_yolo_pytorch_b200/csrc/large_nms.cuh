@@ -1,0 +1,280 @@
+// large_nms.cuh -- decode + per-class NMS for images with more candidate cells than one CTA can keep in shared
+// memory (decode_nms.cuh stages ~40 B per cell: about 5.6 k cells in 227 KB).  SURVEY.md 8(d) asks for the 832x832
+// variant of config 5: heads (N,75,26,26) + (N,75,52,52) = 10 140 cells per image.
+//
+// One CTA of 1024 threads per image, same reference semantics as the fused kernel (yolo_loss.py:186-203,
+// utils/box.py:16-30, torchvision nms) and the same arithmetic (SFU sigmoid / exp, class near-tie fallback,
+// divide-free pair test with the exact torchvision decision inside the guard band):
+//   P1  decode every cell (thread per cell, plane loads coalesced); a passing cell's record {box, conf, score,
+//       t*area*2^-13, class} goes to the caller's workspace (32 B per cell, stays in L2) and its 64-bit sort key
+//       (class asc | score desc | cell id asc) to shared memory -- 8 B per cell is all the CTA stages;
+//   P2  bitonic sort of the keys (padded to a power of two with ~0);
+//   P3  class starts / tile table (warp 0);
+//   P4  greedy NMS over tasks = (class, tile of 32 sorted candidates), claimed from a counter in tile-major
+//       order (tile 0 of every class, tile 1 of every class, ...: the classes advance side by side).  A task
+//       (lane = candidate) stages each earlier tile of its class as the 32 columns of one pair block of
+//       decode_nms.cuh (block_fast / block_exact: the same arithmetic as the fused kernel), ANDs the block's
+//       word with the tile's KEPT word -- it spins on a per-tile ready flag; a task only depends on tasks
+//       claimed before it, so the spin cannot deadlock -- then resolves its own tile in score order and
+//       publishes its kept word.  No n^2 mask storage: the worst case (one class holding everything) is
+//       bounded by time, not memory;
+//   P5  kept rows in (class asc, score desc) order -> out / out_idx / out_count.
+#pragma once
+#include "decode_nms.cuh"
+
+namespace b200yolo {
+
+constexpr int kLargeThreads = 1024;
+constexpr int kLargeMaxKeys = 16384;   // 128 KB of keys
+constexpr int kLargeStageBytes = 32 * 16 + 40 * 8;   // per warp: 32 boxes + 32 (+8 padding) {box address, t*area} entries
+
+struct LargeParams {
+    HeadDesc head[2];
+    int N, A, C, attrs;
+    int K, P;            // cells per image; P = smallest power of two >= max(K, 32)
+    int T;               // tile slots: K/32 + C + 1
+    float conf_thr;
+    IouThr iou;
+    float4 *rec;         // workspace [N][K][2]
+    float *out;          // [N][K][7]
+    int *out_count;      // [N]
+    int *out_idx;        // [N][K] or null
+};
+
+__host__ __device__ inline size_t large_smem_bytes(int P, int C, int T) {
+    size_t o = (size_t)8 * P + (size_t)4 * (3 * (C + 2)) + (size_t)12 * T + 64;
+    o = (o + 15) & ~(size_t)15;
+    return o + (size_t)(kLargeThreads / 32) * kLargeStageBytes;
+}
+
+__device__ __forceinline__ void large_decode_head(const LargeParams &p, int b, const HeadDesc &hd, int cid0,
+                                                  unsigned long long *keys, int *cnt) {
+    const int C = p.C, attrs = p.attrs, HW = hd.HW;
+    const int cells = p.A * HW;
+    const float *hb = hd.ptr + (size_t)b * p.A * attrs * HW;
+    for (int local = threadIdx.x; local < cells; local += kLargeThreads) {
+        const int cid = cid0 + local;
+        const int a = fastdiv(local, hd.magicHW);
+        const int pos = local - a * HW;
+        const float *q = hb + (size_t)a * attrs * HW + pos;
+        const float tx = __ldcs(q), ty = __ldcs(q + HW), tw = __ldcs(q + 2 * (size_t)HW), th = __ldcs(q + 3 * (size_t)HW);
+        const float conf = sigmoid_fast(__ldcs(q + 4 * (size_t)HW));   // yolo_loss.py:189,197
+        unsigned long long key = ~0ull;
+        if (conf > p.conf_thr) {                                       // :201
+            const float *qc = q + 5 * (size_t)HW;
+            float m1 = __ldg(qc);
+            for (int c = 1; c < C; ++c) m1 = fmaxf(m1, __ldg(qc + (size_t)c * HW));
+            float best;
+            const float win = tie_window(m1, &best);
+            const float lo = __fsub_rn(m1, win);
+            int bi = -1, nnear = 0;
+            for (int c = 0; c < C; ++c) {
+                const bool nr = __ldg(qc + (size_t)c * HW) >= lo;
+                if (nr && bi < 0) bi = c;
+                nnear += nr ? 1 : 0;
+            }
+            bi = max(bi, 0);
+            if (C > 1 && nnear != 1) best = class_tie_break(qc, HW, C, lo, m1, bi, &bi);   // :198
+            const int j = fastdiv(pos, hd.magicW), i = pos - j * hd.W;
+            const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
+            const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
+            const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194
+            const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+            const float bw = __fmul_rn(ew, hd.aw[a]), bh = __fmul_rn(eh, hd.ah[a]);   // :195
+            float4 bx;
+            bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244-247
+            bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));
+            bx.z = __fadd_rn(bw, bx.x);
+            bx.w = __fadd_rn(bh, bx.y);
+            float4 *r = p.rec + ((size_t)b * p.K + cid) * 2;
+            r[0] = bx;
+            r[1] = make_float4(conf, best, make_ta(bx, p.iou), __int_as_float(bi));
+            const float sc = __fmul_rn(best, conf);                      // box.py:27
+            key = ((unsigned long long)bi << 48) | ((unsigned long long)(~float_order_key(sc)) << 16) | (unsigned long long)cid;
+            atomicAdd(&cnt[bi], 1);
+        }
+        keys[cid] = key;
+    }
+}
+
+__device__ __forceinline__ void large_bitonic_sort(unsigned long long *k, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += kLargeThreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(const LargeParams p) {
+    extern __shared__ __align__(16) unsigned char lsm[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(lsm);
+    int *cnt = reinterpret_cast<int *>(keys + p.P);       // [C+2]
+    int *start = cnt + (p.C + 2);                         // [C+2]
+    int *ktile = start + (p.C + 2);                       // [C+2]
+    uint32_t *keptw = reinterpret_cast<uint32_t *>(ktile + (p.C + 2));   // [T]
+    int *ready = reinterpret_cast<int *>(keptw + p.T);    // [T]  (P5: exclusive prefix of the kept counts)
+    uint32_t *tasks = reinterpret_cast<uint32_t *>(ready + p.T);   // [T] (class << 16 | tile), tile-major
+    int *misc = reinterpret_cast<int *>(tasks + p.T);     // [0] task counter, [1] total kept
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, K = p.K;
+    // per-warp staging of one tile of columns for the pair blocks of decode_nms.cuh
+    const size_t stage0 = (((size_t)8 * p.P + (size_t)4 * (3 * (C + 2)) + (size_t)12 * p.T + 64) + 15) & ~(size_t)15;
+    float4 *sbox = reinterpret_cast<float4 *>(lsm + stage0 + (size_t)warp * kLargeStageBytes);
+    uint2 *sord = reinterpret_cast<uint2 *>(sbox + 32);
+    const uint32_t sbox_addr = (uint32_t)__cvta_generic_to_shared(sbox);
+
+    for (int i = tid; i < C + 2; i += kLargeThreads) cnt[i] = 0;
+    for (int i = tid; i < p.T; i += kLargeThreads) { keptw[i] = 0u; ready[i] = 0; }
+    for (int i = K + tid; i < p.P; i += kLargeThreads) keys[i] = ~0ull;
+    if (tid < 2) misc[tid] = 0;
+    if (lane < 8) sord[32 + lane] = make_uint2(sbox_addr, 0x7fc00000u);   // padding read by partial chunks: NaN area
+    __syncthreads();
+    // P1
+    large_decode_head(p, b, p.head[0], 0, keys, cnt);
+    large_decode_head(p, b, p.head[1], p.head[0].cells, keys, cnt);
+    __syncthreads();
+    // P2
+    large_bitonic_sort(keys, p.P);
+    // P3: start[c] = first sorted position of class c, ktile[c] = first tile slot of class c; then the task list,
+    // tile-major (tile 0 of every class, tile 1 of every class, ...): the classes' chains advance side by side,
+    // and a task still depends only on tasks that come before it
+    if (warp == 0) {
+        int cs = 0, ct = 0, maxt = 0;
+        for (int c0 = 0; c0 <= C; c0 += 32) {
+            const int c = c0 + lane;
+            const int n = (c < C) ? cnt[c] : 0;
+            const int nt = (n + 31) >> 5;
+            const int in = warp_inclusive_scan(n, lane), it = warp_inclusive_scan(nt, lane);
+            if (c <= C) { start[c] = cs + in - n; ktile[c] = ct + it - nt; }
+            cs += __shfl_sync(kFullMask, in, 31);
+            ct += __shfl_sync(kFullMask, it, 31);
+            maxt = max(maxt, nt);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxt = max(maxt, __shfl_xor_sync(kFullMask, maxt, o));
+        int q = 0;
+        for (int t = 0; t < maxt; ++t) {
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                const bool has = c < C && ((cnt[c] + 31) >> 5) > t;
+                const uint32_t bal = __ballot_sync(kFullMask, has);
+                if (has) tasks[q + __popc(bal & lanemask_lt())] = ((uint32_t)c << 16) | (uint32_t)t;
+                q += __popc(bal);
+            }
+        }
+    }
+    __syncthreads();
+    const int ntask = ktile[C];
+    const float4 *rec = p.rec + (size_t)b * K * 2;
+    // P4
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&misc[0], 1);
+        q = __shfl_sync(kFullMask, q, 0);
+        if (q >= ntask) break;
+        const uint32_t tk = tasks[q];
+        const int c = (int)(tk >> 16), t = (int)(tk & 0xffffu);
+        const int n = cnt[c], s0 = start[c], g0 = ktile[c];
+        const int idx = 32 * t + lane;
+        const int ncol = min(32, n - 32 * t);
+        bool alive = idx < n;
+        // my candidate (lanes past the end of the class take the last one; they are never alive)
+        const uint32_t cid = (uint32_t)(keys[s0 + min(idx, n - 1)] & 0xffffull);
+        const float4 R = rec[2 * cid];
+        const float rta = rec[2 * cid + 1].z;
+        const bool rslow = __any_sync(kFullMask, rta != rta);   // a degenerate box in the tile: exact arithmetic
+        // earlier tiles of the class: their 32 boxes are staged as the columns of one pair block (the records were
+        // written in P1, so the loads do not wait for the tile's flag; the next tile's are issued before this one
+        // is processed); the block's word AND the tile's kept word says whether a kept box suppresses my candidate
+        float4 nB = R;
+        float nta = rta;
+        if (t > 0) {
+            const uint32_t cidk = (uint32_t)(keys[s0 + lane] & 0xffffull);
+            nB = rec[2 * cidk];
+            nta = rec[2 * cidk + 1].z;
+        }
+        for (int rt = 0; rt < t; ++rt) {
+            sbox[lane] = nB;
+            sord[lane] = make_uint2(sbox_addr + 16u * lane, __float_as_uint(nta));
+            const bool slow = rslow || __any_sync(kFullMask, nta != nta);
+            if (rt + 1 < t) {
+                const uint32_t cidk = (uint32_t)(keys[s0 + 32 * (rt + 1) + lane] & 0xffffull);
+                nB = rec[2 * cidk];
+                nta = rec[2 * cidk + 1].z;
+            }
+            __syncwarp();
+            const uint32_t word = slow ? block_exact(sord, 32, R, p.iou.thr) : block_fast(sord, 32, R, rta, p.iou.thr);
+            if (lane == 0) {
+                while (reinterpret_cast<volatile int *>(ready)[g0 + rt] == 0) __nanosleep(40);
+                __threadfence_block();
+            }
+            __syncwarp();
+            const uint32_t kw = reinterpret_cast<volatile uint32_t *>(keptw)[g0 + rt];
+            if (word & kw) alive = false;
+            if (!__any_sync(kFullMask, alive)) break;
+        }
+        // own tile: later columns a candidate would suppress, then the turns in score order
+        __syncwarp();
+        sbox[lane] = R;
+        sord[lane] = make_uint2(sbox_addr + 16u * lane, __float_as_uint(rta));
+        __syncwarp();
+        uint32_t D = rslow ? block_exact(sord, ncol, R, p.iou.thr) : block_fast(sord, ncol, R, rta, p.iou.thr);
+        D &= ~((2u << lane) - 1u);                    // only LATER columns (2u << 31 == 0: none)
+        uint32_t rem = __ballot_sync(kFullMask, alive);
+        if (!alive) D = 0u;
+        uint32_t nz = __ballot_sync(kFullMask, (D & rem) != 0u);
+        while (nz) {
+            const int i = __ffs(nz) - 1;
+            nz &= nz - 1u;
+            const uint32_t Di = __shfl_sync(kFullMask, D, i);
+            if ((rem >> i) & 1u) rem &= ~Di;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            keptw[g0 + t] = rem;
+            __threadfence_block();
+            reinterpret_cast<volatile int *>(ready)[g0 + t] = 1;
+        }
+    }
+    __syncthreads();
+    // P5: exclusive prefix of the kept counts over the tile slots (reuses ready[]), then the rows
+    if (warp == 0) {
+        int carry = 0;
+        for (int g = 0; g < ntask; g += 32) {
+            const int v = (g + lane < ntask) ? __popc(keptw[g + lane]) : 0;
+            const int inc = warp_inclusive_scan(v, lane);
+            if (g + lane < ntask) ready[g + lane] = carry + inc - v;
+            carry += __shfl_sync(kFullMask, inc, 31);
+        }
+        if (lane == 0) misc[1] = carry;
+    }
+    __syncthreads();
+    float *o = p.out + (size_t)b * K * 7;
+    for (int g = warp; g < ntask; g += kLargeThreads / 32) {
+        const uint32_t word = keptw[g];
+        if (!((word >> lane) & 1u)) continue;
+        int lo = 0, hi = C - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (ktile[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const int c = lo;
+        const uint32_t cid = (uint32_t)(keys[start[c] + 32 * (g - ktile[c]) + lane] & 0xffffull);
+        const int r = ready[g] + __popc(word & lanemask_lt());
+        const float4 bx = rec[2 * cid], cs = rec[2 * cid + 1];
+        float *d = o + (size_t)r * 7;
+        d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
+        d[4] = cs.x; d[5] = cs.y; d[6] = (float)c;                  // cls_idx.float() yolo_loss.py:199
+        if (p.out_idx) p.out_idx[(size_t)b * K + r] = (int)cid;
+    }
+    if (tid == 0) p.out_count[b] = misc[1];
+}
+
+}  // namespace b200yolo

@@ -15,6 +15,7 @@ import torch
 
 from . import _lib
 
+LARGE_MAX_CELLS = 16384   # b200yolo_decode_nms_large: sort keys of one image in shared memory
 NMS_IOU_THRESHOLD = 0.45  # utils/box.py:28
 _WORKSPACES = {}  # (device index, stream) -> cached target-loss workspace tensor
 
@@ -153,9 +154,11 @@ class _on_device:
 def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
                       iou_thr: float = NMS_IOU_THRESHOLD, want_idx: bool = False,
                       out: Optional[torch.Tensor] = None, out_count: Optional[torch.Tensor] = None,
-                      out_idx: Optional[torch.Tensor] = None):
+                      out_idx: Optional[torch.Tensor] = None, force_large: bool = False):
     """b200yolo_decode_nms: ONE launch, no host sync.  Returns (out (N,K,7), out_count (N,)[, out_idx (N,K)]).
-    Pre-allocated outputs may be passed (CUDA-graph capture, NCCL send buffers)."""
+    Pre-allocated outputs may be passed (CUDA-graph capture, NCCL send buffers).  Images with more cells than one
+    CTA can stage in shared memory (e.g. 832x832 inputs: 10 140 cells) go through b200yolo_decode_nms_large with a
+    workspace from torch's allocator; `force_large` takes that path for any shape (tests)."""
     _require_cuda(head0, "head0")
     _require_cuda(head1, "head1")
     attrs = 5 + num_classes
@@ -163,6 +166,8 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
     nhwc = (attrs <= 32 and head0.dim() == 4 and not head0.is_contiguous() and not head1.is_contiguous()
             and head0.is_contiguous(memory_format=torch.channels_last)
             and head1.is_contiguous(memory_format=torch.channels_last))
+    if force_large:
+        nhwc = False
     if not nhwc:
         if not head0.is_contiguous():
             head0 = head0.contiguous()
@@ -188,9 +193,17 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
         args = (N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data, float(np.float32(conf_thr)), float(iou_thr),
                 out.data_ptr(), out_count.data_ptr(), out_idx.data_ptr() if want_idx else None,
                 torch.cuda.current_stream(dev).cuda_stream)
-        rc = (lib.b200yolo_decode_nms_nhwc if nhwc else lib.b200yolo_decode_nms)(head0.data_ptr(), head1.data_ptr(), *args)
-        if rc == -2 and nhwc:  # no shared memory left for the channels-last staging: NCHW copies, then the planar kernel
-            rc = lib.b200yolo_decode_nms(head0.contiguous().data_ptr(), head1.contiguous().data_ptr(), *args)
+        rc = -2
+        if not force_large:
+            rc = (lib.b200yolo_decode_nms_nhwc if nhwc else lib.b200yolo_decode_nms)(head0.data_ptr(), head1.data_ptr(), *args)
+            if rc == -2 and nhwc:  # no shared memory left for the channels-last staging: NCHW copies, then the planar kernel
+                head0, head1 = head0.contiguous(), head1.contiguous()
+                rc = lib.b200yolo_decode_nms(head0.data_ptr(), head1.data_ptr(), *args)
+        if rc == -2 and K <= LARGE_MAX_CELLS:  # too many cells for one CTA's shared memory: records in a workspace
+            if nhwc:
+                head0, head1 = head0.contiguous(), head1.contiguous()
+            ws = torch.empty((int(lib.b200yolo_decode_nms_large_workspace_bytes(N, K)),), dtype=torch.uint8, device=dev)
+            rc = lib.b200yolo_decode_nms_large(head0.data_ptr(), head1.data_ptr(), *args[:-1], ws.data_ptr(), ws.numel(), args[-1])
         if rc:
             _lib.check(rc)
     return (out, out_count, out_idx) if want_idx else (out, out_count)

@@ -303,12 +303,71 @@ def test_host_pipeline_equals_device_call(cuda_device):
         assert torch.equal(out_h[b, :k], out_d[b, :k].cpu())
 
 
+def test_host_pipeline_large_images(cuda_device):
+    """b200yolo_decode_nms_host routes images beyond the fused kernel's shared memory to the large-image path."""
+    h0, h1 = make_heads(5, 20, [(26, 26), (52, 52)], seed=12, conf_shift=-1.0)
+    tables = anchor_tables(VOC_ANCHORS, [832, 832])
+    out_h, cnt_h = ops.decode_nms_host(h0.pin_memory(), h1.pin_memory(), tables, 20, 0.3, device=cuda_device.index or 0)
+    out_d, cnt_d = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, 20, 0.3)
+    assert torch.equal(cnt_h, cnt_d.cpu()) and int(cnt_h.sum()) > 0
+    for b in range(5):
+        k = int(cnt_h[b])
+        assert torch.equal(out_h[b, :k], out_d[b, :k].cpu())
+
+
 def test_unsupported_shape_fails_loudly(cuda_device):
     C = 20
-    h0 = torch.zeros(1, 75, 26, 26, device=cuda_device)
-    h1 = torch.zeros(1, 75, 52, 52, device=cuda_device)  # 10140 cells: more than one CTA can stage
-    with pytest.raises(RuntimeError, match="shared memory"):
-        ops.decode_nms_padded(h0, h1, anchor_tables(VOC_ANCHORS, [832, 832]), C, 0.3)
+    h0 = torch.zeros(1, 75, 40, 40, device=cuda_device)
+    h1 = torch.zeros(1, 75, 80, 80, device=cuda_device)  # 24000 cells: beyond the large-image path as well
+    with pytest.raises(RuntimeError, match="cells per image"):
+        ops.decode_nms_padded(h0, h1, anchor_tables(VOC_ANCHORS, [1280, 1280]), C, 0.3)
+
+
+@pytest.mark.parametrize("C,grids,anchors,img,thr,shift,quant", [
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0, 0),
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, -2.6, 0),
+    (20, [(13, 13), (26, 26)], VOC_ANCHORS, [416, 416], 0.001, 0.0, 0),
+    (20, [(11, 11), (22, 22)], VOC_ANCHORS, [352, 352], 0.3, 0.0, 2),     # logits on a 0.5 grid: ties, identical boxes
+    (10, [(12, 20), (24, 40)], BDD_ANCHORS, [640, 384], 0.3, 0.0, 0),
+    (1, [(7, 5), (14, 10)], VOC_ANCHORS, [160, 224], 0.3, 0.0, 0),        # one class: every candidate in one chain of tiles
+    (80, [(10, 10), (20, 20)], VOC_ANCHORS, [320, 320], 0.3, 0.0, 0),
+    (3, [(2, 3), (4, 6)], VOC_ANCHORS, [96, 64], 0.9, 0.0, 0),            # nearly nothing passes
+])
+def test_large_image_path_equals_fused(C, grids, anchors, img, thr, shift, quant, cuda_device):
+    """b200yolo_decode_nms_large (records in a workspace, tile-by-tile greedy NMS) returns the fused kernel's
+    detections, counts and kept cell ids bit for bit on shapes both can run."""
+    from mobilenet_yolo_pytorch_b200 import _lib
+    h0, h1 = make_heads(7, C, grids, seed=33, conf_shift=shift)
+    if quant:
+        h0, h1 = torch.round(h0 * quant) / quant, torch.round(h1 * quant) / quant
+    tables = anchor_tables(anchors, img)
+    d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+    want = ops.decode_nms_padded(d0, d1, tables, C, thr, want_idx=True)
+    n0 = _lib.launch_count()
+    got = ops.decode_nms_padded(d0, d1, tables, C, thr, want_idx=True, force_large=True)
+    assert _lib.launch_count() == n0 + 1
+    cnt = want[1].cpu().numpy()
+    assert np.array_equal(cnt, got[1].cpu().numpy())
+    for i, k in enumerate(cnt):
+        assert torch.equal(want[0][i, :k], got[0][i, :k]) and torch.equal(want[2][i, :k], got[2][i, :k])
+
+
+@pytest.mark.parametrize("thr,shift", [(0.3, 0.0), (0.001, 0.0), (0.3, -2.6)])
+def test_large_image_832_vs_oracle(thr, shift, cuda_device):
+    """the 832x832 variant of config 5 -- 10 140 cells per image, more than the fused kernel can stage --
+    is routed to the large-image path; kept cells equal the CPU oracle's, floats to 1e-5."""
+    C, grids = 20, [(26, 26), (52, 52)]
+    h0, h1 = make_heads(3, C, grids, seed=5, conf_shift=shift)
+    tables = anchor_tables(VOC_ANCHORS, [832, 832])
+    dets, ids = run_fused(h0, h1, tables, C, thr, cuda_device)
+    o_det, o_ids = oracle.decode_nms(h0.numpy(), h1.numpy(), tables, C, thr)
+    assert sum(len(x) for x in ids) > 0
+    n_same = sum(int(np.array_equal(a, b)) for a, b in zip(ids, o_ids))
+    assert n_same >= len(ids) - 1, f"{len(ids) - n_same} images differ from the CPU oracle"
+    for a, ia, b, ib in zip(dets, ids, o_det, o_ids):
+        if np.array_equal(ia, ib):
+            np.testing.assert_allclose(a[:, :6], b[:, :6], rtol=RTOL, atol=ATOL)
+            assert np.array_equal(a[:, 6], b[:, 6])
 
 
 # ----------------------------------------------------------------------------- pairwise IoU
