@@ -124,6 +124,8 @@ int b200yolo_decode_nms_nhwc(const float *head0, const float *head1, int N, int 
  * (b200yolo_decode_nms_large_workspace_bytes(N, cells) bytes, 16-byte aligned) and the per-class greedy NMS
  * (utils/box.py:16-30 + torchvision nms) runs tile by tile against the kept boxes, without an n^2 mask.
  * Same outputs, same order, as b200yolo_decode_nms.  Limits: cells per image <= 16384.
+ * b200yolo_decode_head and b200yolo_nms switch to their large-image kernels by themselves (no workspace needed:
+ * the decode writes rows straight from registers, the NMS reads boxes from the caller's rows).
  */
 size_t b200yolo_decode_nms_large_workspace_bytes(int N, int cells_per_image);
 int b200yolo_decode_nms_large(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,

@@ -207,6 +207,43 @@ int launch_dn(DNParams &p, cudaStream_t st) {
     return launch_dn_shape<MODE, 1024>(p, make_layout(p.K, p.C, MODE, 1024, (MODE == MODE_DECODE) ? 0u : (uint32_t)(budget - need)), dev, st);
 }
 
+// large_nms.cuh: one CTA per image, sort keys in shared memory.  SRC 0: heads (records in p.rec), 1: caller rows
+template <int SRC>
+int launch_large(LargeParams &p, cudaStream_t st, const char *who) {
+    if (p.K > kLargeMaxKeys)
+        return fail(B200YOLO_EUNSUPPORTED, "%s: %d cells per image (limit %d)", who, p.K, kLargeMaxKeys);
+    p.P = 32;
+    while (p.P < p.K) p.P <<= 1;
+    p.T = p.K / 32 + p.C + 1;
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    const size_t smem = large_smem_bytes(p.P, p.C, p.T);
+    const int lim = smem_optin(dev);
+    if (smem > (size_t)lim)
+        return fail(B200YOLO_EUNSUPPORTED, "%s: %d cells, %d classes need %zu B of shared memory (limit %d B)", who, p.K, p.C,
+                    smem, lim);
+    {
+        static std::mutex mu;
+        static bool configured[64] = {false};
+        std::lock_guard<std::mutex> g(mu);
+        if (dev < 64 && !configured[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(decode_nms_large_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            configured[dev] = true;
+        }
+    }
+    decode_nms_large_kernel<SRC><<<p.N, kLargeThreads, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// does the shared-memory layout of decode_nms.cuh hold K cells at all (one CTA of 1024 threads, opt-in limit)?
+bool fits_one_cta(int K, int C, int mode) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;  // (the regular path reports the error)
+    return (int)make_layout(K, C, mode, 1024, 0).total <= smem_optin(dev);
+}
+
 }  // namespace
 
 extern "C" {
@@ -243,6 +280,19 @@ int b200yolo_decode_head(const float *head, int N, int A, int C, int H, int W, c
     p.conf_thr = conf_thr;
     p.iou = make_thr(0.45);
     p.out = rows; p.out_count = count; p.out_idx = ids;
+    if (!fits_one_cta(p.K, C, MODE_DECODE)) {  // e.g. a 52x52 head (8112 cells): rows straight from registers
+        if (N == 0) return 0;
+        LargeDecodeParams q;
+        memset(&q, 0, sizeof(q));
+        q.head = p.head[0];
+        q.N = N; q.A = A; q.C = C; q.K = p.K;
+        q.conf_thr = conf_thr;
+        q.rows = rows; q.count = count; q.ids = ids;
+        decode_head_large_kernel<<<N, kLargeThreads, 0, (cudaStream_t)stream>>>(q);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     return launch_dn<MODE_DECODE>(p, (cudaStream_t)stream);
 }
 
@@ -264,6 +314,18 @@ int b200yolo_nms(const float *cand0, const int *count0, int stride0, const float
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;
     p.cand[0] = cand0; p.cand_count[0] = count0; p.cand_stride[0] = stride0;
     p.cand[1] = cand1; p.cand_count[1] = count1; p.cand_stride[1] = stride1;
+    if (!fits_one_cta(p.K, C, MODE_NMS)) {  // more rows per image than one CTA stages: keys only (large_nms.cuh)
+        if (N == 0) return 0;
+        LargeParams q;
+        memset(&q, 0, sizeof(q));
+        q.N = N; q.C = C; q.attrs = 5 + C;
+        q.K = p.K;
+        q.iou = p.iou;
+        q.out = out; q.out_count = out_count; q.out_idx = out_idx;
+        q.cand[0] = cand0; q.cand_count[0] = count0; q.cand_stride[0] = stride0;
+        q.cand[1] = cand1; q.cand_count[1] = count1; q.cand_stride[1] = stride1;
+        return launch_large<1>(q, (cudaStream_t)stream, "nms");
+    }
     return launch_dn<MODE_NMS>(p, (cudaStream_t)stream);
 }
 
@@ -668,33 +730,11 @@ int b200yolo_decode_nms_large(const float *head0, const float *head1, int N, int
     fill_head(p.head[1], head1, A, H1, W1, anchor_wh + 2 * A);
     p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
     p.K = (int)cells;
-    p.P = 32;
-    while (p.P < p.K) p.P <<= 1;
-    p.T = p.K / 32 + C + 1;
     p.conf_thr = conf_thr;
     p.iou = make_thr(iou_thr);
     p.rec = (float4 *)workspace;
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;
-    int dev = 0;
-    if (int rc = current_device(&dev)) return rc;
-    const size_t smem = large_smem_bytes(p.P, C, p.T);
-    const int lim = smem_optin(dev);
-    if (smem > (size_t)lim)
-        return fail(B200YOLO_EUNSUPPORTED, "decode_nms_large: %d cells, %d classes need %zu B of shared memory (limit %d B)",
-                    p.K, C, smem, lim);
-    {
-        static std::mutex mu;
-        static bool configured[64] = {false};
-        std::lock_guard<std::mutex> g(mu);
-        if (dev < 64 && !configured[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(decode_nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-            configured[dev] = true;
-        }
-    }
-    decode_nms_large_kernel<<<N, kLargeThreads, smem, (cudaStream_t)stream>>>(p);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    return launch_large<0>(p, (cudaStream_t)stream, "decode_nms_large");
 }
 
 int b200yolo_compact_rows(const float *dets, const int *count, int N, int K, float *packed, int *offsets, void *stream) {

@@ -35,7 +35,10 @@ struct LargeParams {
     int T;               // tile slots: K/32 + C + 1
     float conf_thr;
     IouThr iou;
-    float4 *rec;         // workspace [N][K][2]
+    float4 *rec;         // workspace [N][K][2] (heads as the source)
+    const float *cand[2];        // SRC = 1 (utils.box.nms on caller rows): [N][stride][7] candidate rows of the two heads,
+    const int *cand_count[2];    // their per-image counts
+    int cand_stride[2];
     float *out;          // [N][K][7]
     int *out_count;      // [N]
     int *out_idx;        // [N][K] or null
@@ -47,53 +50,102 @@ __host__ __device__ inline size_t large_smem_bytes(int P, int C, int T) {
     return o + (size_t)(kLargeThreads / 32) * kLargeStageBytes;
 }
 
+struct LargeCell { float4 bx; float conf, best; int bi; };
+
+// one cell of a head (yolo_loss.py:186-199, 243-247); false: conf <= val_conf (:201)
+__device__ __forceinline__ bool large_decode_cell(const HeadDesc &hd, const float *hb, int C, int local, float conf_thr,
+                                                  LargeCell &o) {
+    const int attrs = 5 + C, HW = hd.HW;
+    const int a = fastdiv(local, hd.magicHW);
+    const int pos = local - a * HW;
+    const float *q = hb + (size_t)a * attrs * HW + pos;
+    const float tx = __ldcs(q), ty = __ldcs(q + HW), tw = __ldcs(q + 2 * (size_t)HW), th = __ldcs(q + 3 * (size_t)HW);
+    o.conf = sigmoid_fast(__ldcs(q + 4 * (size_t)HW));             // :189,197
+    if (!(o.conf > conf_thr)) return false;                        // :201
+    const float *qc = q + 5 * (size_t)HW;
+    float m1 = __ldg(qc);
+    for (int c = 1; c < C; ++c) m1 = fmaxf(m1, __ldg(qc + (size_t)c * HW));
+    float best;
+    const float win = tie_window(m1, &best);
+    const float lo = __fsub_rn(m1, win);
+    int bi = -1, nnear = 0;
+    for (int c = 0; c < C; ++c) {
+        const bool nr = __ldg(qc + (size_t)c * HW) >= lo;
+        if (nr && bi < 0) bi = c;
+        nnear += nr ? 1 : 0;
+    }
+    bi = max(bi, 0);
+    if (C > 1 && nnear != 1) best = class_tie_break(qc, HW, C, lo, m1, bi, &bi);   // :198
+    const int j = fastdiv(pos, hd.magicW), i = pos - j * hd.W;
+    const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);      // :187
+    const float ew = exp_fast(tw), eh = exp_fast(th);              // :188
+    const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);    // :194
+    const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+    const float bw = __fmul_rn(ew, hd.aw[a]), bh = __fmul_rn(eh, hd.ah[a]);   // :195
+    o.bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244-247
+    o.bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));
+    o.bx.z = __fadd_rn(bw, o.bx.x);
+    o.bx.w = __fadd_rn(bh, o.bx.y);
+    o.best = best;
+    o.bi = bi;
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long large_key(int cls, float sc, uint32_t cid) {
+    return ((unsigned long long)cls << 48) | ((unsigned long long)(~float_order_key(sc)) << 16) | (unsigned long long)cid;
+}
+
 __device__ __forceinline__ void large_decode_head(const LargeParams &p, int b, const HeadDesc &hd, int cid0,
                                                   unsigned long long *keys, int *cnt) {
-    const int C = p.C, attrs = p.attrs, HW = hd.HW;
-    const int cells = p.A * HW;
-    const float *hb = hd.ptr + (size_t)b * p.A * attrs * HW;
+    const int cells = p.A * hd.HW;
+    const float *hb = hd.ptr + (size_t)b * p.A * p.attrs * hd.HW;
     for (int local = threadIdx.x; local < cells; local += kLargeThreads) {
         const int cid = cid0 + local;
-        const int a = fastdiv(local, hd.magicHW);
-        const int pos = local - a * HW;
-        const float *q = hb + (size_t)a * attrs * HW + pos;
-        const float tx = __ldcs(q), ty = __ldcs(q + HW), tw = __ldcs(q + 2 * (size_t)HW), th = __ldcs(q + 3 * (size_t)HW);
-        const float conf = sigmoid_fast(__ldcs(q + 4 * (size_t)HW));   // yolo_loss.py:189,197
         unsigned long long key = ~0ull;
-        if (conf > p.conf_thr) {                                       // :201
-            const float *qc = q + 5 * (size_t)HW;
-            float m1 = __ldg(qc);
-            for (int c = 1; c < C; ++c) m1 = fmaxf(m1, __ldg(qc + (size_t)c * HW));
-            float best;
-            const float win = tie_window(m1, &best);
-            const float lo = __fsub_rn(m1, win);
-            int bi = -1, nnear = 0;
-            for (int c = 0; c < C; ++c) {
-                const bool nr = __ldg(qc + (size_t)c * HW) >= lo;
-                if (nr && bi < 0) bi = c;
-                nnear += nr ? 1 : 0;
-            }
-            bi = max(bi, 0);
-            if (C > 1 && nnear != 1) best = class_tie_break(qc, HW, C, lo, m1, bi, &bi);   // :198
-            const int j = fastdiv(pos, hd.magicW), i = pos - j * hd.W;
-            const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
-            const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
-            const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194
-            const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
-            const float bw = __fmul_rn(ew, hd.aw[a]), bh = __fmul_rn(eh, hd.ah[a]);   // :195
-            float4 bx;
-            bx.x = __fsub_rn(cx, __fmul_rn(bw, 0.5f));                   // :244-247
-            bx.y = __fsub_rn(cy, __fmul_rn(bh, 0.5f));
-            bx.z = __fadd_rn(bw, bx.x);
-            bx.w = __fadd_rn(bh, bx.y);
+        LargeCell o;
+        if (large_decode_cell(hd, hb, p.C, local, p.conf_thr, o)) {
             float4 *r = p.rec + ((size_t)b * p.K + cid) * 2;
-            r[0] = bx;
-            r[1] = make_float4(conf, best, make_ta(bx, p.iou), __int_as_float(bi));
-            const float sc = __fmul_rn(best, conf);                      // box.py:27
-            key = ((unsigned long long)bi << 48) | ((unsigned long long)(~float_order_key(sc)) << 16) | (unsigned long long)cid;
-            atomicAdd(&cnt[bi], 1);
+            r[0] = o.bx;
+            r[1] = make_float4(o.conf, o.best, make_ta(o.bx, p.iou), __int_as_float(o.bi));
+            key = large_key(o.bi, __fmul_rn(o.best, o.conf), (uint32_t)cid);   // box.py:27
+            atomicAdd(&cnt[o.bi], 1);
         }
         keys[cid] = key;
+    }
+}
+
+// SRC = 1: the caller's candidate rows (utils.box.nms, box.py:17: head 0 rows then head 1 rows)
+__device__ __forceinline__ const float *large_row(const LargeParams &p, int b, int K0, uint32_t cid) {
+    return ((int)cid < K0) ? p.cand[0] + ((size_t)b * p.cand_stride[0] + cid) * 7
+                           : p.cand[1] + ((size_t)b * p.cand_stride[1] + (cid - K0)) * 7;
+}
+
+__device__ __forceinline__ void large_load_rows(const LargeParams &p, int b, int K0, int Kb, unsigned long long *keys, int *cnt) {
+    for (int row = threadIdx.x; row < p.K; row += kLargeThreads) {
+        unsigned long long key = ~0ull;
+        if (row < Kb) {
+            const float *src = large_row(p, b, K0, (uint32_t)row);
+            const float conf = __ldg(src + 4), score = __ldg(src + 5), v = __ldg(src + 6);
+            const int c = (int)v;  // rows whose class column is not an integer in [0,C) match no `== i` (box.py:21)
+            if ((v == (float)c) && c >= 0 && c < p.C) {
+                key = large_key(c, __fmul_rn(score, conf), (uint32_t)row);
+                atomicAdd(&cnt[c], 1);
+            }
+        }
+        keys[row] = key;
+    }
+}
+
+// box and t*area*2^-13 of candidate `cid`
+template <int SRC>
+__device__ __forceinline__ void large_fetch(const LargeParams &p, int b, int K0, const float4 *rec, uint32_t cid, float4 &B, float &ta) {
+    if (SRC == 0) {
+        B = rec[2 * cid];              // (plain loads: the records were written by this kernel)
+        ta = rec[2 * cid + 1].z;
+    } else {
+        const float *src = large_row(p, b, K0, cid);
+        B = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+        ta = make_ta(B, p.iou);
     }
 }
 
@@ -112,6 +164,7 @@ __device__ __forceinline__ void large_bitonic_sort(unsigned long long *k, int P)
     }
 }
 
+template <int SRC>
 __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(const LargeParams p) {
     extern __shared__ __align__(16) unsigned char lsm[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(lsm);
@@ -137,8 +190,15 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
     if (lane < 8) sord[32 + lane] = make_uint2(sbox_addr, 0x7fc00000u);   // padding read by partial chunks: NaN area
     __syncthreads();
     // P1
-    large_decode_head(p, b, p.head[0], 0, keys, cnt);
-    large_decode_head(p, b, p.head[1], p.head[0].cells, keys, cnt);
+    int K0 = 0;
+    if (SRC == 0) {
+        large_decode_head(p, b, p.head[0], 0, keys, cnt);
+        large_decode_head(p, b, p.head[1], p.head[0].cells, keys, cnt);
+    } else {
+        K0 = min(p.cand_count[0][b], p.cand_stride[0]);
+        const int K1 = p.cand[1] ? min(p.cand_count[1][b], p.cand_stride[1]) : 0;
+        large_load_rows(p, b, K0, K0 + K1, keys, cnt);
+    }
     __syncthreads();
     // P2
     large_bitonic_sort(keys, p.P);
@@ -187,28 +247,21 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
         bool alive = idx < n;
         // my candidate (lanes past the end of the class take the last one; they are never alive)
         const uint32_t cid = (uint32_t)(keys[s0 + min(idx, n - 1)] & 0xffffull);
-        const float4 R = rec[2 * cid];
-        const float rta = rec[2 * cid + 1].z;
+        float4 R;
+        float rta;
+        large_fetch<SRC>(p, b, K0, rec, cid, R, rta);
         const bool rslow = __any_sync(kFullMask, rta != rta);   // a degenerate box in the tile: exact arithmetic
         // earlier tiles of the class: their 32 boxes are staged as the columns of one pair block (the records were
         // written in P1, so the loads do not wait for the tile's flag; the next tile's are issued before this one
         // is processed); the block's word AND the tile's kept word says whether a kept box suppresses my candidate
         float4 nB = R;
         float nta = rta;
-        if (t > 0) {
-            const uint32_t cidk = (uint32_t)(keys[s0 + lane] & 0xffffull);
-            nB = rec[2 * cidk];
-            nta = rec[2 * cidk + 1].z;
-        }
+        if (t > 0) large_fetch<SRC>(p, b, K0, rec, (uint32_t)(keys[s0 + lane] & 0xffffull), nB, nta);
         for (int rt = 0; rt < t; ++rt) {
             sbox[lane] = nB;
             sord[lane] = make_uint2(sbox_addr + 16u * lane, __float_as_uint(nta));
             const bool slow = rslow || __any_sync(kFullMask, nta != nta);
-            if (rt + 1 < t) {
-                const uint32_t cidk = (uint32_t)(keys[s0 + 32 * (rt + 1) + lane] & 0xffffull);
-                nB = rec[2 * cidk];
-                nta = rec[2 * cidk + 1].z;
-            }
+            if (rt + 1 < t) large_fetch<SRC>(p, b, K0, rec, (uint32_t)(keys[s0 + 32 * (rt + 1) + lane] & 0xffffull), nB, nta);
             __syncwarp();
             const uint32_t word = slow ? block_exact(sord, 32, R, p.iou.thr) : block_fast(sord, 32, R, rta, p.iou.thr);
             if (lane == 0) {
@@ -268,13 +321,63 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
         const int c = lo;
         const uint32_t cid = (uint32_t)(keys[start[c] + 32 * (g - ktile[c]) + lane] & 0xffffull);
         const int r = ready[g] + __popc(word & lanemask_lt());
-        const float4 bx = rec[2 * cid], cs = rec[2 * cid + 1];
         float *d = o + (size_t)r * 7;
-        d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
-        d[4] = cs.x; d[5] = cs.y; d[6] = (float)c;                  // cls_idx.float() yolo_loss.py:199
+        if (SRC == 0) {
+            const float4 bx = rec[2 * cid], cs = rec[2 * cid + 1];
+            d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
+            d[4] = cs.x; d[5] = cs.y; d[6] = (float)c;              // cls_idx.float() yolo_loss.py:199
+        } else {                                                    // the caller's own rows, bit for bit (box.py:29)
+            const float *src = large_row(p, b, K0, cid);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) d[k] = __ldg(src + k);
+        }
         if (p.out_idx) p.out_idx[(size_t)b * K + r] = (int)cid;
     }
     if (tid == 0) p.out_count[b] = misc[1];
+}
+
+// YOLOLoss.forward(input) for a head with more cells than the stand-alone decode kernel stages (e.g. 52x52x3 = 8112):
+// CTA per image, 1024 cells per round, rows written straight from registers in candidate order (a, j, i) (:203).
+struct LargeDecodeParams {
+    HeadDesc head;
+    int N, A, C, K;
+    float conf_thr;
+    float *rows;   // [N][K][7]
+    int *count;    // [N]
+    int *ids;      // [N][K] or null
+};
+
+__global__ void __launch_bounds__(kLargeThreads, 1) decode_head_large_kernel(const LargeDecodeParams p) {
+    __shared__ int s_warp[kLargeThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cells = p.K;
+    const float *hb = p.head.ptr + (size_t)b * p.A * (5 + p.C) * p.head.HW;
+    float *o = p.rows + (size_t)b * p.K * 7;
+    int running = 0;
+    for (int base = 0; base < cells; base += kLargeThreads) {
+        const int local = base + tid;
+        LargeCell c;
+        const bool pass = local < cells && large_decode_cell(p.head, hb, p.C, local, p.conf_thr, c);
+        const uint32_t bal = __ballot_sync(kFullMask, pass);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < kLargeThreads / 32; ++w) {
+            const int v = s_warp[w];
+            before += (w < warp) ? v : 0;
+            total += v;
+        }
+        if (pass) {
+            const int r = running + before + __popc(bal & lanemask_lt());
+            float *d = o + (size_t)r * 7;
+            d[0] = c.bx.x; d[1] = c.bx.y; d[2] = c.bx.z; d[3] = c.bx.w;
+            d[4] = c.conf; d[5] = c.best; d[6] = (float)c.bi;       // :199
+            if (p.ids) p.ids[(size_t)b * p.K + r] = local;
+        }
+        running += total;
+        __syncthreads();
+    }
+    if (tid == 0) p.count[b] = running;
 }
 
 }  // namespace b200yolo

@@ -303,6 +303,27 @@ def test_host_pipeline_equals_device_call(cuda_device):
         assert torch.equal(out_h[b, :k], out_d[b, :k].cpu())
 
 
+@pytest.mark.parametrize("thr,shift", [(0.3, 0.0), (0.3, -2.6)])
+def test_large_image_832_separate_entry_points(thr, shift, cuda_device):
+    """832x832 heads through the three separate entry points: YOLOLoss.forward(input) on a 52x52 head (8112 cells, more
+    than the stand-alone decode kernel stages), utils.box.nms on ~8 k candidate rows per image (more than the NMS
+    kernel stages) and the fused call: decode rows equal the fused path's candidates, the oracle's NMS on those rows
+    keeps the same cells in the same order, and nms(separate) == fused."""
+    C, grids = 20, [(26, 26), (52, 52)]
+    h0, h1 = make_heads(2, C, grids, seed=8, conf_shift=shift)
+    tables = anchor_tables(VOC_ANCHORS, [832, 832])
+    check_fused_against_oracle(h0, h1, tables, C, thr, cuda_device)
+    losses = [b200.YOLOLoss(VOC_ANCHORS, MASK[i], C, [832, 832], 0.6, 0.55, val_conf=thr) for i in range(2)]
+    d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+    p0, p1 = losses[0](d0), losses[1](d1)
+    sep, sep_idx = b200.nms((p0, p1), C, return_indices=True)
+    fus = b200.decode_nms(d0, d1, losses, C)
+    o_det, o_idx = oracle.nms([np.concatenate((a.cpu().numpy(), b.cpu().numpy()), 0) for a, b in zip(p0, p1)], C)
+    for a, ia, b, oi in zip(sep, sep_idx, fus, o_idx):
+        assert torch.equal(a, b) and len(a) > 0
+        assert np.array_equal(ia.cpu().numpy(), oi)
+
+
 def test_host_pipeline_large_images(cuda_device):
     """b200yolo_decode_nms_host routes images beyond the fused kernel's shared memory to the large-image path."""
     h0, h1 = make_heads(5, 20, [(26, 26), (52, 52)], seed=12, conf_shift=-1.0)
