@@ -70,7 +70,7 @@ extern "C" int b200yolo_decode_nms_host(const float *head0, const float *head1, 
     std::lock_guard<std::mutex> lock(g_host_mu);
     HostCtx &cx = g_host_ctx[device];
     // images too large for the fused kernel's shared memory go through b200yolo_decode_nms_large (records in a workspace)
-    const bool large = (long long)K > (long long)b200yolo_max_cells(device);
+    const bool large = !fits_one_cta((int)K, C, MODE_FUSED);
     const size_t b_ws = large ? b200yolo_decode_nms_large_workspace_bytes(chunk, (int)K) : 0;
     if (int rc = ensure_ctx(cx, device, per0 * chunk * 4, per1 * chunk * 4, K * 7 * chunk * 4, (size_t)chunk * 4, b_ws)) return rc;
     // one chunk: H2D -> kernel -> D2H on the slot's stream

@@ -144,6 +144,24 @@ __device__ __forceinline__ int tl_block_scan(int v, int *misc, int *total) {
     return before + inc - v;
 }
 
+// The matching runs either on the whole CTA (NT = kTLThreads) or on warp 0 alone (NT = 32: the backward kernel, whose
+// other warps stream the dense gradient planes meanwhile): scan and barrier of the cooperating group
+template <int NT>
+__device__ __forceinline__ int tl_group_scan(int v, int *misc, int *total) {
+    if (NT == 32) {
+        const int lane = threadIdx.x & 31;
+        const int inc = warp_inclusive_scan(v, lane);
+        *total = __shfl_sync(kFullMask, inc, 31);
+        return inc - v;
+    }
+    return tl_block_scan(v, misc, total);
+}
+template <int NT>
+__device__ __forceinline__ void tl_group_sync() {
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+}
+
 // decode one cell's box exactly like get_target (:84-92) + wh_to_x2y2 (:243-247)
 __device__ __forceinline__ float4 tl_decode_box(float tx, float ty, float tw, float th, int i, int j, float fW, float fH,
                                                 float aw, float ah) {
@@ -229,11 +247,12 @@ __device__ __noinline__ bool tl_below_exact(const float4 *gbox, const float *gar
 // (GT, k) pairs to the list in (GT, k) order (block scan: the list, and with it every sum, is the same run to run) and
 // flags their cells.  `lead` CTAs also write the per-GT outputs and the status (misc[2]; it travels to the host through
 // slot 12 of the CTA's partial sums).  Ends with the list complete and visible (trailing barrier); misc[0] = length.
+template <int NT>
 __device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, bool lead, const TLSmem &s) {
     const int tid = threadIdx.x;
     const int W = p.W, H = p.H, A = p.A, C = p.C;
     int carry = 0;
-    for (int t0 = 0; t0 < nG; t0 += kTLThreads) {  // (uniform trip count)
+    for (int t0 = 0; t0 < nG; t0 += NT) {  // (uniform trip count)
         const int t = t0 + tid;
         int cellbase = 0;
         unsigned amask = 0u;
@@ -283,7 +302,7 @@ __device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, b
             cellbase = gj * W + gi;
         }
         int total;
-        int e = carry + tl_block_scan(__popc(amask), s.misc, &total);
+        int e = carry + tl_group_scan<NT>(__popc(amask), s.misc, &total);
         for (int k = 0; k < A; ++k) {
             if ((amask >> k) & 1u) {
                 const uint32_t cell = (uint32_t)(k * H * W + cellbase);
@@ -296,16 +315,17 @@ __device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, b
         carry += total;
     }
     if (tid == 0) s.misc[0] = carry;
-    __syncthreads();
+    tl_group_sync<NT>();
 }
 
 // Duplicate chains and the list of distinct assigned cells (in list order): list[e].t gets the index of the next
 // assignment of the same cell; ucell[u] = index of the first assignment of the u-th distinct cell; misc[3] = count.
 // Every thread of the CTA must call it; ends with a barrier.
+template <int NT>
 __device__ __forceinline__ void tl_unique_cells(int nE, const TLSmem &s) {
     const int tid = threadIdx.x;
     int carry = 0;
-    for (int e0 = 0; e0 < nE; e0 += kTLThreads) {
+    for (int e0 = 0; e0 < nE; e0 += NT) {
         const int e = e0 + tid;
         int first = 0;
         if (e < nE) {
@@ -319,12 +339,12 @@ __device__ __forceinline__ void tl_unique_cells(int nE, const TLSmem &s) {
             s.list[e].t |= (uint32_t)(nx + 1) << 11;
         }
         int total;
-        const int u = carry + tl_block_scan(first, s.misc, &total);
+        const int u = carry + tl_group_scan<NT>(first, s.misc, &total);
         if (first) s.ucell[u] = (uint16_t)e;
         carry += total;
     }
     if (tid == 0) s.misc[3] = carry;
-    __syncthreads();
+    tl_group_sync<NT>();
 }
 
 __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams p) {
@@ -363,10 +383,10 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
 #pragma unroll
     for (int q = 0; q < 10; ++q) acc[q] = 0.0;
 
-    tl_match_gt(p, g0, nG, lead, sm);
+    tl_match_gt<kTLThreads>(p, g0, nG, lead, sm);
     const int nE = s_misc[0];
     const bool gt_degenerate = s_misc[1] != 0;
-    if (lead) tl_unique_cells(nE, sm);  // (lead is uniform in the CTA)
+    if (lead) tl_unique_cells<kTLThreads>(nE, sm);  // (lead is uniform in the CTA)
     const int nU = s_misc[3];
 
     // ---------------- P2: per-cell objectness / ignore mask ----------------
@@ -535,19 +555,25 @@ __device__ __forceinline__ double tl_ciou_grad(const float4 &gt, const TLBox4d &
     const double u = dx * dx + dy * dy;
     const double d_u[4] = {-dx, -dy, -dx, -dy};
     const double kk = 4.0 / (3.14159265358979323846 * 3.14159265358979323846);
-    const double delta = atan(w2 / h2) - atan((a2 - a1) / (b2 - b1));
+    // atan(x) - atan(y) = atan((x - y) / (1 + x y)) for x y > -1: one atan and one divide for positive sizes (every
+    // box the matching lets through); anything else takes the two-atan form
+    const double w1 = a2 - a1, h1 = b2 - b1;
+    const double delta = (w1 > 0.0 && h1 > 0.0 && w2 > 0.0 && h2 > 0.0) ? atan((w2 * h1 - w1 * h2) / (h2 * h1 + w2 * w1))
+                                                                       : atan(w2 / h2) - atan(w1 / h1);
     const double Aar = kk * delta * delta;
     const double D = 1.0 - iou + Aar + 0.000001;
+    // the chain below is what the CTA waits for: reciprocals once, multiplications per coordinate
+    const double r_uni2 = 1.0 / (uni * uni), r_c2 = 1.0 / (c * c), r_hw = 1.0 / (h2 * h2 + w2 * w2), r_D2 = 1.0 / (D * D);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const double d_inter = d_iw[q] * ih + iw * d_ih[q];
         const double d_union = d_w2[q] * h2 + w2 * d_h2[q] - d_inter;
-        const double d_iou = (d_inter * uni - inter * d_union) / (uni * uni);
+        const double d_iou = (d_inter * uni - inter * d_union) * r_uni2;
         const double d_c = d_cw[q] * ch + cw * d_ch[q];
-        const double d_dd = (d_u[q] * c - u * d_c) / (c * c);
-        const double d_A = 2.0 * kk * delta * (h2 * d_w2[q] - w2 * d_h2[q]) / (h2 * h2 + w2 * w2);
+        const double d_dd = (d_u[q] * c - u * d_c) * r_c2;
+        const double d_A = 2.0 * kk * delta * (h2 * d_w2[q] - w2 * d_h2[q]) * r_hw;
         const double d_D = -d_iou + d_A;
-        const double d_f = (2.0 * Aar * d_A * D - Aar * Aar * d_D) / (D * D);
+        const double d_f = (2.0 * Aar * d_A * D - Aar * Aar * d_D) * r_D2;
         dv[q] = (c == 0.0) ? 0.0 : d_iou - d_dd - d_f;
     }
     return (c == 0.0) ? 0.0 : iou - (u / c + Aar * Aar / D);
@@ -561,73 +587,71 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
     float4 *s_gbox = sm.gbox;
     int *s_gcls = sm.gcls;
     TLAssign *s_list = sm.list;
-    uint8_t *s_flag = sm.flag;
     int *s_misc = sm.misc;
-    const uint32_t flag_bytes = tl_up16((uint32_t)p.cells);
 
     const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
     const int tid = threadIdx.x;
     const int g0 = p.gt_off[b];
     int nG = p.gt_off[b + 1] - g0;
     const int HW = p.HW, W = p.W, A = p.A;
-    // programmatic dependent launch: the next kernel of the stream may start; this one reads what the forward
-    // call produced (sums, cell states)
+    // Programmatic dependent launch: the next kernel of the stream may start; this one reads what the forward call
+    // produced (sums, cell states).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (nG > p.gcap) nG = 0;  // (the forward call reported it)
+    float *gbase = p.grad_input + (size_t)b * A * p.attrs * HW;
+    const float *hbase = p.head + (size_t)b * A * p.attrs * HW;
+    const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
+    if (tid < 4) s_misc[tid] = 0;
+    {
+        // ---- streaming pass first: every cell as if it were not assigned (only the objectness channel can carry a
+        // gradient).  Its stores need nothing from the matching below, so they drain while the CTA sits in the
+        // matching's barriers; the assigned cells are overwritten after those barriers.
+        constexpr int NS = kTLThreads;
+        const int st = tid;
+        const double inv_w0 = (p.grad_out ? (double)__ldg(p.grad_out) : 1.0) * 2.0 / p.sums[B200YOLO_S_W];
+        const bool vec = (HW & 3) == 0 && (((uintptr_t)p.grad_input | (uintptr_t)p.head) & 15) == 0;
+        if (vec) {
+            // 4 consecutive cells of one anchor plane per thread: 16-byte loads / stores (the slice bounds are multiples of 32)
+            for (int cell = cell_lo + 4 * st; cell < cell_hi; cell += 4 * NS) {
+                const int a = (int)(((float)cell + 0.5f) * p.invHW);
+                const int pos = cell - a * HW;   // multiple of 4; HW is a multiple of 4: the group stays inside the plane
+                const size_t off = (size_t)a * p.attrs * HW + pos;
+                const uchar4 cs4 = *reinterpret_cast<const uchar4 *>(p.cell_state_in + (size_t)b * p.cells + cell);
+                const float4 tc = __ldg(reinterpret_cast<const float4 *>(hbase + off + 4 * (size_t)HW));
+                float4 gc;
+                gc.x = (cs4.x == 1) ? (float)((double)sigmoid_fast(tc.x) * inv_w0) : 0.f;   // target 0
+                gc.y = (cs4.y == 1) ? (float)((double)sigmoid_fast(tc.y) * inv_w0) : 0.f;
+                gc.z = (cs4.z == 1) ? (float)((double)sigmoid_fast(tc.z) * inv_w0) : 0.f;
+                gc.w = (cs4.w == 1) ? (float)((double)sigmoid_fast(tc.w) * inv_w0) : 0.f;
+                float *g = gbase + off;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < p.attrs; ++t) __stcs(reinterpret_cast<float4 *>(g + (size_t)t * HW), t == 4 ? gc : z);
+            }
+        } else {
+            for (int cell = cell_lo + st; cell < cell_hi; cell += NS) {
+                const int a = (int)(((float)cell + 0.5f) * p.invHW);
+                const int pos = cell - a * HW;
+                const size_t off = (size_t)a * p.attrs * HW + pos;
+                const unsigned char cs1 = p.cell_state_in[(size_t)b * p.cells + cell];
+                const float tc = __ldg(hbase + off + 4 * (size_t)HW);
+                float gconf = 0.f;
+                if (cs1 == 1) gconf = (float)((double)sigmoid_fast(tc) * inv_w0);  // target 0
+                float *g = gbase + off;
+                for (int t = 0; t < p.attrs; ++t) __stcs(g + (size_t)t * HW, t == 4 ? gconf : 0.f);
+            }
+        }
+    }
+    // ---- the image's assignments (the same deterministic list as the forward's)
+    __syncthreads();
+    tl_match_gt<kTLThreads>(p, g0, nG, false, sm);
+    tl_unique_cells<kTLThreads>(s_misc[0], sm);
+    __syncthreads();
+    const int nE = s_misc[0], nU = s_misc[3];
     const double go = p.grad_out ? (double)__ldg(p.grad_out) : 1.0;
     const double inv_w = go * 2.0 / p.sums[B200YOLO_S_W];                                    // d L_dense / d o = 2 (o - t) w / sum w
     const double n_assign = p.sums[B200YOLO_S_NASSIGN];
     const double inv_n = n_assign > 0.0 ? go * (double)p.iou_weighting * 2.0 / n_assign : 0.0;  // d (w_iou * L_iou) / d v = 2 (v - 1) / n
-    float *gbase = p.grad_input + (size_t)b * A * p.attrs * HW;
-    const float *hbase = p.head + (size_t)b * A * p.attrs * HW;
-
-
-    // ---- streaming pass first: every cell as if it were not assigned (only the objectness channel can carry a
-    // gradient).  Its stores need nothing from the matching below, so they drain while the CTA sits in the
-    // matching's barriers; the assigned cells are overwritten after those barriers.
-    const int cell_lo = split * p.chunk, cell_hi = min(cell_lo + p.chunk, p.cells);
-    const bool vec = (HW & 3) == 0 && (((uintptr_t)p.grad_input | (uintptr_t)p.head) & 15) == 0;
-    if (vec) {
-        // 4 consecutive cells of one anchor plane per thread: 16-byte loads / stores (the slice bounds are multiples of 32)
-        for (int cell = cell_lo + 4 * tid; cell < cell_hi; cell += 4 * kTLThreads) {
-            const int a = (int)(((float)cell + 0.5f) * p.invHW);
-            const int pos = cell - a * HW;   // multiple of 4; HW is a multiple of 4: the group stays inside the plane
-            const size_t off = (size_t)a * p.attrs * HW + pos;
-            const uchar4 st = *reinterpret_cast<const uchar4 *>(p.cell_state_in + (size_t)b * p.cells + cell);
-            const float4 tc = __ldg(reinterpret_cast<const float4 *>(hbase + off + 4 * (size_t)HW));
-            float4 gc;
-            gc.x = (st.x == 1) ? (float)((double)sigmoid_fast(tc.x) * inv_w) : 0.f;   // target 0
-            gc.y = (st.y == 1) ? (float)((double)sigmoid_fast(tc.y) * inv_w) : 0.f;
-            gc.z = (st.z == 1) ? (float)((double)sigmoid_fast(tc.z) * inv_w) : 0.f;
-            gc.w = (st.w == 1) ? (float)((double)sigmoid_fast(tc.w) * inv_w) : 0.f;
-            // (an assigned cell of the group gets its real values below, after the barrier)
-            float *g = gbase + off;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t = 0; t < p.attrs; ++t) __stcs(reinterpret_cast<float4 *>(g + (size_t)t * HW), t == 4 ? gc : z);
-        }
-    } else {
-        for (int cell = cell_lo + tid; cell < cell_hi; cell += kTLThreads) {
-            const int a = (int)(((float)cell + 0.5f) * p.invHW);
-            const int pos = cell - a * HW;
-            const size_t off = (size_t)a * p.attrs * HW + pos;
-            const unsigned char st = p.cell_state_in[(size_t)b * p.cells + cell];
-            const float tc = __ldg(hbase + off + 4 * (size_t)HW);
-            float gconf = 0.f;
-            if (st == 1) gconf = (float)((double)sigmoid_fast(tc) * inv_w);  // target 0
-            float *g = gbase + off;
-            for (int t = 0; t < p.attrs; ++t) __stcs(g + (size_t)t * HW, t == 4 ? gconf : 0.f);
-        }
-    }
-
-    // ---- the image's assignments (the same deterministic list as the forward's)
-    if (tid < 4) s_misc[tid] = 0;
-    for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
-    if (nG > p.gcap) nG = 0;  // (the forward call reported it)
-    __syncthreads();
-    tl_match_gt(p, g0, nG, false, sm);
-    const int nE = s_misc[0];
-    tl_unique_cells(nE, sm);
-    const int nU = s_misc[3];
 
     // ---- assigned cells of this CTA's slice (after the barrier: they overwrite what the streaming pass stored)
     {
@@ -656,41 +680,56 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
             c4.w = gl * (dv[3] - dv[1]) * 0.5 * bh;
             sm.contrib[e] = c4;
         }
-        __syncthreads();
-        // thread per (distinct cell, channel): all logit loads of the CTA are in flight together
+        // Objectness / class channels of the distinct assigned cells need nothing from the fp64 terms above, which
+        // keep the first ceil(nE / 32) warps busy for a long dependent chain: the OTHER warps take these channels
+        // meanwhile (thread per (cell, channel), all logit loads in flight together).
         const int attrs = p.attrs;
-        for (int it = tid; it < nU * attrs; it += kTLThreads) {
-            const int u = it / attrs, t = it - u * attrs;
+        {
+            int wbusy = (nE + 31) >> 5;
+            if (wbusy > kTLWarps - 1) wbusy = 0;               // (everybody is busy: share the work evenly afterwards)
+            const int first = 32 * wbusy, nw = kTLThreads - first;
+            const int per = attrs - 4;
+            if (tid >= first || wbusy == 0) {
+                for (int it = tid - first; it < nU * per; it += nw) {
+                    const int u = it / per, t = 4 + (it - u * per);
+                    int f = sm.ucell[u];
+                    const uint32_t cell = s_list[f].cell;
+                    if ((int)cell < cell_lo || (int)cell >= cell_hi) continue;
+                    const int a = (int)(((float)cell + 0.5f) * p.invHW);
+                    const int pos = (int)cell - a * HW;
+                    const size_t off = ((size_t)a * attrs + t) * HW + pos;
+                    const float o = sigmoid_f(__ldg(hbase + off));
+                    float target = 1.0f;                       // objectness of an assigned cell (:149-150)
+                    if (t > 4) {                               // class t-5: 0.95 if assigned to the cell, else 0.05 (:425-434)
+                        bool hit = false;
+                        while (f >= 0) {
+                            const uint32_t tn = s_list[f].t;
+                            hit = hit || (s_gcls[tl_entry_gt(tn)] == t - 5);
+                            f = tl_entry_next(tn);
+                        }
+                        target = hit ? 0.95f : 0.05f;
+                    }
+                    gbase[off] = (float)(((double)o - (double)target) * inv_w);
+                }
+            }
+        }
+        __syncthreads();
+        // box channels: thread per (distinct cell, channel), sum over the cell's assignments (duplicates add up)
+        for (int it = tid; it < nU * 4; it += kTLThreads) {
+            const int u = it >> 2, t = it & 3;
             int f = sm.ucell[u];
             const uint32_t cell = s_list[f].cell;
             if ((int)cell < cell_lo || (int)cell >= cell_hi) continue;
             const int a = (int)(((float)cell + 0.5f) * p.invHW);
             const int pos = (int)cell - a * HW;
             const size_t off = ((size_t)a * attrs + t) * HW + pos;
-            float gv;
-            if (t < 4) {                                   // box channels: sum over the cell's assignments (duplicates add up)
-                double acc4 = 0.0;
-                while (f >= 0) {
-                    const double4 c4 = sm.contrib[f];
-                    acc4 += (t == 0) ? c4.x : (t == 1) ? c4.y : (t == 2) ? c4.z : c4.w;
-                    f = tl_entry_next(s_list[f].t);
-                }
-                gv = (float)acc4;
-            } else {
-                const float o = sigmoid_f(__ldg(hbase + off));
-                float target = 1.0f;                       // objectness of an assigned cell (:149-150)
-                if (t > 4) {                               // class t-5: 0.95 if assigned to the cell, else 0.05 (:425-434)
-                    bool hit = false;
-                    while (f >= 0) {
-                        const uint32_t tn = s_list[f].t;
-                        hit = hit || (s_gcls[tl_entry_gt(tn)] == t - 5);
-                        f = tl_entry_next(tn);
-                    }
-                    target = hit ? 0.95f : 0.05f;
-                }
-                gv = (float)(((double)o - (double)target) * inv_w);
+            double acc4 = 0.0;
+            while (f >= 0) {
+                const double4 c4 = sm.contrib[f];
+                acc4 += (t == 0) ? c4.x : (t == 1) ? c4.y : (t == 2) ? c4.z : c4.w;
+                f = tl_entry_next(s_list[f].t);
             }
-            gbase[off] = gv;
+            gbase[off] = (float)acc4;
         }
     }
 }
