@@ -257,6 +257,58 @@ def test_compile_time_shapes_equal_runtime_shape_path(C, grids, anchors, img, cu
         assert torch.equal(a[0][i, :k], b[0][i, :k]) and torch.equal(a[2][i, :k], b[2][i, :k])
 
 
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 128, 129, 257])
+def test_fused_tile_boundaries_one_class(n, cuda_device):
+    """every candidate in ONE class, n of them: class sizes around the 32-row tile boundaries of the pair masks
+    (one anchor, one class, 1 x k grids, threshold below every conf) -- kept indices equal the oracle's."""
+    k0 = max(1, n // 3)
+    k1 = n - k0
+    if k1 == 0:
+        k0, k1 = 1, 1          # (n = 1: two cells, the second head's logit is pushed below the threshold)
+    g = torch.Generator().manual_seed(1000 + n)
+    h0 = torch.randn(3, 6, 1, k0, generator=g)
+    h1 = torch.randn(3, 6, 1, k1, generator=g)
+    # big boxes on a tiny grid: many overlaps, so chains of suppressions cross tile borders
+    h0[:, 2:4] = h0[:, 2:4] * 0.3 + 1.0
+    h1[:, 2:4] = h1[:, 2:4] * 0.3 + 1.0
+    thr = -1.0
+    if n == 1:
+        h1[:, 4] = -30.0
+        thr = 1e-6
+    tables = np.array([[[0.5, 0.4]], [[0.3, 0.6]]], np.float32)
+    dets, ids = check_fused_against_oracle(h0, h1, tables, 1, thr, cuda_device)
+    o_det, o_ids = oracle.decode_nms(h0.numpy(), h1.numpy(), tables, 1, thr)
+    for ia, ib in zip(ids, o_ids):
+        assert np.array_equal(ia, ib)
+    # and the large-image kernel on the same input
+    a = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, 1, thr, want_idx=True)
+    b = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, 1, thr, want_idx=True, force_large=True)
+    assert torch.equal(a[1], b[1])
+    for i, k in enumerate(a[1].cpu().numpy()):
+        assert torch.equal(a[0][i, :k], b[0][i, :k]) and torch.equal(a[2][i, :k], b[2][i, :k])
+
+
+def test_fused_random_shapes_vs_oracle(cuda_device):
+    """40 random small configurations (anchors per head, classes, non-square grids, thresholds, objectness shift):
+    fused kernel == decode kernel + oracle NMS, bit for bit."""
+    r = np.random.RandomState(2024)
+    for trial in range(40):
+        A = int(r.randint(1, 4))
+        C = int(r.choice([1, 2, 3, 5, 7, 20, 33]))
+        H0, W0 = int(r.randint(1, 9)), int(r.randint(1, 9))
+        H1, W1 = int(r.randint(1, 17)), int(r.randint(1, 17))
+        N = int(r.randint(1, 5))
+        thr = float(r.choice([0.05, 0.3, 0.5, 0.9]))
+        shift = float(r.choice([0.0, -1.5, 1.5]))
+        g = torch.Generator().manual_seed(trial)
+        h0 = torch.randn(N, A * (5 + C), H0, W0, generator=g)
+        h1 = torch.randn(N, A * (5 + C), H1, W1, generator=g)
+        h0.view(N, A, 5 + C, H0, W0)[:, :, 4] += shift
+        h1.view(N, A, 5 + C, H1, W1)[:, :, 4] += shift
+        tables = (r.rand(2, A, 2) * 0.6 + 0.05).astype(np.float32)
+        check_fused_against_oracle(h0, h1, tables, C, thr, cuda_device)
+
+
 def test_fused_matches_separate_entry_points(cuda_device):
     """decode_nms(out0,out1) == nms((loss0(out0), loss1(out1))) -- the three separate
     entry points stay callable and equal."""
