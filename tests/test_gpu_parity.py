@@ -598,6 +598,31 @@ def test_loss_backward_vs_oracle_config4_shapes(N, G, grid, C, cuda_device):
     assert np.abs(g - o).max() <= GRAD_TOL * np.abs(o).max()
 
 
+def test_loss_random_shapes_vs_oracle(cuda_device):
+    """25 random small configurations (1-3 anchors of this head out of 6, classes, non-square grids, ragged GT counts
+    incl. empty images, thresholds): assignments bit-exact, the 7-tuple to 1e-5, gradient vs the float64 oracle."""
+    r = np.random.RandomState(77)
+    for trial in range(25):
+        A = int(r.randint(1, 4))
+        mask = sorted(r.choice(6, A, replace=False).tolist())
+        C = int(r.choice([1, 2, 5, 20]))
+        H, W = int(r.randint(2, 14)), int(r.randint(2, 14))
+        N = int(r.randint(1, 5))
+        G = [int(r.choice([0, 1, 3, 17, 60])) for _ in range(N)]
+        ign = float(r.choice([0.3, 0.5623606200028424, 0.7]))
+        iou_t = float(r.choice([0.2, 0.5497280113447018, 0.9]))
+        g = torch.Generator().manual_seed(500 + trial)
+        head = torch.randn(N, A * (5 + C), H, W, generator=g).numpy()
+        targets = synth_targets(N, G, C, seed=900 + trial)
+        img = [W * 16, H * 16]
+        args = (head, targets, VOC_ANCHORS, mask, C, img, ign, iou_t, 0.021830872589525777)
+        compare_loss_with_oracle(*args, cuda_device)
+        got, _ = gpu_loss_grad(*args, cuda_device)
+        o = oracle.target_loss_backward(*args)
+        assert np.array_equal(got != 0, o != 0), f"trial {trial}: gradient support differs"
+        assert np.abs(got - o).max() <= GRAD_TOL * max(np.abs(o).max(), 1e-30), f"trial {trial}"
+
+
 def test_loss_without_grad_has_no_graph(cuda_device):
     head = make_heads(2, 20, [(11, 11)], seed=3)[0].to(cuda_device)
     l = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.55)
