@@ -522,6 +522,32 @@ def run_b200(args, wl):
                                                "ms_per_step": float(tc.item()),
                                                "bytes_gathered_per_rank": int(world * kept_per_launch * 28)}
 
+            # the same gather fused into the kernel: the output phase stores the kept rows into every rank's buffer over
+            # NVLink peer mappings (b200yolo_decode_nms_gather); the fence is the cross-rank barrier a consumer needs
+            try:
+                pg = b2dist.PeerGather(N, K)
+
+                def pstep2(i):
+                    h0, h1 = sets[i % R]
+                    pg.decode_nms(h0, h1, tables, C, conf)
+                    pg.fence()
+                for i in range(3):
+                    pstep2(i)
+                barrier()
+                pgms = time_loop(pstep2, max(10, args.steps // 4)) / max(10, args.steps // 4)
+                tp = torch.tensor([pgms], dtype=torch.float64, device=dev)
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+                same = bool(torch.equal(pg.counts[rank * N:(rank + 1) * N], cnt))
+                extra["with_peer_gather"] = {"images_per_s": world * N / (float(tp.item()) * 1e-3),
+                                             "ms_per_step": float(tp.item()),
+                                             "bytes_stored_per_rank": int(world * kept_per_launch * 28),
+                                             "counts_equal_plain_launch": same,
+                                             "note": "decode + NMS + all-gather in ONE kernel (peer stores over NVLink) + a "
+                                                     "1-element all-reduce as the fence, per step"}
+                pg.close()
+            except Exception as e:  # noqa: BLE001
+                extra["with_peer_gather"] = {"error": repr(e)}
+
     if rank == 0:
         peaks = {}
         try:

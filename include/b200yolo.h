@@ -133,6 +133,30 @@ int b200yolo_decode_nms_large(const float *head0, const float *head1, int N, int
                               int *out_count, int *out_idx, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * Decode + NMS fused with the data-parallel all-gather of the detections (the reference is single-GPU; the
+ * north star shards the batch by image over the GPUs of one NVSwitch box and all-gathers the per-rank detections).
+ * Rank `rank` of R post-processes its N images and its output phase stores every kept row straight into the gather
+ * buffer of EVERY rank -- peer_out[r] dev [R*N][K][7] and peer_count[r] dev int32 [R*N] on rank r, image slot
+ * rank*N + b -- its own through local stores, the others' through NVLink peer mappings (b200yolo_peer_open), so the
+ * transfer overlaps the NMS of the images still in flight instead of following the kernel as a separate collective.
+ * peer_out / peer_count are HOST arrays of R device pointers (R <= 8).  When every rank's launch has completed
+ * (any stream-ordered barrier across the ranks, e.g. a 1-element all-reduce) all R buffers hold the whole batch.
+ */
+int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                               int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *const *peer_out,
+                               int *const *peer_count, int R, int rank, void *stream);
+
+/*
+ * Peer-visible device memory for the call above: b200yolo_peer_alloc = cudaMalloc (zero-filled) + a 64-byte CUDA IPC
+ * handle that the other ranks of the node pass to b200yolo_peer_open (cudaIpcOpenMemHandle with lazy peer access);
+ * b200yolo_peer_close / b200yolo_peer_free undo them.
+ */
+int b200yolo_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64);
+int b200yolo_peer_open(const unsigned char *handle64, void **dev_ptr);
+int b200yolo_peer_close(void *dev_ptr);
+int b200yolo_peer_free(void *dev_ptr);
+
+/*
  * Same computation from HOST buffers (the reference-facing call bench.py times
  * as "e2e"): heads are copied host->device in image chunks on two streams,
  * post-processed, and detections + counts copied back, overlapped.  Pinned

@@ -351,6 +351,70 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
 }
 
+int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
+                               int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *const *peer_out,
+                               int *const *peer_count, int R, int rank, void *stream) {
+    if (!head0 || !head1 || !anchor_wh || !peer_out || !peer_count) return fail(B200YOLO_EINVAL, "decode_nms_gather: null pointer");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
+        return fail(B200YOLO_EINVAL, "decode_nms_gather: bad shape");
+    if (R < 1 || R > kMaxPeers || rank < 0 || rank >= R)
+        return fail(B200YOLO_EINVAL, "decode_nms_gather: %d ranks (1..%d), rank %d", R, kMaxPeers, rank);
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_gather: NaN threshold");
+    for (int r = 0; r < R; ++r)
+        if (!peer_out[r] || !peer_count[r]) return fail(B200YOLO_EINVAL, "decode_nms_gather: null buffer of rank %d", r);
+    const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
+    if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms_gather: more than 65535 cells per image");
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    fill_head(p.head[0], head0, A, H0, W0, anchor_wh);
+    fill_head(p.head[1], head1, A, H1, W1, anchor_wh + 2 * A);
+    p.nheads = 2;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.K = (int)cells;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(iou_thr);
+    p.gR = R;
+    p.gslot = rank * N;
+    for (int r = 0; r < R; ++r) { p.gout[r] = peer_out[r]; p.gcount[r] = peer_count[r]; }
+    return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
+}
+
+/* Peer-visible device memory for the fused all-gather: cudaMalloc + an IPC handle another process of the node opens. */
+int b200yolo_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64) {
+    if (!dev_ptr || !handle64 || bytes == 0) return fail(B200YOLO_EINVAL, "peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *ptr = nullptr;
+    CUDA_TRY(cudaMalloc(&ptr, bytes));
+    cudaError_t e = cudaMemset(ptr, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        return cuda_fail(e, "peer_alloc");
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = ptr;
+    return 0;
+}
+
+int b200yolo_peer_open(const unsigned char *handle64, void **dev_ptr) {
+    if (!dev_ptr || !handle64) return fail(B200YOLO_EINVAL, "peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int b200yolo_peer_close(void *dev_ptr) {
+    if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int b200yolo_peer_free(void *dev_ptr) {
+    if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+    return 0;
+}
+
 int b200yolo_decode_nms_nhwc(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
                              int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
                              int *out_count, int *out_idx, void *stream) {

@@ -60,6 +60,7 @@
 namespace b200yolo {
 
 constexpr int kMaxAnchors = 8;
+constexpr int kMaxPeers = 8;        // GPUs of one NVSwitch box
 
 enum { MODE_FUSED = 0, MODE_DECODE = 1, MODE_NMS = 2 };
 
@@ -103,6 +104,12 @@ struct DNParams {
     float *out;
     int *out_count;
     int *out_idx;
+    // fused all-gather (b200yolo_decode_nms_gather): the output phase stores every kept row into the gather buffer of
+    // EVERY rank (its own and, through NVLink peer mappings, the others'), image slot gslot + b; out / out_count unused
+    int gR;                      // ranks (0: ordinary single-buffer output)
+    int gslot;                   // first image slot of this rank = rank * N
+    float *gout[kMaxPeers];      // [gR] rank r's buffer [gR*N][K][7]
+    int *gcount[kMaxPeers];      // [gR] rank r's counts [gR*N]
     // MODE_NMS inputs
     const float *cand[2];
     const int *cand_count[2];
@@ -963,7 +970,9 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
     const int ntiles = s.ktile[p.C];
-    float *o = p.out + (size_t)b * p.K * 7;
+    const int nbuf = (MODE == MODE_FUSED && p.gR > 0) ? p.gR : 1;   // fused all-gather: one copy per rank
+    const size_t img = (MODE == MODE_FUSED && p.gR > 0) ? (size_t)(p.gslot + b) : (size_t)b;
+    float *o = (MODE == MODE_FUSED && p.gR > 0) ? nullptr : p.out + img * p.K * 7;
     float *scr = s.scratch + warp * (32 * 7);
     // MODE_NMS: the caller's own rows are gathered bit-for-bit (pred_this_cls[index], box.py:29)
     const int K0 = (MODE == MODE_NMS) ? min(p.cand_count[0][b], p.cand_stride[0]) : 0;
@@ -978,7 +987,15 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
     for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
     for (int g = g0; g < g1; ++g) {
         if (g == ntiles) {
-            if (lane == 0) p.out_count[b] = before;
+            if (MODE == MODE_FUSED && p.gR > 0) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < kMaxPeers; ++r)
+                        if (r < nbuf) p.gcount[r][img] = before;
+                }
+            } else if (lane == 0) {
+                p.out_count[b] = before;
+            }
             break;
         }
         const uint32_t word = s.keptbits[g];
@@ -1004,12 +1021,28 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
             if (p.out_idx) p.out_idx[(size_t)b * p.K + before + r] = (int)cid;
         }
         __syncwarp();
-        float *dst = o + (size_t)7 * before;
         const int nf = 7 * nk;
+        if (MODE == MODE_FUSED && p.gR > 0) {
+            float v[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const int f = 32 * k + lane;
-            if (f < nf) dst[f] = scr[f];
+            for (int k = 0; k < 7; ++k) v[k] = (32 * k + lane < nf) ? scr[32 * k + lane] : 0.f;
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r) {  // peer stores travel over NVLink while the next tile is assembled
+                if (r >= nbuf) break;
+                float *dst = p.gout[r] + (img * p.K + before) * 7;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const int f = 32 * k + lane;
+                    if (f < nf) dst[f] = v[k];
+                }
+            }
+        } else {
+            float *dst = o + (size_t)7 * before;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int f = 32 * k + lane;
+                if (f < nf) dst[f] = scr[f];
+            }
         }
         __syncwarp();
         before += nk;

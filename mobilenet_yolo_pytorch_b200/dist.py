@@ -6,11 +6,13 @@ utils/box.py:16, yolo_loss.py:202-203).  The only exchange steps are
   * an all-gather of the fixed-stride detections + counts, and
   * an all-reduce(SUM) of the 16 loss partial sums (the normalisers of
     yolo_loss.py:55,224,170-178 are batch-global).
-No collective sits inside the data path."""
+No collective sits inside the data path.  ``PeerGather`` fuses the first exchange into the kernel: the output phase
+of decode + NMS stores the kept rows into every rank's gather buffer over NVLink peer mappings."""
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -66,3 +68,93 @@ def all_reduce_loss_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
 def split_targets(targets: List, world_size: int, rank: int) -> List:
     lo, hi = shard_bounds(len(targets), world_size, rank)
     return targets[lo:hi]
+
+
+class _RawCuda:
+    """zero-copy view of raw device memory for ``torch.as_tensor`` (CUDA array interface v2)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerGather:
+    """Decode + NMS fused with the all-gather of the detections (``b200yolo_decode_nms_gather``).
+
+    Every rank owns one gather buffer -- ``dets`` (world*n_local, K, 7) fp32 and ``counts`` (world*n_local,) int32 --
+    in memory the other ranks of the node map through CUDA IPC.  ``decode_nms`` post-processes this rank's shard and
+    its output phase stores the kept rows into ALL buffers (its own and, over NVLink, the peers'), so the transfer
+    overlaps the kernel instead of following it as a separate NCCL all-gather; ``fence`` is the cross-rank barrier after
+    which every buffer holds the whole batch (one tiny all-reduce on the current stream).  One process per GPU on one
+    NVSwitch box, at most 8 ranks; ``close`` releases the mappings."""
+
+    def __init__(self, n_local: int, cells_per_image: int, group=None, device: Optional[torch.device] = None):
+        import ctypes as C
+        from . import _lib
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("PeerGather: at most 8 ranks (one NVSwitch box)")
+        self.n_local, self.K = int(n_local), int(cells_per_image)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        total = self.world * self.n_local
+        self._row_bytes = (total * self.K * 7 * 4 + 255) // 256 * 256
+        nbytes = self._row_bytes + total * 4
+        with torch.cuda.device(self.device):
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(lib.b200yolo_peer_alloc(nbytes, C.byref(ptr), handle))
+            self._own = ptr.value
+            handles: List = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._bases, self._opened = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    self._bases.append(self._own)
+                    continue
+                p2 = C.c_void_p()
+                _lib.check(lib.b200yolo_peer_open(handles[r], C.byref(p2)))
+                self._bases.append(p2.value)
+                self._opened.append(p2.value)
+            self._out_ptrs = (C.c_void_p * self.world)(*self._bases)
+            self._cnt_ptrs = (C.c_void_p * self.world)(*[b + self._row_bytes for b in self._bases])
+            raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
+            self.dets = raw[:total * self.K * 7 * 4].view(torch.float32).view(total, self.K, 7)
+            self.counts = raw[self._row_bytes:].view(torch.int32)
+            self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
+        dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
+
+    def decode_nms(self, head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
+                   iou_thr: float = 0.45) -> None:
+        """launch on the current stream; results are complete on every rank after ``fence()``"""
+        from . import _lib, ops
+        ops._require_cuda(head0, "head0")
+        ops._require_cuda(head1, "head1")
+        head0, head1 = head0.contiguous(), head1.contiguous()
+        N, ch, H0, W0 = head0.shape
+        _, _, H1, W1 = head1.shape
+        A = ch // (5 + num_classes)
+        if N != self.n_local or A * (H0 * W0 + H1 * W1) != self.K:
+            raise RuntimeError("PeerGather.decode_nms: shard shape differs from the buffer's")
+        aw = ops._host_f32(anchor_wh2).reshape(2, A, 2)
+        _lib.check(_lib.load().b200yolo_decode_nms_gather(
+            head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
+            float(np.float32(conf_thr)), float(iou_thr), self._out_ptrs, self._cnt_ptrs, self.world, self.rank,
+            torch.cuda.current_stream(self.device).cuda_stream))
+
+    def fence(self) -> None:
+        """stream-ordered barrier across the ranks: when it completes, every rank's launch has completed and its
+        rows are in every buffer"""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self) -> None:
+        from . import _lib
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)     # nobody still writes into a buffer that is about to go away
+        for p2 in self._opened:
+            lib.b200yolo_peer_close(p2)
+        self._opened = []
+        if self._own:
+            self.dets = self.counts = None
+            lib.b200yolo_peer_free(self._own)
+            self._own = None

@@ -50,10 +50,19 @@ def _worker(rank, world, port, N, q):
         dets, cnt = b200.decode_nms_padded(h0[lo:hi].to(dev), h1[lo:hi].to(dev), losses)
         g_dets, g_cnt = b200.dist.all_gather_detections(dets, cnt)
         c_rows, c_cnt = b200.dist.all_gather_detections_compact(dets, cnt)
+        # the same gather fused into the kernel: kept rows stored into every rank's buffer over NVLink peer mappings
+        pg = b200.dist.PeerGather(hi - lo, dets.shape[1])
+        tables = b200.fused.head_anchor_table(losses)
+        for _ in range(3):   # repeated launches reuse the buffers
+            pg.decode_nms(h0[lo:hi].to(dev), h1[lo:hi].to(dev), tables, C, 0.3)
+            pg.fence()
+        torch.cuda.synchronize()
+        p_dets, p_cnt = pg.dets.cpu().numpy().copy(), pg.counts.cpu().numpy().copy()
+        pg.close()
         x = h1[lo:hi].to(dev).requires_grad_(True)
         tup = losses[1](x, targets[lo:hi])
         tup[0].backward()
-        q.put((rank, c_rows.cpu().numpy(), c_cnt.cpu().numpy(), g_dets.cpu().numpy(), g_cnt.cpu().numpy(), float(tup[0].detach()), [float(v) for v in tup[1:4]] + [float(tup[4]), tup[5], tup[6]],
+        q.put((rank, p_dets, p_cnt, c_rows.cpu().numpy(), c_cnt.cpu().numpy(), g_dets.cpu().numpy(), g_cnt.cpu().numpy(), float(tup[0].detach()), [float(v) for v in tup[1:4]] + [float(tup[4]), tup[5], tup[6]],
                x.grad.cpu().numpy(), lo, hi))
     finally:
         dist.destroy_process_group()
@@ -88,8 +97,10 @@ def test_two_gpu_shards_equal_single_gpu():
     tup[0].backward()
     grad = x.grad.cpu().numpy()
     want_rows = np.concatenate([dets[b, :cnt[b]] for b in range(N)], 0)
-    for rank, c_rows, c_cnt, g_dets, g_cnt, loss, stats, g, lo, hi in got:
-        assert np.array_equal(g_cnt, cnt) and np.array_equal(c_cnt, cnt)
+    for rank, p_dets, p_cnt, c_rows, c_cnt, g_dets, g_cnt, loss, stats, g, lo, hi in got:
+        assert np.array_equal(g_cnt, cnt) and np.array_equal(c_cnt, cnt) and np.array_equal(p_cnt, cnt)
+        for b in range(N):                               # fused peer gather: every rank holds the whole batch
+            assert np.array_equal(p_dets[b, :cnt[b]], dets[b, :cnt[b]])
         assert np.array_equal(c_rows, want_rows)            # compact gather: kept rows only, rank-then-image order
         for b in range(N):
             assert np.array_equal(g_dets[b, :cnt[b]], dets[b, :cnt[b]])
