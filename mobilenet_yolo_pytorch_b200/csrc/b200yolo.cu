@@ -375,7 +375,9 @@ int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, in
     p.iou = make_thr(iou_thr);
     p.gR = R;
     p.gslot = rank * N;
-    for (int r = 0; r < R; ++r) { p.gout[r] = peer_out[r]; p.gcount[r] = peer_count[r]; }
+    // every rank starts with its own buffer and walks the ring from there, so at any moment the ranks store into
+    // different peers instead of all hitting rank 0 first
+    for (int i = 0; i < R; ++i) { p.gout[i] = peer_out[(rank + i) % R]; p.gcount[i] = peer_count[(rank + i) % R]; }
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
 }
 
