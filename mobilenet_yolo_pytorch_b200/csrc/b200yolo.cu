@@ -106,13 +106,21 @@ constexpr int kTier1x64 = 162 * 1024;
 template <int MODE, int THREADS, int SHAPE>
 int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     static std::mutex mu;
-    static int configured[64] = {0};  // smem size opted into, per device
+    static int configured[2][64] = {{0}, {0}};  // smem size opted into, per kernel variant and device
+    using Kern = void (*)(const DNParams, const SmemLayout);
+    Kern kern = decode_nms_kernel<MODE, THREADS, SHAPE, 0>;
+    int variant = 0;
+    if constexpr (MODE == MODE_FUSED) {
+        if (p.gR > 0) {  // fused all-gather: the output phase stores into every rank's buffer
+            kern = decode_nms_kernel<MODE, THREADS, SHAPE, 1>;
+            variant = 1;
+        }
+    }
     {
         std::lock_guard<std::mutex> g(mu);
-        if (dev < 64 && configured[dev] < (int)L.total) {
-            CUDA_TRY(cudaFuncSetAttribute(decode_nms_kernel<MODE, THREADS, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem_optin(dev)));
-            configured[dev] = smem_optin(dev);
+        if (dev < 64 && configured[variant][dev] < (int)L.total) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin(dev)));
+            configured[variant][dev] = smem_optin(dev);
         }
     }
     // programmatic dependent launch: consecutive launches of this kernel overlap (decode_nms.cuh, pdl_trigger / pdl_wait)
@@ -127,7 +135,7 @@ int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = (p.flags & 2) ? 0 : 1;  // flag 2: plain stream order
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, decode_nms_kernel<MODE, THREADS, SHAPE>, p, L));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, L));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return 0;

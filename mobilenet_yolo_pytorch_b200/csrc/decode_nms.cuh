@@ -965,14 +965,14 @@ __device__ __forceinline__ void phase_pairs_sweep(const DNParams &p, const Smem 
 // output (class-ascending, score-descending); the warp assembles them in its scratch and
 // writes them with coalesced stores.
 // ---------------------------------------------------------------------------
-template <int MODE, int THREADS>
+template <int MODE, int THREADS, int GATHER>
 __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, int b) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
     const int ntiles = s.ktile[p.C];
-    const int nbuf = (MODE == MODE_FUSED && p.gR > 0) ? p.gR : 1;   // fused all-gather: one copy per rank
-    const size_t img = (MODE == MODE_FUSED && p.gR > 0) ? (size_t)(p.gslot + b) : (size_t)b;
-    float *o = (MODE == MODE_FUSED && p.gR > 0) ? nullptr : p.out + img * p.K * 7;
+    const int nbuf = (GATHER != 0) ? p.gR : 1;   // fused all-gather: one copy per rank
+    const size_t img = (GATHER != 0) ? (size_t)(p.gslot + b) : (size_t)b;
+    float *o = (GATHER != 0) ? nullptr : p.out + img * p.K * 7;
     float *scr = s.scratch + warp * (32 * 7);
     // MODE_NMS: the caller's own rows are gathered bit-for-bit (pred_this_cls[index], box.py:29)
     const int K0 = (MODE == MODE_NMS) ? min(p.cand_count[0][b], p.cand_stride[0]) : 0;
@@ -987,7 +987,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
     for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
     for (int g = g0; g < g1; ++g) {
         if (g == ntiles) {
-            if (MODE == MODE_FUSED && p.gR > 0) {
+            if (GATHER != 0) {
                 if (lane == 0) {
 #pragma unroll
                     for (int r = 0; r < kMaxPeers; ++r)
@@ -1022,7 +1022,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
         }
         __syncwarp();
         const int nf = 7 * nk;
-        if (MODE == MODE_FUSED && p.gR > 0) {
+        if (GATHER != 0) {
             float v[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) v[k] = (32 * k + lane < nf) ? scr[32 * k + lane] : 0.f;
@@ -1052,7 +1052,9 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
 // ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
-template <int MODE, int THREADS, int SHAPE>
+// GATHER: the fused all-gather variant of the output phase (its own instantiation, so the ordinary kernel's register
+// allocation is untouched)
+template <int MODE, int THREADS, int SHAPE, int GATHER = 0>
 __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, L, p.K, p.C, MODE);
@@ -1181,7 +1183,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     stamp(p, b, 4);
     // P6 (the mask buffer is dead now; the row scratch aliases it)
     pdl_wait();
-    phase_output<MODE, THREADS>(p, s, b);
+    phase_output<MODE, THREADS, GATHER>(p, s, b);
     stamp(p, b, 7);
 }
 
