@@ -1023,18 +1023,32 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
         __syncwarp();
         const int nf = 7 * nk;
         if (GATHER != 0) {
-            float v[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) v[k] = (32 * k + lane < nf) ? scr[32 * k + lane] : 0.f;
+            // NVLink likes long requests: the chunk (<= 224 floats, contiguous in every buffer, buffers 256-byte aligned)
+            // goes out as <= 2 sixteen-byte stores per lane plus one scalar store for the unaligned head and tail
+            const size_t e0 = (img * p.K + before) * 7;          // float index of the chunk in a buffer
+            const int hcnt = min((int)((4 - (e0 & 3)) & 3), nf);
+            const int nvec = (nf - hcnt) >> 2;
+            const int tail0 = hcnt + 4 * nvec;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            if (lane < nvec) {
+                const float *q = scr + hcnt + 4 * lane;
+                a0 = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            if (lane + 32 < nvec) {
+                const float *q = scr + hcnt + 4 * (lane + 32);
+                a1 = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            int hidx = -1;                                       // lanes 0-2: head floats, lanes 4-6: tail floats
+            if (lane < hcnt) hidx = lane;
+            else if (lane >= 4 && lane < 8 && tail0 + lane - 4 < nf) hidx = tail0 + lane - 4;
+            const float hv = (hidx >= 0) ? scr[hidx] : 0.f;
 #pragma unroll
             for (int r = 0; r < kMaxPeers; ++r) {  // peer stores travel over NVLink while the next tile is assembled
                 if (r >= nbuf) break;
-                float *dst = p.gout[r] + (img * p.K + before) * 7;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    const int f = 32 * k + lane;
-                    if (f < nf) dst[f] = v[k];
-                }
+                float *dst = p.gout[r] + e0;
+                if (lane < nvec) *reinterpret_cast<float4 *>(dst + hcnt + 4 * lane) = a0;
+                if (lane + 32 < nvec) *reinterpret_cast<float4 *>(dst + hcnt + 4 * (lane + 32)) = a1;
+                if (hidx >= 0) dst[hidx] = hv;
             }
         } else {
             float *dst = o + (size_t)7 * before;
