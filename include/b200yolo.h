@@ -153,6 +153,16 @@ int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, in
  */
 int b200yolo_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64);
 int b200yolo_peer_open(const unsigned char *handle64, void **dev_ptr);
+/*
+ * Fence for the fused all-gather without a collective.  b200yolo_peer_signal (stream-ordered after the launch): rank
+ * `rank` raises slot [rank] of the flag array of EVERY rank (peer_flags: HOST array of R device pointers to int[R]
+ * arrays living in the peer-visible buffers) to `value`, a step number that only grows.  b200yolo_peer_wait: returns
+ * to the stream once all R slots of this rank's own array are >= value, i.e. every rank's launch of this step has
+ * completed and its rows are in this rank's buffer; *timed_out (dev int, zero it once) is set instead if a peer does
+ * not arrive within timeout_s seconds (<= 60; default 5), so a dead peer cannot hang the GPU.
+ */
+int b200yolo_peer_signal(int *const *peer_flags, int R, int rank, int value, void *stream);
+int b200yolo_peer_wait(const int *own_flags, int R, int value, double timeout_s, int *timed_out, void *stream);
 int b200yolo_peer_close(void *dev_ptr);
 int b200yolo_peer_free(void *dev_ptr);
 

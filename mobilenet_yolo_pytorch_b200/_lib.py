@@ -43,6 +43,8 @@ SIGNATURES = {
                                              C.c_void_p]),
     "b200yolo_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "b200yolo_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b200yolo_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200yolo_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "b200yolo_peer_close": (C.c_int, [C.c_void_p]),
     "b200yolo_peer_free": (C.c_int, [C.c_void_p]),
     "b200yolo_decode_nms_host": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

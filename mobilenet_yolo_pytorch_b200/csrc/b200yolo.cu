@@ -215,6 +215,34 @@ int launch_dn(DNParams &p, cudaStream_t st) {
     return launch_dn_shape<MODE, 1024>(p, make_layout(p.K, p.C, MODE, 1024, (MODE == MODE_DECODE) ? 0u : (uint32_t)(budget - need)), dev, st);
 }
 
+// Fence of the fused all-gather without a collective: after its launch every rank raises its slot of the flag array
+// in EVERY rank's buffer to the step number (the stores of the launch before it in the stream are complete at that
+// kernel boundary), then waits until all slots of its own array have reached it.
+struct PeerFlagPtrs { int *p[kMaxPeers]; };
+
+__global__ void peer_signal_kernel(PeerFlagPtrs flags, int R, int rank, int value) {
+    const int r = threadIdx.x;
+    if (r < R) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(flags.p[r] + rank) = value;
+    }
+}
+
+__global__ void peer_wait_kernel(const int *own_flags, int R, int value, long long max_cycles, int *timed_out) {
+    const int r = threadIdx.x;
+    if (r < R) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile int *>(own_flags + r) < value) {
+            if (clock64() - t0 > max_cycles) {   // a peer died: report instead of hanging the GPU
+                *timed_out = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
 // large_nms.cuh: one CTA per image, sort keys in shared memory.  SRC 0: heads (records in p.rec), 1: caller rows
 template <int SRC>
 int launch_large(LargeParams &p, cudaStream_t st, const char *who) {
@@ -412,6 +440,30 @@ int b200yolo_peer_open(const unsigned char *handle64, void **dev_ptr) {
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int b200yolo_peer_signal(int *const *peer_flags, int R, int rank, int value, void *stream) {
+    if (!peer_flags || R < 1 || R > kMaxPeers || rank < 0 || rank >= R) return fail(B200YOLO_EINVAL, "peer_signal: bad argument");
+    PeerFlagPtrs f;
+    memset(&f, 0, sizeof(f));
+    for (int r = 0; r < R; ++r) {
+        if (!peer_flags[r]) return fail(B200YOLO_EINVAL, "peer_signal: null flag array of rank %d", r);
+        f.p[r] = peer_flags[r];
+    }
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, R, rank, value);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200yolo_peer_wait(const int *own_flags, int R, int value, double timeout_s, int *timed_out, void *stream) {
+    if (!own_flags || !timed_out || R < 1 || R > kMaxPeers) return fail(B200YOLO_EINVAL, "peer_wait: bad argument");
+    if (!(timeout_s > 0.0) || timeout_s > 60.0) timeout_s = 5.0;
+    const long long max_cycles = (long long)(timeout_s * 2.0e9);   // SM clock <= 2 GHz: at least timeout_s seconds
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(own_flags, R, value, max_cycles, timed_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

@@ -99,7 +99,8 @@ class PeerGather:
         lib = _lib.load()
         total = self.world * self.n_local
         self._row_bytes = (total * self.K * 7 * 4 + 255) // 256 * 256
-        nbytes = self._row_bytes + total * 4
+        self._flag_off = (self._row_bytes + total * 4 + 255) // 256 * 256     # int[8] arrival flags + int timed_out
+        nbytes = self._flag_off + 64
         with torch.cuda.device(self.device):
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
             _lib.check(lib.b200yolo_peer_alloc(nbytes, C.byref(ptr), handle))
@@ -117,9 +118,12 @@ class PeerGather:
                 self._opened.append(p2.value)
             self._out_ptrs = (C.c_void_p * self.world)(*self._bases)
             self._cnt_ptrs = (C.c_void_p * self.world)(*[b + self._row_bytes for b in self._bases])
+            self._flag_ptrs = (C.c_void_p * self.world)(*[b + self._flag_off for b in self._bases])
+            self._step = 0
             raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
             self.dets = raw[:total * self.K * 7 * 4].view(torch.float32).view(total, self.K, 7)
-            self.counts = raw[self._row_bytes:].view(torch.int32)
+            self.counts = raw[self._row_bytes:self._row_bytes + total * 4].view(torch.int32)
+            self._timed_out = raw[self._flag_off + 32:self._flag_off + 36].view(torch.int32)
             self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
 
@@ -141,10 +145,26 @@ class PeerGather:
             float(np.float32(conf_thr)), float(iou_thr), self._out_ptrs, self._cnt_ptrs, self.world, self.rank,
             torch.cuda.current_stream(self.device).cuda_stream))
 
-    def fence(self) -> None:
-        """stream-ordered barrier across the ranks: when it completes, every rank's launch has completed and its
-        rows are in every buffer"""
-        dist.all_reduce(self._flag, group=self.group)
+    def fence(self, collective: bool = False, timeout_s: float = 5.0) -> None:
+        """Stream-ordered barrier across the ranks: when it completes, every rank's launch has completed and its rows
+        are in every buffer.  Default: two tiny kernels -- this rank raises its arrival flag in every peer's buffer,
+        then waits for all flags of its own buffer (``check()`` tells whether a peer failed to arrive in time);
+        ``collective=True`` uses a 1-element NCCL all-reduce instead."""
+        if collective:
+            dist.all_reduce(self._flag, group=self.group)
+            return
+        from . import _lib
+        lib = _lib.load()
+        self._step += 1
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.b200yolo_peer_signal(self._flag_ptrs, self.world, self.rank, self._step, st))
+        _lib.check(lib.b200yolo_peer_wait(self._own + self._flag_off, self.world, self._step, float(timeout_s),
+                                          self._own + self._flag_off + 32, st))
+
+    def check(self) -> None:
+        """host-synchronising: raise if a fence gave up waiting for a peer"""
+        if int(self._timed_out.item()):
+            raise RuntimeError("PeerGather: a peer did not reach the fence in time")
 
     def close(self) -> None:
         from . import _lib
@@ -155,6 +175,6 @@ class PeerGather:
             lib.b200yolo_peer_close(p2)
         self._opened = []
         if self._own:
-            self.dets = self.counts = None
+            self.dets = self.counts = self._timed_out = None
             lib.b200yolo_peer_free(self._own)
             self._own = None
