@@ -52,6 +52,11 @@
 // The stand-alone decode (P1 + ordered compaction + store) and NMS (load rows,
 // P2..P6) kernels back YOLOLoss.forward(input) and utils.box.nms separately.
 //
+// Variants of the same kernel: channels-last heads (decode_head_nhwc: warps stage 32 cells and transpose through
+// shared memory, no NCHW copy); GATHER = 1 (b200yolo_decode_nms_gather): P6 stores every tile of kept rows into the
+// gather buffer of EVERY rank of the box over NVLink peer mappings -- the data-parallel all-gather fused into the
+// kernel.  Images with more cells than `U` can hold take large_nms.cuh.
+//
 // Consecutive launches overlap (programmatic dependent launch, see pdl_trigger / pdl_wait below): a launch
 // starts on the SM slots its predecessor leaves free and streams its heads under the predecessor's NMS.
 #pragma once
