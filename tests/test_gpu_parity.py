@@ -376,6 +376,41 @@ def test_large_image_832_separate_entry_points(thr, shift, cuda_device):
         assert np.array_equal(ia.cpu().numpy(), oi)
 
 
+def test_peer_gather_single_rank(cuda_device):
+    """b200yolo_decode_nms_gather with a world of one rank (the 2-GPU case is tests/test_dist_nccl.py): the gather
+    variant of the kernel writes the same rows and counts as the ordinary launch, through peer-visible memory, for
+    both fences, on dense and sparse heads, repeatedly into the same buffers."""
+    import socket
+    import torch.distributed as dist
+    own_group = not dist.is_initialized()
+    if own_group:
+        sock = socket.socket()
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+        sock.close()
+        torch.cuda.set_device(cuda_device)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=cuda_device)
+    try:
+        C, N = 20, 19
+        tables = anchor_tables(VOC_ANCHORS, [352, 352])
+        pg = b200.dist.PeerGather(N, 1815)
+        for it, shift in enumerate((0.0, -2.6, 0.0)):
+            h0, h1 = make_heads(N, C, [(11, 11), (22, 22)], seed=40 + it, conf_shift=shift)
+            d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+            want, wcnt = ops.decode_nms_padded(d0, d1, tables, C, 0.3)
+            pg.decode_nms(d0, d1, tables, C, 0.3)
+            pg.fence(collective=(it == 1))
+            torch.cuda.synchronize()
+            pg.check()
+            assert torch.equal(pg.counts, wcnt) and int(wcnt.sum()) > 0
+            for b, k in enumerate(wcnt.cpu().numpy()):
+                assert torch.equal(pg.dets[b, :k], want[b, :k])
+        pg.close()
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+
+
 def test_host_pipeline_large_images(cuda_device):
     """b200yolo_decode_nms_host routes images beyond the fused kernel's shared memory to the large-image path."""
     h0, h1 = make_heads(5, 20, [(26, 26), (52, 52)], seed=12, conf_shift=-1.0)
