@@ -374,6 +374,8 @@ def main():
     case_decode_nms("voc_sparse_n3", VOC, 3, 1, 0.3, conf_shift=-2.6)
     case_decode_nms("voc_none_n2", VOC, 2, 2, 0.999999)
     case_decode_nms("bdd_nonsquare_n2", BDD, 2, 4, 0.3, nonsquare=True)
+    # 832x832 input: 10 140 cells per image (the "~10k boxes" reading of config 5) -> the large-image kernels
+    case_decode_nms("voc832_sparse_n1", dict(VOC, img_size=[832, 832]), 1, 7, 0.3, conf_shift=-1.5)
     case_nms_ties()
     case_iou()
     case_loss("loss_voc_n3", VOC, 3, [6, 0, 14], 5)

@@ -72,7 +72,7 @@ def gpu_decode(head, anchor_wh, C, thr, dev):
 
 
 # ----------------------------------------------------------------------------- decode
-@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2"])
+@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2", "voc832_sparse_n1"])
 def test_decode_head_vs_golden_and_oracle(case, cuda_device):
     d = load_golden(case)
     C, thr = int(d["num_classes"]), float(d["val_conf"])
@@ -104,7 +104,7 @@ def test_yololoss_forward_eval_dropin(cuda_device):
 
 
 # ----------------------------------------------------------------------------- nms
-@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2", "nms_ties"])
+@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2", "voc832_sparse_n1", "nms_ties"])
 def test_nms_on_reference_candidates_bit_exact(case, cuda_device):
     """utils.box.nms fed the reference's own candidate rows: kept rows and keep
     indices must equal the reference's (torchvision) bit for bit."""
@@ -193,7 +193,7 @@ def check_fused_against_oracle(h0, h1, tables, C, thr, dev):
     return dets, ids
 
 
-@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2"])
+@pytest.mark.parametrize("case", ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2", "voc832_sparse_n1"])
 def test_fused_vs_golden(case, cuda_device):
     d = load_golden(case)
     C, thr = int(d["num_classes"]), float(d["val_conf"])

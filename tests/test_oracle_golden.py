@@ -13,7 +13,7 @@ from conftest import load_golden, unpack_ragged
 RTOL = 1e-5
 ATOL = 1e-6  # boxes are normalised to [0,1]; values near 0 need an absolute floor
 
-DECODE_CASES = ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2"]
+DECODE_CASES = ["voc_n2_conf03", "voc_sparse_n3", "voc_none_n2", "bdd_nonsquare_n2", "voc832_sparse_n1"]
 
 
 def head_anchor_wh(d, i):
