@@ -380,6 +380,8 @@ def main():
     case_iou()
     case_loss("loss_voc_n3", VOC, 3, [6, 0, 14], 5)
     case_loss("loss_bdd_nonsquare_n2", BDD, 2, [9, 4], 6, nonsquare=True)
+    # 100 / 60 GT boxes on the 11x11 and 22x22 grids: several GT boxes share a cell and an anchor (duplicate chains)
+    case_loss("loss_voc_dense_n2", VOC, 2, [100, 60], 8)
     case_map("map_n40_c6", 40, 6, 11)
     case_seg("seg_n3_c2", 3, 2, 24, 40, 13)
 

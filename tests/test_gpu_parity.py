@@ -526,7 +526,7 @@ def compare_loss_with_oracle(head, targets, anchors, mask, C, img, ign, iou_t, i
     return res
 
 
-@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2", "loss_voc_dense_n2"])
 def test_target_loss_vs_golden(case, cuda_device):
     d = load_golden(case)
     C = int(d["num_classes"])
@@ -604,7 +604,7 @@ def gpu_loss_grad(head, targets, anchors, mask, C, img, ign, iou_t, iou_w, dev, 
     return x.grad.cpu().numpy(), tup
 
 
-@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2", "loss_voc_dense_n2"])
 def test_loss_backward_vs_reference_autograd_golden(case, cuda_device):
     d = load_golden(case)
     targets = unpack_ragged(d, "targets")

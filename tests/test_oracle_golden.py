@@ -73,7 +73,7 @@ def test_pairwise_iou_and_ciou():
                                    equal_nan=True)
 
 
-@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2", "loss_voc_dense_n2"])
 def test_target_loss_matches_reference(case):
     d = load_golden(case)
     C = int(d["num_classes"])
@@ -102,7 +102,7 @@ def test_out_of_range_gt_raises():
 GRAD_TOL = 1e-5  # |d| <= GRAD_TOL * max|grad|: the reference's autograd runs in fp32
 
 
-@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2"])
+@pytest.mark.parametrize("case", ["loss_voc_n3", "loss_bdd_nonsquare_n2", "loss_voc_dense_n2"])
 def test_target_loss_backward_matches_reference_autograd(case):
     """oracle.target_loss_backward (analytic, float64) vs input.grad after the reference's own
     loss.backward() (tests/golden/make_golden.py)."""
