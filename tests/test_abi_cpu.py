@@ -88,3 +88,20 @@ def test_adjust_confidence_like_the_reference():
     assert m.adjust_confidence(10, 25, 0.3) == 0.3
     assert m.adjust_confidence(10, 0, 0.01) == 0.01          # never below 0.01
     assert m.adjust_confidence(10, torch.tensor([20, 15], dtype=torch.int32), 0.3) == pytest.approx(0.31)
+
+
+def test_bench_reference_arm_runs_without_gpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the CUDA arm) needs no CUDA device and prints
+    the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "decode+NMS images/sec" and line["value"] > 0
+    assert line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
