@@ -61,7 +61,8 @@ void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
 /* Experiment / test switches of the fused kernel (initialised from the B200YOLO_FLAGS
  * environment variable): 1 = no L2 prefetch of head 0, 2 = no programmatic dependent launch (consecutive
  * launches then run in plain stream order), 8 = prefetch both heads, 16 = never
- * use the compile-time head shapes (every shape then runs the runtime-stride decode). */
+ * use the compile-time head shapes (every shape then runs the runtime-stride decode), 32 = always wait for the
+ * previous kernel before the first global read. */
 void b200yolo_debug_set_flags(int flags);
 
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that
@@ -105,6 +106,33 @@ int b200yolo_nms(const float *cand0, const int *count0, int stride0, const float
 int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
                         int W1, const float *anchor_wh, float conf_thr, double iou_thr, float *out,
                         int *out_count, int *out_idx, void *stream);
+
+/*
+ * The same for a LIST of batches of one shape: what a loop over `yolo.forward` of models/mbv2_yolo.py:158-160 does
+ * batch after batch (the evaluation loop train.py:357-395, a serving queue), as one call.  Launch k runs the fused
+ * kernel on batches[k]; because launch k > 0 directly follows the library's own launch k - 1 in the stream -- which
+ * writes nothing that launch k reads -- it is allowed to start on the SM slots its predecessor leaves free and to
+ * stream its heads under the predecessor's NMS (programmatic dependent launch); every launch waits for its
+ * predecessor before it writes.  The first launch waits for whatever precedes the call in the stream before it
+ * reads.  No batch's `out` / `out_count` / `out_idx` may alias another batch's heads.
+ */
+typedef struct b200yolo_batch {
+    const float *head0, *head1; /* dev (N, A*(5+C), H0, W0), (N, A*(5+C), H1, W1) */
+    float *out;                 /* dev [N][K][7] */
+    int *out_count;             /* dev [N] */
+    int *out_idx;               /* dev [N][K] or NULL */
+} b200yolo_batch;
+int b200yolo_decode_nms_batches(const b200yolo_batch *batches, int n_batches, int N, int A, int C, int H0, int W0, int H1,
+                                int W1, const float *anchor_wh, float conf_thr, double iou_thr, void *stream);
+
+/*
+ * Single calls (b200yolo_decode_nms & co.) execute griddepcontrol.wait before their first global read, because the
+ * kernel that precedes them in the stream may be the producer of their inputs.  A caller that issues them back to
+ * back on buffers no kernel of this library writes (a benchmark loop over resident head tensors) may declare that
+ * with b200yolo_set_inputs_ready(1): consecutive single calls then overlap like the launches of
+ * b200yolo_decode_nms_batches.  Process-wide; default 0.
+ */
+void b200yolo_set_inputs_ready(int ready);
 
 /*
  * The same for channels-last heads: head tensors laid out (N, H, W, A*(5+C)) in memory -- what cuDNN prefers for the

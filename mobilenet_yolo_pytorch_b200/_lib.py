@@ -32,6 +32,9 @@ SIGNATURES = {
                                c_f32p, c_i32p, c_i32p, C.c_void_p]),
     "b200yolo_decode_nms": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, c_i32p, C.c_void_p]),
+    "b200yolo_decode_nms_batches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              c_f32p, C.c_float, C.c_double, C.c_void_p]),
+    "b200yolo_set_inputs_ready": (None, [C.c_int]),
     "b200yolo_decode_nms_nhwc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, c_i32p, C.c_void_p]),
     "b200yolo_decode_nms_large_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
@@ -73,6 +76,12 @@ SIGNATURES = {
 # partial-sum slots (enum in include/b200yolo.h)
 S_SQW, S_W, S_IOU_SQ, S_IOU_W, S_NASSIGN, S_OBJ, S_CONF_ALL, S_CLS, S_IOU, S_RECALL, S_NCELLS, S_NIMG = range(12)
 S_COUNT = 16
+
+
+class Batch(C.Structure):
+    """struct b200yolo_batch (include/b200yolo.h)."""
+    _fields_ = [("head0", C.c_void_p), ("head1", C.c_void_p), ("out", C.c_void_p), ("out_count", C.c_void_p),
+                ("out_idx", C.c_void_p)]
 
 
 class B200YoloError(RuntimeError):

@@ -26,6 +26,7 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long *> g_dbg{nullptr};  // profiling aid, see b200yolo_debug_phase_stamps
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_flags{[] { const char *e = getenv("B200YOLO_FLAGS"); return e ? atoi(e) : 0; }()};  // experiment switches
+std::atomic<int> g_inputs_ready{0};   // see b200yolo_set_inputs_ready
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -89,6 +90,8 @@ IouThr make_thr(double thr) {
     t.fast_ok = (thr >= 0.01 && thr <= 1.0) ? 1 : 0;
     const double tt = t.fast_ok ? thr / (1.0 + thr) : 0.0;  // iou > thr <=> inter > tt * (area_a + area_b)
     t.ts = (float)tt * 1.220703125e-4f;                     // * 2^-13, exact
+    t.tf = (float)tt;
+    t.th = (float)(tt * 16.0 * (1.0 - 0.00390625));         // fp16 prefilter: X = x/4, Y = 64*y, margin 2^-8
     return t;
 }
 
@@ -106,7 +109,7 @@ constexpr int kTier1x64 = 162 * 1024;
 template <int MODE, int THREADS, int SHAPE>
 int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     static std::mutex mu;
-    static int configured[2][64] = {{0}, {0}};  // smem size opted into, per kernel variant and device
+    static int configured[3][64] = {{0}, {0}, {0}};  // smem size opted into, per kernel variant and device
     using Kern = void (*)(const DNParams, const SmemLayout);
     Kern kern = decode_nms_kernel<MODE, THREADS, SHAPE, 0>;
     int variant = 0;
@@ -114,6 +117,11 @@ int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
         if (p.gR > 0) {  // fused all-gather: the output phase stores into every rank's buffer
             kern = decode_nms_kernel<MODE, THREADS, SHAPE, 1>;
             variant = 1;
+        } else if constexpr (THREADS == 512 && (SHAPE == 0 || SHAPE == 1)) {
+            if (p.dbg) {  // phase time stamps (profiles/phase_times.py): a separate instantiation
+                kern = decode_nms_kernel<MODE, THREADS, SHAPE, 0, true>;
+                variant = 2;
+            }
         }
     }
     {
@@ -160,7 +168,7 @@ int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) 
     if (MODE == MODE_FUSED && p.nhwc) {
         // the channels-last decode stages 32 cells per warp in the part of U behind clsidx: as many warps as fit
         const uint32_t Kp = align_up((uint32_t)(p.K > 0 ? p.K : 1), 32);
-        const uint32_t free_bytes = (L.u_bytes > 4 * Kp) ? L.u_bytes - 4 * Kp : 0;
+        const uint32_t free_bytes = 8 * Kp;   // the key region of U (decode_nms.cuh, make_layout)
         int nwarps = (int)(free_bytes / (32u * (uint32_t)p.attrs * sizeof(float)));
         if (nwarps > THREADS / 32) nwarps = THREADS / 32;
         if (nwarps < 2)
@@ -190,26 +198,46 @@ int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) 
     return launch_dn_t<MODE, THREADS, 0>(p, L, dev, st);
 }
 
+// limits of the one-CTA-per-image layout beyond shared memory (decode_nms.cuh): the sorting warps carry kRankItems
+// sorted positions per thread over a barrier, tile-padded positions are 16 bits, a class has at most 255 tiles
+bool dn_counts_ok(int K, int C, int mode, int threads) {
+    if (mode == MODE_DECODE) return true;
+    const long long Kp = ((long long)(K > 0 ? K : 1) + 31) / 32 * 32;
+    return K <= kRankItems * (threads - 32) && Kp + 32LL * C <= 65535 && K <= 255 * 32;
+}
+
 template <int MODE>
 int launch_dn(DNParams &p, cudaStream_t st) {
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;
     const int lim = smem_optin(dev);
     const SmemLayout base1k = make_layout(p.K, p.C, MODE, 1024, 0);
-    if ((int)base1k.total > lim)
+    if ((int)base1k.total > lim || !dn_counts_ok(p.K, p.C, MODE, 1024))
         return fail(B200YOLO_EUNSUPPORTED,
                     "%d candidate cells per image with %d classes need %u B of shared memory (limit %d B)", p.K, p.C,
                     base1k.total, lim);
     if (p.N == 0) return 0;
     p.B = pick_buckets(p.C);
+    p.Bshift = 0;
+    while ((1 << p.Bshift) < p.B) ++p.Bshift;
     p.dbg = g_dbg.load();
     p.flags = g_flags.load();
+    // Programmatic dependent launch lets this kernel start while its predecessor in the stream is still running.
+    // That is only harmless when the predecessor does not produce this kernel's inputs -- true for back-to-back
+    // launches of this library on different batches, NOT true in general (CUDA makes a predecessor's writes
+    // visible only after griddepcontrol.wait).  So the kernel waits before its first global read unless the
+    // previous kernel in the stream is known not to produce them: launches 2..n of b200yolo_decode_nms_batches
+    // (their predecessor is our own launch on another batch), or a caller that vouches for it with
+    // b200yolo_set_inputs_ready.  Flag 32 forces the wait.
+    if (g_inputs_ready.load()) p.wait_inputs = 0;
+    if (p.flags & 32) p.wait_inputs = 1;
     const int need512 = (int)make_layout(p.K, p.C, MODE, 512, 0).total;
     const int need = (int)base1k.total;
     // the pair masks get whatever the tier leaves (MODE_DECODE has none)
-    if (need512 <= kTier2x64 && kTier2x64 <= lim)
+    const bool ok512 = dn_counts_ok(p.K, p.C, MODE, 512);
+    if (ok512 && need512 <= kTier2x64 && kTier2x64 <= lim)
         return launch_dn_shape<MODE, 512>(p, make_layout(p.K, p.C, MODE, 512, (MODE == MODE_DECODE) ? 0u : (uint32_t)(kTier2x64 - need512)), dev, st);
-    if (need512 <= kTier2x0 && kTier2x0 <= lim)
+    if (ok512 && need512 <= kTier2x0 && kTier2x0 <= lim)
         return launch_dn_shape<MODE, 512>(p, make_layout(p.K, p.C, MODE, 512, (MODE == MODE_DECODE) ? 0u : (uint32_t)(kTier2x0 - need512)), dev, st);
     const int budget = (need <= kTier1x64 && kTier1x64 <= lim) ? kTier1x64 : lim;
     return launch_dn_shape<MODE, 1024>(p, make_layout(p.K, p.C, MODE, 1024, (MODE == MODE_DECODE) ? 0u : (uint32_t)(budget - need)), dev, st);
@@ -277,7 +305,7 @@ int launch_large(LargeParams &p, cudaStream_t st, const char *who) {
 bool fits_one_cta(int K, int C, int mode) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return true;  // (the regular path reports the error)
-    return (int)make_layout(K, C, mode, 1024, 0).total <= smem_optin(dev);
+    return (int)make_layout(K, C, mode, 1024, 0).total <= smem_optin(dev) && dn_counts_ok(K, C, mode, 1024);
 }
 
 }  // namespace
@@ -290,13 +318,14 @@ unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
 
 void b200yolo_debug_phase_stamps(unsigned long long *dev_buf) { g_dbg.store(dev_buf); }
 void b200yolo_debug_set_flags(int flags) { g_flags.store(flags); }
+void b200yolo_set_inputs_ready(int ready) { g_inputs_ready.store(ready ? 1 : 0); }
 
 int b200yolo_max_cells(int device) {
     const int lim = smem_optin(device);
     int lo = 0, hi = 1 << 16;
     while (lo < hi) {  // largest K whose fused layout fits (C = 80 as a conservative class count)
         int mid = (lo + hi + 1) / 2;
-        if ((int)make_layout(mid, 80, MODE_FUSED, 1024, 0).total <= lim) lo = mid; else hi = mid - 1;
+        if ((int)make_layout(mid, 80, MODE_FUSED, 1024, 0).total <= lim && dn_counts_ok(mid, 80, MODE_FUSED, 1024)) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -329,6 +358,7 @@ int b200yolo_decode_head(const float *head, int N, int A, int C, int H, int W, c
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    p.wait_inputs = 1;
     return launch_dn<MODE_DECODE>(p, (cudaStream_t)stream);
 }
 
@@ -362,6 +392,7 @@ int b200yolo_nms(const float *cand0, const int *count0, int stride0, const float
         q.cand[1] = cand1; q.cand_count[1] = count1; q.cand_stride[1] = stride1;
         return launch_large<1>(q, (cudaStream_t)stream, "nms");
     }
+    p.wait_inputs = 1;
     return launch_dn<MODE_NMS>(p, (cudaStream_t)stream);
 }
 
@@ -384,7 +415,39 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
     p.conf_thr = conf_thr;
     p.iou = make_thr(iou_thr);
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    p.wait_inputs = 1;
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
+}
+
+int b200yolo_decode_nms_batches(const b200yolo_batch *batches, int n_batches, int N, int A, int C, int H0, int W0, int H1,
+                                int W1, const float *anchor_wh, float conf_thr, double iou_thr, void *stream) {
+    if (n_batches < 0 || (n_batches > 0 && !batches)) return fail(B200YOLO_EINVAL, "decode_nms_batches: bad batch list");
+    if (!anchor_wh) return fail(B200YOLO_EINVAL, "decode_nms_batches: null pointer");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
+        return fail(B200YOLO_EINVAL, "decode_nms_batches: bad shape");
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_batches: NaN threshold");
+    const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
+    if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms_batches: more than 65535 cells per image");
+    for (int k = 0; k < n_batches; ++k)
+        if (!batches[k].head0 || !batches[k].head1 || !batches[k].out || !batches[k].out_count)
+            return fail(B200YOLO_EINVAL, "decode_nms_batches: null pointer in batch %d", k);
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    p.nheads = 2;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.K = (int)cells;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(iou_thr);
+    for (int k = 0; k < n_batches; ++k) {
+        fill_head(p.head[0], batches[k].head0, A, H0, W0, anchor_wh);
+        fill_head(p.head[1], batches[k].head1, A, H1, W1, anchor_wh + 2 * A);
+        p.out = batches[k].out; p.out_count = batches[k].out_count; p.out_idx = batches[k].out_idx;
+        // launch k > 0 follows our own launch k - 1 in the stream, which writes nothing this one reads: it may start
+        // on the SM slots its predecessor leaves free and stream its heads under the predecessor's NMS
+        p.wait_inputs = (k == 0) ? 1 : 0;
+        if (int rc = launch_dn<MODE_FUSED>(p, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
 }
 
 int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, int A, int C, int H0, int W0, int H1,
@@ -414,6 +477,7 @@ int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, in
     // every rank starts with its own buffer and walks the ring from there, so at any moment the ranks store into
     // different peers instead of all hitting rank 0 first
     for (int i = 0; i < R; ++i) { p.gout[i] = peer_out[(rank + i) % R]; p.gcount[i] = peer_count[(rank + i) % R]; }
+    p.wait_inputs = 1;
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
 }
 
@@ -499,6 +563,7 @@ int b200yolo_decode_nms_nhwc(const float *head0, const float *head1, int N, int 
     p.iou = make_thr(iou_thr);
     p.out = out; p.out_count = out_count; p.out_idx = out_idx;
     p.nhwc = 1;
+    p.wait_inputs = 1;
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
 }
 

@@ -7,11 +7,12 @@
 // the decode phase streams the heads with ordinary coalesced loads whose in-flight
 // lines live in L1, and L1 is what the CTAs' shared memory leaves of the SM's 228 KB
 // (profiles/micro/load_pattern.cu: the same load pattern runs at 4.3 TB/s with 64 KB of
-// L1 and at 2.9 TB/s with none).  So: structure-of-arrays records by cell id (box 16 B,
-// conf/score 8 B) and one region `U` that is reused by phase.
+// L1 and at 2.9 TB/s with none).  So: records by cell id (box 16 B, conf/score 8 B) and
+// one region `U` that is reused by phase.
 //
-// The kernel is issue-bound once the heads are in (profiles/r01: 0.67 of the issue
-// slots used while an SM is active), so every phase is written for instruction count:
+// The kernel is issue-bound once the heads are in (profiles/r02/NOTES.md: round 1 executed 86.7 k
+// warp instructions per image, 44 % of them the fp32 box-pair loop), so every phase is
+// written for instruction count:
 //
 //   P1 decode     thread per cell, ALL 5+C attribute planes of the cell loaded at
 //                 once (coalesced: consecutive lanes = consecutive cells of a plane).
@@ -22,32 +23,32 @@
 //                 class max / argmax (:198), box (:186-196,243-247) -> box[], cs[],
 //                 and the per-(class, score bucket) arrival index (one shared atomic).
 //   P2 scans      warp per class: exclusive scan of the class's score-bucket histogram; warp 0:
-//                 class segment starts (box.py:20-22).  Then warp 0 builds the kept-bitmap
-//                 tiles, the round table and the strip tasks WHILE the other warps sort (named
-//                 barrier between P3 and P4): the tables are off the critical path.
+//                 class segment starts (box.py:20-22) and the tile tables -- a class owns
+//                 ceil(n/32) TILES of 32 sorted positions.
 //   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort of
-//                 torchvision.ops.nms) into their (class, bucket) segment.
-//   P4 rank       rank inside the bucket -> `sord`: sorted position -> {shared-memory
-//                 address of the box, t * area}.  The pair loop then needs two loads and no
-//                 address arithmetic per column.
-//   P5 pairs+sweep  dynamic warp tasks.  A task is one 32-row strip of one class: the
-//                 lane keeps its row's box in registers and walks the later columns
-//                 (broadcast from shared memory), 32 columns per mask word.  The test is
-//                 divide-free: iou > thr  <=>  inter > t*(area_r+area_c), t = thr/(1+thr);
-//                 d = t*(area_r+area_c) - w*h is one FFMA and its SIGN BIT is the mask
-//                 bit (one funnel shift).  |d| <= 1e-5*t*(area sum) (or any degenerate
-//                 box in the class) sends the lane to the exact torchvision arithmetic
-//                 (inter/(Sa+Sb-inter) > thr in double).  The warp that finishes the last
-//                 strip of a class sweeps it at once (no block barrier): per 32-column
-//                 tile, OR the mask words of the kept earlier rows, then resolve the
-//                 diagonal block by walking only the rows that suppress something.
+//                 torchvision.ops.nms) into their (class, bucket) segment; warp 0 builds the
+//                 pair-task list meanwhile.
+//   P4 rank       rank inside the bucket = sorted position.  Every candidate is then written to the
+//                 tile-padded sorted tables: its cell id (scid) and a CONSERVATIVE fp16 image of
+//                 its box (H16Tile: x1/y1 rounded down, x2/y2 rounded up, a lower bound of
+//                 t*area; two columns per 32-bit word).
+//   P5 pairs + sweep as you go.  Warp tasks claimed from a queue in dependency order; a task is
+//                 one 32x32 block (rows of tile rt, columns of tile ct) of one class.  The block
+//                 is first PREFILTERED in packed fp16 (HMNMX2 / HADD2 / HFMA2, two columns per
+//                 instruction: 8.4 issue cycles per row x column slot against 17.0 for the fp32
+//                 loop, profiles/micro/pair_loop.cu).  The rounding directions and the area
+//                 margin make "inter < t*(Sa+Sb)" in fp16 a PROOF that torchvision does not
+//                 suppress the pair (h16_prefilter below); the few pairs it cannot rule out
+//                 ("maybe") are decided in fp32 with torchvision's exact arithmetic behind a
+//                 guard band (pair_decide).  An off-diagonal block reduces at once to ONE word
+//                 -- the columns suppressed by the KEPT rows of tile rt -- that is OR-ed into the
+//                 column tile's word; the diagonal task of a tile runs when all earlier row
+//                 tiles have contributed and resolves the tile in score order.  No n^2 mask in
+//                 memory, no separate sweep, rows that are already suppressed cost nothing.
 //   P6 output     class-ascending / score-descending rows (box.py:29-30).  A warp owns
-//                 32-column tiles of the kept bitmap: the rows of a tile are consecutive
+//                 tiles of the kept bitmap: the rows of a tile are consecutive
 //                 in the output, so the warp assembles them in a 896-byte scratch and
 //                 stores them with coalesced 4-byte stores.
-//
-// If the masks of all classes do not fit `U`, P5 runs in rounds (groups of whole
-// classes, or column-tile chunks of one huge class) with a block barrier in between.
 //
 // The stand-alone decode (P1 + ordered compaction + store) and NMS (load rows,
 // P2..P6) kernels back YOLOLoss.forward(input) and utils.box.nms separately.
@@ -60,6 +61,8 @@
 // Consecutive launches overlap (programmatic dependent launch, see pdl_trigger / pdl_wait below): a launch
 // starts on the SM slots its predecessor leaves free and streams its heads under the predecessor's NMS.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace b200yolo {
@@ -100,6 +103,8 @@ struct DNParams {
     int N, A, C, attrs;
     int K;               // candidate slots per image = row stride of out / out_idx
     int B;               // score buckets per class of the counting sort (power of two)
+    int Bshift;          // log2(B)
+    int wait_inputs;     // 1: griddepcontrol.wait before the first global read (see launch_dn_t)
     int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads
     int nhwc;            // > 0: heads are channels-last, (N, H, W, A*(5+C)) in memory (fused mode only); the value is the
                          // number of warps that stage + decode (32 cells each per step; what the free shared memory allows)
@@ -121,19 +126,33 @@ struct DNParams {
     int cand_stride[2];
 };
 
+
+// fp16 column table of one tile (32 sorted positions of one class): entry k packs columns k (low half) and k + 16
+// (high half), so one HMNMX2 / HADD2 / HFMA2 works on two columns.  Written in P4, read in P5.
+struct H16Tile {
+    uint4 xy[16];      // .x = X1 pair, .y = Y1 pair, .z = X2 pair, .w = Y2 pair (half2 each); X = x/4, Y = 64*y
+    uint32_t ta[16];   // TA pair: a lower bound of 16 * t * area, or -inf ("always maybe": degenerate box)
+};
+static_assert(sizeof(H16Tile) == 320, "H16Tile layout");
+constexpr uint32_t kTileBytes = sizeof(H16Tile) + 64;   // + scid u16[32]
+
 struct SmemLayout {
-    uint32_t box, cs, cntb, cls, tasks, tilecls, keptbits, tilepref, passbits, rounds, misc, U, total;
+    uint32_t box, cs, cls, tiles, tasks, misc, U, total;
+    uint32_t passbits, tilepref;   // MODE_DECODE
     uint32_t u_bytes;     // bytes in U
-    uint32_t mask_off;    // keys, then pair masks, then the output scratch start here (after sord)
-    uint32_t mask_words;  // 32-bit words available for pair masks
+    uint32_t key_off;     // keys (8 B per cell), also the channels-last staging scratch during the decode
+    uint32_t cntb_off;    // score-bucket counters (live from the decode to the ranking)
+    uint32_t h16_off;     // fp16 tile table (after the ranking); the P6 row scratch aliases it
+    uint32_t nt_max;      // tiles an image can need: Kp/32 + C
+    uint32_t task_cap;    // entries of the pair-task table
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // per-class int arrays, each (C+1) long
-enum { CA_CNT = 0, CA_START, CA_KTILE, CA_MASK, CA_TBASE, CA_DONE, CA_FLAG, CA_NUM };
+enum { CA_CNT = 0, CA_START, CA_KTILE, CA_NUM };
 // misc ints
-enum { M_NROUNDS = 0, M_CLO, M_CHI, M_T0, M_T1, M_NTASK, M_CTR, M_TOTAL, M_KV, M_WSUM = 16, M_NUM = 16 + 32 };
+enum { M_NTASK = 0, M_CTR, M_LEVEL, M_NLEVELS, M_TOTAL, M_KV, M_NUM = 16 };
 
 // score buckets per class: C*B counters, at most 1536 (6 KB)
 __host__ __device__ inline int pick_buckets(int C) {
@@ -143,40 +162,45 @@ __host__ __device__ inline int pick_buckets(int C) {
 }
 
 constexpr uint32_t kScratchPerWarp = 32 * 7 * 4;  // P6: 32 output rows of 7 floats
+constexpr int kRankItems = 8;                     // P4: sorted positions a thread carries over the barrier
 
-// U region by phase (Kp = K rounded up to 32):
-//   decode .. key scatter   clsidx u32[Kp] ........ | key u64[Kp]
-//   rank .. sweep           sord uint2[Kp + 8] .... | (key, dead after rank) pair masks u32[mask_words]
-//   output                  sord .................. | per-warp row scratch
-//   (MODE_DECODE)           clsidx u32[Kp] | outsrc u16[Kp]
-__host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int threads, uint32_t extra_mask_bytes) {
+// U region by phase (Kp = K rounded up to 32, NT = Kp/32 + C tiles):
+//   decode .. rank   clsidx u32[Kp] | key u64[Kp] | cntb int[C*B+1]
+//   pairs            scid u16[32*NT] | H16Tile[NT]
+//   output           scid ........... | per-warp row scratch
+//   (MODE_DECODE)    clsidx u32[Kp] | outsrc u16[Kp]
+// `extra` bytes (what the shared-memory tier leaves) go to the pair-task table.
+__host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int threads, uint32_t extra) {
     SmemLayout L;
     const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
     const uint32_t Cp = align_up((uint32_t)C + 1, 4);
-    const uint32_t tiles = Kp / 32 + (uint32_t)C + 1;
+    const uint32_t NT = Kp / 32 + (uint32_t)C;
     const bool nms = (mode != MODE_DECODE);
     uint32_t o = 0;
     L.box = o; o += 16 * Kp;
     L.cs = o; o += 8 * Kp;
-    L.cntb = o; o += nms ? 4 * align_up((uint32_t)(C * pick_buckets(C)) + 1, 4) : 0;
     L.cls = o; o += nms ? 4 * Cp * CA_NUM : 0;
-    L.tasks = o; o += nms ? 4 * tiles : 0;
-    L.keptbits = o; o += nms ? 4 * tiles : 0;
-    L.tilepref = o; o += nms ? 0 : 4 * (tiles + 1);
+    L.tiles = o; o += nms ? 16 * align_up(NT + 1, 4) : 0;   // keptw, supw, arrived, (ready | class) per tile
+    L.tilepref = o; o += nms ? 0 : 4 * (NT + 2);
     L.passbits = o; o += nms ? 0 : 4 * (Kp / 32);
-    L.tilecls = o; o += nms ? align_up(2 * tiles, 4) : 0;
-    o = align_up(o, 8);
-    L.rounds = o; o += nms ? 8 * (tiles + (uint32_t)C + 2) : 0;
     L.misc = o; o += 4 * M_NUM;
+    // at least one whole level of tasks must fit (a level has at most NT tasks)
+    uint32_t cap = NT + 32 + (extra & ~15u) / 4;
+    if (cap > 16384) cap = 16384;
+    L.task_cap = nms ? cap : 0;
+    L.tasks = o; o += 4 * L.task_cap;
     o = align_up(o, 16);
     L.U = o;
-    const uint32_t scratch = (uint32_t)(threads / 32) * kScratchPerWarp;
-    uint32_t tail = 8 * Kp + (extra_mask_bytes & ~15u);  // keys; pair masks; output scratch
-    if (tail < scratch) tail = scratch;
-    const uint32_t sord_bytes = nms ? 8 * Kp + 64 : 4 * Kp;  // + 8 padding entries (the pair loop reads whole chunks of 8)
-    L.u_bytes = nms ? sord_bytes + tail : 6 * Kp;
-    L.mask_off = L.U + sord_bytes;
-    L.mask_words = (L.u_bytes - sord_bytes) / 4;
+    const uint32_t sort_bytes = 4 * Kp + 8 * Kp + 4 * align_up((uint32_t)(C * pick_buckets(C)) + 1, 4);
+    const uint32_t pair_bytes = 64 * NT + (uint32_t)sizeof(H16Tile) * NT;
+    const uint32_t out_bytes = 64 * NT + (uint32_t)(threads / 32) * kScratchPerWarp;
+    uint32_t u = sort_bytes > pair_bytes ? sort_bytes : pair_bytes;
+    if (out_bytes > u) u = out_bytes;
+    L.u_bytes = nms ? align_up(u, 16) : 6 * Kp;
+    L.key_off = L.U + 4 * Kp;
+    L.cntb_off = L.U + 12 * Kp;
+    L.h16_off = L.U + 64 * NT;
+    L.nt_max = NT;
     L.total = align_up(L.U + L.u_bytes, 16);
     return L;
 }
@@ -184,51 +208,49 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int th
 struct Smem {
     float4 *box;        // [Kp] x1 y1 x2 y2 by cell id            (output columns 0-3)
     float2 *cs;         // [Kp] conf, class score                 (columns 4, 5)
-    uint32_t *clsidx;   // [Kp] (class << 16) | arrival index inside the (class, bucket); ~0u: not a candidate
+    uint32_t *clsidx;   // [Kp] (global bucket c*B+bk << 16) | arrival index inside the bucket; ~0u: not a candidate
     unsigned long long *key;
-    uint2 *sord;        // sorted position -> {shared address of box[cell], t * area * 2^-13 (NaN: degenerate)}
-    uint32_t *mask;     // pair-mask words
+    int *cntb;          // [C*B+1] per (class, score bucket): arrival counter, then exclusive prefix inside the class
+    uint16_t *scid;     // [32*NT] tile-padded sorted position -> cell id
+    H16Tile *h16;       // [NT]
     float *scratch;     // P6: per-warp 32 x 7 floats
     uint16_t *outsrc;   // MODE_DECODE: output row -> cell id
-    uint16_t *tilecls;  // kept-bitmap tile -> class
-    uint32_t *passbits, *keptbits, *tilepref, *tasks;
-    int *cnt, *start, *ktile, *maskbase, *tbase, *done, *flag;
-    int *cntb;          // [C*B+1] per (class, score bucket): arrival counter, then exclusive prefix
-    uint2 *rounds;      // x = c_lo | c_hi << 16, y = t0 | t1 << 16
+    uint32_t *passbits, *tilepref;
+    uint32_t *keptw;    // [NT] kept bitmap of the tile (final once `ready`)
+    uint32_t *supw;     // [NT] columns of the tile suppressed by kept rows of EARLIER tiles (OR-accumulated)
+    int *arrived;       // [NT] earlier row tiles that have contributed to supw
+    int *ready;         // [NT] low 16 bits: 1 once keptw is final; high 16 bits: class of the tile
+    uint32_t *tasks;    // [task_cap] class << 16 | rt << 8 | ct   (rt == ct: the tile's diagonal task)
+    int *cnt, *start, *ktile;
     int *misc;
-    uint32_t box_saddr; // shared-window address of box[0]
 };
 
-__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, int K, int C, int mode) {
+__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L, int K, int C) {
     Smem s;
     const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
     const uint32_t Cp = align_up((uint32_t)C + 1, 4);
+    const uint32_t NTp = align_up(L.nt_max + 1, 4);
     s.box = reinterpret_cast<float4 *>(base + L.box);
     s.cs = reinterpret_cast<float2 *>(base + L.cs);
     s.clsidx = reinterpret_cast<uint32_t *>(base + L.U);
-    s.key = reinterpret_cast<unsigned long long *>(base + L.mask_off);
-    s.sord = reinterpret_cast<uint2 *>(base + L.U);
-    s.mask = reinterpret_cast<uint32_t *>(base + L.mask_off);
-    s.scratch = reinterpret_cast<float *>(base + L.mask_off);
+    s.key = reinterpret_cast<unsigned long long *>(base + L.key_off);
+    s.cntb = reinterpret_cast<int *>(base + L.cntb_off);
+    s.scid = reinterpret_cast<uint16_t *>(base + L.U);
+    s.h16 = reinterpret_cast<H16Tile *>(base + L.h16_off);
+    s.scratch = reinterpret_cast<float *>(base + L.h16_off);
     s.outsrc = reinterpret_cast<uint16_t *>(base + L.U + 4 * Kp);
-    s.tilecls = reinterpret_cast<uint16_t *>(base + L.tilecls);
     s.passbits = reinterpret_cast<uint32_t *>(base + L.passbits);
-    s.keptbits = reinterpret_cast<uint32_t *>(base + L.keptbits);
     s.tilepref = reinterpret_cast<uint32_t *>(base + L.tilepref);
+    s.keptw = reinterpret_cast<uint32_t *>(base + L.tiles);
+    s.supw = s.keptw + NTp;
+    s.arrived = reinterpret_cast<int *>(s.supw + NTp);
+    s.ready = s.arrived + NTp;
     s.tasks = reinterpret_cast<uint32_t *>(base + L.tasks);
     int *ca = reinterpret_cast<int *>(base + L.cls);
     s.cnt = ca + CA_CNT * Cp;
     s.start = ca + CA_START * Cp;
     s.ktile = ca + CA_KTILE * Cp;
-    s.maskbase = ca + CA_MASK * Cp;
-    s.tbase = ca + CA_TBASE * Cp;
-    s.done = ca + CA_DONE * Cp;
-    s.flag = ca + CA_FLAG * Cp;
-    s.cntb = reinterpret_cast<int *>(base + L.cntb);
-    s.rounds = reinterpret_cast<uint2 *>(base + L.rounds);
     s.misc = reinterpret_cast<int *>(base + L.misc);
-    s.box_saddr = (uint32_t)__cvta_generic_to_shared(base + L.box);
-    (void)mode;
     return s;
 }
 
@@ -238,21 +260,20 @@ __device__ __forceinline__ int fastdiv(int n, uint32_t magic) {
 
 __device__ __forceinline__ int tri(int x) { return (x * (x + 1)) >> 1; }
 
-// profiling aid: slot k of image b gets %globaltimer (ns, 256 ns resolution, comparable across SMs) and,
-// 16 slots further, the SM's cycle counter (comparable inside the CTA only)
+// profiling aid (DBG instantiations only; the production kernels carry no trace of it): slot k of image b gets
+// %globaltimer (ns, comparable across SMs) at the CTA's two ends and, 16 slots further, the SM's cycle counter
+template <bool DBG>
 __device__ __forceinline__ void stamp(const DNParams &p, int b, int k) {
-    if (p.dbg && threadIdx.x == 0) {
-        if (k == 0 || k == 7) {  // (reading %globaltimer costs several hundred ns: only at the CTA's two ends)
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            p.dbg[(size_t)b * 32 + k] = t;
+    if constexpr (DBG) {
+        if (p.dbg && threadIdx.x == 0) {
+            if (k == 0 || k == 7) {  // (reading %globaltimer costs several hundred ns: only at the CTA's two ends)
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                p.dbg[(size_t)b * 32 + k] = t;
+            }
+            p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
         }
-        p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
     }
-}
-// inside the decode loop the check is hoisted: `on` = p.dbg != nullptr && threadIdx.x == 0
-__device__ __forceinline__ void stamp_if(bool on, const DNParams &p, int b, int k) {
-    if (on) p.dbg[(size_t)b * 32 + 16 + k] = (unsigned long long)clock64();
 }
 
 // Programmatic dependent launch (the host sets cudaLaunchAttributeProgrammaticStreamSerialization): the NEXT
@@ -354,20 +375,22 @@ __device__ __forceinline__ void emit_candidate(const DNParams &p, const Smem &s,
     bx.w = __fadd_rn(bh, bx.y);                                  // :247
     s.box[cid] = bx;
     s.cs[cid] = make_float2(conf, best);
-    uint32_t idx = 0;
-    if (MODE == MODE_FUSED) idx = (uint32_t)atomicAdd(&s.cntb[bi * p.B + score_bucket(__fmul_rn(best, conf), p.B)], 1);
-    s.clsidx[cid] = ((uint32_t)bi << 16) | idx;
+    if (MODE == MODE_FUSED) {
+        const uint32_t gb = (uint32_t)(bi * p.B + score_bucket(__fmul_rn(best, conf), p.B));  // global score bucket
+        s.clsidx[cid] = (gb << 16) | (uint32_t)atomicAdd(&s.cntb[gb], 1);
+    } else {
+        s.clsidx[cid] = (uint32_t)bi << 16;
+    }
 }
 
 // Compile-time class count and grid: the 5+C loads are one base register plus immediates.  FIRST: this
 // is the first decode of the kernel -- the block barrier that orders the zeroing of the histogram before
 // the first shared atomic is taken AFTER the first round's loads are in flight (hides ~0.5 us of start-up
 // behind the first HBM round trip).
-template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST>
+template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST, bool DBG>
 __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     static_assert(CT >= 1 && CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
     const int tid = threadIdx.x, lane = tid & 31;
-    const bool dbg_on = p.dbg != nullptr && tid == 0;
     constexpr int attrs = CT + 5;
     const int cells = p.A * HWT;
     const float *hb = hd.ptr + (size_t)b * p.A * attrs * HWT;  // uniform
@@ -419,15 +442,14 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
             const unsigned bal = __ballot_sync(kFullMask, pass);
             if (lane == 0 && active) s.passbits[local >> 5] = bal;
         }
-        if (MODE == MODE_FUSED) stamp_if(dbg_on, p, b, 8 + min(3, hh + base / THREADS));
+        if (MODE == MODE_FUSED) stamp<DBG>(p, b, 8 + min(3, hh + base / THREADS));
     }
 }
 
 // Runtime class count and grid (any shape): plane stride in a register, classes in chunks of 24.
-template <int THREADS, int MODE>
+template <int THREADS, int MODE, bool DBG>
 __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const bool dbg_on = p.dbg != nullptr && tid == 0;
     const int C = p.C;
     const int attrs = C + 5;
     const int HW = hd.HW;
@@ -518,7 +540,7 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
             const unsigned bal = __ballot_sync(kFullMask, pass);
             if (lane == 0 && local < cells) s.passbits[local >> 5] = bal;
         }
-        if (MODE == MODE_FUSED) stamp_if(dbg_on, p, b, 8 + min(3, hh + base / THREADS));
+        if (MODE == MODE_FUSED) stamp<DBG>(p, b, 8 + min(3, hh + base / THREADS));
     }
 }
 
@@ -641,8 +663,8 @@ __device__ __forceinline__ void phase_load_rows(const DNParams &p, const Smem &s
             if (ok) {
                 s.box[row] = bx;
                 s.cs[row] = make_float2(conf, score);
-                const uint32_t idx = (uint32_t)atomicAdd(&s.cntb[c * p.B + score_bucket(__fmul_rn(score, conf), p.B)], 1);
-                s.clsidx[row] = ((uint32_t)c << 16) | idx;
+                const uint32_t gb = (uint32_t)(c * p.B + score_bucket(__fmul_rn(score, conf), p.B));
+                s.clsidx[row] = (gb << 16) | (uint32_t)atomicAdd(&s.cntb[gb], 1);
             }
         }
         if (row < p.K && !ok) s.clsidx[row] = 0xffffffffu;
@@ -672,102 +694,6 @@ __device__ __forceinline__ void warp_class_starts(const DNParams &p, const Smem 
     __syncwarp();
 }
 
-__device__ __forceinline__ void warp_class_scan(const DNParams &p, const Smem &s, int mask_cap_words) {
-    const int lane = threadIdx.x & 31;
-    const int C = p.C;
-    int carryT = 0, words = 0;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        const int c = c0 + lane;
-        const int n = (c < C) ? s.cnt[c] : 0;
-        const int T = (n + 31) >> 5;
-        const int incT = warp_inclusive_scan(T, lane);
-        if (c < C) {
-            const int kt = carryT + incT - T;
-            s.ktile[c] = kt;
-            for (int t = 0; t < T; ++t) s.tilecls[kt + t] = (uint16_t)c;
-        }
-        carryT += __shfl_sync(kFullMask, incT, 31);
-        words += 32 * tri(T);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) words += __shfl_xor_sync(kFullMask, words, o);
-    __syncwarp();  // lane 0 reads the other lanes' cnt[] below
-    if (lane == 0) {
-        s.ktile[C] = carryT;
-        const int cap = mask_cap_words;
-        if (words <= cap) {
-            s.rounds[0] = make_uint2((uint32_t)C << 16, 0xffffu << 16);
-            s.misc[M_NROUNDS] = 1;
-        } else {
-            // rare: groups of whole classes, or column-tile chunks of one huge class
-            int r = 0, c = 0;
-            while (c < C) {
-                const int T = (s.cnt[c] + 31) >> 5;
-                if (32 * tri(T) > cap) {
-                    int t0 = 0;
-                    while (t0 < T) {
-                        int t1 = t0, acc = 0;
-                        while (t1 < T && acc + 32 * (t1 + 1) <= cap) { acc += 32 * (t1 + 1); ++t1; }
-                        if (t1 == t0) ++t1;  // cannot happen: cap >= Kp >= 32*T
-                        s.rounds[r++] = make_uint2((uint32_t)c | ((uint32_t)(c + 1) << 16), (uint32_t)t0 | ((uint32_t)t1 << 16));
-                        t0 = t1;
-                    }
-                    ++c;
-                } else {
-                    const int c_lo = c;
-                    int acc = 0;
-                    while (c < C) {
-                        const int w = 32 * tri((s.cnt[c] + 31) >> 5);
-                        if (acc + w > cap) break;
-                        acc += w;
-                        ++c;
-                    }
-                    s.rounds[r++] = make_uint2((uint32_t)c_lo | ((uint32_t)c << 16), 0xffffu << 16);
-                }
-            }
-            s.misc[M_NROUNDS] = r;
-        }
-    }
-    __syncwarp();
-}
-
-// per round (warp 0): mask offsets, strip-task table and completion counters of the round's classes
-__device__ __forceinline__ void warp_round_prefix(const Smem &s, int r) {
-    const int lane = threadIdx.x & 31;
-    const uint2 rd = s.rounds[r];
-    const int c_lo = rd.x & 0xffff, c_hi = rd.x >> 16, t0 = rd.y & 0xffff, t1 = rd.y >> 16;
-    int carryS = 0, carryM = 0;
-    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-        const int c = c0 + lane;
-        int strips = 0, words = 0;
-        if (c < c_hi) {
-            const int T = (s.cnt[c] + 31) >> 5;
-            const int te = min(T, t1);
-            if (te > t0) {
-                strips = te;  // every row tile below te has blocks in column tiles [max(rt,t0), te)
-                words = 32 * (tri(te) - tri(t0));
-            }
-        }
-        const int incS = warp_inclusive_scan(strips, lane);
-        const int incM = warp_inclusive_scan(words, lane);
-        if (c < c_hi) {
-            const int tb = carryS + incS - strips;
-            s.tbase[c] = tb;
-            s.maskbase[c] = carryM + incM - words;
-            s.done[c] = 0;
-            for (int rt = 0; rt < strips; ++rt) s.tasks[tb + rt] = ((uint32_t)c << 16) | (uint32_t)rt;
-        }
-        carryS += __shfl_sync(kFullMask, incS, 31);
-        carryM += __shfl_sync(kFullMask, incM, 31);
-    }
-    if (lane == 0) {
-        s.misc[M_CLO] = c_lo; s.misc[M_CHI] = c_hi; s.misc[M_T0] = t0; s.misc[M_T1] = t1;
-        s.misc[M_NTASK] = carryS;
-        s.misc[M_CTR] = 0;
-    }
-    __syncwarp();
-}
-
 // ---------------------------------------------------------------------------
 // P2a (warp per class): exclusive scan of the class's score-bucket counters in place (position of the
 // bucket INSIDE the class segment); cnt[c] = candidates of the class
@@ -791,51 +717,355 @@ __device__ __forceinline__ void scan_buckets_per_class(const DNParams &p, const 
 }
 
 // ---------------------------------------------------------------------------
+// P2 (warp 0): tile tables.  A class owns ceil(n/32) tiles of 32 sorted positions; tile g of the image is
+// tile g - ktile[c] of class c = ready[g] >> 16.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_tile_tables(const DNParams &p, const Smem &s) {
+    const int lane = threadIdx.x & 31;
+    const int C = p.C;
+    int carryT = 0, tmax = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const int n = (c < C) ? s.cnt[c] : 0;
+        const int T = (n + 31) >> 5;
+        const int incT = warp_inclusive_scan(T, lane);
+        if (c < C) {
+            const int kt = carryT + incT - T;
+            s.ktile[c] = kt;
+            for (int t = 0; t < T; ++t) {
+                s.keptw[kt + t] = 0u;
+                s.supw[kt + t] = 0u;
+                s.arrived[kt + t] = 0;
+                s.ready[kt + t] = c << 16;
+            }
+        }
+        carryT += __shfl_sync(kFullMask, incT, 31);
+        tmax = max(tmax, T);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(kFullMask, tmax, o));
+    if (lane == 0) {
+        s.ktile[C] = carryT;
+        s.misc[M_LEVEL] = 0;
+        s.misc[M_NLEVELS] = tmax > 0 ? 2 * tmax - 1 : 0;
+    }
+    __syncwarp();
+}
+
+// (warp 0) the next window of pair tasks, whole levels at a time.  Level 2r holds the diagonal task of tile r of
+// every class that has one; level 2r+1 the blocks (rows of tile r) x (columns of tile ct), ct > r.  A task only
+// depends on tasks of LOWER levels: the diagonal task of tile ct needs every block (rt < ct, ct), a block
+// (rt, ct) needs the diagonal task of rt.  Tasks are claimed in table order, so a warp that waits for a
+// dependency waits for a task some warp has already claimed: no deadlock.
+__device__ __forceinline__ void warp_build_tasks(const DNParams &p, const Smem &s, int cap) {
+    const int lane = threadIdx.x & 31;
+    const int C = p.C;
+    int level = s.misc[M_LEVEL];
+    const int nlevels = s.misc[M_NLEVELS];
+    int ntask = 0;
+    while (level < nlevels) {
+        const int r = level >> 1;
+        const bool diag = !(level & 1);
+        // tasks of this level
+        int total = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + lane;
+            const int T = (c < C) ? (s.cnt[c] + 31) >> 5 : 0;
+            int m = diag ? (T > r ? 1 : 0) : max(T - r - 1, 0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(kFullMask, m, o);
+            total += m;
+        }
+        if (ntask + total > cap) break;   // (a level has at most NT <= cap tasks, so the first one always fits)
+        int carry = ntask;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + lane;
+            const int T = (c < C) ? (s.cnt[c] + 31) >> 5 : 0;
+            const int m = diag ? (T > r ? 1 : 0) : max(T - r - 1, 0);
+            const int inc = warp_inclusive_scan(m, lane);
+            int o = carry + inc - m;
+            if (diag) {
+                if (m) s.tasks[o] = ((uint32_t)c << 16) | ((uint32_t)r << 8) | (uint32_t)r;
+            } else {
+                for (int ct = r + 1; ct < T; ++ct) s.tasks[o++] = ((uint32_t)c << 16) | ((uint32_t)r << 8) | (uint32_t)ct;
+            }
+            carry += __shfl_sync(kFullMask, inc, 31);
+        }
+        ntask += total;
+        ++level;
+    }
+    if (lane == 0) {
+        s.misc[M_LEVEL] = level;
+        s.misc[M_NTASK] = ntask;
+        s.misc[M_CTR] = 0;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
 // P3/P4: class-major counting sort on score buckets, then rank inside the bucket:
 // the stable descending score sort of torchvision.ops.nms, per class
-// key = score order key (32) | class (16) | 0xffff - cell id (16)
+// key = score order key (32) | 0xffff - cell id (16) | global bucket c*B+bk (16)
 // ---------------------------------------------------------------------------
-template <int THREADS>
 __device__ __forceinline__ void phase_scatter_keys(const DNParams &p, const Smem &s, int tid, int nthr) {
     for (int cid = tid; cid < p.K; cid += nthr) {
         const uint32_t ci = s.clsidx[cid];
         if (ci == 0xffffffffu) continue;
         const float2 cs = s.cs[cid];
         const float sc = __fmul_rn(cs.y, cs.x);  // box.py:27 scores = col5*col4
-        const uint32_t c = ci >> 16;
+        const uint32_t gb = ci >> 16;
         const unsigned long long key =
-            ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)((c << 16) | (0xffffu - (uint32_t)cid));
-        s.key[s.start[c] + s.cntb[(int)c * p.B + score_bucket(sc, p.B)] + (int)(ci & 0xffffu)] = key;
+            ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)(((0xffffu - (uint32_t)cid) << 16) | gb);
+        s.key[s.start[gb >> p.Bshift] + s.cntb[gb] + (int)(ci & 0xffffu)] = key;
     }
 }
 
-template <int THREADS>
-__device__ __forceinline__ void phase_rank_sort(const DNParams &p, const Smem &s, int Kv, int tid, int nthr) {
-    if (tid < 8) s.sord[Kv + tid] = make_uint2(s.box_saddr, 0x7fc00000u);  // padding: a valid address, NaN area
-    for (int t = tid; t < Kv; t += nthr) {
-        const unsigned long long key = s.key[t];
-        const uint32_t lo32 = (uint32_t)key;
-        const uint32_t cid = 0xffffu - (lo32 & 0xffffu);
-        const int c = (int)(lo32 >> 16);
-        const int bk = score_bucket(order_key_to_float((uint32_t)(key >> 32)), p.B);
-        const int base = s.start[c];
-        const int st = base + s.cntb[c * p.B + bk];
-        const int en = base + ((bk == p.B - 1) ? s.cnt[c] : s.cntb[c * p.B + bk + 1]);
-        int rank = 0;
+// rank of every key inside its bucket -> tile-padded sorted position pp = 32 * tile + column, carried in registers
+// (pp << 16 | cell id) over the barrier after which the keys are dead
+template <int ITEMS>
+__device__ __forceinline__ void phase_rank(const DNParams &p, const Smem &s, int Kv, int tid, int nthr, uint32_t (&item)[ITEMS]) {
+    const int Bm = p.B - 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int t = tid + i * nthr;
+        item[i] = 0xffffffffu;
+        if (t < Kv) {
+            const unsigned long long key = s.key[t];
+            const uint32_t lo32 = (uint32_t)key;
+            const int gb = (int)(lo32 & 0xffffu);
+            const int c = gb >> p.Bshift;
+            const int base = s.start[c];
+            const int st = base + s.cntb[gb];
+            const int en = base + (((gb & Bm) == Bm) ? s.cnt[c] : s.cntb[gb + 1]);
+            int rank = 0;
 #pragma unroll 4
-        for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
-        const float ta = make_ta(s.box[cid], p.iou);
-        if (ta != ta) s.flag[c] = 1;  // degenerate box: the class runs the exact pair arithmetic
-        s.sord[st + rank] = make_uint2(s.box_saddr + 16u * cid, __float_as_uint(ta));
+            for (int u = st; u < en; ++u) rank += (s.key[u] > key) ? 1 : 0;
+            const int pc = st + rank - base;                      // position inside the class
+            const uint32_t pp = (uint32_t)(32 * s.ktile[c] + pc);  // tile-padded position
+            item[i] = (pp << 16) | (0xffffu - (lo32 >> 16));
+        }
+    }
+}
+
+// fp16 images of a box for the prefilter (see h16_prefilter).  Scales: X = x / 4, Y = 64 * y, so for |coordinates|
+// <= 2 the enlarged overlap width is <= 1 (HADD2.SAT clamps it at 0 from below for free) and areas down to 1.5e-5
+// (a 1.4 x 1.4 pixel box at 352 x 352) keep a NORMAL fp16 t*area.  Anything else -- non-finite or far-away
+// coordinates, tiny or huge areas, a threshold outside [0.01, 1] -- gets TA = -inf: every pair with the box is a
+// "maybe" and is decided by the exact arithmetic.
+constexpr float kH16SX = 0.25f, kH16SY = 64.0f;
+
+__device__ __forceinline__ void h16_store(const Smem &s, uint32_t pp, const float4 &b, const IouThr &t) {
+    H16Tile &tile = s.h16[pp >> 5];
+    const int k = pp & 15, hi = (pp >> 4) & 1;
+    const float a = box_area(b);
+    const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    const bool ok = t.fast_ok && a >= 1.52587890625e-05f && a <= 16.0f && big <= 2.0f;  // (false for NaN)
+    __half *xy = reinterpret_cast<__half *>(&tile.xy[k]);
+    xy[0 + hi] = ok ? __float2half_rd(__fmul_rn(b.x, kH16SX)) : __ushort_as_half((unsigned short)0);
+    xy[2 + hi] = ok ? __float2half_rd(__fmul_rn(b.y, kH16SY)) : __ushort_as_half((unsigned short)0);
+    xy[4 + hi] = ok ? __float2half_ru(__fmul_rn(b.z, kH16SX)) : __ushort_as_half((unsigned short)0);
+    xy[6 + hi] = ok ? __float2half_ru(__fmul_rn(b.w, kH16SY)) : __ushort_as_half((unsigned short)0);
+    // lower bound of t * area * 16: the 2^-8 margin covers the three fp16 roundings of the test with room to
+    // spare (see h16_prefilter)
+    reinterpret_cast<__half *>(&tile.ta[k])[hi] = ok ? __float2half_rd(__fmul_rn(a, t.th)) : __ushort_as_half((unsigned short)0xfc00);
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void phase_write_sorted(const DNParams &p, const Smem &s, const uint32_t (&item)[ITEMS]) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        if (item[i] != 0xffffffffu) {
+            const uint32_t pp = item[i] >> 16, cid = item[i] & 0xffffu;
+            s.scid[pp] = (uint16_t)cid;
+            h16_store(s, pp, s.box[cid], p.iou);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// P5: pair masks (row-major words: bit k of word (rt, ct)[lane] = row 32rt+lane suppresses
-// column 32ct+k) and the sweep
+// P5: pair blocks.
 // ---------------------------------------------------------------------------
 constexpr float kPairEps = 1e-5f;
 
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+
+// The row operands of the prefilter: the row's own H16Tile entry, broadcast into both halves
+struct H16Row { uint32_t x1, y1, x2, y2, nta; };
+
+__device__ __forceinline__ H16Row h16_row(const H16Tile &t, int lane) {
+    const int k = lane & 15;
+    const uint32_t sel = (lane & 16) ? 0x3232u : 0x1010u;
+    const uint4 e = t.xy[k];
+    H16Row r;
+    r.x1 = __byte_perm(e.x, 0, sel);
+    r.y1 = __byte_perm(e.y, 0, sel);
+    r.x2 = __byte_perm(e.z, 0, sel);
+    r.y2 = __byte_perm(e.w, 0, sel);
+    r.nta = __byte_perm(t.ta[k], 0, sel) ^ 0x80008000u;   // -TA
+    return r;
+}
+
+// Conservative fp16 prefilter of one row against the 32 columns of a tile: bit j CLEAR = torchvision provably
+// does not suppress column j by this row; bit j set = maybe.
+//   W = sat(min(X2r, X2c) - max(X1r, X1c)),  H = min(Y2r, Y2c) - max(Y1r, Y1c),  D = W * H - (TAr + TAc);  maybe iff D >= 0
+// Why D < 0 is a proof.  The fp16 boxes contain the fp32 boxes (x1, y1 rounded down, x2, y2 rounded up; min / max
+// are exact), so the exact overlap extents W*, H* of the fp16 boxes bound the true ones from above (times the
+// scales).  W and H are single roundings of W*, H* (relative error <= 2^-11; differences of fp16 numbers that
+// land below the normal range are exact), the sum is one more rounding, and the FMA computes W * H - SUM with
+// ONE rounding, which never changes a sign (a nonzero result that underflows keeps its sign bit).  Hence
+//   D < 0  =>  16 * inter_true * (1 - 2^-11)^2  <=  W * H  <  SUM  <=  16 * t * (Sa + Sb) * (1 - 2^-8) * (1 + 2^-11)
+//          =>  inter_true  <  t * (Sa + Sb) * (1 - 0.0024)            (Sa, Sb: the fp32 areas torchvision uses)
+// i.e. IoU < thr * (1 - 0.003) in exact arithmetic, and torchvision's fp32 evaluation of the IoU is within 4e-7
+// of the exact one.  If an extent is <= 0 the true boxes do not overlap on that axis either: W clamps to 0, or
+// H <= 0, and D = -SUM < 0.  Degenerate boxes carry TA = -inf, so D = +inf: maybe.  NaN cannot appear: every
+// table entry of a valid column is finite except TA = -inf, and -inf only ever meets finite numbers or itself.
+__device__ __forceinline__ uint32_t h16_prefilter(const H16Tile &t, const H16Row &r) {
+    uint32_t acc = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint4 c = t.xy[k];
+        const __half2 w = __hsub2_sat(__hmin2(u2h(r.x2), u2h(c.z)), __hmax2(u2h(r.x1), u2h(c.x)));
+        const __half2 h = __hsub2(__hmin2(u2h(r.y2), u2h(c.w)), __hmax2(u2h(r.y1), u2h(c.y)));
+        const __half2 nsum = __hsub2(u2h(r.nta), u2h(t.ta[k]));   // -(TAr + TAc)
+        const uint32_t d = h2u(__hfma2(w, h, nsum));
+        acc = (acc >> 1) | (d & 0x80008000u);                      // sign bits; after 16 steps bit k = column k, 16 + k = column 16 + k
+    }
+    return ~acc;
+}
+
+// One pair, decided exactly as torchvision decides it (call site utils/box.py:28).  The divide-free comparison
+// inter > t * (Sa + Sb) is used when it is not a close call: its roundings and torchvision's are each < 5e-7
+// relative, so outside a 1e-5 band the two agree; inside the band, for degenerate magnitudes and for thresholds
+// outside [0.01, 1] the exact routine (IEEE divide, compare in double) decides.
+__device__ __forceinline__ bool pair_decide(const float4 &R, float ra, const float4 &Cb, const IouThr &t) {
+    const float ca = box_area(Cb);
+    const float w = fmaxf(0.0f, __fsub_rn(fminf(R.z, Cb.z), fmaxf(R.x, Cb.x)));
+    const float h = fmaxf(0.0f, __fsub_rn(fminf(R.w, Cb.w), fmaxf(R.y, Cb.y)));
+    const float inter = __fmul_rn(w, h);
+    const float sum = __fadd_rn(ra, ca);
+    const float rhs = __fmul_rn(sum, t.tf);
+    const float diff = __fsub_rn(inter, rhs);
+    const bool safe = t.fast_ok && sum > 1e-30f && sum < 1e30f && inter < 1e30f;   // (false for NaN)
+    if (safe && fabsf(diff) > __fmul_rn(kPairEps, rhs)) return diff > 0.0f;
+    return nms_suppress_exact(R, ra, Cb, ca, t.thr);
+}
+
+// the exact decisions for the "maybe" bits of one block: bit j of the result = this lane's row suppresses column j
+// of tile gct.  Few bits per lane (the common case): every lane walks its own bits; many: the warp walks the union
+// column by column (uniform column loads).
+__device__ __forceinline__ uint32_t resolve_maybe(const DNParams &p, const Smem &s, int gct, uint32_t maybe, int row_pp) {
+    const int mx = __reduce_max_sync(kFullMask, (unsigned)__popc(maybe));
+    if (mx == 0) return 0u;
+    // (lanes without a "maybe" bit may sit past the end of the class: their scid entry is not a cell id)
+    const float4 R = maybe ? s.box[s.scid[row_pp]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float ra = box_area(R);
+    const uint16_t *cids = s.scid + 32 * gct;
+    uint32_t word = 0u;
+    if (mx <= 6) {
+        for (int it = 0; it < mx; ++it) {
+            if (maybe) {
+                const int j = __ffs(maybe) - 1;
+                maybe &= maybe - 1u;
+                if (pair_decide(R, ra, s.box[cids[j]], p.iou)) word |= 1u << j;
+            }
+        }
+    } else {
+        uint32_t uni = __reduce_or_sync(kFullMask, maybe);
+        while (uni) {
+            const int j = __ffs(uni) - 1;
+            uni &= uni - 1u;
+            const float4 Cb = s.box[cids[j]];
+            if (((maybe >> j) & 1u) && pair_decide(R, ra, Cb, p.iou)) word |= 1u << j;
+        }
+    }
+    return word;
+}
+
+// shared-memory hand-overs between the warps of a CTA (release / acquire at CTA scope)
+__device__ __forceinline__ int ld_acquire_s(const int *a) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s(int *a, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add_s(int *a, int v) {
+    asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_s(uint32_t *a, uint32_t v) {
+    asm volatile("red.relaxed.cta.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_s(const uint32_t *a) {
+    uint32_t v;
+    asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
+    const int lane = threadIdx.x & 31;
+    const int ntask = s.misc[M_NTASK];
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&s.misc[M_CTR], 1);
+        q = __shfl_sync(kFullMask, q, 0);
+        if (q >= ntask) break;
+        const uint32_t tk = s.tasks[q];
+        const int c = (int)(tk >> 16), rt = (int)((tk >> 8) & 0xffu), ct = (int)(tk & 0xffu);
+        const int n = s.cnt[c];
+        const int g0 = s.ktile[c];
+        const int grt = g0 + rt, gct = g0 + ct;
+        const int ncol = min(32, n - 32 * ct);
+        const uint32_t valid = (ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u);
+        if (rt == ct) {
+            // diagonal task: the tile's columns that survive the kept rows of all earlier tiles, then the tile's own
+            // turns in score order
+            if (ct > 0) {
+                while (ld_acquire_s(&s.arrived[gct]) < ct) __nanosleep(20);
+            }
+            const uint32_t alive = valid & ~ld_relaxed_s(&s.supw[gct]);
+            uint32_t rem = alive;
+            if (alive & (alive - 1u)) {   // two or more alive candidates
+                uint32_t maybe = 0u;
+                if ((alive >> lane) & 1u)
+                    maybe = h16_prefilter(s.h16[gct], h16_row(s.h16[gct], lane)) & alive & ~((2u << lane) - 1u);  // LATER columns
+                const uint32_t D = resolve_maybe(p, s, gct, maybe, 32 * gct + lane);
+                uint32_t nz = __ballot_sync(kFullMask, D != 0u);
+                while (nz) {
+                    const int i = __ffs(nz) - 1;
+                    nz &= nz - 1u;
+                    const uint32_t Di = __shfl_sync(kFullMask, D, i);
+                    if ((rem >> i) & 1u) rem &= ~Di;
+                }
+            }
+            if (lane == 0) {
+                s.keptw[gct] = rem;
+                st_release_s(&s.ready[gct], (c << 16) | 1);
+            }
+        } else {
+            // block (rows of tile rt) x (columns of tile ct): only KEPT rows matter, and only columns nobody has
+            // suppressed yet
+            while (!(ld_acquire_s(&s.ready[grt]) & 1)) __nanosleep(20);
+            const uint32_t kw = s.keptw[grt];
+            const uint32_t open = valid & ~ld_relaxed_s(&s.supw[gct]);
+            uint32_t sup = 0u;
+            if (kw != 0u && open != 0u) {
+                uint32_t maybe = 0u;
+                if ((kw >> lane) & 1u) maybe = h16_prefilter(s.h16[gct], h16_row(s.h16[grt], lane)) & open;
+                const uint32_t word = resolve_maybe(p, s, gct, maybe, 32 * grt + lane);
+                sup = __reduce_or_sync(kFullMask, word);
+            }
+            if (lane == 0) {
+                if (sup) red_or_s(&s.supw[gct], sup);
+                red_release_add_s(&s.arrived[gct], 1);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// fp32 pair blocks over a {shared address of the box, t*area} table: used by large_nms.cuh
 // exact torchvision decisions of one row against the columns of one tile (slow path)
 __device__ __noinline__ uint32_t block_exact(const uint2 *ordc, int ncol, const float4 R, double thr) {
     const float ra = box_area(R);
@@ -891,80 +1121,6 @@ __device__ __forceinline__ uint32_t block_fast(const uint2 *ordc, int ncol, cons
     return word;
 }
 
-// sweep of one class over the column tiles [t0, te) (earlier tiles' kept words are final)
-__device__ __forceinline__ void sweep_class(const Smem &s, int c, int t0, int te, int tri0) {
-    const int lane = threadIdx.x & 31;
-    const int n = s.cnt[c];
-    uint32_t *kept_w = s.keptbits + s.ktile[c];
-    const uint32_t *mb = s.mask + s.maskbase[c];
-    for (int ct = t0; ct < te; ++ct) {
-        const uint32_t *blk = mb + (tri(ct) - tri0) * 32 + lane;
-        uint32_t sup = 0u;
-        for (int rt = 0; rt < ct; ++rt) {
-            const uint32_t wv = blk[rt * 32];
-            if ((kept_w[rt] >> lane) & 1u) sup |= wv;
-        }
-        sup = __reduce_or_sync(kFullMask, sup);
-        const int ncol = min(32, n - 32 * ct);
-        const uint32_t valid = (ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u);
-        const uint32_t alive = valid & ~sup;
-        // diagonal block: only rows that are alive and suppress an alive column need a turn
-        const uint32_t D = ((alive >> lane) & 1u) ? (blk[ct * 32] & alive) : 0u;
-        uint32_t nz = __ballot_sync(kFullMask, D != 0u);
-        uint32_t rem = alive;
-        while (nz) {
-            const int i = __ffs(nz) - 1;
-            nz &= nz - 1u;
-            const uint32_t Di = __shfl_sync(kFullMask, D, i);
-            if ((rem >> i) & 1u) rem &= ~Di;
-        }
-        if (lane == 0) kept_w[ct] = rem;
-        __syncwarp();
-    }
-}
-
-__device__ __forceinline__ void phase_pairs_sweep(const DNParams &p, const Smem &s) {
-    const int lane = threadIdx.x & 31;
-    const int t0 = s.misc[M_T0], t1 = s.misc[M_T1];
-    const int ntask = s.misc[M_NTASK];
-    const int tri0 = tri(t0);
-    for (;;) {
-        int q = 0;
-        if (lane == 0) q = atomicAdd(&s.misc[M_CTR], 1);
-        q = __shfl_sync(kFullMask, q, 0);
-        if (q >= ntask) break;
-        const uint32_t tk = s.tasks[q];
-        const int c = (int)(tk >> 16), rt = (int)(tk & 0xffffu);
-        const int n = s.cnt[c];
-        const int te = min((n + 31) >> 5, t1);
-        const uint2 *ord = s.sord + s.start[c];
-        const int row = 32 * rt + lane;
-        const uint2 re = ord[min(row, n - 1)];
-        const float4 R = lds_f4(re.x);
-        const float rta = __uint_as_float(re.y);
-        const bool slow = s.flag[c] != 0;
-        uint32_t *mb = s.mask + s.maskbase[c] + (rt - tri0) * 32 + lane;
-        for (int ct = max(rt, t0); ct < te; ++ct) {
-            const int ncol = min(32, n - 32 * ct);
-            uint32_t word = slow ? block_exact(ord + 32 * ct, ncol, R, p.iou.thr) : block_fast(ord + 32 * ct, ncol, R, rta, p.iou.thr);
-            if (ct == rt) word &= ~((2u << lane) - 1u);  // only LATER columns (2u << 31 == 0: none)
-            if (row >= n) word = 0u;
-            mb[tri(ct) * 32] = word;
-        }
-        __syncwarp();
-        int old = 0;
-        if (lane == 0) {
-            __threadfence_block();
-            old = atomicAdd(&s.done[c], 1);
-        }
-        old = __shfl_sync(kFullMask, old, 0);
-        if (old == te - 1) {  // last strip of the class in this round: its masks are complete
-            __threadfence_block();
-            sweep_class(s, c, t0, te, tri0);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // P6: output.  Tile g of the kept bitmap holds up to 32 rows that are consecutive in the
 // output (class-ascending, score-descending); the warp assembles them in its scratch and
@@ -987,7 +1143,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
     const int per = (ntiles + kWarps) / kWarps;  // ceil((ntiles + 1) / kWarps): "tile" ntiles writes the count
     const int g0 = warp * per, g1 = min(g0 + per, ntiles + 1);
     int before = 0;
-    for (int t = lane; t < g0; t += 32) before += __popc(s.keptbits[t]);
+    for (int t = lane; t < g0; t += 32) before += __popc(s.keptw[t]);
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
     for (int g = g0; g < g1; ++g) {
@@ -1003,14 +1159,12 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
             }
             break;
         }
-        const uint32_t word = s.keptbits[g];
+        const uint32_t word = s.keptw[g];
         const int nk = __popc(word);
         if (nk == 0) continue;
-        const int c = s.tilecls[g];
-        const int pos = s.start[c] + 32 * (g - s.ktile[c]) + lane;
         if ((word >> lane) & 1u) {
             const int r = __popc(word & lanemask_lt());
-            const uint32_t cid = (s.sord[pos].x - s.box_saddr) >> 4;
+            const uint32_t cid = s.scid[32 * g + lane];
             float *d = scr + 7 * r;
             if (MODE == MODE_NMS) {
                 const float *src = ((int)cid < K0) ? r0 + (size_t)cid * 7 : r1 + (size_t)((int)cid - K0) * 7;
@@ -1021,7 +1175,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
                 const float2 cs = s.cs[cid];
                 d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
                 d[4] = cs.x; d[5] = cs.y;
-                d[6] = (float)c;  // cls_idx.float() (yolo_loss.py:199)
+                d[6] = (float)(s.ready[g] >> 16);  // cls_idx.float() (yolo_loss.py:199)
             }
             if (p.out_idx) p.out_idx[(size_t)b * p.K + before + r] = (int)cid;
         }
@@ -1072,19 +1226,22 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
 // kernel
 // ---------------------------------------------------------------------------
 // GATHER: the fused all-gather variant of the output phase (its own instantiation, so the ordinary kernel's register
-// allocation is untouched)
-template <int MODE, int THREADS, int SHAPE, int GATHER = 0>
+// allocation is untouched).  DBG: phase time stamps (profiles/phase_times.py).
+template <int MODE, int THREADS, int SHAPE, int GATHER = 0, bool DBG = false>
 __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve(smem_raw, L, p.K, p.C, MODE);
+    const Smem s = carve(smem_raw, L, p.K, p.C);
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.C, K = p.K;
     using SH = ShapeT<SHAPE>;
 
     pdl_trigger();  // the next launch may start filling free SM slots right away (it waits before it writes)
-    if (MODE == MODE_NMS || p.dbg) pdl_wait();  // (inputs written by our own decode kernels; debug stamps are global stores)
-    stamp(p, b, 0);
+    // Inputs another kernel of this library wrote (rows of our own decode kernels), or a producer launched with the
+    // programmatic attribute, must be complete and visible before the first global read: p.wait_inputs is set by the
+    // host unless the caller vouches that the inputs were produced in ordinary stream order (see launch_dn_t).
+    if (MODE == MODE_NMS || p.wait_inputs || (DBG && p.dbg)) pdl_wait();
+    stamp<DBG>(p, b, 0);
     if (MODE != MODE_NMS) {
         // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
         // only issue after the launch ramp) finds its lines on the way (-1 us).  Prefetching more --
@@ -1103,35 +1260,34 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     constexpr bool kStaticShape = (MODE != MODE_NMS && SH::C > 0 && !ShapeIsNhwc<SHAPE>::value);
     if (MODE != MODE_DECODE) {
         for (int i = tid; i <= C * p.B; i += THREADS) s.cntb[i] = 0;
-        for (int i = tid; i <= C; i += THREADS) s.flag[i] = 0;
         if (!kStaticShape) __syncthreads();  // (compile-time shapes: the barrier sits behind the first round's loads)
     }
-    stamp(p, b, 15);
+    stamp<DBG>(p, b, 15);
 
     if constexpr (MODE == MODE_NMS) {
         phase_load_rows<THREADS>(p, s, b);
     } else if constexpr (kStaticShape && MODE == MODE_DECODE) {
-        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, false>(p, s, b, p.head[0], 0, 0);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, false, DBG>(p, s, b, p.head[0], 0, 0);
     } else if constexpr (kStaticShape) {
-        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true>(p, s, b, p.head[0], 0, 0);
-        decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false>(p, s, b, p.head[1], p.head[0].cells, 1);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true, DBG>(p, s, b, p.head[0], 0, 0);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false, DBG>(p, s, b, p.head[1], p.head[0].cells, 1);
     } else if constexpr (kNhwcShape) {
-        // scratch: the part of U that is free during the decode (behind clsidx); the host checked that it fits
-        float *scr = reinterpret_cast<float *>(smem_raw + L.U + 4 * align_up((uint32_t)(K > 0 ? K : 1), 32));
+        // scratch: the key region of U, free during the decode; the host checked that it fits
+        float *scr = reinterpret_cast<float *>(smem_raw + L.key_off);
         decode_head_nhwc<THREADS, SH::C>(p, s, b, p.head[0], 0, scr);
         decode_head_nhwc<THREADS, SH::C>(p, s, b, p.head[1], p.head[0].cells, scr);
     } else {
         if (MODE == MODE_FUSED && p.nhwc) {
-            float *scr = reinterpret_cast<float *>(smem_raw + L.U + 4 * align_up((uint32_t)(K > 0 ? K : 1), 32));
+            float *scr = reinterpret_cast<float *>(smem_raw + L.key_off);
             decode_head_nhwc<THREADS, 0>(p, s, b, p.head[0], 0, scr);
             decode_head_nhwc<THREADS, 0>(p, s, b, p.head[1], p.head[0].cells, scr);
         } else {
-            decode_head_rt<THREADS, MODE>(p, s, b, p.head[0], 0, 0);
-            if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE>(p, s, b, p.head[1], p.head[0].cells, 1);
+            decode_head_rt<THREADS, MODE, DBG>(p, s, b, p.head[0], 0, 0);
+            if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE, DBG>(p, s, b, p.head[1], p.head[0].cells, 1);
         }
     }
     __syncthreads();
-    stamp(p, b, 1);
+    stamp<DBG>(p, b, 1);
 
     if (MODE == MODE_DECODE) {
         // YOLOLoss.get_pred_boxes output: rows in candidate order (:203)
@@ -1169,41 +1325,47 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
         return;
     }
 
-    // P2: bucket positions inside each class (warp per class), then the class starts (warp 0)
+    // P2: bucket positions inside each class (warp per class), then the class starts and tile tables (warp 0)
     scan_buckets_per_class<THREADS>(p, s);
     __syncthreads();
-    stamp(p, b, 12);
-    if (warp == 0) warp_class_starts(p, s);
+    stamp<DBG>(p, b, 12);
+    if (warp == 0) {
+        warp_class_starts(p, s);
+        warp_tile_tables(p, s);
+    }
     __syncthreads();
-    stamp(p, b, 13);
+    stamp<DBG>(p, b, 13);
     const int Kv = s.misc[M_KV];
     if (warp == 0) {
-        // kept-bitmap tiles, round table, strip tasks: only the pair phase needs them, so warp 0 builds
-        // them while the other warps sort
-        warp_class_scan(p, s, (int)L.mask_words);
-        warp_round_prefix(s, 0);
+        // the first window of pair tasks: only the pair phase needs it, so warp 0 builds it while the other warps sort
+        warp_build_tasks(p, s, (int)L.task_cap);
     } else {
-        // P3 / P4 on the other warps (named barrier 1 between the key scatter and the ranking)
-        phase_scatter_keys<THREADS>(p, s, tid - 32, THREADS - 32);
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS - 32) : "memory");
-        phase_rank_sort<THREADS>(p, s, Kv, tid - 32, THREADS - 32);
+        // P3 / P4 on the other warps (named barrier 1 between the key scatter, the ranking, and the writes that
+        // reuse the key memory)
+        constexpr int kSorters = THREADS - 32;
+        uint32_t item[kRankItems];
+        phase_scatter_keys(p, s, tid - 32, kSorters);
+        asm volatile("bar.sync 1, %0;" ::"n"(kSorters) : "memory");
+        phase_rank<kRankItems>(p, s, Kv, tid - 32, kSorters, item);
+        asm volatile("bar.sync 1, %0;" ::"n"(kSorters) : "memory");
+        phase_write_sorted<kRankItems>(p, s, item);
     }
     __syncthreads();
-    stamp(p, b, 3);
-    const int nrounds = s.misc[M_NROUNDS];
-    // P5
-    for (int r = 0;;) {
-        phase_pairs_sweep(p, s);
+    stamp<DBG>(p, b, 3);
+    // P5 (windows of whole task levels; one window unless the image has more blocks than the table holds)
+    for (;;) {
+        phase_pairs(p, s);
         __syncthreads();
-        if (++r >= nrounds) break;
-        if (warp == 0) warp_round_prefix(s, r);
+        if (s.misc[M_LEVEL] >= s.misc[M_NLEVELS]) break;
+        __syncthreads();   // (everybody has read M_LEVEL before warp 0 advances it)
+        if (warp == 0) warp_build_tasks(p, s, (int)L.task_cap);
         __syncthreads();
     }
-    stamp(p, b, 4);
-    // P6 (the mask buffer is dead now; the row scratch aliases it)
+    stamp<DBG>(p, b, 4);
+    // P6 (the fp16 tables are dead now; the row scratch aliases them)
     pdl_wait();
     phase_output<MODE, THREADS, GATHER>(p, s, b);
-    stamp(p, b, 7);
+    stamp<DBG>(p, b, 7);
 }
 
 }  // namespace b200yolo

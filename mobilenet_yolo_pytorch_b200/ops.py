@@ -209,6 +209,52 @@ def decode_nms_padded(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_
     return (out, out_count, out_idx) if want_idx else (out, out_count)
 
 
+class BatchPlan:
+    """A list of batches of ONE shape for ``b200yolo_decode_nms_batches``: the descriptor array is built once, then
+    ``run()`` issues every launch from C in one call (no Python between the launches; launch k > 0 overlaps the tail of
+    launch k - 1, see include/b200yolo.h).  ``batches`` is a sequence of ``(head0, head1, out, out_count[, out_idx])``
+    CUDA tensors (NCHW-contiguous heads of equal shape)."""
+
+    def __init__(self, batches, anchor_wh2, num_classes: int, conf_thr: float, iou_thr: float = NMS_IOU_THRESHOLD):
+        if len(batches) == 0:
+            raise RuntimeError("BatchPlan needs at least one batch")
+        h0, h1 = batches[0][0], batches[0][1]
+        _require_cuda(h0, "head0")
+        _require_cuda(h1, "head1")
+        attrs = 5 + num_classes
+        N, ch, H0, W0 = h0.shape
+        _, _, H1, W1 = h1.shape
+        if ch % attrs:
+            raise RuntimeError("head shapes do not match (N, A*(5+C), H, W)")
+        A = ch // attrs
+        self.K = A * H0 * W0 + A * H1 * W1
+        self.dev = h0.device
+        self.keep = list(batches)   # the tensors must outlive the plan
+        self.aw = _host_f32(anchor_wh2).reshape(2, A, 2)
+        self.arr = (_lib.Batch * len(batches))()
+        for k, bt in enumerate(batches):
+            a0, a1, out, cnt = bt[0], bt[1], bt[2], bt[3]
+            idx = bt[4] if len(bt) > 4 else None
+            if a0.shape != h0.shape or a1.shape != h1.shape or not a0.is_contiguous() or not a1.is_contiguous():
+                raise RuntimeError("BatchPlan: every batch needs NCHW-contiguous heads of the first batch's shape")
+            if tuple(out.shape) != (N, self.K, 7) or cnt.numel() != N:
+                raise RuntimeError("BatchPlan: out must be (N, K, 7) and out_count (N,)")
+            self.arr[k] = _lib.Batch(a0.data_ptr(), a1.data_ptr(), out.data_ptr(), cnt.data_ptr(),
+                                     idx.data_ptr() if idx is not None else None)
+        self.args = (N, A, num_classes, H0, W0, H1, W1, self.aw.ctypes.data, float(np.float32(conf_thr)), float(iou_thr))
+        self.n = len(batches)
+
+    def run(self, first: int = 0, count: Optional[int] = None):
+        """Launch batches [first, first + count) on the current stream of the plan's device."""
+        count = self.n - first if count is None else count
+        if first < 0 or count < 0 or first + count > self.n:
+            raise RuntimeError("BatchPlan.run: range outside the plan")
+        ptr = C.cast(C.byref(self.arr, first * C.sizeof(_lib.Batch)), C.c_void_p)
+        with _on_device(self.dev):
+            _lib.check(_lib.load().b200yolo_decode_nms_batches(ptr, count, *self.args,
+                                                               torch.cuda.current_stream(self.dev).cuda_stream))
+
+
 def decode_nms_host(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
                     iou_thr: float = NMS_IOU_THRESHOLD, device: int = 0, out: Optional[torch.Tensor] = None,
                     out_count: Optional[torch.Tensor] = None):
