@@ -2,24 +2,30 @@
 """bench.py -- decode + NMS images/s of the MobileNet-YOLO detection hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload cfg2|cfg2_sparse|cfg3|cfg5|cfg4_loss]   (cfg4_loss: the YOLOLoss target-assignment path)
+                    [--workload cfg2|cfg2_sparse|cfg3|cfg5|cfg5_832|cfg4_loss] [--no-extra]
 
 A "step" is one pass of the hot path over one batch of synthetic head tensors
 (BASELINE.json configs[1]: MobileNetV2-YOLO 352x352 VOC heads, batch 256 per GPU,
 torch.randn heads, val_conf 0.3).  With N > 1 (launched under torchrun, one rank
-per GPU) the batch shards by image: every rank owns 256 images (weak scaling);
-there is no collective in the data path.  Rank 0 prints ONE JSON line.
+per GPU) the batch shards by image: every rank owns 256 images (weak scaling) and
+a step is kernel + all-gather of the detections + fence ("all-gather
+included for > 1 GPU"): the gather is fused into the kernel's output phase (peer
+stores over NVLink, dist.PeerGather).  Rank 0 prints ONE JSON line.
+
+The K steps of the timed region are issued by ONE C call (b200yolo_decode_nms_batches /
+b200yolo_decode_nms_gather_steps): no Python between the launches.
 
 Keys beyond the base contract: `roofline` (dominant kernel, algorithmic bytes /
 CUDA-event time vs the measured HBM peak), `cpu_baseline` (the CPU oracle port on
 this box's host cores), `e2e` (same metric through the host-buffer C-ABI call,
-H2D + D2H inside the timed region), `extra` (sparse-head variant, NMS-only and
-all-gather timings).
+H2D + D2H inside the timed region), `extra` (the reference's own Python on this box's
+CPU and GPU, NMS alone against torchvision's CUDA kernel, sparse heads, the other
+BASELINE configurations with their own roofline blocks, config-1 latency).
 
-`--impl reference` times the reference's algorithm on the CPU: the reference is
-pure Python that cannot travel to the GPU box (/root/reference is absent there)
-so the arm runs the oracle port (oracle/yolo_oracle.c, OpenMP over all host
-threads) -- see DESIGN.md "Measurement".
+`--impl reference` times the UNMODIFIED reference Python (oracle/_ref snapshot, see
+oracle/snapshot_reference.py) on the host cores in a subprocess with
+CUDA_VISIBLE_DEVICES="" (cpu_baseline.kind "reference"); where the snapshot is
+missing it falls back to the C port (kind "port").
 """
 from __future__ import annotations
 
@@ -27,8 +33,8 @@ import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -43,20 +49,21 @@ BDD_ANCHORS = [[34, 47], [66, 93], [122, 182], [6, 11], [11, 43], [16, 22]]     
 MASK = [[0, 1, 2], [3, 4, 5]]
 
 WORKLOADS = {
-    # name: (batch per GPU, classes, grids (H,W) of head0/head1, anchors, img_size [W,H], val_conf, conf logit shift)
-    "cfg2": dict(N=256, C=20, grids=[(11, 11), (22, 22)], anchors=VOC_ANCHORS, img=[352, 352], conf=0.3, shift=0.0,
+    # N: batch per GPU when the workload is weak-scaled; GB: global batch when BASELINE.json fixes it (strong scaling)
+    "cfg2": dict(N=256, GB=None, C=20, grids=[(11, 11), (22, 22)], anchors=VOC_ANCHORS, img=[352, 352], conf=0.3, shift=0.0,
                  desc="MobileNetV2-YOLO 352x352 VOC 20-class heads, batch 256 per GPU, randn heads, val_conf 0.3"),
-    "cfg2_sparse": dict(N=256, C=20, grids=[(11, 11), (22, 22)], anchors=VOC_ANCHORS, img=[352, 352], conf=0.3,
+    "cfg2_sparse": dict(N=256, GB=None, C=20, grids=[(11, 11), (22, 22)], anchors=VOC_ANCHORS, img=[352, 352], conf=0.3,
                         shift=-2.6, desc="cfg2 with objectness logits shifted by -2.6 (~4% of cells pass, as trained heads do)"),
-    "cfg3": dict(N=128, C=10, grids=[(12, 20), (24, 40)], anchors=BDD_ANCHORS, img=[640, 384], conf=0.3, shift=0.0,
-                 desc="MobileNetV3-YOLO BDD100k 10-class 640x384 heads, batch 1024/8 = 128 per GPU"),
-    "cfg5": dict(N=512, C=20, grids=[(13, 13), (26, 26)], anchors=VOC_ANCHORS, img=[416, 416], conf=0.001, shift=0.0,
-                 desc="dense-candidate NMS stress: 416x416 heads, val_conf 0.001, batch 4096/8 = 512 per GPU"),
-    "cfg5_832": dict(N=128, C=20, grids=[(26, 26), (52, 52)], anchors=VOC_ANCHORS, img=[832, 832], conf=0.001, shift=0.0,
+    "cfg3": dict(N=128, GB=1024, C=10, grids=[(12, 20), (24, 40)], anchors=BDD_ANCHORS, img=[640, 384], conf=0.3, shift=0.0,
+                 desc="MobileNetV3-YOLO BDD100k 10-class 640x384 heads, global batch 1024 sharded over the GPUs"),
+    "cfg5": dict(N=512, GB=4096, C=20, grids=[(13, 13), (26, 26)], anchors=VOC_ANCHORS, img=[416, 416], conf=0.001, shift=0.0,
+                 desc="dense-candidate NMS stress: 416x416 heads, val_conf 0.001 (all 2535 cells pass), global batch 4096 sharded over the GPUs"),
+    "cfg5_832": dict(N=128, GB=None, C=20, grids=[(26, 26), (52, 52)], anchors=VOC_ANCHORS, img=[832, 832], conf=0.001, shift=0.0,
                      desc="the ~10k-boxes-per-image reading of the stress configuration: 832x832 heads (10140 cells per "
                           "image, all pass val_conf 0.001), batch 128 per GPU, large-image path (b200yolo_decode_nms_large)"),
 }
 A = 3
+L2_NOTE = "inputs larger than L2: rotating input sets of >= 400 MB in total (126 MB L2), so every step reads its heads from HBM"
 
 
 def parse_args():
@@ -96,61 +103,99 @@ def cells_per_image(wl):
     return sum(A * H * W for (H, W) in wl["grids"])
 
 
+def local_batch(wl, world, rank=0):
+    if wl["GB"] is None:
+        return wl["N"]
+    base, rem = divmod(wl["GB"], world)
+    return base + (1 if rank < rem else 0)
+
+
+def workload_config(name, wl, world):
+    """Identical in both arms (the driver compares the dicts)."""
+    n = local_batch(wl, world)
+    return {"workload": wl["desc"], "name": name, "batch_per_gpu": n, "global_batch": wl["GB"] if wl["GB"] else world * n,
+            "cells_per_image": cells_per_image(wl), "l2": L2_NOTE}
+
+
+def load_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured"
+    except Exception:  # noqa: BLE001
+        pass
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md), of fallback"
+
+
 # ----------------------------------------------------------------------------- clocks
+_SAMPLER_SRC = r"""
+import json, select, sys, time
+idx = int(sys.argv[1])
+samples, reasons, max_sm = [], set(), None
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+    max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+except Exception:
+    nv = None
+print("ready", flush=True)
+while True:
+    r, _, _ = select.select([sys.stdin], [], [], 0.003)
+    if r:
+        break
+    if nv is not None:
+        try:
+            samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            t = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for k, bit in names.items():
+                if t & bit:
+                    reasons.add(k)
+        except Exception:
+            pass
+samples.sort()
+print(json.dumps({"sm_mhz": (samples[len(samples) // 2] if samples else None), "sm_max_mhz": max_sm,
+                  "reasons": sorted(reasons), "samples": len(samples)}), flush=True)
+"""
+
+
 class ClockSampler:
-    """NVML poll (the recipe's nvidia-smi clocks line, at a few ms instead of 200 ms
-    so that sub-second timed regions are still seen)."""
+    """NVML poll every ~3 ms (the recipe's nvidia-smi clocks line, faster) in a SEPARATE PROCESS, so that it never
+    competes with the launching thread for the interpreter lock."""
 
     def __init__(self, index):
-        self.samples = []
-        self.reasons = set()
-        self._stop = threading.Event()
-        self._thr = None
+        self.proc = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            phys = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(phys)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, text=True)
+            self.proc.stdout.readline()  # "ready"
         except Exception:  # noqa: BLE001
-            self.nv = None
-            self.max_sm = None
-
-    def _poll(self):
-        nv = self.nv
-        names = {
-            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-        }
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.003)
-
-    def start(self):
-        if self.nv is not None:
-            self._thr = threading.Thread(target=self._poll, daemon=True)
-            self._thr.start()
+            self.proc = None
 
     def stop(self):
-        if self._thr is not None:
-            self._stop.set()
-            self._thr.join()
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_sm,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        try:
+            self.proc.stdin.write("\n")
+            self.proc.stdin.flush()
+            line = self.proc.stdout.readline()
+            self.proc.wait(timeout=5)
+            return json.loads(line)
+        except Exception:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
 
-# ----------------------------------------------------------------------------- CPU (oracle) arm
+# ----------------------------------------------------------------------------- CPU arms (oracle port / reference python)
 def host_threads():
     """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it)."""
     try:
@@ -159,28 +204,25 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_decode_nms_rate(wl, budget_s=12.0, max_reps=50):
-    """images/s of the CPU oracle port on this box's cores, bounded sample."""
+def cpu_port_rate(wl, N, budget_s=10.0, max_reps=30):
+    """images/s of the CPU oracle port on this box's cores, bounded sample (median over the passes)."""
     import oracle
     oracle.set_threads(host_threads())
-    N = wl["N"]
     h0, h1 = make_heads(wl, N, seed=0)
     h0, h1 = h0.numpy(), h1.numpy()
     tables = anchor_tables(wl)
     oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])  # warm-up (page-in, thread pool)
     t0 = time.perf_counter()
-    reps = 0
     times = []
-    while reps < max_reps and time.perf_counter() - t0 < budget_s:
+    while len(times) < max_reps and (len(times) < 5 or time.perf_counter() - t0 < budget_s):
         t = time.perf_counter()
         oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])
         times.append(time.perf_counter() - t)
-        reps += 1
     med = statistics.median(times)
-    return N / med, reps, med
+    return N / med, len(times), med
 
 
-def cpu_loss_rate(N, G):
+def cpu_loss_port_rate(N, G):
     """images/s of the CPU oracle port for YOLOLoss.forward(input, targets), both VOC heads."""
     import oracle
     oracle.set_threads(host_threads())
@@ -188,45 +230,81 @@ def cpu_loss_rate(N, G):
     h0, h1 = make_heads(wl, N, seed=100)
     targets = make_targets(N, G, wl["C"], 1)
     args = [(h0.numpy(), MASK[0], VOC_IGNORE[0]), (h1.numpy(), MASK[1], VOC_IGNORE[1])]
-    best = 1e9
-    for _ in range(3):
+    times = []
+    for _ in range(5):
         t = time.perf_counter()
         for h, m, ign in args:
             oracle.target_loss(h, targets, VOC_ANCHORS, m, wl["C"], [352, 352], ign, VOC_IOU_THRESH, VOC_IOU_WEIGHTING)
-        best = min(best, time.perf_counter() - t)
-    return N / best
+        times.append(time.perf_counter() - t)
+    return N / statistics.median(times)
 
 
-def run_reference(args, wl):
-    """--impl reference: the CPU path (oracle port), rank 0 only."""
+def reference_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "models", "yolo_loss.py")) or \
+        os.path.exists("/root/reference/models/yolo_loss.py")
+
+
+def run_ref_bench(device, what, workload, n, reps, budget=40.0, timeout=600):
+    """oracle/ref_bench.py in a subprocess (the reference fixes its device at import, quirk Q4). -> dict or {'error'}"""
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    if device == "cpu":
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--device", device, "--what", what, "--workload", workload,
+           "--n", str(n), "--reps", str(reps), "--budget", str(budget)]
+    if device == "cpu":
+        cmd += ["--threads", str(host_threads())]
+    try:
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+        lines = [l for l in res.stdout.strip().splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"error": (res.stderr or res.stdout)[-400:]}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def run_reference(args, name, wl):
+    """--impl reference: the reference's own CPU path, rank 0 only.  Each step = one pass over a bounded sample of
+    the workload (n_ref images of the same shapes / seeds); value = images/s from the median step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = args.gpus
+    steps, warm = max(1, args.steps), max(args.warmup, 3)
+    cfg = workload_config(name, wl, world)
+    if reference_available():
+        n_ref = 32
+        r = run_ref_bench("cpu", "decode_nms", name if name in WORKLOADS else "cfg2", n_ref, steps, budget=150.0, timeout=900)
+        if "error" not in r:
+            val = r["images_per_s"]
+            line = {
+                "impl": "reference", "metric": "decode+NMS images/sec", "value": val, "unit": "images/s", "n_gpus": world,
+                "steps": r["reps"], "warmup": warm, "ms_per_step": 1e3 * r["median_s"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": val, "unit": "images/s", "cores": r["threads"], "kind": "reference",
+                                 "sample": f"{r['reps']} passes over {n_ref} images of the workload (the batch is {cfg['batch_per_gpu']}): "
+                                           "YOLOLoss.forward x2 + utils.box.nms of the unmodified reference (oracle/_ref), "
+                                           f"torch {r['torch']} / torchvision {r['torchvision']} on the host cores, median pass"},
+                "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "spread": {"min_s": r["min_s"], "max_s": r["max_s"], "median_s": r["median_s"]},
+            }
+            print(json.dumps(line), flush=True)
+            return
+    # no snapshot (or it failed): the C restatement of the algorithm
     import oracle
-    oracle.set_threads(host_threads())
-    N = wl["N"]
-    h0, h1 = make_heads(wl, N, seed=0)
-    h0, h1 = h0.numpy(), h1.numpy()
-    tables = anchor_tables(wl)
-    for _ in range(max(1, min(args.warmup, 3))):
-        oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])
-    steps = max(1, min(args.steps, 40))  # each step = one pass over the same batch of N images; bounded
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        oracle.decode_nms_padded(h0, h1, tables, wl["C"], wl["conf"])
-    dt = time.perf_counter() - t0
-    val = N * steps / dt
+    N = local_batch(wl, world)
+    val, reps, med = cpu_port_rate(wl, N, budget_s=20.0, max_reps=max(5, min(steps, 40)))
     line = {
-        "impl": "reference", "metric": "decode+NMS images/sec", "value": val, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch": N},
+        "impl": "reference", "metric": "decode+NMS images/sec", "value": val, "unit": "images/s", "n_gpus": world,
+        "steps": reps, "warmup": warm, "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": oracle.max_threads(), "kind": "port",
-                         "sample": f"{steps} passes over the full {N}-image batch (oracle/yolo_oracle.c, OpenMP)"},
+                         "sample": f"{reps} passes over the full {N}-image batch (oracle/yolo_oracle.c, OpenMP), median pass; "
+                                   "the reference snapshot oracle/_ref is not present on this box"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python and /root/reference does not exist on the GPU box; this arm is the "
-                "C restatement of its algorithm (pinned by tests/golden), all host threads",
     }
     print(json.dumps(line), flush=True)
 
@@ -246,6 +324,16 @@ def make_targets(N, G, C, seed):
         c = wh / 2 + r.rand(G, 2) * (1 - wh)
         out.append(np.concatenate((r.randint(1, C + 1, (G, 1)), c, wh), 1).astype(np.float32))
     return out
+
+
+def time_loop(fn, steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1)  # ms
 
 
 def time_loss(dev, N, G, steps=100, seed=1):
@@ -294,87 +382,200 @@ def time_loss(dev, N, G, steps=100, seed=1):
 
 
 # ----------------------------------------------------------------------------- B200 arm
-def time_loop(fn, steps, stream=None):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        fn(i)
-    e1.record()
-    e1.synchronize()
-    return e0.elapsed_time(e1)  # ms
+class Dist:
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, v):
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v):
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
 
 
-def run_b200(args, wl):
-    import torch.distributed as dist
+class DecodeNmsRun:
+    """K steps of decode + NMS on this rank's shard, issued by one C call.  world > 1: kernel + fused all-gather
+    (peer stores over NVLink) + fence per step."""
+
+    def __init__(self, D, wl, n_local, steps, gather=True, seed0=0):
+        from mobilenet_yolo_pytorch_b200 import _lib, ops
+        from mobilenet_yolo_pytorch_b200 import dist as b2dist
+        self.D, self.wl, self.N, self.steps = D, wl, n_local, steps
+        self.K = cells_per_image(wl)
+        self.tables = anchor_tables(wl)
+        self.in_bytes = n_local * bytes_in_per_image(wl)
+        self.R = max(4, int(np.ceil(400e6 / max(self.in_bytes, 1))))
+        self.sets = []
+        for r in range(self.R):
+            h0, h1 = make_heads(wl, n_local, seed=seed0 + 1000 * D.rank + r)
+            self.sets.append((h0.to(D.dev), h1.to(D.dev)))
+        self.large = self.K > _lib.load().b200yolo_max_cells(D.local)
+        self.gather = gather and D.world > 1 and not self.large
+        self.out = torch.empty((n_local, self.K, 7), dtype=torch.float32, device=D.dev)
+        self.cnt = torch.empty((n_local,), dtype=torch.int32, device=D.dev)
+        self.ops = ops
+        self.pg = None
+        if self.large:
+            self.plan = None
+        elif self.gather:
+            self.pg = b2dist.PeerGather(n_local, self.K)
+            self.plan = self.pg.run_steps([self.sets[i % self.R] for i in range(steps)], self.tables, wl["C"], wl["conf"])
+            torch.cuda.synchronize()
+        else:
+            self.plan = ops.BatchPlan([(self.sets[i % self.R][0], self.sets[i % self.R][1], self.out, self.cnt) for i in range(steps)],
+                                      self.tables, wl["C"], wl["conf"])
+
+    def run(self, count=None):
+        count = self.steps if count is None else count
+        if self.large:
+            for i in range(count):
+                h0, h1 = self.sets[i % self.R]
+                self.ops.decode_nms_padded(h0, h1, self.tables, self.wl["C"], self.wl["conf"], out=self.out, out_count=self.cnt)
+        elif self.gather:
+            # (a shorter run re-uses the head of the plan)
+            if count == self.steps:
+                self.pg.run_steps(None, None, self.wl["C"], self.wl["conf"], plan=self.plan)
+            else:
+                sub = (self.plan[0], count) + self.plan[2:]
+                self.pg.run_steps(None, None, self.wl["C"], self.wl["conf"], plan=sub)
+        else:
+            self.plan.run(0, count)
+
+    def kept_per_launch(self):
+        """kept rows of this rank's shard, averaged over the rotating sets"""
+        kept = []
+        for r in range(self.R):
+            h0, h1 = self.sets[r]
+            self.ops.decode_nms_padded(h0, h1, self.tables, self.wl["C"], self.wl["conf"], out=self.out, out_count=self.cnt)
+            kept.append(int(self.cnt.sum().item()))
+        return float(np.mean(kept))
+
+    def time(self, warmup):
+        D = self.D
+        self.run(min(max(warmup, 3), self.steps))
+        D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.run()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        D.barrier()
+        if self.pg is not None:
+            self.pg.check()
+        return D.max(ms) / self.steps
+
+    def close(self):
+        if self.pg is not None:
+            self.pg.close()
+            self.pg = None
+        self.sets = None
+
+
+def measure_workload(D, name, steps, warmup, peak):
+    """One BASELINE configuration at this world size -> dict with its own roofline block (rank 0 returns it)."""
+    wl = WORKLOADS[name]
+    n_local = local_batch(wl, D.world, D.rank)
+    run = DecodeNmsRun(D, wl, n_local, steps, seed0=7000)
+    kept = run.kept_per_launch()
+    ms = run.time(warmup)
+    total_images = D.sum(n_local)
+    kept_all = D.sum(kept)
+    in_all = total_images * bytes_in_per_image(wl)
+    algo_rank = run.in_bytes + 28.0 * kept + 4 * n_local       # this rank's kernel
+    gbs = algo_rank / (ms * 1e-3) / 1e9
+    res = {"workload": wl["desc"], "n_gpus": D.world, "global_batch": int(total_images), "batch_per_gpu": n_local,
+           "scaling": "strong" if wl["GB"] else "weak", "ms_per_step": ms, "images_per_s": total_images / (ms * 1e-3),
+           "kept_rows_per_image": kept_all / total_images,
+           "collective": ("fused all-gather of the kept rows (peer stores over NVLink) + fence, inside the timed step" if run.gather
+                          else "none (1 GPU)" if D.world == 1 else "none: large-image path, shards stay on their rank"),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                        "kernel": "decode_nms_large_kernel" if run.large else "decode_nms_kernel<MODE_FUSED>",
+                        "algorithmic_bytes_per_launch": algo_rank,
+                        "note": "per rank: this rank's algorithmic bytes / the step time (max over ranks)"}}
+    if run.gather:
+        res["nvlink_bytes_in_per_rank_per_step"] = 28.0 * (kept_all - kept)
+        res["nvlink_in_gbs"] = 28.0 * (kept_all - kept) / (ms * 1e-3) / 1e9
+    run.close()
+    del in_all
+    return res
+
+
+def run_b200(args, name, wl):
     from mobilenet_yolo_pytorch_b200 import _lib, ops
-    from mobilenet_yolo_pytorch_b200 import dist as b2dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N, C, conf = wl["N"], wl["C"], wl["conf"]
-    tables = anchor_tables(wl)
+    D = Dist()
+    world, rank, local, dev = D.world, D.rank, D.local, D.dev
+    peak, peak_src = load_peak()
+    N, C, conf = local_batch(wl, world, rank), wl["C"], wl["conf"]
     K = cells_per_image(wl)
+    tables = anchor_tables(wl)
+    lib = _lib.load()
 
-    # R rotating input sets so that successive steps never find their heads in the 126 MB L2
-    in_bytes = N * bytes_in_per_image(wl)
-    R = max(4, int(np.ceil(400e6 / in_bytes)))
-    sets = []
-    for r in range(R):
-        h0, h1 = make_heads(wl, N, seed=1000 * rank + r)
-        sets.append((h0.to(dev), h1.to(dev)))
-    out = torch.empty((N, K, 7), dtype=torch.float32, device=dev)
-    cnt = torch.empty((N,), dtype=torch.int32, device=dev)
+    # cpu_baseline: rank 0, and only while it has the host to itself (N = 1); at N > 1 the reference arm's line is the
+    # CPU figure (VERDICT r01: a CPU number taken while 8 ranks share the host means nothing)
+    cpu_base = None
+    if rank == 0 and world == 1:
+        import oracle
+        cpu_val, cpu_reps, cpu_med = cpu_port_rate(wl, N)
+        cpu_base = {"value": cpu_val, "unit": "images/s", "cores": oracle.max_threads(), "kind": "port",
+                    "sample": f"{cpu_reps} passes over the same {N}-image batch, median {cpu_med * 1e3:.1f} ms "
+                              "(oracle/yolo_oracle.c, OpenMP, all host threads); the unmodified reference Python is "
+                              "timed in extra.reference_python and by --impl reference"}
+    D.barrier()
 
-    def step(i):
-        h0, h1 = sets[i % R]
-        ops.decode_nms_padded(h0, h1, tables, C, conf, out=out, out_count=cnt)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    # kept rows per launch (for the algorithmic bytes), averaged over the rotating sets
-    kept = []
-    for r in range(R):
-        step(r)
-        kept.append(int(cnt.sum().item()))
-    kept_per_launch = float(np.mean(kept))
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    if sampler:
-        sampler.start()
+    # ---- headline: K steps from one C call
+    run = DecodeNmsRun(D, wl, N, args.steps)
+    kept_per_launch = run.kept_per_launch()
     l0 = _lib.launch_count()
-    ms = time_loop(step, args.steps)
+    ms_per_step = run.time(args.warmup)
     launches = _lib.launch_count() - l0
-    barrier()
-    # keep the same launch loop running ~0.4 s so the clock sampler sees the GPU under this load
-    if sampler:
-        t_end = time.perf_counter() + 0.4
-        i = 0
-        while time.perf_counter() < t_end:
-            step(i)
-            i += 1
-            if i % 256 == 0:
-                torch.cuda.synchronize()
+    warm_launches = launches - (launches * args.steps) // (args.steps + min(max(args.warmup, 3), args.steps))
+    launches_timed = launches - warm_launches
+    # clocks: the same launches for ~0.4 s under the NVML sampler (a 0.5 ms timed region is shorter than one NVML poll)
+    clocks = None
+    if rank == 0:
+        sampler = ClockSampler(local)
+    D.barrier()
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
+        run.run()
         torch.cuda.synchronize()
+        if world > 1:
+            break  # (ranks must issue the same number of gather steps: one more pass only)
+    D.barrier()
+    if rank == 0:
         clocks = sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = world * N / (ms_per_step * 1e-3)
+    total_images = D.sum(N)
+    value = total_images / (ms_per_step * 1e-3)
+    kept_all = D.sum(kept_per_launch)
+    gathered = run.gather
 
     # ---- e2e: host buffers through the C-ABI host call (H2D + kernel + D2H inside)
     hh0, hh1 = make_heads(wl, N, seed=7 + rank, pin=True)
@@ -383,337 +584,296 @@ def run_b200(args, wl):
     for _ in range(3):
         ops.decode_nms_host(hh0, hh1, tables, C, conf, device=local, out=ho, out_count=hc)
     e2e_steps = max(3, min(args.steps, 30))
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ops.decode_nms_host(hh0, hh1, tables, C, conf, device=local, out=ho, out_count=hc)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * N * e2e_steps / float(t.item())
+    e2e_val = total_images * e2e_steps / D.max(time.perf_counter() - t0)
+    d2h_bytes = int(lib.b200yolo_host_last_d2h_bytes()) if hasattr(lib, "b200yolo_host_last_d2h_bytes") else int(N * K * 28 + 4 * N)
+    del hh0, hh1, ho, hc
 
     extra = {}
     if not args.no_extra:
-        # sparse-head variant of the same workload (trained heads pass ~4% of cells)
-        if wl["shift"] == 0.0:
-            wls = dict(wl, shift=-2.6)
-            ssets = []
-            for r in range(R):
-                h0, h1 = make_heads(wls, N, seed=5000 + 1000 * rank + r)
-                ssets.append((h0.to(dev), h1.to(dev)))
-
-            def sstep(i):
-                h0, h1 = ssets[i % R]
-                ops.decode_nms_padded(h0, h1, tables, C, conf, out=out, out_count=cnt)
-
-            for i in range(5):
-                sstep(i)
-            skept = []
-            for r in range(R):
-                sstep(r)
-                skept.append(int(cnt.sum().item()))
-            barrier()
-            sms = time_loop(sstep, args.steps) / args.steps
-            sbytes = in_bytes + 28 * float(np.mean(skept)) + 4 * N
-            extra["sparse_heads"] = {"images_per_s_per_gpu": N / (sms * 1e-3), "ms_per_step": sms,
-                                     "kept_rows_per_image": float(np.mean(skept)) / N,
-                                     "algorithmic_gbs": sbytes / (sms * 1e-3) / 1e9}
-            # the same launches replayed from a CUDA graph (one graph = one pass over the R input sets): at ~12 us per
-            # step the Python launch loop is the limiter, the graph shows what the GPU does
+        # plain stream order (no programmatic dependent launch): comparable with ncu's gpu__time_duration
+        if not run.large:
+            lib.b200yolo_debug_set_flags(2)
             try:
-                gstream = torch.cuda.Stream(device=dev)
-                with torch.cuda.stream(gstream):
-                    for i in range(R):
-                        sstep(i)
-                gstream.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=gstream):
-                    for i in range(R):
-                        sstep(i)
-                reps = max(2, args.steps // R)
-                for _ in range(2):
-                    graph.replay()
-                barrier()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record()
-                for _ in range(reps):
-                    graph.replay()
-                g1.record()
-                g1.synchronize()
-                gms = g0.elapsed_time(g1) / (reps * R)
-                extra["sparse_heads"]["cuda_graph"] = {"ms_per_step": gms, "images_per_s_per_gpu": N / (gms * 1e-3),
-                                                       "algorithmic_gbs": sbytes / (gms * 1e-3) / 1e9}
-            except Exception as e:  # noqa: BLE001
-                extra["sparse_heads"]["cuda_graph"] = {"error": repr(e)}
-            del ssets
-        # the same loop without programmatic dependent launch (debug flag 2): every launch waits for the previous
-        # one to drain -- the serialized per-launch time, comparable with ncu's gpu__time_duration
-        _lib.load().b200yolo_debug_set_flags(2)
-        try:
-            for i in range(5):
-                step(i)
-            barrier()
-            ser_ms = time_loop(step, args.steps) / args.steps
-        finally:
-            _lib.load().b200yolo_debug_set_flags(0)
-        extra["serialized_launches"] = {"ms_per_step": ser_ms, "images_per_s_per_gpu": N / (ser_ms * 1e-3),
-                                        "note": "plain stream order (no programmatic dependent launch)"}
-        # the same steps issued round-robin on two streams (separate output buffers): consecutive launches
-        # overlap, so one launch's decode (memory phase) runs under the other's NMS (issue-bound phase)
-        s2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        o2 = [torch.empty_like(out) for _ in range(2)]
-        c2 = [torch.empty_like(cnt) for _ in range(2)]
+                ser_ms = run.time(3)
+            finally:
+                lib.b200yolo_debug_set_flags(0)
+            extra["serialized_launches"] = {"ms_per_step": ser_ms, "images_per_s": total_images / (ser_ms * 1e-3),
+                                            "note": "the same steps in plain stream order (every launch waits for the previous one to drain)"}
+        if gathered:
+            # what the step costs without the exchange, and with NCCL's all-gather of the fixed-stride block instead
+            from mobilenet_yolo_pytorch_b200 import dist as b2dist
+            solo = DecodeNmsRun(D, wl, N, args.steps, gather=False)
+            solo_ms = solo.time(args.warmup)
+            extra["without_gather"] = {"ms_per_step": solo_ms, "images_per_s": total_images / (solo_ms * 1e-3),
+                                       "note": "kernels only, every shard stays on its rank (round 1's headline protocol)"}
 
-        def pstep(i):
-            h0, h1 = sets[i % R]
-            with torch.cuda.stream(s2[i & 1]):
-                ops.decode_nms_padded(h0, h1, tables, C, conf, out=o2[i & 1], out_count=c2[i & 1])
-
-        for i in range(6):
-            pstep(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            pstep(i)
-        torch.cuda.synchronize()
-        pms = (time.perf_counter() - t0) * 1e3 / args.steps
-        extra["two_streams"] = {"images_per_s_per_gpu": N / (pms * 1e-3), "ms_per_step": pms,
-                                "note": "throughput of overlapped launches (host wall clock); the headline value is single-stream"}
-        # YOLOLoss target assignment + loss sums, BASELINE config 4 (both heads, 100 GT boxes per image)
-        if rank == 0:
-            try:
-                lN = 512
-                lres = time_loss(dev, lN, 100, steps=max(20, args.steps // 2))
-                lres["hbm_frac"] = lres["algorithmic_gbs"] / float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) \
-                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else lres["algorithmic_gbs"] / 6650.0
-                lres["bound"] = "issue (92.9 M box pairs x ~14 instructions), not HBM"
-                lres["cpu_port_images_per_s"] = cpu_loss_rate(32, 100)
-                extra["loss_cfg4"] = lres
-            except Exception as e:  # noqa: BLE001
-                extra["loss_cfg4"] = {"error": repr(e)}
-        # all-gather of the fixed-stride detections (the only collective the path may need)
-        if world > 1:
             def gstep(i):
-                step(i)
-                b2dist.all_gather_detections(out, cnt)
+                h0, h1 = solo.sets[i % solo.R]
+                ops.decode_nms_padded(h0, h1, tables, C, conf, out=solo.out, out_count=solo.cnt)
+                b2dist.all_gather_detections(solo.out, solo.cnt)
             for i in range(3):
                 gstep(i)
-            barrier()
-            gms = time_loop(gstep, max(10, args.steps // 4)) / max(10, args.steps // 4)
-            tg = torch.tensor([gms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            extra["with_allgather"] = {"images_per_s": world * N / (float(tg.item()) * 1e-3),
-                                       "ms_per_step": float(tg.item()),
-                                       "bytes_gathered_per_rank": int(world * N * (K + 1) * 28)}
-
-            # compact form: kept rows only (one host read of the per-rank totals to size the buffer)
-            def cstep(i):
-                step(i)
-                b2dist.all_gather_detections_compact(out, cnt)
-            for i in range(3):
-                cstep(i)
-            barrier()
-            cms = time_loop(cstep, max(10, args.steps // 4)) / max(10, args.steps // 4)
-            tc = torch.tensor([cms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-            extra["with_allgather_compact"] = {"images_per_s": world * N / (float(tc.item()) * 1e-3),
-                                               "ms_per_step": float(tc.item()),
-                                               "bytes_gathered_per_rank": int(world * kept_per_launch * 28)}
-
-            # the same gather fused into the kernel: the output phase stores the kept rows into every rank's buffer over
-            # NVLink peer mappings (b200yolo_decode_nms_gather); the fence is the cross-rank barrier a consumer needs
+            D.barrier()
+            gn = max(10, args.steps // 4)
+            gms = D.max(time_loop(gstep, gn) / gn)
+            extra["with_nccl_allgather"] = {"ms_per_step": gms, "images_per_s": total_images / (gms * 1e-3),
+                                            "bytes_gathered_per_rank": int(world * N * (K + 1) * 28),
+                                            "note": "kernel, then ncclAllGather of the fixed-stride (N, K+1, 7) block"}
+            solo.close()
+        run.close()
+        # sparse-head variant of the same workload (trained heads pass ~4% of cells), same protocol
+        if wl["shift"] == 0.0 and name == "cfg2":
+            wls = dict(WORKLOADS["cfg2_sparse"])
+            srun = DecodeNmsRun(D, wls, N, args.steps, seed0=5000)
+            skept = srun.kept_per_launch()
+            sms = srun.time(args.warmup)
+            sbytes = srun.in_bytes + 28.0 * skept + 4 * N
+            sg = sbytes / (sms * 1e-3) / 1e9
+            extra["sparse_heads"] = {"ms_per_step": sms, "images_per_s": total_images / (sms * 1e-3),
+                                     "kept_rows_per_image": D.sum(skept) / total_images,
+                                     "collective_in_step": srun.gather,
+                                     "roofline": {"bound": "hbm", "achieved": sg, "peak": peak, "unit": "GB/s", "frac": sg / peak,
+                                                  "algorithmic_bytes_per_launch": sbytes}}
+            srun.close()
+        # the other BASELINE configurations at this world size, each with its own roofline block
+        if name == "cfg2":
+            osteps = max(10, min(args.steps, 40))
+            for other in ("cfg3", "cfg5", "cfg5_832"):
+                try:
+                    r = measure_workload(D, other, osteps if other != "cfg5_832" else max(5, osteps // 4), 3, peak)
+                    if rank == 0:
+                        extra[other] = r
+                except Exception as e:  # noqa: BLE001
+                    if rank == 0:
+                        extra[other] = {"error": repr(e)}
+                torch.cuda.empty_cache()
             try:
-                pg = b2dist.PeerGather(N, K)
-
-                def pstep2(i):
-                    h0, h1 = sets[i % R]
-                    pg.decode_nms(h0, h1, tables, C, conf)
-                    pg.fence(timeout_s=1.0)
-                for i in range(3):
-                    pstep2(i)
-                barrier()
-                pg.check()   # a fence that timed out in the warm-up ends this measurement here (reported as an error)
-                pgms = time_loop(pstep2, max(10, args.steps // 4)) / max(10, args.steps // 4)
-                tp = torch.tensor([pgms], dtype=torch.float64, device=dev)
-                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-                same = bool(torch.equal(pg.counts[rank * N:(rank + 1) * N], cnt))
-                pg.check()
-
-                def pstep3(i):
-                    h0, h1 = sets[i % R]
-                    pg.decode_nms(h0, h1, tables, C, conf)
-                    pg.fence(collective=True)
-                for i in range(3):
-                    pstep3(i)
-                barrier()
-                pcms = time_loop(pstep3, max(10, args.steps // 4)) / max(10, args.steps // 4)
-                tpc = torch.tensor([pcms], dtype=torch.float64, device=dev)
-                dist.all_reduce(tpc, op=dist.ReduceOp.MAX)
-                extra["with_peer_gather"] = {"images_per_s": world * N / (float(tp.item()) * 1e-3),
-                                             "ms_per_step": float(tp.item()),
-                                             "ms_per_step_with_nccl_fence": float(tpc.item()),
-                                             "bytes_stored_per_rank": int(world * kept_per_launch * 28),
-                                             "counts_equal_plain_launch": same,
-                                             "note": "decode + NMS + all-gather in ONE kernel (peer stores over NVLink) + the fence (arrival "
-                                                     "flags in peer memory, two tiny kernels), per step"}
-                pg.close()
+                r = measure_loss(D, max(10, min(args.steps, 50)), 3, peak)
+                if rank == 0:
+                    extra["cfg4_loss"] = r
             except Exception as e:  # noqa: BLE001
-                extra["with_peer_gather"] = {"error": repr(e)}
+                if rank == 0:
+                    extra["cfg4_loss"] = {"error": repr(e)}
+        # the reference's own code on this box (rank 0, one GPU: the host and GPU 0 are otherwise idle now)
+        if rank == 0 and world == 1 and name in ("cfg2", "cfg2_sparse") and reference_available():
+            extra["reference_python"] = reference_legs(dev, wl, name, tables)
+    else:
+        run.close()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        algo_bytes = in_bytes + 28.0 * kept_per_launch + 4 * N
+        algo_bytes = run.in_bytes + 28.0 * kept_per_launch + 4 * N
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "decode_nms_traffic.json")))
-            traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+            traffic = prof.get(name, {}).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
-        cpu_val, cpu_reps, cpu_med = cpu_decode_nms_rate(wl)
-        import oracle
+        cfg = workload_config(name, wl, world)
         line = {
             "metric": "decode+NMS images/sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": N, "global_batch": world * N,
-                       "cells_per_image": K, "kept_rows_per_image": kept_per_launch / N,
-                       "l2": f"{R} rotating input sets ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2, so every step reads its heads from HBM",
-                       "launch": ("one kernel per step on one stream; consecutive launches overlap through programmatic dependent "
-                                  "launch (a launch starts on free SM slots while the previous one finishes, and waits for it before "
-                                  "writing); extra.serialized_launches is the same loop in plain stream order")
-                       if K <= _lib.load().b200yolo_max_cells(local) else "one kernel per step on one stream, plain stream order",
-                       "parallelism": f"dp{world} by image, no data-path collective"},
+            "higher_is_better": True, "scaling": "strong" if wl["GB"] else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "run": {"kept_rows_per_image": kept_all / total_images,
+                    "launch": ("the K steps are issued by ONE C call (b200yolo_decode_nms_batches / _gather_steps); consecutive launches "
+                               "overlap through programmatic dependent launch (a launch starts on free SM slots while the previous one "
+                               "finishes and waits for it before writing); extra.serialized_launches is plain stream order")
+                    if not run.large else "one kernel per step on one stream, plain stream order",
+                    "parallelism": (f"dp{world} by image; every step = kernel + fused all-gather of the kept rows (peer stores over NVLink) + fence"
+                                    if gathered else f"dp{world} by image, no collective (1 GPU)" if world == 1
+                                    else f"dp{world} by image, no data-path collective (large-image path)"),
+                    "limiter": (f"NVLink ingress: every rank receives {28.0 * (kept_all - kept_per_launch) / 1e6:.1f} MB of kept rows per step "
+                                f"({28.0 * (kept_all - kept_per_launch) / (ms_per_step * 1e-3) / 1e9:.0f} GB/s achieved of 900 GB/s nominal per direction, "
+                                "770 GB/s measured peer copy); the kernel itself is issue-bound" if gathered
+                                else "issue-bound after the heads are in (see DESIGN.md 4.1)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": "decode_nms_kernel<MODE_FUSED>" if K <= _lib.load().b200yolo_max_cells(local)
+                         "kernel": "decode_nms_kernel<MODE_FUSED>" if not run.large
                          else "decode_nms_large_kernel (more cells per image than one CTA stages in shared memory)",
-                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src + ", of measured"},
-            "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": oracle.max_threads(), "kind": "port",
-                             "sample": f"{cpu_reps} passes over the same {N}-image batch, median {cpu_med * 1e3:.1f} ms "
-                                       "(oracle/yolo_oracle.c, OpenMP, all host threads)"},
-            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(in_bytes),
-                    "d2h_bytes_per_step": int(N * K * 28 + 4 * N), "steps": e2e_steps,
-                    "api": "b200yolo_decode_nms_host (pinned host heads -> host detections, 4 chunks on 3 streams: H2D, kernel and D2H overlap)",
+                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
+            "cpu_baseline": cpu_base if cpu_base is not None else {
+                "value": None, "unit": "images/s", "cores": 0, "kind": "port",
+                "sample": "not taken at N > 1 (the ranks share the host cores); see the N = 1 line and the reference arm"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(run.in_bytes),
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "api": "b200yolo_decode_nms_host (pinned host heads -> host detections, chunks on 3 streams: H2D, kernel and D2H overlap)",
                     "timer": "host wall clock around the synchronous calls, max over ranks"},
-            "gpu_launches": int(launches) * world,
+            "gpu_launches": int(launches_timed) * world,
             "clocks": clocks,
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
 
 
-def run_loss(args):
-    """--workload cfg4_loss: BASELINE config 4 -- YOLOLoss target assignment + loss (both VOC-352 heads), global batch
-    512 with 100 synthetic GT boxes per image, sharded by image over the ranks (strong scaling); a step is
-    YOLOLoss.forward(input, targets) x2 through the module API, i.e. it includes packing the host targets, their H2D
-    copy, the all-reduce of the 16 partial sums (N > 1) and the D2H read of the sums."""
-    import torch.distributed as dist
+def reference_legs(dev, wl, name, tables):
+    """extra.reference_python: the UNMODIFIED reference (oracle/_ref) on this box -- its CPU path, its CUDA path
+    (torchvision's sm_100 nms kernel per (image, class), utils/box.py:16-29) and NMS alone on identical candidates."""
+    from mobilenet_yolo_pytorch_b200 import ops
+    out = {}
+    n_ref = 64
+    out["cpu"] = run_ref_bench("cpu", "decode_nms", name, n_ref, 5)
+    out["cuda"] = run_ref_bench("cuda", "decode_nms", name, n_ref, 5)
+    out["cuda_nms_only"] = run_ref_bench("cuda", "nms_only", name, n_ref, 5)
+    # b200yolo_nms alone on the candidates the reference's decode produces for the same heads (same seeds)
+    try:
+        C, conf = wl["C"], wl["conf"]
+        h0, h1 = [h.to(dev) for h in make_heads(wl, n_ref, seed=0)]
+        r0, c0 = ops.decode_head_padded(h0, tables[0], C, conf)
+        r1, c1 = ops.decode_head_padded(h1, tables[1], C, conf)
+        for _ in range(3):
+            o, oc = ops.nms_padded(r0, c0, r1, c1, C)
+        torch.cuda.synchronize()
+        reps = 50
+        ms = time_loop(lambda i: ops.nms_padded(r0, c0, r1, c1, C), reps) / reps
+        out["b200yolo_nms_only"] = {"n": n_ref, "ms": ms, "images_per_s": n_ref / (ms * 1e-3),
+                                    "kept_rows_per_image": float(oc.sum().item()) / n_ref,
+                                    "note": "b200yolo_nms (one launch) on the decoded candidates of the same heads"}
+        tv = out["cuda_nms_only"]
+        if "error" not in tv:
+            out["nms_only_speedup_vs_reference_cuda"] = (n_ref / (ms * 1e-3)) / tv["images_per_s"]
+            if "torchvision_batched_nms" in tv:
+                out["nms_only_speedup_vs_torchvision_batched_nms"] = (n_ref / (ms * 1e-3)) / tv["torchvision_batched_nms"]["images_per_s"]
+    except Exception as e:  # noqa: BLE001
+        out["b200yolo_nms_only"] = {"error": repr(e)}
+    # BASELINE config 1: the real model, batch 1 (inference.py:120-124 prints this latency)
+    try:
+        out["config1_batch1"] = config1_latency()
+    except Exception as e:  # noqa: BLE001
+        out["config1_batch1"] = {"error": repr(e)}
+    return out
+
+
+def config1_latency():
+    """MobileNetV2-YOLO 352x352, batch 1, random-init: model(x) latency of the reference on the CPU and on the GPU
+    (subprocesses, quirk Q4) and of the same model with this package patched in (in this process)."""
+    res = {}
+    env_cpu = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    env_cpu.pop("OMP_NUM_THREADS", None)
+    for label, env in (("reference_cpu", env_cpu), ("reference_cuda", dict(os.environ))):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_config1.py"), "--reps", "10"], env=env,
+                               capture_output=True, text=True, timeout=300)
+            lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+            res[label] = json.loads(lines[-1]) if lines else {"error": r.stderr[-300:]}
+        except Exception as e:  # noqa: BLE001
+            res[label] = {"error": repr(e)}
     import mobilenet_yolo_pytorch_b200 as b200
-    from mobilenet_yolo_pytorch_b200 import _lib
+    from oracle import ref_config1
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    def patch(ns, m):
+        b200.patch_reference(models_yolo_loss=ns.yolo_loss, utils_box=ns.box, mbv2_yolo=m, fuse_inference=True)
+    r = ref_config1.run("cuda", reps=20, patch=patch)
+    b200.YOLOLoss.lazy_eval = False
+    res["b200_patched_cuda"] = {"latency_ms": r["latency_ms"], "detections": int(r["dets"].shape[0]),
+                                "note": "the reference's models/mbv2_yolo.py with YOLOLoss / nms replaced by this package "
+                                        "(patch_reference(..., fuse_inference=True)): backbone + heads in cuDNN, post-processing in one launch"}
+    return res
+
+
+def measure_loss(D, steps, warmup, peak):
+    """BASELINE config 4: YOLOLoss.forward(input, targets) x2 (VOC 352 heads), global batch 512 with 100 synthetic GT
+    boxes per image, sharded by image (strong scaling); N > 1: the all-reduce of the 16 partial sums per head is inside
+    the step.  Module API: host target lists in, loss tensor out."""
+    import mobilenet_yolo_pytorch_b200 as b200
     GB, G = 512, 100
     wl = WORKLOADS["cfg2"]
     C = wl["C"]
-    if args.impl == "reference":
-        if rank == 0:
-            n = 32
-            val = cpu_loss_rate(n, G)
-            print(json.dumps({"impl": "reference", "metric": "YOLOLoss target assignment images/sec", "value": val,
-                              "unit": "images/s", "n_gpus": args.gpus, "steps": 3, "warmup": 0, "ms_per_step": 1e3 * n / val,
-                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                              "data": "synthetic", "config": {"workload": "YOLOLoss target assignment, VOC 352 heads, 100 GT boxes per image", "batch": n},
-                              "cpu_baseline": {"value": val, "unit": "images/s", "cores": host_threads(), "kind": "port",
-                                               "sample": f"best of 3 passes over {n} images, both heads (oracle/yolo_oracle.c, OpenMP)"},
-                              "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                              "gpu_launches": 0}), flush=True)
-        return
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-    lo, hi = b200.dist.shard_bounds(GB, world, rank)
+    group = D.dist.group.WORLD if D.world > 1 else None
+    lo, hi = b200.dist.shard_bounds(GB, D.world, D.rank)
     N = hi - lo
     targets = [torch.from_numpy(t) for t in make_targets(GB, G, C, 1)[lo:hi]]
     losses = [b200.YOLOLoss(VOC_ANCHORS, MASK[k], C, [352, 352], VOC_IGNORE[k], VOC_IOU_THRESH, iou_weighting=VOC_IOU_WEIGHTING,
                             process_group=group) for k in range(2)]
     in_bytes = N * bytes_in_per_image(wl)
     R = max(3, int(np.ceil(300e6 / max(in_bytes, 1))))
-    sets = [tuple(h.to(dev) for h in make_heads(wl, N, seed=100 + 17 * rank + r)) for r in range(R)]
+    sets = [tuple(h.to(D.dev) for h in make_heads(wl, N, seed=100 + 17 * D.rank + r)) for r in range(R)]
 
     def step(i):
         h0, h1 = sets[i % R]
         tl = list(targets)  # a new list object every step, like a data loader's: packed once, shared by both heads
         return losses[0](h0, tl)[0] + losses[1](h1, tl)[0]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         step(i)
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    if sampler:
-        sampler.start()
-    l0 = _lib.launch_count()
-    ms = time_loop(step, args.steps)
-    launches = _lib.launch_count() - l0
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    # kernel-only rate (device-resident packed targets, no host sync), for the roofline
-    kres = time_loss(dev, N, G, steps=max(20, args.steps // 2)) if rank == 0 else None
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        value = GB / (ms_per_step * 1e-3)
-        print(json.dumps({
-            "metric": "YOLOLoss target assignment images/sec", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "YOLOLoss.forward(input, targets) x2 (VOC 352 heads), global batch 512, 100 synthetic GT boxes per image",
-                       "name": "cfg4_loss", "batch_per_gpu": N, "global_batch": GB,
-                       "l2": f"{R} rotating head sets ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2",
-                       "parallelism": f"dp{world} by image; one all-reduce(SUM) of 16 doubles per head" if world > 1 else "dp1"},
+    D.barrier()
+    ms = D.max(time_loop(step, steps) / steps)
+    D.barrier()
+    kres = time_loss(D.dev, N, G, steps=max(20, steps)) if D.rank == 0 else None
+    D.barrier()
+    if D.rank != 0:
+        return None
+    return {"workload": "YOLOLoss.forward(input, targets) x2 (VOC 352 heads), global batch 512, 100 synthetic GT boxes per image",
+            "n_gpus": D.world, "global_batch": GB, "batch_per_gpu": N, "scaling": "strong",
+            "module_api": {"ms_per_step": ms, "images_per_s": GB / (ms * 1e-3),
+                           "note": "host target lists in, loss tensor + python stats out"
+                                   + ("; all-reduce(SUM) of 16 doubles per head inside the step" if D.world > 1 else "")},
+            "kernel_only": kres,
             "roofline": {"bound": "hbm", "achieved": kres["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kres["algorithmic_gbs"] / peak, "traffic": None, "kernel": "target_loss_kernel (both heads, kernel-only loop)",
+                         "frac": kres["algorithmic_gbs"] / peak, "traffic": None,
+                         "kernel": "target_loss_kernel (both heads, device-resident packed targets)",
                          "algorithmic_bytes_per_launch": kres["algorithmic_bytes_per_step"],
-                         "note": "the path is bound by the 92.9 M pred-vs-GT box pairs (~14 instructions each), not by HBM"},
-            "cpu_baseline": {"value": cpu_loss_rate(32, G), "unit": "images/s", "cores": host_threads(), "kind": "port",
-                             "sample": "best of 3 passes over 32 images, both heads (oracle/yolo_oracle.c, OpenMP)"},
+                         "note": "bound by the pred-vs-GT box pairs, not by HBM"}}
+
+
+def run_loss(args):
+    """--workload cfg4_loss as the headline (same measurement as extra.cfg4_loss of the default run)."""
+    rank = int(os.environ.get("RANK", "0"))
+    GB, G = 512, 100
+    cfg = {"workload": "YOLOLoss.forward(input, targets) x2 (VOC 352 heads), global batch 512, 100 synthetic GT boxes per image",
+           "name": "cfg4_loss", "batch_per_gpu": GB // max(args.gpus, 1), "global_batch": GB, "cells_per_image": 1815, "l2": L2_NOTE}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if reference_available():
+            r = run_ref_bench("cpu", "loss", "cfg2", 8, max(3, min(args.steps, 10)), budget=120.0, timeout=900)
+        else:
+            r = {"error": "no snapshot"}
+        if "error" in r:
+            val, kind, sample, cores = cpu_loss_port_rate(32, G), "port", "median of 5 passes over 32 images, both heads (oracle/yolo_oracle.c, OpenMP)", host_threads()
+            ms = 1e3 * 32 / val
+        else:
+            val, kind, cores = r["images_per_s"], "reference", r["threads"]
+            sample = f"{r['reps']} passes over 8 images, both heads: the unmodified reference's YOLOLoss.forward(input, targets), median pass"
+            ms = 1e3 * r["median_s"]
+        print(json.dumps({"impl": "reference", "metric": "YOLOLoss target assignment images/sec", "value": val,
+                          "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    from mobilenet_yolo_pytorch_b200 import _lib
+    D = Dist()
+    peak, _ = load_peak()
+    sampler = ClockSampler(D.local) if D.rank == 0 else None
+    l0 = _lib.launch_count()
+    r = measure_loss(D, args.steps, args.warmup, peak)
+    launches = _lib.launch_count() - l0
+    if D.rank == 0:
+        clocks = sampler.stop()
+        value = r["module_api"]["images_per_s"]
+        N = r["batch_per_gpu"]
+        print(json.dumps({
+            "metric": "YOLOLoss target assignment images/sec", "value": value, "unit": "images/s", "n_gpus": D.world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["module_api"]["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "roofline": r["roofline"],
+            "cpu_baseline": {"value": cpu_loss_port_rate(32, G) if D.world == 1 else None, "unit": "images/s", "cores": host_threads(), "kind": "port",
+                             "sample": "median of 5 passes over 32 images, both heads (oracle/yolo_oracle.c, OpenMP)"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": int(2 * (N * G * 20 + 4 * (N + 1))),
                     "d2h_bytes_per_step": 2 * 17 * 8, "api": "YOLOLoss.forward(input, targets): host target lists in, python loss tuple out"},
-            "gpu_launches": int(launches) * world, "clocks": clocks,
-            "extra": {"kernel_only": kres},
+            "gpu_launches": int(launches) * D.world, "clocks": clocks,
+            "extra": {"kernel_only": r["kernel_only"]},
         }), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():
@@ -723,9 +883,9 @@ def main():
         return
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, args.workload, wl)
     else:
-        run_b200(args, wl)
+        run_b200(args, args.workload, wl)
 
 
 if __name__ == "__main__":

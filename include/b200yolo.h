@@ -193,6 +193,36 @@ int b200yolo_peer_signal(int *const *peer_flags, int R, int rank, int value, voi
 int b200yolo_peer_wait(const int *own_flags, int R, int value, double timeout_s, int *timed_out, void *stream);
 int b200yolo_peer_close(void *dev_ptr);
 int b200yolo_peer_free(void *dev_ptr);
+/*
+ * The two fence kernels above as ONE launch that does not serialise the stream: started with the programmatic
+ * attribute right after a b200yolo_decode_nms_gather launch, it waits for that launch to complete, raises this
+ * rank's flag in every rank's array (`value`: a step number that only grows), then waits for all R flags of
+ * own_flags.  The decode launch that FOLLOWS it in the stream may start early and stream its heads, but blocks before
+ * its first store until this fence has completed, i.e. until every rank has arrived.
+ */
+int b200yolo_peer_fence(int *const *peer_flags, const int *own_flags, int R, int rank, int value, double timeout_s,
+                        int *timed_out, void *stream);
+
+/*
+ * A sequence of data-parallel steps in one call: step k = b200yolo_decode_nms_gather of batches[k] (head0 / head1;
+ * the other members are ignored) into the gather buffers of parity (first_step + k) & 1, followed by
+ * b200yolo_peer_fence with value first_step + k + 1.  TWO buffers per rank make the fused gather safe without a
+ * separate release signal: a rank stores into parity p at step s only after its own fence of step s - 1 has
+ * completed, i.e. after every rank has ARRIVED at step s - 1, and a rank's arrival at s - 1 is stream-ordered after
+ * whatever it ran on the buffers of step s - 2 (same parity).  Consumers of step s therefore read the buffers of
+ * parity s & 1 in the stream between this call and the next one, with ordinary kernel launches.
+ */
+typedef struct b200yolo_gather {
+    int R, rank;
+    float *peer_out[2][8];  /* [parity][r]: rank r's buffer dev [R*N][K][7] (own: local, others: b200yolo_peer_open) */
+    int *peer_count[2][8];  /* [parity][r]: rank r's counts dev int32 [R*N] */
+    int *peer_flags[8];     /* [r]: rank r's arrival flags dev int32 [8] */
+    int *timed_out;         /* own dev int32[1], zero it once */
+    double timeout_s;       /* per fence, <= 60; <= 0: 5 s */
+} b200yolo_gather;
+int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_batch *batches, int n_steps, int first_step,
+                                     int N, int A, int C, int H0, int W0, int H1, int W1, const float *anchor_wh,
+                                     float conf_thr, double iou_thr, void *stream);
 
 /*
  * Same computation from HOST buffers (the reference-facing call bench.py times

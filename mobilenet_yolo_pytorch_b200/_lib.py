@@ -48,6 +48,9 @@ SIGNATURES = {
     "b200yolo_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "b200yolo_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200yolo_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "b200yolo_peer_fence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "b200yolo_decode_nms_gather_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_int, C.c_int, C.c_int, c_f32p, C.c_float, C.c_double, C.c_void_p]),
     "b200yolo_peer_close": (C.c_int, [C.c_void_p]),
     "b200yolo_peer_free": (C.c_int, [C.c_void_p]),
     "b200yolo_decode_nms_host": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -82,6 +85,12 @@ class Batch(C.Structure):
     """struct b200yolo_batch (include/b200yolo.h)."""
     _fields_ = [("head0", C.c_void_p), ("head1", C.c_void_p), ("out", C.c_void_p), ("out_count", C.c_void_p),
                 ("out_idx", C.c_void_p)]
+
+
+class Gather(C.Structure):
+    """struct b200yolo_gather (include/b200yolo.h)."""
+    _fields_ = [("R", C.c_int), ("rank", C.c_int), ("peer_out", (C.c_void_p * 8) * 2), ("peer_count", (C.c_void_p * 8) * 2),
+                ("peer_flags", C.c_void_p * 8), ("timed_out", C.c_void_p), ("timeout_s", C.c_double)]
 
 
 class B200YoloError(RuntimeError):

@@ -271,6 +271,51 @@ __global__ void peer_wait_kernel(const int *own_flags, int R, int value, long lo
     }
 }
 
+// Signal + wait in ONE kernel, launched with the programmatic attribute right after the decode launch whose rows it
+// announces: it lets the NEXT decode launch start early (trigger), waits for its predecessor -- the decode launch --
+// to complete and flush (griddepcontrol.wait), raises this rank's arrival flag in every rank's buffer, then waits
+// for all flags of its own.  The next decode launch blocks at ITS griddepcontrol.wait (before its first store) until
+// this kernel has completed, i.e. until every rank has arrived: that is the back-pressure of the double-buffered
+// gather (dist.PeerGather).
+__global__ void peer_fence_kernel(PeerFlagPtrs flags, const int *own_flags, int R, int rank, int value, long long max_cycles,
+                                  int *timed_out) {
+    pdl_trigger();
+    pdl_wait();
+    const int r = threadIdx.x;
+    if (r < R) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(flags.p[r] + rank) = value;
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile int *>(own_flags + r) < value) {
+            if (clock64() - t0 > max_cycles) {   // a peer died: report instead of hanging the GPU
+                *timed_out = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+}
+
+int launch_peer_fence(const PeerFlagPtrs &f, const int *own_flags, int R, int rank, int value, double timeout_s, int *timed_out,
+                      cudaStream_t st) {
+    if (!(timeout_s > 0.0) || timeout_s > 60.0) timeout_s = 5.0;
+    const long long max_cycles = (long long)(timeout_s * 2.0e9);   // SM clock <= 2 GHz: at least timeout_s seconds
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_flags.load() & 2) ? 0 : 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, peer_fence_kernel, f, own_flags, R, rank, value, max_cycles, timed_out));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 // large_nms.cuh: one CTA per image, sort keys in shared memory.  SRC 0: heads (records in p.rec), 1: caller rows
 template <int SRC>
 int launch_large(LargeParams &p, cudaStream_t st, const char *who) {
@@ -481,6 +526,62 @@ int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, in
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
 }
 
+int b200yolo_peer_fence(int *const *peer_flags, const int *own_flags, int R, int rank, int value, double timeout_s,
+                        int *timed_out, void *stream) {
+    if (!peer_flags || !own_flags || !timed_out || R < 1 || R > kMaxPeers || rank < 0 || rank >= R)
+        return fail(B200YOLO_EINVAL, "peer_fence: bad argument");
+    PeerFlagPtrs f;
+    memset(&f, 0, sizeof(f));
+    for (int r = 0; r < R; ++r) {
+        if (!peer_flags[r]) return fail(B200YOLO_EINVAL, "peer_fence: null flag array of rank %d", r);
+        f.p[r] = peer_flags[r];
+    }
+    return launch_peer_fence(f, own_flags, R, rank, value, timeout_s, timed_out, (cudaStream_t)stream);
+}
+
+int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_batch *batches, int n_steps, int first_step,
+                                     int N, int A, int C, int H0, int W0, int H1, int W1, const float *anchor_wh,
+                                     float conf_thr, double iou_thr, void *stream) {
+    if (!g || n_steps < 0 || (n_steps > 0 && !batches) || !anchor_wh || first_step < 0)
+        return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: bad argument");
+    if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
+        return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: bad shape");
+    const int R = g->R, rank = g->rank;
+    if (R < 1 || R > kMaxPeers || rank < 0 || rank >= R || !g->timed_out)
+        return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: %d ranks (1..%d), rank %d", R, kMaxPeers, rank);
+    if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: NaN threshold");
+    for (int par = 0; par < 2; ++par)
+        for (int r = 0; r < R; ++r)
+            if (!g->peer_out[par][r] || !g->peer_count[par][r] || !g->peer_flags[r])
+                return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: null buffer of rank %d", r);
+    const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
+    if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms_gather_steps: more than 65535 cells per image");
+    PeerFlagPtrs f;
+    memset(&f, 0, sizeof(f));
+    for (int r = 0; r < R; ++r) f.p[r] = g->peer_flags[r];
+    DNParams p;
+    memset(&p, 0, sizeof(p));
+    p.nheads = 2;
+    p.N = N; p.A = A; p.C = C; p.attrs = 5 + C;
+    p.K = (int)cells;
+    p.conf_thr = conf_thr;
+    p.iou = make_thr(iou_thr);
+    p.gR = R;
+    p.gslot = rank * N;
+    for (int k = 0; k < n_steps; ++k) {
+        if (!batches[k].head0 || !batches[k].head1) return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: null head in step %d", k);
+        const int step = first_step + k, par = step & 1;
+        fill_head(p.head[0], batches[k].head0, A, H0, W0, anchor_wh);
+        fill_head(p.head[1], batches[k].head1, A, H1, W1, anchor_wh + 2 * A);
+        // every rank starts with its own buffer and walks the ring from there (the ranks hit different peers)
+        for (int i = 0; i < R; ++i) { p.gout[i] = g->peer_out[par][(rank + i) % R]; p.gcount[i] = g->peer_count[par][(rank + i) % R]; }
+        p.wait_inputs = (k == 0) ? 1 : 0;   // k > 0: the predecessor is our own fence kernel
+        if (int rc = launch_dn<MODE_FUSED>(p, (cudaStream_t)stream)) return rc;
+        if (int rc = launch_peer_fence(f, g->peer_flags[rank], R, rank, step + 1, g->timeout_s, g->timed_out, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
+}
+
 /* Peer-visible device memory for the fused all-gather: cudaMalloc + an IPC handle another process of the node opens. */
 int b200yolo_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64) {
     if (!dev_ptr || !handle64 || bytes == 0) return fail(B200YOLO_EINVAL, "peer_alloc: bad argument");
@@ -612,6 +713,7 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
         return fail(B200YOLO_EINVAL, "target_loss: workspace too small (%zu < %zu)", workspace_bytes,
                     b200yolo_target_loss_workspace_bytes(N));
     p.partial = (double *)workspace;
+    p.wait_inputs = g_inputs_ready.load() ? 0 : 1;
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;

@@ -130,7 +130,7 @@ struct DNParams {
 // fp16 column table of one tile (32 sorted positions of one class): entry k packs columns k (low half) and k + 16
 // (high half), so one HMNMX2 / HADD2 / HFMA2 works on two columns.  Written in P4, read in P5.
 struct H16Tile {
-    uint4 xy[16];      // .x = X1 pair, .y = Y1 pair, .z = X2 pair, .w = Y2 pair (half2 each); X = x/4, Y = 64*y
+    uint4 xy[16];      // .x = X1 pair, .y = Y1 pair, .z = X2 pair, .w = Y2 pair (half2 each); X = x/16, Y = 256*y
     uint32_t ta[16];   // TA pair: a lower bound of 16 * t * area, or -inf ("always maybe": degenerate box)
 };
 static_assert(sizeof(H16Tile) == 320, "H16Tile layout");
@@ -152,7 +152,7 @@ __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v
 // per-class int arrays, each (C+1) long
 enum { CA_CNT = 0, CA_START, CA_KTILE, CA_NUM };
 // misc ints
-enum { M_NTASK = 0, M_CTR, M_LEVEL, M_NLEVELS, M_TOTAL, M_KV, M_NUM = 16 };
+enum { M_NTASK = 0, M_CTR, M_NLEVELS, M_TOTAL, M_KV, M_NUM = 16 };
 
 // score buckets per class: C*B counters, at most 1536 (6 KB)
 __host__ __device__ inline int pick_buckets(int C) {
@@ -169,7 +169,6 @@ constexpr int kRankItems = 8;                     // P4: sorted positions a thre
 //   pairs            scid u16[32*NT] | H16Tile[NT]
 //   output           scid ........... | per-warp row scratch
 //   (MODE_DECODE)    clsidx u32[Kp] | outsrc u16[Kp]
-// `extra` bytes (what the shared-memory tier leaves) go to the pair-task table.
 __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int threads, uint32_t extra) {
     SmemLayout L;
     const uint32_t Kp = align_up((uint32_t)(K > 0 ? K : 1), 32);
@@ -184,10 +183,8 @@ __host__ __device__ inline SmemLayout make_layout(int K, int C, int mode, int th
     L.tilepref = o; o += nms ? 0 : 4 * (NT + 2);
     L.passbits = o; o += nms ? 0 : 4 * (Kp / 32);
     L.misc = o; o += 4 * M_NUM;
-    // at least one whole level of tasks must fit (a level has at most NT tasks)
-    uint32_t cap = NT + 32 + (extra & ~15u) / 4;
-    if (cap > 16384) cap = 16384;
-    L.task_cap = nms ? cap : 0;
+    (void)extra;
+    L.task_cap = nms ? align_up(2 * NT + 1, 4) : 0;   // a head task and at most one tail task per tile
     L.tasks = o; o += 4 * L.task_cap;
     o = align_up(o, 16);
     L.U = o;
@@ -219,8 +216,8 @@ struct Smem {
     uint32_t *keptw;    // [NT] kept bitmap of the tile (final once `ready`)
     uint32_t *supw;     // [NT] columns of the tile suppressed by kept rows of EARLIER tiles (OR-accumulated)
     int *arrived;       // [NT] earlier row tiles that have contributed to supw
-    int *ready;         // [NT] low 16 bits: 1 once keptw is final; high 16 bits: class of the tile
-    uint32_t *tasks;    // [task_cap] class << 16 | rt << 8 | ct   (rt == ct: the tile's diagonal task)
+    int *ready;         // [NT] class of the tile << 16 | 1 once keptw is final (set for tiles that have a tail task)
+    uint32_t *tasks;    // [task_cap] class << 16 | kTaskTail? | tile (phase_pairs)
     int *cnt, *start, *ktile;
     int *misc;
 };
@@ -746,57 +743,37 @@ __device__ __forceinline__ void warp_tile_tables(const DNParams &p, const Smem &
     for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(kFullMask, tmax, o));
     if (lane == 0) {
         s.ktile[C] = carryT;
-        s.misc[M_LEVEL] = 0;
-        s.misc[M_NLEVELS] = tmax > 0 ? 2 * tmax - 1 : 0;
+        s.misc[M_NLEVELS] = tmax;   // tiles of the largest class
     }
     __syncwarp();
 }
 
-// (warp 0) the next window of pair tasks, whole levels at a time.  Level 2r holds the diagonal task of tile r of
-// every class that has one; level 2r+1 the blocks (rows of tile r) x (columns of tile ct), ct > r.  A task only
-// depends on tasks of LOWER levels: the diagonal task of tile ct needs every block (rt < ct, ct), a block
-// (rt, ct) needs the diagonal task of rt.  Tasks are claimed in table order, so a warp that waits for a
-// dependency waits for a task some warp has already claimed: no deadlock.
-__device__ __forceinline__ void warp_build_tasks(const DNParams &p, const Smem &s, int cap) {
+constexpr int kTailMin = 4;          // a tail task exists when tile rt has at least this many tiles beyond rt + 1
+constexpr uint32_t kTaskTail = 0x8000u;
+
+__device__ __forceinline__ bool has_tail(int T, int rt) { return T - rt - 2 >= kTailMin; }
+
+// (warp 0) the task table, tile-major: head tasks of tile 0 of every class that has one, their tail tasks, head tasks
+// of tile 1, ... (class << 16 | kTaskTail? | tile); at most 2 * NT entries
+__device__ __forceinline__ void warp_build_tasks(const DNParams &p, const Smem &s) {
     const int lane = threadIdx.x & 31;
     const int C = p.C;
-    int level = s.misc[M_LEVEL];
-    const int nlevels = s.misc[M_NLEVELS];
-    int ntask = 0;
-    while (level < nlevels) {
-        const int r = level >> 1;
-        const bool diag = !(level & 1);
-        // tasks of this level
-        int total = 0;
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            const int c = c0 + lane;
-            const int T = (c < C) ? (s.cnt[c] + 31) >> 5 : 0;
-            int m = diag ? (T > r ? 1 : 0) : max(T - r - 1, 0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(kFullMask, m, o);
-            total += m;
-        }
-        if (ntask + total > cap) break;   // (a level has at most NT <= cap tasks, so the first one always fits)
-        int carry = ntask;
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            const int c = c0 + lane;
-            const int T = (c < C) ? (s.cnt[c] + 31) >> 5 : 0;
-            const int m = diag ? (T > r ? 1 : 0) : max(T - r - 1, 0);
-            const int inc = warp_inclusive_scan(m, lane);
-            int o = carry + inc - m;
-            if (diag) {
-                if (m) s.tasks[o] = ((uint32_t)c << 16) | ((uint32_t)r << 8) | (uint32_t)r;
-            } else {
-                for (int ct = r + 1; ct < T; ++ct) s.tasks[o++] = ((uint32_t)c << 16) | ((uint32_t)r << 8) | (uint32_t)ct;
+    const int tmax = s.misc[M_NLEVELS];
+    int q = 0;
+    for (int t = 0; t < tmax; ++t) {
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                const int T = (c < C) ? (s.cnt[c] + 31) >> 5 : 0;
+                const bool has = pass ? has_tail(T, t) : T > t;
+                const uint32_t bal = __ballot_sync(kFullMask, has);
+                if (has) s.tasks[q + __popc(bal & lanemask_lt())] = ((uint32_t)c << 16) | (pass ? kTaskTail : 0u) | (uint32_t)t;
+                q += __popc(bal);
             }
-            carry += __shfl_sync(kFullMask, inc, 31);
         }
-        ntask += total;
-        ++level;
     }
     if (lane == 0) {
-        s.misc[M_LEVEL] = level;
-        s.misc[M_NTASK] = ntask;
+        s.misc[M_NTASK] = q;
         s.misc[M_CTR] = 0;
     }
     __syncwarp();
@@ -847,19 +824,19 @@ __device__ __forceinline__ void phase_rank(const DNParams &p, const Smem &s, int
     }
 }
 
-// fp16 images of a box for the prefilter (see h16_prefilter).  Scales: X = x / 4, Y = 64 * y, so for |coordinates|
-// <= 2 the enlarged overlap width is <= 1 (HADD2.SAT clamps it at 0 from below for free) and areas down to 1.5e-5
-// (a 1.4 x 1.4 pixel box at 352 x 352) keep a NORMAL fp16 t*area.  Anything else -- non-finite or far-away
-// coordinates, tiny or huge areas, a threshold outside [0.01, 1] -- gets TA = -inf: every pair with the box is a
-// "maybe" and is decided by the exact arithmetic.
-constexpr float kH16SX = 0.25f, kH16SY = 64.0f;
+// fp16 images of a box for the prefilter (see h16_prefilter).  Scales: X = x / 16, Y = 256 * y, so for |coordinates|
+// <= 8 the enlarged overlap width is <= 1 (HADD2.SAT clamps it at 0 from below for free), overlap heights stay below
+// 4096, and areas down to 1.5e-5 (a 1.4 x 1.4 pixel box at 352 x 352) keep a NORMAL fp16 t*area*16.  Anything else --
+// non-finite or far-away coordinates, tiny or huge areas, a threshold outside [0.01, 1] -- gets TA = -inf: every
+// pair with the box is a "maybe" and is decided by the exact arithmetic.
+constexpr float kH16SX = 0.0625f, kH16SY = 256.0f;
 
 __device__ __forceinline__ void h16_store(const Smem &s, uint32_t pp, const float4 &b, const IouThr &t) {
     H16Tile &tile = s.h16[pp >> 5];
     const int k = pp & 15, hi = (pp >> 4) & 1;
     const float a = box_area(b);
     const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
-    const bool ok = t.fast_ok && a >= 1.52587890625e-05f && a <= 16.0f && big <= 2.0f;  // (false for NaN)
+    const bool ok = t.fast_ok && a >= 1.52587890625e-05f && a <= 256.0f && big <= 8.0f;  // (false for NaN)
     __half *xy = reinterpret_cast<__half *>(&tile.xy[k]);
     xy[0 + hi] = ok ? __float2half_rd(__fmul_rn(b.x, kH16SX)) : __ushort_as_half((unsigned short)0);
     xy[2 + hi] = ok ? __float2half_rd(__fmul_rn(b.y, kH16SY)) : __ushort_as_half((unsigned short)0);
@@ -920,18 +897,27 @@ __device__ __forceinline__ H16Row h16_row(const H16Tile &t, int lane) {
 // of the exact one.  If an extent is <= 0 the true boxes do not overlap on that axis either: W clamps to 0, or
 // H <= 0, and D = -SUM < 0.  Degenerate boxes carry TA = -inf, so D = +inf: maybe.  NaN cannot appear: every
 // table entry of a valid column is finite except TA = -inf, and -inf only ever meets finite numbers or itself.
-__device__ __forceinline__ uint32_t h16_prefilter(const H16Tile &t, const H16Row &r) {
+// S: steps = column pairs (k, k + 16) visited; S < 16 serves tiles with at most S valid columns (the class's last tile)
+template <int S>
+__device__ __forceinline__ uint32_t h16_prefilter_steps(const H16Tile &t, const H16Row &r) {
     uint32_t acc = 0u;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < S; ++k) {
         const uint4 c = t.xy[k];
         const __half2 w = __hsub2_sat(__hmin2(u2h(r.x2), u2h(c.z)), __hmax2(u2h(r.x1), u2h(c.x)));
         const __half2 h = __hsub2(__hmin2(u2h(r.y2), u2h(c.w)), __hmax2(u2h(r.y1), u2h(c.y)));
         const __half2 nsum = __hsub2(u2h(r.nta), u2h(t.ta[k]));   // -(TAr + TAc)
         const uint32_t d = h2u(__hfma2(w, h, nsum));
-        acc = (acc >> 1) | (d & 0x80008000u);                      // sign bits; after 16 steps bit k = column k, 16 + k = column 16 + k
+        acc = (acc >> 1) | (d & 0x80008000u);                      // sign bits: step k's land at 16 - S + k and 32 - S + k
     }
-    return ~acc;
+    return (S == 16) ? ~acc : ((~acc >> (16 - S)) & ((1u << S) - 1u));
+}
+
+__device__ __forceinline__ uint32_t h16_prefilter(const H16Tile &t, const H16Row &r, int ncol) {
+    if (ncol > 12) return h16_prefilter_steps<16>(t, r);   // (13..16 columns: the high halves are masked by `valid`)
+    if (ncol > 8) return h16_prefilter_steps<12>(t, r);
+    if (ncol > 4) return h16_prefilter_steps<8>(t, r);
+    return h16_prefilter_steps<4>(t, r);
 }
 
 // One pair, decided exactly as torchvision decides it (call site utils/box.py:28).  The divide-free comparison
@@ -952,8 +938,8 @@ __device__ __forceinline__ bool pair_decide(const float4 &R, float ra, const flo
 }
 
 // the exact decisions for the "maybe" bits of one block: bit j of the result = this lane's row suppresses column j
-// of tile gct.  Few bits per lane (the common case): every lane walks its own bits; many: the warp walks the union
-// column by column (uniform column loads).
+// of tile gct.  Either every lane walks its own bits (max popcount turns), or the warp walks the union column by column
+// (uniform column loads, popcount(union) turns): whichever is fewer instructions.
 __device__ __forceinline__ uint32_t resolve_maybe(const DNParams &p, const Smem &s, int gct, uint32_t maybe, int row_pp) {
     const int mx = __reduce_max_sync(kFullMask, (unsigned)__popc(maybe));
     if (mx == 0) return 0u;
@@ -962,7 +948,8 @@ __device__ __forceinline__ uint32_t resolve_maybe(const DNParams &p, const Smem 
     const float ra = box_area(R);
     const uint16_t *cids = s.scid + 32 * gct;
     uint32_t word = 0u;
-    if (mx <= 6) {
+    uint32_t uni = __reduce_or_sync(kFullMask, maybe);
+    if (5 * mx <= 4 * __popc(uni)) {
         for (int it = 0; it < mx; ++it) {
             if (maybe) {
                 const int j = __ffs(maybe) - 1;
@@ -971,7 +958,6 @@ __device__ __forceinline__ uint32_t resolve_maybe(const DNParams &p, const Smem 
             }
         }
     } else {
-        uint32_t uni = __reduce_or_sync(kFullMask, maybe);
         while (uni) {
             const int j = __ffs(uni) - 1;
             uni &= uni - 1u;
@@ -1003,6 +989,40 @@ __device__ __forceinline__ uint32_t ld_relaxed_s(const uint32_t *a) {
     return v;
 }
 
+// Tasks.  HEAD task of tile rt of class c: (1) when the kept rows of all earlier tiles have contributed to the tile's
+// suppressed-column word (arrived[g] == rt), the tile is resolved in score order (its diagonal block) and its kept word
+// is final; (2) its kept rows meet the columns of tile rt + 1 -- the block the next head task waits for -- and, unless
+// the class has many tiles left, of every later tile too.  TAIL task of tile rt (classes with many tiles): the kept
+// rows of tile rt against the tiles rt + 2, rt + 3, ... in that order, on another warp.  Every block reduces at once
+// to one word (the columns its KEPT rows suppress) that is OR-ed into supw[ct]; rows that are already suppressed and
+// columns that are already suppressed cost nothing.  The head tasks of a class form a chain (two blocks per link); the
+// tail strips run beside it and deliver a column tile before the chain needs it.  Tasks are claimed in table order --
+// heads of tile 0, tails of tile 0, heads of tile 1, ... -- so a warp only ever waits for tasks that some warp has
+// already claimed: no deadlock.
+// (Tried and dropped, profiles/r02/NOTES.md: evaluating a task's blocks for ALL rows before looking at its dependency --
+// full parallelism, but 19 % slower on cfg2: more code in the loop body and no skipping.)
+
+// kept rows of tile grt (word rem, this lane's row operands `row`) against the column tiles [ct0, ct1) of the class
+__device__ __forceinline__ void strip_blocks(const DNParams &p, const Smem &s, int n, int grt, int rt, int ct0, int ct1, uint32_t rem,
+                                             const H16Row &row) {
+    const int lane = threadIdx.x & 31;
+    const bool kept = (rem >> lane) & 1u;
+    for (int ct = ct0; ct < ct1; ++ct) {
+        const int gct = grt + (ct - rt);
+        const int ncol = min(32, n - 32 * ct);
+        const uint32_t open = ((ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u)) & ~ld_relaxed_s(&s.supw[gct]);
+        uint32_t sup = 0u;
+        if (rem != 0u && open != 0u) {
+            const uint32_t maybe = kept ? (h16_prefilter(s.h16[gct], row, ncol) & open) : 0u;
+            sup = __reduce_or_sync(kFullMask, resolve_maybe(p, s, gct, maybe, 32 * grt + lane));
+        }
+        if (lane == 0) {
+            if (sup) red_or_s(&s.supw[gct], sup);
+            red_release_add_s(&s.arrived[gct], 1);
+        }
+    }
+}
+
 __device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
     const int lane = threadIdx.x & 31;
     const int ntask = s.misc[M_NTASK];
@@ -1012,25 +1032,31 @@ __device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= ntask) break;
         const uint32_t tk = s.tasks[q];
-        const int c = (int)(tk >> 16), rt = (int)((tk >> 8) & 0xffu), ct = (int)(tk & 0xffu);
+        const int c = (int)(tk >> 16), rt = (int)(tk & 0x7fffu);
         const int n = s.cnt[c];
-        const int g0 = s.ktile[c];
-        const int grt = g0 + rt, gct = g0 + ct;
-        const int ncol = min(32, n - 32 * ct);
-        const uint32_t valid = (ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u);
-        if (rt == ct) {
-            // diagonal task: the tile's columns that survive the kept rows of all earlier tiles, then the tile's own
-            // turns in score order
-            if (ct > 0) {
-                while (ld_acquire_s(&s.arrived[gct]) < ct) __nanosleep(20);
+        const int T = (n + 31) >> 5;
+        const int grt = s.ktile[c] + rt;
+        const H16Row row = h16_row(s.h16[grt], lane);
+        uint32_t rem;
+        int ct0, ct1;
+        if (tk & kTaskTail) {
+            while (!(ld_acquire_s(&s.ready[grt]) & 1)) __nanosleep(20);
+            rem = s.keptw[grt];
+            ct0 = rt + 2;
+            ct1 = T;
+        } else {
+            const int nrow = min(32, n - 32 * rt);
+            const uint32_t validr = (nrow >= 32) ? 0xffffffffu : ((1u << nrow) - 1u);
+            // (1) the tile's own turns
+            if (rt > 0) {
+                while (ld_acquire_s(&s.arrived[grt]) < rt) __nanosleep(20);
             }
-            const uint32_t alive = valid & ~ld_relaxed_s(&s.supw[gct]);
-            uint32_t rem = alive;
+            const uint32_t alive = validr & ~ld_relaxed_s(&s.supw[grt]);
+            rem = alive;
             if (alive & (alive - 1u)) {   // two or more alive candidates
                 uint32_t maybe = 0u;
-                if ((alive >> lane) & 1u)
-                    maybe = h16_prefilter(s.h16[gct], h16_row(s.h16[gct], lane)) & alive & ~((2u << lane) - 1u);  // LATER columns
-                const uint32_t D = resolve_maybe(p, s, gct, maybe, 32 * gct + lane);
+                if ((alive >> lane) & 1u) maybe = h16_prefilter(s.h16[grt], row, nrow) & alive & ~((2u << lane) - 1u);  // LATER columns
+                const uint32_t D = resolve_maybe(p, s, grt, maybe, 32 * grt + lane);
                 uint32_t nz = __ballot_sync(kFullMask, D != 0u);
                 while (nz) {
                     const int i = __ffs(nz) - 1;
@@ -1039,28 +1065,16 @@ __device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
                     if ((rem >> i) & 1u) rem &= ~Di;
                 }
             }
+            const bool tail = has_tail(T, rt);
             if (lane == 0) {
-                s.keptw[gct] = rem;
-                st_release_s(&s.ready[gct], (c << 16) | 1);
+                s.keptw[grt] = rem;
+                if (tail) st_release_s(&s.ready[grt], (c << 16) | 1);
             }
-        } else {
-            // block (rows of tile rt) x (columns of tile ct): only KEPT rows matter, and only columns nobody has
-            // suppressed yet
-            while (!(ld_acquire_s(&s.ready[grt]) & 1)) __nanosleep(20);
-            const uint32_t kw = s.keptw[grt];
-            const uint32_t open = valid & ~ld_relaxed_s(&s.supw[gct]);
-            uint32_t sup = 0u;
-            if (kw != 0u && open != 0u) {
-                uint32_t maybe = 0u;
-                if ((kw >> lane) & 1u) maybe = h16_prefilter(s.h16[gct], h16_row(s.h16[grt], lane)) & open;
-                const uint32_t word = resolve_maybe(p, s, gct, maybe, 32 * grt + lane);
-                sup = __reduce_or_sync(kFullMask, word);
-            }
-            if (lane == 0) {
-                if (sup) red_or_s(&s.supw[gct], sup);
-                red_release_add_s(&s.arrived[gct], 1);
-            }
+            // (2) the kept rows against the next tile (the tail task takes the others), or against all later tiles
+            ct0 = rt + 1;
+            ct1 = tail ? rt + 2 : T;
         }
+        strip_blocks(p, s, n, grt, rt, ct0, ct1, rem, row);   // (one call site: the block code exists once)
         __syncwarp();
     }
 }
@@ -1337,8 +1351,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     stamp<DBG>(p, b, 13);
     const int Kv = s.misc[M_KV];
     if (warp == 0) {
-        // the first window of pair tasks: only the pair phase needs it, so warp 0 builds it while the other warps sort
-        warp_build_tasks(p, s, (int)L.task_cap);
+        // the strip tasks: only the pair phase needs them, so warp 0 builds them while the other warps sort
+        warp_build_tasks(p, s);
     } else {
         // P3 / P4 on the other warps (named barrier 1 between the key scatter, the ranking, and the writes that
         // reuse the key memory)
@@ -1352,15 +1366,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     }
     __syncthreads();
     stamp<DBG>(p, b, 3);
-    // P5 (windows of whole task levels; one window unless the image has more blocks than the table holds)
-    for (;;) {
-        phase_pairs(p, s);
-        __syncthreads();
-        if (s.misc[M_LEVEL] >= s.misc[M_NLEVELS]) break;
-        __syncthreads();   // (everybody has read M_LEVEL before warp 0 advances it)
-        if (warp == 0) warp_build_tasks(p, s, (int)L.task_cap);
-        __syncthreads();
-    }
+    // P5
+    phase_pairs(p, s);
+    __syncthreads();
     stamp<DBG>(p, b, 4);
     // P6 (the fp16 tables are dead now; the row scratch aliases them)
     pdl_wait();

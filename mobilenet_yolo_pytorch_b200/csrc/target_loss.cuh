@@ -71,6 +71,8 @@ struct TLParams {
     const float *grad_out;      // device scalar d(total)/d(loss), or null = 1
     float *grad_input;          // (N, A*(5+C), H, W)
     float iou_weighting;
+    int wait_inputs;            // 1: griddepcontrol.wait before the first global read (the predecessor in the stream may
+                                // have produced head / gt); 0: the caller vouches for the inputs (b200yolo_set_inputs_ready)
 };
 
 struct TLAssign {
@@ -274,7 +276,6 @@ __device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, b
             s.gcls[t] = cls;
             const int gi = (int)__fmul_rn(gx, p.fW), gj = (int)__fmul_rn(gy, p.fH);  // :128,136-137
             const bool ok = gi >= 0 && gi < W && gj >= 0 && gj < H && cls >= 0 && cls < C;
-            if (!ok && lead) atomicMax(&s.misc[2], 1);
             // anchor-vs-GT IoU on (0,0,w,h) shapes, ALL anchors (:129-133)
             const float4 gb = make_float4(0.f, 0.f, gw, gh);
             const float ga = box_area(gb);
@@ -288,7 +289,13 @@ __device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, b
                 if (v > p.iou_thr) over |= 1u << n;                      // :139
             }
             for (int k = 0; k < A; ++k) {
-                const bool asg = ok && (p.mask[k] == best_n || ((over >> p.mask[k]) & 1u));  // :141-145
+                const bool want = (p.mask[k] == best_n || ((over >> p.mask[k]) & 1u));      // :141-145
+                // The reference indexes [gj, gi] and the class only for a GT it assigns on THIS head (:146-169): a box
+                // outside the grid that another head owns trains fine upstream, so only an assigned one is an error
+                // (status 1 -> IndexError in the shim).  Divergence kept on purpose: negative cells / class 0 wrap
+                // around silently in the reference (python negative indexing); here they are errors too.
+                if (want && !ok && lead) atomicMax(&s.misc[2], 1);
+                const bool asg = ok && want;
                 if (asg) amask |= 1u << k;
                 if (p.assign && lead) {
                     int *r = p.assign + ((size_t)(g0 + t) * A + k) * 4;
@@ -362,15 +369,17 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
     const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
     const bool lead = (split == 0);  // the CTA of the image that owns the per-GT outputs and the assignments
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g0 = p.gt_off[b];
-    int nG = p.gt_off[b + 1] - g0;
     const int HW = p.HW, W = p.W, A = p.A, C = p.C;
 
-    // Programmatic dependent launch (see decode_nms.cuh): the next kernel of the stream may start now; this one
-    // waits for its predecessor before its first global store (the workspace of partial sums is shared by
-    // consecutive calls; the optional per-GT / per-cell outputs are written early, so they wait here).
+    // Programmatic dependent launch (see decode_nms.cuh): the next kernel of the stream may start now.  This one waits
+    // for its predecessor before its first global READ unless the caller has declared the inputs ready (the kernel
+    // before it in the stream may be the producer of head / gt, and its writes are only guaranteed visible after
+    // griddepcontrol.wait), and in any case before its first global store (the workspace of partial sums is shared
+    // by consecutive calls; the optional per-GT / per-cell outputs are written early, so they wait here).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (p.assign || p.terms || p.cell_state) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.wait_inputs || p.assign || p.terms || p.cell_state) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int g0 = p.gt_off[b];
+    int nG = p.gt_off[b + 1] - g0;
     if (tid < 4) s_misc[tid] = 0;  // assignment list length; any degenerate GT box; status; distinct cells
     for (int c = tid; c < (int)flag_bytes; c += kTLThreads) s_flag[c] = 0;
     __syncthreads();
@@ -591,13 +600,13 @@ __global__ void __launch_bounds__(kTLThreads, 4) target_loss_backward_kernel(con
 
     const int b = blockIdx.x / p.S, split = blockIdx.x - b * p.S;
     const int tid = threadIdx.x;
-    const int g0 = p.gt_off[b];
-    int nG = p.gt_off[b + 1] - g0;
     const int HW = p.HW, W = p.W, A = p.A;
     // Programmatic dependent launch: the next kernel of the stream may start; this one reads what the forward call
-    // produced (sums, cell states).
+    // produced (sums, cell states), so it waits before its first global read.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int g0 = p.gt_off[b];
+    int nG = p.gt_off[b + 1] - g0;
     if (nG > p.gcap) nG = 0;  // (the forward call reported it)
     float *gbase = p.grad_input + (size_t)b * A * p.attrs * HW;
     const float *hbase = p.head + (size_t)b * A * p.attrs * HW;

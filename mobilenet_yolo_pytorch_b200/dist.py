@@ -80,12 +80,21 @@ class _RawCuda:
 class PeerGather:
     """Decode + NMS fused with the all-gather of the detections (``b200yolo_decode_nms_gather``).
 
-    Every rank owns one gather buffer -- ``dets`` (world*n_local, K, 7) fp32 and ``counts`` (world*n_local,) int32 --
-    in memory the other ranks of the node map through CUDA IPC.  ``decode_nms`` post-processes this rank's shard and
-    its output phase stores the kept rows into ALL buffers (its own and, over NVLink, the peers'), so the transfer
-    overlaps the kernel instead of following it as a separate NCCL all-gather; ``fence`` is the cross-rank barrier after
-    which every buffer holds the whole batch (one tiny all-reduce on the current stream).  One process per GPU on one
-    NVSwitch box, at most 8 ranks; ``close`` releases the mappings."""
+    Every rank owns TWO gather buffers (parity = step & 1) -- ``dets[p]`` (world*n_local, K, 7) fp32 and
+    ``counts[p]`` (world*n_local,) int32 -- in memory the other ranks of the node map through CUDA IPC.  A step
+    post-processes this rank's shard; its output phase stores the kept rows into the buffers of ALL ranks (its own
+    and, over NVLink, the peers'), so the transfer overlaps the kernel instead of following it as a separate NCCL
+    all-gather.  ``fence`` is the cross-rank barrier after which every rank's buffer of that step holds the whole
+    batch: ONE small kernel (``b200yolo_peer_fence``: raise this rank's arrival flag everywhere, wait for all flags of
+    its own), which does not serialise the stream -- the next step's kernel starts under it and blocks before its
+    first store until the fence has completed.
+
+    Back-pressure (why two buffers are enough).  A rank stores into parity p at step s only after its own fence of
+    step s-1 has completed, i.e. after EVERY rank has arrived at step s-1; a rank's arrival at step s-1 is
+    stream-ordered after everything it enqueued on the buffers of step s-2 (same parity p).  So: consume the result of
+    step s -- ``current()`` -- with ordinary kernel launches on the same stream BEFORE launching step s+1, and no
+    peer can overwrite what a consumer still reads.  One process per GPU on one NVSwitch box, at most 8 ranks;
+    ``close`` releases the mappings.  ``group`` may be a gloo group (the rendezvous only moves the IPC handles)."""
 
     def __init__(self, n_local: int, cells_per_image: int, group=None, device: Optional[torch.device] = None):
         import ctypes as C
@@ -98,9 +107,11 @@ class PeerGather:
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         lib = _lib.load()
         total = self.world * self.n_local
-        self._row_bytes = (total * self.K * 7 * 4 + 255) // 256 * 256
-        self._flag_off = (self._row_bytes + total * 4 + 255) // 256 * 256     # int[8] arrival flags + int timed_out
-        nbytes = self._flag_off + 64
+        row_bytes = (total * self.K * 7 * 4 + 255) // 256 * 256
+        cnt_bytes = (total * 4 + 255) // 256 * 256
+        self._par_bytes = row_bytes + cnt_bytes
+        self._flag_off = 2 * self._par_bytes            # int[8] arrival flags + int timed_out
+        nbytes = self._flag_off + 256
         with torch.cuda.device(self.device):
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
             _lib.check(lib.b200yolo_peer_alloc(nbytes, C.byref(ptr), handle))
@@ -116,50 +127,112 @@ class PeerGather:
                 _lib.check(lib.b200yolo_peer_open(handles[r], C.byref(p2)))
                 self._bases.append(p2.value)
                 self._opened.append(p2.value)
-            self._out_ptrs = (C.c_void_p * self.world)(*self._bases)
-            self._cnt_ptrs = (C.c_void_p * self.world)(*[b + self._row_bytes for b in self._bases])
+            g = _lib.Gather()
+            g.R, g.rank = self.world, self.rank
+            for par in range(2):
+                for r in range(self.world):
+                    g.peer_out[par][r] = self._bases[r] + par * self._par_bytes
+                    g.peer_count[par][r] = self._bases[r] + par * self._par_bytes + row_bytes
+            for r in range(self.world):
+                g.peer_flags[r] = self._bases[r] + self._flag_off
+            g.timed_out = self._own + self._flag_off + 64
+            g.timeout_s = 5.0
+            self._g = g
+            self._out_ptrs = [(C.c_void_p * self.world)(*[self._bases[r] + par * self._par_bytes for r in range(self.world)])
+                              for par in range(2)]
+            self._cnt_ptrs = [(C.c_void_p * self.world)(*[self._bases[r] + par * self._par_bytes + row_bytes for r in range(self.world)])
+                              for par in range(2)]
             self._flag_ptrs = (C.c_void_p * self.world)(*[b + self._flag_off for b in self._bases])
-            self._step = 0
+            self._step = 0        # steps launched so far
+            self._fenced = 0      # steps whose fence has been launched
             raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
-            self.dets = raw[:total * self.K * 7 * 4].view(torch.float32).view(total, self.K, 7)
-            self.counts = raw[self._row_bytes:self._row_bytes + total * 4].view(torch.int32)
-            self._timed_out = raw[self._flag_off + 32:self._flag_off + 36].view(torch.int32)
+            self._dets = [raw[par * self._par_bytes:par * self._par_bytes + total * self.K * 7 * 4].view(torch.float32).view(total, self.K, 7)
+                          for par in range(2)]
+            self._counts = [raw[par * self._par_bytes + row_bytes:par * self._par_bytes + row_bytes + total * 4].view(torch.int32)
+                            for par in range(2)]
+            self._timed_out = raw[self._flag_off + 64:self._flag_off + 68].view(torch.int32)
             self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
 
-    def decode_nms(self, head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
-                   iou_thr: float = 0.45) -> None:
-        """launch on the current stream; results are complete on every rank after ``fence()``"""
-        from . import _lib, ops
+    # ---- results of the most recently launched step (valid on the stream after its fence)
+    @property
+    def dets(self) -> torch.Tensor:
+        return self._dets[(self._step - 1) & 1]
+
+    @property
+    def counts(self) -> torch.Tensor:
+        return self._counts[(self._step - 1) & 1]
+
+    def current(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.dets, self.counts
+
+    def _shape_args(self, head0, head1, anchor_wh2, num_classes):
+        from . import ops
         ops._require_cuda(head0, "head0")
         ops._require_cuda(head1, "head1")
-        head0, head1 = head0.contiguous(), head1.contiguous()
         N, ch, H0, W0 = head0.shape
         _, _, H1, W1 = head1.shape
         A = ch // (5 + num_classes)
         if N != self.n_local or A * (H0 * W0 + H1 * W1) != self.K:
-            raise RuntimeError("PeerGather.decode_nms: shard shape differs from the buffer's")
+            raise RuntimeError("PeerGather: shard shape differs from the buffer's")
         aw = ops._host_f32(anchor_wh2).reshape(2, A, 2)
+        return N, A, H0, W0, H1, W1, aw
+
+    def decode_nms(self, head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
+                   iou_thr: float = 0.45) -> None:
+        """launch one step on the current stream; results are complete on every rank after ``fence()``"""
+        from . import _lib
+        if self._fenced != self._step:
+            raise RuntimeError("PeerGather: fence() the previous step before launching the next one")
+        head0, head1 = head0.contiguous(), head1.contiguous()
+        N, A, H0, W0, H1, W1, aw = self._shape_args(head0, head1, anchor_wh2, num_classes)
+        par = self._step & 1
         _lib.check(_lib.load().b200yolo_decode_nms_gather(
             head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
-            float(np.float32(conf_thr)), float(iou_thr), self._out_ptrs, self._cnt_ptrs, self.world, self.rank,
+            float(np.float32(conf_thr)), float(iou_thr), self._out_ptrs[par], self._cnt_ptrs[par], self.world, self.rank,
             torch.cuda.current_stream(self.device).cuda_stream))
+        self._step += 1
 
     def fence(self, collective: bool = False, timeout_s: float = 5.0) -> None:
-        """Stream-ordered barrier across the ranks: when it completes, every rank's launch has completed and its rows
-        are in every buffer.  Default: two tiny kernels -- this rank raises its arrival flag in every peer's buffer,
-        then waits for all flags of its own buffer (``check()`` tells whether a peer failed to arrive in time);
-        ``collective=True`` uses a 1-element NCCL all-reduce instead."""
-        if collective:
-            dist.all_reduce(self._flag, group=self.group)
-            return
+        """Stream-ordered barrier across the ranks for the step just launched: when it completes, every rank's launch
+        has completed and its rows are in every buffer (``check()`` tells whether a peer failed to arrive in time).
+        ``collective=True`` additionally runs a 1-element NCCL all-reduce (for comparison; the flags are still raised,
+        they carry the back-pressure)."""
         from . import _lib
         lib = _lib.load()
-        self._step += 1
+        if self._fenced >= self._step:
+            return
         st = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(lib.b200yolo_peer_signal(self._flag_ptrs, self.world, self.rank, self._step, st))
-        _lib.check(lib.b200yolo_peer_wait(self._own + self._flag_off, self.world, self._step, float(timeout_s),
-                                          self._own + self._flag_off + 32, st))
+        _lib.check(lib.b200yolo_peer_fence(self._flag_ptrs, self._own + self._flag_off, self.world, self.rank, self._step,
+                                           float(timeout_s), self._own + self._flag_off + 64, st))
+        self._fenced = self._step
+        if collective:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def run_steps(self, heads, anchor_wh2, num_classes: int, conf_thr: float, iou_thr: float = 0.45, plan=None):
+        """``len(heads)`` steps -- kernel + fence each -- issued from C in ONE call (``b200yolo_decode_nms_gather_steps``);
+        ``heads`` is a sequence of (head0, head1).  Returns a reusable plan (pass it back as ``plan`` to skip the set-up).
+        Only for pipelines without a per-step consumer (benchmarks, or consumers that read ``current()`` after the call)."""
+        import ctypes as C
+        from . import _lib
+        if self._fenced != self._step:
+            raise RuntimeError("PeerGather: fence() the previous step first")
+        if plan is None:
+            h0, h1 = heads[0]
+            N, A, H0, W0, H1, W1, aw = self._shape_args(h0, h1, anchor_wh2, num_classes)
+            arr = (_lib.Batch * len(heads))()
+            for k, (a0, a1) in enumerate(heads):
+                if a0.shape != h0.shape or a1.shape != h1.shape or not a0.is_contiguous() or not a1.is_contiguous():
+                    raise RuntimeError("PeerGather.run_steps: NCHW-contiguous heads of one shape")
+                arr[k] = _lib.Batch(a0.data_ptr(), a1.data_ptr(), None, None, None)
+            plan = (arr, len(heads), list(heads), (N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data, float(np.float32(conf_thr)),
+                                                  float(iou_thr)), aw)
+        arr, n = plan[0], plan[1]
+        _lib.check(_lib.load().b200yolo_decode_nms_gather_steps(
+            C.byref(self._g), arr, n, self._step, *plan[3], torch.cuda.current_stream(self.device).cuda_stream))
+        self._step += n
+        self._fenced = self._step
+        return plan
 
     def check(self) -> None:
         """host-synchronising: raise if a fence gave up waiting for a peer"""
@@ -175,6 +248,6 @@ class PeerGather:
             lib.b200yolo_peer_close(p2)
         self._opened = []
         if self._own:
-            self.dets = self.counts = self._timed_out = None
+            self._dets = self._counts = self._timed_out = None
             lib.b200yolo_peer_free(self._own)
             self._own = None

@@ -305,16 +305,21 @@ def pairwise(set_1: torch.Tensor, set_2: torch.Tensor, mode: int) -> torch.Tenso
     return out
 
 
-_PACK_CACHE = {}     # device -> (key, targets list (kept alive), packed result): both heads of a step pass the same list
+_PACK_CACHE = {}     # device -> [key, targets list, packed result]: ONE more use only (the second head of the same step)
 _PIN_STAGING = {}    # device -> [pinned staging tensor for the packed rows, event of the last copy out of it]
 
 
 def pack_targets(targets, device) -> Tuple[torch.Tensor, torch.Tensor, int, List[int]]:
     """list[N] of (n_b,5) tensors/arrays (reference: CPU tensors, train.py:246) -> one (G,5) device buffer + (N+1,)
-    device offsets.  One concatenation, one staged H2D copy each; the result is reused when the same list object comes
-    back (the reference hands one `targets` list to both heads, mbv2_yolo.py:158)."""
-    key = (id(targets), len(targets), id(targets[0]) if len(targets) else 0, id(targets[-1]) if len(targets) else 0)
-    hit = _PACK_CACHE.get(device)
+    device offsets.  One concatenation, one staged H2D copy each.  The reference hands ONE `targets` list to both
+    heads of a step (mbv2_yolo.py:158), so the packed copy serves exactly one more call with the same list object --
+    same length, same first / last tensors at the same in-place version -- and is dropped then: a list that is
+    mutated or refilled between steps is always packed again, and nothing is kept alive beyond the step."""
+    def _ver(t):
+        return (id(t), getattr(t, "_version", 0), t.data_ptr() if isinstance(t, torch.Tensor) else 0)
+    key = (id(targets), len(targets)) + ((_ver(targets[0]) + _ver(targets[-1]) + _ver(targets[len(targets) // 2]))
+                                         if len(targets) else ())
+    hit = _PACK_CACHE.pop(device, None)
     if hit is not None and hit[0] == key and hit[1] is targets:
         return hit[2]
     try:  # the reference's case: CPU tensors of shape (n_b, 5) -- one torch.cat, no per-image Python work beyond the counts
@@ -345,7 +350,7 @@ def pack_targets(targets, device) -> Tuple[torch.Tensor, torch.Tensor, int, List
         gt = torch.zeros((1, 5), dtype=torch.float32, device=device)
     off_d = torch.from_numpy(offs).to(device)
     res = (gt, off_d, G, counts)
-    _PACK_CACHE[device] = (key, targets, res)
+    _PACK_CACHE[device] = [key, targets, res]
     return res
 
 
