@@ -91,7 +91,7 @@ IouThr make_thr(double thr) {
     const double tt = t.fast_ok ? thr / (1.0 + thr) : 0.0;  // iou > thr <=> inter > tt * (area_a + area_b)
     t.ts = (float)tt * 1.220703125e-4f;                     // * 2^-13, exact
     t.tf = (float)tt;
-    t.th = (float)(tt * 16.0 * (1.0 - 0.00390625));         // fp16 prefilter: X = x/4, Y = 64*y, margin 2^-8
+    t.th = (float)(tt * 64.0 * (1.0 - 0.00390625));         // fp16 prefilter: X = x/16, Y = 1024*y, margin 2^-8
     return t;
 }
 

@@ -66,7 +66,7 @@ struct IouThr {
     double thr;
     float ts;     // thr/(1+thr) * 2^-13 (large_nms.cuh: the fp32 pair loop works on widths scaled into [0,1))
     float tf;     // thr/(1+thr) rounded to fp32 (decode_nms.cuh, pair_decide)
-    float th;     // thr/(1+thr) * 16 * (1 - 2^-8): scale and safety margin of the fp16 prefilter (h16_store)
+    float th;     // thr/(1+thr) * 64 * (1 - 2^-8): scale and safety margin of the fp16 prefilter (h16_store)
     int fast_ok;  // thr in [0.01, 1]
 };
 

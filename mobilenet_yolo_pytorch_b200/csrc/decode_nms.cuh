@@ -130,8 +130,8 @@ struct DNParams {
 // fp16 column table of one tile (32 sorted positions of one class): entry k packs columns k (low half) and k + 16
 // (high half), so one HMNMX2 / HADD2 / HFMA2 works on two columns.  Written in P4, read in P5.
 struct H16Tile {
-    uint4 xy[16];      // .x = X1 pair, .y = Y1 pair, .z = X2 pair, .w = Y2 pair (half2 each); X = x/16, Y = 256*y
-    uint32_t ta[16];   // TA pair: a lower bound of 16 * t * area, or -inf ("always maybe": degenerate box)
+    uint4 xy[16];      // .x = X1 pair, .y = Y1 pair, .z = X2 pair, .w = Y2 pair (half2 each); X = x/16, Y = 1024*y
+    uint32_t ta[16];   // TA pair: a lower bound of 64 * t * area, or -inf ("always maybe": degenerate box)
 };
 static_assert(sizeof(H16Tile) == 320, "H16Tile layout");
 constexpr uint32_t kTileBytes = sizeof(H16Tile) + 64;   // + scid u16[32]
@@ -824,25 +824,25 @@ __device__ __forceinline__ void phase_rank(const DNParams &p, const Smem &s, int
     }
 }
 
-// fp16 images of a box for the prefilter (see h16_prefilter).  Scales: X = x / 16, Y = 256 * y, so for |coordinates|
+// fp16 images of a box for the prefilter (see h16_prefilter).  Scales: X = x / 16, Y = 1024 * y, so for |coordinates|
 // <= 8 the enlarged overlap width is <= 1 (HADD2.SAT clamps it at 0 from below for free), overlap heights stay below
-// 4096, and areas down to 1.5e-5 (a 1.4 x 1.4 pixel box at 352 x 352) keep a NORMAL fp16 t*area*16.  Anything else --
+// 16384, and areas down to 3.8e-6 (a 0.7 x 0.7 pixel box at 352 x 352) keep a NORMAL fp16 t*area*64.  Anything else --
 // non-finite or far-away coordinates, tiny or huge areas, a threshold outside [0.01, 1] -- gets TA = -inf: every
 // pair with the box is a "maybe" and is decided by the exact arithmetic.
-constexpr float kH16SX = 0.0625f, kH16SY = 256.0f;
+constexpr float kH16SX = 0.0625f, kH16SY = 1024.0f;
 
 __device__ __forceinline__ void h16_store(const Smem &s, uint32_t pp, const float4 &b, const IouThr &t) {
     H16Tile &tile = s.h16[pp >> 5];
     const int k = pp & 15, hi = (pp >> 4) & 1;
     const float a = box_area(b);
     const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
-    const bool ok = t.fast_ok && a >= 1.52587890625e-05f && a <= 256.0f && big <= 8.0f;  // (false for NaN)
+    const bool ok = t.fast_ok && a >= 3.814697265625e-06f && a <= 256.0f && big <= 8.0f;  // (false for NaN)
     __half *xy = reinterpret_cast<__half *>(&tile.xy[k]);
     xy[0 + hi] = ok ? __float2half_rd(__fmul_rn(b.x, kH16SX)) : __ushort_as_half((unsigned short)0);
     xy[2 + hi] = ok ? __float2half_rd(__fmul_rn(b.y, kH16SY)) : __ushort_as_half((unsigned short)0);
     xy[4 + hi] = ok ? __float2half_ru(__fmul_rn(b.z, kH16SX)) : __ushort_as_half((unsigned short)0);
     xy[6 + hi] = ok ? __float2half_ru(__fmul_rn(b.w, kH16SY)) : __ushort_as_half((unsigned short)0);
-    // lower bound of t * area * 16: the 2^-8 margin covers the three fp16 roundings of the test with room to
+    // lower bound of t * area * 64: the 2^-8 margin covers the three fp16 roundings of the test with room to
     // spare (see h16_prefilter)
     reinterpret_cast<__half *>(&tile.ta[k])[hi] = ok ? __float2half_rd(__fmul_rn(a, t.th)) : __ushort_as_half((unsigned short)0xfc00);
 }
@@ -891,7 +891,7 @@ __device__ __forceinline__ H16Row h16_row(const H16Tile &t, int lane) {
 // scales).  W and H are single roundings of W*, H* (relative error <= 2^-11; differences of fp16 numbers that
 // land below the normal range are exact), the sum is one more rounding, and the FMA computes W * H - SUM with
 // ONE rounding, which never changes a sign (a nonzero result that underflows keeps its sign bit).  Hence
-//   D < 0  =>  16 * inter_true * (1 - 2^-11)^2  <=  W * H  <  SUM  <=  16 * t * (Sa + Sb) * (1 - 2^-8) * (1 + 2^-11)
+//   D < 0  =>  64 * inter_true * (1 - 2^-11)^2  <=  W * H  <  SUM  <=  64 * t * (Sa + Sb) * (1 - 2^-8) * (1 + 2^-11)
 //          =>  inter_true  <  t * (Sa + Sb) * (1 - 0.0024)            (Sa, Sb: the fp32 areas torchvision uses)
 // i.e. IoU < thr * (1 - 0.003) in exact arithmetic, and torchvision's fp32 evaluation of the IoU is within 4e-7
 // of the exact one.  If an extent is <= 0 the true boxes do not overlap on that axis either: W clamps to 0, or

@@ -586,11 +586,24 @@ def test_yololoss_forward_train_dropin(cuda_device):
 
 
 def test_target_loss_out_of_range_gt_raises(cuda_device):
-    l = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.55)
-    head = make_heads(1, 20, [(11, 11)], seed=0)[0].to(cuda_device)
+    """A GT box outside the grid (cx == 1.0 -> gi == W) or with a class beyond num_classes raises IndexError exactly
+    where the reference does (probed on the unmodified reference): only on the head that ASSIGNS it -- the reference
+    indexes [gj, gi] / the class inside the assigned branch (yolo_loss.py:138-169) -- so the same box trains fine on
+    the head whose anchors do not own it."""
+    l0 = b200.YOLOLoss(VOC_ANCHORS, MASK[0], 20, [352, 352], 0.6, 0.55)
+    l1 = b200.YOLOLoss(VOC_ANCHORS, MASK[1], 20, [352, 352], 0.6, 0.55)
+    head0, head1 = [h.to(cuda_device) for h in make_heads(1, 20, [(11, 11), (22, 22)], seed=0)]
+    small = [torch.tensor([[1.0, 1.0, 0.5, 0.1, 0.1]])]    # best anchor 3 (20x37): owned by head 1
+    large = [torch.tensor([[1.0, 1.0, 0.5, 0.8, 0.8]])]    # best anchor 2 (280x279): owned by head 0
     with pytest.raises(IndexError):
-        l(head, [torch.tensor([[1.0, 1.0, 0.5, 0.1, 0.1]])])  # cx == 1.0 -> gi == W (yolo_loss.py:128,149)
-    empty = l(head, [torch.zeros(0, 5)])  # no GT at all: loss is the pure no-object term, stats 0
+        l0(head0, large)
+    with pytest.raises(IndexError):
+        l1(head1, small)
+    with pytest.raises(IndexError):
+        l0(head0, [torch.tensor([[21.0, 0.5, 0.5, 0.8, 0.8]])])   # class 21 of 20 on the owning head
+    assert l0(head0, small)[6] == 0.0 and l1(head1, large)[6] == 0.0      # not assigned here: no error, count 0
+    assert l1(head1, [torch.tensor([[21.0, 0.5, 0.5, 0.8, 0.8]])])[6] == 0.0
+    empty = l0(head0, [torch.zeros(0, 5)])  # no GT at all: loss is the pure no-object term, stats 0
     assert empty[1:] == (0.0, 0.0, 0.0, 0, 0.0, 0.0)
 
 
