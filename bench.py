@@ -568,12 +568,16 @@ def run_b200(args, name, wl):
     if rank == 0:
         sampler = ClockSampler(local)
     D.barrier()
-    t_end = time.perf_counter() + 0.4
-    while time.perf_counter() < t_end:
-        run.run()
+    if world == 1:
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            run.run()
+            torch.cuda.synchronize()
+    else:
+        # (the ranks must issue the same number of gather steps: a fixed number of passes, ~0.2-0.5 s)
+        for _ in range(max(1, 4000 // max(args.steps, 1))):
+            run.run()
         torch.cuda.synchronize()
-        if world > 1:
-            break  # (ranks must issue the same number of gather steps: one more pass only)
     D.barrier()
     if rank == 0:
         clocks = sampler.stop()

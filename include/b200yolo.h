@@ -11,8 +11,8 @@
  * Conventions
  *  - plain pointers and sizes only; no torch / C++ types.
  *  - "dev" pointers are device memory owned by the caller; the library never
- *    allocates, frees or retains device memory passed to it (the *_host entry
- *    point owns an internal, reusable staging context).
+ *    allocates, frees or retains device memory passed to it (only the convenience
+ *    form b200yolo_decode_nms_host keeps a staging buffer of its own; the _ws form takes the caller's).
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*;
  *    NULL = legacy default stream) and performs no host synchronisation, so
  *    calls are CUDA-graph capturable.  The *_host entry point is synchronous.
@@ -194,45 +194,65 @@ int b200yolo_peer_wait(const int *own_flags, int R, int value, double timeout_s,
 int b200yolo_peer_close(void *dev_ptr);
 int b200yolo_peer_free(void *dev_ptr);
 /*
- * The two fence kernels above as ONE launch that does not serialise the stream: started with the programmatic
- * attribute right after a b200yolo_decode_nms_gather launch, it waits for that launch to complete, raises this
- * rank's flag in every rank's array (`value`: a step number that only grows), then waits for all R flags of
- * own_flags.  The decode launch that FOLLOWS it in the stream may start early and stream its heads, but blocks before
- * its first store until this fence has completed, i.e. until every rank has arrived.
+ * The two fence kernels above as launches that do not serialise the stream (programmatic launch): the signal kernel
+ * waits for the b200yolo_decode_nms_gather launch right before it to complete, then raises this rank's flag in every
+ * rank's array (`value`: the number of steps this rank has completed, it only grows); the wait kernel polls own_flags
+ * until all R slots have reached `value`.  A kernel launched after them may start early; it must not rely on them for
+ * ordering against the decode launch (b200yolo_decode_nms_gather_steps uses the flags themselves for that).
  */
 int b200yolo_peer_fence(int *const *peer_flags, const int *own_flags, int R, int rank, int value, double timeout_s,
                         int *timed_out, void *stream);
 
 /*
- * A sequence of data-parallel steps in one call: step k = b200yolo_decode_nms_gather of batches[k] (head0 / head1;
- * the other members are ignored) into the gather buffers of parity (first_step + k) & 1, followed by
- * b200yolo_peer_fence with value first_step + k + 1.  TWO buffers per rank make the fused gather safe without a
- * separate release signal: a rank stores into parity p at step s only after its own fence of step s - 1 has
- * completed, i.e. after every rank has ARRIVED at step s - 1, and a rank's arrival at s - 1 is stream-ordered after
- * whatever it ran on the buffers of step s - 2 (same parity).  Consumers of step s therefore read the buffers of
- * parity s & 1 in the stream between this call and the next one, with ordinary kernel launches.
+ * A sequence of data-parallel steps in one call -- ONE kernel launch per step.  Step s (= first_step + k) runs the
+ * fused decode + NMS + all-gather on batches[k] (head0 / head1; the other members are ignored) into gather buffer
+ * s % 3 of every rank.  This rank's arrival flag for step s (value s + 1 in every rank's flag array) is raised by an
+ * extra CTA of the launch of step s + 1, which waits for the launch before it to complete (no separate signal launch:
+ * an extra kernel per step costs ~2.3 us of launch processing); the call's last step is announced by the final fence,
+ * or, with final_fence == 0, by the caller's b200yolo_peer_fence.
+ * Back-pressure without a release signal: before its first store the kernel of step s waits (in the kernel, on this
+ * rank's own flag array) until EVERY rank has completed step s - 2; the launch of step s - 2 follows -- in that rank's
+ * stream -- whatever it ran on the buffer of step s - 3, the previous user of buffer s % 3.  In a pipeline that runs
+ * in step these flags arrived a whole step ago: the wait never stalls.
+ * final_fence != 0 appends b200yolo_peer_fence (value first_step + n_steps): when it completes, every rank's rows of
+ * the call's last step are in this rank's buffers.
+ * Contract for consumers: read the buffers of step s after its fence, with ordinary launches, before launching step
+ * s + 1.
  */
+#define B200YOLO_GATHER_BUFFERS 3
 typedef struct b200yolo_gather {
     int R, rank;
-    float *peer_out[2][8];  /* [parity][r]: rank r's buffer dev [R*N][K][7] (own: local, others: b200yolo_peer_open) */
-    int *peer_count[2][8];  /* [parity][r]: rank r's counts dev int32 [R*N] */
+    float *peer_out[B200YOLO_GATHER_BUFFERS][8];  /* [buffer][r]: rank r's buffer dev [R*N][K][7] (own: local, others: b200yolo_peer_open) */
+    int *peer_count[B200YOLO_GATHER_BUFFERS][8];  /* [buffer][r]: rank r's counts dev int32 [R*N] */
     int *peer_flags[8];     /* [r]: rank r's arrival flags dev int32 [8] */
     int *timed_out;         /* own dev int32[1], zero it once */
-    double timeout_s;       /* per fence, <= 60; <= 0: 5 s */
+    double timeout_s;       /* per wait, <= 60; <= 0: 5 s */
 } b200yolo_gather;
 int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_batch *batches, int n_steps, int first_step,
-                                     int N, int A, int C, int H0, int W0, int H1, int W1, const float *anchor_wh,
-                                     float conf_thr, double iou_thr, void *stream);
+                                     int final_fence, int N, int A, int C, int H0, int W0, int H1, int W1,
+                                     const float *anchor_wh, float conf_thr, double iou_thr, void *stream);
 
 /*
- * Same computation from HOST buffers (the reference-facing call bench.py times
- * as "e2e"): heads are copied host->device in image chunks on two streams,
- * post-processed, and detections + counts copied back, overlapped.  Pinned
- * host memory is recommended (pageable works, slower).  Synchronous.
+ * Same computation from HOST buffers (the reference-facing call bench.py times as "e2e"; inference.py:121 and
+ * train.py:366 hand host data to the model): heads are copied host->device in image chunks on three streams,
+ * post-processed, and counts + detections copied back, overlapped.  Only rows that can be kept travel back: per chunk
+ * ONE strided copy whose width is the largest count of the chunk (rows past an image's count are left untouched).
+ * Pinned host memory is recommended (pageable works, slower).  Synchronous; thread-safe without a lock (streams
+ * are per thread).
+ *   b200yolo_decode_nms_host_ws   device staging provided by the CALLER (SURVEY 8b ownership): dev_workspace of
+ *                                 b200yolo_decode_nms_host_workspace_bytes(...) bytes on `device`; concurrent calls
+ *                                 need distinct workspaces
+ *   b200yolo_decode_nms_host      convenience form: the library keeps one grow-only workspace per (thread, device)
+ *   b200yolo_host_last_d2h_bytes  device->host bytes of this thread's last call (counts + rows)
  */
+size_t b200yolo_decode_nms_host_workspace_bytes(int N, int A, int C, int H0, int W0, int H1, int W1);
+int b200yolo_decode_nms_host_ws(const float *head0, const float *head1, int N, int A, int C, int H0, int W0,
+                                int H1, int W1, const float *anchor_wh, float conf_thr, double iou_thr,
+                                float *out, int *out_count, void *dev_workspace, size_t dev_workspace_bytes, int device);
 int b200yolo_decode_nms_host(const float *head0, const float *head1, int N, int A, int C, int H0, int W0,
                              int H1, int W1, const float *anchor_wh, float conf_thr, double iou_thr,
                              float *out, int *out_count, int device);
+size_t b200yolo_host_last_d2h_bytes(void);
 
 /*
  * Compaction of fixed-stride detections for the data-parallel all-gather (no counterpart in the reference, which is
@@ -359,6 +379,9 @@ enum {
  * partial sums: result[7] = loss, recall, avg_iou, obj, no_obj, cls, count/N.
  */
 int b200yolo_loss_finalize(const double *sums, float iou_weighting, double *result);
+/* The same on the device (sums dev double[16] -> result dev float[7], one tiny launch): a training step can keep the
+ * loss tensor on the device and read the statistics later, without a host round trip per head. */
+int b200yolo_loss_finalize_dev(const double *sums, float iou_weighting, float *result, void *stream);
 
 #ifdef __cplusplus
 }

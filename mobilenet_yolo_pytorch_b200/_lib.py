@@ -49,12 +49,16 @@ SIGNATURES = {
     "b200yolo_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200yolo_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "b200yolo_peer_fence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
-    "b200yolo_decode_nms_gather_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "b200yolo_decode_nms_gather_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                    C.c_int, C.c_int, C.c_int, c_f32p, C.c_float, C.c_double, C.c_void_p]),
     "b200yolo_peer_close": (C.c_int, [C.c_void_p]),
     "b200yolo_peer_free": (C.c_int, [C.c_void_p]),
     "b200yolo_decode_nms_host": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, C.c_int]),
+    "b200yolo_decode_nms_host_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200yolo_decode_nms_host_ws": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, C.c_void_p, C.c_size_t, C.c_int]),
+    "b200yolo_host_last_d2h_bytes": (C.c_size_t, []),
     "b200yolo_compact_rows": (C.c_int, [c_f32p, c_i32p, C.c_int, C.c_int, c_f32p, c_i32p, C.c_void_p]),
     "b200yolo_pairwise": (C.c_int, [c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "b200yolo_target_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
@@ -65,6 +69,7 @@ SIGNATURES = {
                                                 c_f32p, c_i32p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_float, c_f32p, c_f32p, C.c_void_p]),
     "b200yolo_loss_finalize": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "b200yolo_loss_finalize_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "b200yolo_seg_loss_workspace_bytes": (C.c_size_t, []),
     "b200yolo_seg_loss": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),
@@ -89,7 +94,7 @@ class Batch(C.Structure):
 
 class Gather(C.Structure):
     """struct b200yolo_gather (include/b200yolo.h)."""
-    _fields_ = [("R", C.c_int), ("rank", C.c_int), ("peer_out", (C.c_void_p * 8) * 2), ("peer_count", (C.c_void_p * 8) * 2),
+    _fields_ = [("R", C.c_int), ("rank", C.c_int), ("peer_out", (C.c_void_p * 8) * 3), ("peer_count", (C.c_void_p * 8) * 3),
                 ("peer_flags", C.c_void_p * 8), ("timed_out", C.c_void_p), ("timeout_s", C.c_double)]
 
 

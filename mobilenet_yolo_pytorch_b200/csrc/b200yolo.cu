@@ -134,7 +134,7 @@ int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     // programmatic dependent launch: consecutive launches of this kernel overlap (decode_nms.cuh, pdl_trigger / pdl_wait)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)p.N);
+    cfg.gridDim = dim3((unsigned)p.N + ((variant == 1 && p.gsignal > 0) ? 1u : 0u));   // (+ the signalling CTA, decode_nms.cuh)
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = st;
@@ -234,6 +234,13 @@ int launch_dn(DNParams &p, cudaStream_t st) {
     const int need512 = (int)make_layout(p.K, p.C, MODE, 512, 0).total;
     const int need = (int)base1k.total;
     // the pair masks get whatever the tier leaves (MODE_DECODE has none)
+    if constexpr (MODE == MODE_FUSED) {
+        // experiment (flag 64): three CTAs of 384 threads per SM (<= 74 KB of shared memory each, <= 56 registers)
+        if ((p.flags & 64) && !p.nhwc && p.gR == 0 && shape_is<1>(p) && dn_counts_ok(p.K, p.C, MODE, 384)) {
+            const SmemLayout L3 = make_layout(p.K, p.C, MODE, 384, 0);
+            if ((int)L3.total <= 74 * 1024) return launch_dn_t<MODE, 384, 1>(p, L3, dev, st);
+        }
+    }
     const bool ok512 = dn_counts_ok(p.K, p.C, MODE, 512);
     if (ok512 && need512 <= kTier2x64 && kTier2x64 <= lim)
         return launch_dn_shape<MODE, 512>(p, make_layout(p.K, p.C, MODE, 512, (MODE == MODE_DECODE) ? 0u : (uint32_t)(kTier2x64 - need512)), dev, st);
@@ -271,20 +278,24 @@ __global__ void peer_wait_kernel(const int *own_flags, int R, int value, long lo
     }
 }
 
-// Signal + wait in ONE kernel, launched with the programmatic attribute right after the decode launch whose rows it
-// announces: it lets the NEXT decode launch start early (trigger), waits for its predecessor -- the decode launch --
-// to complete and flush (griddepcontrol.wait), raises this rank's arrival flag in every rank's buffer, then waits
-// for all flags of its own.  The next decode launch blocks at ITS griddepcontrol.wait (before its first store) until
-// this kernel has completed, i.e. until every rank has arrived: that is the back-pressure of the double-buffered
-// gather (dist.PeerGather).
-__global__ void peer_fence_kernel(PeerFlagPtrs flags, const int *own_flags, int R, int rank, int value, long long max_cycles,
-                                  int *timed_out) {
+// The two halves of the gather's fence as kernels that do not serialise the stream (programmatic launch, trigger at
+// their start).  peer_signal_pdl_kernel directly follows the decode launch whose rows it announces: it waits for
+// that launch to complete and flush (griddepcontrol.wait), then raises this rank's arrival flag in every rank's
+// array.  peer_wait_pdl_kernel depends on nothing in its stream: it only polls this rank's own flags.
+__global__ void peer_signal_pdl_kernel(PeerFlagPtrs flags, int R, int rank, int value) {
     pdl_trigger();
     pdl_wait();
     const int r = threadIdx.x;
     if (r < R) {
         __threadfence_system();
         *reinterpret_cast<volatile int *>(flags.p[r] + rank) = value;
+    }
+}
+
+__global__ void peer_wait_pdl_kernel(const int *own_flags, int R, int value, long long max_cycles, int *timed_out) {
+    pdl_trigger();
+    const int r = threadIdx.x;
+    if (r < R) {
         const long long t0 = clock64();
         while (*reinterpret_cast<const volatile int *>(own_flags + r) < value) {
             if (clock64() - t0 > max_cycles) {   // a peer died: report instead of hanging the GPU
@@ -297,10 +308,13 @@ __global__ void peer_fence_kernel(PeerFlagPtrs flags, const int *own_flags, int 
     }
 }
 
-int launch_peer_fence(const PeerFlagPtrs &f, const int *own_flags, int R, int rank, int value, double timeout_s, int *timed_out,
-                      cudaStream_t st) {
+long long timeout_cycles(double timeout_s) {
     if (!(timeout_s > 0.0) || timeout_s > 60.0) timeout_s = 5.0;
-    const long long max_cycles = (long long)(timeout_s * 2.0e9);   // SM clock <= 2 GHz: at least timeout_s seconds
+    return (long long)(timeout_s * 2.0e9);   // SM clock <= 2 GHz: at least timeout_s seconds
+}
+
+template <typename... Args>
+int launch_pdl_1warp(cudaStream_t st, void (*kern)(Args...), Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(1);
@@ -311,9 +325,29 @@ int launch_peer_fence(const PeerFlagPtrs &f, const int *own_flags, int R, int ra
     attr[0].val.programmaticStreamSerializationAllowed = (g_flags.load() & 2) ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, peer_fence_kernel, f, own_flags, R, rank, value, max_cycles, timed_out));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args...));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
+}
+
+// yolo_loss.py:170-178, 219-236 on the device (same formulas as b200yolo_loss_finalize): result[7] = loss, recall,
+// avg_iou, obj, no_obj, cls, count/N as fp32 -- lets a training step keep the loss on the device (no host round trip)
+__global__ void loss_finalize_kernel(const double *s, float iou_weighting, float *r) {
+    if (threadIdx.x != 0) return;
+    const double count = s[B200YOLO_S_NASSIGN];
+    const double l_dense = s[B200YOLO_S_SQW] / s[B200YOLO_S_W];
+    const double l_iou = count > 0 ? s[B200YOLO_S_IOU_SQ] / count : 0.0;
+    r[0] = (float)(l_dense + l_iou * (double)iou_weighting);
+    if (count > 0) {
+        r[1] = (float)(s[B200YOLO_S_RECALL] / count);
+        r[2] = (float)(s[B200YOLO_S_IOU] / count);
+        r[3] = (float)(s[B200YOLO_S_OBJ] / count);
+        r[4] = (float)((s[B200YOLO_S_CONF_ALL] - s[B200YOLO_S_OBJ]) / (s[B200YOLO_S_NCELLS] - count));
+        r[5] = (float)(s[B200YOLO_S_CLS] / count);
+    } else {
+        r[1] = r[2] = r[3] = r[4] = r[5] = 0.f;
+    }
+    r[6] = (float)(s[B200YOLO_S_NIMG] > 0 ? count / s[B200YOLO_S_NIMG] : 0.0);
 }
 
 // large_nms.cuh: one CTA per image, sort keys in shared memory.  SRC 0: heads (records in p.rec), 1: caller rows
@@ -536,12 +570,13 @@ int b200yolo_peer_fence(int *const *peer_flags, const int *own_flags, int R, int
         if (!peer_flags[r]) return fail(B200YOLO_EINVAL, "peer_fence: null flag array of rank %d", r);
         f.p[r] = peer_flags[r];
     }
-    return launch_peer_fence(f, own_flags, R, rank, value, timeout_s, timed_out, (cudaStream_t)stream);
+    if (int rc = launch_pdl_1warp((cudaStream_t)stream, peer_signal_pdl_kernel, f, R, rank, value)) return rc;
+    return launch_pdl_1warp((cudaStream_t)stream, peer_wait_pdl_kernel, own_flags, R, value, timeout_cycles(timeout_s), timed_out);
 }
 
 int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_batch *batches, int n_steps, int first_step,
-                                     int N, int A, int C, int H0, int W0, int H1, int W1, const float *anchor_wh,
-                                     float conf_thr, double iou_thr, void *stream) {
+                                     int final_fence, int N, int A, int C, int H0, int W0, int H1, int W1,
+                                     const float *anchor_wh, float conf_thr, double iou_thr, void *stream) {
     if (!g || n_steps < 0 || (n_steps > 0 && !batches) || !anchor_wh || first_step < 0)
         return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: bad argument");
     if (N < 0 || A < 1 || A > kMaxAnchors || C < 1 || C > 4096 || H0 < 1 || W0 < 1 || H1 < 1 || W1 < 1)
@@ -550,15 +585,15 @@ int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_ba
     if (R < 1 || R > kMaxPeers || rank < 0 || rank >= R || !g->timed_out)
         return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: %d ranks (1..%d), rank %d", R, kMaxPeers, rank);
     if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: NaN threshold");
-    for (int par = 0; par < 2; ++par)
+    for (int par = 0; par < B200YOLO_GATHER_BUFFERS; ++par)
         for (int r = 0; r < R; ++r)
             if (!g->peer_out[par][r] || !g->peer_count[par][r] || !g->peer_flags[r])
                 return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: null buffer of rank %d", r);
     const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
     if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms_gather_steps: more than 65535 cells per image");
-    PeerFlagPtrs f;
-    memset(&f, 0, sizeof(f));
-    for (int r = 0; r < R; ++r) f.p[r] = g->peer_flags[r];
+    if (n_steps == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long cyc = timeout_cycles(g->timeout_s);
     DNParams p;
     memset(&p, 0, sizeof(p));
     p.nheads = 2;
@@ -568,16 +603,35 @@ int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_ba
     p.iou = make_thr(iou_thr);
     p.gR = R;
     p.gslot = rank * N;
+    p.gwait_flags = g->peer_flags[rank];
+    p.gtimed_out = g->timed_out;
+    p.gwait_cycles = cyc;
+    p.grank = rank;
+    for (int r = 0; r < R; ++r) p.gflags[r] = g->peer_flags[r];
     for (int k = 0; k < n_steps; ++k) {
         if (!batches[k].head0 || !batches[k].head1) return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: null head in step %d", k);
-        const int step = first_step + k, par = step & 1;
+        const int step = first_step + k, par = step % B200YOLO_GATHER_BUFFERS;
         fill_head(p.head[0], batches[k].head0, A, H0, W0, anchor_wh);
         fill_head(p.head[1], batches[k].head1, A, H1, W1, anchor_wh + 2 * A);
         // every rank starts with its own buffer and walks the ring from there (the ranks hit different peers)
         for (int i = 0; i < R; ++i) { p.gout[i] = g->peer_out[par][(rank + i) % R]; p.gcount[i] = g->peer_count[par][(rank + i) % R]; }
-        p.wait_inputs = (k == 0) ? 1 : 0;   // k > 0: the predecessor is our own fence kernel
-        if (int rc = launch_dn<MODE_FUSED>(p, (cudaStream_t)stream)) return rc;
-        if (int rc = launch_peer_fence(f, g->peer_flags[rank], R, rank, step + 1, g->timeout_s, g->timed_out, (cudaStream_t)stream)) return rc;
+        // Buffer step % 3 was last used by step - 3.  A rank whose flag shows step - 1 has COMPLETED step - 2, whose
+        // launch follows -- in that rank's stream -- everything it ran on the buffers of step - 3.  Waiting for the
+        // flags of two steps ago never stalls a pipeline that runs in step.
+        p.gwait_value = step - 1;
+        p.wait_inputs = (k == 0) ? 1 : 0;   // k > 0: the predecessor is our own launch
+        // k > 0: this launch also announces that step - 1 -- the launch right before it in the stream -- is complete
+        p.gsignal = (k > 0) ? step : 0;
+        if (int rc = launch_dn<MODE_FUSED>(p, st)) return rc;
+    }
+    // the last step's arrival signal and the consumer-side fence: when it completes, the rows of the call's last step
+    // -- and of every step before it -- are in this rank's buffers
+    if (final_fence) {
+        PeerFlagPtrs f;
+        memset(&f, 0, sizeof(f));
+        for (int r = 0; r < R; ++r) f.p[r] = g->peer_flags[r];
+        if (int rc = launch_pdl_1warp(st, peer_signal_pdl_kernel, f, R, rank, first_step + n_steps)) return rc;
+        return launch_pdl_1warp(st, peer_wait_pdl_kernel, (const int *)g->peer_flags[rank], R, first_step + n_steps, cyc, g->timed_out);
     }
     return 0;
 }
@@ -1042,6 +1096,14 @@ int b200yolo_compact_rows(const float *dets, const int *count, int N, int K, flo
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
     }
+    return 0;
+}
+
+int b200yolo_loss_finalize_dev(const double *sums, float iou_weighting, float *result, void *stream) {
+    if (!sums || !result) return fail(B200YOLO_EINVAL, "loss_finalize_dev: null pointer");
+    loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, iou_weighting, result);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

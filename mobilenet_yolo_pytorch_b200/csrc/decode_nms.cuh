@@ -120,6 +120,17 @@ struct DNParams {
     int gslot;                   // first image slot of this rank = rank * N
     float *gout[kMaxPeers];      // [gR] rank r's buffer [gR*N][K][7]
     int *gcount[kMaxPeers];      // [gR] rank r's counts [gR*N]
+    // back-pressure of the fused all-gather: before its first store the kernel waits until every rank's arrival flag
+    // (this rank's own array, written by the peers over NVLink) has reached gwait_value (0: no wait)
+    const int *gwait_flags;
+    int gwait_value;
+    int *gtimed_out;
+    long long gwait_cycles;
+    // arrival signal of the fused all-gather, riding on the NEXT step's launch: when gsignal > 0 the grid has one extra
+    // CTA that waits for the previous launch in the stream (the previous step) to complete and then raises slot grank
+    // of every rank's flag array to gsignal
+    int *gflags[kMaxPeers];
+    int grank, gsignal;
     // MODE_NMS inputs
     const float *cand[2];
     const int *cand_count[2];
@@ -1242,7 +1253,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
 // GATHER: the fused all-gather variant of the output phase (its own instantiation, so the ordinary kernel's register
 // allocation is untouched).  DBG: phase time stamps (profiles/phase_times.py).
 template <int MODE, int THREADS, int SHAPE, int GATHER = 0, bool DBG = false>
-__global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
+__global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, L, p.K, p.C);
     const int b = blockIdx.x;
@@ -1251,6 +1262,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     using SH = ShapeT<SHAPE>;
 
     pdl_trigger();  // the next launch may start filling free SM slots right away (it waits before it writes)
+    if constexpr (GATHER != 0) {
+        // The arrival signal of the PREVIOUS step rides on this launch (a kernel of its own per step costs ~2.3 us of
+        // launch processing, and a system-scope fence in every CTA of the step itself flushes the L1 the decode
+        // streams through: +8 us, profiles/r02/NOTES.md).  The extra CTA idles in one of 296 slots until the
+        // previous launch has completed and flushed, then publishes: the peers may read that step's rows.
+        if (b == p.N) {
+            pdl_wait();
+            if (tid < p.gR) {
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(p.gflags[tid] + p.grank) = p.gsignal;
+            }
+            return;
+        }
+    }
     // Inputs another kernel of this library wrote (rows of our own decode kernels), or a producer launched with the
     // programmatic attribute, must be complete and visible before the first global read: p.wait_inputs is set by the
     // host unless the caller vouches that the inputs were produced in ordinary stream order (see launch_dn_t).
@@ -1372,6 +1397,22 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 2 : 1) decode_nms_
     stamp<DBG>(p, b, 4);
     // P6 (the fp16 tables are dead now; the row scratch aliases them)
     pdl_wait();
+    if constexpr (GATHER != 0) {
+        // the gather buffer this step writes was last used three steps ago: wait until every rank has completed the
+        // previous step, i.e. has moved past everything it ran on that buffer (dist.PeerGather, back-pressure)
+        if (p.gwait_value > 0) {
+            if (warp == 0 && lane < p.gR) {
+                const long long t0 = clock64();
+                while (*reinterpret_cast<const volatile int *>(p.gwait_flags + lane) < p.gwait_value) {
+                    if (clock64() - t0 > p.gwait_cycles) { *p.gtimed_out = 1; break; }   // a dead peer must not hang the GPU
+                    __nanosleep(64);
+                }
+                // (no fence: what follows are STORES that depend on this load's outcome; a system-scope fence here would
+                // also flush the L1 the co-resident CTA streams its heads through)
+            }
+            __syncthreads();
+        }
+    }
     phase_output<MODE, THREADS, GATHER>(p, s, b);
     stamp<DBG>(p, b, 7);
 }

@@ -80,21 +80,24 @@ class _RawCuda:
 class PeerGather:
     """Decode + NMS fused with the all-gather of the detections (``b200yolo_decode_nms_gather``).
 
-    Every rank owns TWO gather buffers (parity = step & 1) -- ``dets[p]`` (world*n_local, K, 7) fp32 and
-    ``counts[p]`` (world*n_local,) int32 -- in memory the other ranks of the node map through CUDA IPC.  A step
-    post-processes this rank's shard; its output phase stores the kept rows into the buffers of ALL ranks (its own
-    and, over NVLink, the peers'), so the transfer overlaps the kernel instead of following it as a separate NCCL
-    all-gather.  ``fence`` is the cross-rank barrier after which every rank's buffer of that step holds the whole
-    batch: ONE small kernel (``b200yolo_peer_fence``: raise this rank's arrival flag everywhere, wait for all flags of
-    its own), which does not serialise the stream -- the next step's kernel starts under it and blocks before its
-    first store until the fence has completed.
+    Every rank owns THREE gather buffers (buffer = step % 3) -- ``dets`` (world*n_local, K, 7) fp32 and ``counts``
+    (world*n_local,) int32 each -- in memory the other ranks of the node map through CUDA IPC.  A step post-processes
+    this rank's shard; its output phase stores the kept rows into the buffers of ALL ranks (its own and, over NVLink,
+    the peers'), so the transfer overlaps the kernel instead of following it as a separate NCCL all-gather.
+    ``fence`` raises this rank's arrival flag in every rank's flag array once the step's kernel has completed and
+    waits until all flags of this rank's own array show the step: every rank's rows are then in this rank's buffer.
+    Inside ``run_steps`` a step is ONE kernel launch -- the arrival signal of step s rides on the launch of step s+1
+    -- so consecutive steps overlap exactly as they do on one GPU.
 
-    Back-pressure (why two buffers are enough).  A rank stores into parity p at step s only after its own fence of
-    step s-1 has completed, i.e. after EVERY rank has arrived at step s-1; a rank's arrival at step s-1 is
-    stream-ordered after everything it enqueued on the buffers of step s-2 (same parity p).  So: consume the result of
-    step s -- ``current()`` -- with ordinary kernel launches on the same stream BEFORE launching step s+1, and no
-    peer can overwrite what a consumer still reads.  One process per GPU on one NVSwitch box, at most 8 ranks;
-    ``close`` releases the mappings.  ``group`` may be a gloo group (the rendezvous only moves the IPC handles)."""
+    Back-pressure without a release signal.  The kernel of step s stores into buffer s % 3, last used by step s-3.
+    ``run_steps`` makes it wait, inside the kernel and before its first store, until EVERY rank has completed step
+    s-1; with the per-step API the fence of step s-1 precedes it in the stream.  A rank that has completed step s-1
+    has -- in stream order -- moved past whatever it enqueued on the buffer of step s-3.  So: consume the result of
+    step s -- ``current()`` -- after its fence with ordinary kernel launches on the same stream BEFORE launching step
+    s+1, and no peer can overwrite what a consumer still reads.  One process per GPU on one NVSwitch box, at most 8
+    ranks; ``close`` releases the mappings.  ``group`` may be a gloo group (the rendezvous only moves IPC handles)."""
+
+    NBUF = 3
 
     def __init__(self, n_local: int, cells_per_image: int, group=None, device: Optional[torch.device] = None):
         import ctypes as C
@@ -110,7 +113,7 @@ class PeerGather:
         row_bytes = (total * self.K * 7 * 4 + 255) // 256 * 256
         cnt_bytes = (total * 4 + 255) // 256 * 256
         self._par_bytes = row_bytes + cnt_bytes
-        self._flag_off = 2 * self._par_bytes            # int[8] arrival flags + int timed_out
+        self._flag_off = self.NBUF * self._par_bytes    # int[8] arrival flags + int timed_out
         nbytes = self._flag_off + 256
         with torch.cuda.device(self.device):
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -129,7 +132,7 @@ class PeerGather:
                 self._opened.append(p2.value)
             g = _lib.Gather()
             g.R, g.rank = self.world, self.rank
-            for par in range(2):
+            for par in range(self.NBUF):
                 for r in range(self.world):
                     g.peer_out[par][r] = self._bases[r] + par * self._par_bytes
                     g.peer_count[par][r] = self._bases[r] + par * self._par_bytes + row_bytes
@@ -139,17 +142,17 @@ class PeerGather:
             g.timeout_s = 5.0
             self._g = g
             self._out_ptrs = [(C.c_void_p * self.world)(*[self._bases[r] + par * self._par_bytes for r in range(self.world)])
-                              for par in range(2)]
+                              for par in range(self.NBUF)]
             self._cnt_ptrs = [(C.c_void_p * self.world)(*[self._bases[r] + par * self._par_bytes + row_bytes for r in range(self.world)])
-                              for par in range(2)]
+                              for par in range(self.NBUF)]
             self._flag_ptrs = (C.c_void_p * self.world)(*[b + self._flag_off for b in self._bases])
             self._step = 0        # steps launched so far
             self._fenced = 0      # steps whose fence has been launched
             raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
             self._dets = [raw[par * self._par_bytes:par * self._par_bytes + total * self.K * 7 * 4].view(torch.float32).view(total, self.K, 7)
-                          for par in range(2)]
+                          for par in range(self.NBUF)]
             self._counts = [raw[par * self._par_bytes + row_bytes:par * self._par_bytes + row_bytes + total * 4].view(torch.int32)
-                            for par in range(2)]
+                            for par in range(self.NBUF)]
             self._timed_out = raw[self._flag_off + 64:self._flag_off + 68].view(torch.int32)
             self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
@@ -157,11 +160,11 @@ class PeerGather:
     # ---- results of the most recently launched step (valid on the stream after its fence)
     @property
     def dets(self) -> torch.Tensor:
-        return self._dets[(self._step - 1) & 1]
+        return self._dets[(self._step - 1) % self.NBUF]
 
     @property
     def counts(self) -> torch.Tensor:
-        return self._counts[(self._step - 1) & 1]
+        return self._counts[(self._step - 1) % self.NBUF]
 
     def current(self) -> Tuple[torch.Tensor, torch.Tensor]:
         return self.dets, self.counts
@@ -181,23 +184,23 @@ class PeerGather:
     def decode_nms(self, head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
                    iou_thr: float = 0.45) -> None:
         """launch one step on the current stream; results are complete on every rank after ``fence()``"""
+        import ctypes as C
         from . import _lib
         if self._fenced != self._step:
             raise RuntimeError("PeerGather: fence() the previous step before launching the next one")
         head0, head1 = head0.contiguous(), head1.contiguous()
         N, A, H0, W0, H1, W1, aw = self._shape_args(head0, head1, anchor_wh2, num_classes)
-        par = self._step & 1
-        _lib.check(_lib.load().b200yolo_decode_nms_gather(
-            head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
-            float(np.float32(conf_thr)), float(iou_thr), self._out_ptrs[par], self._cnt_ptrs[par], self.world, self.rank,
-            torch.cuda.current_stream(self.device).cuda_stream))
+        one = (_lib.Batch * 1)(_lib.Batch(head0.data_ptr(), head1.data_ptr(), None, None, None))
+        _lib.check(_lib.load().b200yolo_decode_nms_gather_steps(
+            C.byref(self._g), one, 1, self._step, 0, N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
+            float(np.float32(conf_thr)), float(iou_thr), torch.cuda.current_stream(self.device).cuda_stream))
         self._step += 1
 
     def fence(self, collective: bool = False, timeout_s: float = 5.0) -> None:
-        """Stream-ordered barrier across the ranks for the step just launched: when it completes, every rank's launch
-        has completed and its rows are in every buffer (``check()`` tells whether a peer failed to arrive in time).
-        ``collective=True`` additionally runs a 1-element NCCL all-reduce (for comparison; the flags are still raised,
-        they carry the back-pressure)."""
+        """Cross-rank fence for the step just launched: this rank's arrival is announced to every rank once the step's
+        kernel has completed, and the stream then waits until every rank has announced the step -- all rows are in this
+        rank's buffer (``check()`` tells whether a peer failed to arrive in time).  ``collective=True`` additionally
+        runs a 1-element NCCL all-reduce (for comparison; the flags are still raised, they carry the back-pressure)."""
         from . import _lib
         lib = _lib.load()
         if self._fenced >= self._step:
@@ -210,9 +213,11 @@ class PeerGather:
             dist.all_reduce(self._flag, group=self.group)
 
     def run_steps(self, heads, anchor_wh2, num_classes: int, conf_thr: float, iou_thr: float = 0.45, plan=None):
-        """``len(heads)`` steps -- kernel + fence each -- issued from C in ONE call (``b200yolo_decode_nms_gather_steps``);
-        ``heads`` is a sequence of (head0, head1).  Returns a reusable plan (pass it back as ``plan`` to skip the set-up).
-        Only for pipelines without a per-step consumer (benchmarks, or consumers that read ``current()`` after the call)."""
+        """``len(heads)`` steps -- kernel + arrival signal + fence each -- issued from C in ONE call
+        (``b200yolo_decode_nms_gather_steps``); ``heads`` is a sequence of (head0, head1).  The fence of a step is issued
+        one step late (it then costs nothing) and the last one at the end of the call.  Returns a reusable plan (pass it
+        back as ``plan`` to skip the set-up).  For pipelines without a per-step consumer (benchmarks, or consumers that
+        read ``current()`` after the call)."""
         import ctypes as C
         from . import _lib
         if self._fenced != self._step:
@@ -229,7 +234,7 @@ class PeerGather:
                                                   float(iou_thr)), aw)
         arr, n = plan[0], plan[1]
         _lib.check(_lib.load().b200yolo_decode_nms_gather_steps(
-            C.byref(self._g), arr, n, self._step, *plan[3], torch.cuda.current_stream(self.device).cuda_stream))
+            C.byref(self._g), arr, n, self._step, 1, *plan[3], torch.cuda.current_stream(self.device).cuda_stream))
         self._step += n
         self._fenced = self._step
         return plan

@@ -18,6 +18,7 @@ from . import _lib
 LARGE_MAX_CELLS = 16384   # b200yolo_decode_nms_large: sort keys of one image in shared memory
 NMS_IOU_THRESHOLD = 0.45  # utils/box.py:28
 _WORKSPACES = {}  # (device index, stream) -> cached target-loss workspace tensor
+_HOST_WS = {}     # device index -> staging of decode_nms_host (b200yolo_decode_nms_host_ws)
 
 
 def scaled_anchors(anchors, img_size) -> np.ndarray:
@@ -258,8 +259,9 @@ class BatchPlan:
 def decode_nms_host(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_classes: int, conf_thr: float,
                     iou_thr: float = NMS_IOU_THRESHOLD, device: int = 0, out: Optional[torch.Tensor] = None,
                     out_count: Optional[torch.Tensor] = None):
-    """b200yolo_decode_nms_host: HOST tensors in (pinned recommended), HOST padded
-    detections out; chunked H2D / kernel / D2H pipeline inside the library."""
+    """b200yolo_decode_nms_host_ws: HOST tensors in (pinned recommended), HOST padded detections out (rows past an
+    image's count are not written); chunked H2D / kernel / D2H pipeline inside the library, device staging from
+    torch's allocator.  Not for concurrent use from several threads on one device (one staging buffer per device)."""
     if head0.is_cuda or head1.is_cuda:
         raise RuntimeError("decode_nms_host takes host tensors")
     head0, head1 = head0.contiguous(), head1.contiguous()
@@ -273,9 +275,15 @@ def decode_nms_host(head0: torch.Tensor, head1: torch.Tensor, anchor_wh2, num_cl
         out = torch.empty((N, K, 7), dtype=torch.float32).pin_memory()
     if out_count is None:
         out_count = torch.empty((N,), dtype=torch.int32).pin_memory()
-    _lib.check(_lib.load().b200yolo_decode_nms_host(
+    lib = _lib.load()
+    # device staging from torch's allocator (the library allocates nothing), kept per device and grown on demand
+    need = int(lib.b200yolo_decode_nms_host_workspace_bytes(N, A, num_classes, H0, W0, H1, W1))
+    ws = _HOST_WS.get(int(device))
+    if ws is None or ws.numel() < need:
+        ws = _HOST_WS[int(device)] = torch.empty((need,), dtype=torch.uint8, device=torch.device("cuda", int(device)))
+    _lib.check(lib.b200yolo_decode_nms_host_ws(
         head0.data_ptr(), head1.data_ptr(), N, A, num_classes, H0, W0, H1, W1, aw.ctypes.data,
-        float(np.float32(conf_thr)), float(iou_thr), out.data_ptr(), out_count.data_ptr(), int(device)))
+        float(np.float32(conf_thr)), float(iou_thr), out.data_ptr(), out_count.data_ptr(), ws.data_ptr(), ws.numel(), int(device)))
     return out, out_count
 
 
@@ -411,6 +419,31 @@ def target_loss_backward(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Ten
             gt_off.data_ptr(), int(G), float(np.float32(iou_thr)), int(max_gt), cell_state.data_ptr(), sums.data_ptr(),
             float(np.float32(iou_weighting)), go.data_ptr() if go is not None else None, grad.data_ptr(), _stream(head)))
     return grad
+
+
+class PackedTargets:
+    """Ground truth already on the device in the layout of ``b200yolo_target_loss``: ``gt`` (G, 5) fp32 rows
+    [cls(1-based), cx, cy, w, h] of all images back to back, ``gt_off`` (N+1,) int32 first row of every image,
+    ``max_gt`` an upper bound on the rows of one image.  ``YOLOLoss.forward(input, PackedTargets)`` skips the host-side
+    packing of the reference's list of CPU tensors (a data loader can build this once per batch for both heads)."""
+
+    def __init__(self, gt: torch.Tensor, gt_off: torch.Tensor, G: int, max_gt: int):
+        self.gt, self.gt_off, self.G, self.max_gt = gt, gt_off, int(G), int(max_gt)
+
+    @classmethod
+    def from_list(cls, targets, device) -> "PackedTargets":
+        gt, off, G, counts = pack_targets(targets, device)
+        return cls(gt, off, G, max(counts + [1]))
+
+
+def loss_finalize_dev(sums: torch.Tensor, iou_weighting: float) -> torch.Tensor:
+    """b200yolo_loss_finalize_dev: (16,) float64 device sums -> (7,) float32 device [loss, recall, avg_iou, obj, no_obj,
+    cls, count/N]; no host synchronisation."""
+    with _on_device(sums.device):
+        out = torch.empty((7,), dtype=torch.float32, device=sums.device)
+        _lib.check(_lib.load().b200yolo_loss_finalize_dev(sums.data_ptr(), float(np.float32(iou_weighting)), out.data_ptr(),
+                                                          _stream(sums)))
+    return out
 
 
 def loss_finalize(sums_host: np.ndarray, iou_weighting: float) -> np.ndarray:

@@ -33,6 +33,12 @@ class YOLOLoss(nn.Module):
     (models/mbv2_yolo.py:158-160) runs the fused decode + NMS kernel, so the reference's own call sites get the
     one-launch path.  ``patch_reference(..., fuse_inference=True)`` switches it on.
 
+    ``lazy_stats`` (attribute, default False): ``forward(input, targets)`` then performs NO host synchronisation: the
+    loss and the six statistics come back as 0-dim float32 device tensors (computed by ``b200yolo_loss_finalize_dev``),
+    and an out-of-range ground-truth box -- the reference's IndexError -- is reported by ``check()`` or by the next
+    ``forward`` call instead of this one.  ``targets`` may also be an ``ops.PackedTargets`` (ground truth already on the
+    device): together they take a 512-image step from 0.8 ms of host work to the kernels' own time.
+
     ``process_group``: optional torch.distributed group.  When set, the batch is a
     shard of a data-parallel batch and the 16 partial sums are all-reduced (NCCL)
     before the batch-global normalisation of yolo_loss.py:55,224,170-178.
@@ -55,6 +61,8 @@ class YOLOLoss(nn.Module):
         self.iou_weighting = iou_weighting
         self.process_group = process_group
         self.last_sums: Optional[torch.Tensor] = None
+        self.lazy_stats = False
+        self._pending_status: Optional[torch.Tensor] = None
 
     # yolo_loss.py:214
     def scaled_anchors(self):
@@ -79,11 +87,28 @@ class YOLOLoss(nn.Module):
                                                   want_ids=True)
         return ops._as_list(rows, count, ids)
 
+    @staticmethod
+    def _raise_status(st: int) -> None:
+        if st == 1:
+            raise IndexError("a GT box maps outside the grid or has a class outside [1, num_classes] "
+                             "(the reference raises IndexError at yolo_loss.py:149)")
+        if st == 2:
+            raise RuntimeError("more than 1024 GT boxes in one image are not supported by the target-assignment kernel")
+
+    def check(self) -> None:
+        """lazy_stats: raise what the last ``forward(input, targets)`` would have raised (one host read)"""
+        if self._pending_status is not None:
+            st, self._pending_status = int(self._pending_status.item()), None
+            self._raise_status(st)
+
     def forward(self, input: torch.Tensor, targets=None):
         if targets is None:
             return self.get_pred_boxes(input)
-        gt, gt_off, G, counts = ops.pack_targets(targets, input.device)
-        max_gt = max(counts + [1])
+        if isinstance(targets, ops.PackedTargets):
+            gt, gt_off, G, max_gt = targets.gt, targets.gt_off, targets.G, targets.max_gt
+        else:
+            gt, gt_off, G, counts = ops.pack_targets(targets, input.device)
+            max_gt = max(counts + [1])
         need_grad = torch.is_grad_enabled() and input.requires_grad
         x = input.detach()
         N, _, H, W = x.shape
@@ -95,13 +120,16 @@ class YOLOLoss(nn.Module):
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.process_group)
             dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.process_group)
         self.last_sums = sums
+        if self.lazy_stats:
+            self.check()                       # the previous call's status (already on its way, no stall in steady state)
+            self._pending_status = status
+            r = ops.loss_finalize_dev(sums, self.iou_weighting)
+            loss = r[0]
+            if need_grad:
+                loss = _LossGrad.apply(input, loss, self, gt, gt_off, G, max_gt, state, sums)
+            return loss, r[1], r[2], r[3], r[4], r[5], r[6]
         host = torch.cat((sums, status.to(torch.float64))).cpu().numpy()  # one D2H sync (the reference has ~5 per GT)
-        st = int(host[-1])
-        if st == 1:
-            raise IndexError("a GT box maps outside the grid or has a class outside [1, num_classes] "
-                             "(the reference raises IndexError at yolo_loss.py:149)")
-        if st == 2:
-            raise RuntimeError("more than 1024 GT boxes in one image are not supported by the target-assignment kernel")
+        self._raise_status(int(host[-1]))
         r = ops.loss_finalize(host[:_lib.S_COUNT], self.iou_weighting)
         loss = torch.tensor(r[0], dtype=torch.float32, device=input.device)
         if need_grad:

@@ -103,5 +103,17 @@ def test_bench_reference_arm_runs_without_gpu():
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["metric"] == "decode+NMS images/sec" and line["value"] > 0
     assert line["unit"] == "images/s" and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference Python where its snapshot (oracle/_ref) or checkout exists, else the C port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["name"] == "cfg2" and line["config"]["batch_per_gpu"] == 256   # same config dict as the CUDA arm
+
+
+def test_bench_config_dict_is_shared_by_both_arms():
+    """the driver compares the two arms' `config`: it is built by one function from the workload alone"""
+    import bench
+    for world in (1, 2, 8):
+        c = bench.workload_config("cfg2", bench.WORKLOADS["cfg2"], world)
+        assert c["global_batch"] == 256 * world and c["cells_per_image"] == 1815
+    assert bench.workload_config("cfg3", bench.WORKLOADS["cfg3"], 8)["batch_per_gpu"] == 128
+    assert bench.local_batch(bench.WORKLOADS["cfg5"], 8, 3) == 512

@@ -45,10 +45,19 @@ def anchor_tables(anchors, img_size):
     return np.stack([sa[MASK[0]], sa[MASK[1]]])
 
 
-def check_candidates(gpu_rows, gpu_ids, ora_rows, ora_ids, thr):
+def _class_scores(head, C, b, cid):
+    """float64 sigmoid of the C class logits of cell `cid` (= (a*H + j)*W + i) of image b"""
+    _, _, H, W = head.shape
+    a, pos = divmod(int(cid), H * W)
+    j, i = divmod(pos, W)
+    x = np.asarray(head[b, a * (5 + C) + 5:a * (5 + C) + 5 + C, j, i], np.float64)
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def check_candidates(gpu_rows, gpu_ids, ora_rows, ora_ids, thr, head=None, C=None):
     """same candidate set (cell ids) except cells whose conf sits within 1e-6 of the
-    threshold; common rows agree to 1e-5; class ids agree unless the top-2 class
-    scores are a near tie."""
+    threshold; common rows agree to 1e-5; class ids agree unless -- proven per mismatch
+    from the raw logits -- the two classes' scores coincide to within fp32 rounding."""
     for b in range(len(ora_rows)):
         gi, oi = gpu_ids[b], ora_ids[b]
         common, ga, oa = np.intersect1d(gi, oi, return_indices=True)
@@ -58,8 +67,13 @@ def check_candidates(gpu_rows, gpu_ids, ora_rows, ora_ids, thr):
                 assert abs(conf - np.float32(thr)) < 1e-6, f"image {b} cell {cid}: candidate set differs, conf={conf}"
         g, o = gpu_rows[b][ga], ora_rows[b][oa]
         np.testing.assert_allclose(g[:, :6], o[:, :6], rtol=RTOL, atol=ATOL)
-        bad = g[:, 6] != o[:, 6]
-        assert bad.sum() <= 2, f"{bad.sum()} class-id mismatches"  # near ties only, vanishingly rare
+        for r in np.nonzero(g[:, 6] != o[:, 6])[0]:
+            # a different argmax is only acceptable when the two classes' sigmoids are equal up to fp32 rounding
+            # (the reference's argmax over fp32 sigmoids is then decided by the last ulp of its own libm)
+            assert head is not None, "class-id mismatch and no head tensor to justify it"
+            sc = _class_scores(head, C, b, common[r])
+            sg, so = sc[int(g[r, 6])], sc[int(o[r, 6])]
+            assert abs(sg - so) <= 3e-7 * max(sg, so), f"image {b} cell {common[r]}: class {g[r, 6]} vs {o[r, 6]}, scores {sg} vs {so}"
         # order: ids strictly increasing = reference row-major order (yolo_loss.py:203)
         assert np.all(np.diff(gi) > 0)
 
@@ -82,7 +96,7 @@ def test_decode_head_vs_golden_and_oracle(case, cuda_device):
         aw = sa[d["mask"][i]]
         g_rows, g_ids = gpu_decode(head, aw, C, thr, cuda_device)
         o_rows, o_ids = oracle.decode_head(d[f"head{i}"], aw, C, thr)
-        check_candidates(g_rows, g_ids, o_rows, o_ids, thr)
+        check_candidates(g_rows, g_ids, o_rows, o_ids, thr, head=d[f"head{i}"], C=C)
         ref = unpack_ragged(d, f"p{i}")  # the reference's own rows
         assert [len(r) for r in g_rows] == [len(r) for r in ref]
         for a, b in zip(g_rows, ref):
@@ -176,6 +190,28 @@ def run_fused(h0, h1, tables, C, thr, dev):
     return [out[b, :cnt[b]] for b in range(len(cnt))], [idx[b, :cnt[b]] for b in range(len(cnt))]
 
 
+def fragile_decisions(cand, C, thr, tol=2e-5):
+    """How many of the reference's decisions on these candidate rows sit within `tol` (relative) of flipping: a conf at the
+    threshold, two neighbouring scores of a class in the sort, or a same-class pair whose IoU is at 0.45."""
+    n = int(np.sum(np.abs(cand[:, 4] - np.float32(thr)) <= tol * max(abs(thr), 1e-3)))
+    for c in range(C):
+        r = cand[cand[:, 6] == c]
+        if len(r) < 2:
+            continue
+        sc = np.sort((r[:, 5] * r[:, 4]).astype(np.float64))
+        n += int(np.sum(np.diff(sc) <= tol * sc[1:]))
+        x1, y1, x2, y2 = [r[:, k].astype(np.float64) for k in range(4)]
+        area = (x2 - x1) * (y2 - y1)
+        w = np.clip(np.minimum(x2[:, None], x2[None]) - np.maximum(x1[:, None], x1[None]), 0, None)
+        h = np.clip(np.minimum(y2[:, None], y2[None]) - np.maximum(y1[:, None], y1[None]), 0, None)
+        inter = w * h
+        with np.errstate(divide="ignore", invalid="ignore"):
+            iou = inter / (area[:, None] + area[None] - inter)
+        iu = iou[np.triu_indices(len(r), 1)]
+        n += int(np.sum(np.abs(iu - 0.45) <= tol * 0.45))
+    return n
+
+
 def check_fused_against_oracle(h0, h1, tables, C, thr, dev):
     """(1) the fused kernel's candidates == the stand-alone decode kernel's; (2) the
     oracle's NMS fed those SAME candidate rows keeps exactly the same cells in the
@@ -225,11 +261,16 @@ def test_fused_configs_vs_oracle(name, N, C, grids, anchors, img, thr, shift, cu
     # end-to-end against the pure-CPU oracle (its own sigmoid/exp): same kept cells
     # except near-threshold flips, floats to 1e-5
     o_det, o_ids = oracle.decode_nms(h0.numpy(), h1.numpy(), tables, C, thr)
-    n_same = sum(int(np.array_equal(a, b)) for a, b in zip(ids, o_ids))
-    assert n_same >= len(ids) - max(1, len(ids) // 50), f"{len(ids) - n_same} images differ from the CPU oracle"
-    for a, ia, b, ib in zip(dets, ids, o_det, o_ids):
+    o_r0, _ = oracle.decode_head(h0.numpy(), tables[0], C, thr)
+    o_r1, _ = oracle.decode_head(h1.numpy(), tables[1], C, thr)
+    for b, (a, ia, ob, ib) in enumerate(zip(dets, ids, o_det, o_ids)):
         if np.array_equal(ia, ib):
-            np.testing.assert_allclose(a[:, :6], b[:, :6], rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(a[:, :6], ob[:, :6], rtol=RTOL, atol=ATOL)
+        else:
+            # the decoded floats of the two implementations differ by an ulp or two (SFU vs libm), so a keep set may
+            # differ -- but only where the reference's own decision hangs on the last digits: prove it per image
+            assert fragile_decisions(np.concatenate((o_r0[b], o_r1[b]), 0), C, thr) > 0, \
+                f"image {b}: kept cells differ from the CPU oracle without a near-tie that explains it"
 
 
 @pytest.mark.parametrize("C,grids,anchors,img", [
@@ -542,11 +583,16 @@ def test_target_loss_vs_golden(case, cuda_device):
                                        d["img_size"].tolist(), float(d["ignore_thresh"][i]), float(d["iou_thresh"]),
                                        float(d["iou_weighting"]), cuda_device)
         np.testing.assert_allclose(res, d[f"tuple{i}"], rtol=RTOL, atol=1e-7)  # the reference's own 7-tuple
-        # assignment flags vs the reference mirror
+        # assignment TUPLES (b, t, k, gj, gi, best_n) vs the index-tracking mirror of the reference itself
+        # (tests/golden/make_golden.py, asserted there against the reference's own targets tensor)
         _, _, assign, _ = run_loss(d[f"head{i}"], targets, d["anchors"].tolist(), d["mask"][i].tolist(), C,
                                    d["img_size"].tolist(), float(d["ignore_thresh"][i]), float(d["iou_thresh"]),
                                    float(d["iou_weighting"]), cuda_device)
-        assert int(assign[:, :, 0].sum()) == len(d[f"assign{i}"])
+        offs = np.concatenate(([0], np.cumsum([len(t) for t in targets])))
+        got = [(b, t, k, assign[offs[b] + t, k, 1], assign[offs[b] + t, k, 2], assign[offs[b] + t, k, 3])
+               for b in range(len(targets)) for t in range(len(targets[b])) for k in range(assign.shape[1])
+               if assign[offs[b] + t, k, 0]]
+        assert np.array_equal(np.array(got, np.int64).reshape(-1, 6), np.asarray(d[f"assign{i}"], np.int64).reshape(-1, 6))
 
 
 def synth_targets(N, G, C, seed):
@@ -1040,3 +1086,84 @@ def test_channels_last_heads_equal_nchw(C, grids, anchors, img, thr, shift, quan
     assert np.array_equal(cnt, got[1].cpu().numpy()) and cnt.sum() > 0
     for i, k in enumerate(cnt):
         assert torch.equal(want[0][i, :k], got[0][i, :k]) and torch.equal(want[2][i, :k], got[2][i, :k])
+
+
+# ----------------------------------------------------------------------------- round-2 entry points
+def test_batches_entry_equals_single_calls(cuda_device):
+    """b200yolo_decode_nms_batches: every launch of the list (launch k > 0 overlaps its predecessor and skips the input
+    wait) writes exactly what a single call writes, indices included; then again with flag 32 (always wait)."""
+    C = 20
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    N = 40
+    batches, want = [], []
+    for k in range(5):
+        h0, h1 = make_heads(N, C, [(11, 11), (22, 22)], seed=300 + k, conf_shift=(-2.6 if k % 2 else 0.0))
+        d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+        want.append(ops.decode_nms_padded(d0, d1, tables, C, 0.3, want_idx=True))
+        batches.append((d0, d1, torch.zeros_like(want[-1][0]), torch.zeros_like(want[-1][1]), torch.zeros_like(want[-1][2])))
+    plan = ops.BatchPlan(batches, tables, C, 0.3)
+    for flags in (0, 32):
+        ops._lib.load().b200yolo_debug_set_flags(flags)
+        try:
+            for bt in batches:
+                bt[2].zero_(); bt[3].zero_(); bt[4].zero_()
+            plan.run()
+            torch.cuda.synchronize()
+        finally:
+            ops._lib.load().b200yolo_debug_set_flags(0)
+        for (o, c, i), bt in zip(want, batches):
+            assert torch.equal(c, bt[3]) and int(c.sum()) > 0
+            for b, k in enumerate(c.cpu().numpy()):
+                assert torch.equal(o[b, :k], bt[2][b, :k]) and torch.equal(i[b, :k], bt[4][b, :k])
+    plan.run(1, 2)   # a sub-range of the plan
+    torch.cuda.synchronize()
+    assert torch.equal(want[2][1], batches[2][3])
+
+
+def test_lazy_stats_and_packed_targets(cuda_device):
+    """YOLOLoss with lazy_stats (no host synchronisation, device scalars) and pre-packed device targets returns the
+    same seven values and the same gradient as the default (drop-in) path; an out-of-range box surfaces in check()."""
+    C = 20
+    head = make_heads(6, C, [(22, 22)], seed=11)[0]
+    targets = [torch.from_numpy(t) for t in synth_targets(6, [5, 0, 17, 3, 40, 1], C, seed=4)]
+    eager = b200.YOLOLoss(VOC_ANCHORS, MASK[1], C, [352, 352], 0.6, 0.55, iou_weighting=0.02)
+    lazy = b200.YOLOLoss(VOC_ANCHORS, MASK[1], C, [352, 352], 0.6, 0.55, iou_weighting=0.02)
+    lazy.lazy_stats = True
+    x0 = head.to(cuda_device).requires_grad_(True)
+    x1 = head.to(cuda_device).requires_grad_(True)
+    t0 = eager(x0, targets)
+    t1 = lazy(x1, ops.PackedTargets.from_list(targets, cuda_device))
+    assert all(isinstance(v, torch.Tensor) and v.is_cuda for v in t1)
+    lazy.check()
+    np.testing.assert_allclose([float(v) for v in t1], [float(v) for v in t0], rtol=2e-7, atol=1e-9)
+    t0[0].backward()
+    t1[0].backward()
+    assert torch.equal(x0.grad, x1.grad)
+    # deferred error: nothing raises at the call, check() (or the next call) does
+    bad = [torch.tensor([[1.0, 1.0, 0.5, 0.1, 0.1]])] + [torch.zeros(0, 5)] * 5
+    lazy(head.to(cuda_device), bad)
+    with pytest.raises(IndexError):
+        lazy.check()
+    lazy(head.to(cuda_device), bad)
+    with pytest.raises(IndexError):
+        lazy(head.to(cuda_device), targets)     # the previous call's status surfaces at the next call
+    lazy._pending_status = None
+
+
+def test_host_entry_copies_kept_rows_only(cuda_device):
+    """b200yolo_decode_nms_host_ws (caller-provided device staging): same rows and counts as the device call; rows past an
+    image's count are not written (only what can be kept travels back)."""
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    h0, h1 = make_heads(37, 20, [(11, 11), (22, 22)], seed=77, conf_shift=-2.6)
+    out = torch.full((37, 1815, 7), -7.0).pin_memory()
+    cnt = torch.zeros(37, dtype=torch.int32).pin_memory()
+    ops.decode_nms_host(h0.pin_memory(), h1.pin_memory(), tables, 20, 0.3, device=cuda_device.index or 0, out=out, out_count=cnt)
+    out_d, cnt_d = ops.decode_nms_padded(h0.to(cuda_device), h1.to(cuda_device), tables, 20, 0.3)
+    assert torch.equal(cnt, cnt_d.cpu())
+    mx = int(cnt.max())
+    assert 0 < mx < 400
+    for b, k in enumerate(cnt.numpy()):
+        assert torch.equal(out[b, :k], out_d[b, :k].cpu())
+    assert bool((out[:, mx:] == -7.0).all())          # never touched
+    d2h = int(ops._lib.load().b200yolo_host_last_d2h_bytes())
+    assert d2h <= 37 * 4 + 4 * 16 * 28 * mx * 37 // 37 * 37 and d2h < 37 * 1815 * 28 // 4
