@@ -814,6 +814,25 @@ def measure_loss(D, steps, warmup, peak):
     D.barrier()
     ms = D.max(time_loop(step, steps) / steps)
     D.barrier()
+    # the same step without host round trips: ground truth packed on the device once per batch (ops.PackedTargets, what a
+    # prefetching data loader hands over) and lazy_stats (loss and statistics stay device scalars; b200yolo_loss_finalize_dev)
+    from mobilenet_yolo_pytorch_b200 import ops as _ops
+    packed = _ops.PackedTargets.from_list(targets, D.dev)
+    for l in losses:
+        l.lazy_stats = True
+
+    def step_lazy(i):
+        h0, h1 = sets[i % R]
+        return losses[0](h0, packed)[0] + losses[1](h1, packed)[0]
+
+    for i in range(max(warmup, 3)):
+        step_lazy(i)
+    D.barrier()
+    ms_lazy = D.max(time_loop(step_lazy, steps) / steps)
+    for l in losses:
+        l.check()
+        l.lazy_stats = False
+    D.barrier()
     kres = time_loss(D.dev, N, G, steps=max(20, steps)) if D.rank == 0 else None
     D.barrier()
     if D.rank != 0:
@@ -823,6 +842,10 @@ def measure_loss(D, steps, warmup, peak):
             "module_api": {"ms_per_step": ms, "images_per_s": GB / (ms * 1e-3),
                            "note": "host target lists in, loss tensor + python stats out"
                                    + ("; all-reduce(SUM) of 16 doubles per head inside the step" if D.world > 1 else "")},
+            "module_api_device_targets_lazy_stats": {
+                "ms_per_step": ms_lazy, "images_per_s": GB / (ms_lazy * 1e-3),
+                "note": "YOLOLoss.forward(input, ops.PackedTargets) x2 with lazy_stats: no host synchronisation, loss tensor and "
+                        "statistics stay on the device"},
             "kernel_only": kres,
             "roofline": {"bound": "hbm", "achieved": kres["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kres["algorithmic_gbs"] / peak, "traffic": None,

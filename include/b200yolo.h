@@ -62,7 +62,9 @@ void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
  * environment variable): 1 = no L2 prefetch of head 0, 2 = no programmatic dependent launch (consecutive
  * launches then run in plain stream order), 8 = prefetch both heads, 16 = never
  * use the compile-time head shapes (every shape then runs the runtime-stride decode), 32 = always wait for the
- * previous kernel before the first global read. */
+ * previous kernel before the first global read, 64 = three CTAs of 384 threads per SM for the VOC-352 shape
+ * (experiment), 128 = "exact" decode: IEEE sigmoid / expf and a true division by the grid size, the reference's own
+ * operations, instead of the SFU forms and the multiplication by the reciprocal (profiles/exact_decode.py). */
 void b200yolo_debug_set_flags(int flags);
 
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that
@@ -133,6 +135,15 @@ int b200yolo_decode_nms_batches(const b200yolo_batch *batches, int n_batches, in
  * b200yolo_decode_nms_batches.  Process-wide; default 0.
  */
 void b200yolo_set_inputs_ready(int ready);
+
+/*
+ * Decode arithmetic of YOLOLoss.get_pred_boxes (models/yolo_loss.py:186-199).  Default (0): SFU sigmoid / exp and a
+ * multiplication by the reciprocal of the grid size -- within 1e-5 of the reference (the north star's tolerance).
+ * exact != 0: the reference's own operations -- 1/(1+expf(-x)), expf, a true division by the grid size -- so that
+ * decoded rows AND final detections are bit-identical to the unmodified reference running on device='cuda'
+ * (tests/test_reference_integration.py, profiles/exact_decode.py); costs ~3 % of the fused kernel.  Process-wide.
+ */
+void b200yolo_set_exact_decode(int exact);
 
 /*
  * The same for channels-last heads: head tensors laid out (N, H, W, A*(5+C)) in memory -- what cuDNN prefers for the

@@ -398,6 +398,9 @@ unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
 void b200yolo_debug_phase_stamps(unsigned long long *dev_buf) { g_dbg.store(dev_buf); }
 void b200yolo_debug_set_flags(int flags) { g_flags.store(flags); }
 void b200yolo_set_inputs_ready(int ready) { g_inputs_ready.store(ready ? 1 : 0); }
+void b200yolo_set_exact_decode(int exact) {
+    if (exact) g_flags.fetch_or(128); else g_flags.fetch_and(~128);
+}
 
 int b200yolo_max_cells(int device) {
     const int lim = smem_optin(device);
@@ -762,6 +765,7 @@ int b200yolo_target_loss(const float *head, int N, int A, int C, int H, int W, c
     p.ignore_thr = ignore_thr; p.iou_thr = iou_thr;
     // iou < thr <=> inter < thr/(1+thr) * (area_g + area_p); outside [0.01, 1] every cell takes the exact path
     p.ts = (ignore_thr >= 0.01f && ignore_thr <= 1.0f) ? (float)((double)ignore_thr / (1.0 + (double)ignore_thr)) * 1.220703125e-4f : 0.0f;
+    p.th16 = (ignore_thr >= 0.01f && ignore_thr <= 1.0f) ? (float)((double)ignore_thr / (1.0 + (double)ignore_thr) * 64.0 * (1.0 - 0.00390625)) : 0.0f;
     p.sums = sums; p.assign = assign; p.terms = terms; p.status = status; p.cell_state = cell_state;
     if (N > 0 && (!workspace || workspace_bytes < b200yolo_target_loss_workspace_bytes(N)))
         return fail(B200YOLO_EINVAL, "target_loss: workspace too small (%zu < %zu)", workspace_bytes,

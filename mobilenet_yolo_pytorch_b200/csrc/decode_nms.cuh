@@ -333,18 +333,18 @@ __device__ __forceinline__ void l2_prefetch_span(const void *ptr, size_t bytes) 
 }
 
 // class score of a cell whose top logits are closer than the sigmoid's evaluation
-// error: evaluate like the reference (sigmoid first, then first max, yolo_loss.py:198)
+// error: evaluate like the reference (IEEE sigmoid first, then first max, yolo_loss.py:198)
 __device__ __noinline__ float class_tie_break(const float *qc, int HW, int C, float lo, float m1, int i1, int *bi_out) {
     float best = -1.0f;
     int bi = 0;
     for (int cc = 0; cc < C; ++cc) {
         const float x = __ldg(qc + (size_t)cc * HW);
         if (!(x < lo)) {
-            const float sg = sigmoid_fast(x);
+            const float sg = sigmoid_f(x);   // (the IEEE form torch.sigmoid computes: the tie is decided like the reference's)
             if (sg > best) { best = sg; bi = cc; }
         }
     }
-    if (best < 0.0f) { best = sigmoid_fast(m1); bi = i1; }  // only NaN logits in the window
+    if (best < 0.0f) { best = sigmoid_f(m1); bi = i1; }  // only NaN logits in the window
     *bi_out = bi;
     return best;
 }
@@ -362,6 +362,19 @@ __device__ __forceinline__ float tie_window(float m, float *best) {
     return __fmul_rn(7.6293945e-06f, rcp_fast(__fmul_rn(e1, s1)));
 }
 
+// conf = sigmoid(tc) against the threshold (yolo_loss.py:189,201).  The SFU sigmoid is within ~4 ulp of the IEEE one, so
+// a cell whose confidence lands within 2e-6 (relative) of the threshold is re-evaluated with the IEEE form
+// 1/(1+expf(-x)) -- what torch.sigmoid computes -- and that value decides and is reported: the candidate SET then
+// matches the reference's own arithmetic.  exact (flag 128): every cell takes the IEEE form.
+constexpr float kConfBand = 2e-6f;
+
+__device__ __forceinline__ bool conf_pass(float tc, float thr, bool exact, float *conf_out) {
+    float conf = exact ? sigmoid_f(tc) : sigmoid_fast(tc);
+    if (!exact && fabsf(__fsub_rn(conf, thr)) <= __fmul_rn(kConfBand, fabsf(thr))) conf = sigmoid_f(tc);
+    *conf_out = conf;
+    return conf > thr;
+}
+
 // ---------------------------------------------------------------------------
 // P1: decode every cell of one head, single pass.  All 5+C plane loads of a cell are
 // issued before the first use.
@@ -370,10 +383,14 @@ __device__ __forceinline__ float tie_window(float m, float *best) {
 template <int MODE>
 __device__ __forceinline__ void emit_candidate(const DNParams &p, const Smem &s, const HeadDesc &hd, int cid, int a, int i, int j,
                                                float tx, float ty, float tw, float th, float conf, float best, int bi) {
-    const float sx = sigmoid_fast(tx), sy = sigmoid_fast(ty);    // :187
-    const float ew = exp_fast(tw), eh = exp_fast(th);            // :188
-    const float cx = __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194 (x * 1/W)
-    const float cy = __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+    // flag 128 ("exact"): the reference's own operations -- IEEE sigmoid / expf and a true division by the grid size --
+    // instead of the SFU forms and the multiplication by 1/W (profiles/exact_decode.py: what bit-equality with the
+    // reference on CUDA costs)
+    const bool exact = (p.flags & 128) != 0;
+    const float sx = exact ? sigmoid_f(tx) : sigmoid_fast(tx), sy = exact ? sigmoid_f(ty) : sigmoid_fast(ty);    // :187
+    const float ew = exact ? expf(tw) : exp_fast(tw), eh = exact ? expf(th) : exp_fast(th);                      // :188
+    const float cx = exact ? __fdiv_rn(__fadd_rn(sx, (float)i), hd.fW) : __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194
+    const float cy = exact ? __fdiv_rn(__fadd_rn(sy, (float)j), hd.fH) : __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
     const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
     const float bh = __fmul_rn(eh, hd.ah[a]);
     float4 bx;
@@ -424,8 +441,8 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
         bool pass = false;
         if (active) {
             const int cid = cid0 + local;
-            const float conf = sigmoid_fast(tc);  // yolo_loss.py:189,197
-            pass = conf > p.conf_thr;             // :201 (threshold already rounded to fp32)
+            float conf;
+            pass = conf_pass(tc, p.conf_thr, (p.flags & 128) != 0, &conf);   // yolo_loss.py:189,197,201 (threshold already rounded to fp32)
             if (pass) {
                 float m1 = x[0];
 #pragma unroll
@@ -440,6 +457,7 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
                 int bi = nb ? __ffs(nb) - 1 : 0;
                 const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
                 if (CT > 1 && tie) best = class_tie_break(q + 5 * HWT, HWT, CT, lo, m1, bi, &bi);
+                else if (p.flags & 128) best = sigmoid_f(m1);
                 const int j = pos / WT;
                 emit_candidate<MODE>(p, s, hd, cid, a, pos - j * WT, j, tx, ty, tw, th, conf, best, bi);
             } else if (MODE == MODE_FUSED) {
@@ -503,8 +521,7 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
                 }
                 qb += (uint64_t)st * (uint32_t)nv;
                 if (c0 == 0) {
-                    conf = sigmoid_fast(tc);   // yolo_loss.py:189,197
-                    pass = conf > p.conf_thr;  // :201 (threshold already rounded to fp32)
+                    pass = conf_pass(tc, p.conf_thr, (p.flags & 128) != 0, &conf);   // yolo_loss.py:189,197,201
                 }
                 float cm = x[0];
 #pragma unroll
@@ -538,6 +555,7 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
             if (pass) {
                 int bi = i1;
                 if (C > 1 && tie) best = class_tie_break(q + 5 * HW, HW, C, __fsub_rn(m1, win), m1, i1, &bi);
+                else if (p.flags & 128) best = sigmoid_f(m1);
                 const int j = fastdiv(pos, hd.magicW);
                 emit_candidate<MODE>(p, s, hd, cid, a, pos - j * hd.W, j, tx, ty, tw, th, conf, best, bi);
             } else if (MODE == MODE_FUSED) {
@@ -603,8 +621,8 @@ __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &
             const int j = fastdiv(pos, hd.magicW), i = pos - j * hd.W;
             const int cid = cid0 + a * hd.HW + pos;          // reference order: (a*H + j)*W + i
             const float *xs = scr + lane * attrs;
-            const float conf = sigmoid_fast(xs[4]);         // yolo_loss.py:189,197
-            if (conf > p.conf_thr) {                        // :201
+            float conf;
+            if (conf_pass(xs[4], p.conf_thr, (p.flags & 128) != 0, &conf)) {   // yolo_loss.py:189,197,201
                 float best;
                 int bi;
                 if constexpr (CT > 0) {
@@ -623,6 +641,7 @@ __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &
                     bi = nb ? __ffs(nb) - 1 : 0;
                     const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
                     if (CT > 1 && tie) best = class_tie_break(hb + (size_t)m * attrs + 5, 1, CT, lo, m1, bi, &bi);
+                    else if (p.flags & 128) best = sigmoid_f(m1);
                 } else {
                     float m1 = xs[5];
                     for (int c = 1; c < C; ++c) m1 = fmaxf(m1, xs[5 + c]);
@@ -637,6 +656,7 @@ __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &
                     }
                     bi = max(bi, 0);
                     if (C > 1 && nnear != 1) best = class_tie_break(hb + (size_t)m * attrs + 5, 1, C, lo, m1, bi, &bi);
+                    else if (p.flags & 128) best = sigmoid_f(m1);
                 }
                 emit_candidate<MODE_FUSED>(p, s, hd, cid, a, i, j, xs[0], xs[1], xs[2], xs[3], conf, best, bi);
             } else {

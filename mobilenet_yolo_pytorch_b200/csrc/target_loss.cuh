@@ -60,6 +60,7 @@ struct TLParams {
     int G;
     float ignore_thr, iou_thr;
     float ts;        // ignore_thr/(1+ignore_thr) * 2^-13 (0: the divide-free test is off)
+    float th16;      // ignore_thr/(1+ignore_thr) * 64 * (1 - 2^-8): the fp16 prefilter's area factor (0: prefilter off)
     double *sums;
     double *partial;  // [N][S][kTLSums]
     int *assign;      // [G][A][4] or null
@@ -92,6 +93,7 @@ struct TLSmem {
     uint8_t *flag;     // [cells] cell is assigned
     double *red;       // [kTLSums][kTLWarps]
     int *misc;         // [16]: 0 nE, 1 any degenerate GT, 2 status, 3 nU, 4..11 warp totals of the block scans
+    H16Tile *gh16;     // [ceil(gcap/32)] conservative fp16 images of the GT boxes (decode_nms.cuh, h16_prefilter)
     double4 *contrib;  // backward: [A*gcap] box-gradient contribution of every assignment
 };
 
@@ -100,6 +102,7 @@ __host__ __device__ inline uint32_t tl_up16(uint32_t v) { return (v + 15u) / 16u
 __host__ __device__ inline uint32_t tl_smem_bytes(int cells, int gcap, int A, bool backward = false) {
     const uint32_t g = (uint32_t)gcap, l = (uint32_t)(gcap * A);
     uint32_t o = 36 * g + 8 * l + tl_up16(2 * l) + tl_up16((uint32_t)cells) + 8 * kTLSums * kTLWarps + 64;
+    o = tl_up16(o) + (uint32_t)sizeof(H16Tile) * ((g + 31) / 32);
     if (backward) o += 32 * l;
     return o;
 }
@@ -118,6 +121,8 @@ __device__ __forceinline__ TLSmem tl_carve(unsigned char *base, int cells, int g
     s.flag = reinterpret_cast<uint8_t *>(base + o); o += tl_up16((uint32_t)cells);
     s.red = reinterpret_cast<double *>(base + o); o += 8 * kTLSums * kTLWarps;
     s.misc = reinterpret_cast<int *>(base + o); o += 64;
+    o = tl_up16(o);
+    s.gh16 = reinterpret_cast<H16Tile *>(base + o); o += (uint32_t)sizeof(H16Tile) * ((g + 31) / 32);
     s.contrib = reinterpret_cast<double4 *>(base + o);
     return s;
 }
@@ -184,6 +189,34 @@ __device__ __forceinline__ float4 tl_decode_box(float tx, float ty, float tw, fl
 __device__ __forceinline__ float tl_iou(const float4 &a, float area_a, const float4 &b, float area_b) {
     const float inter = pair_inter(a, b);
     return __fdiv_rn(inter, pair_union(area_a, area_b, inter));
+}
+
+// conservative fp16 image of a box (decode_nms.cuh: h16_store / h16_prefilter): outward-rounded coordinates and a
+// lower bound of t*area*64; boxes the fp16 format cannot hold get TA = -inf ("always maybe")
+__device__ __forceinline__ void tl_h16_put(H16Tile *tiles, int idx, const float4 &b, float area, float th16) {
+    H16Tile &tile = tiles[idx >> 5];
+    const int k = idx & 15, hi = (idx >> 4) & 1;
+    const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    const bool ok = th16 > 0.0f && area >= 3.814697265625e-06f && area <= 256.0f && big <= 8.0f;   // (false for NaN)
+    __half *xy = reinterpret_cast<__half *>(&tile.xy[k]);
+    xy[0 + hi] = ok ? __float2half_rd(__fmul_rn(b.x, kH16SX)) : __ushort_as_half((unsigned short)0);
+    xy[2 + hi] = ok ? __float2half_rd(__fmul_rn(b.y, kH16SY)) : __ushort_as_half((unsigned short)0);
+    xy[4 + hi] = ok ? __float2half_ru(__fmul_rn(b.z, kH16SX)) : __ushort_as_half((unsigned short)0);
+    xy[6 + hi] = ok ? __float2half_ru(__fmul_rn(b.w, kH16SY)) : __ushort_as_half((unsigned short)0);
+    reinterpret_cast<__half *>(&tile.ta[k])[hi] = ok ? __float2half_rd(__fmul_rn(area, th16)) : __ushort_as_half((unsigned short)0xfc00);
+}
+
+__device__ __forceinline__ H16Row tl_h16_row(const float4 &b, float area, float th16) {
+    const float big = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    const bool ok = th16 > 0.0f && area >= 3.814697265625e-06f && area <= 256.0f && big <= 8.0f;
+    auto dup = [](__half h) { const uint32_t u = (uint32_t)__half_as_ushort(h); return u | (u << 16); };
+    H16Row r;
+    r.x1 = ok ? dup(__float2half_rd(__fmul_rn(b.x, kH16SX))) : 0u;
+    r.y1 = ok ? dup(__float2half_rd(__fmul_rn(b.y, kH16SY))) : 0u;
+    r.x2 = ok ? dup(__float2half_ru(__fmul_rn(b.z, kH16SX))) : 0u;
+    r.y2 = ok ? dup(__float2half_ru(__fmul_rn(b.w, kH16SY))) : 0u;
+    r.nta = ok ? (dup(__float2half_rd(__fmul_rn(area, th16))) ^ 0x80008000u) : 0x7c007c00u;   // -TA, or +inf
+    return r;
 }
 
 // t * area * 2^-13 for the divide-free test; NaN when the box must take the exact path
@@ -271,6 +304,7 @@ __device__ __forceinline__ void tl_match_gt(const TLParams &p, int g0, int nG, b
             s.gbox[t] = bx;
             s.garea[t] = barea;
             s.gta[t] = bta;
+            tl_h16_put(s.gh16, t, bx, barea, p.th16);
             if (bta != bta) s.misc[1] = 1;
             const int cls = (int)__fsub_rn(gc, 1.0f);                   // :131,147
             s.gcls[t] = cls;
@@ -430,18 +464,26 @@ __global__ void __launch_bounds__(kTLThreads) target_loss_kernel(const TLParams 
             const float4 pb = tl_decode_box(tx, ty, tw, th, i, j, p.fW, p.fH, p.aw_all[p.mask[a]], p.ah_all[p.mask[a]]);
             const float pa = box_area(pb);
             const float pta = tl_ta(pb, pa, p.ts);
-            // divide-free pass over the GT boxes: d > 0 <=> iou < thr
+            // Pass over the GT boxes.  First the conservative fp16 prefilter of decode_nms.cuh, two GT boxes per
+            // instruction: a clear bit PROVES iou < ignore_thr * (1 - 0.003) for that box; then, only for the boxes it
+            // cannot rule out, the divide-free fp32 test (d > 0 <=> iou < thr) with its guard band.
             float dmin = INFINITY, m = INFINITY;
-#pragma unroll 4
-            for (int t = 0; t < nG; ++t) {
-                const float4 gb = s_gbox[t];
-                const float w = __fsub_rn(fminf(pb.z, gb.z), fmaxf(pb.x, gb.x));
-                const float h = __fsub_rn(fminf(pb.w, gb.w), fmaxf(pb.y, gb.y));
-                const float ws = __saturatef(__fmul_rn(w, 1.220703125e-4f));  // max(w,0) * 2^-13
-                const float sum = __fadd_rn(pta, s_gta[t]);
-                const float d = __fmaf_rn(-ws, h, sum);
-                dmin = fminf(dmin, d);
-                m = fminf(m, __fmaf_rn(sum, -kTLEps, fabsf(d)));
+            const H16Row row = tl_h16_row(pb, pa, p.th16);
+            for (int t0 = 0; t0 < nG; t0 += 32) {
+                const int ncol = min(32, nG - t0);
+                uint32_t maybe = h16_prefilter(sm.gh16[t0 >> 5], row, ncol) & ((ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u));
+                while (maybe) {
+                    const int t = t0 + __ffs(maybe) - 1;
+                    maybe &= maybe - 1u;
+                    const float4 gb = s_gbox[t];
+                    const float w = __fsub_rn(fminf(pb.z, gb.z), fmaxf(pb.x, gb.x));
+                    const float h = __fsub_rn(fminf(pb.w, gb.w), fmaxf(pb.y, gb.y));
+                    const float ws = __saturatef(__fmul_rn(w, 1.220703125e-4f));  // max(w,0) * 2^-13
+                    const float sum = __fadd_rn(pta, s_gta[t]);
+                    const float d = __fmaf_rn(-ws, h, sum);
+                    dmin = fminf(dmin, d);
+                    m = fminf(m, __fmaf_rn(sum, -kTLEps, fabsf(d)));
+                }
             }
             bool below;
             if (gt_degenerate || pta != pta || !(m > 0.0f)) below = tl_below_exact(s_gbox, s_garea, nG, pb, pa, p.ignore_thr);

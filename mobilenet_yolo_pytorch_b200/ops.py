@@ -21,6 +21,12 @@ _WORKSPACES = {}  # (device index, stream) -> cached target-loss workspace tenso
 _HOST_WS = {}     # device index -> staging of decode_nms_host (b200yolo_decode_nms_host_ws)
 
 
+def set_exact_decode(exact: bool) -> None:
+    """b200yolo_set_exact_decode: decode with the reference's own operations (IEEE sigmoid / expf, true division) so that
+    rows and detections are bit-identical to the reference on device='cuda'; ~3 % slower.  Process-wide, default off."""
+    _lib.load().b200yolo_set_exact_decode(1 if exact else 0)
+
+
 def scaled_anchors(anchors, img_size) -> np.ndarray:
     """yolo_loss.py:214: python-double division, rounded to fp32 when it enters a
     FloatTensor (pre_maps :67-68)."""

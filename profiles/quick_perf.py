@@ -38,8 +38,9 @@ for name in a.workloads:
     torch.cuda.synchronize()
     kept = float(cnt.sum().item())
     res = {}
+    base_flags = int(os.environ.get("B200YOLO_FLAGS", "0"))
     for label, flags in (("overlapped", 0), ("stream_order", 2)):
-        _lib.load().b200yolo_debug_set_flags(flags)
+        _lib.load().b200yolo_debug_set_flags(flags | base_flags)
         plan.run(0, min(10, a.steps))
         torch.cuda.synchronize()
         best = 1e9
@@ -51,7 +52,7 @@ for name in a.workloads:
             e1.synchronize()
             best = min(best, e0.elapsed_time(e1) / a.steps * 1e3)
         res[label] = best
-    _lib.load().b200yolo_debug_set_flags(0)
+    _lib.load().b200yolo_debug_set_flags(base_flags)
     algo = in_bytes + 28 * kept + 4 * N
     print(f"{name:12s} N={N} kept/img={kept / N:7.1f}  overlapped {res['overlapped']:7.2f} us ({algo / res['overlapped'] / 1e3:6.0f} GB/s, "
           f"frac {algo / res['overlapped'] / 1e3 / peak:.3f})  stream order {res['stream_order']:7.2f} us  "

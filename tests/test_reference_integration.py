@@ -160,3 +160,47 @@ def test_config1_training_tuple_and_backward_through_the_real_model():
     for g, h in ((g0, h0), (g1, h1)):
         assert np.abs(g).max() > 0
         assert np.abs(g - h).max() <= 1e-4 * np.abs(g).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("conf_shift", [0.0, -2.6])
+def test_exact_decode_is_bit_equal_to_the_reference_on_cuda(conf_shift):
+    """SURVEY section 7's first-choice test: the unmodified reference on device='cuda' (ATen kernels + torchvision's CUDA
+    nms, driven per (image, class) by utils/box.py:16-29) against this library on the same head tensors -- torch.equal
+    on the decoded rows of both heads AND on the final detections -- with the exact decode switched on
+    (ops.set_exact_decode: the reference's own IEEE operations).  The default decode is within 1e-5 of the same."""
+    _need_reference()
+    import mobilenet_yolo_pytorch_b200 as b200
+    from mobilenet_yolo_pytorch_b200 import ops
+    ref = ref_loader.load()
+    dev = torch.device("cuda", 0)
+    N, C = 48, 20
+    g = torch.Generator().manual_seed(5)
+    h0 = torch.randn(N, 75, 11, 11, generator=g)
+    h1 = torch.randn(N, 75, 22, 22, generator=g)
+    if conf_shift:
+        h0.view(N, 3, 25, 11, 11)[:, :, 4] += conf_shift
+        h1.view(N, 3, 25, 22, 22)[:, :, 4] += conf_shift
+    h0, h1 = h0.to(dev), h1.to(dev)
+    r_losses = [ref.YOLOLoss(b200_anchors(), MASK[i], C, [352, 352], 0.6, 0.55, val_conf=0.3) for i in range(2)]
+    with torch.no_grad():
+        preds = [r_losses[0](h0), r_losses[1](h1)]
+        want = ref.nms(preds, C)
+    losses = [b200.YOLOLoss(b200_anchors(), MASK[i], C, [352, 352], 0.6, 0.55, val_conf=0.3) for i in range(2)]
+    ops.set_exact_decode(True)
+    try:
+        got_preds = [losses[0](h0), losses[1](h1)]
+        dets = b200.decode_nms(h0, h1, losses, C)
+        sep = b200.nms(got_preds, C)
+    finally:
+        ops.set_exact_decode(False)
+    for i in range(2):
+        for b in range(N):
+            assert torch.equal(got_preds[i][b], preds[i][b]), f"head {i} image {b}: decoded rows are not bit-equal"
+    for b in range(N):
+        assert torch.equal(dets[b], want[b]), f"image {b}: fused detections are not bit-equal to the reference on CUDA"
+        assert torch.equal(sep[b], want[b])
+    fast = b200.decode_nms(h0, h1, losses, C)
+    for b in range(N):
+        assert fast[b].shape == want[b].shape and torch.equal(fast[b][:, 6], want[b][:, 6])
+        assert torch.allclose(fast[b], want[b], rtol=RTOL, atol=ATOL)
