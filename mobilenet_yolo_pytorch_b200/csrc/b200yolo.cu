@@ -109,10 +109,24 @@ constexpr int kTier1x64 = 162 * 1024;
 template <int MODE, int THREADS, int SHAPE>
 int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     static std::mutex mu;
-    static int configured[3][64] = {{0}, {0}, {0}};  // smem size opted into, per kernel variant and device
+    static int configured[5][64] = {{0}, {0}, {0}, {0}, {0}};  // smem size opted into, per kernel variant and device
     using Kern = void (*)(const DNParams, const SmemLayout);
     Kern kern = decode_nms_kernel<MODE, THREADS, SHAPE, 0>;
     int variant = 0;
+    if constexpr (SHAPE == 0 && MODE != MODE_NMS && (THREADS == 512 || THREADS == 1024)) {
+        if (p.flags & 128) {   // exact decode (b200yolo_set_exact_decode): the runtime-shape variants carry it
+            if constexpr (MODE == MODE_FUSED) {
+                if (p.gR > 0) { kern = decode_nms_kernel<MODE, THREADS, 0, 1, false, true>; variant = 4; }
+                else { kern = decode_nms_kernel<MODE, THREADS, 0, 0, false, true>; variant = 3; }
+            } else {
+                kern = decode_nms_kernel<MODE, THREADS, 0, 0, false, true>;
+                variant = 3;
+            }
+        }
+    }
+    if (variant >= 3) {
+        // (fall through to the launch)
+    } else
     if constexpr (MODE == MODE_FUSED) {
         if (p.gR > 0) {  // fused all-gather: the output phase stores into every rank's buffer
             kern = decode_nms_kernel<MODE, THREADS, SHAPE, 1>;
@@ -134,7 +148,7 @@ int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     // programmatic dependent launch: consecutive launches of this kernel overlap (decode_nms.cuh, pdl_trigger / pdl_wait)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)p.N + ((variant == 1 && p.gsignal > 0) ? 1u : 0u));   // (+ the signalling CTA, decode_nms.cuh)
+    cfg.gridDim = dim3((unsigned)p.N + (((variant == 1 || variant == 4) && p.gsignal > 0) ? 1u : 0u));   // (+ the signalling CTA, decode_nms.cuh)
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = st;
@@ -175,18 +189,18 @@ int launch_dn_shape(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) 
             return fail(B200YOLO_EUNSUPPORTED, "decode_nms_nhwc: %d cells per image leave no room for the channels-last staging "
                         "(convert the heads to NCHW)", p.K);
         p.nhwc = nwarps;
-        if (THREADS == 512 && !(p.flags & 16)) {
+        if (THREADS == 512 && !(p.flags & (16 | 128))) {
             constexpr bool kOn = (MODE == MODE_FUSED && THREADS == 512);
             if (p.C == 20) return launch_dn_t<MODE, THREADS, kOn ? 21 : 0>(p, L, dev, st);
             if (p.C == 10) return launch_dn_t<MODE, THREADS, kOn ? 22 : 0>(p, L, dev, st);
         }
     }
-    if (MODE == MODE_FUSED && !(p.flags & 16) && !p.nhwc) {  // flag 16: force the runtime-shape path (tests)
+    if (MODE == MODE_FUSED && !(p.flags & (16 | 128)) && !p.nhwc) {  // flag 16: force the runtime-shape path (tests); 128: exact decode
         if (THREADS == 512 && shape_is<1>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 1 : 0>(p, L, dev, st);
         if (THREADS == 512 && shape_is<2>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 512) ? 2 : 0>(p, L, dev, st);
         if (THREADS == 1024 && shape_is<3>(p)) return launch_dn_t<MODE, THREADS, (MODE == MODE_FUSED && THREADS == 1024) ? 3 : 0>(p, L, dev, st);
     }
-    if (MODE == MODE_DECODE && THREADS == 512 && !(p.flags & 16)) {
+    if (MODE == MODE_DECODE && THREADS == 512 && !(p.flags & (16 | 128))) {
         constexpr bool kOn = (MODE == MODE_DECODE && THREADS == 512);
         if (head_is<11>(p)) return launch_dn_t<MODE, THREADS, kOn ? 11 : 0>(p, L, dev, st);
         if (head_is<12>(p)) return launch_dn_t<MODE, THREADS, kOn ? 12 : 0>(p, L, dev, st);

@@ -365,12 +365,15 @@ __device__ __forceinline__ float tie_window(float m, float *best) {
 // conf = sigmoid(tc) against the threshold (yolo_loss.py:189,201).  The SFU sigmoid is within ~4 ulp of the IEEE one, so
 // a cell whose confidence lands within 2e-6 (relative) of the threshold is re-evaluated with the IEEE form
 // 1/(1+expf(-x)) -- what torch.sigmoid computes -- and that value decides and is reported: the candidate SET then
-// matches the reference's own arithmetic.  exact (flag 128): every cell takes the IEEE form.
+// matches the reference's own arithmetic.  EXACT (b200yolo_set_exact_decode): every cell takes the IEEE form.
 constexpr float kConfBand = 2e-6f;
 
-__device__ __forceinline__ bool conf_pass(float tc, float thr, bool exact, float *conf_out) {
-    float conf = exact ? sigmoid_f(tc) : sigmoid_fast(tc);
-    if (!exact && fabsf(__fsub_rn(conf, thr)) <= __fmul_rn(kConfBand, fabsf(thr))) conf = sigmoid_f(tc);
+__device__ __noinline__ float sigmoid_ieee_call(float x) { return sigmoid_f(x); }   // (out of line: the hot path keeps a branch only)
+
+template <bool EXACT>
+__device__ __forceinline__ bool conf_pass(float tc, float thr, float *conf_out) {
+    float conf = EXACT ? sigmoid_f(tc) : sigmoid_fast(tc);
+    if (!EXACT && fabsf(__fsub_rn(conf, thr)) <= __fmul_rn(kConfBand, fabsf(thr))) conf = sigmoid_ieee_call(tc);
     *conf_out = conf;
     return conf > thr;
 }
@@ -380,17 +383,16 @@ __device__ __forceinline__ bool conf_pass(float tc, float thr, bool exact, float
 // issued before the first use.
 // ---------------------------------------------------------------------------
 // box arithmetic + records of one passing cell (yolo_loss.py:186-199, 243-247)
-template <int MODE>
+template <int MODE, bool EXACT>
 __device__ __forceinline__ void emit_candidate(const DNParams &p, const Smem &s, const HeadDesc &hd, int cid, int a, int i, int j,
                                                float tx, float ty, float tw, float th, float conf, float best, int bi) {
-    // flag 128 ("exact"): the reference's own operations -- IEEE sigmoid / expf and a true division by the grid size --
-    // instead of the SFU forms and the multiplication by 1/W (profiles/exact_decode.py: what bit-equality with the
-    // reference on CUDA costs)
-    const bool exact = (p.flags & 128) != 0;
-    const float sx = exact ? sigmoid_f(tx) : sigmoid_fast(tx), sy = exact ? sigmoid_f(ty) : sigmoid_fast(ty);    // :187
-    const float ew = exact ? expf(tw) : exp_fast(tw), eh = exact ? expf(th) : exp_fast(th);                      // :188
-    const float cx = exact ? __fdiv_rn(__fadd_rn(sx, (float)i), hd.fW) : __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194
-    const float cy = exact ? __fdiv_rn(__fadd_rn(sy, (float)j), hd.fH) : __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
+    // EXACT (b200yolo_set_exact_decode; its own instantiations, the default kernels carry none of it): the reference's
+    // own operations -- IEEE sigmoid / expf and a true division by the grid size -- instead of the SFU forms and the
+    // multiplication by 1/W: rows bit-identical to the reference on CUDA (profiles/exact_decode.py)
+    const float sx = EXACT ? sigmoid_f(tx) : sigmoid_fast(tx), sy = EXACT ? sigmoid_f(ty) : sigmoid_fast(ty);    // :187
+    const float ew = EXACT ? expf(tw) : exp_fast(tw), eh = EXACT ? expf(th) : exp_fast(th);                      // :188
+    const float cx = EXACT ? __fdiv_rn(__fadd_rn(sx, (float)i), hd.fW) : __fmul_rn(__fadd_rn(sx, (float)i), hd.rW);  // :194
+    const float cy = EXACT ? __fdiv_rn(__fadd_rn(sy, (float)j), hd.fH) : __fmul_rn(__fadd_rn(sy, (float)j), hd.rH);
     const float bw = __fmul_rn(ew, hd.aw[a]);                    // :195
     const float bh = __fmul_rn(eh, hd.ah[a]);
     float4 bx;
@@ -412,7 +414,7 @@ __device__ __forceinline__ void emit_candidate(const DNParams &p, const Smem &s,
 // is the first decode of the kernel -- the block barrier that orders the zeroing of the histogram before
 // the first shared atomic is taken AFTER the first round's loads are in flight (hides ~0.5 us of start-up
 // behind the first HBM round trip).
-template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST, bool DBG>
+template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST, bool DBG, bool EXACT>
 __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     static_assert(CT >= 1 && CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
     const int tid = threadIdx.x, lane = tid & 31;
@@ -442,7 +444,7 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
         if (active) {
             const int cid = cid0 + local;
             float conf;
-            pass = conf_pass(tc, p.conf_thr, (p.flags & 128) != 0, &conf);   // yolo_loss.py:189,197,201 (threshold already rounded to fp32)
+            pass = conf_pass<EXACT>(tc, p.conf_thr, &conf);   // yolo_loss.py:189,197,201 (threshold already rounded to fp32)
             if (pass) {
                 float m1 = x[0];
 #pragma unroll
@@ -457,9 +459,9 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
                 int bi = nb ? __ffs(nb) - 1 : 0;
                 const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
                 if (CT > 1 && tie) best = class_tie_break(q + 5 * HWT, HWT, CT, lo, m1, bi, &bi);
-                else if (p.flags & 128) best = sigmoid_f(m1);
+                else if (EXACT) best = sigmoid_f(m1);
                 const int j = pos / WT;
-                emit_candidate<MODE>(p, s, hd, cid, a, pos - j * WT, j, tx, ty, tw, th, conf, best, bi);
+                emit_candidate<MODE, EXACT>(p, s, hd, cid, a, pos - j * WT, j, tx, ty, tw, th, conf, best, bi);
             } else if (MODE == MODE_FUSED) {
                 s.clsidx[cid] = 0xffffffffu;
             }
@@ -473,7 +475,7 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
 }
 
 // Runtime class count and grid (any shape): plane stride in a register, classes in chunks of 24.
-template <int THREADS, int MODE, bool DBG>
+template <int THREADS, int MODE, bool DBG, bool EXACT>
 __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = p.C;
@@ -521,7 +523,7 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
                 }
                 qb += (uint64_t)st * (uint32_t)nv;
                 if (c0 == 0) {
-                    pass = conf_pass(tc, p.conf_thr, (p.flags & 128) != 0, &conf);   // yolo_loss.py:189,197,201
+                    pass = conf_pass<EXACT>(tc, p.conf_thr, &conf);   // yolo_loss.py:189,197,201
                 }
                 float cm = x[0];
 #pragma unroll
@@ -555,9 +557,9 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
             if (pass) {
                 int bi = i1;
                 if (C > 1 && tie) best = class_tie_break(q + 5 * HW, HW, C, __fsub_rn(m1, win), m1, i1, &bi);
-                else if (p.flags & 128) best = sigmoid_f(m1);
+                else if (EXACT) best = sigmoid_f(m1);
                 const int j = fastdiv(pos, hd.magicW);
-                emit_candidate<MODE>(p, s, hd, cid, a, pos - j * hd.W, j, tx, ty, tw, th, conf, best, bi);
+                emit_candidate<MODE, EXACT>(p, s, hd, cid, a, pos - j * hd.W, j, tx, ty, tw, th, conf, best, bi);
             } else if (MODE == MODE_FUSED) {
                 s.clsidx[cid] = 0xffffffffu;
             }
@@ -582,7 +584,7 @@ __device__ __forceinline__ void decode_head_rt(const DNParams &p, const Smem &s,
 // (a, j, i).  CT: compile-time class count (0 = runtime).
 constexpr int kNhwcMaxAttrs = 32;   // 5 + C <= 32 on this path
 
-template <int THREADS, int CT>
+template <int THREADS, int CT, bool EXACT>
 __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, float *scr_base) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = p.nhwc;
@@ -622,7 +624,7 @@ __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &
             const int cid = cid0 + a * hd.HW + pos;          // reference order: (a*H + j)*W + i
             const float *xs = scr + lane * attrs;
             float conf;
-            if (conf_pass(xs[4], p.conf_thr, (p.flags & 128) != 0, &conf)) {   // yolo_loss.py:189,197,201
+            if (conf_pass<EXACT>(xs[4], p.conf_thr, &conf)) {   // yolo_loss.py:189,197,201
                 float best;
                 int bi;
                 if constexpr (CT > 0) {
@@ -641,7 +643,7 @@ __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &
                     bi = nb ? __ffs(nb) - 1 : 0;
                     const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
                     if (CT > 1 && tie) best = class_tie_break(hb + (size_t)m * attrs + 5, 1, CT, lo, m1, bi, &bi);
-                    else if (p.flags & 128) best = sigmoid_f(m1);
+                    else if (EXACT) best = sigmoid_f(m1);
                 } else {
                     float m1 = xs[5];
                     for (int c = 1; c < C; ++c) m1 = fmaxf(m1, xs[5 + c]);
@@ -656,9 +658,9 @@ __device__ __forceinline__ void decode_head_nhwc(const DNParams &p, const Smem &
                     }
                     bi = max(bi, 0);
                     if (C > 1 && nnear != 1) best = class_tie_break(hb + (size_t)m * attrs + 5, 1, C, lo, m1, bi, &bi);
-                    else if (p.flags & 128) best = sigmoid_f(m1);
+                    else if (EXACT) best = sigmoid_f(m1);
                 }
-                emit_candidate<MODE_FUSED>(p, s, hd, cid, a, i, j, xs[0], xs[1], xs[2], xs[3], conf, best, bi);
+                emit_candidate<MODE_FUSED, EXACT>(p, s, hd, cid, a, i, j, xs[0], xs[1], xs[2], xs[3], conf, best, bi);
             } else {
                 s.clsidx[cid] = 0xffffffffu;
             }
@@ -1271,8 +1273,9 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
 // kernel
 // ---------------------------------------------------------------------------
 // GATHER: the fused all-gather variant of the output phase (its own instantiation, so the ordinary kernel's register
-// allocation is untouched).  DBG: phase time stamps (profiles/phase_times.py).
-template <int MODE, int THREADS, int SHAPE, int GATHER = 0, bool DBG = false>
+// allocation is untouched).  DBG: phase time stamps (profiles/phase_times.py).  EXACT: the reference's own decode
+// arithmetic (b200yolo_set_exact_decode), instantiated for the runtime-shape variants only.
+template <int MODE, int THREADS, int SHAPE, int GATHER = 0, bool DBG = false, bool EXACT = false>
 __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 512) ? 2 : 1) decode_nms_kernel(const DNParams p, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, L, p.K, p.C);
@@ -1326,23 +1329,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     if constexpr (MODE == MODE_NMS) {
         phase_load_rows<THREADS>(p, s, b);
     } else if constexpr (kStaticShape && MODE == MODE_DECODE) {
-        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, false, DBG>(p, s, b, p.head[0], 0, 0);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, false, DBG, EXACT>(p, s, b, p.head[0], 0, 0);
     } else if constexpr (kStaticShape) {
-        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true, DBG>(p, s, b, p.head[0], 0, 0);
-        decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false, DBG>(p, s, b, p.head[1], p.head[0].cells, 1);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true, DBG, EXACT>(p, s, b, p.head[0], 0, 0);
+        decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false, DBG, EXACT>(p, s, b, p.head[1], p.head[0].cells, 1);
     } else if constexpr (kNhwcShape) {
         // scratch: the key region of U, free during the decode; the host checked that it fits
         float *scr = reinterpret_cast<float *>(smem_raw + L.key_off);
-        decode_head_nhwc<THREADS, SH::C>(p, s, b, p.head[0], 0, scr);
-        decode_head_nhwc<THREADS, SH::C>(p, s, b, p.head[1], p.head[0].cells, scr);
+        decode_head_nhwc<THREADS, SH::C, EXACT>(p, s, b, p.head[0], 0, scr);
+        decode_head_nhwc<THREADS, SH::C, EXACT>(p, s, b, p.head[1], p.head[0].cells, scr);
     } else {
         if (MODE == MODE_FUSED && p.nhwc) {
             float *scr = reinterpret_cast<float *>(smem_raw + L.key_off);
-            decode_head_nhwc<THREADS, 0>(p, s, b, p.head[0], 0, scr);
-            decode_head_nhwc<THREADS, 0>(p, s, b, p.head[1], p.head[0].cells, scr);
+            decode_head_nhwc<THREADS, 0, EXACT>(p, s, b, p.head[0], 0, scr);
+            decode_head_nhwc<THREADS, 0, EXACT>(p, s, b, p.head[1], p.head[0].cells, scr);
         } else {
-            decode_head_rt<THREADS, MODE, DBG>(p, s, b, p.head[0], 0, 0);
-            if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE, DBG>(p, s, b, p.head[1], p.head[0].cells, 1);
+            decode_head_rt<THREADS, MODE, DBG, EXACT>(p, s, b, p.head[0], 0, 0);
+            if (MODE == MODE_FUSED) decode_head_rt<THREADS, MODE, DBG, EXACT>(p, s, b, p.head[1], p.head[0].cells, 1);
         }
     }
     __syncthreads();
