@@ -1001,14 +1001,18 @@ __device__ __forceinline__ uint32_t resolve_maybe(const DNParams &p, const Smem 
     return word;
 }
 
-// shared-memory hand-overs between the warps of a CTA (release / acquire at CTA scope)
+// Shared-memory hand-overs between the warps of a CTA: release / acquire at CTA scope, and EVERY access to a word that
+// another warp may touch concurrently is an atomic instruction (ATOMS) -- the hardware cost is a handful of
+// instructions per task, and compute-sanitizer's racecheck, which only understands barriers and atomics, stays clean
+// (profiles/r02/sanitizer_racecheck.log) instead of reporting hand-overs that are ordered by flags.
 __device__ __forceinline__ int ld_acquire_s(const int *a) {
     int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
+    asm volatile("atom.acquire.cta.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_s(int *a, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
+    int old;
+    asm volatile("atom.release.cta.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_add_s(int *a, int v) {
     asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
@@ -1018,8 +1022,12 @@ __device__ __forceinline__ void red_or_s(uint32_t *a, uint32_t v) {
 }
 __device__ __forceinline__ uint32_t ld_relaxed_s(const uint32_t *a) {
     uint32_t v;
-    asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
+    asm volatile("atom.relaxed.cta.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_s(uint32_t *a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.relaxed.cta.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
 }
 
 // Tasks.  HEAD task of tile rt of class c: (1) when the kept rows of all earlier tiles have contributed to the tile's
@@ -1043,7 +1051,10 @@ __device__ __forceinline__ void strip_blocks(const DNParams &p, const Smem &s, i
     for (int ct = ct0; ct < ct1; ++ct) {
         const int gct = grt + (ct - rt);
         const int ncol = min(32, n - 32 * ct);
-        const uint32_t open = ((ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u)) & ~ld_relaxed_s(&s.supw[gct]);
+        uint32_t supd = 0u;
+        if (lane == 0) supd = ld_relaxed_s(&s.supw[gct]);
+        supd = __shfl_sync(kFullMask, supd, 0);
+        const uint32_t open = ((ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u)) & ~supd;
         uint32_t sup = 0u;
         if (rem != 0u && open != 0u) {
             const uint32_t maybe = kept ? (h16_prefilter(s.h16[gct], row, ncol) & open) : 0u;
@@ -1073,18 +1084,27 @@ __device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
         uint32_t rem;
         int ct0, ct1;
         if (tk & kTaskTail) {
-            while (!(ld_acquire_s(&s.ready[grt]) & 1)) __nanosleep(20);
-            rem = s.keptw[grt];
+            rem = 0u;
+            if (lane == 0) {
+                while (!(ld_acquire_s(&s.ready[grt]) & 1)) __nanosleep(20);
+                rem = ld_relaxed_s(&s.keptw[grt]);
+            }
+            rem = __shfl_sync(kFullMask, rem, 0);
             ct0 = rt + 2;
             ct1 = T;
         } else {
             const int nrow = min(32, n - 32 * rt);
             const uint32_t validr = (nrow >= 32) ? 0xffffffffu : ((1u << nrow) - 1u);
             // (1) the tile's own turns
-            if (rt > 0) {
-                while (ld_acquire_s(&s.arrived[grt]) < rt) __nanosleep(20);
+            uint32_t supd = 0u;
+            if (lane == 0) {
+                if (rt > 0) {
+                    while (ld_acquire_s(&s.arrived[grt]) < rt) __nanosleep(20);
+                }
+                supd = ld_relaxed_s(&s.supw[grt]);
             }
-            const uint32_t alive = validr & ~ld_relaxed_s(&s.supw[grt]);
+            supd = __shfl_sync(kFullMask, supd, 0);
+            const uint32_t alive = validr & ~supd;
             rem = alive;
             if (alive & (alive - 1u)) {   // two or more alive candidates
                 uint32_t maybe = 0u;
@@ -1100,7 +1120,7 @@ __device__ __forceinline__ void phase_pairs(const DNParams &p, const Smem &s) {
             }
             const bool tail = has_tail(T, rt);
             if (lane == 0) {
-                s.keptw[grt] = rem;
+                st_relaxed_s(&s.keptw[grt], rem);
                 if (tail) st_release_s(&s.ready[grt], (c << 16) | 1);
             }
             // (2) the kept rows against the next tile (the tail task takes the others), or against all later tiles

@@ -258,18 +258,20 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
         float nta = rta;
         if (t > 0) large_fetch<SRC>(p, b, K0, rec, (uint32_t)(keys[s0 + lane] & 0xffffull), nB, nta);
         for (int rt = 0; rt < t; ++rt) {
+            __syncwarp();   // (every lane has finished reading the previous tile's columns out of the staging buffer)
             sbox[lane] = nB;
             sord[lane] = make_uint2(sbox_addr + 16u * lane, __float_as_uint(nta));
             const bool slow = rslow || __any_sync(kFullMask, nta != nta);
             if (rt + 1 < t) large_fetch<SRC>(p, b, K0, rec, (uint32_t)(keys[s0 + 32 * (rt + 1) + lane] & 0xffffull), nB, nta);
             __syncwarp();
             const uint32_t word = slow ? block_exact(sord, 32, R, p.iou.thr) : block_fast(sord, 32, R, rta, p.iou.thr);
+            // (hand-over through atomics with release / acquire semantics: see decode_nms.cuh, ld_acquire_s)
+            uint32_t kw = 0u;
             if (lane == 0) {
-                while (reinterpret_cast<volatile int *>(ready)[g0 + rt] == 0) __nanosleep(40);
-                __threadfence_block();
+                while (ld_acquire_s(&ready[g0 + rt]) == 0) __nanosleep(40);
+                kw = ld_relaxed_s(&keptw[g0 + rt]);
             }
-            __syncwarp();
-            const uint32_t kw = reinterpret_cast<volatile uint32_t *>(keptw)[g0 + rt];
+            kw = __shfl_sync(kFullMask, kw, 0);
             if (word & kw) alive = false;
             if (!__any_sync(kFullMask, alive)) break;
         }
@@ -291,9 +293,8 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
         }
         __syncwarp();
         if (lane == 0) {
-            keptw[g0 + t] = rem;
-            __threadfence_block();
-            reinterpret_cast<volatile int *>(ready)[g0 + t] = 1;
+            st_relaxed_s(&keptw[g0 + t], rem);
+            st_release_s(&ready[g0 + t], 1);
         }
     }
     __syncthreads();
