@@ -1438,8 +1438,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     phase_pairs(p, s);
     __syncthreads();
     stamp<DBG>(p, b, 4);
-    // P6 (the fp16 tables are dead now; the row scratch aliases them)
-    pdl_wait();
+    // P6 (the fp16 tables are dead now; the row scratch aliases them).  The ordinary kernel waits for its predecessor
+    // before its first store (consecutive launches may share the output buffers).  The gather variant needs no such
+    // wait: consecutive steps store into different buffers, and what orders a step against the previous users of ITS
+    // buffer is the flag wait below -- so a step's stores, and their NVLink round trips, overlap the previous step's tail.
+    if constexpr (GATHER == 0) pdl_wait();
     if constexpr (GATHER != 0) {
         // the gather buffer this step writes was last used three steps ago: wait until every rank has completed the
         // previous step, i.e. has moved past everything it ran on that buffer (dist.PeerGather, back-pressure)
