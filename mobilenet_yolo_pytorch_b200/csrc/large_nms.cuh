@@ -4,7 +4,7 @@
 //
 // One CTA of 1024 threads per image, same reference semantics as the fused kernel (yolo_loss.py:186-203,
 // utils/box.py:16-30, torchvision nms) and the same arithmetic (SFU sigmoid / exp, class near-tie fallback,
-// divide-free pair test with the exact torchvision decision inside the guard band):
+// conservative fp16 prefilter of the box pairs with the exact torchvision decision for the pairs it cannot rule out):
 //   P1  decode every cell (thread per cell, plane loads coalesced); a passing cell's record {box, conf, score,
 //       t*area*2^-13, class} goes to the caller's workspace (32 B per cell, stays in L2) and its 64-bit sort key
 //       (class asc | score desc | cell id asc) to shared memory -- 8 B per cell is all the CTA stages;
@@ -12,11 +12,12 @@
 //   P3  class starts / tile table (warp 0);
 //   P4  greedy NMS over tasks = (class, tile of 32 sorted candidates), claimed from a counter in tile-major
 //       order (tile 0 of every class, tile 1 of every class, ...: the classes advance side by side).  A task
-//       (lane = candidate) stages each earlier tile of its class as the 32 columns of one pair block of
-//       decode_nms.cuh (block_fast / block_exact: the same arithmetic as the fused kernel), ANDs the block's
-//       word with the tile's KEPT word -- it spins on a per-tile ready flag; a task only depends on tasks
-//       claimed before it, so the spin cannot deadlock -- then resolves its own tile in score order and
-//       publishes its kept word.  No n^2 mask storage: the worst case (one class holding everything) is
+//       (lane = candidate) stages each earlier tile of its class as the 32 columns of one pair block (fp32 boxes
+//       + their H16Tile), runs the fp16 prefilter of decode_nms.cuh (h16_prefilter) and decides exactly
+//       (pair_decide) only the "maybe" pairs whose column was KEPT -- the tile's kept word comes from a per-tile
+//       ready flag; a task only depends on tasks claimed before it, so the spin cannot deadlock -- then resolves
+//       its own tile in score order and publishes its kept word.  (Round 1 evaluated the fp32 pair block for every
+//       column: 0.53 ms per 128-image step at 832x832; now 0.43 ms.)  No n^2 mask storage: the worst case (one class holding everything) is
 //       bounded by time, not memory;
 //   P5  kept rows in (class asc, score desc) order -> out / out_idx / out_count.
 #pragma once
@@ -26,7 +27,7 @@ namespace b200yolo {
 
 constexpr int kLargeThreads = 1024;
 constexpr int kLargeMaxKeys = 16384;   // 128 KB of keys
-constexpr int kLargeStageBytes = 32 * 16 + 40 * 8;   // per warp: 32 boxes + 32 (+8 padding) {box address, t*area} entries
+constexpr int kLargeStageBytes = 32 * 16 + 320;   // per warp: 32 staged column boxes + their H16Tile (decode_nms.cuh)
 
 struct LargeParams {
     HeadDesc head[2];
@@ -180,14 +181,12 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
     // per-warp staging of one tile of columns for the pair blocks of decode_nms.cuh
     const size_t stage0 = (((size_t)8 * p.P + (size_t)4 * (3 * (C + 2)) + (size_t)12 * p.T + 64) + 15) & ~(size_t)15;
     float4 *sbox = reinterpret_cast<float4 *>(lsm + stage0 + (size_t)warp * kLargeStageBytes);
-    uint2 *sord = reinterpret_cast<uint2 *>(sbox + 32);
-    const uint32_t sbox_addr = (uint32_t)__cvta_generic_to_shared(sbox);
+    H16Tile *stile = reinterpret_cast<H16Tile *>(sbox + 32);
 
     for (int i = tid; i < C + 2; i += kLargeThreads) cnt[i] = 0;
     for (int i = tid; i < p.T; i += kLargeThreads) { keptw[i] = 0u; ready[i] = 0; }
     for (int i = K + tid; i < p.P; i += kLargeThreads) keys[i] = ~0ull;
     if (tid < 2) misc[tid] = 0;
-    if (lane < 8) sord[32 + lane] = make_uint2(sbox_addr, 0x7fc00000u);   // padding read by partial chunks: NaN area
     __syncthreads();
     // P1
     int K0 = 0;
@@ -250,21 +249,33 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
         float4 R;
         float rta;
         large_fetch<SRC>(p, b, K0, rec, cid, R, rta);
-        const bool rslow = __any_sync(kFullMask, rta != rta);   // a degenerate box in the tile: exact arithmetic
+        // The pair blocks use the conservative fp16 prefilter of decode_nms.cuh (h16_prefilter: a clear bit proves that
+        // torchvision does not suppress the pair) and decide the pairs it cannot rule out exactly (pair_decide).
+        const float ra = box_area(R);
+        const H16Row myrow = tl_h16_row(R, ra, p.iou.th);
+        // the exact decisions for this lane's "maybe" columns of the staged tile
+        auto resolve = [&](uint32_t maybe) -> uint32_t {
+            uint32_t word = 0u;
+            while (maybe) {
+                const int j = __ffs(maybe) - 1;
+                maybe &= maybe - 1u;
+                if (pair_decide(R, ra, sbox[j], p.iou)) word |= 1u << j;
+            }
+            return word;
+        };
         // earlier tiles of the class: their 32 boxes are staged as the columns of one pair block (the records were
         // written in P1, so the loads do not wait for the tile's flag; the next tile's are issued before this one
-        // is processed); the block's word AND the tile's kept word says whether a kept box suppresses my candidate
+        // is processed); only columns that were KEPT can suppress my candidate
         float4 nB = R;
         float nta = rta;
         if (t > 0) large_fetch<SRC>(p, b, K0, rec, (uint32_t)(keys[s0 + lane] & 0xffffull), nB, nta);
         for (int rt = 0; rt < t; ++rt) {
             __syncwarp();   // (every lane has finished reading the previous tile's columns out of the staging buffer)
             sbox[lane] = nB;
-            sord[lane] = make_uint2(sbox_addr + 16u * lane, __float_as_uint(nta));
-            const bool slow = rslow || __any_sync(kFullMask, nta != nta);
+            tl_h16_put(stile, lane, nB, box_area(nB), p.iou.th);
             if (rt + 1 < t) large_fetch<SRC>(p, b, K0, rec, (uint32_t)(keys[s0 + 32 * (rt + 1) + lane] & 0xffffull), nB, nta);
             __syncwarp();
-            const uint32_t word = slow ? block_exact(sord, 32, R, p.iou.thr) : block_fast(sord, 32, R, rta, p.iou.thr);
+            uint32_t maybe = alive ? h16_prefilter(*stile, myrow, 32) : 0u;
             // (hand-over through atomics with release / acquire semantics: see decode_nms.cuh, ld_acquire_s)
             uint32_t kw = 0u;
             if (lane == 0) {
@@ -272,18 +283,17 @@ __global__ void __launch_bounds__(kLargeThreads, 1) decode_nms_large_kernel(cons
                 kw = ld_relaxed_s(&keptw[g0 + rt]);
             }
             kw = __shfl_sync(kFullMask, kw, 0);
-            if (word & kw) alive = false;
+            if (resolve(maybe & kw)) alive = false;
             if (!__any_sync(kFullMask, alive)) break;
         }
         // own tile: later columns a candidate would suppress, then the turns in score order
         __syncwarp();
         sbox[lane] = R;
-        sord[lane] = make_uint2(sbox_addr + 16u * lane, __float_as_uint(rta));
+        tl_h16_put(stile, lane, R, ra, p.iou.th);
         __syncwarp();
-        uint32_t D = rslow ? block_exact(sord, ncol, R, p.iou.thr) : block_fast(sord, ncol, R, rta, p.iou.thr);
-        D &= ~((2u << lane) - 1u);                    // only LATER columns (2u << 31 == 0: none)
+        const uint32_t validc = (ncol >= 32) ? 0xffffffffu : ((1u << ncol) - 1u);
+        uint32_t D = alive ? resolve(h16_prefilter(*stile, myrow, ncol) & validc & ~((2u << lane) - 1u)) : 0u;   // only LATER columns
         uint32_t rem = __ballot_sync(kFullMask, alive);
-        if (!alive) D = 0u;
         uint32_t nz = __ballot_sync(kFullMask, (D & rem) != 0u);
         while (nz) {
             const int i = __ffs(nz) - 1;
