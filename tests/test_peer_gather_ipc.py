@@ -2,7 +2,8 @@
 GPU: two processes share cuda:0, rendezvous over gloo, and map each other's gather buffers through CUDA IPC exactly
 as two ranks on two GPUs do (the 2-GPU NCCL variant is tests/test_dist_nccl.py).  Several steps with different
 inputs, a consumer that reads the gathered buffers between the fence of a step and the launch of the next one
-(the double-buffered back-pressure), and the one-call multi-step entry.
+(the back-pressure), the one-call multi-step entry, and the sharded YOLOLoss with its all-reduce of the 16
+partial sums (loss, statistics and gradient slices equal the unsharded ones).
 """
 import os
 import socket
@@ -32,6 +33,17 @@ def _heads(N, step):
         h0.view(N, 3, 25, 11, 11)[:, :, 4] -= 2.6
         h1.view(N, 3, 25, 22, 22)[:, :, 4] -= 2.6
     return h0, h1
+
+
+def _targets(N):
+    r = np.random.RandomState(9)
+    out = []
+    for b in range(N):
+        n = [4, 0, 25, 2, 60, 9, 1, 13][b % 8]
+        wh = r.rand(n, 2) * 0.45 + 0.02
+        c = wh / 2 + r.rand(n, 2) * (1 - wh)
+        out.append(torch.from_numpy(np.concatenate((r.randint(1, C + 1, (n, 1)), c, wh), 1).astype(np.float32)))
+    return out
 
 
 def _digest(dets, counts):
@@ -71,7 +83,16 @@ def _worker(rank, world, port, N, q):
         out = [(a.cpu().numpy(), b.cpu().numpy()) for a, b in digests]
         rows = d.cpu().numpy().copy()
         pg.close()
-        q.put((rank, out, rows))
+        # the other exchange step of the path: YOLOLoss on a shard with the 16 partial sums all-reduced before the
+        # batch-global division (here over gloo, which stages the CUDA tensor through the host; NCCL on real ranks)
+        lh0, lh1 = _heads(N, 50)
+        targets = _targets(N)
+        ll = b200.YOLOLoss(VOC_ANCHORS, MASKS[1], C, [352, 352], 0.6, 0.55, iou_weighting=0.02, process_group=dist.group.WORLD)
+        x = lh1[lo:hi].to(dev).requires_grad_(True)
+        tup = ll(x, targets[lo:hi])
+        tup[0].backward()
+        loss_out = ([float(tup[0].detach()), tup[1], tup[2], tup[3], float(tup[4]), tup[5], tup[6]], x.grad.cpu().numpy(), lo, hi)
+        q.put((rank, out, rows, loss_out))
     finally:
         dist.destroy_process_group()
 
@@ -110,7 +131,20 @@ def test_peer_gather_two_processes_one_gpu():
         a, b = _digest(dets, cnt)
         want.append((a.cpu().numpy(), b.cpu().numpy()))
         last_rows = (dets.cpu().numpy(), cnt.cpu().numpy())
-    for rank, digests, rows in got:
+    # the unsharded loss and gradient
+    _, lh1 = _heads(N, 50)
+    targets = _targets(N)
+    ll = b200.YOLOLoss(VOC_ANCHORS, MASKS[1], C, [352, 352], 0.6, 0.55, iou_weighting=0.02)
+    x = lh1.to(dev).requires_grad_(True)
+    tup = ll(x, targets)
+    tup[0].backward()
+    full = [float(tup[0].detach()), tup[1], tup[2], tup[3], float(tup[4]), tup[5], tup[6]]
+    grad = x.grad.cpu().numpy()
+    for rank, digests, rows, (lt, g, lo, hi) in got:
+        # reduce-then-normalise: every shard reports the loss and statistics of the WHOLE batch, and its gradient is the
+        # slice of the full-batch gradient (the backward kernel reads the all-reduced sums)
+        np.testing.assert_allclose(lt, full, rtol=1e-6, atol=1e-9)
+        assert np.abs(g - grad[lo:hi]).max() <= 1e-6 * np.abs(grad).max()
         assert len(digests) == len(want)
         for k, ((c_got, s_got), (c_want, s_want)) in enumerate(zip(digests, want)):
             assert np.array_equal(c_got, c_want), f"rank {rank}, step {k}: counts differ"
