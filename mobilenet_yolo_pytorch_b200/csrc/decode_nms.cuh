@@ -172,7 +172,8 @@ __host__ __device__ inline int pick_buckets(int C) {
     return B;
 }
 
-constexpr uint32_t kScratchPerWarp = 32 * 7 * 4;  // P6: 32 output rows of 7 floats
+constexpr uint32_t kScratchFloats = 320;              // P6: per-warp staging: one tile of 32 x 7 floats + what the previous flush left (< 96)
+constexpr uint32_t kScratchPerWarp = kScratchFloats * 4;
 constexpr int kRankItems = 8;                     // P4: sorted positions a thread carries over the barrier
 
 // U region by phase (Kp = K rounded up to 32, NT = Kp/32 + C tiles):
@@ -1189,19 +1190,141 @@ __device__ __forceinline__ uint32_t block_fast(const uint2 *ordc, int ncol, cons
 }
 
 // ---------------------------------------------------------------------------
-// P6: output.  Tile g of the kept bitmap holds up to 32 rows that are consecutive in the
-// output (class-ascending, score-descending); the warp assembles them in its scratch and
-// writes them with coalesced stores.
+// P6: output.  Tile g of the kept bitmap holds up to 32 rows that are consecutive in the output (class-ascending,
+// score-descending); a warp owns a contiguous range of tiles, hence a CONTIGUOUS range of the output.  It streams
+// that range through its scratch: rows are appended as 7 floats each, and whenever >= 96 floats are pending (and at
+// the end of the range) the pending floats leave as 16-byte stores aligned to 16 bytes in global memory -- only the
+// first and the last < 4 floats of the warp's range go out as scalars.  Few, long, aligned requests: what HBM likes
+// and, for the fused all-gather, what NVLink likes (trained-like heads keep ~4 rows per class: a store per tile
+// would be a 100-byte packet per class and peer).
 // ---------------------------------------------------------------------------
 template <int MODE, int THREADS, int GATHER>
-__device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, int b) {
+__device__ __forceinline__ void phase_output_stream(const DNParams &p, const Smem &s, int b) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
     const int ntiles = s.ktile[p.C];
     const int nbuf = (GATHER != 0) ? p.gR : 1;   // fused all-gather: one copy per rank
     const size_t img = (GATHER != 0) ? (size_t)(p.gslot + b) : (size_t)b;
-    float *o = (GATHER != 0) ? nullptr : p.out + img * p.K * 7;
-    float *scr = s.scratch + warp * (32 * 7);
+    float *scr = s.scratch + warp * kScratchFloats;
+    // MODE_NMS: the caller's own rows are gathered bit-for-bit (pred_this_cls[index], box.py:29)
+    const int K0 = (MODE == MODE_NMS) ? min(p.cand_count[0][b], p.cand_stride[0]) : 0;
+    const float *r0 = (MODE == MODE_NMS) ? p.cand[0] + (size_t)b * p.cand_stride[0] * 7 : nullptr;
+    const float *r1 = (MODE == MODE_NMS && p.cand[1]) ? p.cand[1] + (size_t)b * p.cand_stride[1] * 7 : nullptr;
+    // each warp owns a contiguous range of tiles: one prefix over the kept bitmap per warp
+    const int per = (ntiles + kWarps) / kWarps;  // ceil((ntiles + 1) / kWarps): "tile" ntiles writes the count
+    const int g0 = warp * per, g1 = min(g0 + per, ntiles + 1);
+    int before = 0;
+    for (int t = lane; t < g0; t += 32) before += __popc(s.keptw[t]);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
+    // Streaming state.  e = float index (in a gather buffer / in `out`) of the next float this warp emits; scratch[i]
+    // holds the float that belongs at gbase + i, gbase a multiple of 4 in the sense of the 16-byte alignment of the
+    // destination; the first `hole` entries (only before the first flush) belong to the warp before this one.
+    size_t e = (img * (size_t)p.K + (size_t)before) * 7;
+    const float *abase = (GATHER != 0) ? p.gout[0] : p.out;          // (every buffer has the same alignment: 256 B)
+    int hole = (int)((((uintptr_t)(abase + e)) >> 2) & 3);
+    size_t gbase = e - (size_t)hole;
+    int pend = hole;
+    // the pending floats [hole, pend) leave: scalars for a first group with holes, 16-byte stores for whole groups, and
+    // (final) scalars for the last < 4 floats; what stays moves to the front of the scratch
+    auto flush = [&](bool final) {
+        __syncwarp();
+        int v0 = 0;
+        const int nvec = pend >> 2;
+        if (hole > 0 && (nvec > 0 || final)) {
+            const int hi = min(4, pend);
+            if (lane >= hole && lane < hi) {
+                const float v = scr[lane];
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; ++r) {
+                    if (r >= nbuf) break;
+                    ((GATHER != 0) ? p.gout[r] : p.out)[gbase + lane] = v;
+                }
+            }
+            hole = 0;
+            v0 = 1;
+        }
+        for (int v = v0 + lane; v < nvec; v += 32) {
+            const float4 a = *reinterpret_cast<const float4 *>(scr + 4 * v);
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r) {  // (peer stores travel over NVLink while the next tiles are assembled)
+                if (r >= nbuf) break;
+                *reinterpret_cast<float4 *>(((GATHER != 0) ? p.gout[r] : p.out) + gbase + 4 * (size_t)v) = a;
+            }
+        }
+        const int done = min(pend, 4 * max(nvec, v0));   // scratch entries that are out (a first group with holes counts)
+        const int rem = pend - done;                      // 0..3
+        float keep = 0.f;
+        if (lane < rem) keep = scr[done + lane];
+        if (final && lane < rem && done + lane >= hole) {
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r) {
+                if (r >= nbuf) break;
+                ((GATHER != 0) ? p.gout[r] : p.out)[gbase + done + lane] = keep;
+            }
+        }
+        __syncwarp();
+        if (!final && done > 0 && lane < rem) scr[lane] = keep;
+        if (!final) {
+            gbase += (size_t)done;
+            pend = rem;
+        }
+        __syncwarp();
+    };
+    for (int g = g0; g < g1; ++g) {
+        if (g == ntiles) {
+            if (GATHER != 0) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < kMaxPeers; ++r)
+                        if (r < nbuf) p.gcount[r][img] = before;
+                }
+            } else if (lane == 0) {
+                p.out_count[b] = before;
+            }
+            break;
+        }
+        const uint32_t word = s.keptw[g];
+        const int nk = __popc(word);
+        if (nk == 0) continue;
+        if ((word >> lane) & 1u) {
+            const int r = __popc(word & lanemask_lt());
+            const uint32_t cid = s.scid[32 * g + lane];
+            float *d = scr + pend + 7 * r;
+            if (MODE == MODE_NMS) {
+                const float *src = ((int)cid < K0) ? r0 + (size_t)cid * 7 : r1 + (size_t)((int)cid - K0) * 7;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) d[k] = __ldg(src + k);
+            } else {
+                const float4 bx = s.box[cid];
+                const float2 cs = s.cs[cid];
+                d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
+                d[4] = cs.x; d[5] = cs.y;
+                d[6] = (float)(s.ready[g] >> 16);  // cls_idx.float() (yolo_loss.py:199)
+            }
+            if (p.out_idx) p.out_idx[(size_t)b * p.K + before + r] = (int)cid;
+        }
+        pend += 7 * nk;
+        before += nk;
+        if (pend >= 96) flush(false);   // (a tile adds at most 224 floats: 95 + 224 < kScratchFloats)
+    }
+    if (pend > hole) flush(true);
+}
+
+// The ordinary (single-buffer) kernel keeps the simpler per-tile writer: a tile's rows are assembled in the scratch and
+// leave with coalesced 4-byte stores.  HBM does not care about the request size the way NVLink does, and the
+// streaming writer's bookkeeping costs this kernel 4-7 % (measured, profiles/r02/NOTES.md).
+template <int MODE, int THREADS, int GATHER>
+__device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, int b) {
+    if constexpr (GATHER != 0) {
+        phase_output_stream<MODE, THREADS, GATHER>(p, s, b);
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+    const int ntiles = s.ktile[p.C];
+    float *o = p.out + (size_t)b * p.K * 7;
+    float *scr = s.scratch + warp * kScratchFloats;
     // MODE_NMS: the caller's own rows are gathered bit-for-bit (pred_this_cls[index], box.py:29)
     const int K0 = (MODE == MODE_NMS) ? min(p.cand_count[0][b], p.cand_stride[0]) : 0;
     const float *r0 = (MODE == MODE_NMS) ? p.cand[0] + (size_t)b * p.cand_stride[0] * 7 : nullptr;
@@ -1215,15 +1338,7 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
     for (int sh = 16; sh > 0; sh >>= 1) before += __shfl_xor_sync(kFullMask, before, sh);
     for (int g = g0; g < g1; ++g) {
         if (g == ntiles) {
-            if (GATHER != 0) {
-                if (lane == 0) {
-#pragma unroll
-                    for (int r = 0; r < kMaxPeers; ++r)
-                        if (r < nbuf) p.gcount[r][img] = before;
-                }
-            } else if (lane == 0) {
-                p.out_count[b] = before;
-            }
+            if (lane == 0) p.out_count[b] = before;
             break;
         }
         const uint32_t word = s.keptw[g];
@@ -1248,41 +1363,11 @@ __device__ __forceinline__ void phase_output(const DNParams &p, const Smem &s, i
         }
         __syncwarp();
         const int nf = 7 * nk;
-        if (GATHER != 0) {
-            // NVLink likes long requests: the chunk (<= 224 floats, contiguous in every buffer, buffers 256-byte aligned)
-            // goes out as <= 2 sixteen-byte stores per lane plus one scalar store for the unaligned head and tail
-            const size_t e0 = (img * p.K + before) * 7;          // float index of the chunk in a buffer
-            const int hcnt = min((int)((4 - (e0 & 3)) & 3), nf);
-            const int nvec = (nf - hcnt) >> 2;
-            const int tail0 = hcnt + 4 * nvec;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-            if (lane < nvec) {
-                const float *q = scr + hcnt + 4 * lane;
-                a0 = make_float4(q[0], q[1], q[2], q[3]);
-            }
-            if (lane + 32 < nvec) {
-                const float *q = scr + hcnt + 4 * (lane + 32);
-                a1 = make_float4(q[0], q[1], q[2], q[3]);
-            }
-            int hidx = -1;                                       // lanes 0-2: head floats, lanes 4-6: tail floats
-            if (lane < hcnt) hidx = lane;
-            else if (lane >= 4 && lane < 8 && tail0 + lane - 4 < nf) hidx = tail0 + lane - 4;
-            const float hv = (hidx >= 0) ? scr[hidx] : 0.f;
+        float *dst = o + (size_t)7 * before;
 #pragma unroll
-            for (int r = 0; r < kMaxPeers; ++r) {  // peer stores travel over NVLink while the next tile is assembled
-                if (r >= nbuf) break;
-                float *dst = p.gout[r] + e0;
-                if (lane < nvec) *reinterpret_cast<float4 *>(dst + hcnt + 4 * lane) = a0;
-                if (lane + 32 < nvec) *reinterpret_cast<float4 *>(dst + hcnt + 4 * (lane + 32)) = a1;
-                if (hidx >= 0) dst[hidx] = hv;
-            }
-        } else {
-            float *dst = o + (size_t)7 * before;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const int f = 32 * k + lane;
-                if (f < nf) dst[f] = scr[f];
-            }
+        for (int k = 0; k < 7; ++k) {
+            const int f = 32 * k + lane;
+            if (f < nf) dst[f] = scr[f];
         }
         __syncwarp();
         before += nk;
