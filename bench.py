@@ -428,7 +428,7 @@ class DecodeNmsRun:
     """K steps of decode + NMS on this rank's shard, issued by one C call.  world > 1: kernel + fused all-gather
     (peer stores over NVLink) + fence per step."""
 
-    def __init__(self, D, wl, n_local, steps, gather=True, seed0=0):
+    def __init__(self, D, wl, n_local, steps, gather=True, seed0=0, graph=True):
         from mobilenet_yolo_pytorch_b200 import _lib, ops
         from mobilenet_yolo_pytorch_b200 import dist as b2dist
         self.D, self.wl, self.N, self.steps = D, wl, n_local, steps
@@ -455,6 +455,8 @@ class DecodeNmsRun:
         else:
             self.plan = ops.BatchPlan([(self.sets[i % self.R][0], self.sets[i % self.R][1], self.out, self.cnt) for i in range(steps)],
                                       self.tables, wl["C"], wl["conf"])
+            if graph:
+                self.plan.capture()   # b200yolo_plan_create: the K launches as one CUDA graph (K kernel nodes, programmatic edges)
 
     def run(self, count=None):
         count = self.steps if count is None else count
@@ -483,13 +485,21 @@ class DecodeNmsRun:
 
     def time(self, warmup):
         D = self.D
-        self.run(min(max(warmup, 3), self.steps))
+        if getattr(self.plan, "_graph", None) is not None:
+            self.run()                 # the plan replays as a whole: its K >= W steps are the warm-up
+            if self.steps < max(warmup, 3):
+                self.run()
+        else:
+            self.run(min(max(warmup, 3), self.steps))
         D.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        from mobilenet_yolo_pytorch_b200 import _lib
+        c0 = _lib.launch_count()
         e0.record()
         self.run()
         e1.record()
         e1.synchronize()
+        self.timed_launches = _lib.launch_count() - c0   # kernels of this library inside the timed region
         ms = e0.elapsed_time(e1)
         D.barrier()
         if self.pg is not None:
@@ -558,11 +568,8 @@ def run_b200(args, name, wl):
     # ---- headline: K steps from one C call
     run = DecodeNmsRun(D, wl, N, args.steps)
     kept_per_launch = run.kept_per_launch()
-    l0 = _lib.launch_count()
     ms_per_step = run.time(args.warmup)
-    launches = _lib.launch_count() - l0
-    warm_launches = launches - (launches * args.steps) // (args.steps + min(max(args.warmup, 3), args.steps))
-    launches_timed = launches - warm_launches
+    launches_timed = run.timed_launches
     # clocks: the same launches for ~0.4 s under the NVML sampler (a 0.5 ms timed region is shorter than one NVML poll)
     clocks = None
     if rank == 0:
@@ -606,11 +613,21 @@ def run_b200(args, name, wl):
     if not args.no_extra:
         # plain stream order (no programmatic dependent launch): comparable with ncu's gpu__time_duration
         if not run.large:
+            # (the graph froze the launch attributes: these two legs issue the K launches directly)
+            held, held_graph = (run.plan, run.plan._graph) if getattr(run.plan, "_graph", None) is not None else (None, None)
+            if held is not None:
+                held._graph = None
+                direct_ms = run.time(3)
+                extra["direct_launches"] = {"ms_per_step": direct_ms, "images_per_s": total_images / (direct_ms * 1e-3),
+                                            "note": "the same K overlapping launches issued one by one from one C call "
+                                                    "(b200yolo_decode_nms_batches) instead of one graph launch"}
             lib.b200yolo_debug_set_flags(2)
             try:
                 ser_ms = run.time(3)
             finally:
                 lib.b200yolo_debug_set_flags(0)
+                if held is not None:
+                    held._graph = held_graph
             extra["serialized_launches"] = {"ms_per_step": ser_ms, "images_per_s": total_images / (ser_ms * 1e-3),
                                             "note": "the same steps in plain stream order (every launch waits for the previous one to drain)"}
         if gathered:
@@ -707,9 +724,11 @@ def run_b200(args, name, wl):
             "higher_is_better": True, "scaling": "strong" if wl["GB"] else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg,
             "run": {"kept_rows_per_image": kept_all / total_images,
-                    "launch": ("the K steps are issued by ONE C call (b200yolo_decode_nms_batches / _gather_steps); consecutive launches "
-                               "overlap through programmatic dependent launch (a launch starts on free SM slots while the previous one "
-                               "finishes and waits for it before writing); extra.serialized_launches is plain stream order")
+                    "launch": (("the K steps are K kernel nodes of ONE CUDA graph (b200yolo_plan_create / _launch)" if not gathered else
+                                "the K steps are issued by ONE C call (b200yolo_decode_nms_gather_steps)")
+                               + "; consecutive launches overlap through programmatic dependent launch (a launch starts on free SM "
+                               "slots while the previous one finishes and waits for it before writing); extra.serialized_launches is "
+                               "plain stream order")
                     if not run.large else "one kernel per step on one stream, plain stream order",
                     "parallelism": (f"dp{world} by image; every step = kernel + fused all-gather of the kept rows (peer stores over NVLink) + fence"
                                     if gathered else f"dp{world} by image, no collective (1 GPU)" if world == 1

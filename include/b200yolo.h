@@ -128,6 +128,21 @@ int b200yolo_decode_nms_batches(const b200yolo_batch *batches, int n_batches, in
                                 int W1, const float *anchor_wh, float conf_thr, double iou_thr, void *stream);
 
 /*
+ * The same list as a replayable plan: the launches of b200yolo_decode_nms_batches captured once into a CUDA graph (with
+ * their programmatic-launch edges) and issued by ONE cudaGraphLaunch per b200yolo_plan_launch -- for a loop that visits
+ * the same device buffers again and again (an evaluation loop over a resident ring of head buffers, train.py:357-395; a
+ * serving queue with fixed slots).  Creation must run with the buffers' device current and does not touch the caller's
+ * streams (thread-local capture on a private stream); the pointers and thresholds are frozen into the plan.  A plan may
+ * be launched any number of times on any stream of its device, one launch at a time; destroy it when no launch is in
+ * flight.
+ */
+typedef struct b200yolo_plan b200yolo_plan;
+int b200yolo_plan_create(const b200yolo_batch *batches, int n_batches, int N, int A, int C, int H0, int W0, int H1, int W1,
+                         const float *anchor_wh, float conf_thr, double iou_thr, b200yolo_plan **plan_out);
+int b200yolo_plan_launch(b200yolo_plan *plan, void *stream);
+int b200yolo_plan_destroy(b200yolo_plan *plan);
+
+/*
  * Single calls (b200yolo_decode_nms & co.) execute griddepcontrol.wait before their first global read, because the
  * kernel that precedes them in the stream may be the producer of their inputs.  A caller that issues them back to
  * back on buffers no kernel of this library writes (a benchmark loop over resident head tensors) may declare that

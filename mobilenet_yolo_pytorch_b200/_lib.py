@@ -34,6 +34,10 @@ SIGNATURES = {
                                       c_f32p, C.c_float, C.c_double, c_f32p, c_i32p, c_i32p, C.c_void_p]),
     "b200yolo_decode_nms_batches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               c_f32p, C.c_float, C.c_double, C.c_void_p]),
+    "b200yolo_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_float, C.c_double, C.POINTER(C.c_void_p)]),
+    "b200yolo_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200yolo_plan_destroy": (C.c_int, [C.c_void_p]),
     "b200yolo_set_inputs_ready": (None, [C.c_int]),
     "b200yolo_set_exact_decode": (None, [C.c_int]),
     "b200yolo_decode_nms_nhwc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 
 #include "decode_nms.cuh"  // (after the helpers it uses)
 #include "target_loss.cuh"
@@ -543,6 +544,81 @@ int b200yolo_decode_nms_batches(const b200yolo_batch *batches, int n_batches, in
         p.wait_inputs = (k == 0) ? 1 : 0;
         if (int rc = launch_dn<MODE_FUSED>(p, (cudaStream_t)stream)) return rc;
     }
+    return 0;
+}
+
+// The list of batches as ONE CUDA graph: the launches of b200yolo_decode_nms_batches are captured (thread-local capture on
+// a private stream, so nothing else the process does is affected) with their programmatic-launch edges, and replayed by
+// one cudaGraphLaunch -- the host's per-launch cost (~2.5 us each, which the GPU outruns at the start of a short list)
+// is paid once at creation.
+struct b200yolo_plan {
+    cudaGraphExec_t exec;
+    int device, n_batches;
+    unsigned long long kernel_nodes;   // what one launch of the plan adds to b200yolo_launch_count()
+};
+
+int b200yolo_plan_create(const b200yolo_batch *batches, int n_batches, int N, int A, int C, int H0, int W0, int H1, int W1,
+                         const float *anchor_wh, float conf_thr, double iou_thr, b200yolo_plan **plan_out) {
+    if (!plan_out) return fail(B200YOLO_EINVAL, "plan_create: null pointer");
+    *plan_out = nullptr;
+    if (n_batches < 1) return fail(B200YOLO_EINVAL, "plan_create: empty batch list");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaStream_t s = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(s);
+        return fail(B200YOLO_ECUDA, "plan_create: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    }
+    const unsigned long long counted = g_launches.load();
+    const int rc = b200yolo_decode_nms_batches(batches, n_batches, N, A, C, H0, W0, H1, W1, anchor_wh, conf_thr, iou_thr, s);
+    g_launches.fetch_sub(g_launches.load() - counted);   // captured, not executed (a plan is created by one thread at a time)
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(s, &graph);
+    if (rc) {                                  // b200yolo_last_error() already names the cause
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(s);
+        (void)cudaGetLastError();
+        return rc;
+    }
+    if (e != cudaSuccess || !graph) {
+        cudaStreamDestroy(s);
+        return fail(B200YOLO_ECUDA, "plan_create: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    }
+    size_t nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nodes);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e == cudaSuccess) {                    // move the executable graph to the device now, not inside the first launch
+        e = cudaGraphUpload(exec, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) cudaGraphExecDestroy(exec);
+    }
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return fail(B200YOLO_ECUDA, "plan_create: cudaGraphInstantiate / Upload: %s", cudaGetErrorString(e));
+    b200yolo_plan *pl = new (std::nothrow) b200yolo_plan{exec, dev, n_batches, (unsigned long long)nodes};
+    if (!pl) {
+        cudaGraphExecDestroy(exec);
+        return fail(B200YOLO_ECUDA, "plan_create: out of host memory");
+    }
+    *plan_out = pl;
+    return 0;
+}
+
+int b200yolo_plan_launch(b200yolo_plan *plan, void *stream) {
+    if (!plan || !plan->exec) return fail(B200YOLO_EINVAL, "plan_launch: null plan");
+    CUDA_TRY(cudaGraphLaunch(plan->exec, (cudaStream_t)stream));
+    g_launches.fetch_add(plan->kernel_nodes, std::memory_order_relaxed);
+    return 0;
+}
+
+int b200yolo_plan_destroy(b200yolo_plan *plan) {
+    if (!plan) return 0;
+    cudaError_t e = plan->exec ? cudaGraphExecDestroy(plan->exec) : cudaSuccess;
+    delete plan;
+    if (e != cudaSuccess) return fail(B200YOLO_ECUDA, "plan_destroy: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -250,12 +250,38 @@ class BatchPlan:
                                      idx.data_ptr() if idx is not None else None)
         self.args = (N, A, num_classes, H0, W0, H1, W1, self.aw.ctypes.data, float(np.float32(conf_thr)), float(iou_thr))
         self.n = len(batches)
+        self._graph = None
+
+    def capture(self) -> "BatchPlan":
+        """b200yolo_plan_create: freeze the whole list into one CUDA graph; ``run()`` over the whole list then costs the
+        host one graph launch instead of one kernel launch per batch."""
+        if self._graph is None:
+            h = C.c_void_p()
+            with _on_device(self.dev):
+                _lib.check(_lib.load().b200yolo_plan_create(C.cast(self.arr, C.c_void_p), self.n, *self.args, C.byref(h)))
+            self._graph = h
+        return self
+
+    def close(self) -> None:
+        if self._graph is not None:
+            h, self._graph = self._graph, None
+            _lib.check(_lib.load().b200yolo_plan_destroy(h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def run(self, first: int = 0, count: Optional[int] = None):
         """Launch batches [first, first + count) on the current stream of the plan's device."""
         count = self.n - first if count is None else count
         if first < 0 or count < 0 or first + count > self.n:
             raise RuntimeError("BatchPlan.run: range outside the plan")
+        if self._graph is not None and first == 0 and count == self.n:
+            with _on_device(self.dev):
+                _lib.check(_lib.load().b200yolo_plan_launch(self._graph, torch.cuda.current_stream(self.dev).cuda_stream))
+            return
         ptr = C.cast(C.byref(self.arr, first * C.sizeof(_lib.Batch)), C.c_void_p)
         with _on_device(self.dev):
             _lib.check(_lib.load().b200yolo_decode_nms_batches(ptr, count, *self.args,
@@ -389,9 +415,10 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
         sums, status = buf[:_lib.S_COUNT], buf[_lib.S_COUNT:].view(torch.int32)[:1]
         ws_bytes = int(lib.b200yolo_target_loss_workspace_bytes(N))
         key = (head.device.index, torch.cuda.current_stream(head.device).cuda_stream)
-        ws = _WORKSPACES.get(key)
-        if ws is None or ws.numel() < ws_bytes:
-            ws = _WORKSPACES[key] = torch.empty((ws_bytes,), dtype=torch.uint8, device=head.device)
+        ent = _WORKSPACES.get(key)
+        if ent is None or ent[0].numel() < ws_bytes:
+            ent = _WORKSPACES[key] = (torch.empty((ws_bytes,), dtype=torch.uint8, device=head.device), N)
+        ws = ent[0]
         assign = torch.empty((max(G, 1), A, 4), dtype=torch.int32, device=head.device) if want_assign else None
         terms = torch.empty((max(G, 1), A, 2), dtype=torch.float32, device=head.device) if want_assign else None
         _lib.check(lib.b200yolo_target_loss(
@@ -401,6 +428,41 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
             status.data_ptr(), cell_state.data_ptr() if cell_state is not None else None, ws.data_ptr(), ws.numel(),
             _stream(head)))
     return (sums, status, assign, terms) if want_assign else (sums, status)
+
+
+def target_loss_lazy(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, sa: np.ndarray, m: np.ndarray,
+                     num_classes: int, ignore_thr: float, iou_thr: float, iou_weighting: float, max_gt: int,
+                     cell_state: Optional[torch.Tensor]):
+    """b200yolo_target_loss + b200yolo_loss_finalize_dev back to back with the host work of ONE call (one stream lookup,
+    two allocations, prepared anchor / mask arrays, thresholds already rounded to fp32): the ``lazy_stats`` path of
+    ``YOLOLoss.forward``.  Returns (sums (16,) f64, status (1,) i32, result (7,) f32), all on the device."""
+    _require_cuda(head, "head")
+    head = head.contiguous()
+    N, ch, H, W = head.shape
+    A = m.shape[0]
+    if ch != A * (5 + num_classes):
+        raise RuntimeError("head channel dim does not match len(mask)*(5+num_classes)")
+    dev = head.device
+    lib = _lib.load()
+    with _on_device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        buf = torch.empty((_lib.S_COUNT + 1,), dtype=torch.float64, device=dev)
+        res = torch.empty((7,), dtype=torch.float32, device=dev)
+        sums, status = buf[:_lib.S_COUNT], buf[_lib.S_COUNT:].view(torch.int32)[:1]
+        key = (dev.index, st)
+        ws = _WORKSPACES.get(key)
+        if ws is None or ws[1] != N:
+            ws_bytes = int(lib.b200yolo_target_loss_workspace_bytes(N))
+            ws = _WORKSPACES.get(key)
+            t = ws[0] if ws is not None and ws[0].numel() >= ws_bytes else torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            ws = _WORKSPACES[key] = (t, N)
+        _lib.check(lib.b200yolo_target_loss(
+            head.data_ptr(), N, A, num_classes, H, W, sa.ctypes.data, sa.shape[0], m.ctypes.data, gt.data_ptr(),
+            gt_off.data_ptr(), int(G), ignore_thr, iou_thr, int(max_gt), buf.data_ptr(), None, None,
+            buf.data_ptr() + 8 * _lib.S_COUNT, cell_state.data_ptr() if cell_state is not None else None,
+            ws[0].data_ptr(), ws[0].numel(), st))
+        _lib.check(lib.b200yolo_loss_finalize_dev(buf.data_ptr(), iou_weighting, res.data_ptr(), st))
+    return sums, status, res
 
 
 def target_loss_backward(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, anchors_all_scaled,

@@ -62,7 +62,9 @@ class YOLOLoss(nn.Module):
         self.process_group = process_group
         self.last_sums: Optional[torch.Tensor] = None
         self.lazy_stats = False
-        self._pending_status: Optional[torch.Tensor] = None
+        self._pending_status = None           # lazy_stats: (pinned host word, event) of the previous forward
+        self._status_slots = None
+        self._status_turn = 0
 
     # yolo_loss.py:214
     def scaled_anchors(self):
@@ -98,8 +100,38 @@ class YOLOLoss(nn.Module):
     def check(self) -> None:
         """lazy_stats: raise what the last ``forward(input, targets)`` would have raised (one host read)"""
         if self._pending_status is not None:
-            st, self._pending_status = int(self._pending_status.item()), None
-            self._raise_status(st)
+            word, ev = self._pending_status
+            self.__dict__["_pending_status"] = None
+            ev.synchronize()                   # the copy was queued right behind that forward's kernel
+            self._raise_status(int(word))
+
+    def _prepared(self):
+        """scaled anchors, mask and fp32-rounded thresholds as the C call takes them, rebuilt when an attribute changed"""
+        key = (tuple(map(tuple, self.anchors)), tuple(self.img_size), tuple(self.mask), self.ignore_threshold, self.iou_thresh,
+               self.iou_weighting)
+        c = self.__dict__.get("_prep")
+        if c is None or c[0] != key:
+            import numpy as np
+            c = (key, (ops._host_f32(self.scaled_anchors()).reshape(-1, 2),
+                       np.ascontiguousarray(np.asarray(self.mask, dtype=np.int32)),
+                       tuple(float(np.float32(v)) for v in key[3:])))
+            self.__dict__["_prep"] = c
+        return c[1]
+
+    def _post_status(self, status: torch.Tensor) -> None:
+        """lazy_stats: queue the status word's copy to pinned host memory behind the kernel and remember its event, so
+        that the next forward (or check()) reads it without waiting for anything launched after it"""
+        if self._status_slots is None or self._status_slots[0].device != status.device:
+            host = torch.zeros((2,), dtype=torch.int32).pin_memory()
+            self.__dict__["_status_slots"] = (status, host, (torch.cuda.Event(), torch.cuda.Event()), (host[0:1], host[1:2]))
+        _, host, evs, views = self._status_slots
+        k = self.__dict__["_status_turn"] = self._status_turn ^ 1
+        views[k].copy_(status, non_blocking=True)
+        if torch.cuda.current_device() == status.device.index:
+            evs[k].record()
+        else:
+            evs[k].record(torch.cuda.current_stream(status.device))
+        self.__dict__["_pending_status"] = (views[k], evs[k])
 
     def forward(self, input: torch.Tensor, targets=None):
         if targets is None:
@@ -113,6 +145,18 @@ class YOLOLoss(nn.Module):
         x = input.detach()
         N, _, H, W = x.shape
         state = torch.empty((N, self.num_mask * H * W), dtype=torch.uint8, device=x.device) if need_grad else None
+        if self.lazy_stats and self.process_group is None:
+            # no host synchronisation and the host work of one call (ops.target_loss_lazy)
+            sa, m, thr = self._prepared()
+            sums, status, res = ops.target_loss_lazy(x, gt, gt_off, G, sa, m, self.num_classes, thr[0], thr[1], thr[2], max_gt, state)
+            d = self.__dict__                  # (nn.Module.__setattr__ costs 5 us per assignment)
+            d["last_sums"] = sums
+            self.check()                       # the previous call's status: its copy completed long ago, no stall
+            self._post_status(status)
+            loss, recall, avg_iou, obj, no_obj, cls_score, count = res.unbind(0)
+            if need_grad:
+                loss = _LossGrad.apply(input, loss, self, gt, gt_off, G, max_gt, state, sums)
+            return loss, recall, avg_iou, obj, no_obj, cls_score, count
         sums, status = ops.target_loss_sums(x, gt, gt_off, G, self.scaled_anchors(), self.mask, self.num_classes,
                                             self.ignore_threshold, self.iou_thresh, max_gt=max_gt, cell_state=state)
         if self.process_group is not None:
@@ -121,13 +165,12 @@ class YOLOLoss(nn.Module):
             dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.process_group)
         self.last_sums = sums
         if self.lazy_stats:
-            self.check()                       # the previous call's status (already on its way, no stall in steady state)
-            self._pending_status = status
-            r = ops.loss_finalize_dev(sums, self.iou_weighting)
-            loss = r[0]
+            self.check()                       # the previous call's status: its copy completed long ago, no stall
+            self._post_status(status)
+            loss, recall, avg_iou, obj, no_obj, cls_score, count = ops.loss_finalize_dev(sums, self.iou_weighting).unbind(0)
             if need_grad:
                 loss = _LossGrad.apply(input, loss, self, gt, gt_off, G, max_gt, state, sums)
-            return loss, r[1], r[2], r[3], r[4], r[5], r[6]
+            return loss, recall, avg_iou, obj, no_obj, cls_score, count
         host = torch.cat((sums, status.to(torch.float64))).cpu().numpy()  # one D2H sync (the reference has ~5 per GT)
         self._raise_status(int(host[-1]))
         r = ops.loss_finalize(host[:_lib.S_COUNT], self.iou_weighting)

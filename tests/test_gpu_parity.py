@@ -1118,6 +1118,26 @@ def test_batches_entry_equals_single_calls(cuda_device):
     plan.run(1, 2)   # a sub-range of the plan
     torch.cuda.synchronize()
     assert torch.equal(want[2][1], batches[2][3])
+    # b200yolo_plan_create / _launch / _destroy: the same list replayed from one CUDA graph, twice, on a side stream
+    plan.capture()
+    side = torch.cuda.Stream(device=cuda_device)
+    for rep in range(2):
+        for bt in batches:
+            bt[2].zero_(); bt[3].zero_(); bt[4].zero_()
+        side.wait_stream(torch.cuda.current_stream(cuda_device))
+        with torch.cuda.stream(side):
+            plan.run()
+        side.synchronize()
+        for (o, c, i), bt in zip(want, batches):
+            assert torch.equal(c, bt[3])
+            for b, k in enumerate(c.cpu().numpy()):
+                assert torch.equal(o[b, :k], bt[2][b, :k]) and torch.equal(i[b, :k], bt[4][b, :k])
+    plan.close()
+    plan.run()       # after close(): plain launches again
+    torch.cuda.synchronize()
+    assert torch.equal(want[4][1], batches[4][3])
+    bad = ops._lib.load().b200yolo_plan_launch(None, None)
+    assert bad == ops._lib.EINVAL if hasattr(ops._lib, "EINVAL") else bad != 0
 
 
 def test_lazy_stats_and_packed_targets(cuda_device):
