@@ -64,7 +64,9 @@ void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
  * use the compile-time head shapes (every shape then runs the runtime-stride decode), 32 = always wait for the
  * previous kernel before the first global read, 64 = three CTAs of 384 threads per SM for the VOC-352 shape
  * (experiment), 128 = "exact" decode: IEEE sigmoid / expf and a true division by the grid size, the reference's own
- * operations, instead of the SFU forms and the multiplication by the reciprocal (profiles/exact_decode.py). */
+ * operations, instead of the SFU forms and the multiplication by the reciprocal (profiles/exact_decode.py),
+ * 512 = with phase stamps: the buffer is a ring of 16 launches ([16][N][32]) and the stamped launches overlap like
+ * production launches (steady-state phase times). */
 void b200yolo_debug_set_flags(int flags);
 
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that

@@ -25,6 +25,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long *> g_dbg{nullptr};  // profiling aid, see b200yolo_debug_phase_stamps
+std::atomic<unsigned> g_dbg_seq{0};
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_flags{[] { const char *e = getenv("B200YOLO_FLAGS"); return e ? atoi(e) : 0; }()};  // experiment switches
 std::atomic<int> g_inputs_ready{0};   // see b200yolo_set_inputs_ready
@@ -237,6 +238,9 @@ int launch_dn(DNParams &p, cudaStream_t st) {
     while ((1 << p.Bshift) < p.B) ++p.Bshift;
     p.dbg = g_dbg.load();
     p.flags = g_flags.load();
+    // flag 512 (profiling aid): the stamp buffer is a ring of 16 launches of N x 32 words and the stamped launches
+    // overlap like production launches (phase times in steady state, profiles/phase_times.py --steady)
+    if (p.dbg && (p.flags & 512)) p.dbg += (size_t)(g_dbg_seq.fetch_add(1) % 16) * (size_t)p.N * 32;
     // Programmatic dependent launch lets this kernel start while its predecessor in the stream is still running.
     // That is only harmless when the predecessor does not produce this kernel's inputs -- true for back-to-back
     // launches of this library on different batches, NOT true in general (CUDA makes a predecessor's writes
@@ -410,7 +414,7 @@ int b200yolo_version(void) { return B200YOLO_VERSION; }
 const char *b200yolo_last_error(void) { return g_err; }
 unsigned long long b200yolo_launch_count(void) { return g_launches.load(); }
 
-void b200yolo_debug_phase_stamps(unsigned long long *dev_buf) { g_dbg.store(dev_buf); }
+void b200yolo_debug_phase_stamps(unsigned long long *dev_buf) { g_dbg.store(dev_buf); g_dbg_seq.store(0); }
 void b200yolo_debug_set_flags(int flags) { g_flags.store(flags); }
 void b200yolo_set_inputs_ready(int ready) { g_inputs_ready.store(ready ? 1 : 0); }
 void b200yolo_set_exact_decode(int exact) {

@@ -710,6 +710,7 @@ __device__ __forceinline__ void warp_class_starts(const DNParams &p, const Smem 
     const int lane = threadIdx.x & 31;
     const int C = p.C;
     int carry = 0;
+#pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
         const int n = (c < C) ? s.cnt[c] : 0;
@@ -755,6 +756,7 @@ __device__ __forceinline__ void warp_tile_tables(const DNParams &p, const Smem &
     const int lane = threadIdx.x & 31;
     const int C = p.C;
     int carryT = 0, tmax = 0;
+#pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + lane;
         const int n = (c < C) ? s.cnt[c] : 0;
@@ -763,6 +765,7 @@ __device__ __forceinline__ void warp_tile_tables(const DNParams &p, const Smem &
         if (c < C) {
             const int kt = carryT + incT - T;
             s.ktile[c] = kt;
+#pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 s.keptw[kt + t] = 0u;
                 s.supw[kt + t] = 0u;
@@ -1407,7 +1410,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     // Inputs another kernel of this library wrote (rows of our own decode kernels), or a producer launched with the
     // programmatic attribute, must be complete and visible before the first global read: p.wait_inputs is set by the
     // host unless the caller vouches that the inputs were produced in ordinary stream order (see launch_dn_t).
-    if (MODE == MODE_NMS || p.wait_inputs || (DBG && p.dbg)) pdl_wait();
+    if (MODE == MODE_NMS || p.wait_inputs || (DBG && p.dbg && !(p.flags & 512))) pdl_wait();
     stamp<DBG>(p, b, 0);
     if (MODE != MODE_NMS) {
         // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
@@ -1496,23 +1499,26 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     scan_buckets_per_class<THREADS>(p, s);
     __syncthreads();
     stamp<DBG>(p, b, 12);
-    if (warp == 0) {
-        warp_class_starts(p, s);
-        warp_tile_tables(p, s);
-    }
+    // A phase that one warp executes alone runs at instruction-fetch latency (the two resident CTAs are in different
+    // phases of a ~100 KB kernel: ~200 cycles per 8 instructions, profiles/r02/NOTES.md), and the other 15 warps wait
+    // for it: only the class starts, which the key scatter needs, stay in such a window.
+    if (warp == 0) warp_class_starts(p, s);
     __syncthreads();
     stamp<DBG>(p, b, 13);
     const int Kv = s.misc[M_KV];
     if (warp == 0) {
-        // the strip tasks: only the pair phase needs them, so warp 0 builds them while the other warps sort
+        // the tile tables (the ranking needs ktile: barrier 2) and the strip tasks (only the pair phase needs them)
+        // are built while the other warps sort
+        warp_tile_tables(p, s);
+        asm volatile("bar.arrive 2, %0;" ::"n"(THREADS) : "memory");
         warp_build_tasks(p, s);
     } else {
-        // P3 / P4 on the other warps (named barrier 1 between the key scatter, the ranking, and the writes that
-        // reuse the key memory)
+        // P3 / P4 on the other warps (barrier 2 between the key scatter and the ranking: all keys in place, and warp 0's
+        // tile tables; named barrier 1 between the ranking and the writes that reuse the key memory)
         constexpr int kSorters = THREADS - 32;
         uint32_t item[kRankItems];
         phase_scatter_keys(p, s, tid - 32, kSorters);
-        asm volatile("bar.sync 1, %0;" ::"n"(kSorters) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory");
         phase_rank<kRankItems>(p, s, Kv, tid - 32, kSorters, item);
         asm volatile("bar.sync 1, %0;" ::"n"(kSorters) : "memory");
         phase_write_sorted<kRankItems>(p, s, item);

@@ -2,7 +2,8 @@
 """Per-phase time of the fused decode+NMS kernel from in-kernel stamps (b200yolo_debug_phase_stamps):
 %globaltimer (256 ns resolution) for the launch span across CTAs, the SM cycle counter for the phases
 inside a CTA.  Prints, per workload, the median over images of each phase.
-    PHASE_N=32 python profiles/phase_times.py cfg2 cfg2_sparse"""
+    PHASE_N=32 python profiles/phase_times.py cfg2 cfg2_sparse
+    PHASE_STEADY=1 ...: 16 overlapping launches from one C call (flag 512), the stamps of launch 9 are reported"""
 import os
 import sys
 
@@ -27,13 +28,35 @@ for name in sys.argv[1:] or ["cfg2", "cfg2_sparse"]:
     sets = [tuple(h.to(dev) for h in bench.make_heads(wl, N, seed=s)) for s in range(3)]
     big = torch.empty(64 << 20, dtype=torch.float32, device=dev)
     dbg = torch.zeros((N, 32), dtype=torch.int64, device=dev)
-    for i in range(4):
-        big.fill_(float(i))
-        if i == 3:
-            _lib.load().b200yolo_debug_phase_stamps(dbg.data_ptr())
-        ops.decode_nms_padded(sets[i % 3][0], sets[i % 3][1], tables, wl["C"], wl["conf"])
-    torch.cuda.synchronize()
-    _lib.load().b200yolo_debug_phase_stamps(None)
+    if os.environ.get("PHASE_STEADY"):
+        K = bench.cells_per_image(wl)
+        sets = [tuple(h.to(dev) for h in bench.make_heads(wl, N, seed=s)) for s in range(9)]
+        out = torch.empty((N, K, 7), dtype=torch.float32, device=dev)
+        cnt = torch.empty((N,), dtype=torch.int32, device=dev)
+        plan = ops.BatchPlan([(sets[i % 9][0], sets[i % 9][1], out, cnt) for i in range(16)], tables, wl["C"], wl["conf"])
+        ring = torch.zeros((16, N, 32), dtype=torch.int64, device=dev)
+        base = int(os.environ.get("B200YOLO_FLAGS", "0"))
+        _lib.load().b200yolo_debug_set_flags(base | 512)
+        _lib.load().b200yolo_debug_phase_stamps(ring.data_ptr())
+        plan.run()
+        torch.cuda.synchronize()
+        _lib.load().b200yolo_debug_phase_stamps(ring.data_ptr())
+        plan.run()
+        torch.cuda.synchronize()
+        _lib.load().b200yolo_debug_phase_stamps(None)
+        _lib.load().b200yolo_debug_set_flags(base)
+        allg = ring.cpu().numpy().astype(np.float64)
+        span = allg[:, :, 7].max() - allg[:, :, 0].min()
+        print(f"== {name}: 16 overlapped stamped launches span {span / 1e3:.1f} us = {span / 16e3:.2f} us per launch")
+        dbg = ring[9]
+    else:
+        for i in range(4):
+            big.fill_(float(i))
+            if i == 3:
+                _lib.load().b200yolo_debug_phase_stamps(dbg.data_ptr())
+            ops.decode_nms_padded(sets[i % 3][0], sets[i % 3][1], tables, wl["C"], wl["conf"])
+        torch.cuda.synchronize()
+        _lib.load().b200yolo_debug_phase_stamps(None)
     raw = dbg.cpu().numpy().astype(np.float64)
     g, c = raw[:, :16], raw[:, 16:]
     t0 = g[:, 0].min()
