@@ -442,8 +442,18 @@ class DecodeNmsRun:
             self.sets.append((h0.to(D.dev), h1.to(D.dev)))
         self.large = self.K > _lib.load().b200yolo_max_cells(D.local)
         self.gather = gather and D.world > 1 and not self.large
-        self.out = torch.empty((n_local, self.K, 7), dtype=torch.float32, device=D.dev)
-        self.cnt = torch.empty((n_local,), dtype=torch.int32, device=D.dev)
+        # two result buffers in rotation (what a consumer that works on step k while step k + 1 runs needs anyway):
+        # consecutive launches then write disjoint outputs and are chained (no wait before the stores, include/b200yolo.h)
+        # Every step of the list keeps its own result buffer (an evaluation loop that collects the detections of every
+        # batch) while that stays below 2 GB, else two buffers in rotation: launches that write disjoint outputs do not
+        # wait for their predecessor before they store (include/b200yolo.h, b200yolo_decode_nms_batches)
+        out_bytes = n_local * self.K * 28
+        n_out = steps if steps * out_bytes <= (2 << 30) else 2
+        if gather and D.world > 1:
+            n_out = 1
+        self.outs = [(torch.empty((n_local, self.K, 7), dtype=torch.float32, device=D.dev),
+                      torch.empty((n_local,), dtype=torch.int32, device=D.dev)) for _ in range(max(n_out, 1))]
+        self.out, self.cnt = self.outs[0]
         self.ops = ops
         self.pg = None
         if self.large:
@@ -453,7 +463,7 @@ class DecodeNmsRun:
             self.plan = self.pg.run_steps([self.sets[i % self.R] for i in range(steps)], self.tables, wl["C"], wl["conf"])
             torch.cuda.synchronize()
         else:
-            self.plan = ops.BatchPlan([(self.sets[i % self.R][0], self.sets[i % self.R][1], self.out, self.cnt) for i in range(steps)],
+            self.plan = ops.BatchPlan([(self.sets[i % self.R][0], self.sets[i % self.R][1]) + self.outs[i % len(self.outs)] for i in range(steps)],
                                       self.tables, wl["C"], wl["conf"])
             if graph:
                 self.plan.capture()   # b200yolo_plan_create: the K launches as one CUDA graph (K kernel nodes, programmatic edges)

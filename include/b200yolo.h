@@ -66,7 +66,9 @@ void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
  * (experiment), 128 = "exact" decode: IEEE sigmoid / expf and a true division by the grid size, the reference's own
  * operations, instead of the SFU forms and the multiplication by the reciprocal (profiles/exact_decode.py),
  * 512 = with phase stamps: the buffer is a ring of 16 launches ([16][N][32]) and the stamped launches overlap like
- * production launches (steady-state phase times). */
+ * production launches (steady-state phase times), 1024 = b200yolo_decode_nms_batches: every launch waits for its
+ * predecessor before it stores even when the outputs are disjoint, 2048 = ... at most two launches in flight even when
+ * no two batches share an output. */
 void b200yolo_debug_set_flags(int flags);
 
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that
@@ -116,9 +118,15 @@ int b200yolo_decode_nms(const float *head0, const float *head1, int N, int A, in
  * batch after batch (the evaluation loop train.py:357-395, a serving queue), as one call.  Launch k runs the fused
  * kernel on batches[k]; because launch k > 0 directly follows the library's own launch k - 1 in the stream -- which
  * writes nothing that launch k reads -- it is allowed to start on the SM slots its predecessor leaves free and to
- * stream its heads under the predecessor's NMS (programmatic dependent launch); every launch waits for its
- * predecessor before it writes.  The first launch waits for whatever precedes the call in the stream before it
- * reads.  No batch's `out` / `out_count` / `out_idx` may alias another batch's heads.
+ * stream its heads under the predecessor's NMS (programmatic dependent launch).  The first launch waits for whatever
+ * precedes the call in the stream before it reads.  No batch's `out` / `out_count` / `out_idx` may alias another batch's
+ * heads.  Outputs and ordering (decided per call from the pointers):
+ *   - some consecutive batches share an output buffer: every launch waits for its predecessor before it stores;
+ *   - consecutive batches write disjoint buffers (results in a ring of two or more): no launch waits before it
+ *     stores; one extra CTA per launch keeps at most two launches in flight, so a buffer is never written while the
+ *     launch that used it two steps earlier still runs;
+ *   - no two batches of the list share an output buffer: launches are not ordered against each other at all.
+ * In every case a launch completes after its predecessor, so whatever follows the call in the stream sees all results.
  */
 typedef struct b200yolo_batch {
     const float *head0, *head1; /* dev (N, A*(5+C), H0, W0), (N, A*(5+C), H1, W1) */

@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <vector>
 #include <new>
 
 #include "decode_nms.cuh"  // (after the helpers it uses)
@@ -150,7 +152,10 @@ int launch_dn_t(DNParams &p, const SmemLayout &L, int dev, cudaStream_t st) {
     // programmatic dependent launch: consecutive launches of this kernel overlap (decode_nms.cuh, pdl_trigger / pdl_wait)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)p.N + (((variant == 1 || variant == 4) && p.gsignal > 0) ? 1u : 0u));   // (+ the signalling CTA, decode_nms.cuh)
+    const bool gather_variant = (variant == 1 || variant == 4);
+    if (gather_variant || MODE != MODE_FUSED) p.chain = 0;
+    // (+ the signalling CTA of the gather, or the chain CTA of a list of batches: decode_nms.cuh)
+    cfg.gridDim = dim3((unsigned)p.N + ((gather_variant ? p.gsignal > 0 : p.chain >= 2) ? 1u : 0u));
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = st;
@@ -539,7 +544,40 @@ int b200yolo_decode_nms_batches(const b200yolo_batch *batches, int n_batches, in
     p.K = (int)cells;
     p.conf_thr = conf_thr;
     p.iou = make_thr(iou_thr);
+    // consecutive batches with disjoint outputs (a ring of two or more result buffers): the launches are chained and
+    // do not wait for their predecessor before they store (DNParams::chain); flag 1024 switches it off
+    bool chained = n_batches >= 2 && N > 0 && !(g_flags.load() & 1024);
+    for (int k = 1; k < n_batches && chained; ++k) {
+        const b200yolo_batch &x = batches[k], &y = batches[k - 1];
+        const size_t rows = (size_t)N * (size_t)cells;
+        const void *px[3] = {x.out, x.out_count, x.out_idx}, *py[3] = {y.out, y.out_count, y.out_idx};
+        const size_t len[3] = {rows * 7 * sizeof(float), (size_t)N * sizeof(int), rows * sizeof(int)};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                if (!px[i] || !py[j]) continue;
+                const uintptr_t a0 = (uintptr_t)px[i], a1 = a0 + len[i], b0 = (uintptr_t)py[j], b1 = b0 + len[j];
+                if (a0 < b1 && b0 < a1) chained = false;
+            }
+    }
+    // ... and when no two batches of the list share an output at all, nothing needs to order the stores (chain 3);
+    // flag 2048 keeps the two-in-flight chain
+    bool all_distinct = chained && !(g_flags.load() & 2048);
+    if (all_distinct) {
+        struct Span { uintptr_t lo, hi; };
+        std::vector<Span> spans;
+        spans.reserve(3 * (size_t)n_batches);
+        const size_t rows = (size_t)N * (size_t)cells;
+        for (int k = 0; k < n_batches; ++k) {
+            spans.push_back({(uintptr_t)batches[k].out, (uintptr_t)batches[k].out + rows * 7 * sizeof(float)});
+            spans.push_back({(uintptr_t)batches[k].out_count, (uintptr_t)batches[k].out_count + (size_t)N * sizeof(int)});
+            if (batches[k].out_idx) spans.push_back({(uintptr_t)batches[k].out_idx, (uintptr_t)batches[k].out_idx + rows * sizeof(int)});
+        }
+        std::sort(spans.begin(), spans.end(), [](const Span &a, const Span &b) { return a.lo < b.lo; });
+        for (size_t i = 1; i < spans.size(); ++i)
+            if (spans[i].lo < spans[i - 1].hi) all_distinct = false;
+    }
     for (int k = 0; k < n_batches; ++k) {
+        p.chain = chained ? (k == 0 ? 1 : all_distinct ? 3 : 2) : 0;
         fill_head(p.head[0], batches[k].head0, A, H0, W0, anchor_wh);
         fill_head(p.head[1], batches[k].head1, A, H1, W1, anchor_wh + 2 * A);
         p.out = batches[k].out; p.out_count = batches[k].out_count; p.out_idx = batches[k].out_idx;

@@ -105,6 +105,15 @@ struct DNParams {
     int B;               // score buckets per class of the counting sort (power of two)
     int Bshift;          // log2(B)
     int wait_inputs;     // 1: griddepcontrol.wait before the first global read (see launch_dn_t)
+    // Launches of a list whose consecutive batches write disjoint outputs (b200yolo_decode_nms_batches) need not wait for
+    // their predecessor before they store.  What keeps the list ordered is a chain: 1 = first launch of such a list: every
+    // CTA waits for whatever precedes the list and only then lets the next launch start; 2 = a later launch: its CTAs
+    // never wait, and one extra CTA (blockIdx.x == N) waits for the previous launch to complete before IT lets the next
+    // launch start -- so launch k + 1 starts after launch k - 1 has completed (two launches in flight, outputs in a
+    // ring of two are safe) and every launch completes after its predecessor.  3 = a later launch of a list in which NO
+    // two batches share an output: nothing orders the stores, the extra CTA only waits (a launch still completes after
+    // its predecessor), and launch k + 1 starts as soon as every CTA of launch k has.  0 = single call: wait before storing.
+    int chain;
     int flags;           // experiment switches (B200YOLO_FLAGS env): 1 = no L2 prefetch, 8 = prefetch both heads
     int nhwc;            // > 0: heads are channels-last, (N, H, W, A*(5+C)) in memory (fused mode only); the value is the
                          // number of warps that stage + decode (32 cells each per step; what the free shared memory allows)
@@ -1392,7 +1401,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     const int C = p.C, K = p.K;
     using SH = ShapeT<SHAPE>;
 
-    pdl_trigger();  // the next launch may start filling free SM slots right away (it waits before it writes)
+    if constexpr (GATHER == 0) {
+        if (p.chain >= 2 && b == p.N) {   // the chain CTA
+            if (p.chain == 3) pdl_trigger();
+            pdl_wait();
+            pdl_trigger();
+            return;
+        }
+        if (p.chain != 1) pdl_trigger();  // the next launch may start filling free SM slots right away
+    } else {
+        pdl_trigger();
+    }
     if constexpr (GATHER != 0) {
         // The arrival signal of the PREVIOUS step rides on this launch (a kernel of its own per step costs ~2.3 us of
         // launch processing, and a system-scope fence in every CTA of the step itself flushes the L1 the decode
@@ -1410,7 +1429,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     // Inputs another kernel of this library wrote (rows of our own decode kernels), or a producer launched with the
     // programmatic attribute, must be complete and visible before the first global read: p.wait_inputs is set by the
     // host unless the caller vouches that the inputs were produced in ordinary stream order (see launch_dn_t).
-    if (MODE == MODE_NMS || p.wait_inputs || (DBG && p.dbg && !(p.flags & 512))) pdl_wait();
+    if (MODE == MODE_NMS || p.wait_inputs || p.chain == 1 || (DBG && p.dbg && !(p.flags & 512))) pdl_wait();
+    if constexpr (GATHER == 0) {
+        if (p.chain == 1) pdl_trigger();
+    }
     stamp<DBG>(p, b, 0);
     if (MODE != MODE_NMS) {
         // Start the HBM -> L2 stream of the FIRST head now, so that the first decode round (which can
@@ -1533,7 +1555,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     // before its first store (consecutive launches may share the output buffers).  The gather variant needs no such
     // wait: consecutive steps store into different buffers, and what orders a step against the previous users of ITS
     // buffer is the flag wait below -- so a step's stores, and their NVLink round trips, overlap the previous step's tail.
-    if constexpr (GATHER == 0) pdl_wait();
+    if constexpr (GATHER == 0) {
+        if (p.chain < 2) pdl_wait();
+    }
     if constexpr (GATHER != 0) {
         // the gather buffer this step writes was last used three steps ago: wait until every rank has completed the
         // previous step, i.e. has moved past everything it ran on that buffer (dist.PeerGather, back-pressure)
@@ -1550,6 +1574,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
             __syncthreads();
         }
     }
+    stamp<DBG>(p, b, 5);
     phase_output<MODE, THREADS, GATHER>(p, s, b);
     stamp<DBG>(p, b, 7);
 }

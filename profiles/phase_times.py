@@ -18,7 +18,7 @@ from mobilenet_yolo_pytorch_b200 import _lib, ops
 ORDER = [(0, "start"), (15, "init"), (8, "decode round 1"), (9, "decode round 2"), (10, "decode round 3"),
          (11, "decode round 4+"), (1, "decode done (barrier)"), (12, "bucket scan per class + barrier"),
          (13, "class starts (warp 0) + barrier"), (3, "tables (warp 0) | scatter, rank (others) + barrier"),
-         (4, "pairs + sweep + barrier"), (7, "output")]
+         (4, "pairs + sweep + barrier"), (5, "wait for the previous launch"), (7, "output (warp 0's tiles)")]
 dev = torch.device("cuda", 0)
 MHZ = 1965.0
 for name in sys.argv[1:] or ["cfg2", "cfg2_sparse"]:

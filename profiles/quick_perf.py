@@ -28,12 +28,14 @@ for name in a.workloads:
     in_bytes = N * bench.bytes_in_per_image(wl)
     R = max(4, int(np.ceil(400e6 / in_bytes)))
     sets = [tuple(h.to(dev) for h in bench.make_heads(wl, N, seed=r)) for r in range(R)]
-    out = torch.empty((N, K, 7), dtype=torch.float32, device=dev)
-    cnt = torch.empty((N,), dtype=torch.int32, device=dev)
+    ring = int(os.environ.get("OUT_RING", "2"))   # result buffers in rotation (>= 2: chained launches, no wait before the stores)
+    ring = a.steps if ring == 0 else ring          # 0: every step has its own result buffer
+    outs = [(torch.empty((N, K, 7), dtype=torch.float32, device=dev), torch.empty((N,), dtype=torch.int32, device=dev)) for _ in range(ring)]
+    out, cnt = outs[0]
     if K > _lib.load().b200yolo_max_cells(0):
         print(name, "large-image path: skipped here")
         continue
-    plan = ops.BatchPlan([(sets[i % R][0], sets[i % R][1], out, cnt) for i in range(a.steps)], tables, wl["C"], wl["conf"])
+    plan = ops.BatchPlan([(sets[i % R][0], sets[i % R][1]) + outs[i % ring] for i in range(a.steps)], tables, wl["C"], wl["conf"])
     plan.run(0, min(10, a.steps))
     torch.cuda.synchronize()
     kept = float(cnt.sum().item())

@@ -1118,6 +1118,25 @@ def test_batches_entry_equals_single_calls(cuda_device):
     plan.run(1, 2)   # a sub-range of the plan
     torch.cuda.synchronize()
     assert torch.equal(want[2][1], batches[2][3])
+    # (the batches above write disjoint outputs: chained launches that do not wait before they store.)  All batches into
+    # ONE output: every launch waits for its predecessor before storing, and the last batch's results are what remains
+    shared = [(bt[0], bt[1], batches[0][2], batches[0][3], batches[0][4]) for bt in batches]
+    ops.BatchPlan(shared, tables, C, 0.3).run()
+    torch.cuda.synchronize()
+    o, c, i = want[-1]
+    assert torch.equal(c, batches[0][3])
+    for b, k in enumerate(c.cpu().numpy()):
+        assert torch.equal(o[b, :k], batches[0][2][b, :k]) and torch.equal(i[b, :k], batches[0][4][b, :k])
+    # a ring of two outputs, 12 launches: slots hold the last two batches
+    ring = [tuple(torch.zeros_like(t) for t in want[0]) for _ in range(2)]
+    order = [k % 5 for k in range(12)]
+    ops.BatchPlan([(batches[k][0], batches[k][1]) + ring[j % 2] for j, k in enumerate(order)], tables, C, 0.3).run()
+    torch.cuda.synchronize()
+    for slot, k in ((0, order[10]), (1, order[11])):
+        o, c, i = want[k]
+        assert torch.equal(c, ring[slot][1])
+        for b, n in enumerate(c.cpu().numpy()):
+            assert torch.equal(o[b, :n], ring[slot][0][b, :n]) and torch.equal(i[b, :n], ring[slot][2][b, :n])
     # b200yolo_plan_create / _launch / _destroy: the same list replayed from one CUDA graph, twice, on a side stream
     plan.capture()
     side = torch.cuda.Stream(device=cuda_device)
