@@ -428,7 +428,7 @@ class DecodeNmsRun:
     """K steps of decode + NMS on this rank's shard, issued by one C call.  world > 1: kernel + fused all-gather
     (peer stores over NVLink) + fence per step."""
 
-    def __init__(self, D, wl, n_local, steps, gather=True, seed0=0, graph=True):
+    def __init__(self, D, wl, n_local, steps, gather=True, seed0=0, graph=True, multicast=False):
         from mobilenet_yolo_pytorch_b200 import _lib, ops
         from mobilenet_yolo_pytorch_b200 import dist as b2dist
         self.D, self.wl, self.N, self.steps = D, wl, n_local, steps
@@ -459,7 +459,7 @@ class DecodeNmsRun:
         if self.large:
             self.plan = None
         elif self.gather:
-            self.pg = b2dist.PeerGather(n_local, self.K)
+            self.pg = b2dist.PeerGather(n_local, self.K, multicast=multicast)
             self.plan = self.pg.run_steps([self.sets[i % self.R] for i in range(steps)], self.tables, wl["C"], wl["conf"])
             torch.cuda.synchronize()
         else:
@@ -661,6 +661,19 @@ def run_b200(args, name, wl):
                                             "bytes_gathered_per_rank": int(world * N * (K + 1) * 28),
                                             "note": "kernel, then ncclAllGather of the fixed-stride (N, K+1, 7) block"}
             solo.close()
+            # the same step with the gather buffers in NVSwitch multicast memory (one store per row, replicated by the switch)
+            mc_ok = [None] * world
+            torch.distributed.all_gather_object(mc_ok, bool(lib.b200yolo_mc_supported(local)))
+            if all(mc_ok):
+                mrun = DecodeNmsRun(D, wl, N, args.steps, multicast=True)
+                mc_ms = mrun.time(args.warmup)
+                mrun.close()
+                extra["with_multicast"] = {"ms_per_step": mc_ms, "images_per_s": total_images / (mc_ms * 1e-3),
+                                           "note": "every row stored once through the switch instead of once per peer: egress drops "
+                                                   "(R-1)-fold, but every rank still RECEIVES all rows -- plus its own copy back "
+                                                   "through the switch -- and ingress is what bounds the exchange"}
+            else:
+                extra["with_multicast"] = {"unavailable": "cuMulticast* not supported on every rank"}
         run.close()
         # sparse-head variant of the same workload (trained heads pass ~4% of cells), same protocol
         if wl["shift"] == 0.0 and name == "cfg2":

@@ -255,6 +255,25 @@ int b200yolo_peer_fence(int *const *peer_flags, const int *own_flags, int R, int
  * Contract for consumers: read the buffers of step s after its fence, with ordinary launches, before launching step
  * s + 1.
  */
+/*
+ * NVSwitch multicast memory for the gather buffers: a store to the multicast view is replicated by the switch into
+ * the memory every GPU of the group has bound at the same offset, so a kept row leaves its GPU once instead of once per
+ * peer (the all-gather's egress drops from (R - 1) x to 1 x).  Set-up, one process per GPU, `bytes` equal on all:
+ *   rank 0:       b200yolo_mc_create -> a POSIX file descriptor, to be passed to the other processes (SCM_RIGHTS)
+ *   other ranks:  b200yolo_mc_import(fd)
+ *   all ranks:    b200yolo_mc_add_device; barrier; b200yolo_mc_bind -> local_ptr (this GPU's memory, for readers) and
+ *                 mc_ptr (the multicast view, for the kernel's stores); barrier before the first store
+ * b200yolo_mc_supported: 1 when the device and driver offer it.  The driver API is resolved at run time (dlopen), so
+ * the library has no link dependency on libcuda.
+ */
+typedef struct b200yolo_mc b200yolo_mc;
+int b200yolo_mc_supported(int device);
+int b200yolo_mc_create(size_t bytes, int n_devices, int *fd, b200yolo_mc **mc);
+int b200yolo_mc_import(size_t bytes, int n_devices, int fd, b200yolo_mc **mc);
+int b200yolo_mc_add_device(b200yolo_mc *mc);
+int b200yolo_mc_bind(b200yolo_mc *mc, void **local_ptr, void **mc_ptr);
+int b200yolo_mc_free(b200yolo_mc *mc);
+
 #define B200YOLO_GATHER_BUFFERS 3
 typedef struct b200yolo_gather {
     int R, rank;
@@ -263,6 +282,8 @@ typedef struct b200yolo_gather {
     int *peer_flags[8];     /* [r]: rank r's arrival flags dev int32 [8] */
     int *timed_out;         /* own dev int32[1], zero it once */
     double timeout_s;       /* per wait, <= 60; <= 0: 5 s */
+    int multicast;          /* != 0: peer_out[buffer][0] / peer_count[buffer][0] are NVSwitch multicast addresses
+                               (b200yolo_mc_bind) that reach the buffer of EVERY rank; the other entries are ignored */
 } b200yolo_gather;
 int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_batch *batches, int n_steps, int first_step,
                                      int final_fence, int N, int A, int C, int H0, int W0, int H1, int W1,

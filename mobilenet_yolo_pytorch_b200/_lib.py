@@ -38,6 +38,12 @@ SIGNATURES = {
                                        C.c_void_p, C.c_float, C.c_double, C.POINTER(C.c_void_p)]),
     "b200yolo_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200yolo_plan_destroy": (C.c_int, [C.c_void_p]),
+    "b200yolo_mc_supported": (C.c_int, [C.c_int]),
+    "b200yolo_mc_create": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "b200yolo_mc_import": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200yolo_mc_add_device": (C.c_int, [C.c_void_p]),
+    "b200yolo_mc_bind": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "b200yolo_mc_free": (C.c_int, [C.c_void_p]),
     "b200yolo_set_inputs_ready": (None, [C.c_int]),
     "b200yolo_set_exact_decode": (None, [C.c_int]),
     "b200yolo_decode_nms_nhwc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -100,7 +106,7 @@ class Batch(C.Structure):
 class Gather(C.Structure):
     """struct b200yolo_gather (include/b200yolo.h)."""
     _fields_ = [("R", C.c_int), ("rank", C.c_int), ("peer_out", (C.c_void_p * 8) * 3), ("peer_count", (C.c_void_p * 8) * 3),
-                ("peer_flags", C.c_void_p * 8), ("timed_out", C.c_void_p), ("timeout_s", C.c_double)]
+                ("peer_flags", C.c_void_p * 8), ("timed_out", C.c_void_p), ("timeout_s", C.c_double), ("multicast", C.c_int)]
 
 
 class B200YoloError(RuntimeError):

@@ -9,6 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda.h>      // driver API types; the entry points are resolved with dlopen (no link dependency)
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -690,6 +693,7 @@ int b200yolo_decode_nms_gather(const float *head0, const float *head1, int N, in
     p.gslot = rank * N;
     // every rank starts with its own buffer and walks the ring from there, so at any moment the ranks store into
     // different peers instead of all hitting rank 0 first
+    p.gnbuf = R;
     for (int i = 0; i < R; ++i) { p.gout[i] = peer_out[(rank + i) % R]; p.gcount[i] = peer_count[(rank + i) % R]; }
     p.wait_inputs = 1;
     return launch_dn<MODE_FUSED>(p, (cudaStream_t)stream);
@@ -722,7 +726,7 @@ int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_ba
     if (!(iou_thr == iou_thr)) return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: NaN threshold");
     for (int par = 0; par < B200YOLO_GATHER_BUFFERS; ++par)
         for (int r = 0; r < R; ++r)
-            if (!g->peer_out[par][r] || !g->peer_count[par][r] || !g->peer_flags[r])
+            if (!g->peer_flags[r] || ((r == 0 || !g->multicast) && (!g->peer_out[par][r] || !g->peer_count[par][r])))
                 return fail(B200YOLO_EINVAL, "decode_nms_gather_steps: null buffer of rank %d", r);
     const long long cells = (long long)A * H0 * W0 + (long long)A * H1 * W1;
     if (cells > 65535) return fail(B200YOLO_EUNSUPPORTED, "decode_nms_gather_steps: more than 65535 cells per image");
@@ -749,7 +753,14 @@ int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_ba
         fill_head(p.head[0], batches[k].head0, A, H0, W0, anchor_wh);
         fill_head(p.head[1], batches[k].head1, A, H1, W1, anchor_wh + 2 * A);
         // every rank starts with its own buffer and walks the ring from there (the ranks hit different peers)
-        for (int i = 0; i < R; ++i) { p.gout[i] = g->peer_out[par][(rank + i) % R]; p.gcount[i] = g->peer_count[par][(rank + i) % R]; }
+        if (g->multicast) {   // one store through the switch reaches every rank's buffer
+            p.gnbuf = 1;
+            p.gout[0] = g->peer_out[par][0];
+            p.gcount[0] = g->peer_count[par][0];
+        } else {
+            p.gnbuf = R;
+            for (int i = 0; i < R; ++i) { p.gout[i] = g->peer_out[par][(rank + i) % R]; p.gcount[i] = g->peer_count[par][(rank + i) % R]; }
+        }
         // Buffer step % 3 was last used by step - 3.  A rank whose flag shows step - 1 has COMPLETED step - 2, whose
         // launch follows -- in that rank's stream -- everything it ran on the buffers of step - 3.  Waiting for the
         // flags of two steps ago never stalls a pipeline that runs in step.
@@ -768,6 +779,243 @@ int b200yolo_decode_nms_gather_steps(const b200yolo_gather *g, const b200yolo_ba
         if (int rc = launch_pdl_1warp(st, peer_signal_pdl_kernel, f, R, rank, first_step + n_steps)) return rc;
         return launch_pdl_1warp(st, peer_wait_pdl_kernel, (const int *)g->peer_flags[rank], R, first_step + n_steps, cyc, g->timed_out);
     }
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// NVSwitch multicast for the gather buffers.  One multicast object spans the GPUs of the job; every rank binds its own
+// physical memory to it and maps two views: the ordinary (unicast) one its consumers read, and the multicast one --
+// a store to a multicast address is replicated by the switch into the bound memory of EVERY GPU at the same offset,
+// so a kept row leaves its GPU once instead of once per peer.  Driver API (virtual memory management + cuMulticast*),
+// resolved at run time with dlopen so that the library still loads on a machine without a driver.
+// ---------------------------------------------------------------------------
+struct DriverApi {
+    void *lib = nullptr;
+    bool ok = false;
+    decltype(&cuDeviceGet) DeviceGet = nullptr;
+    decltype(&cuDeviceGetAttribute) DeviceGetAttribute = nullptr;
+    decltype(&cuGetErrorString) GetErrorString = nullptr;
+    decltype(&cuMulticastGetGranularity) MulticastGetGranularity = nullptr;
+    decltype(&cuMulticastCreate) MulticastCreate = nullptr;
+    decltype(&cuMulticastAddDevice) MulticastAddDevice = nullptr;
+    decltype(&cuMulticastBindMem) MulticastBindMem = nullptr;
+    decltype(&cuMulticastUnbind) MulticastUnbind = nullptr;
+    decltype(&cuMemGetAllocationGranularity) MemGetAllocationGranularity = nullptr;
+    decltype(&cuMemCreate) MemCreate = nullptr;
+    decltype(&cuMemRelease) MemRelease = nullptr;
+    decltype(&cuMemAddressReserve) MemAddressReserve = nullptr;
+    decltype(&cuMemAddressFree) MemAddressFree = nullptr;
+    decltype(&cuMemMap) MemMap = nullptr;
+    decltype(&cuMemUnmap) MemUnmap = nullptr;
+    decltype(&cuMemSetAccess) MemSetAccess = nullptr;
+    decltype(&cuMemExportToShareableHandle) MemExportToShareableHandle = nullptr;
+    decltype(&cuMemImportFromShareableHandle) MemImportFromShareableHandle = nullptr;
+};
+
+const DriverApi &driver_api() {
+    static DriverApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        api.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!api.lib) return;
+        bool all = true;
+#define B200_DRV(field, name)                                              \
+        api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name)); \
+        all = all && api.field != nullptr;
+        B200_DRV(DeviceGet, "cuDeviceGet")
+        B200_DRV(DeviceGetAttribute, "cuDeviceGetAttribute")
+        B200_DRV(GetErrorString, "cuGetErrorString")
+        B200_DRV(MulticastGetGranularity, "cuMulticastGetGranularity")
+        B200_DRV(MulticastCreate, "cuMulticastCreate")
+        B200_DRV(MulticastAddDevice, "cuMulticastAddDevice")
+        B200_DRV(MulticastBindMem, "cuMulticastBindMem")
+        B200_DRV(MulticastUnbind, "cuMulticastUnbind")
+        B200_DRV(MemGetAllocationGranularity, "cuMemGetAllocationGranularity")
+        B200_DRV(MemCreate, "cuMemCreate")
+        B200_DRV(MemRelease, "cuMemRelease")
+        B200_DRV(MemAddressReserve, "cuMemAddressReserve")
+        B200_DRV(MemAddressFree, "cuMemAddressFree")
+        B200_DRV(MemMap, "cuMemMap")
+        B200_DRV(MemUnmap, "cuMemUnmap")
+        B200_DRV(MemSetAccess, "cuMemSetAccess")
+        B200_DRV(MemExportToShareableHandle, "cuMemExportToShareableHandle")
+        B200_DRV(MemImportFromShareableHandle, "cuMemImportFromShareableHandle")
+#undef B200_DRV
+        api.ok = all;
+    });
+    return api;
+}
+
+int drv_fail(CUresult r, const char *what) {
+    const char *msg = nullptr;
+    const DriverApi &d = driver_api();
+    if (d.GetErrorString) d.GetErrorString(r, &msg);
+    return fail(B200YOLO_ECUDA, "%s: %s (CUresult %d)", what, msg ? msg : "?", (int)r);
+}
+
+#define DRV_TRY(expr)                                         \
+    do {                                                      \
+        CUresult _r = (expr);                                 \
+        if (_r != CUDA_SUCCESS) return drv_fail(_r, #expr);   \
+    } while (0)
+
+}  // namespace
+
+struct b200yolo_mc {
+    CUmemGenericAllocationHandle mc = 0, mem = 0;
+    CUdeviceptr local_va = 0, mc_va = 0;
+    size_t size = 0;
+    int device = -1, n_devices = 0;
+    bool added = false, bound = false, mapped_local = false, mapped_mc = false;
+};
+
+namespace {
+
+int mc_prepare(size_t bytes, int n_devices, int *device, CUmulticastObjectProp *prop) {
+    const DriverApi &d = driver_api();
+    if (!d.ok) return fail(B200YOLO_EUNSUPPORTED, "multicast: the CUDA driver library (libcuda.so.1) with cuMulticast* is not available");
+    if (bytes == 0 || n_devices < 2 || n_devices > kMaxPeers) return fail(B200YOLO_EINVAL, "multicast: %d devices (2..%d)", n_devices, kMaxPeers);
+    CUDA_TRY(cudaFree(nullptr));   // (the primary context exists and is current)
+    if (int rc = current_device(device)) return rc;
+    CUdevice dev;
+    DRV_TRY(d.DeviceGet(&dev, *device));
+    int sup = 0;
+    DRV_TRY(d.DeviceGetAttribute(&sup, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev));
+    if (!sup) return fail(B200YOLO_EUNSUPPORTED, "multicast: device %d does not support NVSwitch multicast", *device);
+    memset(prop, 0, sizeof(*prop));
+    prop->numDevices = (unsigned)n_devices;
+    prop->handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    prop->flags = 0;
+    prop->size = bytes;
+    size_t gran = 0;
+    DRV_TRY(d.MulticastGetGranularity(&gran, prop, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = *device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t agran = 0;
+    DRV_TRY(d.MemGetAllocationGranularity(&agran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    if (agran > gran) gran = agran;
+    if (gran == 0) gran = (size_t)2 << 20;
+    prop->size = (bytes + gran - 1) / gran * gran;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200yolo_mc_supported(int device) {
+    const DriverApi &d = driver_api();
+    if (!d.ok) return 0;
+    CUdevice dev;
+    int sup = 0;
+    if (cudaFree(nullptr) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (d.DeviceGet(&dev, device) != CUDA_SUCCESS) return 0;
+    if (d.DeviceGetAttribute(&sup, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS) return 0;
+    return sup ? 1 : 0;
+}
+
+int b200yolo_mc_create(size_t bytes, int n_devices, int *fd, b200yolo_mc **out) {
+    if (!fd || !out) return fail(B200YOLO_EINVAL, "mc_create: null pointer");
+    *out = nullptr;
+    int device = 0;
+    CUmulticastObjectProp prop;
+    if (int rc = mc_prepare(bytes, n_devices, &device, &prop)) return rc;
+    const DriverApi &d = driver_api();
+    b200yolo_mc *m = new (std::nothrow) b200yolo_mc();
+    if (!m) return fail(B200YOLO_ECUDA, "mc_create: out of host memory");
+    m->device = device; m->n_devices = n_devices; m->size = prop.size;
+    CUresult r = d.MulticastCreate(&m->mc, &prop);
+    if (r != CUDA_SUCCESS) { delete m; return drv_fail(r, "cuMulticastCreate"); }
+    int h = -1;
+    r = d.MemExportToShareableHandle(&h, m->mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (r != CUDA_SUCCESS) { d.MemRelease(m->mc); delete m; return drv_fail(r, "cuMemExportToShareableHandle"); }
+    *fd = h;
+    *out = m;
+    return 0;
+}
+
+int b200yolo_mc_import(size_t bytes, int n_devices, int fd, b200yolo_mc **out) {
+    if (!out || fd < 0) return fail(B200YOLO_EINVAL, "mc_import: bad argument");
+    *out = nullptr;
+    int device = 0;
+    CUmulticastObjectProp prop;
+    if (int rc = mc_prepare(bytes, n_devices, &device, &prop)) return rc;
+    const DriverApi &d = driver_api();
+    b200yolo_mc *m = new (std::nothrow) b200yolo_mc();
+    if (!m) return fail(B200YOLO_ECUDA, "mc_import: out of host memory");
+    m->device = device; m->n_devices = n_devices; m->size = prop.size;
+    CUresult r = d.MemImportFromShareableHandle(&m->mc, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (r != CUDA_SUCCESS) { delete m; return drv_fail(r, "cuMemImportFromShareableHandle"); }
+    *out = m;
+    return 0;
+}
+
+int b200yolo_mc_add_device(b200yolo_mc *m) {
+    if (!m || !m->mc) return fail(B200YOLO_EINVAL, "mc_add_device: null object");
+    const DriverApi &d = driver_api();
+    CUdevice dev;
+    DRV_TRY(d.DeviceGet(&dev, m->device));
+    DRV_TRY(d.MulticastAddDevice(m->mc, dev));
+    m->added = true;
+    return 0;
+}
+
+int b200yolo_mc_bind(b200yolo_mc *m, void **local_ptr, void **mc_ptr) {
+    if (!m || !m->mc || !m->added || !local_ptr || !mc_ptr) return fail(B200YOLO_EINVAL, "mc_bind: bad argument (add the device first)");
+    const DriverApi &d = driver_api();
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = m->device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    DRV_TRY(d.MemCreate(&m->mem, m->size, &ap, 0));
+    DRV_TRY(d.MulticastBindMem(m->mc, 0, m->mem, 0, m->size, 0));
+    m->bound = true;
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = m->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    DRV_TRY(d.MemAddressReserve(&m->local_va, m->size, 0, 0, 0));
+    DRV_TRY(d.MemMap(m->local_va, m->size, 0, m->mem, 0));
+    m->mapped_local = true;
+    DRV_TRY(d.MemSetAccess(m->local_va, m->size, &acc, 1));
+    DRV_TRY(d.MemAddressReserve(&m->mc_va, m->size, 0, 0, 0));
+    DRV_TRY(d.MemMap(m->mc_va, m->size, 0, m->mc, 0));
+    m->mapped_mc = true;
+    DRV_TRY(d.MemSetAccess(m->mc_va, m->size, &acc, 1));
+    CUDA_TRY(cudaMemset((void *)m->local_va, 0, m->size));
+    CUDA_TRY(cudaDeviceSynchronize());
+    *local_ptr = (void *)m->local_va;
+    *mc_ptr = (void *)m->mc_va;
+    return 0;
+}
+
+int b200yolo_mc_free(b200yolo_mc *m) {
+    if (!m) return 0;
+    const DriverApi &d = driver_api();
+    if (d.ok) {
+        if (m->mapped_mc) d.MemUnmap(m->mc_va, m->size);
+        if (m->mc_va) d.MemAddressFree(m->mc_va, m->size);
+        if (m->mapped_local) d.MemUnmap(m->local_va, m->size);
+        if (m->local_va) d.MemAddressFree(m->local_va, m->size);
+        if (m->bound) {
+            CUdevice dev;
+            if (d.DeviceGet(&dev, m->device) == CUDA_SUCCESS) d.MulticastUnbind(m->mc, dev, 0, m->size);
+        }
+        if (m->mem) d.MemRelease(m->mem);
+        if (m->mc) d.MemRelease(m->mc);
+    }
+    delete m;
     return 0;
 }
 

@@ -126,6 +126,7 @@ struct DNParams {
     // fused all-gather (b200yolo_decode_nms_gather): the output phase stores every kept row into the gather buffer of
     // EVERY rank (its own and, through NVLink peer mappings, the others'), image slot gslot + b; out / out_count unused
     int gR;                      // ranks (0: ordinary single-buffer output)
+    int gnbuf;                   // buffers the output phase stores into: gR peer mappings, or 1 NVSwitch multicast view
     int gslot;                   // first image slot of this rank = rank * N
     float *gout[kMaxPeers];      // [gR] rank r's buffer [gR*N][K][7]
     int *gcount[kMaxPeers];      // [gR] rank r's counts [gR*N]
@@ -1215,7 +1216,7 @@ __device__ __forceinline__ void phase_output_stream(const DNParams &p, const Sme
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
     const int ntiles = s.ktile[p.C];
-    const int nbuf = (GATHER != 0) ? p.gR : 1;   // fused all-gather: one copy per rank
+    const int nbuf = (GATHER != 0) ? p.gnbuf : 1;   // fused all-gather: one copy per rank, or one multicast store
     const size_t img = (GATHER != 0) ? (size_t)(p.gslot + b) : (size_t)b;
     float *scr = s.scratch + warp * kScratchFloats;
     // MODE_NMS: the caller's own rows are gathered bit-for-bit (pred_this_cls[index], box.py:29)

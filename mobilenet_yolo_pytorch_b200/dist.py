@@ -70,6 +70,40 @@ def split_targets(targets: List, world_size: int, rank: int) -> List:
     return targets[lo:hi]
 
 
+def _pass_fd(fd: Optional[int], group, rank: int, world: int) -> int:
+    """Hand rank 0's file descriptor to every rank of the (single-node) group: SCM_RIGHTS over an abstract unix socket
+    whose name travels through the process group."""
+    import os
+    import socket
+    src = 0 if group is None else dist.get_global_rank(group, 0)
+    obj = [None]
+    srv = None
+    if rank == 0:
+        _pass_fd.counter = getattr(_pass_fd, "counter", 0) + 1
+        name = "\0b200yolo-mc-%d-%d" % (os.getpid(), _pass_fd.counter)
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(name)
+        srv.listen(world)
+        obj = [name]
+    dist.broadcast_object_list(obj, src=src, group=group)
+    if rank == 0:
+        srv.settimeout(60.0)
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            socket.send_fds(conn, [b"f"], [fd])
+            conn.close()
+        srv.close()
+        return fd
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    c.settimeout(60.0)
+    c.connect(obj[0])
+    _, fds, _, _ = socket.recv_fds(c, 16, 1)
+    c.close()
+    if not fds:
+        raise RuntimeError("PeerGather: no file descriptor received from rank 0")
+    return fds[0]
+
+
 class _RawCuda:
     """zero-copy view of raw device memory for ``torch.as_tensor`` (CUDA array interface v2)"""
 
@@ -95,12 +129,19 @@ class PeerGather:
     has -- in stream order -- moved past whatever it enqueued on the buffer of step s-3.  So: consume the result of
     step s -- ``current()`` -- after its fence with ordinary kernel launches on the same stream BEFORE launching step
     s+1, and no peer can overwrite what a consumer still reads.  One process per GPU on one NVSwitch box, at most 8
-    ranks; ``close`` releases the mappings.  ``group`` may be a gloo group (the rendezvous only moves IPC handles)."""
+    ranks; ``close`` releases the mappings.  ``group`` may be a gloo group (the rendezvous only moves IPC handles).
+
+    ``multicast`` (None: the environment variable B200YOLO_MULTICAST=1 switches it on; True: required; False: off): the
+    gather buffers live in memory bound to one NVSwitch multicast object (``b200yolo_mc_*``) and the kernel stores every
+    row ONCE, through the multicast view: the switch replicates it into all ranks' buffers, so a GPU sends 1/(R-1) of
+    the bytes the peer-mapping path sends.  The arrival flags stay on peer mappings.  Needs one GPU per rank."""
 
     NBUF = 3
 
-    def __init__(self, n_local: int, cells_per_image: int, group=None, device: Optional[torch.device] = None):
+    def __init__(self, n_local: int, cells_per_image: int, group=None, device: Optional[torch.device] = None,
+                 multicast: Optional[bool] = None):
         import ctypes as C
+        import os
         from . import _lib
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
@@ -113,7 +154,18 @@ class PeerGather:
         row_bytes = (total * self.K * 7 * 4 + 255) // 256 * 256
         cnt_bytes = (total * 4 + 255) // 256 * 256
         self._par_bytes = row_bytes + cnt_bytes
-        self._flag_off = self.NBUF * self._par_bytes    # int[8] arrival flags + int timed_out
+        want_mc = (os.environ.get("B200YOLO_MULTICAST", "0") == "1") if multicast is None else bool(multicast)
+        self._mc = None
+        if want_mc and self.world >= 2:
+            votes: List = [None] * self.world
+            dist.all_gather_object(votes, bool(lib.b200yolo_mc_supported(self.device.index)), group=group)
+            if all(votes):
+                self._mc_setup(lib, self.NBUF * self._par_bytes)
+            elif multicast:
+                raise RuntimeError("PeerGather: NVSwitch multicast is not available on every rank")
+        self.multicast = self._mc is not None
+        # (multicast: rows and counts live in the multicast-bound memory, the peer-mapped allocation holds the flags only)
+        self._flag_off = 0 if self.multicast else self.NBUF * self._par_bytes    # int[8] arrival flags + int timed_out
         nbytes = self._flag_off + 256
         with torch.cuda.device(self.device):
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -132,7 +184,12 @@ class PeerGather:
                 self._opened.append(p2.value)
             g = _lib.Gather()
             g.R, g.rank = self.world, self.rank
+            g.multicast = 1 if self.multicast else 0
             for par in range(self.NBUF):
+                if self.multicast:
+                    g.peer_out[par][0] = self._mc_view + par * self._par_bytes
+                    g.peer_count[par][0] = self._mc_view + par * self._par_bytes + row_bytes
+                    continue
                 for r in range(self.world):
                     g.peer_out[par][r] = self._bases[r] + par * self._par_bytes
                     g.peer_count[par][r] = self._bases[r] + par * self._par_bytes + row_bytes
@@ -148,14 +205,49 @@ class PeerGather:
             self._flag_ptrs = (C.c_void_p * self.world)(*[b + self._flag_off for b in self._bases])
             self._step = 0        # steps launched so far
             self._fenced = 0      # steps whose fence has been launched
-            raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
+            flags_raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
+            raw = (torch.as_tensor(_RawCuda(self._mc_local, self.NBUF * self._par_bytes), device=self.device)
+                   if self.multicast else flags_raw)
             self._dets = [raw[par * self._par_bytes:par * self._par_bytes + total * self.K * 7 * 4].view(torch.float32).view(total, self.K, 7)
                           for par in range(self.NBUF)]
             self._counts = [raw[par * self._par_bytes + row_bytes:par * self._par_bytes + row_bytes + total * 4].view(torch.int32)
                             for par in range(self.NBUF)]
-            self._timed_out = raw[self._flag_off + 64:self._flag_off + 68].view(torch.int32)
+            self._timed_out = flags_raw[self._flag_off + 64:self._flag_off + 68].view(torch.int32)
             self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
+
+    def _mc_setup(self, lib, nbytes: int) -> None:
+        """the multicast object (rank 0 creates it, the others import its file descriptor), this rank's memory bound to
+        it, and the two views"""
+        import ctypes as C
+        import os
+        from . import _lib
+        with torch.cuda.device(self.device):
+            h = C.c_void_p()
+            fd = C.c_int(-1)
+            err = None
+            if self.rank == 0:
+                try:
+                    _lib.check(lib.b200yolo_mc_create(nbytes, self.world, C.byref(fd), C.byref(h)))
+                except Exception as e:  # noqa: BLE001  (the other ranks must not be left waiting for the descriptor)
+                    err = str(e)
+            errs: List = [None] * self.world
+            dist.all_gather_object(errs, err, group=self.group)
+            if errs[0] is not None:
+                raise RuntimeError("PeerGather: multicast object: " + errs[0])
+            got = _pass_fd(fd.value if self.rank == 0 else None, self.group, self.rank, self.world)
+            try:
+                if self.rank != 0:
+                    _lib.check(lib.b200yolo_mc_import(nbytes, self.world, got, C.byref(h)))
+            finally:
+                os.close(got)               # (the driver keeps its own reference)
+            self._mc = h
+            _lib.check(lib.b200yolo_mc_add_device(h))
+            dist.barrier(group=self.group)      # every device is in the group before memory is bound
+            local, view = C.c_void_p(), C.c_void_p()
+            _lib.check(lib.b200yolo_mc_bind(h, C.byref(local), C.byref(view)))
+            self._mc_local, self._mc_view = local.value, view.value
+            dist.barrier(group=self.group)
 
     # ---- results of the most recently launched step (valid on the stream after its fence)
     @property
@@ -256,3 +348,6 @@ class PeerGather:
             self._dets = self._counts = self._timed_out = None
             lib.b200yolo_peer_free(self._own)
             self._own = None
+        if self._mc is not None:
+            lib.b200yolo_mc_free(self._mc)
+            self._mc = None

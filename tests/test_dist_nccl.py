@@ -60,10 +60,28 @@ def _worker(rank, world, port, N, q):
         pg.check()
         p_dets, p_cnt = pg.dets.cpu().numpy().copy(), pg.counts.cpu().numpy().copy()
         pg.close()
+        # ... and through NVSwitch multicast memory (one store per row, replicated by the switch), where the box has it:
+        # single steps with fences, then the one-call form
+        from mobilenet_yolo_pytorch_b200 import _lib
+        m_dets = m_cnt = None
+        votes = [None] * world
+        dist.all_gather_object(votes, bool(_lib.load().b200yolo_mc_supported(rank)))
+        if all(votes):
+            pm = b200.dist.PeerGather(hi - lo, dets.shape[1], multicast=True)
+            assert pm.multicast
+            for it in range(3):
+                pm.decode_nms(h0[lo:hi].to(dev), h1[lo:hi].to(dev), tables, C, 0.3)
+                pm.fence()
+            hs = [(h0[lo:hi].to(dev).contiguous(), h1[lo:hi].to(dev).contiguous()) for _ in range(4)]
+            pm.run_steps(hs, tables, C, 0.3)
+            torch.cuda.synchronize()
+            pm.check()
+            m_dets, m_cnt = pm.dets.cpu().numpy().copy(), pm.counts.cpu().numpy().copy()
+            pm.close()
         x = h1[lo:hi].to(dev).requires_grad_(True)
         tup = losses[1](x, targets[lo:hi])
         tup[0].backward()
-        q.put((rank, p_dets, p_cnt, c_rows.cpu().numpy(), c_cnt.cpu().numpy(), g_dets.cpu().numpy(), g_cnt.cpu().numpy(), float(tup[0].detach()), [float(v) for v in tup[1:4]] + [float(tup[4]), tup[5], tup[6]],
+        q.put((rank, m_dets, m_cnt, p_dets, p_cnt, c_rows.cpu().numpy(), c_cnt.cpu().numpy(), g_dets.cpu().numpy(), g_cnt.cpu().numpy(), float(tup[0].detach()), [float(v) for v in tup[1:4]] + [float(tup[4]), tup[5], tup[6]],
                x.grad.cpu().numpy(), lo, hi))
     finally:
         dist.destroy_process_group()
@@ -98,8 +116,14 @@ def test_two_gpu_shards_equal_single_gpu():
     tup[0].backward()
     grad = x.grad.cpu().numpy()
     want_rows = np.concatenate([dets[b, :cnt[b]] for b in range(N)], 0)
-    for rank, p_dets, p_cnt, c_rows, c_cnt, g_dets, g_cnt, loss, stats, g, lo, hi in got:
+    for rank, m_dets, m_cnt, p_dets, p_cnt, c_rows, c_cnt, g_dets, g_cnt, loss, stats, g, lo, hi in got:
         assert np.array_equal(g_cnt, cnt) and np.array_equal(c_cnt, cnt) and np.array_equal(p_cnt, cnt)
+        if m_dets is not None:                           # multicast gather: the same, on every rank
+            assert np.array_equal(m_cnt, cnt)
+            for b in range(N):
+                assert np.array_equal(m_dets[b, :cnt[b]], dets[b, :cnt[b]])
+        else:
+            print("NVSwitch multicast not available here: multicast gather not exercised")
         for b in range(N):                               # fused peer gather: every rank holds the whole batch
             assert np.array_equal(p_dets[b, :cnt[b]], dets[b, :cnt[b]])
         assert np.array_equal(c_rows, want_rows)            # compact gather: kept rows only, rank-then-image order
