@@ -604,6 +604,8 @@ def run_b200(args, name, wl):
     gathered = run.gather
 
     # ---- e2e: host buffers through the C-ABI host call (H2D + kernel + D2H inside)
+    # (the rank's thread moves to the CPUs next to its GPU first, so the pinned buffers land on that NUMA node)
+    numa = ops.bind_host_to_gpu(local) if os.environ.get("B200YOLO_NUMA", "1") == "1" else {"bound": False, "why": "B200YOLO_NUMA=0"}
     hh0, hh1 = make_heads(wl, N, seed=7 + rank, pin=True)
     ho = torch.empty((N, K, 7), dtype=torch.float32).pin_memory()
     hc = torch.empty((N,), dtype=torch.int32).pin_memory()
@@ -771,7 +773,8 @@ def run_b200(args, name, wl):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(run.in_bytes),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "b200yolo_decode_nms_host (pinned host heads -> host detections, chunks on 3 streams: H2D, kernel and D2H overlap)",
-                    "timer": "host wall clock around the synchronous calls, max over ranks"},
+                    "timer": "host wall clock around the synchronous calls, max over ranks",
+                    "host_numa_binding": numa},
             "gpu_launches": int(launches_timed) * world,
             "clocks": clocks,
             "extra": extra,

@@ -48,6 +48,34 @@ def _host_f32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+def bind_host_to_gpu(device_index: int) -> dict:
+    """Pin the calling thread to the CPUs closest to a GPU (NVML's affinity mask of the device), so that pinned host
+    buffers allocated afterwards land on that GPU's NUMA node and its H2D / D2H copies do not cross the socket link.
+    For one-process-per-GPU jobs that feed the host entry (``decode_nms_host``); call it before allocating the buffers.
+    Returns {"bound": bool, "cpus": n, ...}; never raises (no NVML, no permission: {"bound": False, "why": ...})."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:  # noqa: BLE001  (older torch without the PCI ids: NVML index = CUDA index when nothing is masked)
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return {"bound": False, "why": "no allowed CPU in the device's affinity mask"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "of": len(allowed), "first_cpu": min(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": str(e)[:120]}
+
+
 class CandidateList(list):
     """list[N] of (n_b, 7) views, as YOLOLoss.forward(input) returns it
     (yolo_loss.py:202-204), that also remembers the padded device buffer it views
@@ -432,10 +460,10 @@ def target_loss_sums(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
 
 def target_loss_lazy(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor, G: int, sa: np.ndarray, m: np.ndarray,
                      num_classes: int, ignore_thr: float, iou_thr: float, iou_weighting: float, max_gt: int,
-                     cell_state: Optional[torch.Tensor]):
+                     cell_state: Optional[torch.Tensor], between=None):
     """b200yolo_target_loss + b200yolo_loss_finalize_dev back to back with the host work of ONE call (one stream lookup,
     two allocations, prepared anchor / mask arrays, thresholds already rounded to fp32): the ``lazy_stats`` path of
-    ``YOLOLoss.forward``.  Returns (sums (16,) f64, status (1,) i32, result (7,) f32), all on the device."""
+    ``YOLOLoss.forward``.  ``between(sums, status)`` runs between the two launches.  Returns (sums (16,) f64, status (1,) i32, result (7,) f32), all on the device."""
     _require_cuda(head, "head")
     head = head.contiguous()
     N, ch, H, W = head.shape
@@ -461,6 +489,8 @@ def target_loss_lazy(head: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
             gt_off.data_ptr(), int(G), ignore_thr, iou_thr, int(max_gt), buf.data_ptr(), None, None,
             buf.data_ptr() + 8 * _lib.S_COUNT, cell_state.data_ptr() if cell_state is not None else None,
             ws[0].data_ptr(), ws[0].numel(), st))
+        if between is not None:
+            between(sums, status)   # data-parallel shards: the all-reduce of the partial sums (and of the status word)
         _lib.check(lib.b200yolo_loss_finalize_dev(buf.data_ptr(), iou_weighting, res.data_ptr(), st))
     return sums, status, res
 

@@ -145,10 +145,20 @@ class YOLOLoss(nn.Module):
         x = input.detach()
         N, _, H, W = x.shape
         state = torch.empty((N, self.num_mask * H * W), dtype=torch.uint8, device=x.device) if need_grad else None
-        if self.lazy_stats and self.process_group is None:
-            # no host synchronisation and the host work of one call (ops.target_loss_lazy)
+        if self.lazy_stats:
+            # no host synchronisation and the host work of one call (ops.target_loss_lazy); shards of a data-parallel
+            # batch all-reduce the 16 partial sums (and the status word) between the two launches
             sa, m, thr = self._prepared()
-            sums, status, res = ops.target_loss_lazy(x, gt, gt_off, G, sa, m, self.num_classes, thr[0], thr[1], thr[2], max_gt, state)
+            between = None
+            if self.process_group is not None:
+                import torch.distributed as dist
+                pg = self.process_group
+
+                def between(sums_, status_):
+                    dist.all_reduce(sums_, op=dist.ReduceOp.SUM, group=pg)
+                    dist.all_reduce(status_, op=dist.ReduceOp.MAX, group=pg)
+            sums, status, res = ops.target_loss_lazy(x, gt, gt_off, G, sa, m, self.num_classes, thr[0], thr[1], thr[2], max_gt, state,
+                                                     between=between)
             d = self.__dict__                  # (nn.Module.__setattr__ costs 5 us per assignment)
             d["last_sums"] = sums
             self.check()                       # the previous call's status: its copy completed long ago, no stall
@@ -164,13 +174,6 @@ class YOLOLoss(nn.Module):
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.process_group)
             dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.process_group)
         self.last_sums = sums
-        if self.lazy_stats:
-            self.check()                       # the previous call's status: its copy completed long ago, no stall
-            self._post_status(status)
-            loss, recall, avg_iou, obj, no_obj, cls_score, count = ops.loss_finalize_dev(sums, self.iou_weighting).unbind(0)
-            if need_grad:
-                loss = _LossGrad.apply(input, loss, self, gt, gt_off, G, max_gt, state, sums)
-            return loss, recall, avg_iou, obj, no_obj, cls_score, count
         host = torch.cat((sums, status.to(torch.float64))).cpu().numpy()  # one D2H sync (the reference has ~5 per GT)
         self._raise_status(int(host[-1]))
         r = ops.loss_finalize(host[:_lib.S_COUNT], self.iou_weighting)

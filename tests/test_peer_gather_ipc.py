@@ -92,6 +92,15 @@ def _worker(rank, world, port, N, q):
         tup = ll(x, targets[lo:hi])
         tup[0].backward()
         loss_out = ([float(tup[0].detach()), tup[1], tup[2], tup[3], float(tup[4]), tup[5], tup[6]], x.grad.cpu().numpy(), lo, hi)
+        # the same shard through the no-synchronisation path (lazy_stats + packed device targets): same seven values
+        ll.lazy_stats = True
+        x2 = lh1[lo:hi].to(dev).requires_grad_(True)
+        lz = ll(x2, b200.ops.PackedTargets.from_list(targets[lo:hi], dev))
+        lz[0].backward()
+        ll.check()
+        assert all(v.is_cuda for v in lz)
+        np.testing.assert_allclose([float(v) for v in lz], loss_out[0], rtol=2e-7, atol=1e-9)
+        assert torch.equal(x2.grad, x.grad)
         q.put((rank, out, rows, loss_out))
     finally:
         dist.destroy_process_group()
