@@ -68,7 +68,8 @@ void b200yolo_debug_phase_stamps(unsigned long long *dev_buf);
  * 512 = with phase stamps: the buffer is a ring of 16 launches ([16][N][32]) and the stamped launches overlap like
  * production launches (steady-state phase times), 1024 = b200yolo_decode_nms_batches: every launch waits for its
  * predecessor before it stores even when the outputs are disjoint, 2048 = ... at most two launches in flight even when
- * no two batches share an output. */
+ * no two batches share an output, 16384 = no objectness-first decode of the second head (decode_nms.cuh,
+ * decode_head_static_sparse). */
 void b200yolo_debug_set_flags(int flags);
 
 /* Largest number of candidate cells per image (sum over heads of A*H*W) that

@@ -426,7 +426,8 @@ __device__ __forceinline__ void emit_candidate(const DNParams &p, const Smem &s,
 // the first shared atomic is taken AFTER the first round's loads are in flight (hides ~0.5 us of start-up
 // behind the first HBM round trip).
 template <int THREADS, int MODE, int CT, int HWT, int WT, bool FIRST, bool DBG, bool EXACT>
-__device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh) {
+__device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0, int hh,
+                                                   int *warp_active = nullptr, int *warp_pass = nullptr) {
     static_assert(CT >= 1 && CT <= 24, "compile-time shapes keep all class bits in one fp32 accumulator");
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr int attrs = CT + 5;
@@ -481,8 +482,100 @@ __device__ __forceinline__ void decode_head_static(const DNParams &p, const Smem
             const unsigned bal = __ballot_sync(kFullMask, pass);
             if (lane == 0 && active) s.passbits[local >> 5] = bal;
         }
+        if (FIRST && MODE == MODE_FUSED && base == 0 && warp_active != nullptr) {   // (decode_head_static_sparse)
+            *warp_active = __popc(__ballot_sync(kFullMask, active));
+            *warp_pass = __popc(__ballot_sync(kFullMask, pass));
+        }
         if (MODE == MODE_FUSED) stamp<DBG>(p, b, 8 + min(3, hh + base / THREADS));
     }
+}
+
+// The second head of a compile-time shape when the image looks sparse to this warp (trained heads pass a few percent of
+// the cells).  The ordinary decode reads all 5 + C planes of every cell -- one HBM round trip per 512 cells, 25 loads a
+// cell -- although only the objectness plane decides whether the other 24 are ever looked at.  Here the warp reads the
+// objectness of ALL its cells of the head first (one load per cell, one round trip for the whole head), and only the
+// lanes that got a passing cell assigned read that cell's other planes (a second round trip): three round trips
+// instead of four per image and a fraction of the bytes on trained-like heads.  Decided per warp, no barrier: a warp
+// whose first-head cells mostly fail tries it; a warp that finds more than 32 passing cells falls back to the ordinary
+// loop.  Only the loads differ -- every passing cell runs the same arithmetic, so the results are identical either way.
+// Returns false: nothing done, decode the head with decode_head_static.
+template <int THREADS, int MODE, int CT, int HWT, int WT, bool EXACT>
+__device__ __forceinline__ bool decode_head_static_sparse(const DNParams &p, const Smem &s, int b, const HeadDesc &hd, int cid0) {
+    constexpr int attrs = CT + 5;
+    constexpr int kMaxRounds = 4;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cells = p.A * HWT;
+    const int rounds = (cells + THREADS - 1) / THREADS;
+    if (rounds > kMaxRounds) return false;
+    const float *hb = hd.ptr + (size_t)b * p.A * attrs * HWT;  // uniform
+    float tc[kMaxRounds];
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+        const int local = r * THREADS + tid;
+        tc[r] = 0.f;
+        if (r < rounds && local < cells) {
+            const int a = local / HWT;
+            tc[r] = __ldcs(hb + (uint32_t)(a * attrs * HWT + (local - a * HWT)) + 4 * HWT);
+        }
+    }
+    uint32_t bal[kMaxRounds];
+    int total = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+        const int local = r * THREADS + tid;
+        bool pass = false;
+        if (r < rounds && local < cells) {
+            float conf;
+            pass = conf_pass<EXACT>(tc[r], p.conf_thr, &conf);
+        }
+        bal[r] = __ballot_sync(kFullMask, pass);
+        total += __popc(bal[r]);
+    }
+    if (total > 32) return false;   // dense after all: the ordinary loop (it writes every record)
+    // cells that fail (the ordinary loop marks them as it goes)
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+        const int local = r * THREADS + tid;
+        if (r < rounds && local < cells && !((bal[r] >> lane) & 1u)) s.clsidx[cid0 + local] = 0xffffffffu;
+    }
+    // lane L takes the L-th passing cell of the warp (round-major)
+    int local = -1, off = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+        const int n = __popc(bal[r]);
+        if (lane >= off && lane < off + n) local = r * THREADS + (tid & ~31) + (int)__fns(bal[r], 0, lane - off + 1);
+        off += n;
+    }
+    if (local >= 0) {
+        const int a = local / HWT;
+        const int pos = local - a * HWT;
+        const float *q = hb + (uint32_t)(a * attrs * HWT + pos);
+        const float tx = __ldcs(q), ty = __ldcs(q + HWT), tw = __ldcs(q + 2 * HWT), th = __ldcs(q + 3 * HWT), tcv = __ldcs(q + 4 * HWT);
+        float x[CT];
+#pragma unroll
+        for (int u = 0; u < CT; ++u) x[u] = __ldcs(q + (5 + u) * HWT);
+        float conf;
+        const bool pass = conf_pass<EXACT>(tcv, p.conf_thr, &conf);   // (true: the same value decided above)
+        if (pass) {
+            float m1 = x[0];
+#pragma unroll
+            for (int u = 1; u < CT; ++u) m1 = fmaxf(m1, x[u]);
+            float best;
+            const float win = tie_window(m1, &best);
+            const float lo = __fsub_rn(m1, win);
+            float near = 0.f;
+#pragma unroll
+            for (int u = 0; u < CT; ++u) near = __fmaf_rn((x[u] >= lo) ? 1.0f : 0.0f, (float)(1u << u), near);
+            const uint32_t nb = __float2uint_rn(near);
+            int bi = nb ? __ffs(nb) - 1 : 0;
+            const bool tie = (nb & (nb - 1u)) != 0u || nb == 0u;
+            if (CT > 1 && tie) best = class_tie_break(q + 5 * HWT, HWT, CT, lo, m1, bi, &bi);
+            else if (EXACT) best = sigmoid_f(m1);
+            const int j = pos / WT;
+            emit_candidate<MODE, EXACT>(p, s, hd, cid0 + local, a, pos - j * WT, j, tx, ty, tw, th, conf, best, bi);
+        }
+    }
+    return true;
 }
 
 // Runtime class count and grid (any shape): plane stride in a register, classes in chunks of 24.
@@ -1462,8 +1555,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 384) ? 3 : (THREADS == 51
     } else if constexpr (kStaticShape && MODE == MODE_DECODE) {
         decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, false, DBG, EXACT>(p, s, b, p.head[0], 0, 0);
     } else if constexpr (kStaticShape) {
-        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true, DBG, EXACT>(p, s, b, p.head[0], 0, 0);
-        decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false, DBG, EXACT>(p, s, b, p.head[1], p.head[0].cells, 1);
+        int h0_active = 0, h0_pass = 0;
+        decode_head_static<THREADS, MODE, SH::C, SH::HW0, SH::W0, true, DBG, EXACT>(p, s, b, p.head[0], 0, 0, &h0_active, &h0_pass);
+        // (warp-uniform) at most an eighth of this warp's first-head cells passed: objectness first.  Warps that own no
+        // first-head cell run ahead with the ordinary loop (probing the first head from them, or letting them try
+        // unconditionally, costs dense images 1 %; loading the second head's objectness together with the first head's
+        // planes costs them 6 % and sparse ones gain nothing more: measured, profiles/r02/NOTES.md).  Flag 16384: off.
+        bool done = false;
+        if (MODE == MODE_FUSED && !(p.flags & 16384) && h0_active > 0 && 8 * h0_pass <= h0_active)
+            done = decode_head_static_sparse<THREADS, MODE, SH::C, SH::HW1, SH::W1, EXACT>(p, s, b, p.head[1], p.head[0].cells);
+        if (!done)
+            decode_head_static<THREADS, MODE, SH::C, SH::HW1, SH::W1, false, DBG, EXACT>(p, s, b, p.head[1], p.head[0].cells, 1);
     } else if constexpr (kNhwcShape) {
         // scratch: the key region of U, free during the decode; the host checked that it fits
         float *scr = reinterpret_cast<float *>(smem_raw + L.key_off);

@@ -1159,6 +1159,39 @@ def test_batches_entry_equals_single_calls(cuda_device):
     assert bad == ops._lib.EINVAL if hasattr(ops._lib, "EINVAL") else bad != 0
 
 
+def test_objectness_first_decode_is_identical(cuda_device):
+    """decode_head_static_sparse (warps whose first-head cells mostly fail read the second head's objectness first and
+    only the passing cells' other planes): rows, counts and cell ids equal the ordinary decode (flag 16384) bit for bit --
+    on sparse heads, on heads where only a band of the second head is dense (some warps fall back) and on a dense second
+    head (every warp tries and falls back); the sparse case also against the oracle."""
+    C = 20
+    tables = anchor_tables(VOC_ANCHORS, [352, 352])
+    N = 24
+    for variant in ("sparse", "banded", "dense_h1"):
+        h0, h1 = make_heads(N, C, [(11, 11), (22, 22)], seed=77, conf_shift=-2.6)
+        if variant == "banded":      # rows 6..11 of the second head pass almost everywhere
+            h1.view(N, 3, 25, 22, 22)[:, :, 4, 6:12, :] += 5.0
+        elif variant == "dense_h1":  # sparse first head, dense second head: every warp tries and falls back
+            h1.view(N, 3, 25, 22, 22)[:, :, 4] += 4.0
+        d0, d1 = h0.to(cuda_device), h1.to(cuda_device)
+        got = ops.decode_nms_padded(d0, d1, tables, C, 0.3, want_idx=True)
+        ops._lib.load().b200yolo_debug_set_flags(16384)
+        try:
+            want = ops.decode_nms_padded(d0, d1, tables, C, 0.3, want_idx=True)
+        finally:
+            ops._lib.load().b200yolo_debug_set_flags(0)
+        assert torch.equal(got[1], want[1]) and int(got[1].sum()) > 0
+        for b, k in enumerate(want[1].cpu().numpy()):
+            assert torch.equal(got[0][b, :k], want[0][b, :k]) and torch.equal(got[2][b, :k], want[2][b, :k])
+        if variant != "sparse":
+            continue   # (dense rows against the oracle, with the per-mismatch proofs for near-ties: the golden / oracle tests above)
+        o_out, o_cnt, _ = oracle.decode_nms_padded(h0.numpy(), h1.numpy(), tables, C, 0.3)
+        assert np.array_equal(o_cnt, got[1].cpu().numpy())
+        g = got[0].cpu().numpy()
+        for b in range(N):
+            np.testing.assert_allclose(g[b, :o_cnt[b]], o_out[b, :o_cnt[b]], rtol=RTOL, atol=ATOL)
+
+
 def test_lazy_stats_and_packed_targets(cuda_device):
     """YOLOLoss with lazy_stats (no host synchronisation, device scalars) and pre-packed device targets returns the
     same seven values and the same gradient as the default (drop-in) path; an out-of-range box surfaces in check()."""
