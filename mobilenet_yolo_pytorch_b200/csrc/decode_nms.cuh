@@ -22,12 +22,16 @@
 //                 conf = sigmoid(tc) > thr (yolo_loss.py:189,201); for passing cells:
 //                 class max / argmax (:198), box (:186-196,243-247) -> box[], cs[],
 //                 and the per-(class, score bucket) arrival index (one shared atomic).
+//                 A warp whose first-head cells mostly fail (trained heads) reads the second head's
+//                 objectness plane first and only the passing cells' other planes
+//                 (decode_head_static_sparse): same results, fewer round trips and bytes.
 //   P2 scans      warp per class: exclusive scan of the class's score-bucket histogram; warp 0:
-//                 class segment starts (box.py:20-22) and the tile tables -- a class owns
-//                 ceil(n/32) TILES of 32 sorted positions.
+//                 class segment starts (box.py:20-22).  Nothing else sits in a window that one warp
+//                 executes while fifteen wait.
 //   P3 key scatter 64-bit keys (score desc, candidate order asc == the stable sort of
-//                 torchvision.ops.nms) into their (class, bucket) segment; warp 0 builds the
-//                 pair-task list meanwhile.
+//                 torchvision.ops.nms) into their (class, bucket) segment; warp 0 builds the tile
+//                 tables (a class owns ceil(n/32) TILES of 32 sorted positions; named barrier 2 orders
+//                 them before the ranking) and the pair-task list meanwhile.
 //   P4 rank       rank inside the bucket = sorted position.  Every candidate is then written to the
 //                 tile-padded sorted tables: its cell id (scid) and a CONSERVATIVE fp16 image of
 //                 its box (H16Tile: x1/y1 rounded down, x2/y2 rounded up, a lower bound of
@@ -59,7 +63,8 @@
 // kernel.  Images with more cells than `U` can hold take large_nms.cuh.
 //
 // Consecutive launches overlap (programmatic dependent launch, see pdl_trigger / pdl_wait below): a launch
-// starts on the SM slots its predecessor leaves free and streams its heads under the predecessor's NMS.
+// starts on the SM slots its predecessor leaves free and streams its heads under the predecessor's NMS.  Whether it
+// must wait for that predecessor before it stores depends on the output buffers of the list (DNParams::chain).
 #pragma once
 #include <cuda_fp16.h>
 
