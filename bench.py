@@ -605,6 +605,7 @@ def run_b200(args, name, wl):
 
     # ---- e2e: host buffers through the C-ABI host call (H2D + kernel + D2H inside)
     # (the rank's thread moves to the CPUs next to its GPU first, so the pinned buffers land on that NUMA node)
+    cpus_before = os.sched_getaffinity(0)
     numa = ops.bind_host_to_gpu(local) if os.environ.get("B200YOLO_NUMA", "1") == "1" else {"bound": False, "why": "B200YOLO_NUMA=0"}
     hh0, hh1 = make_heads(wl, N, seed=7 + rank, pin=True)
     ho = torch.empty((N, K, 7), dtype=torch.float32).pin_memory()
@@ -620,6 +621,7 @@ def run_b200(args, name, wl):
     e2e_val = total_images * e2e_steps / D.max(time.perf_counter() - t0)
     d2h_bytes = int(lib.b200yolo_host_last_d2h_bytes()) if hasattr(lib, "b200yolo_host_last_d2h_bytes") else int(N * K * 28 + 4 * N)
     del hh0, hh1, ho, hc
+    os.sched_setaffinity(0, cpus_before)   # (the CPU legs below use every host thread again)
 
     extra = {}
     if not args.no_extra:
