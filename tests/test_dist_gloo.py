@@ -84,7 +84,23 @@ def _worker(rank, world, port, N, q):
         sums = torch.from_numpy(_sums_from_oracle(o, hi - lo, 3 * 22 * 22))
         b2dist.all_reduce_loss_sums(sums)
         res = ops.loss_finalize(sums.numpy(), IOU_W)
-        q.put((rank, g_out.numpy(), g_cnt.numpy(), res))
+        # ---- the rendezvous of the multicast set-up: rank 0's file descriptor reaches the other rank (SCM_RIGHTS over an
+        # abstract unix socket whose name travels through the process group); here the descriptor is a pipe
+        fd_ok = True
+        if rank == 0:
+            rd, wr = os.pipe()
+            got = b2dist._pass_fd(wr, None, rank, world)
+            assert got == wr
+            dist.barrier()                                   # the peer has written through its copy of the descriptor
+            fd_ok = os.read(rd, 16) == b"from rank 1"
+            os.close(rd)
+            os.close(wr)
+        else:
+            got = b2dist._pass_fd(None, None, rank, world)
+            os.write(got, b"from rank 1")
+            os.close(got)
+            dist.barrier()
+        q.put((rank, g_out.numpy(), g_cnt.numpy(), res, fd_ok))
     finally:
         dist.destroy_process_group()
 
@@ -109,7 +125,8 @@ def test_world2_gloo_shards_equal_unsharded():
     out, oc, _ = oracle.decode_nms_padded(h0, h1, tables, C, 0.3)
     o = oracle.target_loss(h1, targets, VOC_ANCHORS, MASKS[1], C, IMG, IGN, IOU_T, IOU_W)
     want = np.array([o["loss"], o["recall"], o["avg_iou"], o["obj"], o["no_obj"], o["cls"], o["count_per_img"]])
-    for rank, g_out, g_cnt, res in got:
+    for rank, g_out, g_cnt, res, fd_ok in got:
+        assert fd_ok, "the file descriptor handed over by rank 0 did not work on the other rank"
         assert np.array_equal(g_cnt, oc), f"rank {rank}: gathered counts differ from the unsharded run"
         for b in range(N):
             assert np.array_equal(g_out[b, :oc[b]], out[b, :oc[b]]), f"rank {rank}: image {b} rows differ"
