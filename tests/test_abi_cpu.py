@@ -35,6 +35,17 @@ def test_argument_validation_needs_no_gpu(lib):
     rc = lib.b200yolo_pairwise(None, -1, None, 2, 2, None, None)
     assert rc == -1
     assert lib.b200yolo_target_loss_workspace_bytes(4) == 4 * 8 * 16 * 8  # N x (CTAs per image <= 8) x 16 doubles
+    # round-2 entry points: replayable plans and multicast memory
+    import ctypes as C
+    assert lib.b200yolo_plan_launch(None, None) == -1 and b"null plan" in lib.b200yolo_last_error()
+    assert lib.b200yolo_plan_destroy(None) == 0
+    h = C.c_void_p()
+    assert lib.b200yolo_plan_create(None, 0, 1, 3, 20, 11, 11, 22, 22, aw.ctypes.data, 0.3, 0.45, C.byref(h)) == -1 and not h.value
+    assert lib.b200yolo_mc_free(None) == 0
+    assert lib.b200yolo_mc_add_device(None) == -1
+    fd = C.c_int(-1)
+    assert lib.b200yolo_mc_create(0, 8, C.byref(fd), C.byref(h)) != 0 and not h.value   # (no driver here, or zero bytes)
+    assert lib.b200yolo_mc_supported(0) in (0, 1)
 
 
 def test_loss_finalize_matches_reference_formulas(lib):
